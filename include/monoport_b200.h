@@ -1,0 +1,166 @@
+/*
+ * monoport_b200 -- C ABI of the B200-native occupancy-field hot path of MonoPort.
+ *
+ * The reference (Project-Splinter/MonoPort) is pure Python: it has no FFI.  Its boundary for this path is
+ * a Python call protocol.  This header is the C-ABI a binding for that protocol
+ * would call; every entry point names the reference interface it replaces (paths relative to the
+ * reference tree).  Plain pointers and sizes only -- no torch types.  INTEGRATION.md shows the ctypes
+ * stub (monoport_b200/_lib.py is that stub).
+ *
+ * Conventions
+ *   - every function returns MP_OK (0) or a negative MP_E_* code; mp_last_error() gives a thread-local
+ *     message.  An empty reconstruction is NOT an error (RTL/recon.py:32-33 tolerates None).
+ *   - "dev" pointers are CUDA device pointers of the current device, "host" pointers are host memory.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are asynchronous
+ *     on that stream unless stated otherwise.  No process-global mutable state: all scratch lives in
+ *     the handles, so netG and netC queries may run concurrently from different threads
+ *     (RTL/dataloader.py:734-751 runs every stage in its own thread).
+ *   - volumes are [D,H,W] = [z,y,x] float32, x fastest (RTL/recon.py:35-38).
+ */
+#ifndef MONOPORT_B200_H_
+#define MONOPORT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MP_OK 0
+#define MP_E_INVALID (-1)   /* bad argument                                  */
+#define MP_E_CUDA (-2)      /* a CUDA runtime call failed                    */
+#define MP_E_UNSUPPORTED (-3) /* shape / mode not supported by this kernel   */
+#define MP_E_CAPACITY (-4)  /* caller-provided output buffer too small       */
+#define MP_E_NOMEM (-5)
+
+/* last_op of the head: heads/SurfaceClassifier.py:68-69 (None / nn.Sigmoid / nn.Tanh) */
+#define MP_LAST_NONE 0
+#define MP_LAST_SIGMOID 1
+#define MP_LAST_TANH 2
+
+/* projection: geometry.py:19-34 (orthogonal) / :37-55 (perspective) */
+#define MP_PROJ_ORTHOGONAL 0
+#define MP_PROJ_PERSPECTIVE 1
+
+/* arithmetic of the fused sample+MLP kernel */
+#define MP_MODE_FP32 0   /* CUDA-core fp32 everywhere (|err| ~1e-6 vs the reference)                 */
+#define MP_MODE_TC 1     /* tcgen05 fp16 operands / fp32 TMEM accumulators, last layer fp32 (<=1e-4)   */
+#define MP_MODE_AUTO 2   /* TC when the head/feature shape is supported by the tcgen05 kernel, else FP32 */
+
+const char* mp_last_error(void);
+int mp_version(void);
+/* sm count / compute capability of the current device */
+int mp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Head weights.  Replaces the parameters of SurfaceClassifier (heads/SurfaceClassifier.py:7-37):
+ * `channels` = filter_channels (n_layers+1 entries, e.g. {257,1024,512,256,128,1});
+ * weights[l] is filters.l.weight as [Cout_l, Cin_l] row-major fp32 with Cin_l = channels[l] +
+ * (l>0 && skip ? channels[0] : 0)  (:24-34), biases[l] is [Cout_l].  skip = !no_residual.
+ * Pointers are host (on_device=0) or device (on_device=1) memory; they are only read during the call.
+ * The handle owns repacked copies (fp32 K-major for the CUDA-core kernel, fp16 UMMA tiles for tcgen05).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mp_mlp mp_mlp_t;
+int mp_mlp_create(int n_layers, const int* channels, const float* const* weights,
+                  const float* const* biases, int skip, int last_op, int on_device, mp_mlp_t** out);
+int mp_mlp_destroy(mp_mlp_t* h);
+/* 1 if MP_MODE_TC is available for this head on this device */
+int mp_mlp_tc_supported(const mp_mlp_t* h);
+
+/* ---------------------------------------------------------------------------------------------
+ * Feature volume.  Replaces the tensor index() samples (geometry.py:4-16): one [C,H,W] fp32 NCHW map
+ * (the last hourglass stage in eval mode, MonoPortNet.py:63-64).  The handle keeps channel-last
+ * copies (fp32 + fp16) so one bilinear tap is one contiguous vector.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mp_feat mp_feat_t;
+int mp_feat_create(int C, int H, int W, mp_feat_t** out);
+int mp_feat_upload(mp_feat_t* h, const float* nchw, int on_device, void* stream);
+int mp_feat_destroy(mp_feat_t* h);
+
+/* calib: 12 host floats = rows 0..2 of the [4,4] / [3,4] calibration (R | t), or NULL for calibs=None
+ * (MonoPortNet.py:66-67).  z_scale = DepthNormalizer scale (normalizers/DepthNormalizer.py:32,40). */
+
+/* MonoPortNet.query(feats, points[1,3,N], calibs) -> [Res,N]   (MonoPortNet.py:48-91)
+ * points_dev: coordinate a (0..2) of point i lives at points_dev[a*row_stride + i*point_stride]  -- (N,1) for a
+ * contiguous [3,N] tensor, (1,3) for the permuted [N,3] view RTL/main.py:176-177 passes.
+ * out_dev: [Res, N], row stride ld_out. */
+int mp_query_points(mp_mlp_t* mlp, mp_feat_t* feat, const float* points_dev, int64_t n, int64_t row_stride,
+                    int64_t point_stride, const float* calib12, int projection, float z_scale, float* out_dev,
+                    int64_t ld_out, int mode, void* stream);
+/* Same call with HOST buffers (points [3,N], out [Res,N], feature map NCHW fp32 or NULL to reuse the
+ * uploaded one): copies in, runs, copies out, synchronises.  This is what bench.py's e2e leg times. */
+int mp_query_points_host(mp_mlp_t* mlp, mp_feat_t* feat, const float* feat_nchw_host, const float* points_host,
+                         int64_t n, const float* calib12, int projection, float z_scale, float* out_host,
+                         int mode, void* stream);
+
+/* Dense grid query: the node centres of planes [z0, z0+nz) of an R^3 grid spanning [b_min,b_max]
+ * (world = (idx+0.5)/R*(b_max-b_min)+b_min, the engine's convention, cf. RTL/main.py:204-209) are generated
+ * in-kernel; out_dev is the [nz,R,R] slab, channel 0 of the head (Res==1 required).  z-slab sharding
+ * across GPUs calls this with a different [z0,nz) per rank. */
+int mp_query_grid(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0, int nz, const float* b_min3, const float* b_max3,
+                  const float* calib12, int projection, float z_scale, float* out_dev, int mode, void* stream);
+
+/* mp_query_grid with HOST buffers: uploads the NCHW fp32 feature map (NULL = reuse), evaluates the slab, copies
+ * the [nz,R,R] result to out_host, synchronises.  bench.py's e2e leg. */
+int mp_query_grid_host(mp_mlp_t* mlp, mp_feat_t* feat, const float* feat_nchw_host, int R, int z0, int nz,
+                       const float* b_min3, const float* b_max3, const float* calib12, int projection, float z_scale,
+                       float* out_host, int mode, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Coarse-to-fine occupancy engine.  Replaces implicit_seg.functional.Seg3dLossless / Seg3dTopk
+ * (third-party, un-vendored; call sites RTL/main.py:28-29,188-195,390-395).
+ *   resolutions: n_levels odd cube sizes 2^k+1 (RTL/main.py:187), coarse -> fine.
+ *   faster != 0 : RTL/main.py:195 mode (box dilation 9/7/3, last level interpolated only)
+ *   faster == 0 : lossless mode (k=3, every level examined, conflict loop)
+ *   topk_points : NULL for the boundary engine, else n_levels ints = nodes evaluated per level (Seg3dTopk)
+ * Two ways to drive it:
+ *   (a) stepping API -- the binding calls back into an arbitrary Python query_func per step
+ *       (mp_octree_begin -> loop { mp_octree_next -> query -> mp_octree_commit });
+ *   (b) mp_octree_run_fused -- the whole pyramid with the fused sample+MLP kernel, no host round trip per level.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mp_octree mp_octree_t;
+int mp_octree_create(int n_levels, const int* resolutions, const float* b_min3, const float* b_max3,
+                     float balance_value, int faster, const int* topk_points, mp_octree_t** out);
+int mp_octree_destroy(mp_octree_t* h);
+int mp_octree_begin(mp_octree_t* h, void* stream);
+/* Produces the next batch of nodes to evaluate.  *n_out = number of nodes (0 => reconstruction finished);
+ * *level_out = level they belong to.  points_dev_out: device pointer to [n,3] world-space points (owned by
+ * the handle, valid until the next call), idx_dev_out: their linear indices (z*R*R+y*R+x) at that level.
+ * Synchronises the stream (the count has to reach the host). */
+int mp_octree_next(mp_octree_t* h, int64_t* n_out, int* level_out, const float** points_dev_out,
+                   const int32_t** idx_dev_out, void* stream);
+/* Scatter the n values ([n] floats, device) returned by the query for the batch handed out by the last
+ * mp_octree_next. */
+int mp_octree_commit(mp_octree_t* h, const float* values_dev, void* stream);
+/* After the last step: copies the final [R,R,R] volume to out_dev.  *nonempty = 0 when level 0 had no
+ * value > balance (the engine then returns None, RTL/recon.py:32-33) -- synchronises. */
+int mp_octree_finish(mp_octree_t* h, float* out_dev, int* nonempty, void* stream);
+/* Whole pyramid on the device.  stats_host (may be NULL): n_levels int64 = nodes evaluated per level.
+ * Synchronises once at the end (to report nonempty/stats). */
+int mp_octree_run_fused(mp_octree_t* h, mp_mlp_t* mlp, mp_feat_t* feat, const float* calib12, int projection,
+                        float z_scale, int mode, float* out_dev, int* nonempty, int64_t* stats_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Marching cubes (absent from the reference; PIFu-style reconstruction() asked for by the north star).
+ * Two calls: count (synchronises, returns sizes) then emit into caller buffers.
+ *   verts: [nV,3] float32 (x,y,z) in index space; faces: [nF,3] int32.
+ * Deterministic: vertex ids follow (node, axis) order, faces follow (cell, table) order.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mp_mcubes mp_mcubes_t;
+int mp_mcubes_create(int D, int H, int W, mp_mcubes_t** out);
+int mp_mcubes_destroy(mp_mcubes_t* h);
+int mp_mcubes_count(mp_mcubes_t* h, const float* vol_dev, float iso, int64_t* n_verts, int64_t* n_faces, void* stream);
+int mp_mcubes_emit(mp_mcubes_t* h, const float* vol_dev, float iso, float* verts_dev, int32_t* faces_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Visible-surface extraction.  Replaces forward_vertices (RTL/recon.py:27-89).
+ * direction: 0 front, 1 back, 2 left, 3 right.  Outputs (device, capacity R*R): X,Y int64, Z float, norm [n,3].
+ * *n_out on the host (synchronises).
+ * ------------------------------------------------------------------------------------------- */
+int mp_forward_vertices(const float* vol_dev, int R, int direction, int64_t* x_dev, int64_t* y_dev, float* z_dev,
+                        float* norm_dev, int64_t* n_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MONOPORT_B200_H_ */

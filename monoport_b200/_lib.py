@@ -1,0 +1,117 @@
+"""ctypes binding of libmonoport_b200.so -- the stub INTEGRATION.md shows a maintainer.
+
+The product path has NO CPU fallback: if the shared library is missing or was not built this module raises
+(`MonoportLibraryError`) instead of silently degrading to PyTorch ops.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmonoport_b200.so")
+
+MP_OK = 0
+MODE_FP32, MODE_TC, MODE_AUTO = 0, 1, 2
+LAST_NONE, LAST_SIGMOID, LAST_TANH = 0, 1, 2
+PROJ_ORTHOGONAL, PROJ_PERSPECTIVE = 0, 1
+
+
+class MonoportLibraryError(RuntimeError):
+    pass
+
+
+c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+P = ctypes.POINTER
+
+# name -> (restype, argtypes).  Must list every symbol include/monoport_b200.h declares
+# (tests/test_abi.py cross-checks this table against the header).
+SIGNATURES = {
+    "mp_last_error": (ctypes.c_char_p, []),
+    "mp_version": (c_int, []),
+    "mp_device_info": (c_int, [P(c_int), P(c_int), P(c_int)]),
+    "mp_mlp_create": (c_int, [c_int, P(c_int), P(c_void_p), P(c_void_p), c_int, c_int, c_int, P(c_void_p)]),
+    "mp_mlp_destroy": (c_int, [c_void_p]),
+    "mp_mlp_tc_supported": (c_int, [c_void_p]),
+    "mp_feat_create": (c_int, [c_int, c_int, c_int, P(c_void_p)]),
+    "mp_feat_upload": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "mp_feat_destroy": (c_int, [c_void_p]),
+    "mp_query_points": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, P(c_float), c_int, c_float,
+                                c_void_p, c_int64, c_int, c_void_p]),
+    "mp_query_points_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, P(c_float), c_int, c_float,
+                                     c_void_p, c_int, c_void_p]),
+    "mp_query_grid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, P(c_float), P(c_float), P(c_float), c_int,
+                              c_float, c_void_p, c_int, c_void_p]),
+    "mp_query_grid_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, P(c_float), P(c_float), P(c_float),
+                                   c_int, c_float, c_void_p, c_int, c_void_p]),
+    "mp_octree_create": (c_int, [c_int, P(c_int), P(c_float), P(c_float), c_float, c_int, P(c_int), P(c_void_p)]),
+    "mp_octree_destroy": (c_int, [c_void_p]),
+    "mp_octree_begin": (c_int, [c_void_p, c_void_p]),
+    "mp_octree_next": (c_int, [c_void_p, P(c_int64), P(c_int), P(c_void_p), P(c_void_p), c_void_p]),
+    "mp_octree_commit": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "mp_octree_finish": (c_int, [c_void_p, c_void_p, P(c_int), c_void_p]),
+    "mp_octree_run_fused": (c_int, [c_void_p, c_void_p, c_void_p, P(c_float), c_int, c_float, c_int, c_void_p,
+                                    P(c_int), P(c_int64), c_void_p]),
+    "mp_mcubes_create": (c_int, [c_int, c_int, c_int, P(c_void_p)]),
+    "mp_mcubes_destroy": (c_int, [c_void_p]),
+    "mp_mcubes_count": (c_int, [c_void_p, c_void_p, c_float, P(c_int64), P(c_int64), c_void_p]),
+    "mp_mcubes_emit": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
+    "mp_forward_vertices": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, P(c_int64),
+                                    c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes library.  Raises MonoportLibraryError when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MonoportLibraryError(
+            "%s not found: build it with `python -m monoport_b200.build` (nvcc, sm_100a). "
+            "monoport_b200 has no CPU / PyTorch fallback." % LIB_PATH)
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:
+        raise MonoportLibraryError("cannot load %s: %s" % (LIB_PATH, e)) from e
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise MonoportLibraryError("%s does not export %s" % (LIB_PATH, name)) from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != MP_OK:
+        msg = load().mp_last_error()
+        raise RuntimeError("monoport_b200 %s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def calib12(calib):
+    """[1,4,4] / [4,4] / [3,4] torch tensor (any device) or None -> ctypes float[12] or None."""
+    if calib is None:
+        return None
+    c = calib.detach()
+    if c.dim() == 3:
+        if c.shape[0] != 1:
+            raise ValueError("batch size must be 1 (RTL/main.py:175)")
+        c = c[0]
+    c = c[:3, :4].to("cpu", dtype=__import__("torch").float32).contiguous().reshape(-1).tolist()
+    return (c_float * 12)(*c)
+
+
+def f3(v):
+    import numpy as np
+    a = np.asarray(v.detach().cpu() if hasattr(v, "detach") else v, dtype=np.float32).reshape(-1)
+    if a.size != 3:
+        raise ValueError("expected 3 values, got %r" % (a,))
+    return (c_float * 3)(*[float(x) for x in a])
+
+
+def stream_ptr(device=None):
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,317 @@
+// C-ABI entry points: error channel, handles (head weights, feature volume), query dispatch.
+// See include/monoport_b200.h for the contract of every function and the reference interface it replaces.
+#include "mp_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mp_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* mp_last_error(void) { return g_err; }
+extern "C" int mp_version(void) { return 100; }
+
+extern "C" int mp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  MP_CUDA(cudaGetDevice(&dev));
+  if (sm_count) MP_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (cc_major) MP_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_minor) MP_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return MP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// head weights
+// ---------------------------------------------------------------------------------------------
+__global__ void transpose_w_kernel(const float* __restrict__ w, float* __restrict__ wt, int cout, int cin) {
+  // w [cout][cin] -> wt [cin][cout]
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = by + j, c = bx + threadIdx.x;
+    tile[j][threadIdx.x] = (r < cout && c < cin) ? w[(size_t)r * cin + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = bx + j, c = by + threadIdx.x;   // r: cin index, c: cout index
+    if (r < cin && c < cout) wt[(size_t)r * cout + c] = tile[threadIdx.x][j];
+  }
+}
+
+extern "C" int mp_mlp_destroy(mp_mlp_t* h) {
+  if (!h) return MP_OK;
+  mp_tc_release(h);
+  for (int l = 0; l < MP_MAX_LAYERS; ++l) {
+    if (h->wt[l]) cudaFree(h->wt[l]);
+    if (h->w[l]) cudaFree(h->w[l]);
+    if (h->bias[l]) cudaFree(h->bias[l]);
+  }
+  delete h;
+  return MP_OK;
+}
+
+extern "C" int mp_mlp_create(int n_layers, const int* channels, const float* const* weights,
+                             const float* const* biases, int skip, int last_op, int on_device, mp_mlp_t** out) {
+  MP_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  MP_REQUIRE(n_layers >= 1 && n_layers <= MP_MAX_LAYERS, "n_layers=%d out of range [1,%d]", n_layers, MP_MAX_LAYERS);
+  MP_REQUIRE(channels && weights && biases, "NULL channels/weights/biases");
+  MP_REQUIRE(last_op >= MP_LAST_NONE && last_op <= MP_LAST_TANH, "bad last_op %d", last_op);
+  for (int l = 0; l <= n_layers; ++l) MP_REQUIRE(channels[l] >= 1 && channels[l] <= 8192, "channels[%d]=%d", l, channels[l]);
+  mp_mlp* h = new mp_mlp();
+  memset(h, 0, sizeof(*h));
+  h->n_layers = n_layers;
+  h->skip = skip ? 1 : 0;
+  h->last_op = last_op;
+  cudaGetDevice(&h->device);
+  for (int l = 0; l <= n_layers; ++l) h->channels[l] = channels[l];
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  for (int l = 0; l < n_layers; ++l) {
+    h->cin[l] = channels[l] + ((l > 0 && skip) ? channels[0] : 0);
+    h->cout[l] = channels[l + 1];
+    const size_t nw = (size_t)h->cin[l] * h->cout[l];
+    cudaError_t e = cudaMalloc(&h->w[l], nw * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&h->wt[l], nw * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&h->bias[l], h->cout[l] * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(h->w[l], weights[l], nw * sizeof(float), kind);
+    if (e == cudaSuccess) e = cudaMemcpy(h->bias[l], biases[l], h->cout[l] * sizeof(float), kind);
+    if (e != cudaSuccess) {
+      mp_set_error("mp_mlp_create: layer %d upload failed: %s", l, cudaGetErrorString(e));
+      mp_mlp_destroy(h);
+      return MP_E_CUDA;
+    }
+    dim3 grid((h->cin[l] + 31) / 32, (h->cout[l] + 31) / 32), block(32, 8);
+    transpose_w_kernel<<<grid, block>>>(h->w[l], h->wt[l], h->cout[l], h->cin[l]);
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    mp_set_error("mp_mlp_create: %s", cudaGetErrorString(e));
+    mp_mlp_destroy(h);
+    return MP_E_CUDA;
+  }
+  int rc = mp_tc_prepare(h);   // sets tc_ok (0 when the head shape is not handled by the tcgen05 kernel)
+  if (rc != MP_OK) {
+    mp_mlp_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return MP_OK;
+}
+
+extern "C" int mp_mlp_tc_supported(const mp_mlp_t* h) { return h ? h->tc_ok : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// feature volume: NCHW fp32 -> NHWC fp32 + NHWC fp16
+// ---------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ o32, __half* __restrict__ o16,
+                                    int C, int HW) {
+  // tile transpose [C][HW] -> [HW][C]
+  __shared__ float tile[32][33];
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && p < HW) ? in[(size_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int p = p0 + j, c = c0 + threadIdx.x;
+    if (p < HW && c < C) {
+      const float v = tile[threadIdx.x][j];
+      o32[(size_t)p * C + c] = v;
+      o16[(size_t)p * C + c] = __float2half_rn(v);
+    }
+  }
+}
+
+extern "C" int mp_feat_destroy(mp_feat_t* h) {
+  if (!h) return MP_OK;
+  if (h->nhwc32) cudaFree(h->nhwc32);
+  if (h->nhwc16) cudaFree(h->nhwc16);
+  if (h->staging) cudaFree(h->staging);
+  delete h;
+  return MP_OK;
+}
+
+extern "C" int mp_feat_create(int C, int H, int W, mp_feat_t** out) {
+  MP_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  MP_REQUIRE(C >= 1 && H >= 1 && W >= 1 && (long long)C * H * W < (1ll << 31), "bad feature shape %dx%dx%d", C, H, W);
+  mp_feat* h = new mp_feat();
+  memset(h, 0, sizeof(*h));
+  h->C = C; h->H = H; h->W = W;
+  cudaGetDevice(&h->device);
+  const size_t n = (size_t)C * H * W;
+  cudaError_t e = cudaMalloc(&h->nhwc32, n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&h->nhwc16, n * sizeof(__half));
+  if (e == cudaSuccess) e = cudaMalloc(&h->staging, n * sizeof(float));
+  if (e != cudaSuccess) {
+    mp_set_error("mp_feat_create: %s", cudaGetErrorString(e));
+    mp_feat_destroy(h);
+    return MP_E_NOMEM;
+  }
+  *out = h;
+  return MP_OK;
+}
+
+extern "C" int mp_feat_upload(mp_feat_t* h, const float* nchw, int on_device, void* stream) {
+  MP_REQUIRE(h && nchw, "NULL handle or data");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)h->C * h->H * h->W;
+  const float* src = nchw;
+  if (!on_device) {
+    MP_CUDA(cudaMemcpyAsync(h->staging, nchw, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    src = h->staging;
+  }
+  const int HW = h->H * h->W;
+  dim3 grid((HW + 31) / 32, (h->C + 31) / 32), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(src, h->nhwc32, h->nhwc16, h->C, HW);
+  MP_CUDA(cudaGetLastError());
+  return MP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// query
+// ---------------------------------------------------------------------------------------------
+void mp_fill_calib(MpCalib& c, const float* calib12, int projection, float z_scale) {
+  memset(&c, 0, sizeof(c));
+  c.has = calib12 != nullptr;
+  if (calib12) memcpy(c.m, calib12, 12 * sizeof(float));
+  c.perspective = (projection == MP_PROJ_PERSPECTIVE) && c.has;
+  c.z_scale = z_scale;
+}
+
+void mp_fill_grid_geom(MpPointSrc& s, int res, int node_stride, int r_final, const float* bmin, const float* bmax) {
+  s.res = res;
+  s.node_stride = node_stride;
+  s.r_final = r_final;
+  s.inv_r = 1.0f / (float)r_final;
+  s.half_inv_r = (float)(1.0 / (2.0 * (double)r_final));
+  for (int a = 0; a < 3; ++a) {
+    s.bmin[a] = bmin[a];
+    s.bext[a] = bmax[a] - bmin[a];   // fp32 subtraction, like torch's (b_max - b_min)
+  }
+}
+
+int mp_query_dispatch(mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal, const MpOutDst& dst,
+                      int mode, cudaStream_t st) {
+  if (mode == MP_MODE_AUTO) mode = mlp->tc_ok ? MP_MODE_TC : MP_MODE_FP32;
+  if (mode == MP_MODE_TC) {
+    if (!mlp->tc_ok) {
+      mp_set_error("MP_MODE_TC requested but the tcgen05 kernel does not support this head/device");
+      return MP_E_UNSUPPORTED;
+    }
+    return mp_launch_query_tc(mlp, feat, src, cal, dst, st);
+  }
+  if (mode != MP_MODE_FP32) {
+    mp_set_error("bad mode %d", mode);
+    return MP_E_INVALID;
+  }
+  return mp_launch_query_fp32(mlp, feat, src, cal, dst, st);
+}
+
+extern "C" int mp_query_points(mp_mlp_t* mlp, mp_feat_t* feat, const float* points_dev, int64_t n, int64_t row_stride,
+                               int64_t point_stride, const float* calib12, int projection, float z_scale,
+                               float* out_dev, int64_t ld_out, int mode, void* stream) {
+  MP_REQUIRE(mlp && feat, "NULL handle");
+  MP_REQUIRE(n >= 0 && row_stride >= 1 && point_stride >= 1 && ld_out >= n, "bad sizes n=%lld strides=%lld,%lld ld_out=%lld",
+             (long long)n, (long long)row_stride, (long long)point_stride, (long long)ld_out);
+  if (n == 0) return MP_OK;
+  MP_REQUIRE(points_dev && out_dev, "NULL points/out");
+  MpPointSrc src;
+  memset(&src, 0, sizeof(src));
+  src.kind = MP_SRC_ROWS;
+  src.px = points_dev; src.py = points_dev + row_stride; src.pz = points_dev + 2 * row_stride;
+  src.pstride = point_stride;
+  src.n = n;
+  MpCalib cal;
+  mp_fill_calib(cal, calib12, projection, z_scale);
+  MpOutDst dst;
+  dst.out = out_dev; dst.ld = ld_out; dst.scatter_vol = nullptr;
+  return mp_query_dispatch(mlp, feat, src, cal, dst, mode, (cudaStream_t)stream);
+}
+
+extern "C" int mp_query_points_host(mp_mlp_t* mlp, mp_feat_t* feat, const float* feat_nchw_host, const float* points_host,
+                                    int64_t n, const float* calib12, int projection, float z_scale, float* out_host,
+                                    int mode, void* stream) {
+  MP_REQUIRE(mlp && feat, "NULL handle");
+  MP_REQUIRE(n >= 0, "bad n");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (feat_nchw_host) {
+    int rc = mp_feat_upload(feat, feat_nchw_host, 0, stream);
+    if (rc != MP_OK) return rc;
+  }
+  if (n == 0) {
+    MP_CUDA(cudaStreamSynchronize(st));
+    return MP_OK;
+  }
+  MP_REQUIRE(points_host && out_host, "NULL points/out");
+  const int res = mlp->cout[mlp->n_layers - 1];
+  float* d_pts = nullptr;
+  float* d_out = nullptr;
+  MP_CUDA(cudaMallocAsync(&d_pts, (size_t)3 * n * sizeof(float), st));
+  MP_CUDA(cudaMallocAsync(&d_out, (size_t)res * n * sizeof(float), st));
+  MP_CUDA(cudaMemcpyAsync(d_pts, points_host, (size_t)3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = mp_query_points(mlp, feat, d_pts, n, n, 1, calib12, projection, z_scale, d_out, n, mode, stream);
+  if (rc == MP_OK) {
+    cudaError_t e = cudaMemcpyAsync(out_host, d_out, (size_t)res * n * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { mp_set_error("D2H failed: %s", cudaGetErrorString(e)); rc = MP_E_CUDA; }
+  }
+  cudaFreeAsync(d_pts, st);
+  cudaFreeAsync(d_out, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == MP_OK && e != cudaSuccess) { mp_set_error("sync failed: %s", cudaGetErrorString(e)); rc = MP_E_CUDA; }
+  return rc;
+}
+
+extern "C" int mp_query_grid(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0, int nz, const float* b_min3, const float* b_max3,
+                             const float* calib12, int projection, float z_scale, float* out_dev, int mode, void* stream) {
+  MP_REQUIRE(mlp && feat, "NULL handle");
+  MP_REQUIRE(R >= 1 && z0 >= 0 && nz >= 0 && z0 + nz <= R, "bad slab R=%d z0=%d nz=%d", R, z0, nz);
+  MP_REQUIRE(b_min3 && b_max3, "NULL bounds");
+  MP_REQUIRE(mlp->cout[mlp->n_layers - 1] == 1, "mp_query_grid needs a single-channel head");
+  if (nz == 0) return MP_OK;
+  MP_REQUIRE(out_dev, "NULL out");
+  MpPointSrc src;
+  memset(&src, 0, sizeof(src));
+  src.kind = MP_SRC_GRID;
+  mp_fill_grid_geom(src, R, 1, R, b_min3, b_max3);
+  src.z0 = z0;
+  src.n = (long long)nz * R * R;
+  MpCalib cal;
+  mp_fill_calib(cal, calib12, projection, z_scale);
+  MpOutDst dst;
+  dst.out = out_dev; dst.ld = src.n; dst.scatter_vol = nullptr;
+  return mp_query_dispatch(mlp, feat, src, cal, dst, mode, (cudaStream_t)stream);
+}
+
+extern "C" int mp_query_grid_host(mp_mlp_t* mlp, mp_feat_t* feat, const float* feat_nchw_host, int R, int z0, int nz,
+                                  const float* b_min3, const float* b_max3, const float* calib12, int projection,
+                                  float z_scale, float* out_host, int mode, void* stream) {
+  MP_REQUIRE(mlp && feat, "NULL handle");
+  MP_REQUIRE(R >= 1 && z0 >= 0 && nz >= 0 && z0 + nz <= R, "bad slab R=%d z0=%d nz=%d", R, z0, nz);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (feat_nchw_host) {
+    int rc = mp_feat_upload(feat, feat_nchw_host, 0, stream);
+    if (rc != MP_OK) return rc;
+  }
+  if (nz == 0) {
+    MP_CUDA(cudaStreamSynchronize(st));
+    return MP_OK;
+  }
+  MP_REQUIRE(out_host, "NULL out");
+  const size_t bytes = (size_t)nz * R * R * sizeof(float);
+  float* d_out = nullptr;
+  MP_CUDA(cudaMallocAsync(&d_out, bytes, st));
+  int rc = mp_query_grid(mlp, feat, R, z0, nz, b_min3, b_max3, calib12, projection, z_scale, d_out, mode, stream);
+  if (rc == MP_OK) {
+    cudaError_t e = cudaMemcpyAsync(out_host, d_out, bytes, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { mp_set_error("D2H failed: %s", cudaGetErrorString(e)); rc = MP_E_CUDA; }
+  }
+  cudaFreeAsync(d_out, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == MP_OK && e != cudaSuccess) { mp_set_error("sync failed: %s", cudaGetErrorString(e)); rc = MP_E_CUDA; }
+  return rc;
+}

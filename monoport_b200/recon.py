@@ -1,0 +1,137 @@
+"""Surface extraction + mesh reconstruction on the device.
+
+  pifu_calib, forward_vertices : same signatures/returns as RTL/recon.py:4-25 / :27-89 (the reference file itself can
+                                 also be used unchanged on the volumes the engines return);
+  marching_cubes, reconstruction: additions asked for by the north star (the reference has no marching cubes;
+                                 `reconstruction` follows upstream PIFu's signature).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DIRS = {"front": 0, "back": 1, "left": 2, "right": 3}
+
+
+@torch.no_grad()
+def pifu_calib(extrinsic, intrinsic, device="cuda:0"):
+    """inv(K' E' diag(1,-1,1,1)) in float64 -> float32 [1,4,4]  (RTL/recon.py:4-25; host-side, negligible)."""
+    K = np.array(intrinsic, dtype=np.float64, copy=True)
+    E = np.array(extrinsic, dtype=np.float64, copy=True)
+    K[2, 2] = K[0, 0]
+    K[2, 3] = 0
+    E[2, 3] = 0
+    m = np.linalg.inv(K @ E @ np.diag([1.0, -1.0, 1.0, 1.0]))
+    return torch.from_numpy(m).unsqueeze(0).float().to(device)
+
+
+@torch.no_grad()
+def forward_vertices(sdf, direction="front"):
+    """Visible-surface vertices + normals of a [1,1,R,R,R] occupancy volume (RTL/recon.py:27-89), one kernel pass."""
+    if sdf is None:
+        return None, None, None, None
+    if sdf.device.type != "cuda":
+        raise RuntimeError("monoport_b200.forward_vertices: CUDA tensors only (no CPU path)")
+    vol = sdf[0, 0]
+    if vol.dtype != torch.float32 or not vol.is_contiguous():
+        vol = vol.float().contiguous()
+    R = vol.shape[2]
+    assert vol.shape[0] == R and vol.shape[1] == R, "cubic volumes only"
+    dev = vol.device
+    cap = R * R
+    X = torch.empty(cap, dtype=torch.int64, device=dev)
+    Y = torch.empty(cap, dtype=torch.int64, device=dev)
+    Z = torch.empty(cap, dtype=torch.float32, device=dev)
+    N = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+    n = ctypes.c_int64(0)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().mp_forward_vertices(
+            ctypes.c_void_p(vol.data_ptr()), R, _DIRS[direction], ctypes.c_void_p(X.data_ptr()),
+            ctypes.c_void_p(Y.data_ptr()), ctypes.c_void_p(Z.data_ptr()), ctypes.c_void_p(N.data_ptr()),
+            ctypes.byref(n), _lib.stream_ptr(dev)), "mp_forward_vertices")
+    k = n.value
+    return X[:k], Y[:k], Z[:k], N[:k]
+
+
+class _McubesWorkspace:
+    _cache = {}
+
+    @classmethod
+    def get(cls, shape, device):
+        key = (tuple(shape), device.index)
+        h = cls._cache.get(key)
+        if h is None:
+            h = ctypes.c_void_p()
+            with torch.cuda.device(device):
+                _lib.check(_lib.load().mp_mcubes_create(shape[0], shape[1], shape[2], ctypes.byref(h)), "mp_mcubes_create")
+            cls._cache[key] = h
+        return h
+
+
+@torch.no_grad()
+def marching_cubes(vol, iso=0.5):
+    """[D,H,W] (z,y,x) float32 CUDA volume -> (verts [V,3] float32 in index space (x,y,z), faces [F,3] int32).
+    Indexed, watertight, deterministic ordering (see csrc/mcubes.cu)."""
+    if vol.device.type != "cuda":
+        raise RuntimeError("monoport_b200.marching_cubes: CUDA tensors only (no CPU path)")
+    if vol.dim() == 5:
+        vol = vol[0, 0]
+    if vol.dtype != torch.float32 or not vol.is_contiguous():
+        vol = vol.float().contiguous()
+    dev = vol.device
+    lib = _lib.load()
+    h = _McubesWorkspace.get(vol.shape, dev)
+    nv, nf = ctypes.c_int64(0), ctypes.c_int64(0)
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        _lib.check(lib.mp_mcubes_count(h, ctypes.c_void_p(vol.data_ptr()), ctypes.c_float(iso), ctypes.byref(nv),
+                                       ctypes.byref(nf), st), "mp_mcubes_count")
+        verts = torch.empty((nv.value, 3), dtype=torch.float32, device=dev)
+        faces = torch.empty((nf.value, 3), dtype=torch.int32, device=dev)
+        _lib.check(lib.mp_mcubes_emit(h, ctypes.c_void_p(vol.data_ptr()), ctypes.c_float(iso),
+                                      ctypes.c_void_p(verts.data_ptr()), ctypes.c_void_p(faces.data_ptr()), st),
+                   "mp_mcubes_emit")
+    return verts, faces
+
+
+@torch.no_grad()
+def reconstruction(net, cuda, calib_tensor, resolution, b_min, b_max, use_octree=False, num_samples=10000,
+                   transform=None, feats=None, engine=None):
+    """PIFu-shaped mesh reconstruction (upstream signature): evaluate the occupancy field on a
+    `resolution`^3 grid over [b_min,b_max] (dense through the fused kernel, or coarse-to-fine when `use_octree`),
+    run marching cubes at 0.5, map vertices to world space.  `feats` = net.filter(image) output.
+    Returns (verts [V,3] world, faces [F,3], normals None, values None) or -1 when the volume is empty
+    (upstream returns -1 on marching-cubes failure).  `num_samples` is accepted for signature compatibility
+    (the fused kernel needs no batching)."""
+    if feats is None:
+        raise ValueError("pass feats=net.filter(image)")
+    R = int(resolution)
+    device = torch.device(cuda)
+    b_min_t = torch.as_tensor(np.asarray(b_min, dtype=np.float32)).view(3)
+    b_max_t = torch.as_tensor(np.asarray(b_max, dtype=np.float32)).view(3)
+    if use_octree:
+        if engine is None:
+            from .engine import Seg3dLossless, make_query_func
+            res = [R]
+            while res[0] > 17 and (res[0] - 1) % 2 == 0:
+                res.insert(0, (res[0] - 1) // 2 + 1)
+            engine = Seg3dLossless(make_query_func(net), b_min_t.numpy()[None], b_max_t.numpy()[None], res,
+                                   balance_value=0.5, faster=False).to(device)
+        sdf = engine(im_feat_list=feats, calib_tensor=calib_tensor)
+        if sdf is None:
+            return -1
+        vol = sdf[0, 0]
+    else:
+        vol = net.query_grid(feats[-1][0], calib_tensor, R, b_min_t, b_max_t)
+    verts, faces = marching_cubes(vol, 0.5)
+    if verts.shape[0] == 0:
+        return -1
+    # index space -> world:  (v + 0.5)/R * (b_max-b_min) + b_min  (node-centre convention of the engines)
+    scale = ((b_max_t - b_min_t) / R).to(verts.device)
+    verts = (verts + 0.5) * scale + b_min_t.to(verts.device)
+    if transform is not None:
+        T = torch.as_tensor(transform, dtype=torch.float32, device=verts.device)
+        verts = verts @ T[:3, :3].T + T[:3, 3]
+    return verts, faces, None, None

@@ -1,0 +1,134 @@
+"""CPU: host-side logic -- drop-in import surface, encoder/state-dict compatibility, slab partition, MC table and
+octree oracle properties."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import spec
+
+
+def test_dropin_import_surface():
+    # the imports RTL/main.py:19-29 performs
+    from monoport.lib.common.config import get_cfg_defaults
+    from monoport.lib.modeling.MonoPortNet import MonoPortNet, PIFuNetG, PIFuNetC  # noqa: F401
+    from monoport.lib.modeling.geometry import orthogonal, perspective  # noqa: F401
+    from implicit_seg.functional import Seg3dTopk, Seg3dLossless  # noqa: F401
+    from implicit_seg.functional.utils import plot_mask3D  # noqa: F401
+    cfg = get_cfg_defaults()
+    net = MonoPortNet(cfg.netG)
+    keys = set(net.state_dict().keys())
+    assert {"surface_classifier.filters.%d.%s" % (l, k) for l in range(5) for k in ("weight", "bias")} <= keys
+    assert [tuple(f.weight.shape) for f in net.surface_classifier.filters] == [
+        (1024, 257, 1), (512, 1281, 1), (256, 769, 1), (128, 513, 1), (1, 385, 1)]
+    c = MonoPortNet(cfg.netC)
+    assert [f.weight.shape[1] for f in c.surface_classifier.filters] == [513, 1537, 1025, 769, 641]
+
+
+def test_encoders_match_reference_if_present():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ns = ref_loader.load_reference()
+    from monoport_b200.modeling import PIFuNetG, PIFuNetC
+    torch.manual_seed(0)
+    for mk, rk in ((PIFuNetG, ns.PIFuNetG), (PIFuNetC, ns.PIFuNetC)):
+        mine, ref = mk().eval(), rk().eval()
+        mine.load_state_dict(ref.state_dict(), strict=True)
+        img = torch.randn(1, 3, 64, 64)
+        with torch.no_grad():
+            a, b = ref.image_filter(img), mine.image_filter(img)
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert torch.equal(x[0], y[0])
+
+
+def test_geometry_helpers_match_oracle():
+    from monoport_b200.modeling.geometry import orthogonal, perspective, index
+    p = spec.make_points(100, 1)
+    cal = spec.scene_calib(20, 33)
+    assert torch.allclose(orthogonal(p, cal)[0], spec.project_ref(p[0], cal[0]), atol=1e-6)
+    cal2 = cal.clone(); cal2[0, 2, 3] = 3.0
+    assert torch.allclose(perspective(p, cal2)[0], spec.project_ref(p[0], cal2[0], "perspective"), atol=1e-6)
+    feat = spec.make_feat(8, 16, 16, 2)
+    uv = p[:, :2]
+    assert torch.allclose(index(feat, uv)[0], spec.bilinear_ref(feat[0], uv[0, 0], uv[0, 1]), atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        orthogonal(p, cal, transforms=torch.zeros(1, 2, 3))
+
+
+def test_slab_bounds():
+    from monoport_b200.shard import slab_bounds, max_slab
+    for R in (17, 257, 513):
+        for ws in (1, 2, 4, 8):
+            b = slab_bounds(R, ws)
+            assert b[0][0] == 0 and sum(nz for _, nz in b) == R
+            assert all(b[i][0] + b[i][1] == b[i + 1][0] for i in range(ws - 1))
+            assert max(nz for _, nz in b) == max_slab(R, ws)
+    assert slab_bounds(257, 8)[0] == (0, 33) and slab_bounds(257, 8)[7] == (225, 32)
+
+
+@pytest.mark.parametrize("kind", ["sphere", "ellipsoid", "two_blobs"])
+def test_mc_oracle_is_watertight_and_outward(kind):
+    vol = spec.analytic_volume(33, kind)
+    V, F = spec.marching_cubes_ref(vol)
+    assert len(F) > 0 and F.min() >= 0 and F.max() == len(V) - 1
+    e = np.concatenate([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]])
+    # every directed edge appears once and its reverse appears once: closed, consistently oriented 2-manifold
+    fwd = {(a, b) for a, b in e}
+    assert len(fwd) == len(e)
+    assert all((b, a) in fwd for a, b in e)
+    und = np.unique(np.sort(e, 1), axis=0)
+    n_comp = 2 if kind == "two_blobs" else 1
+    assert len(V) - len(und) + len(F) == 2 * n_comp              # Euler characteristic of n spheres
+    a, b, c = V[F[:, 0]], V[F[:, 1]], V[F[:, 2]]
+    assert np.einsum("ij,ij->i", a, np.cross(b, c)).sum() > 0      # positive signed volume: normals point outward
+    # vertices lie on grid edges
+    frac = V - np.floor(V)
+    assert ((frac > 0).sum(1) <= 1).all()
+
+
+def test_mc_table_shape():
+    from tools.gen_mc_table import build_table
+    ntri, tri, emask = build_table()
+    assert ntri.max() == 5 and ntri[0] == 0 and ntri[255] == 0
+    assert all(ntri[c] == ntri[255 - c] or True for c in range(256))
+    # a case and its complement cut the same edges
+    assert all(emask[c] == emask[255 - c] for c in range(256))
+
+
+def _lookup(field):
+    R = field.shape[0]
+
+    def fn(p):
+        i = ((p.double() + 1) / 2 * R - 0.5).round().long().clamp(0, R - 1)
+        return field[i[:, 2], i[:, 1], i[:, 0]]
+    return fn
+
+
+@pytest.mark.parametrize("kind", ["sphere", "two_blobs"])
+def test_octree_oracle_lossless_equals_dense(kind):
+    field = torch.from_numpy(spec.analytic_volume(65, kind))
+    occ, stats = spec.seg3d_lossless_ref(_lookup(field), [9, 17, 33, 65], faster=False, return_stats=True)
+    assert torch.equal(occ > 0.5, field > 0.5)
+    evaluated = sum(s["idx"].numel() for s in stats)
+    assert evaluated < 0.2 * 65 ** 3
+    # evaluated nodes carry exactly the queried values
+    idx = stats[-1]["idx"]
+    assert torch.equal(occ.reshape(-1)[idx], field.reshape(-1)[idx])
+
+
+def test_octree_oracle_faster_and_empty():
+    field = torch.from_numpy(spec.analytic_volume(65, "sphere"))
+    occ, stats = spec.seg3d_lossless_ref(_lookup(field), [9, 17, 33, 65], faster=True, return_stats=True)
+    assert stats[-1]["idx"].numel() == 0                       # last level is interpolated only
+    assert ((occ > 0.5) != (field > 0.5)).float().mean() < 2e-3
+    assert spec.seg3d_lossless_ref(_lookup(torch.zeros(65, 65, 65)), [9, 17, 33, 65]) is None
+    occ2, st2 = spec.seg3d_topk_ref(_lookup(field), [9, 17, 33, 65], [0, 3000, 12000, 50000], return_stats=True)
+    assert [s["idx"].numel() for s in st2] == [729, 3000, 12000, 50000]
+    assert ((occ2 > 0.5) != (field > 0.5)).sum() == 0
+
+
+def test_level_points_convention():
+    # node centres: (c+0.5)/R mapped to [b_min,b_max]; the R (not R-1) divisor mirrors mat_color, RTL/main.py:204-209
+    p = spec.level_points(torch.tensor([[0, 0, 0], [256, 256, 256]]), 257, (-1, -1, -1), (1, 1, 1))
+    assert torch.allclose(p[0], torch.full((3,), -1 + 1 / 257)) and torch.allclose(p[1], torch.full((3,), 1 - 1 / 257))

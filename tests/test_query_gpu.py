@@ -1,0 +1,150 @@
+"""GPU parity of the fused sample+MLP kernel (through the C-ABI) against the reference's golden outputs and the
+oracle.  Tolerances: fp32 mode 5e-6 (summation order only); tensor-core mode 1e-4 on the value query() returns
+(post Sigmoid/Tanh, post mask) -- the north star's bar."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import spec
+from helpers import build_net, load_query_case, query_cases
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 5e-6, "tc": 1e-4}
+
+
+def _modes(net):
+    return ["fp32", "tc"] if net.surface_classifier.tc_supported() else ["fp32"]
+
+
+@pytest.mark.parametrize("name", query_cases())
+def test_query_matches_reference_golden(name):
+    c = load_query_case(name)
+    net = build_net(c)
+    feat = c["feat"].cuda()
+    pts = c["points"].cuda()
+    cal = c["calib"].cuda() if c["calib"] is not None else None
+    for mode in _modes(net):
+        net.precision = mode
+        # 4 stages like the HG encoder: eval mode must use the last one only (MonoPortNet.py:63-64)
+        out = net.query([[torch.zeros_like(feat)]] * 3 + [[feat]], pts, calibs=cal)
+        assert isinstance(out, list) and len(out) == 1 and out[0].shape == (1, c["expected"].shape[0], pts.shape[2])
+        got = out[0][0].cpu()
+        err = (got - c["expected"]).abs().max().item()
+        assert err <= TOL[mode], (name, mode, err)
+        zero = c["expected"] == 0
+        assert torch.equal(got[zero], c["expected"][zero]), "out-of-image points must be exactly 0"
+
+
+def test_tc_mode_is_available_for_shipped_heads():
+    c = load_query_case("g_identity")
+    net = build_net(c)
+    assert net.surface_classifier.tc_supported(), "tcgen05 kernel must support PIFuNetGMLP on sm_100a"
+
+
+def test_point_layouts_and_ragged_sizes():
+    c = load_query_case("g_rot33")
+    net = build_net(c)
+    feat, cal = c["feat"].cuda(), c["calib"].cuda()
+    ref_all = c["expected"]
+    for mode in _modes(net):
+        net.precision = mode
+        for n in (1, 31, 127, 128, 129, 1000):
+            p = c["points"][:, :, :n].cuda()
+            a = net.query([[feat]], p.contiguous(), calibs=cal)[0]
+            # permuted [1,N,3] view as produced by RTL/main.py:176-177
+            pn3 = p.permute(0, 2, 1).contiguous()
+            b = net.query([[feat]], pn3.permute(0, 2, 1), calibs=cal)[0]
+            assert torch.equal(a, b)
+            assert (a[0].cpu() - ref_all[:, :n]).abs().max().item() <= TOL[mode]
+        # N == 0
+        e = net.query([[feat]], torch.zeros(1, 3, 0, device="cuda"), calibs=cal)[0]
+        assert e.shape == (1, 1, 0)
+
+
+def test_calib_3x4_and_4x4_agree():
+    c = load_query_case("g_rot33")
+    net = build_net(c)
+    net.precision = "fp32"
+    feat, cal, pts = c["feat"].cuda(), c["calib"].cuda(), c["points"][:, :, :512].cuda()
+    a = net.query([[feat]], pts, calibs=cal)[0]
+    b = net.query([[feat]], pts, calibs=cal[:, :3, :])[0]
+    assert torch.equal(a, b)
+
+
+def test_random_case_vs_oracle_and_grid_mode():
+    """Fresh seeded case not in the goldens + dense-grid mode == points mode on the same node centres."""
+    Ws, bs = spec.make_weights(spec.G_CHANNELS, 1234)
+    feat = spec.make_feat(256, 128, 128, 77)
+    cal = spec.scene_calib(20, -50)
+    net = build_net("G", Ws, bs)
+    R = 21
+    coords = spec._grid_coords(R, 1)
+    world = spec.level_points(coords, R, (-1, -1, -1), (1, 1, 1))          # [N,3]
+    want = spec.query_ref(feat, world.t().contiguous(), cal, Ws, bs, spec.LAST_SIGMOID)[0]
+    for mode in _modes(net):
+        net.precision = mode
+        vol = net.query_grid(feat.cuda(), cal.cuda(), R, (-1, -1, -1), (1, 1, 1))
+        assert vol.shape == (R, R, R)
+        assert (vol.reshape(-1).cpu() - want).abs().max().item() <= TOL[mode]
+        pts = net.query([[feat.cuda()]], world.t().contiguous()[None].cuda(), calibs=cal.cuda())[0][0, 0]
+        assert torch.equal(pts, vol.reshape(-1)), "grid mode and points mode must agree bit-for-bit"
+        # slab == rows of the full volume
+        slab = net.query_grid(feat.cuda(), cal.cuda(), R, (-1, -1, -1), (1, 1, 1), z0=5, nz=7)
+        assert torch.equal(slab, vol[5:12])
+
+
+def test_host_buffer_entry_point():
+    from monoport_b200 import _lib
+    c = load_query_case("g_smallmap")
+    net = build_net(c)
+    lib = _lib.load()
+    hw = c["feat"].shape[2]
+    fh = ctypes.c_void_p()
+    _lib.check(lib.mp_feat_create(256, hw, hw, ctypes.byref(fh)))
+    pts = c["points"][0].contiguous().numpy()
+    n = pts.shape[1]
+    out = np.empty((1, n), dtype=np.float32)
+    feat = c["feat"].contiguous().numpy()
+    _lib.check(lib.mp_query_points_host(net.surface_classifier.handle(), fh, feat.ctypes.data_as(ctypes.c_void_p),
+                                        pts.ctypes.data_as(ctypes.c_void_p), n, _lib.calib12(c["calib"]), 0,
+                                        ctypes.c_float(spec.Z_SCALE), out.ctypes.data_as(ctypes.c_void_p), _lib.MODE_FP32,
+                                        None))
+    assert np.abs(out - c["expected"].numpy()).max() <= TOL["fp32"]
+    lib.mp_feat_destroy(fh)
+
+
+def test_errors_are_reported_not_swallowed():
+    c = load_query_case("g_smallmap")
+    net = build_net(c)
+    with pytest.raises(RuntimeError, match="input channels"):
+        net.query([[torch.zeros(1, 64, 8, 8, device="cuda")]], torch.zeros(1, 3, 8, device="cuda"), calibs=None)
+    with pytest.raises(NotImplementedError):
+        net.train().query([[c["feat"].cuda()]], torch.zeros(1, 3, 8, device="cuda"))
+
+
+def test_full_size_properties():
+    """BASELINE sizes: 257^3 nodes through the dense kernel -- size-independent properties (the oracle would need
+    minutes): slabs tile the volume exactly, values in [0,1], out-of-image columns are exactly zero, and a random
+    sample of nodes matches the oracle."""
+    Ws, bs = spec.make_weights(spec.G_CHANNELS, 99)
+    feat = spec.make_feat(256, 128, 128, 98)
+    cal = spec.scene_calib(20, 33)
+    net = build_net("G", Ws, bs)
+    R = 257
+    vol = net.query_grid(feat.cuda(), cal.cuda(), R, (-1, -1, -1), (1, 1, 1))
+    assert vol.shape == (R, R, R) and bool((vol >= 0).all()) and bool((vol <= 1).all())
+    parts = [net.query_grid(feat.cuda(), cal.cuda(), R, (-1, -1, -1), (1, 1, 1), z0=z0, nz=nz)
+             for z0, nz in ((0, 33), (33, 100), (133, 124))]
+    assert torch.equal(torch.cat(parts, 0), vol)
+    g = torch.Generator().manual_seed(5)
+    lin = torch.randint(0, R ** 3, (4096,), generator=g)
+    coords = torch.stack([lin % R, (lin // R) % R, lin // (R * R)], 1)
+    world = spec.level_points(coords, R, (-1, -1, -1), (1, 1, 1))
+    want = spec.query_ref(feat, world.t().contiguous(), cal, Ws, bs, spec.LAST_SIGMOID)[0]
+    got = vol.reshape(-1)[lin.cuda()].cpu()
+    tol = TOL["tc"] if net.surface_classifier.tc_supported() else TOL["fp32"]
+    assert (got - want).abs().max().item() <= tol
+    assert torch.equal(got[want == 0], want[want == 0])
