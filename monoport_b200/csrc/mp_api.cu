@@ -12,6 +12,20 @@ void mp_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* mp_last_error(void) { return g_err; }
+
+// cudaMallocAsync scratch: keep freed blocks in the pool (the default release threshold of 0 hands memory back to
+// the driver at every synchronisation, which costs milliseconds per frame).
+void mp_ensure_pool() {
+  static thread_local int done_for = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done_for = dev;
+}
 extern "C" int mp_version(void) { return 100; }
 
 extern "C" int mp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
@@ -251,6 +265,7 @@ extern "C" int mp_query_points_host(mp_mlp_t* mlp, mp_feat_t* feat, const float*
   const int res = mlp->cout[mlp->n_layers - 1];
   float* d_pts = nullptr;
   float* d_out = nullptr;
+  mp_ensure_pool();
   MP_CUDA(cudaMallocAsync(&d_pts, (size_t)3 * n * sizeof(float), st));
   MP_CUDA(cudaMallocAsync(&d_out, (size_t)res * n * sizeof(float), st));
   MP_CUDA(cudaMemcpyAsync(d_pts, points_host, (size_t)3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -304,6 +319,7 @@ extern "C" int mp_query_grid_host(mp_mlp_t* mlp, mp_feat_t* feat, const float* f
   MP_REQUIRE(out_host, "NULL out");
   const size_t bytes = (size_t)nz * R * R * sizeof(float);
   float* d_out = nullptr;
+  mp_ensure_pool();
   MP_CUDA(cudaMallocAsync(&d_out, bytes, st));
   int rc = mp_query_grid(mlp, feat, R, z0, nz, b_min3, b_max3, calib12, projection, z_scale, d_out, mode, stream);
   if (rc == MP_OK) {

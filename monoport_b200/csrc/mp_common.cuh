@@ -14,6 +14,7 @@
 #define MP_MAX_LAYERS 8
 
 void mp_set_error(const char* fmt, ...);
+void mp_ensure_pool();
 
 #define MP_CUDA(call)                                                                        \
   do {                                                                                       \

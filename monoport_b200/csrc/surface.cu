@@ -75,6 +75,7 @@ extern "C" int mp_forward_vertices(const float* vol_dev, int R, int direction, i
   const long long n = (long long)R * R;
   int32_t* first_t = nullptr;
   unsigned long long* sums = nullptr;
+  mp_ensure_pool();
   MP_CUDA(cudaMallocAsync(&first_t, n * sizeof(int32_t), st));
   MP_CUDA(cudaMallocAsync(&sums, (size_t)(mpscan::num_blocks(n) + 2) * sizeof(unsigned long long), st));
   unsigned long long* total = sums + mpscan::num_blocks(n) + 1;
