@@ -14,6 +14,9 @@ from helpers import build_net, load_query_case, query_cases
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 2e-5, "tc": 1e-4}
+# stress case: features scaled x4 (N(0,16)) -- fp16 operand rounding scales with the activations; measured 2.4e-4
+# with the tensor-core path (the survey's probe predicted >1e-4 here); fp32 mode stays at 2e-5.  See DESIGN.md §precision.
+TOL_STRESS = {"fp32": 2e-5, "tc": 4e-4}
 
 
 def _modes(net):
@@ -34,7 +37,7 @@ def test_query_matches_reference_golden(name):
         assert isinstance(out, list) and len(out) == 1 and out[0].shape == (1, c["expected"].shape[0], pts.shape[2])
         got = out[0][0].cpu()
         err = (got - c["expected"]).abs().max().item()
-        assert err <= TOL[mode], (name, mode, err)
+        assert err <= (TOL_STRESS if name == "g_bigfeat" else TOL)[mode], (name, mode, err)
         zero = c["expected"] == 0
         assert torch.equal(got[zero], c["expected"][zero]), "out-of-image points must be exactly 0"
 
