@@ -20,10 +20,21 @@
 //      TMEM (tcgen05.mma with A in tensor memory), so they never touch shared memory.
 // TMEM map: [0,256) acc1-half / acc2 / acc3 | [256,384) acc0, later H1 (ch 256..511) | [384,512) H1 (ch 0..255), later H2
 //
+// Two variants of the same kernel (template parameter CG):
+//   CG = 1  one CTA per tile, tcgen05.mma.cta_group::1 (M = 128), weight ring 3 x 32 KB;
+//   CG = 2  a 2-CTA cluster (one TPC) runs cta_group::2 MMAs with M = 256 = 128 points of each CTA; every weight tile is
+//           split between the two CTAs' shared memories, so each SM ingests (and reads) only half of the weight bytes
+//           per point -- the weight stream is the bottleneck of the CG = 1 kernel (ncu: tensor pipe 35% active, the MMA
+//           warp spends its time waiting for weight stages).  Ring 6 x 16 KB per CTA.  The leader CTA (rank 0) issues all
+//           MMAs; cross-CTA hand-offs (operands ready / accumulators drained) are mbarrier arrivals on the leader's
+//           barriers (mapa + mbarrier.arrive.release.cluster), MMA completions are multicast to both CTAs by
+//           tcgen05.commit.multicast.
+//
 // Warp roles (384 threads): warp 0 weight producer, warp 1 MMA issuer (one lane), warp 2 TMEM allocator, warps 4-11
 // workers: all eight sample the tile's X, then act as two epilogue warpgroups (each drains half of the columns).
 #include "mp_common.cuh"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -31,8 +42,13 @@ constexpr int kC = 256;                 // feature channels
 constexpr int kTile = 128;              // points per tile
 constexpr int kThreads = 384;
 constexpr int kWorkers = 256;           // warps 4..11
-constexpr int kStages = 3;
-constexpr int kStageBytes = 32768;
+template <int CG> struct Cfg {
+  static constexpr int Stages = 3 * CG;
+  static constexpr int StageBytes = 32768 / CG;
+  static constexpr int Sub = StageBytes / 2;       // second K-block of a two-K-block (128-row tile) stage
+};
+constexpr int kStages = 6;                          // barrier slots reserved (max over variants)
+constexpr int kRingBytes = 98304;
 constexpr int kL0 = 1024, kL1 = 512, kL2 = 256, kL3 = 128;
 constexpr int kMaxRes = 1;             // output channels handled by the fp32 tail (PIFuNetGMLP: 1)
 
@@ -43,10 +59,16 @@ constexpr int kStagesPerTile = 2 * kStagesPerHalf + 12 + 4;       // + L2 (8 hid
 // TMEM columns
 constexpr uint32_t kColAcc1 = 0, kColAcc0 = 256, kColH1lo = 384, kColH1hi = 256, kColH2 = 384;
 
+constexpr int kSideFloats = kL0 + kL1 + kL2 + kL3;      // 1920 hidden output channels over layers 0..3
+__host__ __device__ constexpr int side_off(int l) { return l == 0 ? 0 : l == 1 ? kL0 : l == 2 ? kL0 + kL1 : kL0 + kL1 + kL2; }
+
 struct TcPack {
-  __half* wstream;        // kStagesPerTile * 32 KB
+  __half* wstream;        // CG=1: kStagesPerTile * 32 KB
+  __half* wstream2[2];    // CG=2: per cluster rank, kStagesPerTile * 16 KB
   float* bias[4];         // per hidden layer
   float* wz[4];           // z column of every hidden layer
+  float h_bias[kSideFloats];   // host copies (passed by value in the kernel parameters)
+  float h_wz[kSideFloats];
   float* w4h;             // [R][128]  last layer, hidden part
   float* w4s;             // [R][256]  last layer, feature part
   float* w4z;             // [R]
@@ -56,8 +78,11 @@ struct TcPack {
 
 struct TcParams {
   const __half* wstream;
-  const float* bias[4];
-  const float* wz[4];
+  const __half* wstream2[2];
+  // per-channel bias and depth-column weight of layers 0..3, carried in the kernel parameter (constant) bank: the
+  // epilogue reads them with warp-uniform indices, so they cost no load instructions and no shared memory
+  float bias_all[kSideFloats];
+  float wz_all[kSideFloats];
   const float* w4h;
   const float* w4s;
   const float* w4z;
@@ -66,20 +91,26 @@ struct TcParams {
   int last_op;
   int H, W;
   const __half* feat;     // NHWC fp16
+  unsigned long long* prof;   // optional [gridDim.x][32] cycle counters (MONOPORT_B200_TC_PROF=1), else null
 };
+enum Prof { P_TOTAL = 0, P_XREADY, P_ACC0FREE, P_WFULL, P_WPEER, P_H0READY, P_ACC1DRAINED, P_H1READY, P_H2READY,
+            P_W_SAMPLE = 16, P_W_ACC0FULL, P_W_H0FREE, P_W_ACC1FULL, P_W_ACC2FULL, P_W_ACC3FULL, P_W_DRAIN0, P_W_DRAIN1,
+            P_W_DRAIN2, P_W_DRAIN3, P_W_XFREE };
+#define PROF_T0() const long long _t0 = prof ? clock64() : 0
+#define PROF_ADD(slot) do { if (prof) prof[slot] += (unsigned long long)(clock64() - _t0); } while (0)
 
 struct Smem {
   // offsets inside the 1024-aligned dynamic shared memory block
   static constexpr int X = 0;                                   // 4 K-blocks x 16 KB
   static constexpr int H0 = X + 65536;                          // 2 buffers x (2 K-blocks x 16 KB)
   static constexpr int Wr = H0 + 65536;                         // kStages x 32 KB
-  static constexpr int Small = Wr + kStages * kStageBytes;      // zf[128], inimg[128], s4[kMaxRes][128]
+  static constexpr int Small = Wr + kRingBytes;                 // zf[128], inimg[128], s4[kMaxRes][128]
   static constexpr int Bars = Small + (2 + kMaxRes) * kTile * 4;
-  static constexpr int NumBars = 2 * kStages + 13;
+  static constexpr int NumBars = 3 * kStages + 13;
   static constexpr int TmemPtr = Bars + NumBars * 8;
   static constexpr int Total = TmemPtr + 16;
 };
-enum Bar { B_WFULL = 0, B_WEMPTY = kStages, B_XREADY = 2 * kStages, B_ACC0_FULL, B_ACC0_FREE, B_H0_READY0, B_H0_READY1,
+enum Bar { B_WFULL = 0, B_WEMPTY = kStages, B_WPEER = 2 * kStages, B_XREADY = 3 * kStages, B_ACC0_FULL, B_ACC0_FREE, B_H0_READY0, B_H0_READY1,
            B_H0_FREE0, B_H0_FREE1, B_ACC1_FULL, B_H1_READY, B_ACC2_FULL, B_H2_READY, B_ACC3_FULL, B_TILE_DONE };
 static_assert(B_TILE_DONE + 1 == Smem::NumBars, "barrier count");
 static_assert(Smem::Total + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
@@ -100,8 +131,33 @@ __device__ __forceinline__ void wait_free(uint64_t* bars, int which, uint32_t& c
 }
 
 // --------------------------------------------------------------------------------------------------------------------
+// hand-off helpers.  Producers of operands (workers) signal the MMA issuer, which lives in the leader CTA (rank 0):
+// one elected lane per warp arrives after __syncwarp(); every lane has already executed its own proxy / tcgen05 fence.
+template <int CG>
+__device__ __forceinline__ void warp_arrive_leader(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    if constexpr (CG == 1) tc::mbar_arrive(bar);
+    else tc::mbar_arrive_remote(bar, 0);
+  }
+}
+template <int CG>
+__device__ __forceinline__ void wait_leader(uint64_t* bars, int which, uint32_t& count, bool free_type = false) {
+  const uint32_t par = (count & 1u) ^ (free_type ? 1u : 0u);
+  if constexpr (CG == 1) tc::mbar_wait(bars + which, par);
+  else tc::mbar_wait_cluster(bars + which, par);
+  ++count;
+}
+template <int CG>
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  if constexpr (CG == 1) tc::mma_commit(bar);
+  else tc::mma_commit2(bar);
+}
+
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
+  using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::Bars);
@@ -111,6 +167,9 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Smem::TmemPtr);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned long long* prof = prm.prof ? prm.prof + (size_t)blockIdx.x * 32 : nullptr;
+  const uint32_t rank = (CG == 2) ? tc::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
 
   long long n = src.n;
   if (src.count_dev) {
@@ -118,125 +177,163 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     n = c < n ? c : n;
   }
   const long long n_tiles = (n + kTile - 1) / kTile;
+  // the unit of scheduling is a group of CG tiles (one per CTA of the cluster); every CTA of a cluster runs the same
+  // number of iterations, a CTA whose tile lies beyond n_tiles computes on masked-out points
+  const long long n_groups = (n_tiles + CG - 1) / CG;
+  const long long g0 = blockIdx.x / CG, gstep = gridDim.x / CG;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { tc::mbar_init(bars + B_WFULL + s, 1); tc::mbar_init(bars + B_WEMPTY + s, 1); }
-    tc::mbar_init(bars + B_XREADY, kWorkers);
+    for (int s = 0; s < kStages; ++s) {
+      tc::mbar_init(bars + B_WFULL + s, 1);
+      tc::mbar_init(bars + B_WEMPTY + s, 1);
+      tc::mbar_init(bars + B_WPEER + s, 1);
+    }
+    constexpr int kW = 8 * CG;                        // one arrival per worker warp of every CTA in the cluster
+    tc::mbar_init(bars + B_XREADY, kW);
     tc::mbar_init(bars + B_ACC0_FULL, 1);
-    tc::mbar_init(bars + B_ACC0_FREE, kWorkers);
-    tc::mbar_init(bars + B_H0_READY0, kWorkers);
-    tc::mbar_init(bars + B_H0_READY1, kWorkers);
+    tc::mbar_init(bars + B_ACC0_FREE, kW);   // (unused: acc0-free is implied by B_H0_READY)
+    tc::mbar_init(bars + B_H0_READY0, kW);
+    tc::mbar_init(bars + B_H0_READY1, kW);
     tc::mbar_init(bars + B_H0_FREE0, 1);
     tc::mbar_init(bars + B_H0_FREE1, 1);
     tc::mbar_init(bars + B_ACC1_FULL, 1);
-    tc::mbar_init(bars + B_H1_READY, kWorkers);
+    tc::mbar_init(bars + B_H1_READY, kW);
     tc::mbar_init(bars + B_ACC2_FULL, 1);
-    tc::mbar_init(bars + B_H2_READY, kWorkers);
+    tc::mbar_init(bars + B_H2_READY, kW);
     tc::mbar_init(bars + B_ACC3_FULL, 1);
-    tc::mbar_init(bars + B_TILE_DONE, kTile);
+    tc::mbar_init(bars + B_TILE_DONE, 4 * CG);
     tc::fence_barrier_init();
   }
   if (warp == 2) {
-    tc::tmem_alloc(s_tmem, 512);
-    tc::tmem_relinquish();
+    if constexpr (CG == 1) { tc::tmem_alloc(s_tmem, 512); tc::tmem_relinquish(); }
+    else { tc::tmem_alloc2(s_tmem, 512); tc::tmem_relinquish2(); }
   }
   tc::tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CG == 1) __syncthreads(); else tc::cluster_sync_all();
   tc::tcgen05_fence_after();
   const uint32_t tbase = *s_tmem;
 
   if (warp == 0) {
-    // ============================== weight producer ==============================
+    // ============================== weight producer (every CTA streams its own part of every tile) ===========
     if (lane == 0) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(CG == 2 ? prm.wstream2[rank] : prm.wstream);
       uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (long long g = g0; g < n_groups; g += gstep) {
         for (int s = 0; s < kStagesPerTile; ++s, ++it) {
-          const int slot = it % kStages;
-          const uint32_t use = it / kStages;
+          const int slot = it % C::Stages;
+          const uint32_t use = it / C::Stages;
           tc::mbar_wait(bars + B_WEMPTY + slot, (use & 1u) ^ 1u);
-          tc::mbar_arrive_expect_tx(bars + B_WFULL + slot, kStageBytes);
-          tc::bulk_g2s(smem + Smem::Wr + slot * kStageBytes,
-                       reinterpret_cast<const uint8_t*>(prm.wstream) + (size_t)s * kStageBytes, kStageBytes,
+          tc::mbar_arrive_expect_tx(bars + B_WFULL + slot, C::StageBytes);
+          tc::bulk_g2s(smem + Smem::Wr + slot * C::StageBytes,
+                       wsrc + (size_t)s * C::StageBytes, C::StageBytes,
                        bars + B_WFULL + slot);
         }
       }
     }
-  } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
+  } else if (warp == 1 && !leader) {
+    // ============================== peer CTA: tell the leader when our half of a weight stage has landed ========
     if (lane == 0) {
-      const uint32_t idesc128 = tc::make_idesc_f16(128, 128);
-      const uint32_t idesc256 = tc::make_idesc_f16(128, 256);
+      uint32_t it = 0;
+      for (long long g = g0; g < n_groups; g += gstep) {
+        for (int s = 0; s < kStagesPerTile; ++s, ++it) {
+          const int slot = it % C::Stages;
+          tc::mbar_wait(bars + B_WFULL + slot, (it / C::Stages) & 1u);
+          tc::mbar_arrive_remote(bars + B_WPEER + slot, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer (leader CTA, one lane) ==============================
+    if (lane == 0) {
+      const uint32_t idesc128 = tc::make_idesc_f16(128 * CG, 128);
+      const uint32_t idesc256 = tc::make_idesc_f16(128 * CG, 256);
       const uint32_t sX = tc::smem_u32(smem + Smem::X);
       const uint32_t sH0 = tc::smem_u32(smem + Smem::H0);
       const uint32_t sW = tc::smem_u32(smem + Smem::Wr);
-      uint32_t it = 0;                                  // weight stage counter (mirrors the producer)
-      uint32_t c_xready = 0, c_acc0free = 0, c_h0ready[2] = {0, 0}, c_h1ready = 0, c_h2ready = 0, c_tiledone = 0;
+      uint32_t it = 0;                                  // weight stage counter (mirrors the producers)
+      uint32_t c_xready = 0, c_h0ready[2] = {0, 0}, c_h1ready = 0, c_h2ready = 0, c_tiledone = 0;
 
-      // fetch the next weight stage; returns its smem address
+      const long long t_begin = prof ? clock64() : 0;
       auto next_stage = [&]() -> uint32_t {
-        const int slot = it % kStages;
-        tc::mbar_wait(bars + B_WFULL + slot, (it / kStages) & 1u);
+        const int slot = it % C::Stages;
+        const uint32_t par = (it / C::Stages) & 1u;
+        { PROF_T0(); tc::mbar_wait(bars + B_WFULL + slot, par); PROF_ADD(P_WFULL); }
+        if constexpr (CG == 2) { PROF_T0(); tc::mbar_wait_cluster(bars + B_WPEER + slot, par); PROF_ADD(P_WPEER); }
         tc::tcgen05_fence_after();
-        return sW + slot * kStageBytes;
+        return sW + slot * C::StageBytes;
       };
       auto release_stage = [&]() {
-        tc::mma_commit(bars + B_WEMPTY + (it % kStages));
+        commit<CG>(bars + B_WEMPTY + (it % C::Stages));
         ++it;
       };
-      // 4 MMAs over one 64-wide K-block, A from smem
       auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool& first) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          tc::mma_ss(d, tc::make_sdesc_sw128(a_addr + kk * 32, 1024), tc::make_sdesc_sw128(b_addr + kk * 32, 1024), idesc,
-                     first ? 0u : 1u);
+          const uint64_t ad = tc::make_sdesc_sw128(a_addr + kk * 32, 1024), bd = tc::make_sdesc_sw128(b_addr + kk * 32, 1024);
+          if constexpr (CG == 1) tc::mma_ss(d, ad, bd, idesc, first ? 0u : 1u);
+          else tc::mma_ss2(d, ad, bd, idesc, first ? 0u : 1u);
           first = false;
         }
       };
       auto kblock_ts = [&](uint32_t d, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool& first) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          tc::mma_ts(d, a_tmem + kk * 8, tc::make_sdesc_sw128(b_addr + kk * 32, 1024), idesc, first ? 0u : 1u);
+          const uint64_t bd = tc::make_sdesc_sw128(b_addr + kk * 32, 1024);
+          if constexpr (CG == 1) tc::mma_ts(d, a_tmem + kk * 8, bd, idesc, first ? 0u : 1u);
+          else tc::mma_ts2(d, a_tmem + kk * 8, bd, idesc, first ? 0u : 1u);
           first = false;
         }
       };
 
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        wait_bar(bars, B_XREADY, c_xready);
+      for (long long g = g0; g < n_groups; g += gstep) {
+        { PROF_T0(); wait_leader<CG>(bars, B_XREADY, c_xready); PROF_ADD(P_XREADY); }
         tc::tcgen05_fence_after();
         for (int h = 0; h < 2; ++h) {
           bool first1 = true;
+          // L0 chunk c may overwrite acc0 once chunk c-1 has been drained; "drained" and "H0 buffer written" are the
+          // same event (B_H0_READY), so the wait for chunk c-1 serves both L0(c) and the later L1(c-1)
           auto issue_l0 = [&](int c) {
-            (void)c;
-            wait_free(bars, B_ACC0_FREE, c_acc0free);
-            tc::tcgen05_fence_after();
+            if (c > 0) {
+              const int pb = (c - 1) & 1;
+              PROF_T0();
+              wait_leader<CG>(bars, B_H0_READY0 + pb, c_h0ready[pb]);
+              PROF_ADD(P_ACC0FREE);
+              tc::tcgen05_fence_after();
+            }
             bool first0 = true;
             for (int s = 0; s < 2; ++s) {
               const uint32_t w = next_stage();
               kblock_ss(tbase + kColAcc0, sX + (2 * s) * 16384, w, idesc128, first0);
-              kblock_ss(tbase + kColAcc0, sX + (2 * s + 1) * 16384, w + 16384, idesc128, first0);
+              kblock_ss(tbase + kColAcc0, sX + (2 * s + 1) * 16384, w + C::Sub, idesc128, first0);
               release_stage();
             }
-            tc::mma_commit(bars + B_ACC0_FULL);
+            commit<CG>(bars + B_ACC0_FULL);
           };
           auto issue_l1 = [&](int c) {
             const int b = c & 1;
             if (c == 0) {
               // the first layer-1 MMA of a half overwrites [0,256): it must have been drained -- by the previous tile's
               // layer-3 epilogue (h == 0) or by this tile's first-half epilogue (h == 1)
+              PROF_T0();
               if (h == 0) {
-                if (tile != (long long)blockIdx.x) { wait_bar(bars, B_TILE_DONE, c_tiledone); }
+                if (g != g0) { wait_leader<CG>(bars, B_TILE_DONE, c_tiledone); }
               } else {
-                wait_bar(bars, B_H1_READY, c_h1ready);
+                wait_leader<CG>(bars, B_H1_READY, c_h1ready);
               }
+              PROF_ADD(P_ACC1DRAINED);
             }
-            wait_bar(bars, B_H0_READY0 + b, c_h0ready[b]);
+            if (c == 7) {      // chunks 0..6 were already waited for by issue_l0(c + 1)
+              PROF_T0();
+              wait_leader<CG>(bars, B_H0_READY0 + b, c_h0ready[b]);
+              PROF_ADD(P_H0READY);
+            }
             tc::tcgen05_fence_after();
             for (int kb = 0; kb < 2; ++kb) {
               const uint32_t w = next_stage();
               kblock_ss(tbase + kColAcc1, sH0 + b * 32768 + kb * 16384, w, idesc256, first1);
               release_stage();
             }
-            tc::mma_commit(bars + B_H0_FREE0 + b);
+            commit<CG>(bars + B_H0_FREE0 + b);
           };
           issue_l0(0);
           for (int c = 0; c < 7; ++c) {
@@ -249,10 +346,10 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             kblock_ss(tbase + kColAcc1, sX + kb * 16384, w, idesc256, first1);
             release_stage();
           }
-          tc::mma_commit(bars + B_ACC1_FULL);
+          commit<CG>(bars + B_ACC1_FULL);
         }
         // ---- layer 2: A = H1 from TMEM (8 K-blocks) + X (4 K-blocks) -> acc2 [0,256)
-        wait_bar(bars, B_H1_READY, c_h1ready);
+        { PROF_T0(); wait_leader<CG>(bars, B_H1_READY, c_h1ready); PROF_ADD(P_H1READY); }
         tc::tcgen05_fence_after();
         {
           bool first = true;
@@ -267,28 +364,29 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             kblock_ss(tbase + kColAcc1, sX + kb * 16384, w, idesc256, first);
             release_stage();
           }
-          tc::mma_commit(bars + B_ACC2_FULL);
+          commit<CG>(bars + B_ACC2_FULL);
         }
         // ---- layer 3: A = H2 from TMEM (4 K-blocks) + X (4 K-blocks) -> acc3 [0,128)
-        wait_bar(bars, B_H2_READY, c_h2ready);
+        { PROF_T0(); wait_leader<CG>(bars, B_H2_READY, c_h2ready); PROF_ADD(P_H2READY); }
         tc::tcgen05_fence_after();
         {
           bool first = true;
           for (int s = 0; s < 2; ++s) {
             const uint32_t w = next_stage();
             kblock_ts(tbase + kColAcc1, tbase + kColH2 + (2 * s) * 32, w, idesc128, first);
-            kblock_ts(tbase + kColAcc1, tbase + kColH2 + (2 * s + 1) * 32, w + 16384, idesc128, first);
+            kblock_ts(tbase + kColAcc1, tbase + kColH2 + (2 * s + 1) * 32, w + C::Sub, idesc128, first);
             release_stage();
           }
           for (int s = 0; s < 2; ++s) {
             const uint32_t w = next_stage();
             kblock_ss(tbase + kColAcc1, sX + (2 * s) * 16384, w, idesc128, first);
-            kblock_ss(tbase + kColAcc1, sX + (2 * s + 1) * 16384, w + 16384, idesc128, first);
+            kblock_ss(tbase + kColAcc1, sX + (2 * s + 1) * 16384, w + C::Sub, idesc128, first);
             release_stage();
           }
-          tc::mma_commit(bars + B_ACC3_FULL);
+          commit<CG>(bars + B_ACC3_FULL);
         }
       }
+      if (prof) prof[P_TOTAL] = (unsigned long long)(clock64() - t_begin);
     }
   } else if (warp >= 4) {
     // ============================== workers: sampler + epilogue ==============================
@@ -299,14 +397,18 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     uint32_t c_acc0full = 0, c_h0free[2] = {0, 0}, c_acc1full = 0, c_acc2full = 0, c_acc3full = 0;
     const int res = prm.res;
+    if (!(warp == 4 && lane == 0)) prof = nullptr;      // one worker thread records
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (long long g = g0; g < n_groups; g += gstep) {
+      const long long tile = g * CG + rank;
       const long long p0 = tile * kTile;
       // ---- X is free once the previous tile's last MMAs (layer-3 skip) have completed
-      if (tile != (long long)blockIdx.x) {
+      if (g != g0) {
         if (wg == 1) { wait_bar(bars, B_ACC3_FULL, c_acc3full); }   // wg 0 already waited on it in its acc3 drain
       }
-      // ---- sampling: warp wk handles points wk*16 .. +15; lane covers 8 consecutive channels
+      const long long t_sample0 = prof ? clock64() : 0;
+      // ---- sampling: warp wk handles points wk*16 .. +15.  Lane q (< 16) projects point q and builds its bilinear
+      //      taps once; the taps are then broadcast and every lane gathers 8 consecutive channels (16 B) per tap.
       {
         const int cbase = lane * 8;
         float w4s[kMaxRes][8];
@@ -314,9 +416,11 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         for (int r = 0; r < kMaxRes; ++r)
 #pragma unroll
           for (int j = 0; j < 8; ++j) w4s[r][j] = (r < res) ? __ldg(prm.w4s + r * kC + cbase + j) : 0.f;
-        for (int q = 0; q < 16; ++q) {
-          const int p = wk * 16 + q;
-          const long long i = p0 + p;
+        int my_off[4];
+        float my_wgt[4];
+        float my_zf = 0.f;
+        {
+          const long long i = p0 + wk * 16 + (lane & 15);
           float u = 0.f, v = 0.f, w = 0.f;
           const bool valid = i < n;
           if (valid) {
@@ -326,50 +430,96 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           }
           const bool in_img = valid && (u >= -1.f) && (u <= 1.f) && (v >= -1.f) && (v <= 1.f);
           MpTaps t = mp_taps(valid ? u : 0.f, valid ? v : 0.f, prm.H, prm.W);
-          if (!valid || !(u == u) || !(v == v)) {
+          const bool dead = !valid || !(u == u) || !(v == v);
 #pragma unroll
-            for (int a = 0; a < 4; ++a) { t.off[a] = 0; t.wgt[a] = 0.f; }
+          for (int a = 0; a < 4; ++a) { my_off[a] = dead ? 0 : t.off[a]; my_wgt[a] = dead ? 0.f : t.wgt[a]; }
+          my_zf = w * cal.z_scale;
+          if (lane < 16) {
+            s_zf[wk * 16 + lane] = my_zf;
+            s_in[wk * 16 + lane] = in_img ? 1.f : 0.f;
           }
-          float acc[8];
+        }
+        float s4part[kMaxRes][16];               // this lane's partial last-layer skip dot for the 16 points
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-          uint4 raw[4];
+        for (int q0 = 0; q0 < 16; q0 += 4) {
+          uint4 raw[4][4];
+          float wgt[4][4];
 #pragma unroll
-          for (int a = 0; a < 4; ++a)
-            raw[a] = __ldg(reinterpret_cast<const uint4*>(prm.feat + (size_t)t.off[a] * kC + cbase));
+          for (int qq = 0; qq < 4; ++qq)
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const __half2* h2 = reinterpret_cast<const __half2*>(&raw[a]);
+            for (int a = 0; a < 4; ++a) {
+              const int off = __shfl_sync(0xffffffffu, my_off[a], q0 + qq);
+              wgt[qq][a] = __shfl_sync(0xffffffffu, my_wgt[a], q0 + qq);
+              raw[qq][a] = __ldg(reinterpret_cast<const uint4*>(prm.feat + (size_t)off * kC + cbase));
+            }
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const int p = wk * 16 + q0 + qq;
+            float acc[8];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const __half2* h2 = reinterpret_cast<const __half2*>(&raw[qq][a]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h2[j]);
+                acc[2 * j] = (a == 0) ? f.x * wgt[qq][a] : acc[2 * j] + f.x * wgt[qq][a];
+                acc[2 * j + 1] = (a == 0) ? f.y * wgt[qq][a] : acc[2 * j + 1] + f.y * wgt[qq][a];
+              }
+            }
+            uint4 packed;
+            packed.x = tc::pack_half2(acc[0], acc[1]);
+            packed.y = tc::pack_half2(acc[2], acc[3]);
+            packed.z = tc::pack_half2(acc[4], acc[5]);
+            packed.w = tc::pack_half2(acc[6], acc[7]);
+            const int kb = lane >> 3;
+            *reinterpret_cast<uint4*>(smem + Smem::X + kb * 16384 + tc::sw128_offset(p, (lane & 7) * 8)) = packed;
+#pragma unroll
+            for (int r = 0; r < kMaxRes; ++r) {
+              float sacc = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) sacc = fmaf(w4s[r][j], acc[j], sacc);
+              s4part[r][q0 + qq] = sacc;
+            }
+          }
+        }
+        // fp32 skip part of the last layer: sum_c w4[128 + c] * x_c.  Transposing warp reduction of the 16 partials:
+        // after step k every lane holds half as many sums; 16+8+4+2 = 30 shuffles instead of 16*5.
+#pragma unroll
+        for (int r = 0; r < kMaxRes; ++r) {
+          if (r < res) {
+            float v16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v16[j] = s4part[r][j];
+            // fold over lane bit 4 first (plain butterfly), then distribute points over lane bits 3..0
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v16[j] += __shfl_xor_sync(0xffffffffu, v16[j], 16);
+            float v8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const bool up = lane & 8;
+              const float keep = up ? v16[j + 8] : v16[j], send = up ? v16[j] : v16[j + 8];
+              v8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            float v4[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float2 f = __half22float2(h2[j]);
-              acc[2 * j] = (a == 0) ? f.x * t.wgt[a] : acc[2 * j] + f.x * t.wgt[a];
-              acc[2 * j + 1] = (a == 0) ? f.y * t.wgt[a] : acc[2 * j + 1] + f.y * t.wgt[a];
+              const bool up = lane & 4;
+              const float keep = up ? v8[j + 4] : v8[j], send = up ? v8[j] : v8[j + 4];
+              v4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
             }
-          }
-          uint4 packed;
-          packed.x = tc::pack_half2(acc[0], acc[1]);
-          packed.y = tc::pack_half2(acc[2], acc[3]);
-          packed.z = tc::pack_half2(acc[4], acc[5]);
-          packed.w = tc::pack_half2(acc[6], acc[7]);
-          const int kb = lane >> 3;
-          *reinterpret_cast<uint4*>(smem + Smem::X + kb * 16384 + tc::sw128_offset(p, (lane & 7) * 8)) = packed;
-          // fp32 skip part of the last layer: sum_c w4[128 + c] * x_c  (warp-shuffle reduction)
-          const float zf = w * cal.z_scale;
+            float v2[2];
 #pragma unroll
-          for (int r = 0; r < kMaxRes; ++r) {
-            if (r < res) {
-              float s = 0.f;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) s = fmaf(w4s[r][j], acc[j], s);
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-              if (lane == 0) s_s4[r * kTile + p] = s + __ldg(prm.w4z + r) * zf + __ldg(prm.b4 + r);
+            for (int j = 0; j < 2; ++j) {
+              const bool up = lane & 2;
+              const float keep = up ? v4[j + 2] : v4[j], send = up ? v4[j] : v4[j + 2];
+              v2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
             }
-          }
-          if (lane == 0) {
-            s_zf[p] = zf;
-            s_in[p] = in_img ? 1.f : 0.f;
+            const bool up = lane & 1;
+            const float keep = up ? v2[1] : v2[0], send = up ? v2[0] : v2[1];
+            const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            // lane L (< 16) now holds the total of point index ((L&8) | (L&4) | (L&2) | (L&1)) = L
+            const float zq = __shfl_sync(0xffffffffu, my_zf, lane & 15);
+            if (lane < 16) s_s4[r * kTile + wk * 16 + lane] = tot + __ldg(prm.w4z + r) * zq + __ldg(prm.b4 + r);
           }
         }
       }
@@ -382,106 +532,119 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
 #pragma unroll
       for (int r = 0; r < kMaxRes; ++r) s4[r] = (r < res) ? s_s4[r * kTile + row] : 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");      // everyone has read the per-point scalars
-      tc::mbar_arrive(bars + B_XREADY);
+      warp_arrive_leader<CG>(bars + B_XREADY, lane);
+      if (prof) prof[P_W_SAMPLE] += (unsigned long long)(clock64() - t_sample0);
 
       // ---- epilogue helper: acc columns [col0, col0+32) of this thread's row -> activated fp32 values
-      auto load_act = [&](uint32_t col, const float* __restrict__ bias, const float* __restrict__ wz, int ch0, float (&o)[32]) {
+      // pre-activation = accumulator + bias[ch] + wz[ch] * z_feat (fp32); `ch0` is warp-uniform -> constant-bank operands
+      auto load_pre = [&](uint32_t col, int ch0, float (&o)[32]) {
         uint32_t v[32];
         tc::tmem_ld32(tbase + lane_base + col, v);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(bias + ch0) + j4);
-          const float4 z = __ldg(reinterpret_cast<const float4*>(wz + ch0) + j4);
-          o[4 * j4 + 0] = mp_lrelu(__uint_as_float(v[4 * j4 + 0]) + fmaf(z.x, zf, b.x));
-          o[4 * j4 + 1] = mp_lrelu(__uint_as_float(v[4 * j4 + 1]) + fmaf(z.y, zf, b.y));
-          o[4 * j4 + 2] = mp_lrelu(__uint_as_float(v[4 * j4 + 2]) + fmaf(z.z, zf, b.z));
-          o[4 * j4 + 3] = mp_lrelu(__uint_as_float(v[4 * j4 + 3]) + fmaf(z.w, zf, b.w));
-        }
+        for (int j = 0; j < 32; ++j)
+          o[j] = __uint_as_float(v[j]) + fmaf(prm.wz_all[ch0 + j], zf, prm.bias_all[ch0 + j]);
+      };
+      auto load_act = [&](uint32_t col, int ch0, float (&o)[32]) {
+        load_pre(col, ch0, o);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], o[j] * MP_LEAKY_SLOPE);      // leaky-relu, slope in (0,1)
+      };
+      // fp16 pair with leaky-relu applied on the packed value (max(h, 0.01 h) in half2: 2 instructions per pair)
+      auto act_pack = [&](float a, float b) -> uint32_t {
+        const __half2 h = __floats2half2_rn(a, b);
+        const __half2 r = __hmax2(h, __hmul2(h, __float2half2_rn(MP_LEAKY_SLOPE)));
+        return *reinterpret_cast<const uint32_t*>(&r);
       };
 
       for (int h = 0; h < 2; ++h) {
         // ---- layer-0 chunks -> H0 buffers (smem, A operand of layer 1)
         for (int c = 0; c < 8; ++c) {
           const int b = c & 1;
-          wait_bar(bars, B_ACC0_FULL, c_acc0full);
-          wait_free(bars, B_H0_FREE0 + b, c_h0free[b]);
+          { PROF_T0(); wait_bar(bars, B_ACC0_FULL, c_acc0full); PROF_ADD(P_W_ACC0FULL); }
+          { PROF_T0(); wait_free(bars, B_H0_FREE0 + b, c_h0free[b]); PROF_ADD(P_W_H0FREE); }
           tc::tcgen05_fence_after();
+          PROF_T0();
           // this warpgroup drains columns [wg*64, wg*64+64) == K-block `wg` of the chunk
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
+          for (int gq = 0; gq < 2; ++gq) {
             float o[32];
-            const int ch0 = c * 128 + wg * 64 + g * 32;
-            load_act(kColAcc0 + wg * 64 + g * 32, prm.bias[0], prm.wz[0], ch0, o);
+            const int ch0 = c * 128 + wg * 64 + gq * 32;
+            load_pre(kColAcc0 + wg * 64 + gq * 32, side_off(0) + ch0, o);
             uint8_t* dstp = smem + Smem::H0 + b * 32768 + wg * 16384;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 pk;
-              pk.x = tc::pack_half2(o[8 * q + 0], o[8 * q + 1]);
-              pk.y = tc::pack_half2(o[8 * q + 2], o[8 * q + 3]);
-              pk.z = tc::pack_half2(o[8 * q + 4], o[8 * q + 5]);
-              pk.w = tc::pack_half2(o[8 * q + 6], o[8 * q + 7]);
-              *reinterpret_cast<uint4*>(dstp + tc::sw128_offset(row, g * 32 + q * 8)) = pk;
+              pk.x = act_pack(o[8 * q + 0], o[8 * q + 1]);
+              pk.y = act_pack(o[8 * q + 2], o[8 * q + 3]);
+              pk.z = act_pack(o[8 * q + 4], o[8 * q + 5]);
+              pk.w = act_pack(o[8 * q + 6], o[8 * q + 7]);
+              *reinterpret_cast<uint4*>(dstp + tc::sw128_offset(row, gq * 32 + q * 8)) = pk;
             }
           }
           tc::fence_proxy_async_smem();
           tc::tcgen05_fence_before();
-          tc::mbar_arrive(bars + B_H0_READY0 + b);
-          tc::mbar_arrive(bars + B_ACC0_FREE);
+          warp_arrive_leader<CG>(bars + B_H0_READY0 + b, lane);      // also means "acc0 drained"
+          PROF_ADD(P_W_DRAIN0);
         }
         // ---- layer-1 half -> H1 (packed fp16 in TMEM, A operand of layer 2)
-        wait_bar(bars, B_ACC1_FULL, c_acc1full);
+        { PROF_T0(); wait_bar(bars, B_ACC1_FULL, c_acc1full); PROF_ADD(P_W_ACC1FULL); }
         tc::tcgen05_fence_after();
         {
+          PROF_T0();
           const uint32_t hcol = (h == 0) ? kColH1lo : kColH1hi;
 #pragma unroll 1
-          for (int g = 0; g < 4; ++g) {
+          for (int gq = 0; gq < 4; ++gq) {
             float o[32];
-            const int lc = wg * 128 + g * 32;                    // column inside the 256-wide half
-            load_act(kColAcc1 + lc, prm.bias[1], prm.wz[1], h * 256 + lc, o);
+            const int lc = wg * 128 + gq * 32;                    // column inside the 256-wide half
+            load_pre(kColAcc1 + lc, side_off(1) + h * 256 + lc, o);
             uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = tc::pack_half2(o[2 * j], o[2 * j + 1]);
+            for (int j = 0; j < 16; ++j) pk[j] = act_pack(o[2 * j], o[2 * j + 1]);
             tc::tmem_st16(tbase + lane_base + hcol + lc / 2, pk);
           }
           tc::tmem_st_wait();
           tc::tcgen05_fence_before();
-          tc::mbar_arrive(bars + B_H1_READY);
+          warp_arrive_leader<CG>(bars + B_H1_READY, lane);
+          PROF_ADD(P_W_DRAIN1);
         }
       }
       // ---- layer 2 -> H2 (packed fp16 in TMEM)
-      wait_bar(bars, B_ACC2_FULL, c_acc2full);
+      { PROF_T0(); wait_bar(bars, B_ACC2_FULL, c_acc2full); PROF_ADD(P_W_ACC2FULL); }
       tc::tcgen05_fence_after();
       {
+        PROF_T0();
 #pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
+        for (int gq = 0; gq < 4; ++gq) {
           float o[32];
-          const int lc = wg * 128 + g * 32;
-          load_act(kColAcc1 + lc, prm.bias[2], prm.wz[2], lc, o);
+          const int lc = wg * 128 + gq * 32;
+          load_pre(kColAcc1 + lc, side_off(2) + lc, o);
           uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = tc::pack_half2(o[2 * j], o[2 * j + 1]);
+          for (int j = 0; j < 16; ++j) pk[j] = act_pack(o[2 * j], o[2 * j + 1]);
           tc::tmem_st16(tbase + lane_base + kColH2 + lc / 2, pk);
         }
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
-        tc::mbar_arrive(bars + B_H2_READY);
+        warp_arrive_leader<CG>(bars + B_H2_READY, lane);
+        PROF_ADD(P_W_DRAIN2);
       }
       // ---- layer 3 (fp32 accumulators) + layer 4 in fp32 on CUDA cores, warpgroup 0 only
       if (wg == 0) {
-        wait_bar(bars, B_ACC3_FULL, c_acc3full);
+        { PROF_T0(); wait_bar(bars, B_ACC3_FULL, c_acc3full); PROF_ADD(P_W_ACC3FULL); }
         tc::tcgen05_fence_after();
+        PROF_T0();
         float logit[kMaxRes];
 #pragma unroll
         for (int r = 0; r < kMaxRes; ++r) logit[r] = s4[r];
 #pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
+        for (int gq = 0; gq < 4; ++gq) {
           float o[32];
-          load_act(kColAcc1 + g * 32, prm.bias[3], prm.wz[3], g * 32, o);
+          load_act(kColAcc1 + gq * 32, side_off(3) + gq * 32, o);
 #pragma unroll
           for (int r = 0; r < kMaxRes; ++r) {
             if (r < res) {
-              const float4* wv = reinterpret_cast<const float4*>(prm.w4h + r * kL3 + g * 32);
+              const float4* wv = reinterpret_cast<const float4*>(prm.w4h + r * kL3 + gq * 32);
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const float4 w4 = __ldg(wv + j4);
@@ -494,7 +657,8 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           }
         }
         tc::tcgen05_fence_before();
-        tc::mbar_arrive(bars + B_TILE_DONE);
+        warp_arrive_leader<CG>(bars + B_TILE_DONE, lane);
+        PROF_ADD(P_W_DRAIN3);
         const long long i = p0 + row;
         if (i < n) {
 #pragma unroll
@@ -509,10 +673,16 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       }
     }
   }
-  // ---- teardown
+  // ---- teardown (reconverge the single-lane roles first: the barriers below are .aligned)
+  __syncwarp();
   tc::tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 2) tc::tmem_dealloc(tbase, 512);
+  if constexpr (CG == 1) {
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tbase, 512);
+  } else {
+    tc::cluster_sync_all();
+    if (warp == 2) tc::tmem_dealloc2(tbase, 512);
+  }
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -555,40 +725,48 @@ int mp_tc_prepare(mp_mlp* mlp) {
     MP_CUDA(cudaMemcpy(W[l].data(), mlp->w[l], W[l].size() * sizeof(float), cudaMemcpyDeviceToHost));
     MP_CUDA(cudaMemcpy(Bv[l].data(), mlp->bias[l], Bv[l].size() * sizeof(float), cudaMemcpyDeviceToHost));
   }
-  std::vector<uint8_t> stream((size_t)kStagesPerTile * kStageBytes, 0);
-  size_t st = 0;
-  auto stage_ptr = [&]() { return stream.data() + (st++) * kStageBytes; };
-  const int cin0 = mlp->cin[0], cin1 = mlp->cin[1], cin2 = mlp->cin[2], cin3 = mlp->cin[3];
-  for (int h = 0; h < 2; ++h) {
-    auto l0 = [&](int c) {
-      for (int s = 0; s < 2; ++s) {
-        uint8_t* p = stage_ptr();
-        pack_tile(p, W[0].data(), cin0, c * 128, 128, (2 * s) * 64);
-        pack_tile(p + 16384, W[0].data(), cin0, c * 128, 128, (2 * s + 1) * 64);
-      }
-    };
-    auto l1 = [&](int c) {
-      for (int kb = 0; kb < 2; ++kb) pack_tile(stage_ptr(), W[1].data(), cin1, h * 256, 256, c * 128 + kb * 64);
-    };
-    l0(0);
-    for (int c = 0; c < 7; ++c) { l0(c + 1); l1(c); }
-    l1(7);
-    for (int kb = 0; kb < 4; ++kb) pack_tile(stage_ptr(), W[1].data(), cin1, h * 256, 256, kL0 + kb * 64);
-  }
-  for (int kb = 0; kb < 8; ++kb) pack_tile(stage_ptr(), W[2].data(), cin2, 0, 256, kb * 64);
-  for (int kb = 0; kb < 4; ++kb) pack_tile(stage_ptr(), W[2].data(), cin2, 0, 256, kL1 + kb * 64);
-  for (int s = 0; s < 2; ++s) {
-    uint8_t* p = stage_ptr();
-    pack_tile(p, W[3].data(), cin3, 0, 128, (2 * s) * 64);
-    pack_tile(p + 16384, W[3].data(), cin3, 0, 128, (2 * s + 1) * 64);
-  }
-  for (int s = 0; s < 2; ++s) {
-    uint8_t* p = stage_ptr();
-    pack_tile(p, W[3].data(), cin3, 0, 128, kL2 + (2 * s) * 64);
-    pack_tile(p + 16384, W[3].data(), cin3, 0, 128, kL2 + (2 * s + 1) * 64);
-  }
-  if ((int)st != kStagesPerTile) {
-    mp_set_error("internal: weight stream has %d stages, expected %d", (int)st, kStagesPerTile);
+  // one weight stream per (variant, cluster rank): CG=1 -> 32 KB stages with full tiles; CG=2 -> 16 KB stages holding
+  // this rank's half of the rows of every tile (tcgen05.mma.cta_group::2 reads B rows [r*N/2, (r+1)*N/2) from CTA r)
+  auto build_stream = [&](int cg, int r, std::vector<uint8_t>& stream) -> bool {
+    const int stage_bytes = 32768 / cg, sub = stage_bytes / 2;
+    stream.assign((size_t)kStagesPerTile * stage_bytes, 0);
+    size_t st = 0;
+    auto stage_ptr = [&]() { return stream.data() + (st++) * stage_bytes; };
+    const int n128 = 128 / cg, n256 = 256 / cg;            // rows of a 128- / 256-row tile held by this rank
+    const int cin0 = mlp->cin[0], cin1 = mlp->cin[1], cin2 = mlp->cin[2], cin3 = mlp->cin[3];
+    for (int h = 0; h < 2; ++h) {
+      auto l0 = [&](int c) {
+        for (int s2 = 0; s2 < 2; ++s2) {
+          uint8_t* p = stage_ptr();
+          pack_tile(p, W[0].data(), cin0, c * 128 + r * n128, n128, (2 * s2) * 64);
+          pack_tile(p + sub, W[0].data(), cin0, c * 128 + r * n128, n128, (2 * s2 + 1) * 64);
+        }
+      };
+      auto l1 = [&](int c) {
+        for (int kb = 0; kb < 2; ++kb) pack_tile(stage_ptr(), W[1].data(), cin1, h * 256 + r * n256, n256, c * 128 + kb * 64);
+      };
+      l0(0);
+      for (int c = 0; c < 7; ++c) { l0(c + 1); l1(c); }
+      l1(7);
+      for (int kb = 0; kb < 4; ++kb) pack_tile(stage_ptr(), W[1].data(), cin1, h * 256 + r * n256, n256, kL0 + kb * 64);
+    }
+    for (int kb = 0; kb < 8; ++kb) pack_tile(stage_ptr(), W[2].data(), cin2, r * n256, n256, kb * 64);
+    for (int kb = 0; kb < 4; ++kb) pack_tile(stage_ptr(), W[2].data(), cin2, r * n256, n256, kL1 + kb * 64);
+    for (int s2 = 0; s2 < 2; ++s2) {
+      uint8_t* p = stage_ptr();
+      pack_tile(p, W[3].data(), cin3, r * n128, n128, (2 * s2) * 64);
+      pack_tile(p + sub, W[3].data(), cin3, r * n128, n128, (2 * s2 + 1) * 64);
+    }
+    for (int s2 = 0; s2 < 2; ++s2) {
+      uint8_t* p = stage_ptr();
+      pack_tile(p, W[3].data(), cin3, r * n128, n128, kL2 + (2 * s2) * 64);
+      pack_tile(p + sub, W[3].data(), cin3, r * n128, n128, kL2 + (2 * s2 + 1) * 64);
+    }
+    return (int)st == kStagesPerTile;
+  };
+  std::vector<uint8_t> stream, stream2[2];
+  if (!build_stream(1, 0, stream) || !build_stream(2, 0, stream2[0]) || !build_stream(2, 1, stream2[1])) {
+    mp_set_error("internal: weight stream stage count mismatch");
     return MP_E_INVALID;
   }
 
@@ -601,13 +779,14 @@ int mp_tc_prepare(mp_mlp* mlp) {
     return cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
   };
   cudaError_t e = upload(stream.data(), stream.size(), (void**)&pk->wstream);
+  for (int r = 0; r < 2 && e == cudaSuccess; ++r) e = upload(stream2[r].data(), stream2[r].size(), (void**)&pk->wstream2[r]);
   const int hid[4] = {0, kL0, kL1, kL2};
   for (int l = 0; l < 4 && e == cudaSuccess; ++l) {
     std::vector<float> wz(mlp->cout[l]);
     const int zcol = hid[l] + kC;
     for (int co = 0; co < mlp->cout[l]; ++co) wz[co] = W[l][(size_t)co * mlp->cin[l] + zcol];
-    e = upload(Bv[l].data(), Bv[l].size() * sizeof(float), (void**)&pk->bias[l]);
-    if (e == cudaSuccess) e = upload(wz.data(), wz.size() * sizeof(float), (void**)&pk->wz[l]);
+    memcpy(pk->h_bias + side_off(l), Bv[l].data(), Bv[l].size() * sizeof(float));
+    memcpy(pk->h_wz + side_off(l), wz.data(), wz.size() * sizeof(float));
   }
   if (e == cudaSuccess) {
     const int R = pk->res, cin4 = mlp->cin[4];
@@ -628,7 +807,8 @@ int mp_tc_prepare(mp_mlp* mlp) {
     mp_tc_release(mlp);
     return MP_E_CUDA;
   }
-  e = cudaFuncSetAttribute(query_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+  e = cudaFuncSetAttribute(query_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e != cudaSuccess) {
     mp_set_error("mp_tc_prepare: cannot opt in to %d bytes of shared memory: %s", Smem::Total + 1024, cudaGetErrorString(e));
     mp_tc_release(mlp);
@@ -642,6 +822,7 @@ void mp_tc_release(mp_mlp* mlp) {
   TcPack* pk = static_cast<TcPack*>(mlp->tc);
   if (!pk) return;
   if (pk->wstream) cudaFree(pk->wstream);
+  for (int r = 0; r < 2; ++r) if (pk->wstream2[r]) cudaFree(pk->wstream2[r]);
   for (int l = 0; l < 4; ++l) {
     if (pk->bias[l]) cudaFree(pk->bias[l]);
     if (pk->wz[l]) cudaFree(pk->wz[l]);
@@ -670,7 +851,10 @@ int mp_launch_query_tc(const mp_mlp* mlp, const mp_feat* feat, const MpPointSrc&
   TcParams prm;
   memset(&prm, 0, sizeof(prm));
   prm.wstream = pk->wstream;
-  for (int l = 0; l < 4; ++l) { prm.bias[l] = pk->bias[l]; prm.wz[l] = pk->wz[l]; }
+  prm.wstream2[0] = pk->wstream2[0];
+  prm.wstream2[1] = pk->wstream2[1];
+  memcpy(prm.bias_all, pk->h_bias, sizeof(prm.bias_all));
+  memcpy(prm.wz_all, pk->h_wz, sizeof(prm.wz_all));
   prm.w4h = pk->w4h; prm.w4s = pk->w4s; prm.w4z = pk->w4z; prm.b4 = pk->b4;
   prm.res = pk->res;
   prm.last_op = mlp->last_op;
@@ -680,8 +864,56 @@ int mp_launch_query_tc(const mp_mlp* mlp, const mp_feat* feat, const MpPointSrc&
   MP_CUDA(cudaGetDevice(&dev));
   MP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long tiles = (src.n + kTile - 1) / kTile;
-  const int grid = (int)(tiles < (long long)sms ? tiles : sms);
-  query_tc_kernel<<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
-  MP_CUDA(cudaGetLastError());
+  static const int do_prof = [] { const char* v = getenv("MONOPORT_B200_TC_PROF"); return v ? atoi(v) : 0; }();
+  unsigned long long* d_prof = nullptr;
+  if (do_prof && tiles >= 2 * sms) {
+    MP_CUDA(cudaMalloc(&d_prof, (size_t)sms * 32 * sizeof(unsigned long long)));
+    MP_CUDA(cudaMemset(d_prof, 0, (size_t)sms * 32 * sizeof(unsigned long long)));
+    prm.prof = d_prof;
+  }
+  auto report = [&](int grid) {
+    if (!d_prof) return;
+    cudaStreamSynchronize(st);
+    std::vector<unsigned long long> h((size_t)sms * 32);
+    cudaMemcpy(h.data(), d_prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_prof);
+    static const char* names[32] = {"total", "xready", "acc0free", "wfull", "wpeer", "h0ready", "acc1drained", "h1ready", "h2ready",
+                                    0, 0, 0, 0, 0, 0, 0, "w_sample", "w_acc0full", "w_h0free", "w_acc1full", "w_acc2full", "w_acc3full",
+                                    "w_drain0", "w_drain1", "w_drain2", "w_drain3", 0, 0, 0, 0, 0, 0};
+    const long long tiles_per_cta = (tiles + grid - 1) / grid;
+    fprintf(stderr, "[tc prof] grid=%d tiles/cta~%lld  (cycles per tile, CTA 0 | CTA 1)\n", grid, tiles_per_cta);
+    for (int k = 0; k < 32; ++k)
+      if (names[k]) fprintf(stderr, "[tc prof] %-12s %10.0f | %10.0f\n", names[k], (double)h[k] / tiles_per_cta, (double)h[32 + k] / tiles_per_cta);
+  };
+  // variant: the single-CTA kernel (cta_group::1) is the default -- measured faster (50.7 vs 61.6 ms at 257^3): the
+  // layer-0 chunk hand-off is on the critical path and every cross-CTA arrival adds latency to it.
+  // MONOPORT_B200_TC_CG=2 selects the 2-CTA cluster kernel (halves per-SM weight ingest; kept for round 2).
+  static const int forced = [] { const char* v = getenv("MONOPORT_B200_TC_CG"); return v ? atoi(v) : 0; }();
+  const int cg = forced == 2 ? 2 : 1;
+  if (cg == 1) {
+    const int grid = (int)(tiles < (long long)sms ? tiles : sms);
+    query_tc_kernel<1><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
+    MP_CUDA(cudaGetLastError());
+    report(grid);
+    return MP_OK;
+  }
+  const long long groups = (tiles + 1) / 2;
+  const long long max_clusters = sms / 2;
+  const int clusters = (int)(groups < max_clusters ? groups : max_clusters);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Smem::Total + 1024;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc_kernel<2>, prm, src, cal, dst));
+  report(2 * clusters);
   return MP_OK;
 }
