@@ -18,7 +18,9 @@
 //      halves of 256 outputs and layer 0 is recomputed for the second half (+22% MMA work, documented in DESIGN.md);
 //   H1, H2 are written back to TMEM as packed fp16 and consumed by the next layer as the A operand straight from
 //      TMEM (tcgen05.mma with A in tensor memory), so they never touch shared memory.
-// TMEM map: [0,256) acc1-half / acc2 / acc3 | [256,384) acc0, later H1 (ch 256..511) | [384,512) H1 (ch 0..255), later H2
+// TMEM map: [0,256)   acc1-half, later acc2
+//           [256,384) acc0 buffer 0, later H1 (ch 256..511), later acc3
+//           [384,512) acc0 buffer 1 during the FIRST half only (double-buffered layer-0 chunks), then H1 (ch 0..255), later H2
 //
 // Two variants of the same kernel (template parameter CG):
 //   CG = 1  one CTA per tile, tcgen05.mma.cta_group::1 (M = 128), weight ring 3 x 32 KB;
@@ -57,7 +59,7 @@ constexpr int kStagesPerHalf = 16 + 16 + 4;                       // L0 (8 chunk
 constexpr int kStagesPerTile = 2 * kStagesPerHalf + 12 + 4;       // + L2 (8 hidden + 4 skip) + L3 (2 hidden + 2 skip)
 
 // TMEM columns
-constexpr uint32_t kColAcc1 = 0, kColAcc0 = 256, kColH1lo = 384, kColH1hi = 256, kColH2 = 384;
+constexpr uint32_t kColAcc1 = 0, kColAcc0 = 256, kColH1lo = 384, kColH1hi = 256, kColH2 = 384, kColAcc3 = 256;
 
 constexpr int kSideFloats = kL0 + kL1 + kL2 + kL3;      // 1920 hidden output channels over layers 0..3
 __host__ __device__ constexpr int side_off(int l) { return l == 0 ? 0 : l == 1 ? kL0 : l == 2 ? kL0 + kL1 : kL0 + kL1 + kL2; }
@@ -106,13 +108,13 @@ struct Smem {
   static constexpr int Wr = H0 + 65536;                         // kStages x 32 KB
   static constexpr int Small = Wr + kRingBytes;                 // zf[128], inimg[128], s4[kMaxRes][128]
   static constexpr int Bars = Small + (2 + kMaxRes) * kTile * 4;
-  static constexpr int NumBars = 3 * kStages + 13;
+  static constexpr int NumBars = 3 * kStages + 14;
   static constexpr int TmemPtr = Bars + NumBars * 8;
   static constexpr int Total = TmemPtr + 16;
 };
-enum Bar { B_WFULL = 0, B_WEMPTY = kStages, B_WPEER = 2 * kStages, B_XREADY = 3 * kStages, B_ACC0_FULL, B_ACC0_FREE, B_H0_READY0, B_H0_READY1,
-           B_H0_FREE0, B_H0_FREE1, B_ACC1_FULL, B_H1_READY, B_ACC2_FULL, B_H2_READY, B_ACC3_FULL, B_TILE_DONE };
-static_assert(B_TILE_DONE + 1 == Smem::NumBars, "barrier count");
+enum Bar { B_WFULL = 0, B_WEMPTY = kStages, B_WPEER = 2 * kStages, B_XREADY = 3 * kStages, B_ACC0_FULL0, B_ACC0_FULL1, B_H0_READY0, B_H0_READY1,
+           B_H0_FREE0, B_H0_FREE1, B_ACC1_FULL, B_H1_READY, B_ACC2_FULL, B_H2_READY, B_ACC3_FULL, B_TILE_DONE, B_XFREE };
+static_assert(B_XFREE + 1 == Smem::NumBars, "barrier count");
 static_assert(Smem::Total + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
 
 struct PhaseCounter {   // number of completed waits on a barrier -> parity to wait for next
@@ -190,8 +192,9 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     }
     constexpr int kW = 8 * CG;                        // one arrival per worker warp of every CTA in the cluster
     tc::mbar_init(bars + B_XREADY, kW);
-    tc::mbar_init(bars + B_ACC0_FULL, 1);
-    tc::mbar_init(bars + B_ACC0_FREE, kW);   // (unused: acc0-free is implied by B_H0_READY)
+    tc::mbar_init(bars + B_ACC0_FULL0, 1);
+    tc::mbar_init(bars + B_ACC0_FULL1, 1);
+    tc::mbar_init(bars + B_XFREE, 1);
     tc::mbar_init(bars + B_H0_READY0, kW);
     tc::mbar_init(bars + B_H0_READY1, kW);
     tc::mbar_init(bars + B_H0_FREE0, 1);
@@ -288,46 +291,48 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       for (long long g = g0; g < n_groups; g += gstep) {
         { PROF_T0(); wait_leader<CG>(bars, B_XREADY, c_xready); PROF_ADD(P_XREADY); }
         tc::tcgen05_fence_after();
+        // acc0 buffer 0 = [256,384) held acc3 of the previous tile: wait until its fp32 tail has drained it
+        if (g != g0) {
+          PROF_T0();
+          wait_leader<CG>(bars, B_TILE_DONE, c_tiledone);
+          PROF_ADD(P_ACC1DRAINED);
+          tc::tcgen05_fence_after();
+        }
         for (int h = 0; h < 2; ++h) {
           bool first1 = true;
-          // L0 chunk c may overwrite acc0 once chunk c-1 has been drained; "drained" and "H0 buffer written" are the
-          // same event (B_H0_READY), so the wait for chunk c-1 serves both L0(c) and the later L1(c-1)
+          // Layer-0 chunk c goes to acc0 buffer (h == 0 ? c & 1 : 0).  In the first half [384,512) is still free, so the
+          // chunks are double-buffered and the tensor pipe never waits for a drain; in the second half that region holds
+          // H1 and chunk c+1 has to wait until chunk c has been drained ("drained" and "H0 smem buffer written" are the
+          // same event, B_H0_READY).  Buffer 1 held H2 of the previous tile: its last readers (layer-3 hidden MMAs) were
+          // issued earlier by this thread and MMAs execute in order, so overwriting it is safe.
           auto issue_l0 = [&](int c) {
-            if (c > 0) {
-              const int pb = (c - 1) & 1;
-              PROF_T0();
-              wait_leader<CG>(bars, B_H0_READY0 + pb, c_h0ready[pb]);
-              PROF_ADD(P_ACC0FREE);
-              tc::tcgen05_fence_after();
-            }
+            const int ab = (h == 0) ? (c & 1) : 0;
             bool first0 = true;
             for (int s = 0; s < 2; ++s) {
               const uint32_t w = next_stage();
-              kblock_ss(tbase + kColAcc0, sX + (2 * s) * 16384, w, idesc128, first0);
-              kblock_ss(tbase + kColAcc0, sX + (2 * s + 1) * 16384, w + C::Sub, idesc128, first0);
+              kblock_ss(tbase + kColAcc0 + ab * 128, sX + (2 * s) * 16384, w, idesc128, first0);
+              kblock_ss(tbase + kColAcc0 + ab * 128, sX + (2 * s + 1) * 16384, w + C::Sub, idesc128, first0);
               release_stage();
             }
-            commit<CG>(bars + B_ACC0_FULL);
+            commit<CG>(bars + B_ACC0_FULL0 + ab);
+          };
+          auto wait_chunk = [&](int c, int slot) {      // chunk c drained + its H0 smem buffer written
+            const int b = c & 1;
+            PROF_T0();
+            wait_leader<CG>(bars, B_H0_READY0 + b, c_h0ready[b]);
+            if (prof) prof[slot] += (unsigned long long)(clock64() - _t0);
+            tc::tcgen05_fence_after();
           };
           auto issue_l1 = [&](int c) {
             const int b = c & 1;
-            if (c == 0) {
-              // the first layer-1 MMA of a half overwrites [0,256): it must have been drained -- by the previous tile's
-              // layer-3 epilogue (h == 0) or by this tile's first-half epilogue (h == 1)
+            if (c == 0 && h == 1) {
+              // the first layer-1 MMA of the second half overwrites [0,256): the first half must have been drained.
+              // (For h == 0 the region held acc2 of the previous tile, drained before its B_H2_READY, already waited.)
               PROF_T0();
-              if (h == 0) {
-                if (g != g0) { wait_leader<CG>(bars, B_TILE_DONE, c_tiledone); }
-              } else {
-                wait_leader<CG>(bars, B_H1_READY, c_h1ready);
-              }
+              wait_leader<CG>(bars, B_H1_READY, c_h1ready);
               PROF_ADD(P_ACC1DRAINED);
+              tc::tcgen05_fence_after();
             }
-            if (c == 7) {      // chunks 0..6 were already waited for by issue_l0(c + 1)
-              PROF_T0();
-              wait_leader<CG>(bars, B_H0_READY0 + b, c_h0ready[b]);
-              PROF_ADD(P_H0READY);
-            }
-            tc::tcgen05_fence_after();
             for (int kb = 0; kb < 2; ++kb) {
               const uint32_t w = next_stage();
               kblock_ss(tbase + kColAcc1, sH0 + b * 32768 + kb * 16384, w, idesc256, first1);
@@ -335,12 +340,24 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             }
             commit<CG>(bars + B_H0_FREE0 + b);
           };
-          issue_l0(0);
-          for (int c = 0; c < 7; ++c) {
-            issue_l0(c + 1);
-            issue_l1(c);
+          if (h == 0) {
+            issue_l0(0);
+            issue_l0(1);
+            for (int c = 0; c < 8; ++c) {
+              wait_chunk(c, P_ACC0FREE);
+              issue_l1(c);
+              if (c + 2 < 8) issue_l0(c + 2);
+            }
+          } else {
+            issue_l0(0);
+            for (int c = 0; c < 7; ++c) {
+              wait_chunk(c, P_ACC0FREE);
+              issue_l0(c + 1);
+              issue_l1(c);
+            }
+            wait_chunk(7, P_H0READY);
+            issue_l1(7);
           }
-          issue_l1(7);
           for (int kb = 0; kb < 4; ++kb) {                       // skip part of layer 1: A = X
             const uint32_t w = next_stage();
             kblock_ss(tbase + kColAcc1, sX + kb * 16384, w, idesc256, first1);
@@ -366,21 +383,24 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           }
           commit<CG>(bars + B_ACC2_FULL);
         }
-        // ---- layer 3: A = H2 from TMEM (4 K-blocks) + X (4 K-blocks) -> acc3 [0,128)
-        { PROF_T0(); wait_leader<CG>(bars, B_H2_READY, c_h2ready); PROF_ADD(P_H2READY); }
-        tc::tcgen05_fence_after();
+        // ---- layer 3 -> acc3 [256,384) (H1hi's columns: their last readers, the layer-2 MMAs, are already issued).
+        //      The skip part (A = X) goes FIRST: it does not depend on the layer-2 epilogue, and once it has completed X
+        //      is dead, so the workers can start sampling the next tile while layer 3 and the fp32 tail still run.
         {
           bool first = true;
           for (int s = 0; s < 2; ++s) {
             const uint32_t w = next_stage();
-            kblock_ts(tbase + kColAcc1, tbase + kColH2 + (2 * s) * 32, w, idesc128, first);
-            kblock_ts(tbase + kColAcc1, tbase + kColH2 + (2 * s + 1) * 32, w + C::Sub, idesc128, first);
+            kblock_ss(tbase + kColAcc3, sX + (2 * s) * 16384, w, idesc128, first);
+            kblock_ss(tbase + kColAcc3, sX + (2 * s + 1) * 16384, w + C::Sub, idesc128, first);
             release_stage();
           }
+          commit<CG>(bars + B_XFREE);
+          { PROF_T0(); wait_leader<CG>(bars, B_H2_READY, c_h2ready); PROF_ADD(P_H2READY); }
+          tc::tcgen05_fence_after();
           for (int s = 0; s < 2; ++s) {
             const uint32_t w = next_stage();
-            kblock_ss(tbase + kColAcc1, sX + (2 * s) * 16384, w, idesc128, first);
-            kblock_ss(tbase + kColAcc1, sX + (2 * s + 1) * 16384, w + C::Sub, idesc128, first);
+            kblock_ts(tbase + kColAcc3, tbase + kColH2 + (2 * s) * 32, w, idesc128, first);
+            kblock_ts(tbase + kColAcc3, tbase + kColH2 + (2 * s + 1) * 32, w + C::Sub, idesc128, first);
             release_stage();
           }
           commit<CG>(bars + B_ACC3_FULL);
@@ -395,7 +415,7 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     const int quarter = warp & 3;                // TMEM lane quarter this warp may touch
     const int row = quarter * 32 + lane;         // the point (TMEM lane) this thread owns in the epilogue
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    uint32_t c_acc0full = 0, c_h0free[2] = {0, 0}, c_acc1full = 0, c_acc2full = 0, c_acc3full = 0;
+    uint32_t c_acc0full[2] = {0, 0}, c_xfree = 0, c_h0free[2] = {0, 0}, c_acc1full = 0, c_acc2full = 0, c_acc3full = 0;
     const int res = prm.res;
     if (!(warp == 4 && lane == 0)) prof = nullptr;      // one worker thread records
 
@@ -403,9 +423,7 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       const long long tile = g * CG + rank;
       const long long p0 = tile * kTile;
       // ---- X is free once the previous tile's last MMAs (layer-3 skip) have completed
-      if (g != g0) {
-        if (wg == 1) { wait_bar(bars, B_ACC3_FULL, c_acc3full); }   // wg 0 already waited on it in its acc3 drain
-      }
+      if (g != g0) { wait_bar(bars, B_XFREE, c_xfree); }
       const long long t_sample0 = prof ? clock64() : 0;
       // ---- sampling: warp wk handles points wk*16 .. +15.  Lane q (< 16) projects point q and builds its bilinear
       //      taps once; the taps are then broadcast and every lane gathers 8 consecutive channels (16 B) per tap.
@@ -561,7 +579,8 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         // ---- layer-0 chunks -> H0 buffers (smem, A operand of layer 1)
         for (int c = 0; c < 8; ++c) {
           const int b = c & 1;
-          { PROF_T0(); wait_bar(bars, B_ACC0_FULL, c_acc0full); PROF_ADD(P_W_ACC0FULL); }
+          const int ab = (h == 0) ? b : 0;                        // acc0 buffer (double-buffered in the first half)
+          { PROF_T0(); wait_bar(bars, B_ACC0_FULL0 + ab, c_acc0full[ab]); PROF_ADD(P_W_ACC0FULL); }
           { PROF_T0(); wait_free(bars, B_H0_FREE0 + b, c_h0free[b]); PROF_ADD(P_W_H0FREE); }
           tc::tcgen05_fence_after();
           PROF_T0();
@@ -570,7 +589,7 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           for (int gq = 0; gq < 2; ++gq) {
             float o[32];
             const int ch0 = c * 128 + wg * 64 + gq * 32;
-            load_pre(kColAcc0 + wg * 64 + gq * 32, side_off(0) + ch0, o);
+            load_pre(kColAcc0 + ab * 128 + wg * 64 + gq * 32, side_off(0) + ch0, o);
             uint8_t* dstp = smem + Smem::H0 + b * 32768 + wg * 16384;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -640,7 +659,7 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
 #pragma unroll 1
         for (int gq = 0; gq < 4; ++gq) {
           float o[32];
-          load_act(kColAcc1 + gq * 32, side_off(3) + gq * 32, o);
+          load_act(kColAcc3 + gq * 32, side_off(3) + gq * 32, o);
 #pragma unroll
           for (int r = 0; r < kMaxRes; ++r) {
             if (r < res) {
@@ -745,22 +764,27 @@ int mp_tc_prepare(mp_mlp* mlp) {
       auto l1 = [&](int c) {
         for (int kb = 0; kb < 2; ++kb) pack_tile(stage_ptr(), W[1].data(), cin1, h * 256 + r * n256, n256, c * 128 + kb * 64);
       };
-      l0(0);
-      for (int c = 0; c < 7; ++c) { l0(c + 1); l1(c); }
-      l1(7);
+      if (h == 0) {            // double-buffered chunk order (mirrors the MMA issuer)
+        l0(0); l0(1);
+        for (int c = 0; c < 8; ++c) { l1(c); if (c + 2 < 8) l0(c + 2); }
+      } else {
+        l0(0);
+        for (int c = 0; c < 7; ++c) { l0(c + 1); l1(c); }
+        l1(7);
+      }
       for (int kb = 0; kb < 4; ++kb) pack_tile(stage_ptr(), W[1].data(), cin1, h * 256 + r * n256, n256, kL0 + kb * 64);
     }
     for (int kb = 0; kb < 8; ++kb) pack_tile(stage_ptr(), W[2].data(), cin2, r * n256, n256, kb * 64);
     for (int kb = 0; kb < 4; ++kb) pack_tile(stage_ptr(), W[2].data(), cin2, r * n256, n256, kL1 + kb * 64);
+    for (int s2 = 0; s2 < 2; ++s2) {         // layer 3: skip part first
+      uint8_t* p = stage_ptr();
+      pack_tile(p, W[3].data(), cin3, r * n128, n128, kL2 + (2 * s2) * 64);
+      pack_tile(p + sub, W[3].data(), cin3, r * n128, n128, kL2 + (2 * s2 + 1) * 64);
+    }
     for (int s2 = 0; s2 < 2; ++s2) {
       uint8_t* p = stage_ptr();
       pack_tile(p, W[3].data(), cin3, r * n128, n128, (2 * s2) * 64);
       pack_tile(p + sub, W[3].data(), cin3, r * n128, n128, (2 * s2 + 1) * 64);
-    }
-    for (int s2 = 0; s2 < 2; ++s2) {
-      uint8_t* p = stage_ptr();
-      pack_tile(p, W[3].data(), cin3, r * n128, n128, kL2 + (2 * s2) * 64);
-      pack_tile(p + sub, W[3].data(), cin3, r * n128, n128, kL2 + (2 * s2 + 1) * 64);
     }
     return (int)st == kStagesPerTile;
   };
