@@ -145,6 +145,7 @@ extern "C" int mp_feat_destroy(mp_feat_t* h) {
   if (h->nhwc32) cudaFree(h->nhwc32);
   if (h->nhwc16) cudaFree(h->nhwc16);
   if (h->staging) cudaFree(h->staging);
+  if (h->g0) cudaFree(h->g0);
   delete h;
   return MP_OK;
 }
@@ -183,6 +184,7 @@ extern "C" int mp_feat_upload(mp_feat_t* h, const float* nchw, int on_device, vo
   dim3 grid((HW + 31) / 32, (h->C + 31) / 32), block(32, 8);
   nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(src, h->nhwc32, h->nhwc16, h->C, HW);
   MP_CUDA(cudaGetLastError());
+  h->version += 1;
   return MP_OK;
 }
 

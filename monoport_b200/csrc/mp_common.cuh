@@ -60,6 +60,14 @@ struct mp_feat {
   __half* nhwc16;   // [H][W][C] fp16
   float* staging;   // [C][H][W] device staging for host uploads
   int device;
+  // layer-0 pre-activation per texel, G0 = W0[:, :C] . F  ([H*W][g0_n] fp16), built lazily by the tcgen05 v3 path
+  // (bilinear sampling is linear, so sampling G0 equals applying W0 to the sampled features); valid for
+  // (g0_owner == head handle, g0_version == version)
+  __half* g0;
+  int g0_n;
+  const void* g0_owner;
+  unsigned long long g0_version;
+  unsigned long long version;   // bumped by every mp_feat_upload
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -190,7 +198,7 @@ __device__ __forceinline__ float mp_lrelu(float v) { return v > 0.f ? v : v * MP
 // host-side launchers implemented in the kernel files
 int mp_launch_query_fp32(const mp_mlp* mlp, const mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
                          const MpOutDst& dst, cudaStream_t st);
-int mp_launch_query_tc(const mp_mlp* mlp, const mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
+int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
                        const MpOutDst& dst, cudaStream_t st);
 int mp_tc_prepare(mp_mlp* mlp);     // builds mlp->tc; sets tc_ok
 void mp_tc_release(mp_mlp* mlp);

@@ -57,6 +57,7 @@ constexpr int kMaxRes = 1;             // output channels handled by the fp32 ta
 // per-tile weight stream (32 KB stages), in MMA consumption order
 constexpr int kStagesPerHalf = 16 + 16 + 4;                       // L0 (8 chunks x 2) + L1 hidden (8 x 2) + L1 skip
 constexpr int kStagesPerTile = 2 * kStagesPerHalf + 12 + 4;       // + L2 (8 hidden + 4 skip) + L3 (2 hidden + 2 skip)
+constexpr int kStagesPerTile3 = 32 + 8 + 12 + 4;                  // v3: L1 hidden (8 chunks x 2 K-blocks x 2 N-halves) + L1 skip + L2 + L3
 
 // TMEM columns
 constexpr uint32_t kColAcc1 = 0, kColAcc0 = 256, kColH1lo = 384, kColH1hi = 256, kColH2 = 384, kColAcc3 = 256;
@@ -67,6 +68,11 @@ __host__ __device__ constexpr int side_off(int l) { return l == 0 ? 0 : l == 1 ?
 struct TcPack {
   __half* wstream;        // CG=1: kStagesPerTile * 32 KB
   __half* wstream2[2];    // CG=2: per cluster rank, kStagesPerTile * 16 KB
+  __half* w3stream;       // v3 (layer 0 hoisted to texels): kStagesPerTile3 * 32 KB
+  __half* w3stream2[2];   // v3, CG=2
+  float* d_bias0;         // device copies for per-lane channel access (v3 H0 generation)
+  float* d_wz0;
+  float* d_w0f;           // [1024][256] fp32: feature part of layer 0 (operand of the per-texel G0 GEMM)
   float* bias[4];         // per hidden layer
   float* wz[4];           // z column of every hidden layer
   float h_bias[kSideFloats];   // host copies (passed by value in the kernel parameters)
@@ -93,6 +99,9 @@ struct TcParams {
   int last_op;
   int H, W;
   const __half* feat;     // NHWC fp16
+  const __half* g0;       // v3: [H*W][1024] fp16 per-texel layer-0 product
+  const float* d_bias0;
+  const float* d_wz0;
   unsigned long long* prof;   // optional [gridDim.x][32] cycle counters (MONOPORT_B200_TC_PROF=1), else null
 };
 enum Prof { P_TOTAL = 0, P_XREADY, P_ACC0FREE, P_WFULL, P_WPEER, P_H0READY, P_ACC1DRAINED, P_H1READY, P_H2READY,
@@ -704,6 +713,586 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
   }
 }
 
+// ====================================================================================================================
+// v3: layer 0 hoisted from points to texels.
+// Bilinear sampling is linear, so  W0[:, :256] . sample(F)(u,v) == sample(W0[:, :256] . F)(u,v).  G0 = W0f . F is built once
+// per frame per texel (g0_kernel below: 16384 x 1024 x 256 fp32 GEMM, 4.3 GFLOP instead of 17 M points x 0.5 MFLOP), and
+// the kernel *samples* the 1024-channel layer-0 pre-activation: h0 = lrelu(lerp(G0) + b0 + w0z * z).
+//   * no layer-0 MMAs, no layer-0 accumulator in TMEM  =>  layer 1 owns all 512 TMEM columns, no halves, no recompute;
+//   * 1.0 MB less weight traffic per tile (1.84 MB instead of 2.88 MB);
+//   * the layer-0 chunk no longer depends on the tensor pipe (MMA -> drain -> MMA chain gone): workers generate H0
+//     chunks ahead of the MMA issuer through the double-buffered smem ring.
+// TMEM map: acc1 [0,512)  --drain in place-->  H1lo [0,128) | acc2 [128,384) | H1hi [384,512)
+//           --drain-->  H2 [0,128) | (free) | acc3 [384,512)
+// roofline.achieved keeps counting the ALGORITHMIC 2 363 906 FLOP/point; the hoisted layer is not executed per point.
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
+  using C = Cfg<CG>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::Bars);
+  float* s_zf = reinterpret_cast<float*>(smem + Smem::Small);
+  float* s_in = s_zf + kTile;
+  float* s_s4 = s_in + kTile;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Smem::TmemPtr);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned long long* prof = prm.prof ? prm.prof + (size_t)blockIdx.x * 32 : nullptr;
+  const uint32_t rank = (CG == 2) ? tc::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+
+  long long n = src.n;
+  if (src.count_dev) {
+    const long long c = *src.count_dev;
+    n = c < n ? c : n;
+  }
+  const long long n_tiles = (n + kTile - 1) / kTile;
+  const long long n_groups = (n_tiles + CG - 1) / CG;
+  const long long g0 = blockIdx.x / CG, gstep = gridDim.x / CG;
+
+  constexpr uint32_t cAcc1 = 0, cH1lo = 0, cH1hi = 384, cAcc2 = 128, cH2 = 0, cAcc3 = 384;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      tc::mbar_init(bars + B_WFULL + s, 1);
+      tc::mbar_init(bars + B_WEMPTY + s, 1);
+      tc::mbar_init(bars + B_WPEER + s, 1);
+    }
+    constexpr int kW = 8 * CG;
+    tc::mbar_init(bars + B_XREADY, kW);
+    tc::mbar_init(bars + B_H0_READY0, kW);
+    tc::mbar_init(bars + B_H0_READY1, kW);
+    tc::mbar_init(bars + B_H0_FREE0, 1);
+    tc::mbar_init(bars + B_H0_FREE1, 1);
+    tc::mbar_init(bars + B_ACC1_FULL, 1);
+    tc::mbar_init(bars + B_H1_READY, kW);
+    tc::mbar_init(bars + B_ACC2_FULL, 1);
+    tc::mbar_init(bars + B_H2_READY, kW);
+    tc::mbar_init(bars + B_ACC3_FULL, 1);
+    tc::mbar_init(bars + B_TILE_DONE, 4 * CG);
+    tc::mbar_init(bars + B_XFREE, 1);
+    tc::mbar_init(bars + B_ACC0_FULL0, 1);
+    tc::mbar_init(bars + B_ACC0_FULL1, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    if constexpr (CG == 1) { tc::tmem_alloc(s_tmem, 512); tc::tmem_relinquish(); }
+    else { tc::tmem_alloc2(s_tmem, 512); tc::tmem_relinquish2(); }
+  }
+  tc::tcgen05_fence_before();
+  if constexpr (CG == 1) __syncthreads(); else tc::cluster_sync_all();
+  tc::tcgen05_fence_after();
+  const uint32_t tbase = *s_tmem;
+
+  if (warp == 0) {
+    // ============================== weight producer ==============================
+    if (lane == 0) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(CG == 2 ? prm.wstream2[rank] : prm.wstream);
+      uint32_t it = 0;
+      for (long long g = g0; g < n_groups; g += gstep) {
+        for (int s = 0; s < kStagesPerTile3; ++s, ++it) {
+          const int slot = it % C::Stages;
+          const uint32_t use = it / C::Stages;
+          tc::mbar_wait(bars + B_WEMPTY + slot, (use & 1u) ^ 1u);
+          tc::mbar_arrive_expect_tx(bars + B_WFULL + slot, C::StageBytes);
+          tc::bulk_g2s(smem + Smem::Wr + slot * C::StageBytes, wsrc + (size_t)s * C::StageBytes, C::StageBytes,
+                       bars + B_WFULL + slot);
+        }
+      }
+    }
+  } else if (warp == 1 && !leader) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long g = g0; g < n_groups; g += gstep) {
+        for (int s = 0; s < kStagesPerTile3; ++s, ++it) {
+          const int slot = it % C::Stages;
+          tc::mbar_wait(bars + B_WFULL + slot, (it / C::Stages) & 1u);
+          tc::mbar_arrive_remote(bars + B_WPEER + slot, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc128 = tc::make_idesc_f16(128 * CG, 128);
+      const uint32_t idesc256 = tc::make_idesc_f16(128 * CG, 256);
+      const uint32_t sX = tc::smem_u32(smem + Smem::X);
+      const uint32_t sH0 = tc::smem_u32(smem + Smem::H0);
+      const uint32_t sW = tc::smem_u32(smem + Smem::Wr);
+      uint32_t it = 0;
+      uint32_t c_xready = 0, c_h0ready[2] = {0, 0}, c_h1ready = 0, c_h2ready = 0, c_tiledone = 0;
+      const long long t_begin = prof ? clock64() : 0;
+      auto next_stage = [&]() -> uint32_t {
+        const int slot = it % C::Stages;
+        const uint32_t par = (it / C::Stages) & 1u;
+        { PROF_T0(); tc::mbar_wait(bars + B_WFULL + slot, par); PROF_ADD(P_WFULL); }
+        if constexpr (CG == 2) { PROF_T0(); tc::mbar_wait_cluster(bars + B_WPEER + slot, par); PROF_ADD(P_WPEER); }
+        tc::tcgen05_fence_after();
+        return sW + slot * C::StageBytes;
+      };
+      auto release_stage = [&]() {
+        commit<CG>(bars + B_WEMPTY + (it % C::Stages));
+        ++it;
+      };
+      auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool& first) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t ad = tc::make_sdesc_sw128(a_addr + kk * 32, 1024), bd = tc::make_sdesc_sw128(b_addr + kk * 32, 1024);
+          if constexpr (CG == 1) tc::mma_ss(d, ad, bd, idesc, first ? 0u : 1u);
+          else tc::mma_ss2(d, ad, bd, idesc, first ? 0u : 1u);
+          first = false;
+        }
+      };
+      auto kblock_ts = [&](uint32_t d, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool& first) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t bd = tc::make_sdesc_sw128(b_addr + kk * 32, 1024);
+          if constexpr (CG == 1) tc::mma_ts(d, a_tmem + kk * 8, bd, idesc, first ? 0u : 1u);
+          else tc::mma_ts2(d, a_tmem + kk * 8, bd, idesc, first ? 0u : 1u);
+          first = false;
+        }
+      };
+
+      for (long long g = g0; g < n_groups; g += gstep) {
+        // acc1 = [0,512) overlaps the previous tile's H2 (readers already issued, in order), acc2 (drained before
+        // B_H2_READY, waited) and acc3 (drained by the fp32 tail: B_TILE_DONE)
+        if (g != g0) {
+          PROF_T0();
+          wait_leader<CG>(bars, B_TILE_DONE, c_tiledone);
+          PROF_ADD(P_ACC1DRAINED);
+          tc::tcgen05_fence_after();
+        }
+        bool first1[2] = {true, true};
+        // ---- layer 1, hidden part: 8 sampled layer-0 chunks x 2 K-blocks x 2 output halves
+        for (int c = 0; c < 8; ++c) {
+          const int b = c & 1;
+          { PROF_T0(); wait_leader<CG>(bars, B_H0_READY0 + b, c_h0ready[b]); PROF_ADD(P_H0READY); }
+          tc::tcgen05_fence_after();
+          for (int kb = 0; kb < 2; ++kb)
+            for (int nh = 0; nh < 2; ++nh) {
+              const uint32_t w = next_stage();
+              kblock_ss(tbase + cAcc1 + nh * 256, sH0 + b * 32768 + kb * 16384, w, idesc256, first1[nh]);
+              release_stage();
+            }
+          commit<CG>(bars + B_H0_FREE0 + b);
+        }
+        // ---- layer 1, skip part: A = X
+        { PROF_T0(); wait_leader<CG>(bars, B_XREADY, c_xready); PROF_ADD(P_XREADY); }
+        tc::tcgen05_fence_after();
+        for (int kb = 0; kb < 4; ++kb)
+          for (int nh = 0; nh < 2; ++nh) {
+            const uint32_t w = next_stage();
+            kblock_ss(tbase + cAcc1 + nh * 256, sX + kb * 16384, w, idesc256, first1[nh]);
+            release_stage();
+          }
+        commit<CG>(bars + B_ACC1_FULL);
+        // ---- layer 2: A = H1 from TMEM (8 K-blocks) + X (4 K-blocks) -> acc2 [128,384)
+        { PROF_T0(); wait_leader<CG>(bars, B_H1_READY, c_h1ready); PROF_ADD(P_H1READY); }
+        tc::tcgen05_fence_after();
+        {
+          bool first = true;
+          for (int kb = 0; kb < 8; ++kb) {
+            const uint32_t w = next_stage();
+            const uint32_t a = tbase + (kb < 4 ? cH1lo + kb * 32 : cH1hi + (kb - 4) * 32);
+            kblock_ts(tbase + cAcc2, a, w, idesc256, first);
+            release_stage();
+          }
+          for (int kb = 0; kb < 4; ++kb) {
+            const uint32_t w = next_stage();
+            kblock_ss(tbase + cAcc2, sX + kb * 16384, w, idesc256, first);
+            release_stage();
+          }
+          commit<CG>(bars + B_ACC2_FULL);
+        }
+        // ---- layer 3 -> acc3 [384,512); skip part first, then X is dead
+        {
+          bool first = true;
+          for (int s = 0; s < 2; ++s) {
+            const uint32_t w = next_stage();
+            kblock_ss(tbase + cAcc3, sX + (2 * s) * 16384, w, idesc128, first);
+            kblock_ss(tbase + cAcc3, sX + (2 * s + 1) * 16384, w + C::Sub, idesc128, first);
+            release_stage();
+          }
+          commit<CG>(bars + B_XFREE);
+          { PROF_T0(); wait_leader<CG>(bars, B_H2_READY, c_h2ready); PROF_ADD(P_H2READY); }
+          tc::tcgen05_fence_after();
+          for (int s = 0; s < 2; ++s) {
+            const uint32_t w = next_stage();
+            kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * s) * 32, w, idesc128, first);
+            kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * s + 1) * 32, w + C::Sub, idesc128, first);
+            release_stage();
+          }
+          commit<CG>(bars + B_ACC3_FULL);
+        }
+      }
+      if (prof) prof[P_TOTAL] = (unsigned long long)(clock64() - t_begin);
+    }
+  } else if (warp >= 4) {
+    // ============================== workers ==============================
+    const int wk = warp - 4;
+    const int wg = wk >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    uint32_t c_xfree = 0, c_h0free[2] = {0, 0}, c_acc1full = 0, c_acc2full = 0, c_acc3full = 0;
+    const int res = prm.res;
+    if (!(warp == 4 && lane == 0)) prof = nullptr;
+    const int l16 = lane & 15, hw = lane >> 4;
+
+    auto act_pack = [&](float a, float b) -> uint32_t {
+      const __half2 h = __floats2half2_rn(a, b);
+      const __half2 r = __hmax2(h, __hmul2(h, __float2half2_rn(MP_LEAKY_SLOPE)));
+      return *reinterpret_cast<const uint32_t*>(&r);
+    };
+
+    for (long long g = g0; g < n_groups; g += gstep) {
+      const long long tile = g * CG + rank;
+      const long long p0 = tile * kTile;
+      // ---- projection + taps of this warp's 16 points (lane q and q+16 both hold point q)
+      int my_off[4];
+      float my_wgt[4];
+      float my_zf;
+      bool my_in;
+      {
+        const long long i = p0 + wk * 16 + l16;
+        float u = 0.f, v = 0.f, w = 0.f;
+        const bool valid = i < n;
+        if (valid) {
+          float x, y, z;
+          mp_load_point(src, i, x, y, z);
+          mp_project(cal, x, y, z, u, v, w);
+        }
+        my_in = valid && (u >= -1.f) && (u <= 1.f) && (v >= -1.f) && (v <= 1.f);
+        MpTaps t = mp_taps(valid ? u : 0.f, valid ? v : 0.f, prm.H, prm.W);
+        const bool dead = !valid || !(u == u) || !(v == v);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { my_off[a] = dead ? 0 : t.off[a]; my_wgt[a] = dead ? 0.f : t.wgt[a]; }
+        my_zf = w * cal.z_scale;
+      }
+      // ---- one sampled layer-0 chunk: h0[:, c*128 .. +128) = lrelu(lerp(G0) + b0 + w0z z) -> H0 smem buffer c&1.
+      //      A half-warp covers one point (16 lanes x 8 channels), so a pass handles 2 of the warp's 16 points.
+      auto gen_chunk = [&](int c) {
+        const int b = c & 1;
+        { PROF_T0(); wait_free(bars, B_H0_FREE0 + b, c_h0free[b]); PROF_ADD(P_W_H0FREE); }
+        PROF_T0();
+        const int ch = c * 128 + l16 * 8;
+        const float4 bA = __ldg(reinterpret_cast<const float4*>(prm.d_bias0 + ch));
+        const float4 bB = __ldg(reinterpret_cast<const float4*>(prm.d_bias0 + ch) + 1);
+        const float4 zA = __ldg(reinterpret_cast<const float4*>(prm.d_wz0 + ch));
+        const float4 zB = __ldg(reinterpret_cast<const float4*>(prm.d_wz0 + ch) + 1);
+        const float b8[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+        const float z8[8] = {zA.x, zA.y, zA.z, zA.w, zB.x, zB.y, zB.z, zB.w};
+        uint8_t* dstp = smem + Smem::H0 + b * 32768 + (l16 >> 3) * 16384;
+#pragma unroll 1
+        for (int batch = 0; batch < 2; ++batch) {
+          uint4 raw[4][4];
+          float wgt[4][4];
+          float zq[4];
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int q = (batch * 4 + ps) * 2 + hw;
+            zq[ps] = __shfl_sync(0xffffffffu, my_zf, q);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const int off = __shfl_sync(0xffffffffu, my_off[a], q);
+              wgt[ps][a] = __shfl_sync(0xffffffffu, my_wgt[a], q);
+              raw[ps][a] = __ldg(reinterpret_cast<const uint4*>(prm.g0 + (size_t)off * kL0 + ch));
+            }
+          }
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int p = wk * 16 + (batch * 4 + ps) * 2 + hw;
+            float acc[8];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const __half2* h2 = reinterpret_cast<const __half2*>(&raw[ps][a]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h2[j]);
+                acc[2 * j] = (a == 0) ? f.x * wgt[ps][a] : acc[2 * j] + f.x * wgt[ps][a];
+                acc[2 * j + 1] = (a == 0) ? f.y * wgt[ps][a] : acc[2 * j + 1] + f.y * wgt[ps][a];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += fmaf(z8[j], zq[ps], b8[j]);
+            uint4 pk;
+            pk.x = act_pack(acc[0], acc[1]);
+            pk.y = act_pack(acc[2], acc[3]);
+            pk.z = act_pack(acc[4], acc[5]);
+            pk.w = act_pack(acc[6], acc[7]);
+            *reinterpret_cast<uint4*>(dstp + tc::sw128_offset(p, (l16 & 7) * 8)) = pk;
+          }
+        }
+        tc::fence_proxy_async_smem();
+        warp_arrive_leader<CG>(bars + B_H0_READY0 + b, lane);
+        PROF_ADD(P_W_DRAIN0);
+      };
+      gen_chunk(0);
+      gen_chunk(1);
+      // ---- X (skip operand): previous tile's last reader (layer-3 skip MMAs) must be done
+      if (g != g0) { PROF_T0(); wait_bar(bars, B_XFREE, c_xfree); PROF_ADD(P_W_XFREE); }
+      {
+        const long long t_sample0 = prof ? clock64() : 0;
+        const int cbase = lane * 8;
+        float w4s[kMaxRes][8];
+#pragma unroll
+        for (int r = 0; r < kMaxRes; ++r)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w4s[r][j] = (r < res) ? __ldg(prm.w4s + r * kC + cbase + j) : 0.f;
+        float s4part[kMaxRes][16];
+#pragma unroll
+        for (int q0 = 0; q0 < 16; q0 += 4) {
+          uint4 raw[4][4];
+          float wgt[4][4];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq)
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const int off = __shfl_sync(0xffffffffu, my_off[a], q0 + qq);
+              wgt[qq][a] = __shfl_sync(0xffffffffu, my_wgt[a], q0 + qq);
+              raw[qq][a] = __ldg(reinterpret_cast<const uint4*>(prm.feat + (size_t)off * kC + cbase));
+            }
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const int p = wk * 16 + q0 + qq;
+            float acc[8];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const __half2* h2 = reinterpret_cast<const __half2*>(&raw[qq][a]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h2[j]);
+                acc[2 * j] = (a == 0) ? f.x * wgt[qq][a] : acc[2 * j] + f.x * wgt[qq][a];
+                acc[2 * j + 1] = (a == 0) ? f.y * wgt[qq][a] : acc[2 * j + 1] + f.y * wgt[qq][a];
+              }
+            }
+            uint4 packed;
+            packed.x = tc::pack_half2(acc[0], acc[1]);
+            packed.y = tc::pack_half2(acc[2], acc[3]);
+            packed.z = tc::pack_half2(acc[4], acc[5]);
+            packed.w = tc::pack_half2(acc[6], acc[7]);
+            const int kb = lane >> 3;
+            *reinterpret_cast<uint4*>(smem + Smem::X + kb * 16384 + tc::sw128_offset(p, (lane & 7) * 8)) = packed;
+#pragma unroll
+            for (int r = 0; r < kMaxRes; ++r) {
+              float sacc = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) sacc = fmaf(w4s[r][j], acc[j], sacc);
+              s4part[r][q0 + qq] = sacc;
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < kMaxRes; ++r) {
+          if (r < res) {
+            float v16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v16[j] = s4part[r][j] + __shfl_xor_sync(0xffffffffu, s4part[r][j], 16);
+            float v8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const bool up = lane & 8;
+              const float keep = up ? v16[j + 8] : v16[j], send = up ? v16[j] : v16[j + 8];
+              v8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            float v4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool up = lane & 4;
+              const float keep = up ? v8[j + 4] : v8[j], send = up ? v8[j] : v8[j + 4];
+              v4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            float v2[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const bool up = lane & 2;
+              const float keep = up ? v4[j + 2] : v4[j], send = up ? v4[j] : v4[j + 2];
+              v2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            const bool up = lane & 1;
+            const float keep = up ? v2[1] : v2[0], send = up ? v2[0] : v2[1];
+            const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            if (lane < 16) s_s4[r * kTile + wk * 16 + lane] = tot + __ldg(prm.w4z + r) * my_zf + __ldg(prm.b4 + r);
+          }
+        }
+        if (lane < 16) {
+          s_zf[wk * 16 + lane] = my_zf;
+          s_in[wk * 16 + lane] = my_in ? 1.f : 0.f;
+        }
+        tc::fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (prof) prof[P_W_SAMPLE] += (unsigned long long)(clock64() - t_sample0);
+      }
+      const float zf = s_zf[row];
+      const float inimg = s_in[row];
+      float s4[kMaxRes];
+#pragma unroll
+      for (int r = 0; r < kMaxRes; ++r) s4[r] = (r < res) ? s_s4[r * kTile + row] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      warp_arrive_leader<CG>(bars + B_XREADY, lane);
+      for (int c = 2; c < 8; ++c) gen_chunk(c);
+
+      auto load_pre = [&](uint32_t col, int ch0, float (&o)[32]) {
+        uint32_t v[32];
+        tc::tmem_ld32(tbase + lane_base + col, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          o[j] = __uint_as_float(v[j]) + fmaf(prm.wz_all[ch0 + j], zf, prm.bias_all[ch0 + j]);
+      };
+      // ---- layer 1 (512 columns) -> H1, drained IN PLACE: warpgroup 0 walks [0,256) upwards into [0,128), warpgroup 1
+      //      walks [256,512) downwards into [384,512); the packed destination of a group never reaches columns that are
+      //      still unread, and [128,384) comes out free for acc2.
+      { PROF_T0(); wait_bar(bars, B_ACC1_FULL, c_acc1full); PROF_ADD(P_W_ACC1FULL); }
+      tc::tcgen05_fence_after();
+      {
+        PROF_T0();
+#pragma unroll 1
+        for (int gi = 0; gi < 8; ++gi) {
+          const int gq = (wg == 0) ? gi : 7 - gi;
+          const int lc = wg * 256 + gq * 32;                 // accumulator column == layer-1 output channel
+          float o[32];
+          load_pre(cAcc1 + lc, side_off(1) + lc, o);
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = act_pack(o[2 * j], o[2 * j + 1]);
+          const uint32_t dcol = (wg == 0) ? (cH1lo + lc / 2) : (cH1hi + (lc - 256) / 2);
+          tc::tmem_st16(tbase + lane_base + dcol, pk);
+          tc::tmem_st_wait();
+        }
+        tc::tcgen05_fence_before();
+        warp_arrive_leader<CG>(bars + B_H1_READY, lane);
+        PROF_ADD(P_W_DRAIN1);
+      }
+      // ---- layer 2 -> H2 [0,128)
+      { PROF_T0(); wait_bar(bars, B_ACC2_FULL, c_acc2full); PROF_ADD(P_W_ACC2FULL); }
+      tc::tcgen05_fence_after();
+      {
+        PROF_T0();
+#pragma unroll 1
+        for (int gq = 0; gq < 4; ++gq) {
+          float o[32];
+          const int lc = wg * 128 + gq * 32;
+          load_pre(cAcc2 + lc, side_off(2) + lc, o);
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = act_pack(o[2 * j], o[2 * j + 1]);
+          tc::tmem_st16(tbase + lane_base + cH2 + lc / 2, pk);
+        }
+        tc::tmem_st_wait();
+        tc::tcgen05_fence_before();
+        warp_arrive_leader<CG>(bars + B_H2_READY, lane);
+        PROF_ADD(P_W_DRAIN2);
+      }
+      // ---- layer 3 + layer 4 in fp32, warpgroup 0
+      if (wg == 0) {
+        { PROF_T0(); wait_bar(bars, B_ACC3_FULL, c_acc3full); PROF_ADD(P_W_ACC3FULL); }
+        tc::tcgen05_fence_after();
+        PROF_T0();
+        float logit[kMaxRes];
+#pragma unroll
+        for (int r = 0; r < kMaxRes; ++r) logit[r] = s4[r];
+#pragma unroll 1
+        for (int gq = 0; gq < 4; ++gq) {
+          float o[32];
+          load_pre(cAcc3 + gq * 32, side_off(3) + gq * 32, o);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], o[j] * MP_LEAKY_SLOPE);
+#pragma unroll
+          for (int r = 0; r < kMaxRes; ++r) {
+            if (r < res) {
+              const float4* wv = reinterpret_cast<const float4*>(prm.w4h + r * kL3 + gq * 32);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 w4 = __ldg(wv + j4);
+                logit[r] = fmaf(w4.x, o[4 * j4 + 0], logit[r]);
+                logit[r] = fmaf(w4.y, o[4 * j4 + 1], logit[r]);
+                logit[r] = fmaf(w4.z, o[4 * j4 + 2], logit[r]);
+                logit[r] = fmaf(w4.w, o[4 * j4 + 3], logit[r]);
+              }
+            }
+          }
+        }
+        tc::tcgen05_fence_before();
+        warp_arrive_leader<CG>(bars + B_TILE_DONE, lane);
+        PROF_ADD(P_W_DRAIN3);
+        const long long i = p0 + row;
+        if (i < n) {
+#pragma unroll
+          for (int r = 0; r < kMaxRes; ++r) {
+            if (r < res) {
+              const float val = inimg * mp_last_op(logit[r], prm.last_op);
+              if (dst.out) dst.out[(long long)r * dst.ld + i] = val;
+              if (dst.scatter_vol && r == 0) dst.scatter_vol[__ldg(src.nodes + i)] = val;
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc::tcgen05_fence_before();
+  if constexpr (CG == 1) {
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tbase, 512);
+  } else {
+    tc::cluster_sync_all();
+    if (warp == 2) tc::tmem_dealloc2(tbase, 512);
+  }
+}
+
+// G0[texel][n] = sum_k F[texel][k] * W0f[n][k]   (fp32 CUDA-core GEMM, NT; result rounded once to fp16)
+// 128 x 128 tile per CTA, 256 threads, 8 x 8 micro-tile, K step 16.
+__global__ void __launch_bounds__(256)
+g0_kernel(const float* __restrict__ F, const float* __restrict__ W, __half* __restrict__ G, int M, int N, int K) {
+  __shared__ float sA[16][128 + 4];
+  __shared__ float sB[16][128 + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
+  const int tm = (tid >> 4) * 8, tn = (tid & 15) * 8;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    // each thread loads 2 float4 of A and of B: row = tid/4 (+64), k chunk = (tid%4)*4
+    for (int rr = 0; rr < 2; ++rr) {
+      const int r = (tid >> 2) + rr * 64, kc = (tid & 3) * 4;
+      const float4 a = (m0 + r < M) ? *reinterpret_cast<const float4*>(F + (size_t)(m0 + r) * K + k0 + kc) : make_float4(0, 0, 0, 0);
+      const float4 b = (n0 + r < N) ? *reinterpret_cast<const float4*>(W + (size_t)(n0 + r) * K + k0 + kc) : make_float4(0, 0, 0, 0);
+      sA[kc + 0][r] = a.x; sA[kc + 1][r] = a.y; sA[kc + 2][r] = a.z; sA[kc + 3][r] = a.w;
+      sB[kc + 0][r] = b.x; sB[kc + 1][r] = b.y; sB[kc + 2][r] = b.z; sB[kc + 3][r] = b.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[8], b[8];
+      *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&sA[k][tm]);
+      *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(&sA[k][tm + 4]);
+      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&sB[k][tn]);
+      *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(&sB[k][tn + 4]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + tm + i;
+    if (m >= M) continue;
+    uint4 pk;
+    pk.x = tc::pack_half2(acc[i][0], acc[i][1]);
+    pk.y = tc::pack_half2(acc[i][2], acc[i][3]);
+    pk.z = tc::pack_half2(acc[i][4], acc[i][5]);
+    pk.w = tc::pack_half2(acc[i][6], acc[i][7]);
+    *reinterpret_cast<uint4*>(G + (size_t)m * N + n0 + tn) = pk;
+  }
+}
+
 // --------------------------------------------------------------------------------------------------------------------
 // host side: weight packing
 // --------------------------------------------------------------------------------------------------------------------
@@ -793,6 +1382,38 @@ int mp_tc_prepare(mp_mlp* mlp) {
     mp_set_error("internal: weight stream stage count mismatch");
     return MP_E_INVALID;
   }
+  // v3 program (layer 0 hoisted): layer 1 over all 512 outputs as two 256-row tiles per K-block, then layers 2, 3
+  auto build_stream3 = [&](int cg, int r, std::vector<uint8_t>& out) -> bool {
+    const int stage_bytes = 32768 / cg, sub = stage_bytes / 2;
+    out.assign((size_t)kStagesPerTile3 * stage_bytes, 0);
+    size_t st = 0;
+    auto stage_ptr = [&]() { return out.data() + (st++) * stage_bytes; };
+    const int n128 = 128 / cg, n256 = 256 / cg;
+    const int cin1 = mlp->cin[1], cin2 = mlp->cin[2], cin3 = mlp->cin[3];
+    for (int c = 0; c < 8; ++c)
+      for (int kb = 0; kb < 2; ++kb)
+        for (int nh = 0; nh < 2; ++nh) pack_tile(stage_ptr(), W[1].data(), cin1, nh * 256 + r * n256, n256, c * 128 + kb * 64);
+    for (int kb = 0; kb < 4; ++kb)
+      for (int nh = 0; nh < 2; ++nh) pack_tile(stage_ptr(), W[1].data(), cin1, nh * 256 + r * n256, n256, kL0 + kb * 64);
+    for (int kb = 0; kb < 8; ++kb) pack_tile(stage_ptr(), W[2].data(), cin2, r * n256, n256, kb * 64);
+    for (int kb = 0; kb < 4; ++kb) pack_tile(stage_ptr(), W[2].data(), cin2, r * n256, n256, kL1 + kb * 64);
+    for (int s2 = 0; s2 < 2; ++s2) {
+      uint8_t* p = stage_ptr();
+      pack_tile(p, W[3].data(), cin3, r * n128, n128, kL2 + (2 * s2) * 64);
+      pack_tile(p + sub, W[3].data(), cin3, r * n128, n128, kL2 + (2 * s2 + 1) * 64);
+    }
+    for (int s2 = 0; s2 < 2; ++s2) {
+      uint8_t* p = stage_ptr();
+      pack_tile(p, W[3].data(), cin3, r * n128, n128, (2 * s2) * 64);
+      pack_tile(p + sub, W[3].data(), cin3, r * n128, n128, (2 * s2 + 1) * 64);
+    }
+    return (int)st == kStagesPerTile3;
+  };
+  std::vector<uint8_t> s3, s3b[2];
+  if (!build_stream3(1, 0, s3) || !build_stream3(2, 0, s3b[0]) || !build_stream3(2, 1, s3b[1])) {
+    mp_set_error("internal: v3 weight stream stage count mismatch");
+    return MP_E_INVALID;
+  }
 
   TcPack* pk = new TcPack();
   memset(pk, 0, sizeof(*pk));
@@ -804,6 +1425,13 @@ int mp_tc_prepare(mp_mlp* mlp) {
   };
   cudaError_t e = upload(stream.data(), stream.size(), (void**)&pk->wstream);
   for (int r = 0; r < 2 && e == cudaSuccess; ++r) e = upload(stream2[r].data(), stream2[r].size(), (void**)&pk->wstream2[r]);
+  if (e == cudaSuccess) e = upload(s3.data(), s3.size(), (void**)&pk->w3stream);
+  for (int r = 0; r < 2 && e == cudaSuccess; ++r) e = upload(s3b[r].data(), s3b[r].size(), (void**)&pk->w3stream2[r]);
+  if (e == cudaSuccess) {   // feature part of layer 0, fp32 [1024][256], operand of the per-texel G0 GEMM
+    std::vector<float> w0f((size_t)kL0 * kC);
+    for (int co = 0; co < kL0; ++co) memcpy(&w0f[(size_t)co * kC], &W[0][(size_t)co * mlp->cin[0]], kC * sizeof(float));
+    e = upload(w0f.data(), w0f.size() * sizeof(float), (void**)&pk->d_w0f);
+  }
   const int hid[4] = {0, kL0, kL1, kL2};
   for (int l = 0; l < 4 && e == cudaSuccess; ++l) {
     std::vector<float> wz(mlp->cout[l]);
@@ -811,6 +1439,10 @@ int mp_tc_prepare(mp_mlp* mlp) {
     for (int co = 0; co < mlp->cout[l]; ++co) wz[co] = W[l][(size_t)co * mlp->cin[l] + zcol];
     memcpy(pk->h_bias + side_off(l), Bv[l].data(), Bv[l].size() * sizeof(float));
     memcpy(pk->h_wz + side_off(l), wz.data(), wz.size() * sizeof(float));
+    if (l == 0) {
+      e = upload(Bv[0].data(), Bv[0].size() * sizeof(float), (void**)&pk->d_bias0);
+      if (e == cudaSuccess) e = upload(wz.data(), wz.size() * sizeof(float), (void**)&pk->d_wz0);
+    }
   }
   if (e == cudaSuccess) {
     const int R = pk->res, cin4 = mlp->cin[4];
@@ -833,6 +1465,8 @@ int mp_tc_prepare(mp_mlp* mlp) {
   }
   e = cudaFuncSetAttribute(query_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e != cudaSuccess) {
     mp_set_error("mp_tc_prepare: cannot opt in to %d bytes of shared memory: %s", Smem::Total + 1024, cudaGetErrorString(e));
     mp_tc_release(mlp);
@@ -847,6 +1481,11 @@ void mp_tc_release(mp_mlp* mlp) {
   if (!pk) return;
   if (pk->wstream) cudaFree(pk->wstream);
   for (int r = 0; r < 2; ++r) if (pk->wstream2[r]) cudaFree(pk->wstream2[r]);
+  if (pk->w3stream) cudaFree(pk->w3stream);
+  for (int r = 0; r < 2; ++r) if (pk->w3stream2[r]) cudaFree(pk->w3stream2[r]);
+  if (pk->d_bias0) cudaFree(pk->d_bias0);
+  if (pk->d_wz0) cudaFree(pk->d_wz0);
+  if (pk->d_w0f) cudaFree(pk->d_w0f);
   for (int l = 0; l < 4; ++l) {
     if (pk->bias[l]) cudaFree(pk->bias[l]);
     if (pk->wz[l]) cudaFree(pk->wz[l]);
@@ -860,7 +1499,7 @@ void mp_tc_release(mp_mlp* mlp) {
   mlp->tc_ok = 0;
 }
 
-int mp_launch_query_tc(const mp_mlp* mlp, const mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
+int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
                        const MpOutDst& dst, cudaStream_t st) {
   if (src.n <= 0) return MP_OK;
   const TcPack* pk = static_cast<const TcPack*>(mlp->tc);
@@ -909,14 +1548,41 @@ int mp_launch_query_tc(const mp_mlp* mlp, const mp_feat* feat, const MpPointSrc&
     for (int k = 0; k < 32; ++k)
       if (names[k]) fprintf(stderr, "[tc prof] %-12s %10.0f | %10.0f\n", names[k], (double)h[k] / tiles_per_cta, (double)h[32 + k] / tiles_per_cta);
   };
-  // variant: the single-CTA kernel (cta_group::1) is the default -- measured faster (50.7 vs 61.6 ms at 257^3): the
-  // layer-0 chunk hand-off is on the critical path and every cross-CTA arrival adds latency to it.
-  // MONOPORT_B200_TC_CG=2 selects the 2-CTA cluster kernel (halves per-SM weight ingest; kept for round 2).
+  // variant: CTA group.  MONOPORT_B200_TC_CG=1|2 overrides.  Default: 1 for the v2 program (its layer-0 chunk hand-off
+  // is on the critical path and every cross-CTA arrival adds latency to it), see below for v3.
   static const int forced = [] { const char* v = getenv("MONOPORT_B200_TC_CG"); return v ? atoi(v) : 0; }();
-  const int cg = forced == 2 ? 2 : 1;
+  // program: v3 (layer 0 hoisted to texels, needs the per-frame G0 GEMM) for large queries, v2 for small ones where the
+  // 4.3 GFLOP fp32 GEMM would dominate (octree levels).  MONOPORT_B200_TC_VER=2|3 overrides.
+  static const int forced_ver = [] { const char* v = getenv("MONOPORT_B200_TC_VER"); return v ? atoi(v) : 0; }();
+  const int ver = forced_ver == 2 ? 2 : (forced_ver == 3 ? 3 : (src.n >= (1ll << 20) ? 3 : 2));
+  if (ver == 3) {
+    const long long HW = (long long)feat->H * feat->W;
+    if (!feat->g0 || feat->g0_n != kL0) {
+      if (feat->g0) cudaFree(feat->g0);
+      feat->g0 = nullptr;
+      MP_CUDA(cudaMalloc(&feat->g0, (size_t)HW * kL0 * sizeof(__half)));
+      feat->g0_n = kL0;
+      feat->g0_owner = nullptr;
+    }
+    if (feat->g0_owner != (const void*)mlp || feat->g0_version != feat->version) {
+      dim3 gg((unsigned)((HW + 127) / 128), kL0 / 128);
+      g0_kernel<<<gg, 256, 0, st>>>(feat->nhwc32, pk->d_w0f, feat->g0, (int)HW, kL0, kC);
+      MP_CUDA(cudaGetLastError());
+      feat->g0_owner = (const void*)mlp;
+      feat->g0_version = feat->version;
+    }
+    prm.g0 = feat->g0;
+    prm.d_bias0 = pk->d_bias0;
+    prm.d_wz0 = pk->d_wz0;
+    prm.wstream = pk->w3stream;
+    prm.wstream2[0] = pk->w3stream2[0];
+    prm.wstream2[1] = pk->w3stream2[1];
+  }
+  const int cg = forced == 2 ? 2 : (forced == 1 ? 1 : 1);
   if (cg == 1) {
     const int grid = (int)(tiles < (long long)sms ? tiles : sms);
-    query_tc_kernel<1><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
+    if (ver == 3) query_tc3_kernel<1><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
+    else query_tc_kernel<1><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
     MP_CUDA(cudaGetLastError());
     report(grid);
     return MP_OK;
@@ -937,7 +1603,8 @@ int mp_launch_query_tc(const mp_mlp* mlp, const mp_feat* feat, const MpPointSrc&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc_kernel<2>, prm, src, cal, dst));
+  if (ver == 3) MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc3_kernel<2>, prm, src, cal, dst));
+  else MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc_kernel<2>, prm, src, cal, dst));
   report(2 * clusters);
   return MP_OK;
 }
