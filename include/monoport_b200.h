@@ -46,6 +46,9 @@ extern "C" {
 #define MP_MODE_FP32 0   /* CUDA-core fp32 everywhere (|err| ~1e-6 vs the reference)                 */
 #define MP_MODE_TC 1     /* tcgen05 fp16 operands / fp32 TMEM accumulators, last layer fp32 (<=1e-4)   */
 #define MP_MODE_AUTO 2   /* TC when the head/feature shape is supported by the tcgen05 kernel, else FP32 */
+/* MP_MODE_TC picks the tensor-core program by query size; these two pin it (tests / benchmarks):                    */
+#define MP_MODE_TC_V2 3  /* all five layers per point (layer 0 recomputed for the second half of layer 1)            */
+#define MP_MODE_TC_V3 4  /* layer 0 hoisted to texels (per-frame W0.F product, sampled per point); default >= 2^20 pts */
 
 const char* mp_last_error(void);
 int mp_version(void);

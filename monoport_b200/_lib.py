@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmonoport_b200.so")
 
 MP_OK = 0
-MODE_FP32, MODE_TC, MODE_AUTO = 0, 1, 2
+MODE_FP32, MODE_TC, MODE_AUTO, MODE_TC_V2, MODE_TC_V3 = 0, 1, 2, 3, 4
 LAST_NONE, LAST_SIGMOID, LAST_TANH = 0, 1, 2
 PROJ_ORTHOGONAL, PROJ_PERSPECTIVE = 0, 1
 

@@ -214,12 +214,12 @@ void mp_fill_grid_geom(MpPointSrc& s, int res, int node_stride, int r_final, con
 int mp_query_dispatch(mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal, const MpOutDst& dst,
                       int mode, cudaStream_t st) {
   if (mode == MP_MODE_AUTO) mode = mlp->tc_ok ? MP_MODE_TC : MP_MODE_FP32;
-  if (mode == MP_MODE_TC) {
+  if (mode == MP_MODE_TC || mode == MP_MODE_TC_V2 || mode == MP_MODE_TC_V3) {
     if (!mlp->tc_ok) {
       mp_set_error("MP_MODE_TC requested but the tcgen05 kernel does not support this head/device");
       return MP_E_UNSUPPORTED;
     }
-    return mp_launch_query_tc(mlp, feat, src, cal, dst, st);
+    return mp_launch_query_tc(mlp, feat, src, cal, dst, st, mode == MP_MODE_TC_V2 ? 2 : (mode == MP_MODE_TC_V3 ? 3 : 0));
   }
   if (mode != MP_MODE_FP32) {
     mp_set_error("bad mode %d", mode);

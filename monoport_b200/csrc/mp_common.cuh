@@ -199,7 +199,7 @@ __device__ __forceinline__ float mp_lrelu(float v) { return v > 0.f ? v : v * MP
 int mp_launch_query_fp32(const mp_mlp* mlp, const mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
                          const MpOutDst& dst, cudaStream_t st);
 int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
-                       const MpOutDst& dst, cudaStream_t st);
+                       const MpOutDst& dst, cudaStream_t st, int program /* 0 auto, 2, 3 */);
 int mp_tc_prepare(mp_mlp* mlp);     // builds mlp->tc; sets tc_ok
 void mp_tc_release(mp_mlp* mlp);
 

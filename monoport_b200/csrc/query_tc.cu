@@ -760,7 +760,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       tc::mbar_init(bars + B_WPEER + s, 1);
     }
     constexpr int kW = 8 * CG;
-    tc::mbar_init(bars + B_XREADY, kW);
+    tc::mbar_init(bars + B_XREADY, 2 * CG);        // the two sampler warps of every CTA
     tc::mbar_init(bars + B_H0_READY0, kW);
     tc::mbar_init(bars + B_H0_READY1, kW);
     tc::mbar_init(bars + B_H0_FREE0, 1);
@@ -772,7 +772,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     tc::mbar_init(bars + B_ACC3_FULL, 1);
     tc::mbar_init(bars + B_TILE_DONE, 4 * CG);
     tc::mbar_init(bars + B_XFREE, 1);
-    tc::mbar_init(bars + B_ACC0_FULL0, 1);
+    tc::mbar_init(bars + B_ACC0_FULL0, 2);         // v3: "per-point scalars of this tile are in smem" (CTA-local)
     tc::mbar_init(bars + B_ACC0_FULL1, 1);
     tc::fence_barrier_init();
   }
@@ -928,14 +928,142 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       }
       if (prof) prof[P_TOTAL] = (unsigned long long)(clock64() - t_begin);
     }
+  } else if (warp == 2 || warp == 3) {
+    // ============================== samplers: X (skip operand) + per-point scalars ==============================
+    // Two warps, 64 points each, run one tile ahead of the epilogue: they only need X to be dead (B_XFREE).
+    const int sw = warp - 2;
+    const int res = prm.res;
+    uint32_t c_xfree = 0;
+    const int cbase = lane * 8;
+    float w4s[kMaxRes][8];
+#pragma unroll
+    for (int r = 0; r < kMaxRes; ++r)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w4s[r][j] = (r < res) ? __ldg(prm.w4s + r * kC + cbase + j) : 0.f;
+    for (long long g = g0; g < n_groups; g += gstep) {
+      const long long tile = g * CG + rank;
+      const long long p0 = tile * kTile;
+      if (g != g0) wait_bar(bars, B_XFREE, c_xfree);
+#pragma unroll 1
+      for (int grp = 0; grp < 4; ++grp) {
+        const int pbase = sw * 64 + grp * 16;
+        int my_off[4];
+        float my_wgt[4];
+        float my_zf;
+        bool my_in;
+        {
+          const long long i = p0 + pbase + (lane & 15);
+          float u = 0.f, v = 0.f, w = 0.f;
+          const bool valid = i < n;
+          if (valid) {
+            float x, y, z;
+            mp_load_point(src, i, x, y, z);
+            mp_project(cal, x, y, z, u, v, w);
+          }
+          my_in = valid && (u >= -1.f) && (u <= 1.f) && (v >= -1.f) && (v <= 1.f);
+          MpTaps t = mp_taps(valid ? u : 0.f, valid ? v : 0.f, prm.H, prm.W);
+          const bool dead = !valid || !(u == u) || !(v == v);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) { my_off[a] = dead ? 0 : t.off[a]; my_wgt[a] = dead ? 0.f : t.wgt[a]; }
+          my_zf = w * cal.z_scale;
+        }
+        float s4part[kMaxRes][16];
+#pragma unroll
+        for (int q0 = 0; q0 < 16; q0 += 4) {
+          uint4 raw[4][4];
+          float wgt[4][4];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq)
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const int off = __shfl_sync(0xffffffffu, my_off[a], q0 + qq);
+              wgt[qq][a] = __shfl_sync(0xffffffffu, my_wgt[a], q0 + qq);
+              raw[qq][a] = __ldg(reinterpret_cast<const uint4*>(prm.feat + (size_t)off * kC + cbase));
+            }
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const int p = pbase + q0 + qq;
+            float2 acc[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const __half2* h2 = reinterpret_cast<const __half2*>(&raw[qq][a]);
+              const float2 w2 = make_float2(wgt[qq][a], wgt[qq][a]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h2[j]);
+                acc[j] = (a == 0) ? __fmul2_rn(f, w2) : __ffma2_rn(f, w2, acc[j]);
+              }
+            }
+            uint4 packed;
+            packed.x = tc::pack_half2(acc[0].x, acc[0].y);
+            packed.y = tc::pack_half2(acc[1].x, acc[1].y);
+            packed.z = tc::pack_half2(acc[2].x, acc[2].y);
+            packed.w = tc::pack_half2(acc[3].x, acc[3].y);
+            const int kb = lane >> 3;
+            *reinterpret_cast<uint4*>(smem + Smem::X + kb * 16384 + tc::sw128_offset(p, (lane & 7) * 8)) = packed;
+#pragma unroll
+            for (int r = 0; r < kMaxRes; ++r) {
+              float sacc = 0.f;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                sacc = fmaf(w4s[r][2 * j], acc[j].x, sacc);
+                sacc = fmaf(w4s[r][2 * j + 1], acc[j].y, sacc);
+              }
+              s4part[r][q0 + qq] = sacc;
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < kMaxRes; ++r) {
+          if (r < res) {
+            float v16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v16[j] = s4part[r][j] + __shfl_xor_sync(0xffffffffu, s4part[r][j], 16);
+            float v8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const bool up = lane & 8;
+              const float keep = up ? v16[j + 8] : v16[j], send = up ? v16[j] : v16[j + 8];
+              v8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            float v4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool up = lane & 4;
+              const float keep = up ? v8[j + 4] : v8[j], send = up ? v8[j] : v8[j + 4];
+              v4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            float v2[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const bool up = lane & 2;
+              const float keep = up ? v4[j + 2] : v4[j], send = up ? v4[j] : v4[j + 2];
+              v2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            const bool up = lane & 1;
+            const float keep = up ? v2[1] : v2[0], send = up ? v2[0] : v2[1];
+            const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            if (lane < 16) s_s4[r * kTile + pbase + lane] = tot + __ldg(prm.w4z + r) * my_zf + __ldg(prm.b4 + r);
+          }
+        }
+        if (lane < 16) {
+          s_zf[pbase + lane] = my_zf;
+          s_in[pbase + lane] = my_in ? 1.f : 0.f;
+        }
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(bars + B_ACC0_FULL0);        // scalars ready (CTA-local, release)
+      warp_arrive_leader<CG>(bars + B_XREADY, lane);
+    }
   } else if (warp >= 4) {
-    // ============================== workers ==============================
+    // ============================== workers: layer-0 chunk generators + epilogue ==============================
     const int wk = warp - 4;
     const int wg = wk >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    uint32_t c_xfree = 0, c_h0free[2] = {0, 0}, c_acc1full = 0, c_acc2full = 0, c_acc3full = 0;
+    uint32_t c_sready = 0, c_h0free[2] = {0, 0}, c_acc1full = 0, c_acc2full = 0, c_acc3full = 0;
     const int res = prm.res;
     if (!(warp == 4 && lane == 0)) prof = nullptr;
     const int l16 = lane & 15, hw = lane >> 4;
@@ -1003,24 +1131,24 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
 #pragma unroll
           for (int ps = 0; ps < 4; ++ps) {
             const int p = wk * 16 + (batch * 4 + ps) * 2 + hw;
-            float acc[8];
+            // acc = b0 + w0z * z  (+ 4 taps), two channels per packed-fp32 instruction
+            const float2 zq2 = make_float2(zq[ps], zq[ps]);
+            float2 acc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              acc[j] = __ffma2_rn(make_float2(z8[2 * j], z8[2 * j + 1]), zq2, make_float2(b8[2 * j], b8[2 * j + 1]));
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
               const __half2* h2 = reinterpret_cast<const __half2*>(&raw[ps][a]);
+              const float2 w2 = make_float2(wgt[ps][a], wgt[ps][a]);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h2[j]);
-                acc[2 * j] = (a == 0) ? f.x * wgt[ps][a] : acc[2 * j] + f.x * wgt[ps][a];
-                acc[2 * j + 1] = (a == 0) ? f.y * wgt[ps][a] : acc[2 * j + 1] + f.y * wgt[ps][a];
-              }
+              for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(__half22float2(h2[j]), w2, acc[j]);
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += fmaf(z8[j], zq[ps], b8[j]);
             uint4 pk;
-            pk.x = act_pack(acc[0], acc[1]);
-            pk.y = act_pack(acc[2], acc[3]);
-            pk.z = act_pack(acc[4], acc[5]);
-            pk.w = act_pack(acc[6], acc[7]);
+            pk.x = act_pack(acc[0].x, acc[0].y);
+            pk.y = act_pack(acc[1].x, acc[1].y);
+            pk.z = act_pack(acc[2].x, acc[2].y);
+            pk.w = act_pack(acc[3].x, acc[3].y);
             *reinterpret_cast<uint4*>(dstp + tc::sw128_offset(p, (l16 & 7) * 8)) = pk;
           }
         }
@@ -1030,108 +1158,14 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       };
       gen_chunk(0);
       gen_chunk(1);
-      // ---- X (skip operand): previous tile's last reader (layer-3 skip MMAs) must be done
-      if (g != g0) { PROF_T0(); wait_bar(bars, B_XFREE, c_xfree); PROF_ADD(P_W_XFREE); }
-      {
-        const long long t_sample0 = prof ? clock64() : 0;
-        const int cbase = lane * 8;
-        float w4s[kMaxRes][8];
-#pragma unroll
-        for (int r = 0; r < kMaxRes; ++r)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) w4s[r][j] = (r < res) ? __ldg(prm.w4s + r * kC + cbase + j) : 0.f;
-        float s4part[kMaxRes][16];
-#pragma unroll
-        for (int q0 = 0; q0 < 16; q0 += 4) {
-          uint4 raw[4][4];
-          float wgt[4][4];
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq)
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              const int off = __shfl_sync(0xffffffffu, my_off[a], q0 + qq);
-              wgt[qq][a] = __shfl_sync(0xffffffffu, my_wgt[a], q0 + qq);
-              raw[qq][a] = __ldg(reinterpret_cast<const uint4*>(prm.feat + (size_t)off * kC + cbase));
-            }
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            const int p = wk * 16 + q0 + qq;
-            float acc[8];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              const __half2* h2 = reinterpret_cast<const __half2*>(&raw[qq][a]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h2[j]);
-                acc[2 * j] = (a == 0) ? f.x * wgt[qq][a] : acc[2 * j] + f.x * wgt[qq][a];
-                acc[2 * j + 1] = (a == 0) ? f.y * wgt[qq][a] : acc[2 * j + 1] + f.y * wgt[qq][a];
-              }
-            }
-            uint4 packed;
-            packed.x = tc::pack_half2(acc[0], acc[1]);
-            packed.y = tc::pack_half2(acc[2], acc[3]);
-            packed.z = tc::pack_half2(acc[4], acc[5]);
-            packed.w = tc::pack_half2(acc[6], acc[7]);
-            const int kb = lane >> 3;
-            *reinterpret_cast<uint4*>(smem + Smem::X + kb * 16384 + tc::sw128_offset(p, (lane & 7) * 8)) = packed;
-#pragma unroll
-            for (int r = 0; r < kMaxRes; ++r) {
-              float sacc = 0.f;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) sacc = fmaf(w4s[r][j], acc[j], sacc);
-              s4part[r][q0 + qq] = sacc;
-            }
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < kMaxRes; ++r) {
-          if (r < res) {
-            float v16[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v16[j] = s4part[r][j] + __shfl_xor_sync(0xffffffffu, s4part[r][j], 16);
-            float v8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const bool up = lane & 8;
-              const float keep = up ? v16[j + 8] : v16[j], send = up ? v16[j] : v16[j + 8];
-              v8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-            float v4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const bool up = lane & 4;
-              const float keep = up ? v8[j + 4] : v8[j], send = up ? v8[j] : v8[j + 4];
-              v4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-            float v2[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const bool up = lane & 2;
-              const float keep = up ? v4[j + 2] : v4[j], send = up ? v4[j] : v4[j + 2];
-              v2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-            const bool up = lane & 1;
-            const float keep = up ? v2[1] : v2[0], send = up ? v2[0] : v2[1];
-            const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-            if (lane < 16) s_s4[r * kTile + wk * 16 + lane] = tot + __ldg(prm.w4z + r) * my_zf + __ldg(prm.b4 + r);
-          }
-        }
-        if (lane < 16) {
-          s_zf[wk * 16 + lane] = my_zf;
-          s_in[wk * 16 + lane] = my_in ? 1.f : 0.f;
-        }
-        tc::fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (prof) prof[P_W_SAMPLE] += (unsigned long long)(clock64() - t_sample0);
-      }
+      for (int c = 2; c < 8; ++c) gen_chunk(c);
+      // per-point scalars of this tile (written by the sampler warps)
+      { PROF_T0(); wait_bar(bars, B_ACC0_FULL0, c_sready); PROF_ADD(P_W_XFREE); }
       const float zf = s_zf[row];
       const float inimg = s_in[row];
       float s4[kMaxRes];
 #pragma unroll
       for (int r = 0; r < kMaxRes; ++r) s4[r] = (r < res) ? s_s4[r * kTile + row] : 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      warp_arrive_leader<CG>(bars + B_XREADY, lane);
-      for (int c = 2; c < 8; ++c) gen_chunk(c);
 
       auto load_pre = [&](uint32_t col, int ch0, float (&o)[32]) {
         uint32_t v[32];
@@ -1500,7 +1534,7 @@ void mp_tc_release(mp_mlp* mlp) {
 }
 
 int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
-                       const MpOutDst& dst, cudaStream_t st) {
+                       const MpOutDst& dst, cudaStream_t st, int program) {
   if (src.n <= 0) return MP_OK;
   const TcPack* pk = static_cast<const TcPack*>(mlp->tc);
   if (!pk || !mlp->tc_ok) {
@@ -1554,7 +1588,8 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
   // program: v3 (layer 0 hoisted to texels, needs the per-frame G0 GEMM) for large queries, v2 for small ones where the
   // 4.3 GFLOP fp32 GEMM would dominate (octree levels).  MONOPORT_B200_TC_VER=2|3 overrides.
   static const int forced_ver = [] { const char* v = getenv("MONOPORT_B200_TC_VER"); return v ? atoi(v) : 0; }();
-  const int ver = forced_ver == 2 ? 2 : (forced_ver == 3 ? 3 : (src.n >= (1ll << 20) ? 3 : 2));
+  const int want = program ? program : forced_ver;
+  const int ver = want == 2 ? 2 : (want == 3 ? 3 : (src.n >= (1ll << 20) ? 3 : 2));
   if (ver == 3) {
     const long long HW = (long long)feat->H * feat->W;
     if (!feat->g0 || feat->g0_n != kL0) {

@@ -135,3 +135,41 @@ def reconstruction(net, cuda, calib_tensor, resolution, b_min, b_max, use_octree
         T = torch.as_tensor(transform, dtype=torch.float32, device=verts.device)
         verts = verts @ T[:3, :3].T + T[:3, 3]
     return verts, faces, None, None
+
+
+@torch.no_grad()
+def make_mat_color(resolution, b_min, b_max, device):
+    """Voxel index -> world matrix of the demo (RTL/main.py:201-210): diag((b_max-b_min)/R) with translation b_min."""
+    b_min = torch.as_tensor(np.asarray(b_min, dtype=np.float32)).view(3)
+    b_max = torch.as_tensor(np.asarray(b_max, dtype=np.float32)).view(3)
+    mat = torch.eye(4, dtype=torch.float32)
+    length = b_max - b_min
+    for a in range(3):
+        mat[a, a] = length[a] / resolution
+    mat[0:3, 3] = b_min
+    return mat.to(device)
+
+
+@torch.no_grad()
+def colorization(netC, feat_tensor_C, X, Y, Z, calib_tensor, norm=None, resolution=257, b_min=(-1, -1, -1),
+                 b_max=(1, 1, 1), canvas=None):
+    """Direct rendering of the visible surface (RTL/main.py:212-249): either normals as colours, or netC queried at the
+    visible vertices (X, Y, R - Z) mapped to world space by mat_color, `pred * 0.5 + 0.5`, scattered into an [R,R,3]
+    canvas.  Returns None when there is no surface (X is None), like the reference."""
+    if X is None:
+        return None
+    device = calib_tensor.device
+    if canvas is None:
+        canvas = torch.ones((resolution, resolution, 3), dtype=torch.float32, device=device)
+    image = canvas.clone()
+    if norm is not None:
+        image[X, Y, :] = ((norm + 1) / 2).clamp(0, 1)
+        return image
+    from .modeling.geometry import orthogonal
+    verts = torch.stack([X.float(), Y.float(), resolution - Z.float()], dim=1)          # RTL/main.py:231-233
+    samples = verts.unsqueeze(0).permute(0, 2, 1).contiguous()                          # [1,3,N]
+    samples = orthogonal(samples, make_mat_color(resolution, b_min, b_max, device).unsqueeze(0))
+    feats = [[f.to(device) for f in fs] for fs in feat_tensor_C]
+    preds = netC.query(feats, points=samples, calibs=calib_tensor)[0]
+    image[X, Y, :] = (preds[0] * 0.5 + 0.5).t()
+    return image

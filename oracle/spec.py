@@ -448,3 +448,23 @@ def analytic_volume(R, kind="sphere"):
     else:
         raise ValueError(kind)
     return np.clip(np.float32(0.5) + np.float32(4.0) * f, np.float32(0), np.float32(1)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
+# colorization  --  RTL/main.py:212-249 (restated; RTL/main.py itself cannot be imported: flask, cv2, GL ...)
+# ----------------------------------------------------------------------------------------------
+@torch.no_grad()
+def colorization_ref(query_c, X, Y, Z, calib, resolution=257, b_min=(-1, -1, -1), b_max=(1, 1, 1), norm=None):
+    """query_c(points[1,3,N], calib) -> [3,N] in [-1,1] (netC).  Returns the [R,R,3] image."""
+    image = torch.ones((resolution, resolution, 3), dtype=torch.float32)
+    if norm is not None:
+        image[X, Y, :] = ((norm + 1) / 2).clamp(0, 1)
+        return image
+    b_min = torch.tensor(b_min, dtype=torch.float32)
+    b_max = torch.tensor(b_max, dtype=torch.float32)
+    scale = (b_max - b_min) / resolution
+    verts = torch.stack([X.float(), Y.float(), resolution - Z.float()], 1)
+    world = verts * scale[None] + b_min[None]
+    preds = query_c(world.t().contiguous()[None], calib)
+    image[X, Y, :] = (preds * 0.5 + 0.5).t()
+    return image

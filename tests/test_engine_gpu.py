@@ -95,7 +95,7 @@ def test_fused_engine_equals_generic_engine_with_mlp():
     feats = [[feat.cuda()]]
     b = np.array([[-1.0, -1.0, -1.0]], dtype=np.float32)
     res = [17, 33, 65, 129]
-    for mode in (["fp32", "tc"] if net.surface_classifier.tc_supported() else ["fp32"]):
+    for mode in (["fp32", "tc", "tc_v3"] if net.surface_classifier.tc_supported() else ["fp32"]):
         net.precision = mode
         for faster in (True, False):
             fused = Seg3dLossless(make_query_func(net), b, -b, res, balance_value=0.5, faster=faster).to("cuda")
@@ -184,3 +184,26 @@ def test_reconstruction_dense_vs_octree():
     assert dense != -1 and octree != -1
     assert torch.equal(dense[1], octree[1]) and torch.allclose(dense[0], octree[0], atol=1e-5)
     assert dense[0].abs().max() <= 1.0
+
+
+def test_colorization_matches_restatement():
+    """netC colour pass of the demo (RTL/main.py:212-249): visible vertices -> world -> netC.query -> canvas."""
+    from monoport_b200.recon import forward_vertices, colorization
+    Wc, bc = spec.make_weights(spec.C_CHANNELS, 21)
+    featc = spec.make_feat(512, 128, 128, 22)
+    netC = build_net("C", Wc, bc)
+    vol = torch.from_numpy(spec.analytic_volume(65, "ellipsoid"))[None, None]
+    cal = spec.scene_calib(20, 33)
+    X, Y, Z, n = forward_vertices(vol.cuda(), "front")
+    img = colorization(netC, [[featc.cuda()]], X, Y, Z, cal.cuda(), resolution=65)
+
+    def qc(points, calib):
+        return spec.query_ref(featc, points, calib, Wc, bc, spec.LAST_TANH)
+    Xo, Yo, Zo, _ = spec.forward_vertices_ref(vol, "front")
+    want = spec.colorization_ref(qc, Xo, Yo, Zo, cal, resolution=65)
+    assert img.shape == (65, 65, 3)
+    assert (img.cpu() - want).abs().max().item() <= 5e-5
+    imgn = colorization(netC, None, X, Y, Z, cal.cuda(), norm=n, resolution=65)
+    wantn = spec.colorization_ref(None, Xo, Yo, Zo, cal, resolution=65, norm=spec.forward_vertices_ref(vol, "front")[3])
+    assert torch.allclose(imgn.cpu(), wantn, atol=1e-6, equal_nan=True)
+    assert colorization(netC, None, None, None, None, cal.cuda()) is None
