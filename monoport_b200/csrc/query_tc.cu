@@ -1589,7 +1589,8 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
   // 4.3 GFLOP fp32 GEMM would dominate (octree levels).  MONOPORT_B200_TC_VER=2|3 overrides.
   static const int forced_ver = [] { const char* v = getenv("MONOPORT_B200_TC_VER"); return v ? atoi(v) : 0; }();
   const int want = program ? program : forced_ver;
-  const int ver = want == 2 ? 2 : (want == 3 ? 3 : (src.n >= (1ll << 20) ? 3 : 2));
+  // (a device-side count means an octree node list: src.n is only a capacity bound there, and the lists are small)
+  const int ver = want == 2 ? 2 : (want == 3 ? 3 : ((src.n >= (1ll << 20) && !src.count_dev) ? 3 : 2));
   if (ver == 3) {
     const long long HW = (long long)feat->H * feat->W;
     if (!feat->g0 || feat->g0_n != kL0) {
