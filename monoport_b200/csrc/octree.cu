@@ -18,10 +18,6 @@
 
 namespace {
 
-struct LevelGeom {
-  int res_c, res_f;
-};
-
 __device__ __forceinline__ float up_axis(float a, float b, bool odd) {
   // align_corners=True 2x: even fine index -> coarse node; odd -> 0.5*a + 0.5*b (exact products, one rounding)
   return odd ? __fadd_rn(__fmul_rn(0.5f, a), __fmul_rn(0.5f, b)) : a;
@@ -131,15 +127,6 @@ __global__ void scatter_kernel(const int32_t* __restrict__ idx, const int32_t* c
     if (write_vals) vol[node] = nv;
     if (known) known[node] = 1;
   }
-}
-
-// before a fused query scatters in place we must remember the interpolated values to detect conflicts
-__global__ void gather_kernel(const int32_t* __restrict__ idx, const int32_t* count_dev, long long n_max,
-                              const float* __restrict__ vol, float* __restrict__ out) {
-  long long n = n_max;
-  if (count_dev) { const long long c = *count_dev; n = c < n ? c : n; }
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = vol[idx[i]];
 }
 
 // candidates = unknown nodes with a conflict in their 27-neighbourhood (transposed output); clears nothing
@@ -397,8 +384,6 @@ static int build_level_list(mp_octree* h, int level, cudaStream_t st) {
     // count = k exactly
     const int32_t kk = (int32_t)k;
     MP_CUDA(cudaMemcpyAsync(h->count, &kk, sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    long long* stat = h->stats + level;
-    (void)stat;
     return MP_OK;
   }
   if (interp_only) {

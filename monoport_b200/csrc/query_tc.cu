@@ -126,11 +126,6 @@ enum Bar { B_WFULL = 0, B_WEMPTY = kStages, B_WPEER = 2 * kStages, B_XREADY = 3 
 static_assert(B_XFREE + 1 == Smem::NumBars, "barrier count");
 static_assert(Smem::Total + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
 
-struct PhaseCounter {   // number of completed waits on a barrier -> parity to wait for next
-  uint32_t n = 0;
-  __device__ __forceinline__ uint32_t parity() const { return n & 1u; }
-};
-
 __device__ __forceinline__ void wait_bar(uint64_t* bars, int which, uint32_t& count) {
   tc::mbar_wait(bars + which, count & 1u);
   ++count;

@@ -159,3 +159,39 @@ def test_full_size_properties():
         v2 = net.query_grid(feat.cuda(), cal.cuda(), R, (-1, -1, -1), (1, 1, 1), z0=100, nz=40)
         assert (v2 - vol[100:140]).abs().max().item() <= 1.5e-4
         net.precision = "auto"
+
+
+def test_concurrent_queries_from_threads():
+    """The demo runs every pipeline stage in its own Python thread (RTL/dataloader.py:734-751): a netG query and a netC
+    query on different streams/threads must not interfere (all scratch lives in the handles)."""
+    import threading
+    cg = load_query_case("g_rot33")
+    cc = load_query_case("c_rot33")
+    netG, netC = build_net(cg), build_net(cc)
+    netG.precision = "auto"
+    fg, fc = cg["feat"].cuda(), cc["feat"].cuda()
+    pg, pc = cg["points"].cuda(), cc["points"].cuda()
+    calg, calc = cg["calib"].cuda(), cc["calib"].cuda()
+    # warm (handle creation is not what is being raced)
+    netG.query([[fg]], pg, calibs=calg); netC.query([[fc]], pc, calibs=calc)
+    torch.cuda.synchronize()
+    errs = []
+
+    def run(net, f, p, cal, want, tol, n_iter):
+        try:
+            torch.cuda.set_device(0)
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(n_iter):
+                    out = net.query([[f]], p, calibs=cal)[0][0]
+                st.synchronize()
+                e = (out.cpu() - want).abs().max().item()
+                if e > tol:
+                    errs.append(e)
+        except Exception as ex:   # pragma: no cover
+            errs.append(repr(ex))
+
+    tg = threading.Thread(target=run, args=(netG, fg, pg, calg, cg["expected"], 1e-4, 20))
+    tcol = threading.Thread(target=run, args=(netC, fc, pc, calc, cc["expected"], 2e-5, 20))
+    tg.start(); tcol.start(); tg.join(); tcol.join()
+    assert not errs, errs
