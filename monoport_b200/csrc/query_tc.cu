@@ -37,7 +37,6 @@
 #include "mp_common.cuh"
 #include "tc_ptx.cuh"
 #include <stdlib.h>
-#include <type_traits>
 
 namespace {
 
@@ -853,7 +852,12 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       for (long long g = g0; g < n_groups; g += gstep) {
         // acc1 = [0,512) overlaps the previous tile's H2 (readers already issued, in order), acc2 (drained before
         // B_H2_READY, waited) and acc3 (drained by the fp32 tail: B_TILE_DONE)
-        bool need_tile_done = g != g0;
+        if (g != g0) {
+          PROF_T0();
+          wait_leader<CG>(bars, B_TILE_DONE, c_tiledone);
+          PROF_ADD(P_ACC1DRAINED);
+          tc::tcgen05_fence_after();
+        }
         bool first1[2] = {true, true};
         // ---- layer 1, hidden part: 8 sampled layer-0 chunks x 2 K-blocks x 2 output halves
         for (int c = 0; c < 8; ++c) {
@@ -863,15 +867,6 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           for (int kb = 0; kb < 2; ++kb)
             for (int nh = 0; nh < 2; ++nh) {
               const uint32_t w = next_stage();
-              if (nh == 1 && need_tile_done) {
-                // [384,512) still holds the previous tile's acc3 until its fp32 tail has drained it; the lower half of
-                // acc1 does not overlap it, so only the first MMA into [256,512) has to wait
-                PROF_T0();
-                wait_leader<CG>(bars, B_TILE_DONE, c_tiledone);
-                PROF_ADD(P_ACC1DRAINED);
-                tc::tcgen05_fence_after();
-                need_tile_done = false;
-              }
               kblock_ss(tbase + cAcc1 + nh * 256, sH0 + b * 32768 + kb * 16384, w, idesc256, first1[nh]);
               release_stage();
             }
@@ -1112,12 +1107,14 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         const float b8[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
         const float z8[8] = {zA.x, zA.y, zA.z, zA.w, zB.x, zB.y, zB.z, zB.w};
         uint8_t* dstp = smem + Smem::H0 + b * 32768 + (l16 >> 3) * 16384;
-        // 8 passes of 2 points, software-pipelined in batches of 2 passes: the gathers of batch k+1 are in flight while
-        // batch k is interpolated, activated and stored
-        auto issue = [&](int bt, uint4 (&raw)[2][4], float (&wgt)[2][4], float (&zq)[2]) {
+#pragma unroll 1
+        for (int batch = 0; batch < 2; ++batch) {
+          uint4 raw[4][4];
+          float wgt[4][4];
+          float zq[4];
 #pragma unroll
-          for (int ps = 0; ps < 2; ++ps) {
-            const int q = (bt * 2 + ps) * 2 + hw;
+          for (int ps = 0; ps < 4; ++ps) {
+            const int q = (batch * 4 + ps) * 2 + hw;
             zq[ps] = __shfl_sync(0xffffffffu, my_zf, q);
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
@@ -1126,11 +1123,9 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
               raw[ps][a] = __ldg(reinterpret_cast<const uint4*>(prm.g0 + (size_t)off * kL0 + ch));
             }
           }
-        };
-        auto finish = [&](int bt, const uint4 (&raw)[2][4], const float (&wgt)[2][4], const float (&zq)[2]) {
 #pragma unroll
-          for (int ps = 0; ps < 2; ++ps) {
-            const int p = wk * 16 + (bt * 2 + ps) * 2 + hw;
+          for (int ps = 0; ps < 4; ++ps) {
+            const int p = wk * 16 + (batch * 4 + ps) * 2 + hw;
             // acc = b0 + w0z * z  (+ 4 taps), two channels per packed-fp32 instruction
             const float2 zq2 = make_float2(zq[ps], zq[ps]);
             float2 acc[4];
@@ -1151,18 +1146,6 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             pk.w = act_pack(acc[3].x, acc[3].y);
             *reinterpret_cast<uint4*>(dstp + tc::sw128_offset(p, (l16 & 7) * 8)) = pk;
           }
-        };
-        {
-          uint4 rawA[2][4], rawB[2][4];
-          float wA[2][4], wB[2][4], zqA[2], zqB[2];
-          issue(0, rawA, wA, zqA);
-          issue(1, rawB, wB, zqB);
-          finish(0, rawA, wA, zqA);
-          issue(2, rawA, wA, zqA);
-          finish(1, rawB, wB, zqB);
-          issue(3, rawB, wB, zqB);
-          finish(2, rawA, wA, zqA);
-          finish(3, rawB, wB, zqB);
         }
         tc::fence_proxy_async_smem();
         warp_arrive_leader<CG>(bars + B_H0_READY0 + b, lane);
@@ -1179,38 +1162,34 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
 #pragma unroll
       for (int r = 0; r < kMaxRes; ++r) s4[r] = (r < res) ? s_s4[r * kTile + row] : 0.f;
 
+      auto load_pre = [&](uint32_t col, int ch0, float (&o)[32]) {
+        uint32_t v[32];
+        tc::tmem_ld32(tbase + lane_base + col, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          o[j] = __uint_as_float(v[j]) + fmaf(prm.wz_all[ch0 + j], zf, prm.bias_all[ch0 + j]);
+      };
       // ---- layer 1 (512 columns) -> H1, drained IN PLACE: warpgroup 0 walks [0,256) upwards into [0,128), warpgroup 1
       //      walks [256,512) downwards into [384,512); the packed destination of a group never reaches columns that are
-      //      still unread, and [128,384) comes out free for acc2.  The warpgroup is a template argument so that every
-      //      channel index is a compile-time constant: bias and depth weights become constant-bank operands of the FMAs.
+      //      still unread, and [128,384) comes out free for acc2.
       { PROF_T0(); wait_bar(bars, B_ACC1_FULL, c_acc1full); PROF_ADD(P_W_ACC1FULL); }
       tc::tcgen05_fence_after();
       {
         PROF_T0();
-        auto drain1 = [&](auto wg_tag) {
-          constexpr int WG = decltype(wg_tag)::value;
-          // software-pipelined: the TMEM load of group g+1 is in flight while group g is activated, packed and stored
-          uint32_t v[2][32];
-          tc::tmem_ld32(tbase + lane_base + cAcc1 + WG * 256 + (WG == 0 ? 0 : 7) * 32, v[0]);
+#pragma unroll 1
+        for (int gi = 0; gi < 8; ++gi) {
+          const int gq = (wg == 0) ? gi : 7 - gi;
+          const int lc = wg * 256 + gq * 32;                 // accumulator column == layer-1 output channel
+          float o[32];
+          load_pre(cAcc1 + lc, side_off(1) + lc, o);
+          uint32_t pk[16];
 #pragma unroll
-          for (int gi = 0; gi < 8; ++gi) {
-            const int lc = WG * 256 + (WG == 0 ? gi : 7 - gi) * 32;     // accumulator column == layer-1 output channel
-            tc::tmem_ld_wait();
-            if (gi + 1 < 8) tc::tmem_ld32(tbase + lane_base + cAcc1 + WG * 256 + (WG == 0 ? gi + 1 : 6 - gi) * 32, v[(gi + 1) & 1]);
-            const int ch0 = side_off(1) + lc;
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float a = __uint_as_float(v[gi & 1][2 * j]) + fmaf(prm.wz_all[ch0 + 2 * j], zf, prm.bias_all[ch0 + 2 * j]);
-              const float b = __uint_as_float(v[gi & 1][2 * j + 1]) + fmaf(prm.wz_all[ch0 + 2 * j + 1], zf, prm.bias_all[ch0 + 2 * j + 1]);
-              pk[j] = act_pack(a, b);
-            }
-            const uint32_t dcol = (WG == 0) ? (cH1lo + lc / 2) : (cH1hi + (lc - 256) / 2);
-            tc::tmem_st16(tbase + lane_base + dcol, pk);        // destination columns were read (and waited for) earlier
-          }
-        };
-        if (wg == 0) drain1(std::integral_constant<int, 0>{}); else drain1(std::integral_constant<int, 1>{});
-        tc::tmem_st_wait();
+          for (int j = 0; j < 16; ++j) pk[j] = act_pack(o[2 * j], o[2 * j + 1]);
+          const uint32_t dcol = (wg == 0) ? (cH1lo + lc / 2) : (cH1hi + (lc - 256) / 2);
+          tc::tmem_st16(tbase + lane_base + dcol, pk);
+          tc::tmem_st_wait();
+        }
         tc::tcgen05_fence_before();
         warp_arrive_leader<CG>(bars + B_H1_READY, lane);
         PROF_ADD(P_W_DRAIN1);
@@ -1220,27 +1199,16 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       tc::tcgen05_fence_after();
       {
         PROF_T0();
-        auto drain2 = [&](auto wg_tag) {
-          constexpr int WG = decltype(wg_tag)::value;
-          uint32_t v[2][32];
-          tc::tmem_ld32(tbase + lane_base + cAcc2 + WG * 128, v[0]);
+#pragma unroll 1
+        for (int gq = 0; gq < 4; ++gq) {
+          float o[32];
+          const int lc = wg * 128 + gq * 32;
+          load_pre(cAcc2 + lc, side_off(2) + lc, o);
+          uint32_t pk[16];
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
-            const int lc = WG * 128 + gq * 32;
-            tc::tmem_ld_wait();
-            if (gq + 1 < 4) tc::tmem_ld32(tbase + lane_base + cAcc2 + lc + 32, v[(gq + 1) & 1]);
-            const int ch0 = side_off(2) + lc;
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float a = __uint_as_float(v[gq & 1][2 * j]) + fmaf(prm.wz_all[ch0 + 2 * j], zf, prm.bias_all[ch0 + 2 * j]);
-              const float b = __uint_as_float(v[gq & 1][2 * j + 1]) + fmaf(prm.wz_all[ch0 + 2 * j + 1], zf, prm.bias_all[ch0 + 2 * j + 1]);
-              pk[j] = act_pack(a, b);
-            }
-            tc::tmem_st16(tbase + lane_base + cH2 + lc / 2, pk);
-          }
-        };
-        if (wg == 0) drain2(std::integral_constant<int, 0>{}); else drain2(std::integral_constant<int, 1>{});
+          for (int j = 0; j < 16; ++j) pk[j] = act_pack(o[2 * j], o[2 * j + 1]);
+          tc::tmem_st16(tbase + lane_base + cH2 + lc / 2, pk);
+        }
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
         warp_arrive_leader<CG>(bars + B_H2_READY, lane);
@@ -1254,32 +1222,23 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         float logit[kMaxRes];
 #pragma unroll
         for (int r = 0; r < kMaxRes; ++r) logit[r] = s4[r];
-        {
-          uint32_t v[2][32];
-          tc::tmem_ld32(tbase + lane_base + cAcc3, v[0]);
+#pragma unroll 1
+        for (int gq = 0; gq < 4; ++gq) {
+          float o[32];
+          load_pre(cAcc3 + gq * 32, side_off(3) + gq * 32, o);
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
-            tc::tmem_ld_wait();
-            if (gq + 1 < 4) tc::tmem_ld32(tbase + lane_base + cAcc3 + (gq + 1) * 32, v[(gq + 1) & 1]);
-            const int ch0 = side_off(3) + gq * 32;
+          for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], o[j] * MP_LEAKY_SLOPE);
 #pragma unroll
-            for (int r = 0; r < kMaxRes; ++r) {
-              if (r < res) {
-                const float4* wv = reinterpret_cast<const float4*>(prm.w4h + r * kL3 + gq * 32);
+          for (int r = 0; r < kMaxRes; ++r) {
+            if (r < res) {
+              const float4* wv = reinterpret_cast<const float4*>(prm.w4h + r * kL3 + gq * 32);
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                  const float4 w4 = __ldg(wv + j4);
-                  float o[4];
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float pre = __uint_as_float(v[gq & 1][4 * j4 + e]) + fmaf(prm.wz_all[ch0 + 4 * j4 + e], zf, prm.bias_all[ch0 + 4 * j4 + e]);
-                    o[e] = fmaxf(pre, pre * MP_LEAKY_SLOPE);
-                  }
-                  logit[r] = fmaf(w4.x, o[0], logit[r]);
-                  logit[r] = fmaf(w4.y, o[1], logit[r]);
-                  logit[r] = fmaf(w4.z, o[2], logit[r]);
-                  logit[r] = fmaf(w4.w, o[3], logit[r]);
-                }
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 w4 = __ldg(wv + j4);
+                logit[r] = fmaf(w4.x, o[4 * j4 + 0], logit[r]);
+                logit[r] = fmaf(w4.y, o[4 * j4 + 1], logit[r]);
+                logit[r] = fmaf(w4.z, o[4 * j4 + 2], logit[r]);
+                logit[r] = fmaf(w4.w, o[4 * j4 + 3], logit[r]);
               }
             }
           }
