@@ -335,7 +335,25 @@ def run_ours(args):
             v, fcs = marching_cubes(sdf[0, 0])
         torch.cuda.synchronize()
         fps_mc = nfr / (time.perf_counter() - t0)
+        # configs[2]: geometry + colour -- netC (513-wide head, fp32 fused kernel) queried at the visible vertices
+        from monoport_b200.modeling import PIFuNetC
+        from monoport_b200.recon import colorization
+        netC = PIFuNetC()
+        netC.surface_classifier.to(dev)
+        netC.eval()
+        gC = torch.Generator().manual_seed(11)
+        featC = [[(torch.randn(1, 512, 128, 128, generator=gC) * 0.5).to(dev)]]
+        img = colorization(netC, featC, X, Y, Z, cal)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(nfr):
+            sdf = eng(im_feat_list=[[feats[i % 4]]], calib_tensor=cal)
+            X, Y, Z, nrm = forward_vertices(sdf, "front")
+            img = colorization(netC, featC, X, Y, Z, cal)
+        torch.cuda.synchronize()
+        fps_color = nfr / (time.perf_counter() - t0)
         recon = {"workload": "configs[1]: netG 256^3 Seg3dLossless(faster=True) from resident features, per frame",
+                 "frames_per_s_geometry_plus_netC_colour": fps_color,
                  "frames_per_s_with_forward_vertices": fps_fv, "frames_per_s_with_marching_cubes": fps_mc,
                  "points_evaluated_per_frame": int(sum(eng.last_stats)), "per_level": eng.last_stats,
                  "visible_vertices": int(X.numel()), "mesh_vertices": int(v.shape[0]), "mesh_faces": int(fcs.shape[0])}

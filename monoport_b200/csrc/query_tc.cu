@@ -831,7 +831,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         ++it;
       };
       auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool& first) {
-#pragma unroll
+#pragma unroll 1
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t ad = tc::make_sdesc_sw128(a_addr + kk * 32, 1024), bd = tc::make_sdesc_sw128(b_addr + kk * 32, 1024);
           if constexpr (CG == 1) tc::mma_ss(d, ad, bd, idesc, first ? 0u : 1u);
@@ -840,7 +840,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         }
       };
       auto kblock_ts = [&](uint32_t d, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool& first) {
-#pragma unroll
+#pragma unroll 1
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t bd = tc::make_sdesc_sw128(b_addr + kk * 32, 1024);
           if constexpr (CG == 1) tc::mma_ts(d, a_tmem + kk * 8, bd, idesc, first ? 0u : 1u);
@@ -1151,9 +1151,8 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         warp_arrive_leader<CG>(bars + B_H0_READY0 + b, lane);
         PROF_ADD(P_W_DRAIN0);
       };
-      gen_chunk(0);
-      gen_chunk(1);
-      for (int c = 2; c < 8; ++c) gen_chunk(c);
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) gen_chunk(c);
       // per-point scalars of this tile (written by the sampler warps)
       { PROF_T0(); wait_bar(bars, B_ACC0_FULL0, c_sready); PROF_ADD(P_W_XFREE); }
       const float zf = s_zf[row];
