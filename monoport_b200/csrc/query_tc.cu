@@ -117,13 +117,14 @@ struct Smem {
   static constexpr int Wr = H0 + 65536;                         // kStages x 32 KB
   static constexpr int Small = Wr + kRingBytes;                 // zf[128], inimg[128], s4[kMaxRes][128]
   static constexpr int Bars = Small + (2 + kMaxRes) * kTile * 4;
-  static constexpr int NumBars = 3 * kStages + 14;
+  static constexpr int NumBars = 3 * kStages + 20;
   static constexpr int TmemPtr = Bars + NumBars * 8;
   static constexpr int Total = TmemPtr + 16;
 };
 enum Bar { B_WFULL = 0, B_WEMPTY = kStages, B_WPEER = 2 * kStages, B_XREADY = 3 * kStages, B_ACC0_FULL0, B_ACC0_FULL1, B_H0_READY0, B_H0_READY1,
-           B_H0_FREE0, B_H0_FREE1, B_ACC1_FULL, B_H1_READY, B_ACC2_FULL, B_H2_READY, B_ACC3_FULL, B_TILE_DONE, B_XFREE };
-static_assert(B_XFREE + 1 == Smem::NumBars, "barrier count");
+           B_H0_FREE0, B_H0_FREE1, B_ACC1_FULL, B_H1_READY, B_ACC2_FULL, B_H2_READY, B_ACC3_FULL, B_TILE_DONE, B_XFREE,
+           B_P_H0_0, B_P_H0_1, B_P_X, B_P_H1, B_P_H2, B_P_TD };   // v3 / cta_group::2: events forwarded by the peer CTA's relay
+static_assert(B_P_TD + 1 == Smem::NumBars, "barrier count");
 static_assert(Smem::Total + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
 
 __device__ __forceinline__ void wait_bar(uint64_t* bars, int which, uint32_t& count) {
@@ -146,6 +147,10 @@ __device__ __forceinline__ void warp_arrive_leader(uint64_t* bar, int lane) {
     if constexpr (CG == 1) tc::mbar_arrive(bar);
     else tc::mbar_arrive_remote(bar, 0);
   }
+}
+__device__ __forceinline__ void warp_arrive_local(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) tc::mbar_arrive(bar);
 }
 template <int CG>
 __device__ __forceinline__ void wait_leader(uint64_t* bars, int which, uint32_t& count, bool free_type = false) {
@@ -754,8 +759,12 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       tc::mbar_init(bars + B_WEMPTY + s, 1);
       tc::mbar_init(bars + B_WPEER + s, 1);
     }
-    constexpr int kW = 8 * CG;
-    tc::mbar_init(bars + B_XREADY, 2 * CG);        // the two sampler warps of every CTA
+    // hand-off barriers are CTA-local (workers never touch the peer CTA: a cluster-scope release from 8 warps per event
+    // costs far more than one forwarded arrival); with cta_group::2 the peer's relay thread forwards every event to the
+    // leader's B_P_* barriers
+    constexpr int kW = 8;
+    for (int i = B_P_H0_0; i <= B_P_TD; ++i) tc::mbar_init(bars + i, 1);
+    tc::mbar_init(bars + B_XREADY, 2);             // the two sampler warps
     tc::mbar_init(bars + B_H0_READY0, kW);
     tc::mbar_init(bars + B_H0_READY1, kW);
     tc::mbar_init(bars + B_H0_FREE0, 1);
@@ -765,7 +774,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     tc::mbar_init(bars + B_ACC2_FULL, 1);
     tc::mbar_init(bars + B_H2_READY, kW);
     tc::mbar_init(bars + B_ACC3_FULL, 1);
-    tc::mbar_init(bars + B_TILE_DONE, 4 * CG);
+    tc::mbar_init(bars + B_TILE_DONE, 4);
     tc::mbar_init(bars + B_XFREE, 1);
     tc::mbar_init(bars + B_ACC0_FULL0, 2);         // v3: "per-point scalars of this tile are in smem" (CTA-local)
     tc::mbar_init(bars + B_ACC0_FULL1, 1);
@@ -797,13 +806,40 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       }
     }
   } else if (warp == 1 && !leader) {
+    // ============================== peer CTA relay ==============================
+    // One thread forwards to the leader (a) "our half of weight stage s has landed" and (b) every operand hand-off of
+    // this CTA's workers, polling the local barriers without blocking so that neither stream delays the other.
     if (lane == 0) {
-      uint32_t it = 0;
-      for (long long g = g0; g < n_groups; g += gstep) {
-        for (int s = 0; s < kStagesPerTile3; ++s, ++it) {
+      uint32_t it = 0;                        // weight stages forwarded
+      const uint32_t total_stages = (uint32_t)(((n_groups - g0 + gstep - 1) / gstep) * kStagesPerTile3);
+      // per-tile event sequence (the order in which the leader consumes them)
+      constexpr int kEvents = 12;
+      const int ev_local[kEvents] = {B_H0_READY0, B_H0_READY1, B_H0_READY0, B_H0_READY1, B_H0_READY0, B_H0_READY1,
+                                     B_H0_READY0, B_H0_READY1, B_XREADY, B_H1_READY, B_H2_READY, B_TILE_DONE};
+      const int ev_peer[kEvents] = {B_P_H0_0, B_P_H0_1, B_P_H0_0, B_P_H0_1, B_P_H0_0, B_P_H0_1, B_P_H0_0, B_P_H0_1,
+                                    B_P_X, B_P_H1, B_P_H2, B_P_TD};
+      uint32_t cnt[Smem::NumBars];
+      for (int i = 0; i < Smem::NumBars; ++i) cnt[i] = 0;
+      const long long n_my_tiles = (n_groups - g0 + gstep - 1) / gstep;
+      long long tile_i = 0;
+      int ev = 0;
+      while (it < total_stages || tile_i < n_my_tiles) {
+        if (it < total_stages) {
           const int slot = it % C::Stages;
-          tc::mbar_wait(bars + B_WFULL + slot, (it / C::Stages) & 1u);
-          tc::mbar_arrive_remote(bars + B_WPEER + slot, 0);
+          if (tc::mbar_test_wait(bars + B_WFULL + slot, (it / C::Stages) & 1u)) {
+            tc::mbar_arrive_remote(bars + B_WPEER + slot, 0);
+            ++it;
+          }
+        }
+        if (tile_i < n_my_tiles) {
+          const int lb = ev_local[ev];
+          if (tc::mbar_test_wait(bars + lb, cnt[lb] & 1u)) {
+            ++cnt[lb];
+            tc::tcgen05_fence_after();
+            tc::tcgen05_fence_before();
+            tc::mbar_arrive_remote(bars + ev_peer[ev], 0);
+            if (++ev == kEvents) { ev = 0; ++tile_i; }
+          }
         }
       }
     }
@@ -818,6 +854,12 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       uint32_t it = 0;
       uint32_t c_xready = 0, c_h0ready[2] = {0, 0}, c_h1ready = 0, c_h2ready = 0, c_tiledone = 0;
       const long long t_begin = prof ? clock64() : 0;
+      // an operand is ready when this CTA's workers (local barrier) and, with cta_group::2, the peer's (forwarded) are
+      auto wait_both = [&](int local_bar, int peer_bar, uint32_t& count) {
+        tc::mbar_wait(bars + local_bar, count & 1u);
+        if constexpr (CG == 2) tc::mbar_wait_cluster(bars + peer_bar, count & 1u);
+        ++count;
+      };
       auto next_stage = [&]() -> uint32_t {
         const int slot = it % C::Stages;
         const uint32_t par = (it / C::Stages) & 1u;
@@ -854,7 +896,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         // B_H2_READY, waited) and acc3 (drained by the fp32 tail: B_TILE_DONE)
         if (g != g0) {
           PROF_T0();
-          wait_leader<CG>(bars, B_TILE_DONE, c_tiledone);
+          wait_both(B_TILE_DONE, B_P_TD, c_tiledone);
           PROF_ADD(P_ACC1DRAINED);
           tc::tcgen05_fence_after();
         }
@@ -862,7 +904,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         // ---- layer 1, hidden part: 8 sampled layer-0 chunks x 2 K-blocks x 2 output halves
         for (int c = 0; c < 8; ++c) {
           const int b = c & 1;
-          { PROF_T0(); wait_leader<CG>(bars, B_H0_READY0 + b, c_h0ready[b]); PROF_ADD(P_H0READY); }
+          { PROF_T0(); wait_both(B_H0_READY0 + b, B_P_H0_0 + b, c_h0ready[b]); PROF_ADD(P_H0READY); }
           tc::tcgen05_fence_after();
           for (int kb = 0; kb < 2; ++kb)
             for (int nh = 0; nh < 2; ++nh) {
@@ -873,7 +915,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           commit<CG>(bars + B_H0_FREE0 + b);
         }
         // ---- layer 1, skip part: A = X
-        { PROF_T0(); wait_leader<CG>(bars, B_XREADY, c_xready); PROF_ADD(P_XREADY); }
+        { PROF_T0(); wait_both(B_XREADY, B_P_X, c_xready); PROF_ADD(P_XREADY); }
         tc::tcgen05_fence_after();
         for (int kb = 0; kb < 4; ++kb)
           for (int nh = 0; nh < 2; ++nh) {
@@ -883,7 +925,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           }
         commit<CG>(bars + B_ACC1_FULL);
         // ---- layer 2: A = H1 from TMEM (8 K-blocks) + X (4 K-blocks) -> acc2 [128,384)
-        { PROF_T0(); wait_leader<CG>(bars, B_H1_READY, c_h1ready); PROF_ADD(P_H1READY); }
+        { PROF_T0(); wait_both(B_H1_READY, B_P_H1, c_h1ready); PROF_ADD(P_H1READY); }
         tc::tcgen05_fence_after();
         {
           bool first = true;
@@ -910,7 +952,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             release_stage();
           }
           commit<CG>(bars + B_XFREE);
-          { PROF_T0(); wait_leader<CG>(bars, B_H2_READY, c_h2ready); PROF_ADD(P_H2READY); }
+          { PROF_T0(); wait_both(B_H2_READY, B_P_H2, c_h2ready); PROF_ADD(P_H2READY); }
           tc::tcgen05_fence_after();
           for (int s = 0; s < 2; ++s) {
             const uint32_t w = next_stage();
@@ -1049,7 +1091,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       tc::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(bars + B_ACC0_FULL0);        // scalars ready (CTA-local, release)
-      warp_arrive_leader<CG>(bars + B_XREADY, lane);
+      warp_arrive_local(bars + B_XREADY, lane);
     }
   } else if (warp >= 4) {
     // ============================== workers: layer-0 chunk generators + epilogue ==============================
@@ -1148,7 +1190,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           }
         }
         tc::fence_proxy_async_smem();
-        warp_arrive_leader<CG>(bars + B_H0_READY0 + b, lane);
+        warp_arrive_local(bars + B_H0_READY0 + b, lane);
         PROF_ADD(P_W_DRAIN0);
       };
 #pragma unroll 1
@@ -1190,7 +1232,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           tc::tmem_st_wait();
         }
         tc::tcgen05_fence_before();
-        warp_arrive_leader<CG>(bars + B_H1_READY, lane);
+        warp_arrive_local(bars + B_H1_READY, lane);
         PROF_ADD(P_W_DRAIN1);
       }
       // ---- layer 2 -> H2 [0,128)
@@ -1210,7 +1252,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         }
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
-        warp_arrive_leader<CG>(bars + B_H2_READY, lane);
+        warp_arrive_local(bars + B_H2_READY, lane);
         PROF_ADD(P_W_DRAIN2);
       }
       // ---- layer 3 + layer 4 in fp32, warpgroup 0
@@ -1243,7 +1285,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           }
         }
         tc::tcgen05_fence_before();
-        warp_arrive_leader<CG>(bars + B_TILE_DONE, lane);
+        warp_arrive_local(bars + B_TILE_DONE, lane);
         PROF_ADD(P_W_DRAIN3);
         const long long i = p0 + row;
         if (i < n) {
