@@ -901,6 +901,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           tc::tcgen05_fence_after();
         }
         bool first1[2] = {true, true};
+        const long long t_ph0 = prof ? clock64() : 0;
         // ---- layer 1, hidden part: 8 sampled layer-0 chunks x 2 K-blocks x 2 output halves
         for (int c = 0; c < 8; ++c) {
           const int b = c & 1;
@@ -914,8 +915,10 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             }
           commit<CG>(bars + B_H0_FREE0 + b);
         }
+        if (prof) prof[9] += (unsigned long long)(clock64() - t_ph0);
         // ---- layer 1, skip part: A = X
         { PROF_T0(); wait_both(B_XREADY, B_P_X, c_xready); PROF_ADD(P_XREADY); }
+        const long long t_ph1 = prof ? clock64() : 0;
         tc::tcgen05_fence_after();
         for (int kb = 0; kb < 4; ++kb)
           for (int nh = 0; nh < 2; ++nh) {
@@ -924,12 +927,15 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             release_stage();
           }
         commit<CG>(bars + B_ACC1_FULL);
+        if (prof) prof[10] += (unsigned long long)(clock64() - t_ph1);
         // ---- layer 2: A = H1 from TMEM (8 K-blocks) + X (4 K-blocks) -> acc2 [128,384)
         { PROF_T0(); wait_both(B_H1_READY, B_P_H1, c_h1ready); PROF_ADD(P_H1READY); }
         tc::tcgen05_fence_after();
         {
+          const long long t_ph2 = prof ? clock64() : 0;
           bool first = true;
           for (int kb = 0; kb < 8; ++kb) {
+            if (prof && kb == 4) prof[11] += (unsigned long long)(clock64() - t_ph2);   // first 4 TS K-blocks (16 MMAs N=256)
             const uint32_t w = next_stage();
             const uint32_t a = tbase + (kb < 4 ? cH1lo + kb * 32 : cH1hi + (kb - 4) * 32);
             kblock_ts(tbase + cAcc2, a, w, idesc256, first);
@@ -1611,7 +1617,7 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     cudaMemcpy(h.data(), d_prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(d_prof);
     static const char* names[32] = {"total", "xready", "acc0free", "wfull", "wpeer", "h0ready", "acc1drained", "h1ready", "h2ready",
-                                    0, 0, 0, 0, 0, 0, 0, "w_sample", "w_acc0full", "w_h0free", "w_acc1full", "w_acc2full", "w_acc3full",
+                                    "ph_L1hid(32st)", "ph_L1skip(8st)", "ph_L2_TS(4st)", 0, 0, 0, 0, "w_sample", "w_acc0full", "w_h0free", "w_acc1full", "w_acc2full", "w_acc3full",
                                     "w_drain0", "w_drain1", "w_drain2", "w_drain3", 0, 0, 0, 0, 0, 0};
     const long long tiles_per_cta = (tiles + grid - 1) / grid;
     fprintf(stderr, "[tc prof] grid=%d tiles/cta~%lld  (cycles per tile, CTA 0 | CTA 1)\n", grid, tiles_per_cta);
