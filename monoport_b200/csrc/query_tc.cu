@@ -89,8 +89,8 @@ struct TcParams {
   const __half* wstream2[2];
   // per-channel bias and depth-column weight of layers 0..3, carried in the kernel parameter (constant) bank: the
   // epilogue reads them with warp-uniform indices, so they cost no load instructions and no shared memory
-  float bias_all[kSideFloats];
-  float wz_all[kSideFloats];
+  alignas(16) float bias_all[kSideFloats];
+  alignas(16) float wz_all[kSideFloats];
   const float* w4h;
   const float* w4s;
   const float* w4z;
@@ -1213,9 +1213,17 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         uint32_t v[32];
         tc::tmem_ld32(tbase + lane_base + col, v);
         tc::tmem_ld_wait();
+        // 128-bit constant-bank loads (ch0 is a multiple of 32): 16 LDC.128 instead of 64 scalar constant loads
+        const float4* bz = reinterpret_cast<const float4*>(&prm.bias_all[ch0]);
+        const float4* wz = reinterpret_cast<const float4*>(&prm.wz_all[ch0]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          o[j] = __uint_as_float(v[j]) + fmaf(prm.wz_all[ch0 + j], zf, prm.bias_all[ch0 + j]);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b = bz[j4], z = wz[j4];
+          o[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + fmaf(z.x, zf, b.x);
+          o[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + fmaf(z.y, zf, b.y);
+          o[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + fmaf(z.z, zf, b.z);
+          o[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + fmaf(z.w, zf, b.w);
+        }
       };
       // ---- layer 1 (512 columns) -> H1, drained IN PLACE: warpgroup 0 walks [0,256) upwards into [0,128), warpgroup 1
       //      walks [256,512) downwards into [384,512); the packed destination of a group never reaches columns that are
