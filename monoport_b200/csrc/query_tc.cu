@@ -1117,16 +1117,13 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       return *reinterpret_cast<const uint32_t*>(&r);
     };
 
-    for (long long g = g0; g < n_groups; g += gstep) {
-      const long long tile = g * CG + rank;
-      const long long p0 = tile * kTile;
-      // ---- projection + taps of this warp's 16 points (lane q and q+16 both hold point q)
-      int my_off[4];
-      float my_wgt[4];
-      float my_zf;
-      bool my_in;
+    // ---- projection + taps of this warp's 16 points of a tile (lane q and q+16 both hold point q)
+    int my_off[4];
+    float my_wgt[4];
+    float my_zf = 0.f;
+    auto compute_taps = [&](long long g) {
       {
-        const long long i = p0 + wk * 16 + l16;
+        const long long i = (g * CG + rank) * kTile + wk * 16 + l16;
         float u = 0.f, v = 0.f, w = 0.f;
         const bool valid = i < n;
         if (valid) {
@@ -1134,13 +1131,14 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           mp_load_point(src, i, x, y, z);
           mp_project(cal, x, y, z, u, v, w);
         }
-        my_in = valid && (u >= -1.f) && (u <= 1.f) && (v >= -1.f) && (v <= 1.f);
         MpTaps t = mp_taps(valid ? u : 0.f, valid ? v : 0.f, prm.H, prm.W);
         const bool dead = !valid || !(u == u) || !(v == v);
 #pragma unroll
         for (int a = 0; a < 4; ++a) { my_off[a] = dead ? 0 : t.off[a]; my_wgt[a] = dead ? 0.f : t.wgt[a]; }
         my_zf = w * cal.z_scale;
       }
+    };
+    {
       // ---- one sampled layer-0 chunk: h0[:, c*128 .. +128) = lrelu(lerp(G0) + b0 + w0z z) -> H0 smem buffer c&1.
       //      A half-warp covers one point (16 lanes x 8 channels), so a pass handles 2 of the warp's 16 points.
       auto gen_chunk = [&](int c) {
@@ -1199,16 +1197,14 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         warp_arrive_local(bars + B_H0_READY0 + b, lane);
         PROF_ADD(P_W_DRAIN0);
       };
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) gen_chunk(c);
-      // per-point scalars of this tile (written by the sampler warps)
-      { PROF_T0(); wait_bar(bars, B_ACC0_FULL0, c_sready); PROF_ADD(P_W_XFREE); }
-      const float zf = s_zf[row];
-      const float inimg = s_in[row];
+      // The worker loop is software-pipelined across tiles: the first two sampled layer-0 chunks of the NEXT tile are
+      // generated while this tile's layer-2 / layer-3 MMAs run (the workers would idle there), so the next tile's
+      // layer 1 can start the moment the tensor pipe is free.  A virtual first iteration (g = g0 - gstep) only performs
+      // that pre-generation.  Every routine has a single call site to keep the instruction footprint small.
+      float zf = 0.f, inimg = 0.f;
       float s4[kMaxRes];
 #pragma unroll
-      for (int r = 0; r < kMaxRes; ++r) s4[r] = (r < res) ? s_s4[r * kTile + row] : 0.f;
-
+      for (int r = 0; r < kMaxRes; ++r) s4[r] = 0.f;
       auto load_pre = [&](uint32_t col, int ch0, float (&o)[32]) {
         uint32_t v[32];
         tc::tmem_ld32(tbase + lane_base + col, v);
@@ -1225,6 +1221,24 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           o[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + fmaf(z.w, zf, b.w);
         }
       };
+      for (long long g = g0 - gstep; g < n_groups; g += gstep) {
+        const bool real = g >= g0;
+        const bool has_next = g + gstep < n_groups;
+        const long long p0 = (g * CG + rank) * kTile;
+#pragma unroll 1
+        for (int step = 0; step < 11; ++step) {
+          int gc = -1;
+          if (step < 6) { if (real) gc = step + 2; }
+          else if (step == 7) { if (has_next) { compute_taps(g + gstep); gc = 0; } }
+          else if (step == 10) { if (has_next) gc = 1; }    // after the fp32 tail: B_TILE_DONE gates the next tile
+          if (gc >= 0) gen_chunk(gc);
+          if (!real) continue;
+          if (step == 6) {
+          { PROF_T0(); wait_bar(bars, B_ACC0_FULL0, c_sready); PROF_ADD(P_W_XFREE); }
+          zf = s_zf[row];
+          inimg = s_in[row];
+#pragma unroll
+          for (int r = 0; r < kMaxRes; ++r) s4[r] = (r < res) ? s_s4[r * kTile + row] : 0.f;
       // ---- layer 1 (512 columns) -> H1, drained IN PLACE: warpgroup 0 walks [0,256) upwards into [0,128), warpgroup 1
       //      walks [256,512) downwards into [384,512); the packed destination of a group never reaches columns that are
       //      still unread, and [128,384) comes out free for acc2.
@@ -1249,6 +1263,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         warp_arrive_local(bars + B_H1_READY, lane);
         PROF_ADD(P_W_DRAIN1);
       }
+          } else if (step == 8) {
       // ---- layer 2 -> H2 [0,128)
       { PROF_T0(); wait_bar(bars, B_ACC2_FULL, c_acc2full); PROF_ADD(P_W_ACC2FULL); }
       tc::tcgen05_fence_after();
@@ -1269,6 +1284,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         warp_arrive_local(bars + B_H2_READY, lane);
         PROF_ADD(P_W_DRAIN2);
       }
+          } else if (step == 9) {
       // ---- layer 3 + layer 4 in fp32, warpgroup 0
       if (wg == 0) {
         { PROF_T0(); wait_bar(bars, B_ACC3_FULL, c_acc3full); PROF_ADD(P_W_ACC3FULL); }
@@ -1310,6 +1326,9 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
               if (dst.out) dst.out[(long long)r * dst.ld + i] = val;
               if (dst.scatter_vol && r == 0) dst.scatter_vol[__ldg(src.nodes + i)] = val;
             }
+          }
+        }
+      }
           }
         }
       }
