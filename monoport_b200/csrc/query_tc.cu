@@ -894,12 +894,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       for (long long g = g0; g < n_groups; g += gstep) {
         // acc1 = [0,512) overlaps the previous tile's H2 (readers already issued, in order), acc2 (drained before
         // B_H2_READY, waited) and acc3 (drained by the fp32 tail: B_TILE_DONE)
-        if (g != g0) {
-          PROF_T0();
-          wait_both(B_TILE_DONE, B_P_TD, c_tiledone);
-          PROF_ADD(P_ACC1DRAINED);
-          tc::tcgen05_fence_after();
-        }
+        bool need_tile_done = g != g0;
         bool first1[2] = {true, true};
         const long long t_ph0 = prof ? clock64() : 0;
         // ---- layer 1, hidden part: 8 sampled layer-0 chunks x 2 K-blocks x 2 output halves
@@ -910,6 +905,15 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           for (int kb = 0; kb < 2; ++kb)
             for (int nh = 0; nh < 2; ++nh) {
               const uint32_t w = next_stage();
+              if (nh == 1 && need_tile_done) {
+                // [384,512) holds the previous tile's acc3 until its fp32 tail has drained it; the lower half of acc1
+                // does not overlap it, so only the first MMA into [256,512) has to wait
+                PROF_T0();
+                wait_both(B_TILE_DONE, B_P_TD, c_tiledone);
+                PROF_ADD(P_ACC1DRAINED);
+                tc::tcgen05_fence_after();
+                need_tile_done = false;
+              }
               kblock_ss(tbase + cAcc1 + nh * 256, sH0 + b * 32768 + kb * 16384, w, idesc256, first1[nh]);
               release_stage();
             }
