@@ -43,7 +43,7 @@ namespace {
 constexpr int kC = 256;                 // feature channels
 constexpr int kTile = 128;              // points per tile
 constexpr int kThreads = 384;
-constexpr int kWorkers = 256;           // warps 4..11
+
 template <int CG> struct Cfg {
   static constexpr int Stages = 3 * CG;
   static constexpr int StageBytes = 32768 / CG;
@@ -135,6 +135,132 @@ __device__ __forceinline__ void wait_bar(uint64_t* bars, int which, uint32_t& co
 __device__ __forceinline__ void wait_free(uint64_t* bars, int which, uint32_t& count) {
   tc::mbar_wait(bars + which, (count & 1u) ^ 1u);
   ++count;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// sampling helpers shared by both programs
+// --------------------------------------------------------------------------------------------------------------------
+struct PointTaps {
+  int off[4];       // texel indices of the four bilinear taps (0 when the point is invalid)
+  float wgt[4];     // tap weights (0 for out-of-range taps, geometry.py:15 zeros padding)
+  float zf;         // depth feature z * scale (DepthNormalizer.py:32)
+  bool in_img;      // MonoPortNet.py:74
+};
+
+// projection (geometry.py:19-55) + mask + taps of point i (i >= n: masked-out padding point)
+__device__ __forceinline__ PointTaps point_taps(const MpPointSrc& src, const MpCalib& cal, int H, int W, long long i, long long n) {
+  PointTaps pt;
+  float u = 0.f, v = 0.f, w = 0.f;
+  const bool valid = i < n;
+  if (valid) {
+    float x, y, z;
+    mp_load_point(src, i, x, y, z);
+    mp_project(cal, x, y, z, u, v, w);
+  }
+  pt.in_img = valid && (u >= -1.f) && (u <= 1.f) && (v >= -1.f) && (v <= 1.f);
+  const MpTaps t = mp_taps(valid ? u : 0.f, valid ? v : 0.f, H, W);
+  const bool dead = !valid || !(u == u) || !(v == v);      // NaN coordinates (perspective with w == 0): keep taps finite
+#pragma unroll
+  for (int a = 0; a < 4; ++a) { pt.off[a] = dead ? 0 : t.off[a]; pt.wgt[a] = dead ? 0.f : t.wgt[a]; }
+  pt.zf = w * cal.z_scale;
+  return pt;
+}
+
+// Transposing warp reduction: every lane holds 16 partial sums (one per point); afterwards lane L (< 16) holds the total of
+// point L over all 32 lanes.  16+8+4+2+1 = 31 shuffles instead of 16 x 5.
+__device__ __forceinline__ float warp_reduce16(const float (&part)[16], int lane) {
+  float v16[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v16[j] = part[j] + __shfl_xor_sync(0xffffffffu, part[j], 16);
+  float v8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool up = lane & 8;
+    const float keep = up ? v16[j + 8] : v16[j], send = up ? v16[j] : v16[j + 8];
+    v8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float v4[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool up = lane & 4;
+    const float keep = up ? v8[j + 4] : v8[j], send = up ? v8[j] : v8[j + 4];
+    v4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  float v2[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const bool up = lane & 2;
+    const float keep = up ? v4[j + 2] : v4[j], send = up ? v4[j] : v4[j + 2];
+    v2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const bool up = lane & 1;
+  const float keep = up ? v2[1] : v2[0], send = up ? v2[0] : v2[1];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+// Whole warp: sample the 16 points whose taps sit in lanes 0..15 (`pt`, duplicated in lanes 16..31) into rows
+// [pbase, pbase+16) of the fp16 X tile (K-major SWIZZLE_128B, 4 K-blocks of 64 channels; lane covers 8 channels) and
+// publish the per-point scalars: depth feature, in-image flag and the fp32 skip part of the last layer
+// sum_c w4[128 + c] * x_c + w4z * z + b4 (computed from the fp32 samples, before they are rounded to fp16).
+__device__ __forceinline__ void sample_x_group(const TcParams& prm, uint8_t* smem_x, float* s_zf, float* s_in, float* s_s4,
+                                               const PointTaps& pt, int pbase, int lane, const float (&w4s)[kMaxRes][8]) {
+  const int cbase = lane * 8;
+  float s4part[kMaxRes][16];
+#pragma unroll
+  for (int q0 = 0; q0 < 16; q0 += 4) {
+    uint4 raw[4][4];
+    float wgt[4][4];
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int off = __shfl_sync(0xffffffffu, pt.off[a], q0 + qq);
+        wgt[qq][a] = __shfl_sync(0xffffffffu, pt.wgt[a], q0 + qq);
+        raw[qq][a] = __ldg(reinterpret_cast<const uint4*>(prm.feat + (size_t)off * kC + cbase));
+      }
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      const int p = pbase + q0 + qq;
+      float2 acc[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {                   // same accumulation order as grid_sample: nw, ne, sw, se
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[qq][a]);
+        const float2 w2 = make_float2(wgt[qq][a], wgt[qq][a]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          acc[j] = (a == 0) ? __fmul2_rn(f, w2) : __ffma2_rn(f, w2, acc[j]);
+        }
+      }
+      uint4 packed;
+      packed.x = tc::pack_half2(acc[0].x, acc[0].y);
+      packed.y = tc::pack_half2(acc[1].x, acc[1].y);
+      packed.z = tc::pack_half2(acc[2].x, acc[2].y);
+      packed.w = tc::pack_half2(acc[3].x, acc[3].y);
+      *reinterpret_cast<uint4*>(smem_x + (lane >> 3) * 16384 + tc::sw128_offset(p, (lane & 7) * 8)) = packed;
+#pragma unroll
+      for (int r = 0; r < kMaxRes; ++r) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sacc = fmaf(w4s[r][2 * j], acc[j].x, sacc);
+          sacc = fmaf(w4s[r][2 * j + 1], acc[j].y, sacc);
+        }
+        s4part[r][q0 + qq] = sacc;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kMaxRes; ++r) {
+    if (r < prm.res) {
+      const float tot = warp_reduce16(s4part[r], lane);
+      if (lane < 16) s_s4[r * kTile + pbase + lane] = tot + __ldg(prm.w4z + r) * pt.zf + __ldg(prm.b4 + r);
+    }
+  }
+  if (lane < 16) {
+    s_zf[pbase + lane] = pt.zf;
+    s_in[pbase + lane] = pt.in_img ? 1.f : 0.f;
+  }
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -437,118 +563,13 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       // ---- sampling: warp wk handles points wk*16 .. +15.  Lane q (< 16) projects point q and builds its bilinear
       //      taps once; the taps are then broadcast and every lane gathers 8 consecutive channels (16 B) per tap.
       {
-        const int cbase = lane * 8;
         float w4s[kMaxRes][8];
 #pragma unroll
         for (int r = 0; r < kMaxRes; ++r)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) w4s[r][j] = (r < res) ? __ldg(prm.w4s + r * kC + cbase + j) : 0.f;
-        int my_off[4];
-        float my_wgt[4];
-        float my_zf = 0.f;
-        {
-          const long long i = p0 + wk * 16 + (lane & 15);
-          float u = 0.f, v = 0.f, w = 0.f;
-          const bool valid = i < n;
-          if (valid) {
-            float x, y, z;
-            mp_load_point(src, i, x, y, z);
-            mp_project(cal, x, y, z, u, v, w);
-          }
-          const bool in_img = valid && (u >= -1.f) && (u <= 1.f) && (v >= -1.f) && (v <= 1.f);
-          MpTaps t = mp_taps(valid ? u : 0.f, valid ? v : 0.f, prm.H, prm.W);
-          const bool dead = !valid || !(u == u) || !(v == v);
-#pragma unroll
-          for (int a = 0; a < 4; ++a) { my_off[a] = dead ? 0 : t.off[a]; my_wgt[a] = dead ? 0.f : t.wgt[a]; }
-          my_zf = w * cal.z_scale;
-          if (lane < 16) {
-            s_zf[wk * 16 + lane] = my_zf;
-            s_in[wk * 16 + lane] = in_img ? 1.f : 0.f;
-          }
-        }
-        float s4part[kMaxRes][16];               // this lane's partial last-layer skip dot for the 16 points
-#pragma unroll
-        for (int q0 = 0; q0 < 16; q0 += 4) {
-          uint4 raw[4][4];
-          float wgt[4][4];
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq)
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              const int off = __shfl_sync(0xffffffffu, my_off[a], q0 + qq);
-              wgt[qq][a] = __shfl_sync(0xffffffffu, my_wgt[a], q0 + qq);
-              raw[qq][a] = __ldg(reinterpret_cast<const uint4*>(prm.feat + (size_t)off * kC + cbase));
-            }
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            const int p = wk * 16 + q0 + qq;
-            float acc[8];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              const __half2* h2 = reinterpret_cast<const __half2*>(&raw[qq][a]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h2[j]);
-                acc[2 * j] = (a == 0) ? f.x * wgt[qq][a] : acc[2 * j] + f.x * wgt[qq][a];
-                acc[2 * j + 1] = (a == 0) ? f.y * wgt[qq][a] : acc[2 * j + 1] + f.y * wgt[qq][a];
-              }
-            }
-            uint4 packed;
-            packed.x = tc::pack_half2(acc[0], acc[1]);
-            packed.y = tc::pack_half2(acc[2], acc[3]);
-            packed.z = tc::pack_half2(acc[4], acc[5]);
-            packed.w = tc::pack_half2(acc[6], acc[7]);
-            const int kb = lane >> 3;
-            *reinterpret_cast<uint4*>(smem + Smem::X + kb * 16384 + tc::sw128_offset(p, (lane & 7) * 8)) = packed;
-#pragma unroll
-            for (int r = 0; r < kMaxRes; ++r) {
-              float sacc = 0.f;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) sacc = fmaf(w4s[r][j], acc[j], sacc);
-              s4part[r][q0 + qq] = sacc;
-            }
-          }
-        }
-        // fp32 skip part of the last layer: sum_c w4[128 + c] * x_c.  Transposing warp reduction of the 16 partials:
-        // after step k every lane holds half as many sums; 16+8+4+2 = 30 shuffles instead of 16*5.
-#pragma unroll
-        for (int r = 0; r < kMaxRes; ++r) {
-          if (r < res) {
-            float v16[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v16[j] = s4part[r][j];
-            // fold over lane bit 4 first (plain butterfly), then distribute points over lane bits 3..0
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v16[j] += __shfl_xor_sync(0xffffffffu, v16[j], 16);
-            float v8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const bool up = lane & 8;
-              const float keep = up ? v16[j + 8] : v16[j], send = up ? v16[j] : v16[j + 8];
-              v8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-            float v4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const bool up = lane & 4;
-              const float keep = up ? v8[j + 4] : v8[j], send = up ? v8[j] : v8[j + 4];
-              v4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-            float v2[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const bool up = lane & 2;
-              const float keep = up ? v4[j + 2] : v4[j], send = up ? v4[j] : v4[j + 2];
-              v2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-            const bool up = lane & 1;
-            const float keep = up ? v2[1] : v2[0], send = up ? v2[0] : v2[1];
-            const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-            // lane L (< 16) now holds the total of point index ((L&8) | (L&4) | (L&2) | (L&1)) = L
-            const float zq = __shfl_sync(0xffffffffu, my_zf, lane & 15);
-            if (lane < 16) s_s4[r * kTile + wk * 16 + lane] = tot + __ldg(prm.w4z + r) * zq + __ldg(prm.b4 + r);
-          }
-        }
+          for (int j = 0; j < 8; ++j) w4s[r][j] = (r < res) ? __ldg(prm.w4s + r * kC + lane * 8 + j) : 0.f;
+        const PointTaps pt = point_taps(src, cal, prm.H, prm.W, p0 + wk * 16 + (lane & 15), n);
+        sample_x_group(prm, smem + Smem::X, s_zf, s_in, s_s4, pt, wk * 16, lane, w4s);
       }
       tc::fence_proxy_async_smem();
       // make s_zf/s_in/s_s4 visible to the epilogue role of all worker threads
@@ -994,109 +1015,8 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
 #pragma unroll 1
       for (int grp = 0; grp < 4; ++grp) {
         const int pbase = sw * 64 + grp * 16;
-        int my_off[4];
-        float my_wgt[4];
-        float my_zf;
-        bool my_in;
-        {
-          const long long i = p0 + pbase + (lane & 15);
-          float u = 0.f, v = 0.f, w = 0.f;
-          const bool valid = i < n;
-          if (valid) {
-            float x, y, z;
-            mp_load_point(src, i, x, y, z);
-            mp_project(cal, x, y, z, u, v, w);
-          }
-          my_in = valid && (u >= -1.f) && (u <= 1.f) && (v >= -1.f) && (v <= 1.f);
-          MpTaps t = mp_taps(valid ? u : 0.f, valid ? v : 0.f, prm.H, prm.W);
-          const bool dead = !valid || !(u == u) || !(v == v);
-#pragma unroll
-          for (int a = 0; a < 4; ++a) { my_off[a] = dead ? 0 : t.off[a]; my_wgt[a] = dead ? 0.f : t.wgt[a]; }
-          my_zf = w * cal.z_scale;
-        }
-        float s4part[kMaxRes][16];
-#pragma unroll
-        for (int q0 = 0; q0 < 16; q0 += 4) {
-          uint4 raw[4][4];
-          float wgt[4][4];
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq)
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              const int off = __shfl_sync(0xffffffffu, my_off[a], q0 + qq);
-              wgt[qq][a] = __shfl_sync(0xffffffffu, my_wgt[a], q0 + qq);
-              raw[qq][a] = __ldg(reinterpret_cast<const uint4*>(prm.feat + (size_t)off * kC + cbase));
-            }
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            const int p = pbase + q0 + qq;
-            float2 acc[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              const __half2* h2 = reinterpret_cast<const __half2*>(&raw[qq][a]);
-              const float2 w2 = make_float2(wgt[qq][a], wgt[qq][a]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h2[j]);
-                acc[j] = (a == 0) ? __fmul2_rn(f, w2) : __ffma2_rn(f, w2, acc[j]);
-              }
-            }
-            uint4 packed;
-            packed.x = tc::pack_half2(acc[0].x, acc[0].y);
-            packed.y = tc::pack_half2(acc[1].x, acc[1].y);
-            packed.z = tc::pack_half2(acc[2].x, acc[2].y);
-            packed.w = tc::pack_half2(acc[3].x, acc[3].y);
-            const int kb = lane >> 3;
-            *reinterpret_cast<uint4*>(smem + Smem::X + kb * 16384 + tc::sw128_offset(p, (lane & 7) * 8)) = packed;
-#pragma unroll
-            for (int r = 0; r < kMaxRes; ++r) {
-              float sacc = 0.f;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                sacc = fmaf(w4s[r][2 * j], acc[j].x, sacc);
-                sacc = fmaf(w4s[r][2 * j + 1], acc[j].y, sacc);
-              }
-              s4part[r][q0 + qq] = sacc;
-            }
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < kMaxRes; ++r) {
-          if (r < res) {
-            float v16[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v16[j] = s4part[r][j] + __shfl_xor_sync(0xffffffffu, s4part[r][j], 16);
-            float v8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const bool up = lane & 8;
-              const float keep = up ? v16[j + 8] : v16[j], send = up ? v16[j] : v16[j + 8];
-              v8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-            float v4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const bool up = lane & 4;
-              const float keep = up ? v8[j + 4] : v8[j], send = up ? v8[j] : v8[j + 4];
-              v4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-            float v2[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const bool up = lane & 2;
-              const float keep = up ? v4[j + 2] : v4[j], send = up ? v4[j] : v4[j + 2];
-              v2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-            const bool up = lane & 1;
-            const float keep = up ? v2[1] : v2[0], send = up ? v2[0] : v2[1];
-            const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-            if (lane < 16) s_s4[r * kTile + pbase + lane] = tot + __ldg(prm.w4z + r) * my_zf + __ldg(prm.b4 + r);
-          }
-        }
-        if (lane < 16) {
-          s_zf[pbase + lane] = my_zf;
-          s_in[pbase + lane] = my_in ? 1.f : 0.f;
-        }
+        const PointTaps pt = point_taps(src, cal, prm.H, prm.W, p0 + pbase + (lane & 15), n);
+        sample_x_group(prm, smem + Smem::X, s_zf, s_in, s_s4, pt, pbase, lane, w4s);
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
@@ -1126,21 +1046,10 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     float my_wgt[4];
     float my_zf = 0.f;
     auto compute_taps = [&](long long g) {
-      {
-        const long long i = (g * CG + rank) * kTile + wk * 16 + l16;
-        float u = 0.f, v = 0.f, w = 0.f;
-        const bool valid = i < n;
-        if (valid) {
-          float x, y, z;
-          mp_load_point(src, i, x, y, z);
-          mp_project(cal, x, y, z, u, v, w);
-        }
-        MpTaps t = mp_taps(valid ? u : 0.f, valid ? v : 0.f, prm.H, prm.W);
-        const bool dead = !valid || !(u == u) || !(v == v);
+      const PointTaps pt = point_taps(src, cal, prm.H, prm.W, (g * CG + rank) * kTile + wk * 16 + l16, n);
 #pragma unroll
-        for (int a = 0; a < 4; ++a) { my_off[a] = dead ? 0 : t.off[a]; my_wgt[a] = dead ? 0.f : t.wgt[a]; }
-        my_zf = w * cal.z_scale;
-      }
+      for (int a = 0; a < 4; ++a) { my_off[a] = pt.off[a]; my_wgt[a] = pt.wgt[a]; }
+      my_zf = pt.zf;
     };
     {
       // ---- one sampled layer-0 chunk: h0[:, c*128 .. +128) = lrelu(lerp(G0) + b0 + w0z z) -> H0 smem buffer c&1.
