@@ -11,6 +11,7 @@ runs in the sm_100a kernels of csrc/octree.cu through the C-ABI.  Two drive mode
               at the end (mp_octree_run_fused).
 """
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -54,9 +55,9 @@ class _Seg3dBase(nn.Module):
         self._handles = {}
         self.last_stats = None
 
-    # one engine workspace per device
+    # one engine workspace per (device, calling thread)
     def _handle(self, device):
-        key = device.index if device.index is not None else torch.cuda.current_device()
+        key = (device.index if device.index is not None else torch.cuda.current_device(), threading.get_ident())
         h = self._handles.get(key)
         if h is None:
             n = len(self.resolutions)

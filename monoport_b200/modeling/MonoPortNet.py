@@ -4,6 +4,7 @@ through the C-ABI of libmonoport_b200.  There is no PyTorch / CPU fallback for q
 library raise."""
 import ctypes
 import os
+import threading
 
 import torch
 import torch.nn as nn
@@ -78,7 +79,9 @@ class MonoPortNet(nn.Module):
         if feat.device.type != "cuda":
             raise RuntimeError("monoport_b200.query: features must be CUDA tensors (there is no CPU path)")
         _, C, H, W = feat.shape
-        key = (C, H, W, feat.device.index)
+        # one handle per calling thread: the handle carries the channel-last copies of the CURRENT frame, and the
+        # demo-style pipelines query different frames from different threads (RTL/dataloader.py:734-751)
+        key = (C, H, W, feat.device.index, threading.get_ident())
         h = self._feat_handles.get(key)
         if h is None:
             h = self._feat_handles[key] = FeatureHandle(C, H, W, feat.device)

@@ -6,6 +6,7 @@
                                  `reconstruction` follows upstream PIFu's signature).
 """
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -60,7 +61,7 @@ class _McubesWorkspace:
 
     @classmethod
     def get(cls, shape, device):
-        key = (tuple(shape), device.index)
+        key = (tuple(shape), device.index, threading.get_ident())
         h = cls._cache.get(key)
         if h is None:
             h = ctypes.c_void_p()

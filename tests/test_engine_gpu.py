@@ -207,3 +207,36 @@ def test_colorization_matches_restatement():
     wantn = spec.colorization_ref(None, Xo, Yo, Zo, cal, resolution=65, norm=spec.forward_vertices_ref(vol, "front")[3])
     assert torch.allclose(imgn.cpu(), wantn, atol=1e-6, equal_nan=True)
     assert colorization(netC, None, None, None, None, cal.cuda()) is None
+
+
+def test_frame_pipeline_overlap_equals_sequential():
+    """processors=[...] pipeline with 2 overlapping lanes (threads + streams) == the same stages run sequentially."""
+    from monoport_b200.engine import Seg3dLossless, make_query_func
+    from monoport_b200.pipeline import FramePipeline
+    from monoport_b200.recon import forward_vertices
+    Ws, bs = spec.make_weights(spec.G_CHANNELS, 3)
+    base = spec.make_feat(256, 128, 128, 4, 0.5)
+    feats = []
+    for k in range(3):
+        W2, b2, f, _ = spec.heightfield_person(Ws, bs, base * (1.0 + 0.1 * k), channel=0)
+        feats.append(f.cuda())
+    net = build_net("G", W2, b2)
+    net.precision = "tc_v2"
+    cal = spec.scene_calib(20, 33).cuda()
+    b = np.array([[-1.0, -1.0, -1.0]], dtype=np.float32)
+    eng = Seg3dLossless(make_query_func(net), b, -b, [17, 33, 65], balance_value=0.5, faster=True).to("cuda")
+
+    def recon_stage(f):
+        return eng(im_feat_list=[[f]], calib_tensor=cal)
+
+    def surf_stage(sdf):
+        X, Y, Z, n = forward_vertices(sdf, "front")
+        return sdf, X, Y, Z
+
+    seq = [surf_stage(recon_stage(f)) for f in (feats * 3)]
+    pipe = FramePipeline([recon_stage, surf_stage], "cuda:0", n_lanes=2)
+    par = list(pipe.run(f for f in (feats * 3)))
+    pipe.close()
+    assert len(par) == len(seq) == 9
+    for a, c in zip(seq, par):
+        assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1]) and torch.equal(a[3], c[3])

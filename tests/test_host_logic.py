@@ -132,3 +132,28 @@ def test_level_points_convention():
     # node centres: (c+0.5)/R mapped to [b_min,b_max]; the R (not R-1) divisor mirrors mat_color, RTL/main.py:204-209
     p = spec.level_points(torch.tensor([[0, 0, 0], [256, 256, 256]]), 257, (-1, -1, -1), (1, 1, 1))
     assert torch.allclose(p[0], torch.full((3,), -1 + 1 / 257)) and torch.allclose(p[1], torch.full((3,), 1 - 1 / 257))
+
+
+def test_obj_writer_matches_reference_format(tmp_path):
+    """Same bytes as monoport/lib/mesh_util.py:223-242 (run against the reference when it is present)."""
+    from monoport.lib.mesh_util import save_obj_mesh, save_obj_mesh_with_color
+    rng = np.random.default_rng(0)
+    V = rng.normal(size=(57, 3)).astype(np.float32)
+    Fc = rng.integers(0, 57, size=(101, 3)).astype(np.int32)
+    C = rng.random((57, 3)).astype(np.float32)
+    a, b = tmp_path / "a.obj", tmp_path / "b.obj"
+    save_obj_mesh(str(a), V, Fc)
+    save_obj_mesh_with_color(str(b), torch.from_numpy(V), torch.from_numpy(Fc), C)
+    la, lb = a.read_text().splitlines(), b.read_text().splitlines()
+    assert len(la) == 57 + 101 and la[0] == "v %.4f %.4f %.4f" % tuple(V[0]) and la[57] == "f %d %d %d" % tuple(Fc[0] + 1)
+    assert lb[0] == "v %.4f %.4f %.4f %.4f %.4f %.4f" % (tuple(V[0]) + tuple(C[0]))
+    from oracle import ref_loader
+    if ref_loader.available():
+        import importlib.util, os
+        spec_ = importlib.util.spec_from_file_location("_ref_mesh_util", os.path.join(ref_loader.REF_ROOT, "monoport/lib/mesh_util.py"))
+        ref = importlib.util.module_from_spec(spec_)
+        spec_.loader.exec_module(ref)
+        ra, rb = tmp_path / "ra.obj", tmp_path / "rb.obj"
+        ref.save_obj_mesh(str(ra), V, Fc)
+        ref.save_obj_mesh_with_color(str(rb), V, Fc, C)
+        assert ra.read_text() == a.read_text() and rb.read_text() == b.read_text()
