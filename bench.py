@@ -337,6 +337,7 @@ def run_ours(args):
             v, fcs = marching_cubes(sdf[0, 0])
         torch.cuda.synchronize()
         fps_mc = nfr / (time.perf_counter() - t0)
+        recon_stats = list(eng.last_stats)
         # configs[2]: geometry + colour -- netC (513-wide head, fp32 fused kernel) queried at the visible vertices
         from monoport_b200.modeling import PIFuNetC
         from monoport_b200.recon import colorization
@@ -383,10 +384,13 @@ def run_ours(args):
                 stream_fps[lanes] = nst / (time.perf_counter() - t0)
                 pipe.close()
         recon = {"workload": "configs[1]: netG 256^3 Seg3dLossless(faster=True) from resident features, per frame",
-                 "frames_per_s_stream_with_pytorch_encoder": {"1_lane": stream_fps[1], "2_lanes": stream_fps[2]},
+                 "frames_per_s_stream_with_pytorch_encoder": {
+                     "1_lane": stream_fps[1], "2_lanes": stream_fps[2],
+                     "note": "512x512 frame -> HGFilter (PyTorch fp32, random init => noise field, %d points/frame) -> recon -> "
+                             "forward_vertices; lanes = overlapped frames (FramePipeline)" % int(sum(eng.last_stats))},
                  "frames_per_s_geometry_plus_netC_colour": fps_color,
                  "frames_per_s_with_forward_vertices": fps_fv, "frames_per_s_with_marching_cubes": fps_mc,
-                 "points_evaluated_per_frame": int(sum(eng.last_stats)), "per_level": eng.last_stats,
+                 "points_evaluated_per_frame": int(sum(recon_stats)), "per_level": recon_stats,
                  "visible_vertices": int(X.numel()), "mesh_vertices": int(v.shape[0]), "mesh_faces": int(fcs.shape[0])}
 
     # ---- CPU baseline (reported, not the target): the oracle port on a bounded sample, rank 0, N=1 only ----
