@@ -72,8 +72,8 @@ int mp_mlp_tc_supported(const mp_mlp_t* h);
 
 /* ---------------------------------------------------------------------------------------------
  * Feature volume.  Replaces the tensor index() samples (geometry.py:4-16): one [C,H,W] fp32 NCHW map
- * (the last hourglass stage in eval mode, MonoPortNet.py:63-64).  The handle keeps channel-last
- * copies (fp32 + fp16) so one bilinear tap is one contiguous vector.
+ * (the last hourglass stage in eval mode, MonoPortNet.py:63-64).  The handle keeps a channel-last fp32
+ * copy so one bilinear tap is one contiguous vector (taps are always read in fp32).
  * ------------------------------------------------------------------------------------------- */
 typedef struct mp_feat mp_feat_t;
 int mp_feat_create(int C, int H, int W, mp_feat_t** out);

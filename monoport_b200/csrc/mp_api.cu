@@ -118,10 +118,9 @@ extern "C" int mp_mlp_create(int n_layers, const int* channels, const float* con
 extern "C" int mp_mlp_tc_supported(const mp_mlp_t* h) { return h ? h->tc_ok : 0; }
 
 // ---------------------------------------------------------------------------------------------
-// feature volume: NCHW fp32 -> NHWC fp32 + NHWC fp16
+// feature volume: NCHW fp32 -> NHWC fp32 (channel-last: one bilinear tap = one contiguous vector)
 // ---------------------------------------------------------------------------------------------
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ o32, __half* __restrict__ o16,
-                                    int C, int HW) {
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ o32, int C, int HW) {
   // tile transpose [C][HW] -> [HW][C]
   __shared__ float tile[32][33];
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -133,9 +132,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restr
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int p = p0 + j, c = c0 + threadIdx.x;
     if (p < HW && c < C) {
-      const float v = tile[threadIdx.x][j];
-      o32[(size_t)p * C + c] = v;
-      o16[(size_t)p * C + c] = __float2half_rn(v);
+      o32[(size_t)p * C + c] = tile[threadIdx.x][j];
     }
   }
 }
@@ -143,7 +140,6 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restr
 extern "C" int mp_feat_destroy(mp_feat_t* h) {
   if (!h) return MP_OK;
   if (h->nhwc32) cudaFree(h->nhwc32);
-  if (h->nhwc16) cudaFree(h->nhwc16);
   if (h->staging) cudaFree(h->staging);
   if (h->g0) cudaFree(h->g0);
   delete h;
@@ -160,7 +156,6 @@ extern "C" int mp_feat_create(int C, int H, int W, mp_feat_t** out) {
   cudaGetDevice(&h->device);
   const size_t n = (size_t)C * H * W;
   cudaError_t e = cudaMalloc(&h->nhwc32, n * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&h->nhwc16, n * sizeof(__half));
   if (e == cudaSuccess) e = cudaMalloc(&h->staging, n * sizeof(float));
   if (e != cudaSuccess) {
     mp_set_error("mp_feat_create: %s", cudaGetErrorString(e));
@@ -182,7 +177,7 @@ extern "C" int mp_feat_upload(mp_feat_t* h, const float* nchw, int on_device, vo
   }
   const int HW = h->H * h->W;
   dim3 grid((HW + 31) / 32, (h->C + 31) / 32), block(32, 8);
-  nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(src, h->nhwc32, h->nhwc16, h->C, HW);
+  nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(src, h->nhwc32, h->C, HW);
   MP_CUDA(cudaGetLastError());
   h->version += 1;
   return MP_OK;

@@ -98,7 +98,8 @@ struct TcParams {
   int res;
   int last_op;
   int H, W;
-  const __half* feat;     // NHWC fp16
+  const float* feat32;    // NHWC fp32 (bilinear taps are read in fp32: the last layer's skip access to the input
+                          // makes the output sensitive to the precision of x -- see DESIGN.md, precision)
   const __half* g0;       // v3: [H*W][1024] fp16 per-texel layer-0 product
   const float* d_bias0;
   const float* d_wz0;
@@ -199,7 +200,8 @@ __device__ __forceinline__ float warp_reduce16(const float (&part)[16], int lane
 }
 
 // Whole warp: sample the 16 points whose taps sit in lanes 0..15 (`pt`, duplicated in lanes 16..31) into rows
-// [pbase, pbase+16) of the fp16 X tile (K-major SWIZZLE_128B, 4 K-blocks of 64 channels; lane covers 8 channels) and
+// [pbase, pbase+16) of the fp16 X tile (K-major SWIZZLE_128B, 4 K-blocks of 64 channels; lane covers 8 channels; the
+// taps are read from the fp32 map and the interpolated value is rounded to fp16 exactly once) and
 // publish the per-point scalars: depth feature, in-image flag and the fp32 skip part of the last layer
 // sum_c w4[128 + c] * x_c + w4z * z + b4 (computed from the fp32 samples, before they are rounded to fp16).
 __device__ __forceinline__ void sample_x_group(const TcParams& prm, uint8_t* smem_x, float* s_zf, float* s_in, float* s_s4,
@@ -207,30 +209,30 @@ __device__ __forceinline__ void sample_x_group(const TcParams& prm, uint8_t* sme
   const int cbase = lane * 8;
   float s4part[kMaxRes][16];
 #pragma unroll
-  for (int q0 = 0; q0 < 16; q0 += 4) {
-    uint4 raw[4][4];
-    float wgt[4][4];
+  for (int q0 = 0; q0 < 16; q0 += 2) {
+    float4 raw[2][4][2];                     // [point][tap][8 fp32 channels]
+    float wgt[2][4];
 #pragma unroll
-    for (int qq = 0; qq < 4; ++qq)
+    for (int qq = 0; qq < 2; ++qq)
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         const int off = __shfl_sync(0xffffffffu, pt.off[a], q0 + qq);
         wgt[qq][a] = __shfl_sync(0xffffffffu, pt.wgt[a], q0 + qq);
-        raw[qq][a] = __ldg(reinterpret_cast<const uint4*>(prm.feat + (size_t)off * kC + cbase));
+        const float4* src4 = reinterpret_cast<const float4*>(prm.feat32 + (size_t)off * kC + cbase);
+        raw[qq][a][0] = __ldg(src4);
+        raw[qq][a][1] = __ldg(src4 + 1);
       }
 #pragma unroll
-    for (int qq = 0; qq < 4; ++qq) {
+    for (int qq = 0; qq < 2; ++qq) {
       const int p = pbase + q0 + qq;
       float2 acc[4];
 #pragma unroll
       for (int a = 0; a < 4; ++a) {                   // same accumulation order as grid_sample: nw, ne, sw, se
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[qq][a]);
         const float2 w2 = make_float2(wgt[qq][a], wgt[qq][a]);
+        const float2 f[4] = {make_float2(raw[qq][a][0].x, raw[qq][a][0].y), make_float2(raw[qq][a][0].z, raw[qq][a][0].w),
+                             make_float2(raw[qq][a][1].x, raw[qq][a][1].y), make_float2(raw[qq][a][1].z, raw[qq][a][1].w)};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(h2[j]);
-          acc[j] = (a == 0) ? __fmul2_rn(f, w2) : __ffma2_rn(f, w2, acc[j]);
-        }
+        for (int j = 0; j < 4; ++j) acc[j] = (a == 0) ? __fmul2_rn(f[j], w2) : __ffma2_rn(f[j], w2, acc[j]);
       }
       uint4 packed;
       packed.x = tc::pack_half2(acc[0].x, acc[0].y);
@@ -1538,7 +1540,7 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
   prm.res = pk->res;
   prm.last_op = mlp->last_op;
   prm.H = feat->H; prm.W = feat->W;
-  prm.feat = feat->nhwc16;
+  prm.feat32 = feat->nhwc32;
   int dev = 0, sms = 148;
   MP_CUDA(cudaGetDevice(&dev));
   MP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
