@@ -14,9 +14,9 @@ from helpers import build_net, load_query_case, query_cases
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 2e-5, "tc": 1e-4, "tc_v2": 1e-4, "tc_v3": 1e-4}
-# stress case: features scaled x4 (N(0,16)) -- fp16 operand rounding scales with the activations; measured 2.4e-4
+# stress case: features scaled x4 (N(0,16)) -- fp16 operand rounding scales with the activations; measured 1.07e-4
 # with the tensor-core path (the survey's probe predicted >1e-4 here); fp32 mode stays at 2e-5.  See DESIGN.md §precision.
-TOL_STRESS = {"fp32": 2e-5, "tc": 4e-4, "tc_v2": 4e-4, "tc_v3": 4e-4}
+TOL_STRESS = {"fp32": 2e-5, "tc": 2e-4, "tc_v2": 2e-4, "tc_v3": 2e-4}
 
 
 def _modes(net):
