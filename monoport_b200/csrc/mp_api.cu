@@ -296,10 +296,8 @@ extern "C" int mp_query_grid(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0, int 
   mp_fill_calib(cal, calib12, projection, z_scale);
   MpOutDst dst;
   dst.out = out_dev; dst.ld = src.n; dst.scatter_vol = nullptr;
-  // The tensor-core program is chosen from the size of the WHOLE grid, not of the slab, so that a z-sharded volume is
-  // bit-identical to the single-GPU volume for every rank count.
-  if ((mode == MP_MODE_TC || mode == MP_MODE_AUTO) && mlp->tc_ok)
-    mode = ((long long)R * R * R >= (1ll << 20)) ? MP_MODE_TC_V3 : MP_MODE_TC_V2;
+  // (the tensor-core program never depends on the slab size, so a z-sharded volume is bit-identical to the single-GPU
+  // volume for every rank count)
   return mp_query_dispatch(mlp, feat, src, cal, dst, mode, (cudaStream_t)stream);
 }
 

@@ -24,42 +24,93 @@ __device__ __forceinline__ float up_axis(float a, float b, bool odd) {
 }
 
 // candidates_t may be null (top-k engine / last "faster" level): then only the interpolation runs.
+// One thread = one COARSE cell (k,j,i) -> its 2x2x2 fine nodes (2k+a, 2j+b, 2i+c): the eight corner loads are shared by
+// the eight interpolations (same operations per output as the per-node form, so bit-identical), and the eight box
+// tests share one pass over the union of their boxes -- per axis the box of parity 0 is [l0,h0], of parity 1 [l1,h1]
+// with l0<=l1<=h0<=h1, so the union is [l0,h1]; a box is "mixed" iff OR != AND of its occupancy bits, and OR/AND
+// separate per axis.  All loads are unconditional (no early exit) so they pipeline.
+// Launch: grid (ceil(res_c^2 / 256), res_c).
 __global__ void __launch_bounds__(256)
 upsample_kernel(const float* __restrict__ vc, const uint8_t* __restrict__ known_c, float* __restrict__ vf,
                 uint8_t* __restrict__ known_f, uint8_t* __restrict__ candidates_t, int res_c, int res_f, int radius,
                 float balance) {
-  const long long n = (long long)res_f * res_f * res_f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % res_f);
-    const int y = (int)((i / res_f) % res_f);
-    const int z = (int)(i / ((long long)res_f * res_f));
-    const int x0 = x >> 1, y0 = y >> 1, z0 = z >> 1;
-    const bool ox = x & 1, oy = y & 1, oz = z & 1;
-    const int x1 = x0 + (ox ? 1 : 0), y1 = y0 + (oy ? 1 : 0), z1 = z0 + (oz ? 1 : 0);
-    auto at = [&](int zz, int yy, int xx) { return __ldg(vc + ((long long)zz * res_c + yy) * res_c + xx); };
-    const float c00 = up_axis(at(z0, y0, x0), at(z0, y0, x1), ox);
-    const float c01 = up_axis(at(z0, y1, x0), at(z0, y1, x1), ox);
-    const float c10 = up_axis(at(z1, y0, x0), at(z1, y0, x1), ox);
-    const float c11 = up_axis(at(z1, y1, x0), at(z1, y1, x1), ox);
-    const float v = up_axis(up_axis(c00, c01, oy), up_axis(c10, c11, oy), oz);
-    vf[i] = v;
-    const bool known = !(ox || oy || oz) && (known_c == nullptr || known_c[((long long)z0 * res_c + y0) * res_c + x0]);
-    if (known_f) known_f[i] = known ? 1 : 0;
-    if (candidates_t) {
-      bool cand = false;
-      if (!known) {
-        const int lx = max(x - radius, 0) >> 1, hx = (min(x + radius, res_f - 1) + 1) >> 1;
-        const int ly = max(y - radius, 0) >> 1, hy = (min(y + radius, res_f - 1) + 1) >> 1;
-        const int lz = max(z - radius, 0) >> 1, hz = (min(z + radius, res_f - 1) + 1) >> 1;
-        const bool first = at(lz, ly, lx) > balance;
-        for (int zz = lz; zz <= hz && !cand; ++zz)
-          for (int yy = ly; yy <= hy && !cand; ++yy)
-            for (int xx = lx; xx <= hx; ++xx)
-              if ((at(zz, yy, xx) > balance) != first) { cand = true; break; }
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= res_c * res_c) return;
+  const int i = blockIdx.y;
+  const int j = p / res_c, k = p - j * res_c;
+  const int ex = (k + 1 < res_c) ? 1 : 0, ey = (j + 1 < res_c) ? 1 : 0, ez = (i + 1 < res_c) ? 1 : 0;   // odd nodes exist
+  float c[2][2][2];
+#pragma unroll
+  for (int zi = 0; zi < 2; ++zi)
+#pragma unroll
+    for (int yj = 0; yj < 2; ++yj) {
+      const float* row = vc + ((long long)(i + zi * ez) * res_c + (j + yj * ey)) * res_c + k;
+      c[zi][yj][0] = __ldg(row);
+      c[zi][yj][1] = __ldg(row + ex);
+    }
+  const long long plane_f = (long long)res_f * res_f;
+  const bool cell_known = known_c == nullptr || known_c[((long long)i * res_c + j) * res_c + k];
+#pragma unroll
+  for (int cz = 0; cz < 2; ++cz)
+#pragma unroll
+    for (int by = 0; by < 2; ++by)
+#pragma unroll
+      for (int ax = 0; ax < 2; ++ax) {
+        if ((cz && !ez) || (by && !ey) || (ax && !ex)) continue;
+        const float c00 = up_axis(c[0][0][0], c[0][0][1], ax), c01 = up_axis(c[0][1][0], c[0][1][1], ax);
+        const float c10 = up_axis(c[1][0][0], c[1][0][1], ax), c11 = up_axis(c[1][1][0], c[1][1][1], ax);
+        const float v = up_axis(up_axis(c00, c01, by), up_axis(c10, c11, by), cz);
+        const long long o = (long long)(2 * i + cz) * plane_f + (long long)(2 * j + by) * res_f + (2 * k + ax);
+        vf[o] = v;
+        if (known_f) known_f[o] = (!(cz | by | ax) && cell_known) ? 1 : 0;
       }
-      candidates_t[((long long)x * res_f + y) * res_f + z] = cand ? 1 : 0;
+  if (!candidates_t) return;
+  int lx[2], hx[2], ly[2], hy[2], lz[2], hz[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int fx = 2 * k + q, fy = 2 * j + q, fz = 2 * i + q;
+    lx[q] = max(fx - radius, 0) >> 1; hx[q] = (min(fx + radius, res_f - 1) + 1) >> 1;
+    ly[q] = max(fy - radius, 0) >> 1; hy[q] = (min(fy + radius, res_f - 1) + 1) >> 1;
+    lz[q] = max(fz - radius, 0) >> 1; hz[q] = (min(fz + radius, res_f - 1) + 1) >> 1;
+  }
+  // bit (4*cz + 2*by + ax) of orm / andm: OR / AND of the occupancy bits over that node's box
+  unsigned orm = 0u, andm = 0xFFu;
+  for (int zz = lz[0]; zz <= min(hz[1], res_c - 1); ++zz) {
+    const unsigned zin = ((zz <= hz[0]) ? 1u : 0u) | ((zz >= lz[1]) ? 2u : 0u);
+    for (int yy = ly[0]; yy <= min(hy[1], res_c - 1); ++yy) {
+      const unsigned yin = ((yy <= hy[0]) ? 1u : 0u) | ((yy >= ly[1]) ? 2u : 0u);
+      const float* row = vc + ((long long)zz * res_c + yy) * res_c;
+      unsigned o0 = 0u, a0 = 1u, o1 = 0u, a1 = 1u;
+#pragma unroll 6
+      for (int xx = lx[0]; xx <= min(hx[1], res_c - 1); ++xx) {
+        const unsigned bit = (__ldg(row + xx) > balance) ? 1u : 0u;
+        if (xx <= hx[0]) { o0 |= bit; a0 &= bit; }
+        if (xx >= lx[1]) { o1 |= bit; a1 &= bit; }
+      }
+      const unsigned orow = o0 | (o1 << 1), arow = a0 | (a1 << 1);   // per x parity
+#pragma unroll
+      for (int cz = 0; cz < 2; ++cz)
+#pragma unroll
+        for (int by = 0; by < 2; ++by)
+          if (((zin >> cz) & 1u) && ((yin >> by) & 1u)) {
+            const int sh = 4 * cz + 2 * by;
+            orm |= orow << sh;
+            andm &= ~(0x3u << sh) | (arow << sh);
+          }
     }
   }
+  const unsigned mixed = orm & ~andm;
+#pragma unroll
+  for (int cz = 0; cz < 2; ++cz)
+#pragma unroll
+    for (int by = 0; by < 2; ++by)
+#pragma unroll
+      for (int ax = 0; ax < 2; ++ax) {
+        if ((cz && !ez) || (by && !ey) || (ax && !ex)) continue;
+        const bool known = !(cz | by | ax) && cell_known;
+        const bool cand = !known && ((mixed >> (4 * cz + 2 * by + ax)) & 1u);
+        candidates_t[((long long)(2 * k + ax) * res_f + (2 * j + by)) * res_f + (2 * i + cz)] = cand ? 1 : 0;
+      }
 }
 
 // functors for the ordered compaction -------------------------------------------------------------
@@ -360,7 +411,7 @@ static int build_level_list(mp_octree* h, int level, cudaStream_t st) {
   const int src_buf = h->cur, dst_buf = h->cur ^ 1;
   const bool last = level == h->n_levels - 1;
   const bool interp_only = h->use_topk || (h->faster && last);
-  upsample_kernel<<<grid_for(nf), 256, 0, st>>>(h->vol[src_buf], h->use_topk ? nullptr : h->known[src_buf],
+  upsample_kernel<<<dim3((unsigned)(((long long)res_c * res_c + 255) / 256), (unsigned)res_c), 256, 0, st>>>(h->vol[src_buf], h->use_topk ? nullptr : h->known[src_buf],
                                                 h->vol[dst_buf], h->use_topk ? nullptr : h->known[dst_buf],
                                                 interp_only ? nullptr : h->cand_t, res_c, res_f, radius_for(h, level),
                                                 h->balance);
@@ -415,7 +466,7 @@ static int build_conflict_list(mp_octree* h, int level, cudaStream_t st) {
 static int reset_run(mp_octree* h, cudaStream_t st) {
   MP_CUDA(cudaMemsetAsync(h->nonempty, 0, sizeof(int), st));
   MP_CUDA(cudaMemsetAsync(h->stats, 0, sizeof(long long) * (MP_MAX_LAYERS + 4), st));
-  MP_CUDA(cudaMemsetAsync(h->conflict, 0, h->vol_elems, st));
+  if (!h->use_topk && !h->faster) MP_CUDA(cudaMemsetAsync(h->conflict, 0, h->vol_elems, st));   // only the lossless loop reads it
   h->cur = 0;
   return MP_OK;
 }
@@ -534,16 +585,8 @@ extern "C" int mp_octree_finish(mp_octree_t* h, float* out_dev, int* nonempty, v
 }
 
 // ---- fused run --------------------------------------------------------------------------------------
-extern "C" int mp_octree_run_fused(mp_octree_t* h, mp_mlp_t* mlp, mp_feat_t* feat, const float* calib12, int projection,
-                                   float z_scale, int mode, float* out_dev, int* nonempty, int64_t* stats_host,
-                                   void* stream) {
-  MP_REQUIRE(h && mlp && feat && out_dev && nonempty, "NULL argument");
-  MP_REQUIRE(mlp->cout[mlp->n_layers - 1] == 1, "the occupancy engine needs a single-channel head");
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc = reset_run(h, st);
-  if (rc != MP_OK) return rc;
-  MpCalib cal;
-  mp_fill_calib(cal, calib12, projection, z_scale);
+static int run_fused_levels(mp_octree* h, mp_mlp_t* mlp, mp_feat_t* feat, const MpCalib& cal, int mode, cudaStream_t st) {
+  int rc = MP_OK;
   // level 0: dense
   {
     const int r0 = h->res[0];
@@ -603,7 +646,30 @@ extern "C" int mp_octree_run_fused(mp_octree_t* h, mp_mlp_t* mlp, mp_feat_t* fea
     }
   }
   h->level = h->n_levels - 1;
-  MP_CUDA(cudaMemcpyAsync(out_dev, h->vol[h->cur], h->vol_elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return MP_OK;
+}
+
+extern "C" int mp_octree_run_fused(mp_octree_t* h, mp_mlp_t* mlp, mp_feat_t* feat, const float* calib12, int projection,
+                                   float z_scale, int mode, float* out_dev, int* nonempty, int64_t* stats_host,
+                                   void* stream) {
+  MP_REQUIRE(h && mlp && feat && out_dev && nonempty, "NULL argument");
+  MP_REQUIRE(mlp->cout[mlp->n_layers - 1] == 1, "the occupancy engine needs a single-channel head");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = reset_run(h, st);
+  if (rc != MP_OK) return rc;
+  MpCalib cal;
+  mp_fill_calib(cal, calib12, projection, z_scale);
+  // The level buffers ping-pong (level l is written to buffer l & 1), so the caller's volume stands in for the buffer
+  // the last level lands in: the result is produced in place instead of being copied out (68 MB at 257^3).
+  const int final_buf = (h->n_levels - 1) & 1;
+  float* const own_buf = h->vol[final_buf];
+  h->vol[final_buf] = out_dev;
+  rc = run_fused_levels(h, mlp, feat, cal, mode, st);
+  const bool in_place = h->cur == final_buf;
+  const float* result = h->vol[h->cur];
+  h->vol[final_buf] = own_buf;
+  if (rc != MP_OK) return rc;
+  if (!in_place) MP_CUDA(cudaMemcpyAsync(out_dev, result, h->vol_elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
   long long stats[MP_MAX_LAYERS + 4];
   int ne = 0;
   MP_CUDA(cudaMemcpyAsync(&ne, h->nonempty, sizeof(int), cudaMemcpyDeviceToHost, st));

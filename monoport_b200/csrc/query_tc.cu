@@ -70,9 +70,10 @@ struct TcPack {
   __half* wstream2[2];    // CG=2: per cluster rank, kStagesPerTile * 16 KB
   __half* w3stream;       // v3 (layer 0 hoisted to texels): kStagesPerTile3 * 32 KB
   __half* w3stream2[2];   // v3, CG=2
-  float* d_bias0;         // device copies for per-lane channel access (v3 H0 generation)
-  float* d_wz0;
-  float* d_w0f;           // [1024][256] fp32: feature part of layer 0 (operand of the per-texel G0 GEMM)
+  __half* d_bias0;        // fp16 device copies of the layer-0 bias / depth column for per-lane channel access (v3 H0 generation)
+  __half* d_wz0;
+  float* d_w0f;           // [1024][256] fp32: feature part of layer 0 (operand of the fp32 per-texel G0 GEMM, debug path)
+  uint8_t* d_w0t;         // the same as fp16 SWIZZLE_128B tiles [n tile 4][K block 4][256 x 64] for g0_tc_kernel
   float* bias[4];         // per hidden layer
   float* wz[4];           // z column of every hidden layer
   float h_bias[kSideFloats];   // host copies (passed by value in the kernel parameters)
@@ -101,10 +102,16 @@ struct TcParams {
   const float* feat32;    // NHWC fp32 (bilinear taps are read in fp32: the last layer's skip access to the input
                           // makes the output sensitive to the precision of x -- see DESIGN.md, precision)
   const __half* g0;       // v3: [H*W][1024] fp16 per-texel layer-0 product
-  const float* d_bias0;
-  const float* d_wz0;
+  const __half* d_bias0;  // v3: layer-0 bias and depth-feature column, fp16 [1024]
+  const __half* d_wz0;
   unsigned long long* prof;   // optional [gridDim.x][32] cycle counters (MONOPORT_B200_TC_PROF=1), else null
+  int exp;                    // timing experiments only (MONOPORT_B200_TC_EXP bitmask; results are WRONG when set):
+                              // 1 = weights not re-streamed, 2 = layer-0 gathers all hit texel 0, 4 = X taps all hit texel 0
+  unsigned long long* trace;  // optional [128] absolute clock64 stamps of CTA 0's tile kTraceTile (MONOPORT_B200_TC_TRACE=1)
 };
+constexpr int kTraceTile = 8;
+// v3 event ids: MMA issuer 0..31, worker warp 4 at 32.., worker warp 8 at 64.., sampler warp 2 at 96..
+#define TRACE(cond, id) do { if (prm.trace && (cond)) prm.trace[id] = (unsigned long long)clock64(); } while (0)
 enum Prof { P_TOTAL = 0, P_XREADY, P_ACC0FREE, P_WFULL, P_WPEER, P_H0READY, P_ACC1DRAINED, P_H1READY, P_H2READY,
             P_W_SAMPLE = 16, P_W_ACC0FULL, P_W_H0FREE, P_W_ACC1FULL, P_W_ACC2FULL, P_W_ACC3FULL, P_W_DRAIN0, P_W_DRAIN1,
             P_W_DRAIN2, P_W_DRAIN3, P_W_XFREE };
@@ -822,6 +829,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           const int slot = it % C::Stages;
           const uint32_t use = it / C::Stages;
           tc::mbar_wait(bars + B_WEMPTY + slot, (use & 1u) ^ 1u);
+          if ((prm.exp & 1) && it >= (uint32_t)C::Stages) { tc::mbar_arrive(bars + B_WFULL + slot); continue; }
           tc::mbar_arrive_expect_tx(bars + B_WFULL + slot, C::StageBytes);
           tc::bulk_g2s(smem + Smem::Wr + slot * C::StageBytes, wsrc + (size_t)s * C::StageBytes, C::StageBytes,
                        bars + B_WFULL + slot);
@@ -919,11 +927,14 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         // B_H2_READY, waited) and acc3 (drained by the fp32 tail: B_TILE_DONE)
         bool need_tile_done = g != g0;
         bool first1[2] = {true, true};
+        const bool tr = blockIdx.x == 0 && (g - g0) / gstep == kTraceTile;
+        TRACE(tr, 0);
         const long long t_ph0 = prof ? clock64() : 0;
         // ---- layer 1, hidden part: 8 sampled layer-0 chunks x 2 K-blocks x 2 output halves
         for (int c = 0; c < 8; ++c) {
           const int b = c & 1;
           { PROF_T0(); wait_both(B_H0_READY0 + b, B_P_H0_0 + b, c_h0ready[b]); PROF_ADD(P_H0READY); }
+          TRACE(tr, 1 + c);
           tc::tcgen05_fence_after();
           for (int kb = 0; kb < 2; ++kb)
             for (int nh = 0; nh < 2; ++nh) {
@@ -943,8 +954,10 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           commit<CG>(bars + B_H0_FREE0 + b);
         }
         if (prof) prof[9] += (unsigned long long)(clock64() - t_ph0);
+        TRACE(tr, 9);
         // ---- layer 1, skip part: A = X
         { PROF_T0(); wait_both(B_XREADY, B_P_X, c_xready); PROF_ADD(P_XREADY); }
+        TRACE(tr, 10);
         const long long t_ph1 = prof ? clock64() : 0;
         tc::tcgen05_fence_after();
         for (int kb = 0; kb < 4; ++kb)
@@ -955,8 +968,10 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           }
         commit<CG>(bars + B_ACC1_FULL);
         if (prof) prof[10] += (unsigned long long)(clock64() - t_ph1);
+        TRACE(tr, 11);
         // ---- layer 2: A = H1 from TMEM (8 K-blocks) + X (4 K-blocks) -> acc2 [128,384)
         { PROF_T0(); wait_both(B_H1_READY, B_P_H1, c_h1ready); PROF_ADD(P_H1READY); }
+        TRACE(tr, 12);
         tc::tcgen05_fence_after();
         {
           const long long t_ph2 = prof ? clock64() : 0;
@@ -974,6 +989,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             release_stage();
           }
           commit<CG>(bars + B_ACC2_FULL);
+          TRACE(tr, 13);
         }
         // ---- layer 3 -> acc3 [384,512); skip part first, then X is dead
         {
@@ -985,7 +1001,9 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             release_stage();
           }
           commit<CG>(bars + B_XFREE);
+          TRACE(tr, 14);
           { PROF_T0(); wait_both(B_H2_READY, B_P_H2, c_h2ready); PROF_ADD(P_H2READY); }
+          TRACE(tr, 15);
           tc::tcgen05_fence_after();
           for (int s = 0; s < 2; ++s) {
             const uint32_t w = next_stage();
@@ -994,6 +1012,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             release_stage();
           }
           commit<CG>(bars + B_ACC3_FULL);
+          TRACE(tr, 16);
         }
       }
       if (prof) prof[P_TOTAL] = (unsigned long long)(clock64() - t_begin);
@@ -1013,17 +1032,22 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     for (long long g = g0; g < n_groups; g += gstep) {
       const long long tile = g * CG + rank;
       const long long p0 = tile * kTile;
+      const bool tr = blockIdx.x == 0 && sw == 0 && lane == 0 && (g - g0) / gstep == kTraceTile;
+      TRACE(tr, 96);
       if (g != g0) wait_bar(bars, B_XFREE, c_xfree);
+      TRACE(tr, 97);
 #pragma unroll 1
       for (int grp = 0; grp < 4; ++grp) {
         const int pbase = sw * 64 + grp * 16;
-        const PointTaps pt = point_taps(src, cal, prm.H, prm.W, p0 + pbase + (lane & 15), n);
+        PointTaps pt = point_taps(src, cal, prm.H, prm.W, p0 + pbase + (lane & 15), n);
+        if (prm.exp & 4) { pt.off[0] = pt.off[1] = pt.off[2] = pt.off[3] = 0; }
         sample_x_group(prm, smem + Smem::X, s_zf, s_in, s_s4, pt, pbase, lane, w4s);
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(bars + B_ACC0_FULL0);        // scalars ready (CTA-local, release)
       warp_arrive_local(bars + B_XREADY, lane);
+      TRACE(tr, 98);
     }
   } else if (warp >= 4) {
     // ============================== workers: layer-0 chunk generators + epilogue ==============================
@@ -1035,7 +1059,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     uint32_t c_sready = 0, c_h0free[2] = {0, 0}, c_acc1full = 0, c_acc2full = 0, c_acc3full = 0;
     const int res = prm.res;
     if (!(warp == 4 && lane == 0)) prof = nullptr;
-    const int l16 = lane & 15, hw = lane >> 4;
+    const int l16 = lane & 15;
 
     auto act_pack = [&](float a, float b) -> uint32_t {
       const __half2 h = __floats2half2_rn(a, b);
@@ -1043,73 +1067,98 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       return *reinterpret_cast<const uint32_t*>(&r);
     };
 
-    // ---- projection + taps of this warp's 16 points of a tile (lane q and q+16 both hold point q)
-    int my_off[4];
-    float my_wgt[4];
-    float my_zf = 0.f;
+    // ---- projection + taps of this warp's 16 points of a tile.  A quarter-warp (8 lanes x 16 channels) covers one
+    //      point, so a lane works on four fixed points (q = 4*i + lane/8) for the whole tile and keeps their taps in
+    //      registers: texel indices packed two per register (H*W <= 65536), weights and depth feature as fp16.
+    const int l8 = lane & 7, qw = lane >> 3;
+    uint32_t t_off[4][2], t_wgt[4][2], t_z[4];
+    int gtr = -1;                              // trace slot base for the chunk being generated (-1: off)
     auto compute_taps = [&](long long g) {
       const PointTaps pt = point_taps(src, cal, prm.H, prm.W, (g * CG + rank) * kTile + wk * 16 + l16, n);
+      const uint32_t o01 = (uint32_t)pt.off[0] | ((uint32_t)pt.off[1] << 16), o23 = (uint32_t)pt.off[2] | ((uint32_t)pt.off[3] << 16);
+      const uint32_t w01 = tc::pack_half2(pt.wgt[0], pt.wgt[1]), w23 = tc::pack_half2(pt.wgt[2], pt.wgt[3]);
+      const uint32_t zz = tc::pack_half2(pt.zf, pt.zf);
 #pragma unroll
-      for (int a = 0; a < 4; ++a) { my_off[a] = pt.off[a]; my_wgt[a] = pt.wgt[a]; }
-      my_zf = pt.zf;
+      for (int i = 0; i < 4; ++i) {
+        const int q = 4 * i + qw;
+        t_off[i][0] = __shfl_sync(0xffffffffu, o01, q);
+        t_off[i][1] = __shfl_sync(0xffffffffu, o23, q);
+        t_wgt[i][0] = __shfl_sync(0xffffffffu, w01, q);
+        t_wgt[i][1] = __shfl_sync(0xffffffffu, w23, q);
+        t_z[i] = __shfl_sync(0xffffffffu, zz, q);
+      }
     };
     {
       // ---- one sampled layer-0 chunk: h0[:, c*128 .. +128) = lrelu(lerp(G0) + b0 + w0z z) -> H0 smem buffer c&1.
-      //      A half-warp covers one point (16 lanes x 8 channels), so a pass handles 2 of the warp's 16 points.
+      //      The interpolation runs on packed fp16 FMAs (HFMA2: the taps are fp16 already, so no conversions): a
+      //      lane loads 2 x 16 B per tap (channels 8*l8.. of both 64-channel K-blocks) and issues 8 HFMA2 per tap.
+      //      tools/precision_emulate.py: the extra fp16 roundings do not move the output error (2.76e-5 vs 2.75e-5).
       auto gen_chunk = [&](int c) {
         const int b = c & 1;
+        TRACE(gtr >= 0, gtr + 0);
         { PROF_T0(); wait_free(bars, B_H0_FREE0 + b, c_h0free[b]); PROF_ADD(P_W_H0FREE); }
+        TRACE(gtr >= 0, gtr + 1);
         PROF_T0();
-        const int ch = c * 128 + l16 * 8;
-        const float4 bA = __ldg(reinterpret_cast<const float4*>(prm.d_bias0 + ch));
-        const float4 bB = __ldg(reinterpret_cast<const float4*>(prm.d_bias0 + ch) + 1);
-        const float4 zA = __ldg(reinterpret_cast<const float4*>(prm.d_wz0 + ch));
-        const float4 zB = __ldg(reinterpret_cast<const float4*>(prm.d_wz0 + ch) + 1);
-        const float b8[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
-        const float z8[8] = {zA.x, zA.y, zA.z, zA.w, zB.x, zB.y, zB.z, zB.w};
-        uint8_t* dstp = smem + Smem::H0 + b * 32768 + (l16 >> 3) * 16384;
-#pragma unroll 1
-        for (int batch = 0; batch < 2; ++batch) {
-          uint4 raw[4][4];
-          float wgt[4][4];
-          float zq[4];
+        const int ch = c * 128 + l8 * 8;
+        __half2 b8[8], z8[8];
+        {
+          const uint4 bA = __ldg(reinterpret_cast<const uint4*>(prm.d_bias0 + ch)), bB = __ldg(reinterpret_cast<const uint4*>(prm.d_bias0 + ch + 64));
+          const uint4 zA = __ldg(reinterpret_cast<const uint4*>(prm.d_wz0 + ch)), zB = __ldg(reinterpret_cast<const uint4*>(prm.d_wz0 + ch + 64));
+          *reinterpret_cast<uint4*>(&b8[0]) = bA; *reinterpret_cast<uint4*>(&b8[4]) = bB;
+          *reinterpret_cast<uint4*>(&z8[0]) = zA; *reinterpret_cast<uint4*>(&z8[4]) = zB;
+        }
+        uint8_t* dstp = smem + Smem::H0 + b * 32768;
+        const __half2 slope2 = __float2half2_rn(MP_LEAKY_SLOPE);
 #pragma unroll
-          for (int ps = 0; ps < 4; ++ps) {
-            const int q = (batch * 4 + ps) * 2 + hw;
-            zq[ps] = __shfl_sync(0xffffffffu, my_zf, q);
+        for (int batch = 0; batch < 2; ++batch) {      // (unrolled: the tap registers are indexed statically)
+          uint4 raw[2][4][2];                  // [point][tap][K-block]
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              const int off = __shfl_sync(0xffffffffu, my_off[a], q);
-              wgt[ps][a] = __shfl_sync(0xffffffffu, my_wgt[a], q);
-              raw[ps][a] = __ldg(reinterpret_cast<const uint4*>(prm.g0 + (size_t)off * kL0 + ch));
-            }
-          }
-#pragma unroll
-          for (int ps = 0; ps < 4; ++ps) {
-            const int p = wk * 16 + (batch * 4 + ps) * 2 + hw;
-            // acc = b0 + w0z * z  (+ 4 taps), two channels per packed-fp32 instruction
-            const float2 zq2 = make_float2(zq[ps], zq[ps]);
-            float2 acc[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              acc[j] = __ffma2_rn(make_float2(z8[2 * j], z8[2 * j + 1]), zq2, make_float2(b8[2 * j], b8[2 * j + 1]));
+          for (int ps = 0; ps < 2; ++ps) {
+            const int i = batch * 2 + ps;
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-              const __half2* h2 = reinterpret_cast<const __half2*>(&raw[ps][a]);
-              const float2 w2 = make_float2(wgt[ps][a], wgt[ps][a]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(__half22float2(h2[j]), w2, acc[j]);
+              uint32_t off = (a & 1) ? (t_off[i][a >> 1] >> 16) : (t_off[i][a >> 1] & 0xFFFFu);
+              if (prm.exp & 2) off = 0;
+              const uint4* srcp = reinterpret_cast<const uint4*>(prm.g0 + (size_t)off * kL0 + ch);
+              raw[ps][a][0] = __ldg(srcp);
+              raw[ps][a][1] = __ldg(srcp + 8);      // + 64 channels
             }
-            uint4 pk;
-            pk.x = act_pack(acc[0].x, acc[0].y);
-            pk.y = act_pack(acc[1].x, acc[1].y);
-            pk.z = act_pack(acc[2].x, acc[2].y);
-            pk.w = act_pack(acc[3].x, acc[3].y);
-            *reinterpret_cast<uint4*>(dstp + tc::sw128_offset(p, (l16 & 7) * 8)) = pk;
           }
+          TRACE(gtr >= 0, gtr + 2 + 2 * batch);
+#pragma unroll
+          for (int ps = 0; ps < 2; ++ps) {
+            const int i = batch * 2 + ps;
+            const int p = wk * 16 + 4 * i + qw;
+            const __half2 zq2 = *reinterpret_cast<const __half2*>(&t_z[i]);
+            __half2 acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = __hfma2(z8[j], zq2, b8[j]);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {          // same tap order as grid_sample: nw, ne, sw, se
+              const __half2 wp = *reinterpret_cast<const __half2*>(&t_wgt[i][a >> 1]);
+              const __half2 w2 = (a & 1) ? __high2half2(wp) : __low2half2(wp);
+              const __half2* h0 = reinterpret_cast<const __half2*>(&raw[ps][a][0]);
+              const __half2* h1 = reinterpret_cast<const __half2*>(&raw[ps][a][1]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                acc[j] = __hfma2(h0[j], w2, acc[j]);
+                acc[4 + j] = __hfma2(h1[j], w2, acc[4 + j]);
+              }
+            }
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __half2 r = __hmax2(acc[j], __hmul2(acc[j], slope2));
+              o[j] = *reinterpret_cast<const uint32_t*>(&r);
+            }
+            *reinterpret_cast<uint4*>(dstp + tc::sw128_offset(p, l8 * 8)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(dstp + 16384 + tc::sw128_offset(p, l8 * 8)) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+          TRACE(gtr >= 0, gtr + 3 + 2 * batch);
         }
         tc::fence_proxy_async_smem();
         warp_arrive_local(bars + B_H0_READY0 + b, lane);
+        TRACE(gtr >= 0, gtr + 6);
         PROF_ADD(P_W_DRAIN0);
       };
       // The worker loop is software-pipelined across tiles: the first two sampled layer-0 chunks of the NEXT tile are
@@ -1140,12 +1189,16 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         const bool real = g >= g0;
         const bool has_next = g + gstep < n_groups;
         const long long p0 = (g * CG + rank) * kTile;
+        const bool tr = blockIdx.x == 0 && real && (wk & 3) == 0 && lane == 0 && (g - g0) / gstep == kTraceTile;
+        const int tb = 32 + wg * 32;
 #pragma unroll 1
         for (int step = 0; step < 11; ++step) {
+          TRACE(tr, tb + step);
           int gc = -1;
           if (step < 6) { if (real) gc = step + 2; }
           else if (step == 7) { if (has_next) { compute_taps(g + gstep); gc = 0; } }
           else if (step == 10) { if (has_next) gc = 1; }    // after the fp32 tail: B_TILE_DONE gates the next tile
+          gtr = (tr && step == 2) ? tb + 18 : -1;       // trace the inside of one chunk (chunk 4)
           if (gc >= 0) gen_chunk(gc);
           if (!real) continue;
           if (step == 6) {
@@ -1158,6 +1211,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       //      walks [256,512) downwards into [384,512); the packed destination of a group never reaches columns that are
       //      still unread, and [128,384) comes out free for acc2.
       { PROF_T0(); wait_bar(bars, B_ACC1_FULL, c_acc1full); PROF_ADD(P_W_ACC1FULL); }
+      TRACE(tr, tb + 11);
       tc::tcgen05_fence_after();
       {
         PROF_T0();
@@ -1177,10 +1231,12 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         tc::tcgen05_fence_before();
         warp_arrive_local(bars + B_H1_READY, lane);
         PROF_ADD(P_W_DRAIN1);
+        TRACE(tr, tb + 12);
       }
           } else if (step == 8) {
       // ---- layer 2 -> H2 [0,128)
       { PROF_T0(); wait_bar(bars, B_ACC2_FULL, c_acc2full); PROF_ADD(P_W_ACC2FULL); }
+      TRACE(tr, tb + 13);
       tc::tcgen05_fence_after();
       {
         PROF_T0();
@@ -1198,11 +1254,13 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         tc::tcgen05_fence_before();
         warp_arrive_local(bars + B_H2_READY, lane);
         PROF_ADD(P_W_DRAIN2);
+        TRACE(tr, tb + 14);
       }
           } else if (step == 9) {
       // ---- layer 3 + layer 4 in fp32, warpgroup 0
       if (wg == 0) {
         { PROF_T0(); wait_bar(bars, B_ACC3_FULL, c_acc3full); PROF_ADD(P_W_ACC3FULL); }
+        TRACE(tr, tb + 15);
         tc::tcgen05_fence_after();
         PROF_T0();
         float logit[kMaxRes];
@@ -1232,6 +1290,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         tc::tcgen05_fence_before();
         warp_arrive_local(bars + B_TILE_DONE, lane);
         PROF_ADD(P_W_DRAIN3);
+        TRACE(tr, tb + 16);
         const long long i = p0 + row;
         if (i < n) {
 #pragma unroll
@@ -1309,6 +1368,108 @@ g0_kernel(const float* __restrict__ F, const float* __restrict__ W, __half* __re
     pk.w = tc::pack_half2(acc[i][6], acc[i][7]);
     *reinterpret_cast<uint4*>(G + (size_t)m * N + n0 + tn) = pk;
   }
+}
+
+// G0 on the tensor cores: the same GEMM as g0_kernel with fp16 operands (F rounded once while staging, W0f pre-packed on
+// the host as SWIZZLE_128B tiles) and fp32 accumulation in TMEM.  One CTA = one 128 (texels) x 256 (outputs) tile over the
+// whole K = 256: A is staged by all threads K-block by K-block (fp32 global -> fp16 swizzled smem), B arrives as four
+// 32 KB bulk copies, thread 0 issues each K-block's four MMAs right after its staging barrier so they overlap the next
+// block's loads; the epilogue reads the accumulator back (tcgen05.ld), rounds to fp16 and writes G rows.
+// 4.3 GFLOP per frame: ~15 us instead of the ~150 us fp32 version, which lets program v3 serve octree-sized queries too.
+constexpr int kG0Threads = 256;
+constexpr int kG0TileN = 256;
+constexpr uint32_t kG0SmemA = 4 * 16384, kG0SmemB = 4 * 32768;
+constexpr uint32_t kG0Smem = kG0SmemA + kG0SmemB + 1024 /*align*/ + 64 /*barriers + tmem slot*/;
+
+__global__ void __launch_bounds__(kG0Threads, 1)
+g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half* __restrict__ G, int M) {
+  extern __shared__ uint8_t g0_smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g0_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = base;
+  uint8_t* sB = base + kG0SmemA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + kG0SmemA + kG0SmemB);   // [0..3] B K-block landed, [4] MMAs done
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 5);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m0 = blockIdx.x * 128, nt = blockIdx.y;
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
+    tc::mbar_init(&bars[4], 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) {
+    tc::tmem_alloc(tslot, 256);
+    tc::tmem_relinquish();
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tbase = *tslot;
+  if (tid == 0) {
+    const uint8_t* src = Wt + (size_t)nt * kG0SmemB;
+    for (int kb = 0; kb < 4; ++kb) {
+      tc::mbar_arrive_expect_tx(&bars[kb], 32768);
+      tc::bulk_g2s(sB + kb * 32768, src + (size_t)kb * 32768, 32768, &bars[kb]);
+    }
+  }
+  // A staging: thread -> (row = tid / 2, 32-column half of each 64-wide K-block)
+  const int row = tid >> 1, half = tid & 1;
+  const bool live = (m0 + row) < M;
+  const float* frow = F + (size_t)(live ? m0 + row : 0) * kC + half * 32;
+  constexpr uint32_t idesc = tc::make_idesc_f16(128, kG0TileN);
+  for (int kb = 0; kb < 4; ++kb) {
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = live ? __ldg(reinterpret_cast<const float4*>(frow + kb * 64) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 pk;
+      pk.x = tc::pack_half2(v[2 * j].x, v[2 * j].y);
+      pk.y = tc::pack_half2(v[2 * j].z, v[2 * j].w);
+      pk.z = tc::pack_half2(v[2 * j + 1].x, v[2 * j + 1].y);
+      pk.w = tc::pack_half2(v[2 * j + 1].z, v[2 * j + 1].w);
+      *reinterpret_cast<uint4*>(sA + kb * 16384 + tc::sw128_offset(row, half * 32 + j * 8)) = pk;
+    }
+    tc::fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc::mbar_wait(&bars[kb], 0);
+      tc::tcgen05_fence_after();
+      const uint32_t a0 = tc::smem_u32(sA + kb * 16384), b0 = tc::smem_u32(sB + kb * 32768);
+#pragma unroll
+      for (int k16 = 0; k16 < 4; ++k16)
+        tc::mma_ss(tbase, tc::make_sdesc_sw128(a0 + k16 * 32, 1024), tc::make_sdesc_sw128(b0 + k16 * 32, 1024), idesc, (kb | k16) ? 1u : 0u);
+      if (kb == 3) tc::mma_commit(&bars[4]);
+    }
+  }
+  tc::mbar_wait(&bars[4], 0);
+  __syncwarp();
+  tc::tcgen05_fence_after();
+  // epilogue: warp w reads lanes 32*(w%4).. (its TMEM sub-partition), columns 128*(w/4)..+127
+  {
+    const int lane = tid & 31, sub = warp & 3, ch = warp >> 2;
+    const int m = m0 + sub * 32 + lane;
+    __half* grow = G + (size_t)(m < M ? m : 0) * kL0 + nt * kG0TileN + ch * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tc::tmem_ld32(tbase + ((uint32_t)(sub * 32) << 16) + ch * 128 + c * 32, r);
+      tc::tmem_ld_wait();
+      if (m < M) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 pk;
+          pk.x = tc::pack_half2(__uint_as_float(r[8 * q + 0]), __uint_as_float(r[8 * q + 1]));
+          pk.y = tc::pack_half2(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3]));
+          pk.z = tc::pack_half2(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5]));
+          pk.w = tc::pack_half2(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7]));
+          *reinterpret_cast<uint4*>(grow + c * 32 + q * 8) = pk;
+        }
+      }
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, 256);
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -1449,6 +1610,12 @@ int mp_tc_prepare(mp_mlp* mlp) {
     std::vector<float> w0f((size_t)kL0 * kC);
     for (int co = 0; co < kL0; ++co) memcpy(&w0f[(size_t)co * kC], &W[0][(size_t)co * mlp->cin[0]], kC * sizeof(float));
     e = upload(w0f.data(), w0f.size() * sizeof(float), (void**)&pk->d_w0f);
+    if (e == cudaSuccess) {
+      std::vector<uint8_t> w0t((size_t)(kL0 / kG0TileN) * 4 * 32768);
+      for (int nt = 0; nt < kL0 / kG0TileN; ++nt)
+        for (int kb = 0; kb < 4; ++kb) pack_tile(w0t.data() + ((size_t)nt * 4 + kb) * 32768, W[0].data(), mlp->cin[0], nt * kG0TileN, kG0TileN, kb * 64);
+      e = upload(w0t.data(), w0t.size(), (void**)&pk->d_w0t);
+    }
   }
   const int hid[4] = {0, kL0, kL1, kL2};
   for (int l = 0; l < 4 && e == cudaSuccess; ++l) {
@@ -1458,8 +1625,10 @@ int mp_tc_prepare(mp_mlp* mlp) {
     memcpy(pk->h_bias + side_off(l), Bv[l].data(), Bv[l].size() * sizeof(float));
     memcpy(pk->h_wz + side_off(l), wz.data(), wz.size() * sizeof(float));
     if (l == 0) {
-      e = upload(Bv[0].data(), Bv[0].size() * sizeof(float), (void**)&pk->d_bias0);
-      if (e == cudaSuccess) e = upload(wz.data(), wz.size() * sizeof(float), (void**)&pk->d_wz0);
+      std::vector<__half> b0h(Bv[0].size()), wz0h(wz.size());
+      for (size_t i = 0; i < b0h.size(); ++i) { b0h[i] = __float2half_rn(Bv[0][i]); wz0h[i] = __float2half_rn(wz[i]); }
+      e = upload(b0h.data(), b0h.size() * sizeof(__half), (void**)&pk->d_bias0);
+      if (e == cudaSuccess) e = upload(wz0h.data(), wz0h.size() * sizeof(__half), (void**)&pk->d_wz0);
     }
   }
   if (e == cudaSuccess) {
@@ -1485,6 +1654,7 @@ int mp_tc_prepare(mp_mlp* mlp) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(g0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG0Smem);
   if (e != cudaSuccess) {
     mp_set_error("mp_tc_prepare: cannot opt in to %d bytes of shared memory: %s", Smem::Total + 1024, cudaGetErrorString(e));
     mp_tc_release(mlp);
@@ -1504,6 +1674,7 @@ void mp_tc_release(mp_mlp* mlp) {
   if (pk->d_bias0) cudaFree(pk->d_bias0);
   if (pk->d_wz0) cudaFree(pk->d_wz0);
   if (pk->d_w0f) cudaFree(pk->d_w0f);
+  if (pk->d_w0t) cudaFree(pk->d_w0t);
   for (int l = 0; l < 4; ++l) {
     if (pk->bias[l]) cudaFree(pk->bias[l]);
     if (pk->wz[l]) cudaFree(pk->wz[l]);
@@ -1552,7 +1723,26 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     MP_CUDA(cudaMemset(d_prof, 0, (size_t)sms * 32 * sizeof(unsigned long long)));
     prm.prof = d_prof;
   }
+  static const int exp_mask = [] { const char* v = getenv("MONOPORT_B200_TC_EXP"); return v ? atoi(v) : 0; }();
+  prm.exp = exp_mask;
+  static const int do_trace = [] { const char* v = getenv("MONOPORT_B200_TC_TRACE"); return v ? atoi(v) : 0; }();
+  unsigned long long* d_trace = nullptr;
+  if (do_trace && !d_prof && tiles >= (long long)(kTraceTile + 2) * sms) {
+    MP_CUDA(cudaMalloc(&d_trace, 128 * sizeof(unsigned long long)));
+    MP_CUDA(cudaMemset(d_trace, 0, 128 * sizeof(unsigned long long)));
+    prm.trace = d_trace;
+  }
   auto report = [&](int grid) {
+    if (d_trace) {
+      cudaStreamSynchronize(st);
+      unsigned long long h[128];
+      cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+      cudaFree(d_trace);
+      unsigned long long t0 = ~0ull;
+      for (int k = 0; k < 128; ++k) if (h[k] && h[k] < t0) t0 = h[k];
+      for (int k = 0; k < 128; ++k) if (h[k]) fprintf(stderr, "[tc trace] %3d %8llu\n", k, h[k] - t0);
+      return;
+    }
     if (!d_prof) return;
     cudaStreamSynchronize(st);
     std::vector<unsigned long long> h((size_t)sms * 32);
@@ -1569,12 +1759,12 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
   // variant: CTA group.  MONOPORT_B200_TC_CG=1|2 overrides.  Default: 1 for the v2 program (its layer-0 chunk hand-off
   // is on the critical path and every cross-CTA arrival adds latency to it), see below for v3.
   static const int forced = [] { const char* v = getenv("MONOPORT_B200_TC_CG"); return v ? atoi(v) : 0; }();
-  // program: v3 (layer 0 hoisted to texels, needs the per-frame G0 GEMM) for large queries, v2 for small ones where the
-  // 4.3 GFLOP fp32 GEMM would dominate (octree levels).  MONOPORT_B200_TC_VER=2|3 overrides.
+  // program: v3 (layer 0 hoisted to texels; the per-frame G0 GEMM runs on the tensor cores in ~15 us, so it pays off for
+  // octree-sized queries too); v2 stays selectable (MP_MODE_TC_V2 / MONOPORT_B200_TC_VER=2) as the self-contained variant.
   static const int forced_ver = [] { const char* v = getenv("MONOPORT_B200_TC_VER"); return v ? atoi(v) : 0; }();
   const int want = program ? program : forced_ver;
-  // (a device-side count means an octree node list: src.n is only a capacity bound there, and the lists are small)
-  const int ver = want == 2 ? 2 : (want == 3 ? 3 : ((src.n >= (1ll << 20) && !src.count_dev) ? 3 : 2));
+  // (v3 keeps texel indices as 16-bit pairs in registers: maps above 65536 texels take the self-contained program)
+  const int ver = (want == 2 || (long long)feat->H * feat->W > 65536) ? 2 : 3;
   if (ver == 3) {
     const long long HW = (long long)feat->H * feat->W;
     if (!feat->g0 || feat->g0_n != kL0) {
@@ -1585,8 +1775,15 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
       feat->g0_owner = nullptr;
     }
     if (feat->g0_owner != (const void*)mlp || feat->g0_version != feat->version) {
-      dim3 gg((unsigned)((HW + 127) / 128), kL0 / 128);
-      g0_kernel<<<gg, 256, 0, st>>>(feat->nhwc32, pk->d_w0f, feat->g0, (int)HW, kL0, kC);
+      // MONOPORT_B200_G0=fp32 selects the CUDA-core GEMM (debug / precision A-B only)
+      static const bool g0_fp32 = [] { const char* v = getenv("MONOPORT_B200_G0"); return v && !strcmp(v, "fp32"); }();
+      if (g0_fp32) {
+        dim3 gg((unsigned)((HW + 127) / 128), kL0 / 128);
+        g0_kernel<<<gg, 256, 0, st>>>(feat->nhwc32, pk->d_w0f, feat->g0, (int)HW, kL0, kC);
+      } else {
+        dim3 gg((unsigned)((HW + 127) / 128), kL0 / kG0TileN);
+        g0_tc_kernel<<<gg, kG0Threads, kG0Smem, st>>>(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW);
+      }
       MP_CUDA(cudaGetLastError());
       feat->g0_owner = (const void*)mlp;
       feat->g0_version = feat->version;

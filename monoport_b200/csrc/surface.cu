@@ -20,16 +20,32 @@ __device__ __forceinline__ long long a_index(int dir, int R, int x, int y, int k
   }
 }
 
+// A[x,y,k] = vol[base + k * stride]: the column walk of a_index as an affine index
+__device__ __forceinline__ void column_walk(int dir, int R, int x, int y, long long& base, long long& stride) {
+  base = a_index(dir, R, x, y, 0);
+  stride = a_index(dir, R, x, y, 1) - base;
+}
+
 __global__ void __launch_bounds__(256)
 first_hit_kernel(const float* __restrict__ vol, int R, int dir, int32_t* __restrict__ first_t) {
   // thread -> column; for front/back consecutive threads walk consecutive x (coalesced); for left/right consecutive
   // threads walk consecutive y rows of the same (x) plane -- k is then the contiguous axis, handled per thread.
+  // The column is read in batches of 16 unconditional loads (independent, so they overlap) and tested afterwards:
+  // a serial load-test-break chain costs one memory round trip per node, ~100 us for R = 257.
+  constexpr int kBatch = 16;
   const int n = R * R;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
     const int x = c % R, y = c / R;
+    long long base, stride;
+    column_walk(dir, R, x, y, base, stride);
     int hit = -1;
-    for (int k = 0; k < R; ++k) {
-      if (__ldg(vol + a_index(dir, R, x, y, k)) > 0.5f) { hit = k; break; }
+    for (int k0 = 0; k0 < R && hit < 0; k0 += kBatch) {
+      float v[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) v[j] = (k0 + j < R) ? __ldg(vol + base + (long long)(k0 + j) * stride) : 0.f;
+#pragma unroll
+      for (int j = kBatch - 1; j >= 0; --j)
+        if (v[j] > 0.5f) hit = k0 + j;
     }
     first_t[x * R + y] = hit;    // transposed: scan order is x-major
   }

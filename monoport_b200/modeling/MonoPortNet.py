@@ -30,9 +30,12 @@ class FeatureHandle:
         with torch.cuda.device(device):
             _lib.check(_lib.load().mp_feat_create(C, H, W, ctypes.byref(self.ptr)), "mp_feat_create")
         self.key = None
+        self._src = None
 
     def upload(self, feat):
-        key = (feat.data_ptr(), feat._version)
+        # identity of the uploaded frame = (storage address, version counter).  `_src` keeps that tensor alive so the
+        # caching allocator cannot hand its address to the NEXT frame's features (which would look "unchanged").
+        key = (feat.data_ptr(), feat._version, feat.dtype)
         if key == self.key:
             return
         f = feat.detach()
@@ -41,6 +44,7 @@ class FeatureHandle:
         _lib.check(_lib.load().mp_feat_upload(self.ptr, ctypes.c_void_p(f.data_ptr()), 1, _lib.stream_ptr(self.device)),
                    "mp_feat_upload")
         self.key = key
+        self._src = feat
 
     def __del__(self):
         try:
