@@ -142,6 +142,8 @@ extern "C" int mp_feat_destroy(mp_feat_t* h) {
   if (h->nhwc32) cudaFree(h->nhwc32);
   if (h->staging) cudaFree(h->staging);
   if (h->g0) cudaFree(h->g0);
+  if (h->f16) cudaFree(h->f16);
+  if (h->s4tex) cudaFree(h->s4tex);
   delete h;
   return MP_OK;
 }

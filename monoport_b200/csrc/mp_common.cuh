@@ -63,6 +63,8 @@ struct mp_feat {
   // (bilinear sampling is linear, so sampling G0 equals applying W0 to the sampled features); valid for
   // (g0_owner == head handle, g0_version == version)
   __half* g0;
+  __half* f16;      // [H*W][C] fp16 copy of the map (X operand taps of the v3 program), same validity as g0
+  float* s4tex;     // [H*W][n_out] fp32: last layer's feature part applied per texel (sampled in fp32 by the v3 program)
   int g0_n;
   const void* g0_owner;
   unsigned long long g0_version;

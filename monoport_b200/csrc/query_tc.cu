@@ -72,7 +72,6 @@ struct TcPack {
   __half* w3stream2[2];   // v3, CG=2
   __half* d_bias0;        // fp16 device copies of the layer-0 bias / depth column for per-lane channel access (v3 H0 generation)
   __half* d_wz0;
-  float* d_w0f;           // [1024][256] fp32: feature part of layer 0 (operand of the fp32 per-texel G0 GEMM, debug path)
   uint8_t* d_w0t;         // the same as fp16 SWIZZLE_128B tiles [n tile 4][K block 4][256 x 64] for g0_tc_kernel
   float* bias[4];         // per hidden layer
   float* wz[4];           // z column of every hidden layer
@@ -102,6 +101,8 @@ struct TcParams {
   const float* feat32;    // NHWC fp32 (bilinear taps are read in fp32: the last layer's skip access to the input
                           // makes the output sensitive to the precision of x -- see DESIGN.md, precision)
   const __half* g0;       // v3: [H*W][1024] fp16 per-texel layer-0 product
+  const __half* feat16;   // v3: NHWC fp16 copy of the map (taps of the X operand)
+  const float* s4tex;     // v3: [H*W][kMaxRes] fp32 per-texel last-layer feature part
   const __half* d_bias0;  // v3: layer-0 bias and depth-feature column, fp16 [1024]
   const __half* d_wz0;
   unsigned long long* prof;   // optional [gridDim.x][32] cycle counters (MONOPORT_B200_TC_PROF=1), else null
@@ -267,6 +268,59 @@ __device__ __forceinline__ void sample_x_group(const TcParams& prm, uint8_t* sme
     }
   }
   if (lane < 16) {
+    s_zf[pbase + lane] = pt.zf;
+    s_in[pbase + lane] = pt.in_img ? 1.f : 0.f;
+  }
+}
+
+// Program v3 variant: the X operand is sampled from the fp16 copy of the map (half the bytes through L1), four points per
+// batch; the last layer's direct feature access is NOT derived from these samples but from S4 (fp32, per texel), which
+// the lane owning the point interpolates in fp32.
+__device__ __forceinline__ void sample_x_group16(const TcParams& prm, uint8_t* smem_x, float* s_zf, float* s_in, float* s_s4,
+                                                 PointTaps pt, int pbase, int lane) {
+  const int cbase = lane * 8;
+#pragma unroll 1
+  for (int q0 = 0; q0 < 16; q0 += 4) {
+    uint4 raw[4][4];                         // [point][tap] 8 fp16 channels
+    float wgt[4][4];
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int off = __shfl_sync(0xffffffffu, pt.off[a], q0 + qq);
+        wgt[qq][a] = __shfl_sync(0xffffffffu, pt.wgt[a], q0 + qq);
+        raw[qq][a] = __ldg(reinterpret_cast<const uint4*>(prm.feat16 + (size_t)off * kC + cbase));
+      }
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      const int p = pbase + q0 + qq;
+      float2 acc[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {                   // same accumulation order as grid_sample: nw, ne, sw, se
+        const float2 w2 = make_float2(wgt[qq][a], wgt[qq][a]);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[qq][a]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = (a == 0) ? __fmul2_rn(__half22float2(h2[j]), w2) : __ffma2_rn(__half22float2(h2[j]), w2, acc[j]);
+      }
+      uint4 packed;
+      packed.x = tc::pack_half2(acc[0].x, acc[0].y);
+      packed.y = tc::pack_half2(acc[1].x, acc[1].y);
+      packed.z = tc::pack_half2(acc[2].x, acc[2].y);
+      packed.w = tc::pack_half2(acc[3].x, acc[3].y);
+      *reinterpret_cast<uint4*>(smem_x + (lane >> 3) * 16384 + tc::sw128_offset(p, (lane & 7) * 8)) = packed;
+    }
+  }
+  if (lane < 16) {
+    if (prm.exp & 4) { pt.off[0] = pt.off[1] = pt.off[2] = pt.off[3] = 0; }
+#pragma unroll
+    for (int r = 0; r < kMaxRes; ++r) {
+      if (r < prm.res) {
+        float s = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) s = fmaf(pt.wgt[a], __ldg(prm.s4tex + (size_t)pt.off[a] * kMaxRes + r), s);
+        s_s4[r * kTile + pbase + lane] = s + __ldg(prm.w4z + r) * pt.zf + __ldg(prm.b4 + r);
+      }
+    }
     s_zf[pbase + lane] = pt.zf;
     s_in[pbase + lane] = pt.in_img ? 1.f : 0.f;
   }
@@ -1023,12 +1077,6 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     const int sw = warp - 2;
     const int res = prm.res;
     uint32_t c_xfree = 0;
-    const int cbase = lane * 8;
-    float w4s[kMaxRes][8];
-#pragma unroll
-    for (int r = 0; r < kMaxRes; ++r)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) w4s[r][j] = (r < res) ? __ldg(prm.w4s + r * kC + cbase + j) : 0.f;
     for (long long g = g0; g < n_groups; g += gstep) {
       const long long tile = g * CG + rank;
       const long long p0 = tile * kTile;
@@ -1041,7 +1089,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         const int pbase = sw * 64 + grp * 16;
         PointTaps pt = point_taps(src, cal, prm.H, prm.W, p0 + pbase + (lane & 15), n);
         if (prm.exp & 4) { pt.off[0] = pt.off[1] = pt.off[2] = pt.off[3] = 0; }
-        sample_x_group(prm, smem + Smem::X, s_zf, s_in, s_s4, pt, pbase, lane, w4s);
+        sample_x_group16(prm, smem + Smem::X, s_zf, s_in, s_s4, pt, pbase, lane);
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
@@ -1319,70 +1367,23 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
   }
 }
 
-// G0[texel][n] = sum_k F[texel][k] * W0f[n][k]   (fp32 CUDA-core GEMM, NT; result rounded once to fp16)
-// 128 x 128 tile per CTA, 256 threads, 8 x 8 micro-tile, K step 16.
-__global__ void __launch_bounds__(256)
-g0_kernel(const float* __restrict__ F, const float* __restrict__ W, __half* __restrict__ G, int M, int N, int K) {
-  __shared__ float sA[16][128 + 4];
-  __shared__ float sB[16][128 + 4];
-  const int tid = threadIdx.x;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
-  const int tm = (tid >> 4) * 8, tn = (tid & 15) * 8;
-  float acc[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    // each thread loads 2 float4 of A and of B: row = tid/4 (+64), k chunk = (tid%4)*4
-    for (int rr = 0; rr < 2; ++rr) {
-      const int r = (tid >> 2) + rr * 64, kc = (tid & 3) * 4;
-      const float4 a = (m0 + r < M) ? *reinterpret_cast<const float4*>(F + (size_t)(m0 + r) * K + k0 + kc) : make_float4(0, 0, 0, 0);
-      const float4 b = (n0 + r < N) ? *reinterpret_cast<const float4*>(W + (size_t)(n0 + r) * K + k0 + kc) : make_float4(0, 0, 0, 0);
-      sA[kc + 0][r] = a.x; sA[kc + 1][r] = a.y; sA[kc + 2][r] = a.z; sA[kc + 3][r] = a.w;
-      sB[kc + 0][r] = b.x; sB[kc + 1][r] = b.y; sB[kc + 2][r] = b.z; sB[kc + 3][r] = b.w;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      float a[8], b[8];
-      *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&sA[k][tm]);
-      *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(&sA[k][tm + 4]);
-      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&sB[k][tn]);
-      *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(&sB[k][tn + 4]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = m0 + tm + i;
-    if (m >= M) continue;
-    uint4 pk;
-    pk.x = tc::pack_half2(acc[i][0], acc[i][1]);
-    pk.y = tc::pack_half2(acc[i][2], acc[i][3]);
-    pk.z = tc::pack_half2(acc[i][4], acc[i][5]);
-    pk.w = tc::pack_half2(acc[i][6], acc[i][7]);
-    *reinterpret_cast<uint4*>(G + (size_t)m * N + n0 + tn) = pk;
-  }
-}
-
-// G0 on the tensor cores: the same GEMM as g0_kernel with fp16 operands (F rounded once while staging, W0f pre-packed on
+// G0[texel][n] = sum_k F[texel][k] * W0f[n][k] on the tensor cores: fp16 operands (F rounded once while staging, W0f pre-packed on
 // the host as SWIZZLE_128B tiles) and fp32 accumulation in TMEM.  One CTA = one 128 (texels) x 256 (outputs) tile over the
 // whole K = 256: A is staged by all threads K-block by K-block (fp32 global -> fp16 swizzled smem), B arrives as four
 // 32 KB bulk copies, thread 0 issues each K-block's four MMAs right after its staging barrier so they overlap the next
 // block's loads; the epilogue reads the accumulator back (tcgen05.ld), rounds to fp16 and writes G rows.
-// 4.3 GFLOP per frame: ~15 us instead of the ~150 us fp32 version, which lets program v3 serve octree-sized queries too.
+// The CTAs of the first output tile also publish what the staging pass has in hand anyway: the fp16 copy of the map
+// (F16, taps of the X operand) and S4 = W4s . F per texel in fp32 (the last layer's direct access to the features:
+// sampling S4 in fp32 keeps that path out of the fp16 roundings -- bilinear sampling commutes with the dot product).
+// 4.3 GFLOP per frame in ~40 us, which lets program v3 serve octree-sized queries too.
 constexpr int kG0Threads = 256;
 constexpr int kG0TileN = 256;
 constexpr uint32_t kG0SmemA = 4 * 16384, kG0SmemB = 4 * 32768;
 constexpr uint32_t kG0Smem = kG0SmemA + kG0SmemB + 1024 /*align*/ + 64 /*barriers + tmem slot*/;
 
 __global__ void __launch_bounds__(kG0Threads, 1)
-g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half* __restrict__ G, int M) {
+g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half* __restrict__ G, int M,
+             __half* __restrict__ F16, float* __restrict__ S4, const float* __restrict__ w4s, int res) {
   extern __shared__ uint8_t g0_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g0_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;
@@ -1416,6 +1417,10 @@ g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half
   const bool live = (m0 + row) < M;
   const float* frow = F + (size_t)(live ? m0 + row : 0) * kC + half * 32;
   constexpr uint32_t idesc = tc::make_idesc_f16(128, kG0TileN);
+  const bool side = nt == 0 && live;            // this thread also publishes F16 / S4 for its (row, 32-channel half)
+  float s4acc[kMaxRes];
+#pragma unroll
+  for (int r = 0; r < kMaxRes; ++r) s4acc[r] = 0.f;
   for (int kb = 0; kb < 4; ++kb) {
     float4 v[8];
 #pragma unroll
@@ -1428,6 +1433,20 @@ g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half
       pk.z = tc::pack_half2(v[2 * j + 1].x, v[2 * j + 1].y);
       pk.w = tc::pack_half2(v[2 * j + 1].z, v[2 * j + 1].w);
       *reinterpret_cast<uint4*>(sA + kb * 16384 + tc::sw128_offset(row, half * 32 + j * 8)) = pk;
+      if (side) *reinterpret_cast<uint4*>(F16 + (size_t)(m0 + row) * kC + kb * 64 + half * 32 + j * 8) = pk;
+    }
+    if (nt == 0) {
+#pragma unroll
+      for (int r = 0; r < kMaxRes; ++r)
+        if (r < res) {
+          const float4* wv = reinterpret_cast<const float4*>(w4s + r * kC + kb * 64 + half * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w = __ldg(wv + j);
+            s4acc[r] = fmaf(w.x, v[j].x, s4acc[r]); s4acc[r] = fmaf(w.y, v[j].y, s4acc[r]);
+            s4acc[r] = fmaf(w.z, v[j].z, s4acc[r]); s4acc[r] = fmaf(w.w, v[j].w, s4acc[r]);
+          }
+        }
     }
     tc::fence_proxy_async_smem();
     __syncthreads();
@@ -1439,6 +1458,13 @@ g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half
       for (int k16 = 0; k16 < 4; ++k16)
         tc::mma_ss(tbase, tc::make_sdesc_sw128(a0 + k16 * 32, 1024), tc::make_sdesc_sw128(b0 + k16 * 32, 1024), idesc, (kb | k16) ? 1u : 0u);
       if (kb == 3) tc::mma_commit(&bars[4]);
+    }
+  }
+  if (nt == 0) {                                  // (nt is CTA-uniform: all lanes take part in the shuffle)
+#pragma unroll
+    for (int r = 0; r < kMaxRes; ++r) {
+      const float tot = s4acc[r] + __shfl_xor_sync(0xffffffffu, s4acc[r], 1);
+      if (side && half == 0 && r < res) S4[(size_t)(m0 + row) * kMaxRes + r] = tot;
     }
   }
   tc::mbar_wait(&bars[4], 0);
@@ -1606,10 +1632,7 @@ int mp_tc_prepare(mp_mlp* mlp) {
   for (int r = 0; r < 2 && e == cudaSuccess; ++r) e = upload(stream2[r].data(), stream2[r].size(), (void**)&pk->wstream2[r]);
   if (e == cudaSuccess) e = upload(s3.data(), s3.size(), (void**)&pk->w3stream);
   for (int r = 0; r < 2 && e == cudaSuccess; ++r) e = upload(s3b[r].data(), s3b[r].size(), (void**)&pk->w3stream2[r]);
-  if (e == cudaSuccess) {   // feature part of layer 0, fp32 [1024][256], operand of the per-texel G0 GEMM
-    std::vector<float> w0f((size_t)kL0 * kC);
-    for (int co = 0; co < kL0; ++co) memcpy(&w0f[(size_t)co * kC], &W[0][(size_t)co * mlp->cin[0]], kC * sizeof(float));
-    e = upload(w0f.data(), w0f.size() * sizeof(float), (void**)&pk->d_w0f);
+  {   // feature part of layer 0 as fp16 SWIZZLE_128B tiles, operand of the per-texel G0 GEMM
     if (e == cudaSuccess) {
       std::vector<uint8_t> w0t((size_t)(kL0 / kG0TileN) * 4 * 32768);
       for (int nt = 0; nt < kL0 / kG0TileN; ++nt)
@@ -1673,7 +1696,6 @@ void mp_tc_release(mp_mlp* mlp) {
   for (int r = 0; r < 2; ++r) if (pk->w3stream2[r]) cudaFree(pk->w3stream2[r]);
   if (pk->d_bias0) cudaFree(pk->d_bias0);
   if (pk->d_wz0) cudaFree(pk->d_wz0);
-  if (pk->d_w0f) cudaFree(pk->d_w0f);
   if (pk->d_w0t) cudaFree(pk->d_w0t);
   for (int l = 0; l < 4; ++l) {
     if (pk->bias[l]) cudaFree(pk->bias[l]);
@@ -1771,24 +1793,21 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
       if (feat->g0) cudaFree(feat->g0);
       feat->g0 = nullptr;
       MP_CUDA(cudaMalloc(&feat->g0, (size_t)HW * kL0 * sizeof(__half)));
+      if (!feat->f16) MP_CUDA(cudaMalloc(&feat->f16, (size_t)HW * kC * sizeof(__half)));
+      if (!feat->s4tex) MP_CUDA(cudaMalloc(&feat->s4tex, (size_t)HW * kMaxRes * sizeof(float)));
       feat->g0_n = kL0;
       feat->g0_owner = nullptr;
     }
     if (feat->g0_owner != (const void*)mlp || feat->g0_version != feat->version) {
-      // MONOPORT_B200_G0=fp32 selects the CUDA-core GEMM (debug / precision A-B only)
-      static const bool g0_fp32 = [] { const char* v = getenv("MONOPORT_B200_G0"); return v && !strcmp(v, "fp32"); }();
-      if (g0_fp32) {
-        dim3 gg((unsigned)((HW + 127) / 128), kL0 / 128);
-        g0_kernel<<<gg, 256, 0, st>>>(feat->nhwc32, pk->d_w0f, feat->g0, (int)HW, kL0, kC);
-      } else {
-        dim3 gg((unsigned)((HW + 127) / 128), kL0 / kG0TileN);
-        g0_tc_kernel<<<gg, kG0Threads, kG0Smem, st>>>(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW);
-      }
+      dim3 gg((unsigned)((HW + 127) / 128), kL0 / kG0TileN);
+      g0_tc_kernel<<<gg, kG0Threads, kG0Smem, st>>>(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s, pk->res);
       MP_CUDA(cudaGetLastError());
       feat->g0_owner = (const void*)mlp;
       feat->g0_version = feat->version;
     }
     prm.g0 = feat->g0;
+    prm.feat16 = feat->f16;
+    prm.s4tex = feat->s4tex;
     prm.d_bias0 = pk->d_bias0;
     prm.d_wz0 = pk->d_wz0;
     prm.wstream = pk->w3stream;

@@ -1,7 +1,6 @@
-"""GPU check of the tcgen05 G0 GEMM (layer 0 hoisted to texels): program v3 with G0 from the tensor cores vs. the oracle,
-vs. the fp32 CUDA-core G0 (MONOPORT_B200_G0=fp32, run as a child process because the switch is read once), and the cost
-of one G0 refresh (query after a feature upload vs. query on an unchanged feature map)."""
-import sys, os, subprocess
+"""GPU check of the tcgen05 G0 GEMM (layer 0 hoisted to texels): program v3 vs. the oracle at several sizes, and the cost
+of one per-frame refresh (query after a feature upload vs. query on an unchanged feature map)."""
+import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -22,16 +21,7 @@ for n in (100, 1000, 20000, 148 * 128 * 3 + 17):
     torch.cuda.synchronize()
     out[n] = got.cpu()
     err = (got.cpu() - want).abs()
-    print("[%s] n=%7d  max|v3 - oracle| = %.3e  mean = %.3e" % (os.environ.get("MONOPORT_B200_G0", "tc"), n, err.max().item(), err.mean().item()), flush=True)
-if len(sys.argv) > 1 and sys.argv[1] == "--child":
-    torch.save(out, sys.argv[2])
-    sys.exit(0)
-env = dict(os.environ, MONOPORT_B200_G0="fp32")
-tmp = "/tmp/g0_child.pt"
-subprocess.run([sys.executable, os.path.abspath(__file__), "--child", tmp], env=env, check=True)
-ref = torch.load(tmp)
-for n in out:
-    print("n=%7d  max|G0 tc - G0 fp32| on outputs = %.3e" % (n, (out[n] - ref[n]).abs().max().item()))
+    print("n=%7d  max|v3 - oracle| = %.3e  mean = %.3e" % (n, err.max().item(), err.mean().item()), flush=True)
 # cost of a G0 refresh: small query with / without a feature re-upload
 f = feat.cuda(); c = cal.cuda()
 pts = spec.make_points(4096, 3).cuda()

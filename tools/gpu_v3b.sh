@@ -8,3 +8,4 @@ import json
 d=json.load(open('gpurun_out/bench_iter.json'))
 print('bench', round(d['value'],1),'Mpts/s', round(d['ms_per_step'],2),'ms', 'frac',round(d['roofline']['frac'],3), d['clocks'])
 PY
+timeout 1200 python -m pytest tests -x -q -m gpu --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
