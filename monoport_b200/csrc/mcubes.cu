@@ -148,7 +148,8 @@ extern "C" int mp_mcubes_create(int D, int H, int W, mp_mcubes_t** out) {
   if (e == cudaSuccess) e = cudaMalloc(&h->cases, h->n);
   if (e == cudaSuccess) e = cudaMalloc(&h->voff, h->n * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->sums, (size_t)(mpscan::num_blocks(h->n) + 1) * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMalloc(&h->total, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&h->total, 2 * sizeof(unsigned long long));                 // [0] total, [1] scan ticket
+  if (e == cudaSuccess) e = cudaMemset(h->total, 0, 2 * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     mp_set_error("mp_mcubes_create: %s", cudaGetErrorString(e));
     mp_mcubes_destroy(h);

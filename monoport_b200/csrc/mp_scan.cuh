@@ -2,7 +2,8 @@
 // marching cubes and the visible-surface kernel.  Output order is always ascending element index --
 // never atomics-ordered -- so index lists and mesh topology are bit-reproducible.
 //
-// Three launches:  block sums -> scan of block sums (single CTA) -> re-evaluate + local scan + emit.
+// Two launches:  block sums, whose last CTA to finish (ticket counter) also scans the block sums and runs an optional
+// `post(total)` hook (device-side counts for the next kernel) -> re-evaluate + local scan + emit.
 // The per-element value comes from a functor `uint64 f(i)` (two packed 32-bit counters are allowed),
 // `emit(i, value, exclusive_prefix)` consumes the result.  HBM-bound: the functor's reads happen twice.
 #pragma once
@@ -42,8 +43,15 @@ __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long
   return base + incl - v;
 }
 
-template <class F>
-__global__ void __launch_bounds__(kThreads) block_sums_kernel(F f, long long n, unsigned long long* __restrict__ sums) {
+struct NoPost {
+  __device__ void operator()(unsigned long long) const {}
+};
+
+// sums[0..nb) <- exclusive scan of the CTA totals, total[0] <- grand total.  total[1] is the ticket counter: zero on entry
+// (zero-initialised once by the owner of the workspace), reset to zero by the last CTA.
+template <class F, class P>
+__global__ void __launch_bounds__(kThreads) block_sums_kernel(F f, long long n, unsigned long long* __restrict__ sums, int nb,
+                                                              unsigned long long* __restrict__ total, P post) {
   const long long base = (long long)blockIdx.x * kChunk + (long long)threadIdx.x * kItems;
   unsigned long long s = 0;
 #pragma unroll
@@ -53,27 +61,34 @@ __global__ void __launch_bounds__(kThreads) block_sums_kernel(F f, long long n, 
   }
   unsigned long long tot;
   block_excl_scan(s, &tot);
-  if (threadIdx.x == 0) sums[blockIdx.x] = tot;
-}
-
-// in-place exclusive scan of `nb` block sums by a single CTA; total written to *total (device)
-static __global__ void __launch_bounds__(kThreads) scan_sums_kernel(unsigned long long* __restrict__ sums, int nb,
-                                                             unsigned long long* __restrict__ total) {
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    sums[blockIdx.x] = tot;
+    __threadfence();
+    is_last = atomicAdd(&total[1], 1ull) == (unsigned long long)(nb - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
   __shared__ unsigned long long carry_s;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  for (int base = 0; base < nb; base += kThreads) {
-    const int i = base + threadIdx.x;
-    const unsigned long long v = i < nb ? sums[i] : 0ull;
-    unsigned long long tot;
-    const unsigned long long ex = block_excl_scan(v, &tot);
+  for (int b0 = 0; b0 < nb; b0 += kThreads) {
+    const int i = b0 + threadIdx.x;
+    const unsigned long long v = i < nb ? __ldcg(sums + i) : 0ull;
+    unsigned long long t;
+    const unsigned long long ex = block_excl_scan(v, &t);
     const unsigned long long carry = carry_s;
     if (i < nb) sums[i] = carry + ex;
     __syncthreads();
-    if (threadIdx.x == 0) carry_s = carry + tot;
+    if (threadIdx.x == 0) carry_s = carry + t;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *total = carry_s;
+  if (threadIdx.x == 0) {
+    total[0] = carry_s;
+    total[1] = 0;
+    post(carry_s);
+  }
 }
 
 template <class F, class E>
@@ -99,15 +114,14 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(F f, E emit, long long n
 
 inline int num_blocks(long long n) { return (int)((n + kChunk - 1) / kChunk); }
 
-// `sums` needs num_blocks(n) entries, `total` one entry (both device memory).
-template <class F, class E>
+// `sums` needs num_blocks(n) entries, `total` two: [0] receives the grand total, [1] is the ticket counter and must be
+// zero on entry (it is left at zero).  Both device memory.
+template <class F, class E, class P = NoPost>
 inline cudaError_t scan_emit(F f, E emit, long long n, unsigned long long* sums, unsigned long long* total,
-                             cudaStream_t st) {
-  if (n <= 0) return cudaMemsetAsync(total, 0, sizeof(unsigned long long), st);
-  const int nb = num_blocks(n);
-  block_sums_kernel<F><<<nb, kThreads, 0, st>>>(f, n, sums);
-  scan_sums_kernel<<<1, kThreads, 0, st>>>(sums, nb, total);
-  emit_kernel<F, E><<<nb, kThreads, 0, st>>>(f, emit, n, sums);
+                             cudaStream_t st, P post = P()) {
+  const int nb = num_blocks(n > 0 ? n : 1);
+  block_sums_kernel<F, P><<<nb, kThreads, 0, st>>>(f, n > 0 ? n : 0, sums, nb, total, post);
+  if (n > 0) emit_kernel<F, E><<<nb, kThreads, 0, st>>>(f, emit, n, sums);
   return cudaGetLastError();
 }
 

@@ -23,13 +23,16 @@ __device__ __forceinline__ float up_axis(float a, float b, bool odd) {
   return odd ? __fadd_rn(__fmul_rn(0.5f, a), __fmul_rn(0.5f, b)) : a;
 }
 
-// candidates_t may be null (top-k engine / last "faster" level): then only the interpolation runs.
+// candidates_t may be null (top-k engine / last "faster" level): then only the interpolation runs (W = 0).
 // One thread = one COARSE cell (k,j,i) -> its 2x2x2 fine nodes (2k+a, 2j+b, 2i+c): the eight corner loads are shared by
 // the eight interpolations (same operations per output as the per-node form, so bit-identical), and the eight box
 // tests share one pass over the union of their boxes -- per axis the box of parity 0 is [l0,h0], of parity 1 [l1,h1]
-// with l0<=l1<=h0<=h1, so the union is [l0,h1]; a box is "mixed" iff OR != AND of its occupancy bits, and OR/AND
-// separate per axis.  All loads are unconditional (no early exit) so they pipeline.
+// with l0<=l1<=h0<=h1, so the union is [l0,h1] (at most W = radius + 2 wide); a box is "mixed" iff OR != AND of its
+// occupancy bits, and OR/AND separate per axis.  A z slice of the union (W x W values) is loaded unconditionally
+// (clamped addresses, masked afterwards) before any of it is used: the loads of a slice overlap, which matters on the
+// small levels where a handful of threads per SM walk a cold L1 (a load-test-branch chain costs ~30 us there).
 // Launch: grid (ceil(res_c^2 / 256), res_c).
+template <int W>
 __global__ void __launch_bounds__(256)
 upsample_kernel(const float* __restrict__ vc, const uint8_t* __restrict__ known_c, float* __restrict__ vf,
                 uint8_t* __restrict__ known_f, uint8_t* __restrict__ candidates_t, int res_c, int res_f, int radius,
@@ -64,53 +67,64 @@ upsample_kernel(const float* __restrict__ vc, const uint8_t* __restrict__ known_
         vf[o] = v;
         if (known_f) known_f[o] = (!(cz | by | ax) && cell_known) ? 1 : 0;
       }
-  if (!candidates_t) return;
-  int lx[2], hx[2], ly[2], hy[2], lz[2], hz[2];
+  if constexpr (W > 0) {
+    int lx[2], hx[2], ly[2], hy[2], lz[2], hz[2];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int fx = 2 * k + q, fy = 2 * j + q, fz = 2 * i + q;
-    lx[q] = max(fx - radius, 0) >> 1; hx[q] = (min(fx + radius, res_f - 1) + 1) >> 1;
-    ly[q] = max(fy - radius, 0) >> 1; hy[q] = (min(fy + radius, res_f - 1) + 1) >> 1;
-    lz[q] = max(fz - radius, 0) >> 1; hz[q] = (min(fz + radius, res_f - 1) + 1) >> 1;
-  }
-  // bit (4*cz + 2*by + ax) of orm / andm: OR / AND of the occupancy bits over that node's box
-  unsigned orm = 0u, andm = 0xFFu;
-  for (int zz = lz[0]; zz <= min(hz[1], res_c - 1); ++zz) {
-    const unsigned zin = ((zz <= hz[0]) ? 1u : 0u) | ((zz >= lz[1]) ? 2u : 0u);
-    for (int yy = ly[0]; yy <= min(hy[1], res_c - 1); ++yy) {
-      const unsigned yin = ((yy <= hy[0]) ? 1u : 0u) | ((yy >= ly[1]) ? 2u : 0u);
-      const float* row = vc + ((long long)zz * res_c + yy) * res_c;
-      unsigned o0 = 0u, a0 = 1u, o1 = 0u, a1 = 1u;
-#pragma unroll 6
-      for (int xx = lx[0]; xx <= min(hx[1], res_c - 1); ++xx) {
-        const unsigned bit = (__ldg(row + xx) > balance) ? 1u : 0u;
-        if (xx <= hx[0]) { o0 |= bit; a0 &= bit; }
-        if (xx >= lx[1]) { o1 |= bit; a1 &= bit; }
-      }
-      const unsigned orow = o0 | (o1 << 1), arow = a0 | (a1 << 1);   // per x parity
-#pragma unroll
-      for (int cz = 0; cz < 2; ++cz)
-#pragma unroll
-        for (int by = 0; by < 2; ++by)
-          if (((zin >> cz) & 1u) && ((yin >> by) & 1u)) {
-            const int sh = 4 * cz + 2 * by;
-            orm |= orow << sh;
-            andm &= ~(0x3u << sh) | (arow << sh);
-          }
+    for (int q = 0; q < 2; ++q) {
+      const int fx = 2 * k + q, fy = 2 * j + q, fz = 2 * i + q;
+      lx[q] = max(fx - radius, 0) >> 1; hx[q] = (min(fx + radius, res_f - 1) + 1) >> 1;
+      ly[q] = max(fy - radius, 0) >> 1; hy[q] = (min(fy + radius, res_f - 1) + 1) >> 1;
+      lz[q] = max(fz - radius, 0) >> 1; hz[q] = (min(fz + radius, res_f - 1) + 1) >> 1;
     }
-  }
-  const unsigned mixed = orm & ~andm;
+    // bit (4*cz + 2*by + ax) of orm / andm: OR / AND of the occupancy bits over that node's box
+    unsigned orm = 0u, andm = 0xFFu;
+    for (int zz = lz[0]; zz <= hz[1]; ++zz) {
+      const unsigned zin = ((zz <= hz[0]) ? 1u : 0u) | ((zz >= lz[1]) ? 2u : 0u);
+      float v[W][W];
 #pragma unroll
-  for (int cz = 0; cz < 2; ++cz)
+      for (int yi = 0; yi < W; ++yi) {
+        const float* row = vc + ((long long)zz * res_c + min(ly[0] + yi, res_c - 1)) * res_c;
 #pragma unroll
-    for (int by = 0; by < 2; ++by)
-#pragma unroll
-      for (int ax = 0; ax < 2; ++ax) {
-        if ((cz && !ez) || (by && !ey) || (ax && !ex)) continue;
-        const bool known = !(cz | by | ax) && cell_known;
-        const bool cand = !known && ((mixed >> (4 * cz + 2 * by + ax)) & 1u);
-        candidates_t[((long long)(2 * k + ax) * res_f + (2 * j + by)) * res_f + (2 * i + cz)] = cand ? 1 : 0;
+        for (int xi = 0; xi < W; ++xi) v[yi][xi] = __ldg(row + min(lx[0] + xi, res_c - 1));
       }
+#pragma unroll
+      for (int yi = 0; yi < W; ++yi) {
+        const int yy = ly[0] + yi;
+        // rows beyond the union take part in no box: yin = 0
+        const unsigned yin = (yy <= hy[1]) ? (((yy <= hy[0]) ? 1u : 0u) | ((yy >= ly[1]) ? 2u : 0u)) : 0u;
+        unsigned o0 = 0u, a0 = 1u, o1 = 0u, a1 = 1u;
+#pragma unroll
+        for (int xi = 0; xi < W; ++xi) {
+          const int xx = lx[0] + xi;
+          const unsigned bit = (v[yi][xi] > balance) ? 1u : 0u;
+          if (xx <= hx[0]) { o0 |= bit; a0 &= bit; }
+          if (xx >= lx[1] && xx <= hx[1]) { o1 |= bit; a1 &= bit; }
+        }
+        const unsigned orow = o0 | (o1 << 1), arow = a0 | (a1 << 1);   // per x parity
+#pragma unroll
+        for (int cz = 0; cz < 2; ++cz)
+#pragma unroll
+          for (int by = 0; by < 2; ++by)
+            if (((zin >> cz) & 1u) && ((yin >> by) & 1u)) {
+              const int sh = 4 * cz + 2 * by;
+              orm |= orow << sh;
+              andm &= ~(0x3u << sh) | (arow << sh);
+            }
+      }
+    }
+    const unsigned mixed = orm & ~andm;
+#pragma unroll
+    for (int cz = 0; cz < 2; ++cz)
+#pragma unroll
+      for (int by = 0; by < 2; ++by)
+#pragma unroll
+        for (int ax = 0; ax < 2; ++ax) {
+          if ((cz && !ez) || (by && !ey) || (ax && !ex)) continue;
+          const bool known = !(cz | by | ax) && cell_known;
+          const bool cand = !known && ((mixed >> (4 * cz + 2 * by + ax)) & 1u);
+          candidates_t[((long long)(2 * k + ax) * res_f + (2 * j + by)) * res_f + (2 * i + cz)] = cand ? 1 : 0;
+        }
+  }
 }
 
 // functors for the ordered compaction -------------------------------------------------------------
@@ -130,12 +144,15 @@ struct EmitNodesT {      // i indexes the transposed [x][y][z] flag volume
   }
 };
 
-__global__ void total_to_count_kernel(const unsigned long long* total, int32_t* count, long long cap, long long* stat) {
-  unsigned long long t = *total;
-  if ((long long)t > cap) t = (unsigned long long)cap;
-  *count = (int32_t)t;
-  if (stat) *stat += (long long)t;
-}
+// scan hook: clamp the number of candidates to the list capacity and publish it as the device-side point count
+struct CountPost {
+  int32_t* count; long long cap; long long* stat;
+  __device__ void operator()(unsigned long long t) const {
+    if ((long long)t > cap) t = (unsigned long long)cap;
+    *count = (int32_t)t;
+    if (stat) *stat += (long long)t;
+  }
+};
 
 __global__ void iota_kernel(int32_t* idx, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) idx[i] = i;
@@ -379,7 +396,8 @@ extern "C" int mp_octree_create(int n_levels, const int* resolutions, const floa
   if (e == cudaSuccess) e = cudaMalloc(&h->points, cap * 3 * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&h->vals, cap * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&h->sums, (size_t)(mpscan::num_blocks(V) + 1) * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMalloc(&h->total, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&h->total, 2 * sizeof(unsigned long long));                 // [0] total, [1] scan ticket
+  if (e == cudaSuccess) e = cudaMemset(h->total, 0, 2 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&h->count, sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->nonempty, sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&h->stats, sizeof(long long) * (MP_MAX_LAYERS + 4));
@@ -411,10 +429,21 @@ static int build_level_list(mp_octree* h, int level, cudaStream_t st) {
   const int src_buf = h->cur, dst_buf = h->cur ^ 1;
   const bool last = level == h->n_levels - 1;
   const bool interp_only = h->use_topk || (h->faster && last);
-  upsample_kernel<<<dim3((unsigned)(((long long)res_c * res_c + 255) / 256), (unsigned)res_c), 256, 0, st>>>(h->vol[src_buf], h->use_topk ? nullptr : h->known[src_buf],
-                                                h->vol[dst_buf], h->use_topk ? nullptr : h->known[dst_buf],
-                                                interp_only ? nullptr : h->cand_t, res_c, res_f, radius_for(h, level),
-                                                h->balance);
+  {
+    const dim3 grid((unsigned)(((long long)res_c * res_c + 255) / 256), (unsigned)res_c);
+    const float* vc = h->vol[src_buf];
+    const uint8_t* kc = h->use_topk ? nullptr : h->known[src_buf];
+    float* vf = h->vol[dst_buf];
+    // (the last level of the `faster` engine is interpolation only: nothing reads its known mask afterwards)
+    uint8_t* kf = (h->use_topk || (h->faster && last)) ? nullptr : h->known[dst_buf];
+    const int radius = radius_for(h, level);
+    // the union of the eight boxes of a cell is at most radius + 2 coarse nodes wide
+    if (interp_only) upsample_kernel<0><<<grid, 256, 0, st>>>(vc, kc, vf, kf, nullptr, res_c, res_f, radius, h->balance);
+    else if (radius <= 1) upsample_kernel<3><<<grid, 256, 0, st>>>(vc, kc, vf, kf, h->cand_t, res_c, res_f, radius, h->balance);
+    else if (radius <= 3) upsample_kernel<5><<<grid, 256, 0, st>>>(vc, kc, vf, kf, h->cand_t, res_c, res_f, radius, h->balance);
+    else if (radius <= 4) upsample_kernel<6><<<grid, 256, 0, st>>>(vc, kc, vf, kf, h->cand_t, res_c, res_f, radius, h->balance);
+    else { mp_set_error("octree: box radius %d not supported", radius); return MP_E_UNSUPPORTED; }
+  }
   MP_CUDA(cudaGetLastError());
   h->cur = dst_buf;
   if (h->use_topk) {
@@ -443,8 +472,7 @@ static int build_level_list(mp_octree* h, int level, cudaStream_t st) {
   }
   FlagF f{h->cand_t};
   EmitNodesT em{h->idx, res_f, h->cap};
-  MP_CUDA(mpscan::scan_emit(f, em, nf, h->sums, h->total, st));
-  total_to_count_kernel<<<1, 1, 0, st>>>(h->total, h->count, h->cap, h->stats + level);
+  MP_CUDA(mpscan::scan_emit(f, em, nf, h->sums, h->total, st, CountPost{h->count, h->cap, h->stats + level}));
   MP_CUDA(cudaGetLastError());
   return MP_OK;
 }
@@ -457,8 +485,7 @@ static int build_conflict_list(mp_octree* h, int level, cudaStream_t st) {
   MP_CUDA(cudaMemsetAsync(h->conflict, 0, nf, st));
   FlagF f{h->cand_t};
   EmitNodesT em{h->idx, res, h->cap};
-  MP_CUDA(mpscan::scan_emit(f, em, nf, h->sums, h->total, st));
-  total_to_count_kernel<<<1, 1, 0, st>>>(h->total, h->count, h->cap, h->stats + level);
+  MP_CUDA(mpscan::scan_emit(f, em, nf, h->sums, h->total, st, CountPost{h->count, h->cap, h->stats + level}));
   MP_CUDA(cudaGetLastError());
   return MP_OK;
 }

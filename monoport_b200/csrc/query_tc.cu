@@ -1367,19 +1367,21 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
   }
 }
 
-// G0[texel][n] = sum_k F[texel][k] * W0f[n][k] on the tensor cores: fp16 operands (F rounded once while staging, W0f pre-packed on
-// the host as SWIZZLE_128B tiles) and fp32 accumulation in TMEM.  One CTA = one 128 (texels) x 256 (outputs) tile over the
-// whole K = 256: A is staged by all threads K-block by K-block (fp32 global -> fp16 swizzled smem), B arrives as four
-// 32 KB bulk copies, thread 0 issues each K-block's four MMAs right after its staging barrier so they overlap the next
-// block's loads; the epilogue reads the accumulator back (tcgen05.ld), rounds to fp16 and writes G rows.
-// The CTAs of the first output tile also publish what the staging pass has in hand anyway: the fp16 copy of the map
-// (F16, taps of the X operand) and S4 = W4s . F per texel in fp32 (the last layer's direct access to the features:
-// sampling S4 in fp32 keeps that path out of the fp16 roundings -- bilinear sampling commutes with the dot product).
-// 4.3 GFLOP per frame in ~40 us, which lets program v3 serve octree-sized queries too.
-constexpr int kG0Threads = 256;
+// G0[texel][n] = sum_k F[texel][k] * W0f[n][k] on the tensor cores: fp16 operands (F rounded once while staging, W0f
+// pre-packed on the host as SWIZZLE_128B tiles [n tile][K block][256 x 64]) and fp32 accumulation in TMEM.
+// One CTA = 128 texels x all 1024 outputs: the A operand (128 x 256) is staged ONCE by warps 0-7 (fp32 global -> fp16
+// swizzled smem, the latency-bound part), the 16 B tiles stream through a 4-stage bulk-copy ring (warp 8), warp 9 issues
+// the MMAs of the four 256-wide output tiles into two alternating TMEM accumulators, and warps 0-7 drain tile nt
+// (tcgen05.ld -> fp16 -> G rows) while tile nt+1 is being multiplied.  The staging pass also publishes what it has in
+// hand: the fp16 copy of the map (F16, taps of the X operand) and S4 = W4s . F per texel in fp32 (the last layer's
+// direct access to the features: sampling S4 in fp32 keeps that path out of the fp16 roundings -- bilinear sampling
+// commutes with the dot product).  4.3 GFLOP per frame, one wave of 128 CTAs.
+constexpr int kG0Threads = 320;
 constexpr int kG0TileN = 256;
-constexpr uint32_t kG0SmemA = 4 * 16384, kG0SmemB = 4 * 32768;
-constexpr uint32_t kG0Smem = kG0SmemA + kG0SmemB + 1024 /*align*/ + 64 /*barriers + tmem slot*/;
+constexpr int kG0NT = kL0 / kG0TileN;                 // 4 output tiles
+constexpr int kG0Stages = 4;
+constexpr uint32_t kG0SmemA = 4 * 16384, kG0SmemB = kG0Stages * 32768;
+constexpr uint32_t kG0Smem = kG0SmemA + kG0SmemB + 1024 /*align*/ + 128 /*barriers + tmem slot*/;
 
 __global__ void __launch_bounds__(kG0Threads, 1)
 g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half* __restrict__ G, int M,
@@ -1388,54 +1390,86 @@ g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g0_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;
   uint8_t* sB = base + kG0SmemA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + kG0SmemA + kG0SmemB);   // [0..3] B K-block landed, [4] MMAs done
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 5);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int m0 = blockIdx.x * 128, nt = blockIdx.y;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + kG0SmemA + kG0SmemB);
+  uint64_t* b_full = bars;                   // [4] B stage landed
+  uint64_t* b_empty = bars + 4;              // [4] B stage consumed (tcgen05.commit)
+  uint64_t* acc_full = bars + 8;             // [2] accumulator complete
+  uint64_t* acc_free = bars + 10;            // [2] accumulator drained by the 8 epilogue warps
+  uint64_t* a_ready = bars + 12;             // A staged (8 warps)
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 13);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * 128;
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
-    tc::mbar_init(&bars[4], 1);
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_free[i], 8); }
+    tc::mbar_init(a_ready, 8);
     tc::fence_barrier_init();
   }
-  if (warp == 0) {
-    tc::tmem_alloc(tslot, 256);
+  if (warp == 8) {
+    tc::tmem_alloc(tslot, 512);
     tc::tmem_relinquish();
   }
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tbase = *tslot;
-  if (tid == 0) {
-    const uint8_t* src = Wt + (size_t)nt * kG0SmemB;
-    for (int kb = 0; kb < 4; ++kb) {
-      tc::mbar_arrive_expect_tx(&bars[kb], 32768);
-      tc::bulk_g2s(sB + kb * 32768, src + (size_t)kb * 32768, 32768, &bars[kb]);
-    }
-  }
-  // A staging: thread -> (row = tid / 2, 32-column half of each 64-wide K-block)
-  const int row = tid >> 1, half = tid & 1;
-  const bool live = (m0 + row) < M;
-  const float* frow = F + (size_t)(live ? m0 + row : 0) * kC + half * 32;
   constexpr uint32_t idesc = tc::make_idesc_f16(128, kG0TileN);
-  const bool side = nt == 0 && live;            // this thread also publishes F16 / S4 for its (row, 32-channel half)
-  float s4acc[kMaxRes];
-#pragma unroll
-  for (int r = 0; r < kMaxRes; ++r) s4acc[r] = 0.f;
-  for (int kb = 0; kb < 4; ++kb) {
-    float4 v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = live ? __ldg(reinterpret_cast<const float4*>(frow + kb * 64) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 pk;
-      pk.x = tc::pack_half2(v[2 * j].x, v[2 * j].y);
-      pk.y = tc::pack_half2(v[2 * j].z, v[2 * j].w);
-      pk.z = tc::pack_half2(v[2 * j + 1].x, v[2 * j + 1].y);
-      pk.w = tc::pack_half2(v[2 * j + 1].z, v[2 * j + 1].w);
-      *reinterpret_cast<uint4*>(sA + kb * 16384 + tc::sw128_offset(row, half * 32 + j * 8)) = pk;
-      if (side) *reinterpret_cast<uint4*>(F16 + (size_t)(m0 + row) * kC + kb * 64 + half * 32 + j * 8) = pk;
+
+  if (warp == 8) {
+    // ---- B producer: 16 tiles in (nt, kb) order through the ring
+    if (lane == 0) {
+      for (int s = 0; s < kG0NT * 4; ++s) {
+        const int slot = s % kG0Stages;
+        if (s >= kG0Stages) tc::mbar_wait(&b_empty[slot], ((s / kG0Stages) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&b_full[slot], 32768);
+        tc::bulk_g2s(sB + slot * 32768, Wt + (size_t)s * 32768, 32768, &b_full[slot]);
+      }
     }
-    if (nt == 0) {
+  } else if (warp == 9) {
+    // ---- MMA issuer
+    if (lane == 0) {
+      tc::mbar_wait(a_ready, 0);
+      tc::tcgen05_fence_after();
+      for (int nt = 0; nt < kG0NT; ++nt) {
+        const int buf = nt & 1;
+        if (nt >= 2) { tc::mbar_wait(&acc_free[buf], ((nt >> 1) & 1) ^ 1); tc::tcgen05_fence_after(); }
+        for (int kb = 0; kb < 4; ++kb) {
+          const int s = nt * 4 + kb, slot = s % kG0Stages;
+          tc::mbar_wait(&b_full[slot], (s / kG0Stages) & 1);
+          tc::tcgen05_fence_after();
+          const uint32_t a0 = tc::smem_u32(sA + kb * 16384), b0 = tc::smem_u32(sB + slot * 32768);
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16)
+            tc::mma_ss(tbase + buf * kG0TileN, tc::make_sdesc_sw128(a0 + k16 * 32, 1024), tc::make_sdesc_sw128(b0 + k16 * 32, 1024), idesc,
+                       (kb | k16) ? 1u : 0u);
+          tc::mma_commit(&b_empty[slot]);
+        }
+        tc::mma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ---- warps 0-7: stage A (thread -> row = tid / 2, 32-column half of each 64-wide K-block), then drain
+    const int row = tid >> 1, half = tid & 1;
+    const bool live = (m0 + row) < M;
+    const float* frow = F + (size_t)(live ? m0 + row : 0) * kC + half * 32;
+    float s4acc[kMaxRes];
+#pragma unroll
+    for (int r = 0; r < kMaxRes; ++r) s4acc[r] = 0.f;
+#pragma unroll 1
+    for (int kb = 0; kb < 4; ++kb) {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = live ? __ldg(reinterpret_cast<const float4*>(frow + kb * 64) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 pk;
+        pk.x = tc::pack_half2(v[2 * j].x, v[2 * j].y);
+        pk.y = tc::pack_half2(v[2 * j].z, v[2 * j].w);
+        pk.z = tc::pack_half2(v[2 * j + 1].x, v[2 * j + 1].y);
+        pk.w = tc::pack_half2(v[2 * j + 1].z, v[2 * j + 1].w);
+        *reinterpret_cast<uint4*>(sA + kb * 16384 + tc::sw128_offset(row, half * 32 + j * 8)) = pk;
+        if (live) *reinterpret_cast<uint4*>(F16 + (size_t)(m0 + row) * kC + kb * 64 + half * 32 + j * 8) = pk;
+      }
 #pragma unroll
       for (int r = 0; r < kMaxRes; ++r)
         if (r < res) {
@@ -1449,53 +1483,48 @@ g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half
         }
     }
     tc::fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc::mbar_wait(&bars[kb], 0);
-      tc::tcgen05_fence_after();
-      const uint32_t a0 = tc::smem_u32(sA + kb * 16384), b0 = tc::smem_u32(sB + kb * 32768);
-#pragma unroll
-      for (int k16 = 0; k16 < 4; ++k16)
-        tc::mma_ss(tbase, tc::make_sdesc_sw128(a0 + k16 * 32, 1024), tc::make_sdesc_sw128(b0 + k16 * 32, 1024), idesc, (kb | k16) ? 1u : 0u);
-      if (kb == 3) tc::mma_commit(&bars[4]);
-    }
-  }
-  if (nt == 0) {                                  // (nt is CTA-uniform: all lanes take part in the shuffle)
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(a_ready);
 #pragma unroll
     for (int r = 0; r < kMaxRes; ++r) {
       const float tot = s4acc[r] + __shfl_xor_sync(0xffffffffu, s4acc[r], 1);
-      if (side && half == 0 && r < res) S4[(size_t)(m0 + row) * kMaxRes + r] = tot;
+      if (live && half == 0 && r < res) S4[(size_t)(m0 + row) * kMaxRes + r] = tot;
     }
-  }
-  tc::mbar_wait(&bars[4], 0);
-  __syncwarp();
-  tc::tcgen05_fence_after();
-  // epilogue: warp w reads lanes 32*(w%4).. (its TMEM sub-partition), columns 128*(w/4)..+127
-  {
-    const int lane = tid & 31, sub = warp & 3, ch = warp >> 2;
+    // epilogue: warp w reads lanes 32*(w%4).. (its TMEM sub-partition), columns 128*(w/4)..+127 of the 256-wide tile
+    const int sub = warp & 3, ch = warp >> 2;
     const int m = m0 + sub * 32 + lane;
-    __half* grow = G + (size_t)(m < M ? m : 0) * kL0 + nt * kG0TileN + ch * 128;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tc::tmem_ld32(tbase + ((uint32_t)(sub * 32) << 16) + ch * 128 + c * 32, r);
-      tc::tmem_ld_wait();
-      if (m < M) {
+    for (int nt = 0; nt < kG0NT; ++nt) {
+      const int buf = nt & 1;
+      tc::mbar_wait(&acc_full[buf], (nt >> 1) & 1);
+      __syncwarp();
+      tc::tcgen05_fence_after();
+      __half* grow = G + (size_t)(m < M ? m : 0) * kL0 + nt * kG0TileN + ch * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld32(tbase + ((uint32_t)(sub * 32) << 16) + buf * kG0TileN + ch * 128 + c * 32, r);
+        tc::tmem_ld_wait();
+        if (m < M) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 pk;
-          pk.x = tc::pack_half2(__uint_as_float(r[8 * q + 0]), __uint_as_float(r[8 * q + 1]));
-          pk.y = tc::pack_half2(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3]));
-          pk.z = tc::pack_half2(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5]));
-          pk.w = tc::pack_half2(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7]));
-          *reinterpret_cast<uint4*>(grow + c * 32 + q * 8) = pk;
+          for (int q = 0; q < 4; ++q) {
+            uint4 pk;
+            pk.x = tc::pack_half2(__uint_as_float(r[8 * q + 0]), __uint_as_float(r[8 * q + 1]));
+            pk.y = tc::pack_half2(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3]));
+            pk.z = tc::pack_half2(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5]));
+            pk.w = tc::pack_half2(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7]));
+            *reinterpret_cast<uint4*>(grow + c * 32 + q * 8) = pk;
+          }
         }
       }
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_free[buf]);
     }
   }
   tc::tcgen05_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tbase, 256);
+  if (warp == 8) tc::tmem_dealloc(tbase, 512);
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -1799,8 +1828,7 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
       feat->g0_owner = nullptr;
     }
     if (feat->g0_owner != (const void*)mlp || feat->g0_version != feat->version) {
-      dim3 gg((unsigned)((HW + 127) / 128), kL0 / kG0TileN);
-      g0_tc_kernel<<<gg, kG0Threads, kG0Smem, st>>>(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s, pk->res);
+      g0_tc_kernel<<<(unsigned)((HW + 127) / 128), kG0Threads, kG0Smem, st>>>(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s, pk->res);
       MP_CUDA(cudaGetLastError());
       feat->g0_owner = (const void*)mlp;
       feat->g0_version = feat->version;

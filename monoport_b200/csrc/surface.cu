@@ -93,8 +93,9 @@ extern "C" int mp_forward_vertices(const float* vol_dev, int R, int direction, i
   unsigned long long* sums = nullptr;
   mp_ensure_pool();
   MP_CUDA(cudaMallocAsync(&first_t, n * sizeof(int32_t), st));
-  MP_CUDA(cudaMallocAsync(&sums, (size_t)(mpscan::num_blocks(n) + 2) * sizeof(unsigned long long), st));
+  MP_CUDA(cudaMallocAsync(&sums, (size_t)(mpscan::num_blocks(n) + 3) * sizeof(unsigned long long), st));
   unsigned long long* total = sums + mpscan::num_blocks(n) + 1;
+  cudaMemsetAsync(total + 1, 0, sizeof(unsigned long long), st);   // ticket counter of the scan
   const int grid = (int)((n + 255) / 256);
   first_hit_kernel<<<grid, 256, 0, st>>>(vol_dev, R, direction, first_t);
   HitF f{first_t};
