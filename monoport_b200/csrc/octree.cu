@@ -283,6 +283,9 @@ struct TopkEmit {
   }
 };
 
+// per-level evaluated-node counters [MP_MAX_LAYERS + 4] + one slot for the non-empty flag
+constexpr int kStatSlots = MP_MAX_LAYERS + 5;
+
 inline int grid_for(long long n, int threads = 256, int cap = 148 * 8) {
   long long b = (n + threads - 1) / threads;
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
@@ -340,7 +343,6 @@ extern "C" int mp_octree_destroy(mp_octree_t* h) {
   if (h->sums) cudaFree(h->sums);
   if (h->total) cudaFree(h->total);
   if (h->count) cudaFree(h->count);
-  if (h->nonempty) cudaFree(h->nonempty);
   if (h->stats) cudaFree(h->stats);
   if (h->sel) cudaFree(h->sel);
   delete h;
@@ -399,8 +401,9 @@ extern "C" int mp_octree_create(int n_levels, const int* resolutions, const floa
   if (e == cudaSuccess) e = cudaMalloc(&h->total, 2 * sizeof(unsigned long long));                 // [0] total, [1] scan ticket
   if (e == cudaSuccess) e = cudaMemset(h->total, 0, 2 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&h->count, sizeof(int32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&h->nonempty, sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&h->stats, sizeof(long long) * (MP_MAX_LAYERS + 4));
+  if (e == cudaSuccess) e = cudaMalloc(&h->stats, sizeof(long long) * kStatSlots);
+  // the non-empty flag lives in the last slot of the stats buffer: one memset resets both, one copy reads both back
+  if (e == cudaSuccess) h->nonempty = reinterpret_cast<int*>(h->stats + kStatSlots - 1);
   if (e == cudaSuccess) e = cudaMalloc(&h->sel, sizeof(SelectState));
   if (e != cudaSuccess) {
     mp_set_error("mp_octree_create: %s", cudaGetErrorString(e));
@@ -491,8 +494,7 @@ static int build_conflict_list(mp_octree* h, int level, cudaStream_t st) {
 }
 
 static int reset_run(mp_octree* h, cudaStream_t st) {
-  MP_CUDA(cudaMemsetAsync(h->nonempty, 0, sizeof(int), st));
-  MP_CUDA(cudaMemsetAsync(h->stats, 0, sizeof(long long) * (MP_MAX_LAYERS + 4), st));
+  MP_CUDA(cudaMemsetAsync(h->stats, 0, sizeof(long long) * kStatSlots, st));   // includes the non-empty flag
   if (!h->use_topk && !h->faster) MP_CUDA(cudaMemsetAsync(h->conflict, 0, h->vol_elems, st));   // only the lossless loop reads it
   h->cur = 0;
   return MP_OK;
@@ -697,11 +699,11 @@ extern "C" int mp_octree_run_fused(mp_octree_t* h, mp_mlp_t* mlp, mp_feat_t* fea
   h->vol[final_buf] = own_buf;
   if (rc != MP_OK) return rc;
   if (!in_place) MP_CUDA(cudaMemcpyAsync(out_dev, result, h->vol_elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  long long stats[MP_MAX_LAYERS + 4];
+  long long stats[kStatSlots];
   int ne = 0;
-  MP_CUDA(cudaMemcpyAsync(&ne, h->nonempty, sizeof(int), cudaMemcpyDeviceToHost, st));
   MP_CUDA(cudaMemcpyAsync(stats, h->stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
   MP_CUDA(cudaStreamSynchronize(st));
+  ne = *reinterpret_cast<const int*>(stats + kStatSlots - 1);
   *nonempty = ne;
   if (stats_host) for (int l = 0; l < h->n_levels; ++l) stats_host[l] = stats[l];
   h->phase = 2;

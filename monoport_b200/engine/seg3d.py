@@ -64,7 +64,7 @@ class _Seg3dBase(nn.Module):
             res = (ctypes.c_int * n)(*self.resolutions)
             topk = None if self.topk_points is None else (ctypes.c_int * n)(*self.topk_points)
             h = ctypes.c_void_p()
-            with torch.cuda.device(device):
+            with _lib.device_guard(device):
                 _lib.check(_lib.load().mp_octree_create(
                     n, res, _lib.f3(self.b_min), _lib.f3(self.b_max), ctypes.c_float(self.balance_value),
                     1 if self.faster else 0, topk, ctypes.byref(h)), "mp_octree_create")
@@ -101,7 +101,7 @@ class _Seg3dBase(nn.Module):
         nonempty = ctypes.c_int(0)
         stats = (ctypes.c_int64 * len(self.resolutions))()
         from ..modeling.geometry import perspective
-        with torch.cuda.device(device):
+        with _lib.device_guard(device):
             fh = net.feature_handle(feat)
             proj = _lib.PROJ_PERSPECTIVE if net.projection is perspective else _lib.PROJ_ORTHOGONAL
             _lib.check(lib.mp_octree_run_fused(
@@ -115,7 +115,7 @@ class _Seg3dBase(nn.Module):
         lib = _lib.load()
         h = self._handle(device)
         stats = [0] * len(self.resolutions)
-        with torch.cuda.device(device):
+        with _lib.device_guard(device):
             st = _lib.stream_ptr(device)
             _lib.check(lib.mp_octree_begin(h, st), "mp_octree_begin")
             while True:

@@ -27,7 +27,7 @@ class FeatureHandle:
         self.shape = (C, H, W)
         self.device = device
         self.ptr = ctypes.c_void_p()
-        with torch.cuda.device(device):
+        with _lib.device_guard(device):
             _lib.check(_lib.load().mp_feat_create(C, H, W, ctypes.byref(self.ptr)), "mp_feat_create")
         self.key = None
         self._src = None
@@ -129,7 +129,7 @@ class MonoPortNet(nn.Module):
         out = torch.empty((1, res, n), dtype=torch.float32, device=feat.device)
         if n == 0:
             return [out]
-        with torch.cuda.device(feat.device):
+        with _lib.device_guard(feat.device):
             fh = self.feature_handle(feat)
             proj = _lib.PROJ_PERSPECTIVE if self.projection is perspective else _lib.PROJ_ORTHOGONAL
             _lib.check(_lib.load().mp_query_points(
@@ -144,7 +144,7 @@ class MonoPortNet(nn.Module):
         nz = R - z0 if nz is None else int(nz)
         if out is None:
             out = torch.empty((nz, R, R), dtype=torch.float32, device=feat.device)
-        with torch.cuda.device(feat.device):
+        with _lib.device_guard(feat.device):
             fh = self.feature_handle(feat)
             proj = _lib.PROJ_PERSPECTIVE if self.projection is perspective else _lib.PROJ_ORTHOGONAL
             _lib.check(_lib.load().mp_query_grid(

@@ -47,7 +47,7 @@ def forward_vertices(sdf, direction="front"):
     Z = torch.empty(cap, dtype=torch.float32, device=dev)
     N = torch.empty((cap, 3), dtype=torch.float32, device=dev)
     n = ctypes.c_int64(0)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.check(_lib.load().mp_forward_vertices(
             ctypes.c_void_p(vol.data_ptr()), R, _DIRS[direction], ctypes.c_void_p(X.data_ptr()),
             ctypes.c_void_p(Y.data_ptr()), ctypes.c_void_p(Z.data_ptr()), ctypes.c_void_p(N.data_ptr()),
@@ -65,7 +65,7 @@ class _McubesWorkspace:
         h = cls._cache.get(key)
         if h is None:
             h = ctypes.c_void_p()
-            with torch.cuda.device(device):
+            with _lib.device_guard(device):
                 _lib.check(_lib.load().mp_mcubes_create(shape[0], shape[1], shape[2], ctypes.byref(h)), "mp_mcubes_create")
             cls._cache[key] = h
         return h
@@ -85,7 +85,7 @@ def marching_cubes(vol, iso=0.5):
     lib = _lib.load()
     h = _McubesWorkspace.get(vol.shape, dev)
     nv, nf = ctypes.c_int64(0), ctypes.c_int64(0)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         st = _lib.stream_ptr(dev)
         _lib.check(lib.mp_mcubes_count(h, ctypes.c_void_p(vol.data_ptr()), ctypes.c_float(iso), ctypes.byref(nv),
                                        ctypes.byref(nf), st), "mp_mcubes_count")

@@ -195,3 +195,40 @@ def test_concurrent_queries_from_threads():
     tcol = threading.Thread(target=run, args=(netC, fc, pc, calc, cc["expected"], 2e-5, 20))
     tg.start(); tcol.start(); tg.join(); tcol.join()
     assert not errs, errs
+
+
+def test_new_frame_at_a_recycled_address_is_uploaded():
+    """The demo loop produces a fresh feature tensor per frame; the caching allocator readily hands the freed
+    storage of frame t to frame t+1.  (address, version) alone would call that "unchanged" and keep stale features."""
+    c = load_query_case("g_rot33")
+    net = build_net(c)
+    pts, cal = c["points"][:, :, :2000].cuda(), c["calib"].cuda()
+    ref_net = build_net(c)
+    for mode in _modes(net):
+        net.precision = mode
+        ref_net.precision = mode
+        for seed in (1, 2, 3):
+            f = spec.make_feat(256, 128, 128, 700 + seed).cuda()
+            net.query([[f]], pts, calibs=cal)
+            del f                                                      # frame t is gone ...
+            f2 = spec.make_feat(256, 128, 128, 800 + seed).cuda()      # ... frame t+1 has the same shape (same pool bucket)
+            got = net.query([[f2]], pts, calibs=cal)[0].clone()
+            want = ref_net.query([[f2.clone()]], pts, calibs=cal)[0]
+            assert torch.equal(got, want), (mode, seed)
+            # in-place update of a live tensor bumps the version: must be re-uploaded too
+            f2.mul_(0.5)
+            half = net.query([[f2]], pts, calibs=cal)[0]
+            assert not torch.equal(half, want)
+
+
+def test_calib_cache_follows_inplace_updates():
+    c = load_query_case("g_rot33")
+    net = build_net(c)
+    feat, pts = c["feat"].cuda(), c["points"][:, :, :500].cuda()
+    cal = c["calib"].cuda().clone()
+    a = net.query([[feat]], pts, calibs=cal)[0].clone()
+    cal[0, 0, 3] += 0.05                                               # same tensor, new content
+    b = net.query([[feat]], pts, calibs=cal)[0].clone()
+    assert not torch.equal(a, b)
+    fresh = build_net(c).query([[feat]], pts, calibs=cal.clone())[0]
+    assert torch.equal(b, fresh)
