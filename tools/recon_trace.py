@@ -9,7 +9,9 @@ import bench
 ap = argparse.ArgumentParser()
 ap.add_argument("--color", action="store_true")
 ap.add_argument("--frames", type=int, default=5)
-ap.add_argument("--no-profiler", action="store_true", help="just run frames (for ncu)")
+ap.add_argument("--no-profiler", action="store_true", help="just run frames inside a cudaProfilerStart/Stop range "
+                                                          "(ncu --profile-from-start off)")
+ap.add_argument("--mc", action="store_true", help="also run marching cubes on every frame")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.cuda.set_device(dev)
@@ -24,7 +26,7 @@ net.eval()
 feats = [f.to(dev) for f in feats]
 cal = bench.scene_calib().to(dev)
 from monoport_b200.engine import Seg3dLossless, make_query_func
-from monoport_b200.recon import forward_vertices, colorization
+from monoport_b200.recon import forward_vertices, colorization, marching_cubes
 b = np.array([bench.B_MIN], dtype=np.float32)
 eng = Seg3dLossless(make_query_func(net), b, -b, [17, 33, 65, 129, 257], balance_value=0.5, faster=True).to(dev)
 netC = featC = None
@@ -37,6 +39,8 @@ if a.color:
 def frame(i):
     sdf = eng(im_feat_list=[[feats[i % 4]]], calib_tensor=cal)
     X, Y, Z, nrm = forward_vertices(sdf, "front")
+    if a.mc:
+        marching_cubes(sdf[0, 0])
     if a.color:
         return colorization(netC, featC, X, Y, Z, cal)
     return X
@@ -45,9 +49,11 @@ for i in range(3):
     frame(i)
 torch.cuda.synchronize()
 if a.no_profiler:
+    torch.cuda.profiler.start()
     for i in range(a.frames):
         frame(i)
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     sys.exit(0)
 t0 = time.perf_counter()
 for i in range(20):
