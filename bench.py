@@ -431,11 +431,11 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from profiles/r01_ncu_tc_v5_hoisted_summary.txt
-                         # (ncu --set full, 257^3, N=1): 47.39 MB + 42.23 MB per launch
-                         "traffic": (89.62e6 if (launches_per_step == 3 and world == 1 and R == R_GRID) else None),
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from profiles/r01_final_ncu_tc_summary.txt
+                         # (ncu --set full, 257^3, N=1, final code of round 1): 45.55 MB + 38.89 MB per launch
+                         "traffic": (84.44e6 if (launches_per_step == 3 and world == 1 and R == R_GRID) else None),
                          "traffic_unit": "bytes/launch (ncu capture r01, not re-measured in this run)",
-                         "kernel": ("query_tc3_kernel (+ g0_kernel, the per-frame per-texel layer-0 GEMM)" if launches_per_step == 3
+                         "kernel": ("query_tc3_kernel (+ g0_tc_kernel, the per-frame per-texel layer-0 GEMM, 26 us)" if launches_per_step == 3
                                     else "query_%s_kernel" % mode_used),
                          "kernel_ms": 1e3 * k_avg_s, "peak_source": pk["source"] + " bf16 sustained (cuBLAS loop)",
                          "frac_of_burst": achieved_tf / pk["tf_burst"],
