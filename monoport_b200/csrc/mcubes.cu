@@ -3,115 +3,18 @@
 // HBM-bound byte/integer work.  Indexed, watertight mesh with deterministic ids:
 //   vertex id = rank of (node, axis) among active owned edges (every grid edge is owned by its lower node);
 //   face order = (cell linear index, table order).
-// count:  classify_kernel (1 read of the volume: per node 3 owned-edge bits + per cell case/tri count, packed in
-//         one byte per node)  ->  ordered scan of (verts, tris) packed in one uint64  -> totals.
-// emit :  the scan is re-run with an emit functor that writes vertices (coalesced by node order) and faces.
+// count:  classify_kernel (1 read of the volume, rows walked by warps, no divisions: per node 3 owned-edge bits + the
+//         triangle count of its cell packed in one byte, + the cell's case byte)  ->  ordered scan of (verts, tris)
+//         packed in one uint64 (8-byte loads of the code bytes); the emit half of the scan stores the exclusive vertex
+//         offset of the nodes that own a vertex (sparse: faces look up nothing else)  -> totals.
+// emit :  mesh_emit_kernel re-runs the block-local scan, queues the block's active nodes in shared memory and spreads
+//         their up to 3 vertices + 15 face corners over the whole CTA (one short dependent chain per thread instead of
+//         one thread walking a whole cell).
 #include "mp_common.cuh"
-#include "mp_scan.cuh"
-#include "mc_table.inc"
+#include "mcubes_kernels.cuh"
 
-namespace {
+using namespace mcubes;
 
-// per node byte: bits 0..2 = owned +x/+y/+z edge active; bits 3..5 = triangle count of the cell whose corner 0 is
-// this node (0 when the node is on the +face of the grid)
-__global__ void __launch_bounds__(256)
-classify_kernel(const float* __restrict__ vol, uint8_t* __restrict__ code, uint8_t* __restrict__ cases, int D, int H,
-                int W, float iso) {
-  const long long n = (long long)D * H * W;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W), y = (int)((i / W) % H), z = (int)(i / ((long long)W * H));
-    const bool xi = x + 1 < W, yi = y + 1 < H, zi = z + 1 < D;
-    auto in = [&](int dz, int dy, int dx) { return __ldg(vol + i + ((long long)dz * H + dy) * W + dx) > iso; };
-    const bool b0 = in(0, 0, 0);
-    uint8_t c = 0;
-    if (xi && (in(0, 0, 1) != b0)) c |= 1;
-    if (yi && (in(0, 1, 0) != b0)) c |= 2;
-    if (zi && (in(1, 0, 0) != b0)) c |= 4;
-    uint8_t cs = 0;
-    if (xi && yi && zi) {
-      int k = b0 ? 1 : 0;
-      k |= in(0, 0, 1) ? 2 : 0;
-      k |= in(0, 1, 0) ? 4 : 0;
-      k |= in(0, 1, 1) ? 8 : 0;
-      k |= in(1, 0, 0) ? 16 : 0;
-      k |= in(1, 0, 1) ? 32 : 0;
-      k |= in(1, 1, 0) ? 64 : 0;
-      k |= in(1, 1, 1) ? 128 : 0;
-      cs = (uint8_t)k;
-      c |= (uint8_t)(c_mc_ntri[k] << 3);
-    }
-    code[i] = c;
-    cases[i] = cs;
-  }
-}
-
-struct CountF {    // low 32: vertices owned by node i, high 32: triangles of cell i
-  const uint8_t* code;
-  __device__ unsigned long long operator()(long long i) const {
-    const uint32_t c = code[i];
-    return (unsigned long long)__popc(c & 7u) | ((unsigned long long)(c >> 3) << 32);
-  }
-};
-
-struct OffsetsEmit {   // stores the exclusive vertex offset of every node (faces need random access to it)
-  uint32_t* voff;
-  __device__ void operator()(long long i, unsigned long long, unsigned long long pre) const { voff[i] = (uint32_t)pre; }
-};
-
-struct MeshEmit {
-  const float* vol; const uint8_t* code; const uint8_t* cases; const uint32_t* voff;
-  float* verts; int32_t* faces; int D, H, W; float iso;
-  __device__ void operator()(long long i, unsigned long long val, unsigned long long pre) const {
-    if (!val) return;
-    const uint32_t c = code[i];
-    const int x = (int)(i % W), y = (int)((i / W) % H), z = (int)(i / ((long long)W * H));
-    // vertices on the owned edges, axis order
-    if (c & 7u) {
-      uint32_t v = (uint32_t)pre;
-      const float va = vol[i];
-      const long long step[3] = {1, W, (long long)W * H};
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        if (!(c >> a & 1u)) continue;
-        const float vb = vol[i + step[a]];
-        const float t = __fdiv_rn(__fsub_rn(iso, va), __fsub_rn(vb, va));
-        float p[3] = {(float)x, (float)y, (float)z};
-        p[a] = __fadd_rn(p[a], t);
-        verts[3ll * v + 0] = p[0]; verts[3ll * v + 1] = p[1]; verts[3ll * v + 2] = p[2];
-        ++v;
-      }
-    }
-    const int nt = (int)(c >> 3);
-    if (nt) {
-      const int k = cases[i];
-      long long f = (long long)(pre >> 32);
-      for (int t = 0; t < nt; ++t) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int e = c_mc_tri[k][3 * t + j];
-          // edge -> owning node + axis.  edges 0-3 along x at (y,z) offsets, 4-7 along y at (x,z), 8-11 along z at (x,y)
-          const int axis = e >> 2, q = e & 3;
-          int ox = 0, oy = 0, oz = 0;
-          if (axis == 0) { oy = q & 1; oz = q >> 1; }
-          else if (axis == 1) { ox = q & 1; oz = q >> 1; }
-          else { ox = q & 1; oy = q >> 1; }
-          const long long node = i + ((long long)oz * H + oy) * W + ox;
-          const uint32_t cn = code[node] & 7u;
-          const uint32_t rank = __popc(cn & ((1u << axis) - 1u));
-          faces[3 * f + j] = (int32_t)(voff[node] + rank);
-        }
-        ++f;
-      }
-    }
-  }
-};
-
-inline int grid_for(long long n) {
-  long long b = (n + 255) / 256;
-  return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
-}
-
-}  // namespace
 
 struct mp_mcubes {
   int D, H, W;
@@ -139,7 +42,7 @@ extern "C" int mp_mcubes_destroy(mp_mcubes_t* h) {
 extern "C" int mp_mcubes_create(int D, int H, int W, mp_mcubes_t** out) {
   MP_REQUIRE(out != nullptr, "out is NULL");
   *out = nullptr;
-  MP_REQUIRE(D >= 2 && H >= 2 && W >= 2 && (long long)D * H * W < (1ll << 31), "bad volume shape %dx%dx%d", D, H, W);
+  MP_REQUIRE(D >= 2 && H >= 2 && W >= 2 && (long long)D * H * W < (1ll << 31) && H <= kClassRows * 65535, "bad volume shape %dx%dx%d", D, H, W);
   mp_mcubes* h = new mp_mcubes();
   memset(h, 0, sizeof(*h));
   h->D = D; h->H = H; h->W = W;
@@ -163,7 +66,8 @@ extern "C" int mp_mcubes_count(mp_mcubes_t* h, const float* vol_dev, float iso, 
                                void* stream) {
   MP_REQUIRE(h && vol_dev && n_verts && n_faces, "NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
-  classify_kernel<<<grid_for(h->n), 256, 0, st>>>(vol_dev, h->code, h->cases, h->D, h->H, h->W, iso);
+  classify_kernel<<<dim3((unsigned)h->D, (unsigned)((h->H + kClassRows - 1) / kClassRows)), dim3(32, kClassRows), 0, st>>>(
+      vol_dev, h->code, h->cases, h->D, h->H, h->W, iso);
   MP_CUDA(cudaGetLastError());
   CountF f{h->code};
   OffsetsEmit em{h->voff};
@@ -186,10 +90,9 @@ extern "C" int mp_mcubes_emit(mp_mcubes_t* h, const float* vol_dev, float iso, f
   if (h->nv == 0 && h->nf == 0) return MP_OK;
   MP_REQUIRE(verts_dev && faces_dev, "NULL output buffers");
   cudaStream_t st = (cudaStream_t)stream;
-  CountF f{h->code};
-  MeshEmit em{vol_dev, h->code, h->cases, h->voff, verts_dev, faces_dev, h->D, h->H, h->W, iso};
   // block offsets in h->sums are still valid from the count pass: only the emit launch is needed
-  mpscan::emit_kernel<CountF, MeshEmit><<<mpscan::num_blocks(h->n), mpscan::kThreads, 0, st>>>(f, em, h->n, h->sums);
+  mesh_emit_kernel<<<mpscan::num_blocks(h->n), mpscan::kThreads, 0, st>>>(vol_dev, h->code, h->cases, h->voff, h->sums, verts_dev,
+                                                                         faces_dev, h->H, h->W, h->n, iso);
   MP_CUDA(cudaGetLastError());
   return MP_OK;
 }

@@ -6,6 +6,8 @@
 // `post(total)` hook (device-side counts for the next kernel) -> re-evaluate + local scan + emit.
 // The per-element value comes from a functor `uint64 f(i)` (two packed 32-bit counters are allowed),
 // `emit(i, value, exclusive_prefix)` consumes the result.  HBM-bound: the functor's reads happen twice.
+// A functor declares `static constexpr bool kVec8`; when true it also provides `load8(i, v[8])` for eight consecutive
+// elements starting at a multiple of 8 (one 8-byte load instead of eight byte loads for the flag / code volumes).
 #pragma once
 #include <stdint.h>
 
@@ -47,18 +49,42 @@ struct NoPost {
   __device__ void operator()(unsigned long long) const {}
 };
 
+static_assert(kItems == 8, "load8 functors cover exactly one thread's items");
+
+// the kItems values of the thread whose first element is `base` (a multiple of kItems); elements >= n count as 0
+template <class F>
+__device__ __forceinline__ void load_items(const F& f, long long base, long long n, unsigned long long (&v)[kItems]) {
+  if constexpr (F::kVec8) {
+    if (base + kItems <= n) {
+      f.load8(base, v);
+      return;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) v[j] = (base + j < n) ? f(base + j) : 0ull;
+}
+
+// eight consecutive bytes at p + i (i a multiple of 8, p 8-byte aligned) as one load; byte j lands in b[j]
+__device__ __forceinline__ void load_bytes8(const uint8_t* p, long long i, uint32_t (&b)[kItems]) {
+  const uint2 w = __ldg(reinterpret_cast<const uint2*>(p + i));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    b[j] = (w.x >> (8 * j)) & 0xFFu;
+    b[4 + j] = (w.y >> (8 * j)) & 0xFFu;
+  }
+}
+
 // sums[0..nb) <- exclusive scan of the CTA totals, total[0] <- grand total.  total[1] is the ticket counter: zero on entry
 // (zero-initialised once by the owner of the workspace), reset to zero by the last CTA.
 template <class F, class P>
 __global__ void __launch_bounds__(kThreads) block_sums_kernel(F f, long long n, unsigned long long* __restrict__ sums, int nb,
                                                               unsigned long long* __restrict__ total, P post) {
   const long long base = (long long)blockIdx.x * kChunk + (long long)threadIdx.x * kItems;
+  unsigned long long v[kItems];
+  load_items(f, base, n, v);
   unsigned long long s = 0;
 #pragma unroll
-  for (int j = 0; j < kItems; ++j) {
-    const long long i = base + j;
-    if (i < n) s += f(i);
-  }
+  for (int j = 0; j < kItems; ++j) s += v[j];
   unsigned long long tot;
   block_excl_scan(s, &tot);
   __shared__ bool is_last;
@@ -96,13 +122,10 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(F f, E emit, long long n
                                                         const unsigned long long* __restrict__ offsets) {
   const long long base = (long long)blockIdx.x * kChunk + (long long)threadIdx.x * kItems;
   unsigned long long v[kItems];
+  load_items(f, base, n, v);
   unsigned long long s = 0;
 #pragma unroll
-  for (int j = 0; j < kItems; ++j) {
-    const long long i = base + j;
-    v[j] = i < n ? f(i) : 0ull;
-    s += v[j];
-  }
+  for (int j = 0; j < kItems; ++j) s += v[j];
   unsigned long long run = offsets[blockIdx.x] + block_excl_scan(s, nullptr);
 #pragma unroll
   for (int j = 0; j < kItems; ++j) {
@@ -114,6 +137,7 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(F f, E emit, long long n
 
 inline int num_blocks(long long n) { return (int)((n + kChunk - 1) / kChunk); }
 
+#ifdef __CUDACC__   // (the launcher below is the only part tests/emu cannot take)
 // `sums` needs num_blocks(n) entries, `total` two: [0] receives the grand total, [1] is the ticket counter and must be
 // zero on entry (it is left at zero).  Both device memory.
 template <class F, class E, class P = NoPost>
@@ -124,5 +148,6 @@ inline cudaError_t scan_emit(F f, E emit, long long n, unsigned long long* sums,
   if (n > 0) emit_kernel<F, E><<<nb, kThreads, 0, st>>>(f, emit, n, sums);
   return cudaGetLastError();
 }
+#endif  // __CUDACC__
 
 }  // namespace mpscan

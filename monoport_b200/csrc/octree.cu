@@ -129,8 +129,15 @@ upsample_kernel(const float* __restrict__ vc, const uint8_t* __restrict__ known_
 
 // functors for the ordered compaction -------------------------------------------------------------
 struct FlagF {
-  const uint8_t* flags;
+  const uint8_t* flags;       // cudaMalloc'ed (8-byte aligned) 0/1 flags
+  static constexpr bool kVec8 = true;
   __device__ unsigned long long operator()(long long i) const { return flags[i]; }
+  __device__ void load8(long long i, unsigned long long (&v)[8]) const {
+    uint32_t b[8];
+    mpscan::load_bytes8(flags, i, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = b[j];
+  }
 };
 struct EmitNodesT {      // i indexes the transposed [x][y][z] flag volume
   int32_t* idx;
@@ -268,6 +275,7 @@ __global__ void select_pick_kernel(SelectState* s, int pass) {
 
 struct TopkF {   // low 32 bits: key < T ; high 32 bits: key == T
   const float* v; float balance; const SelectState* s;
+  static constexpr bool kVec8 = false;
   __device__ unsigned long long operator()(long long i) const {
     const uint32_t key = topk_key(v[i], balance), t = s->threshold;
     return key < t ? 1ull : (key == t ? (1ull << 32) : 0ull);

@@ -53,6 +53,7 @@ first_hit_kernel(const float* __restrict__ vol, int R, int dir, int32_t* __restr
 
 struct HitF {
   const int32_t* first_t;
+  static constexpr bool kVec8 = false;
   __device__ unsigned long long operator()(long long i) const { return first_t[i] >= 0 ? 1ull : 0ull; }
 };
 

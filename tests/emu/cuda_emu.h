@@ -1,0 +1,102 @@
+// TEST INFRASTRUCTURE ONLY -- a minimal CPU emulation of the CUDA execution model, just enough to run the integer /
+// byte kernels of monoport_b200/csrc (*_kernels.cuh, mp_scan.cuh) UNMODIFIED on the build container, which has no GPU:
+// one OS thread per CUDA thread, CTAs executed one after the other, __syncthreads() = a pthread barrier over the CTA,
+// warp shuffles = an exchange buffer between two 32-thread barriers, `__shared__` = a static variable (valid because
+// only one CTA is alive at a time).  It checks index arithmetic, scan / queue logic and table use against the oracle
+// before a kernel is ever sent to a B200; it says nothing about performance or memory-model subtleties.
+// Nothing under monoport_b200/ includes this file.
+#pragma once
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <pthread.h>
+#include <thread>
+#include <vector>
+
+#define MP_CUDA_EMU 1
+
+struct uint3_emu { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct uint2 { unsigned x, y; };
+
+inline thread_local uint3_emu threadIdx, blockIdx;
+inline thread_local dim3 blockDim, gridDim;
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __constant__
+
+namespace cuda_emu {
+constexpr int kMaxThreads = 1024;
+inline pthread_barrier_t g_cta_barrier;
+inline pthread_barrier_t g_warp_barrier[kMaxThreads / 32];
+inline unsigned long long g_shfl[kMaxThreads];
+inline int linear_tid() { return (int)(threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)); }
+
+// run `body` once per CUDA thread of a grid x block launch.  The CTA's threads are created once per launch and walk the
+// grid together (one barrier between CTAs, so the static "shared memory" is never reused while a thread is still in
+// the previous CTA).
+template <class Body>
+void launch(dim3 grid, dim3 block, Body body) {
+  const int nt = (int)(block.x * block.y * block.z);
+  if (nt > kMaxThreads || nt % 32 != 0) { fprintf(stderr, "cuda_emu: block of %d threads unsupported\n", nt); abort(); }
+  pthread_barrier_init(&g_cta_barrier, nullptr, nt);
+  for (int w = 0; w < nt / 32; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, 32);
+  std::vector<std::thread> th;
+  th.reserve(nt);
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([=] {
+      threadIdx = {(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
+      blockDim = block;
+      gridDim = grid;
+      for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+          for (unsigned bx = 0; bx < grid.x; ++bx) {
+            blockIdx = {bx, by, bz};
+            body();
+            pthread_barrier_wait(&g_cta_barrier);
+          }
+    });
+  for (auto& x : th) x.join();
+  pthread_barrier_destroy(&g_cta_barrier);
+  for (int w = 0; w < nt / 32; ++w) pthread_barrier_destroy(&g_warp_barrier[w]);
+}
+}  // namespace cuda_emu
+
+inline void __syncthreads() { pthread_barrier_wait(&cuda_emu::g_cta_barrier); }
+inline void __syncwarp() { pthread_barrier_wait(&cuda_emu::g_warp_barrier[cuda_emu::linear_tid() >> 5]); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+
+inline unsigned long long __shfl_up_sync(unsigned, unsigned long long v, int delta) {
+  const int tid = cuda_emu::linear_tid(), lane = tid & 31;
+  cuda_emu::g_shfl[tid] = v;
+  pthread_barrier_wait(&cuda_emu::g_warp_barrier[tid >> 5]);
+  const unsigned long long r = lane >= delta ? cuda_emu::g_shfl[tid - delta] : v;
+  pthread_barrier_wait(&cuda_emu::g_warp_barrier[tid >> 5]);
+  return r;
+}
+
+template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __ldcg(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fsqrt_rn(float a) { return sqrtf(a); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T min(T a, T b) { return a < b ? a : b; }
+template <class T> inline T max(T a, T b) { return a > b ? a : b; }

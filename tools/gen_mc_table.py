@@ -155,6 +155,12 @@ def write_inc(path):
         for c in range(256):
             f.write("  {%s},\n" % ",".join(str(int(v)) for v in tri[c]))
         f.write("};\n")
+        # the same table in global memory, rows padded to 16 bytes: divergent per-lane lookups (one case per active cell)
+        # go through L1 instead of serialising on the constant cache
+        f.write("static __device__ const signed char g_mc_tri[256][16] = {\n")
+        for c in range(256):
+            f.write("  {%s},\n" % ",".join([str(int(v)) for v in tri[c]] + ["-1"] * (16 - tri.shape[1])))
+        f.write("};\n")
     return maxt
 
 
