@@ -96,24 +96,23 @@ __global__ void __launch_bounds__(kThreads) block_sums_kernel(F f, long long n, 
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  __shared__ unsigned long long carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int b0 = 0; b0 < nb; b0 += kThreads) {
-    const int i = b0 + threadIdx.x;
-    const unsigned long long v = i < nb ? __ldcg(sums + i) : 0ull;
-    unsigned long long t;
-    const unsigned long long ex = block_excl_scan(v, &t);
-    const unsigned long long carry = carry_s;
-    if (i < nb) sums[i] = carry + ex;
-    __syncthreads();
-    if (threadIdx.x == 0) carry_s = carry + t;
-    __syncthreads();
+  // the last CTA turns the nb CTA totals into exclusive offsets: thread t owns the contiguous run [t*per, (t+1)*per)
+  // (two independent passes over L2-resident values + ONE block scan, instead of a block scan per 256 entries)
+  const int per = (nb + kThreads - 1) / kThreads;
+  const int b0 = (int)threadIdx.x * per, b1 = min(b0 + per, nb);
+  unsigned long long local = 0;
+  for (int i = b0; i < b1; ++i) local += __ldcg(sums + i);
+  unsigned long long grand;
+  unsigned long long run = block_excl_scan(local, &grand);
+  for (int i = b0; i < b1; ++i) {
+    const unsigned long long v = __ldcg(sums + i);
+    sums[i] = run;
+    run += v;
   }
   if (threadIdx.x == 0) {
-    total[0] = carry_s;
+    total[0] = grand;
     total[1] = 0;
-    post(carry_s);
+    post(grand);
   }
 }
 

@@ -87,6 +87,16 @@ inline unsigned long long __shfl_up_sync(unsigned, unsigned long long v, int del
   return r;
 }
 
+inline unsigned __ballot_sync(unsigned, bool pred) {
+  const int tid = cuda_emu::linear_tid(), w0 = tid & ~31;
+  cuda_emu::g_shfl[tid] = pred ? 1ull : 0ull;
+  pthread_barrier_wait(&cuda_emu::g_warp_barrier[tid >> 5]);
+  unsigned r = 0;
+  for (int l = 0; l < 32; ++l) r |= (unsigned)cuda_emu::g_shfl[w0 + l] << l;
+  pthread_barrier_wait(&cuda_emu::g_warp_barrier[tid >> 5]);
+  return r;
+}
+
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcg(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
