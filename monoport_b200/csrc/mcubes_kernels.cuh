@@ -10,78 +10,50 @@ namespace mcubes {
 
 // per node byte: bits 0..2 = owned +x/+y/+z edge active; bits 3..5 = triangle count of the cell whose corner 0 is
 // this node (0 when the node is on the +face of the grid).
-// Block (32, 8) = eight rows of one z plane, one warp per row; grid (D, ceil(H/8)).  A warp walks its row in groups of
-// kClassGroup chunks of 32 nodes: every node's value is loaded ONCE per neighbouring row (4 coalesced loads per chunk,
-// all loads of a group in flight together), turned into an inside/outside ballot, and the x+1 neighbour of a node is
-// the next bit of the same ballot (bit 0 of the following chunk's for lane 31) -- no second load, no divisions.
+// Block (32, 8) = eight rows of one z plane, a warp walks its row 32 nodes at a time (coalesced); grid (D, ceil(H/8)).
+// Eight loads per node, four of which hit the lines the neighbouring lane just fetched.  (A variant that loads every
+// value once and derives the x+1 neighbours from warp ballots measured SLOWER on B200 -- 100 us instead of 70 us at
+// 257^3: the kernel is instruction-bound, not load-bound; profiles/r01_final3_recon_trace_ballot_classify.txt.)
 constexpr int kClassRows = 8;
-constexpr int kClassGroup = 4;
 __global__ void __launch_bounds__(32 * kClassRows)
 classify_kernel(const float* __restrict__ vol, uint8_t* __restrict__ code, uint8_t* __restrict__ cases, int D, int H,
                 int W, float iso) {
   const int z = blockIdx.x, y = blockIdx.y * kClassRows + threadIdx.y;
-  if (y >= H) return;                    // (a whole warp: blockDim.x == 32)
-  const int lane = threadIdx.x;
+  if (y >= H) return;
   const bool yi = y + 1 < H, zi = z + 1 < D;
   const size_t row = ((size_t)z * H + y) * W;
   // neighbour rows; a missing neighbour aliases the row itself (its bits are masked by yi / zi below)
-  const float* r[4];
-  r[0] = vol + row;
-  r[1] = r[0] + (yi ? (size_t)W : 0);
-  r[2] = r[0] + (zi ? (size_t)H * W : 0);
-  r[3] = r[2] + (yi ? (size_t)W : 0);
-  // inside/outside ballots of chunk `xs` (lanes beyond the row re-read its last node: in bounds, never consumed)
-  unsigned m[kClassGroup + 1][4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) m[0][q] = __ballot_sync(0xffffffffu, __ldg(r[q] + min(lane, W - 1)) > iso);
-  for (int g0 = 0; g0 < W; g0 += 32 * kClassGroup) {
-    float v[kClassGroup][4];
-#pragma unroll
-    for (int c = 0; c < kClassGroup; ++c) {
-      const int xs = g0 + 32 * (c + 1);                       // warp-uniform
-      const int xl = min(xs + lane, W - 1);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) v[c][q] = (xs < W) ? __ldg(r[q] + xl) : 0.f;
+  const float* r00 = vol + row;
+  const float* r01 = r00 + (yi ? (size_t)W : 0);
+  const float* r10 = r00 + (zi ? (size_t)H * W : 0);
+  const float* r11 = r10 + (yi ? (size_t)W : 0);
+#pragma unroll 2
+  for (int x = threadIdx.x; x < W; x += 32) {
+    const bool xi = x + 1 < W;
+    const int x1 = xi ? x + 1 : x;
+    const bool b000 = __ldg(r00 + x) > iso, b001 = __ldg(r00 + x1) > iso;
+    const bool b010 = __ldg(r01 + x) > iso, b011 = __ldg(r01 + x1) > iso;
+    const bool b100 = __ldg(r10 + x) > iso, b101 = __ldg(r10 + x1) > iso;
+    const bool b110 = __ldg(r11 + x) > iso, b111 = __ldg(r11 + x1) > iso;
+    uint8_t c = 0;
+    if (xi && (b001 != b000)) c |= 1;
+    if (yi && (b010 != b000)) c |= 2;
+    if (zi && (b100 != b000)) c |= 4;
+    uint8_t cs = 0;
+    if (xi && yi && zi) {
+      int k = b000 ? 1 : 0;
+      k |= b001 ? 2 : 0;
+      k |= b010 ? 4 : 0;
+      k |= b011 ? 8 : 0;
+      k |= b100 ? 16 : 0;
+      k |= b101 ? 32 : 0;
+      k |= b110 ? 64 : 0;
+      k |= b111 ? 128 : 0;
+      cs = (uint8_t)k;
+      c |= (uint8_t)(c_mc_ntri[k] << 3);
     }
-#pragma unroll
-    for (int c = 0; c < kClassGroup; ++c)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) m[c + 1][q] = __ballot_sync(0xffffffffu, v[c][q] > iso);
-#pragma unroll
-    for (int c = 0; c < kClassGroup; ++c) {
-      const int x = g0 + 32 * c + lane;
-      if (x < W) {
-        const bool xi = x + 1 < W;
-        // corner (dz, dy, dx): row q = 2*dz + dy, bit lane + dx of that row's ballot
-        auto at = [&](int q, int dx) -> bool {
-          const int l = lane + dx;
-          return ((l < 32 ? (m[c][q] >> l) : m[c + 1][q]) & 1u) != 0u;
-        };
-        const bool b000 = at(0, 0), b001 = at(0, 1), b010 = at(1, 0), b011 = at(1, 1);
-        const bool b100 = at(2, 0), b101 = at(2, 1), b110 = at(3, 0), b111 = at(3, 1);
-        uint8_t cd = 0;
-        if (xi && (b001 != b000)) cd |= 1;
-        if (yi && (b010 != b000)) cd |= 2;
-        if (zi && (b100 != b000)) cd |= 4;
-        uint8_t cs = 0;
-        if (xi && yi && zi) {
-          int k = b000 ? 1 : 0;
-          k |= b001 ? 2 : 0;
-          k |= b010 ? 4 : 0;
-          k |= b011 ? 8 : 0;
-          k |= b100 ? 16 : 0;
-          k |= b101 ? 32 : 0;
-          k |= b110 ? 64 : 0;
-          k |= b111 ? 128 : 0;
-          cs = (uint8_t)k;
-          cd |= (uint8_t)(c_mc_ntri[k] << 3);
-        }
-        code[row + x] = cd;
-        cases[row + x] = cs;
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) m[0][q] = m[kClassGroup][q];
+    code[row + x] = c;
+    cases[row + x] = cs;
   }
 }
 
