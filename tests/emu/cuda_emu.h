@@ -97,6 +97,19 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
   return r;
 }
 
+// block-wide OR of a predicate (two barriers around a flag; a third before the flag is cleared for the next use)
+inline int __syncthreads_or(int pred) {
+  static int flag = 0;
+  pthread_barrier_wait(&cuda_emu::g_cta_barrier);
+  if (pred) __atomic_store_n(&flag, 1, __ATOMIC_SEQ_CST);
+  pthread_barrier_wait(&cuda_emu::g_cta_barrier);
+  const int r = __atomic_load_n(&flag, __ATOMIC_SEQ_CST);
+  pthread_barrier_wait(&cuda_emu::g_cta_barrier);
+  if (cuda_emu::linear_tid() == 0) __atomic_store_n(&flag, 0, __ATOMIC_SEQ_CST);
+  pthread_barrier_wait(&cuda_emu::g_cta_barrier);
+  return r;
+}
+
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcg(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
@@ -105,6 +118,9 @@ inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fsqrt_rn(float a) { return sqrtf(a); }
+inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

@@ -101,3 +101,73 @@ def _check_scan(exe, tmp_path, n, vec):
     if n:
         want = (np.cumsum(lo) - lo) + ((np.cumsum(hi) - hi) << np.uint64(32))
         assert np.array_equal(np.fromfile(fout, dtype=np.uint64), want)
+
+
+# ---- coarse-to-fine engine kernels (octree_kernels.cuh) against the restatement: volume AND evaluated node lists --------
+@pytest.fixture(scope="module")
+def emu_octree(tmp_path_factory):
+    return _build(str(tmp_path_factory.mktemp("emu_octree")), "emu_octree")
+
+
+def _run_octree(exe, tmp_path, mode, field, res, kpts=None):
+    fin, fvol, fidx = (str(tmp_path / n) for n in ("dense.f32", "vol.f32", "idx.i32"))
+    np.ascontiguousarray(field, dtype=np.float32).tofile(fin)
+    args = [exe, mode, "0.5", fin, fvol, fidx, str(len(res))] + [str(r) for r in res] + [str(k) for k in (kpts or [])]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr
+    out = [int(x) for x in r.stdout.split()]
+    vol = np.fromfile(fvol, dtype=np.float32)
+    return out[0], out[1:], vol, np.fromfile(fidx, dtype=np.int32)
+
+
+@pytest.mark.parametrize("mode,field_kind,res", [
+    ("faster", "sphere", [9, 17, 33, 65]), ("faster", "two_blobs", [5, 9, 17, 33, 65]), ("faster", "ellipsoid", [9, 17, 33]),
+    ("lossless", "sphere", [9, 17, 33]), ("lossless", "two_blobs", [9, 17, 33]),
+    ("topk", "sphere", [9, 17, 33]), ("topk", "ellipsoid", [9, 17, 33])])
+def test_octree_kernels_match_restatement(emu_octree, tmp_path, mode, field_kind, res):
+    import torch
+    from helpers import lookup_query
+    R = res[-1]
+    field = spec.analytic_volume(R, field_kind)
+    fn_o, _ = lookup_query(torch.from_numpy(field))
+    kpts = [0, 1500, 5000] if mode == "topk" else None
+    if mode == "topk":
+        want, stats = spec.seg3d_topk_ref(fn_o, res, kpts, return_stats=True)
+    else:
+        want, stats = spec.seg3d_lossless_ref(fn_o, res, faster=(mode == "faster"), return_stats=True)
+    nonempty, counts, vol, idx = _run_octree(emu_octree, tmp_path, mode, field, res, kpts)
+    assert nonempty == 1 and want is not None
+    assert counts == [int(s["idx"].numel()) for s in stats]
+    assert np.array_equal(vol.reshape(R, R, R), want.numpy()), "volume must be bit-identical to the restatement"
+    assert np.array_equal(idx, np.concatenate([s["idx"].numpy().astype(np.int32) for s in stats])), "node lists / order"
+
+
+def test_octree_kernels_empty_field(emu_octree, tmp_path):
+    nonempty, counts, vol, idx = _run_octree(emu_octree, tmp_path, "faster", np.zeros((33, 33, 33), np.float32), [9, 17, 33])
+    assert nonempty == 0 and counts[0] == 729 and sum(counts[1:]) == 0 and vol.size == 0
+
+
+# ---- visible-surface kernels (surface_kernels.cuh) against the goldens produced by the unmodified RTL/recon.py -------------
+@pytest.fixture(scope="module")
+def emu_surface(tmp_path_factory):
+    return _build(str(tmp_path_factory.mktemp("emu_surface")), "emu_surface")
+
+
+@pytest.mark.parametrize("golden", ["fv_sphere_33", "fv_two_blobs_65", "fv_ellipsoid_65"])
+def test_surface_kernels_match_reference_golden(emu_surface, tmp_path, golden_dir, golden):
+    g = np.load(os.path.join(golden_dir, golden + ".npz"))
+    R = int(g["R"])
+    fin, fout = str(tmp_path / "vol.f32"), str(tmp_path / "out.bin")
+    spec.analytic_volume(R, str(g["kind"])).tofile(fin)
+    for di, d in enumerate(("front", "back", "left", "right")):
+        r = subprocess.run([emu_surface, str(R), str(di), fin, fout], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        k = int(r.stdout)
+        raw = open(fout, "rb").read()
+        X = np.frombuffer(raw[:8 * k], dtype=np.int64)
+        Y = np.frombuffer(raw[8 * k:16 * k], dtype=np.int64)
+        Z = np.frombuffer(raw[16 * k:20 * k], dtype=np.float32)
+        N = np.frombuffer(raw[20 * k:32 * k], dtype=np.float32).reshape(-1, 3)
+        assert np.array_equal(X, g["X_" + d]) and np.array_equal(Y, g["Y_" + d])
+        np.testing.assert_allclose(Z, g["Z_" + d], rtol=0, atol=1e-5, equal_nan=True)
+        np.testing.assert_allclose(N, g["N_" + d], rtol=0, atol=1e-6, equal_nan=True)
