@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("MONOPORT_B200_MODE", "auto"), choices=["auto", "tc", "fp32"])
     ap.add_argument("--res", type=int, default=R_GRID)
+    ap.add_argument("--fused-gather", action="store_true", default=os.environ.get("MONOPORT_B200_FUSED_GATHER", "0") == "1",
+                    help="N>1: store the slab into every rank's volume from the kernel epilogue (peer memory) instead of "
+                         "the NCCL all-gather (experimental, opt-in)")
     ap.add_argument("--no-recon", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -209,7 +212,7 @@ def run_ours(args):
     import torch.distributed as dist
     from monoport_b200 import _lib
     from monoport_b200.modeling import PIFuNetG
-    from monoport_b200.shard import slab_bounds, gather_slabs
+    from monoport_b200.shard import slab_bounds, gather_slabs, PeerVolumes, query_grid_fused
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -243,6 +246,9 @@ def run_ours(args):
     slab = torch.empty((nz, R, R), dtype=torch.float32, device=dev)
     full = torch.empty((R, R, R), dtype=torch.float32, device=dev)
 
+    fused = bool(args.fused_gather and world > 1)
+    peers = PeerVolumes(R, rank, world, dev) if fused else None
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -250,6 +256,9 @@ def run_ours(args):
 
     def step(i):
         f = feats[i % len(feats)]
+        if fused:
+            query_grid_fused(net, f, cal, R, B_MIN, B_MAX, peers)
+            return
         net.query_grid(f, cal, R, B_MIN, B_MAX, z0=z0, nz=nz, out=slab)
         if world > 1:
             gather_slabs(slab, R, rank, world, out=full)
@@ -269,10 +278,14 @@ def run_ours(args):
         ev[i][0].record()
         fh = net.feature_handle(f)                 # channel-last repack kernel (part of the step)
         kev[i][0].record()
-        net.query_grid(f, cal, R, B_MIN, B_MAX, z0=z0, nz=nz, out=slab)
-        kev[i][1].record()
-        if world > 1:
-            gather_slabs(slab, R, rank, world, out=full)
+        if fused:
+            query_grid_fused(net, f, cal, R, B_MIN, B_MAX, peers)      # kernel with peer stores + barrier
+            kev[i][1].record()
+        else:
+            net.query_grid(f, cal, R, B_MIN, B_MAX, z0=z0, nz=nz, out=slab)
+            kev[i][1].record()
+            if world > 1:
+                gather_slabs(slab, R, rank, world, out=full)
         ev[i][1].record()
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -422,7 +435,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f16" if mode_used == "tc" else "f32", "data": "synthetic",
             "config": {"workload": "netG dense %d^3 grid query (%d points/step), [1,256,128,128] features, scene calib "
-                                   "yaw20/pitch33, z-slab sharded over %d GPU(s) + 1 all-gather" % (R, n_pts_total, world),
+                                   "yaw20/pitch33, z-slab sharded over %d GPU(s) + %s" % (R, n_pts_total, world, "peer-memory stores from the kernel epilogue + 1 barrier" if fused else "1 all-gather"),
                        "kernel_mode": mode_used, "l2_flush_between_steps": True, "grid": R,
                        "accumulate": "fp32", "last_layer": "fp32"},
             "e2e": {"value": e2e_value, "unit": "Mpoints/s", "h2d_bytes_per_step": 256 * 128 * 128 * 4 + 48,
@@ -447,6 +460,9 @@ def run_ours(args):
         if recon:
             line["recon"] = recon
         print(json.dumps(line))
+    if peers is not None:
+        barrier()
+        peers.close()
     if world > 1:
         dist.destroy_process_group()
 

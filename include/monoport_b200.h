@@ -20,6 +20,7 @@
 #ifndef MONOPORT_B200_H_
 #define MONOPORT_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -102,6 +103,22 @@ int mp_query_points_host(mp_mlp_t* mlp, mp_feat_t* feat, const float* feat_nchw_
  * across GPUs calls this with a different [z0,nz) per rank. */
 int mp_query_grid(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0, int nz, const float* b_min3, const float* b_max3,
                   const float* calib12, int projection, float z_scale, float* out_dev, int mode, void* stream);
+
+/* Fused slab exchange (instead of the all-gather): the slab [z0, z0+nz) is evaluated like mp_query_grid,
+ * but every value is stored straight into the FULL [R,R,R] volumes of all n_peers ranks (peer_vols: host array of
+ * device pointers, the caller's own volume included; peers' volumes are peer-memory mappings obtained through
+ * mp_ipc_open) while the tiles are computed -- compute and transfer in ONE kernel over NVLink.  The caller synchronises
+ * the ranks afterwards (any barrier ordered after this call on `stream`); with two alternating volume sets one barrier
+ * per frame suffices.  MP_MODE_TC / AUTO only (tensor-core program v3); n_peers <= 8. */
+int mp_query_grid_peers(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0, int nz, const float* b_min3, const float* b_max3,
+                        const float* calib12, int projection, float z_scale, float* const* peer_vols, int n_peers,
+                        int mode, void* stream);
+/* Exportable device memory for such volumes: cudaMalloc + the 64-byte cudaIpcMemHandle_t to hand to the other ranks
+ * (one process per GPU), which map it with mp_ipc_open (enables peer access) and unmap it with mp_ipc_close. */
+int mp_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+int mp_ipc_open(const unsigned char* handle64, void** dev_ptr);
+int mp_ipc_close(void* dev_ptr);
+int mp_ipc_free(void* dev_ptr);
 
 /* mp_query_grid with HOST buffers: uploads the NCHW fp32 feature map (NULL = reuse), evaluates the slab, copies
  * the [nz,R,R] result to out_host, synchronises.  bench.py's e2e leg. */

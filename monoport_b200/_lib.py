@@ -41,6 +41,12 @@ SIGNATURES = {
                                      c_void_p, c_int, c_void_p]),
     "mp_query_grid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, P(c_float), P(c_float), P(c_float), c_int,
                               c_float, c_void_p, c_int, c_void_p]),
+    "mp_query_grid_peers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, P(c_float), P(c_float), P(c_float), c_int,
+                                    c_float, P(c_void_p), c_int, c_int, c_void_p]),
+    "mp_ipc_alloc": (c_int, [ctypes.c_size_t, P(c_void_p), ctypes.c_char_p]),
+    "mp_ipc_open": (c_int, [ctypes.c_char_p, P(c_void_p)]),
+    "mp_ipc_close": (c_int, [c_void_p]),
+    "mp_ipc_free": (c_int, [c_void_p]),
     "mp_query_grid_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, P(c_float), P(c_float), P(c_float),
                                    c_int, c_float, c_void_p, c_int, c_void_p]),
     "mp_octree_create": (c_int, [c_int, P(c_int), P(c_float), P(c_float), c_float, c_int, P(c_int), P(c_void_p)]),

@@ -303,6 +303,73 @@ extern "C" int mp_query_grid(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0, int 
   return mp_query_dispatch(mlp, feat, src, cal, dst, mode, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused slab exchange (multi-GPU z-slab sharding without a data collective)
+// ---------------------------------------------------------------------------------------------
+extern "C" int mp_query_grid_peers(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0, int nz, const float* b_min3,
+                                   const float* b_max3, const float* calib12, int projection, float z_scale,
+                                   float* const* peer_vols, int n_peers, int mode, void* stream) {
+  MP_REQUIRE(mlp && feat, "NULL handle");
+  MP_REQUIRE(R >= 1 && z0 >= 0 && nz >= 0 && z0 + nz <= R, "bad slab R=%d z0=%d nz=%d", R, z0, nz);
+  MP_REQUIRE(b_min3 && b_max3, "NULL bounds");
+  MP_REQUIRE(mlp->cout[mlp->n_layers - 1] == 1, "mp_query_grid_peers needs a single-channel head");
+  MP_REQUIRE(peer_vols && n_peers >= 1 && n_peers <= MP_MAX_PEERS, "n_peers=%d out of range [1,%d]", n_peers, MP_MAX_PEERS);
+  for (int p = 0; p < n_peers; ++p) MP_REQUIRE(peer_vols[p] != nullptr, "peer volume %d is NULL", p);
+  if (nz == 0) return MP_OK;
+  MpPointSrc src;
+  memset(&src, 0, sizeof(src));
+  src.kind = MP_SRC_GRID;
+  mp_fill_grid_geom(src, R, 1, R, b_min3, b_max3);
+  src.z0 = z0;
+  src.n = (long long)nz * R * R;
+  MpCalib cal;
+  mp_fill_calib(cal, calib12, projection, z_scale);
+  MpOutDst dst;
+  dst.out = nullptr; dst.ld = src.n; dst.scatter_vol = nullptr;
+  for (int p = 0; p < n_peers; ++p) dst.peer[p] = peer_vols[p];
+  dst.n_peers = n_peers;
+  dst.peer_off = (long long)z0 * R * R;        // the slab's position inside every full [R,R,R] volume
+  return mp_query_dispatch(mlp, feat, src, cal, dst, mode, (cudaStream_t)stream);
+}
+
+// Volumes that other processes of the node write into: plain cudaMalloc blocks (exportable; the caching allocators of
+// frameworks hand out sub-blocks, which legacy IPC handles cannot describe) + their 64-byte IPC handle.
+extern "C" int mp_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64) {
+  MP_REQUIRE(dev_ptr && handle64 && bytes > 0, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  *dev_ptr = nullptr;
+  MP_CUDA(cudaMalloc(dev_ptr, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *dev_ptr);
+  if (e != cudaSuccess) {
+    cudaFree(*dev_ptr);
+    *dev_ptr = nullptr;
+    mp_set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    return MP_E_CUDA;
+  }
+  memcpy(handle64, &h, 64);
+  return MP_OK;
+}
+
+extern "C" int mp_ipc_open(const unsigned char* handle64, void** dev_ptr) {
+  MP_REQUIRE(dev_ptr && handle64, "bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  *dev_ptr = nullptr;
+  MP_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return MP_OK;
+}
+
+extern "C" int mp_ipc_close(void* dev_ptr) {
+  if (dev_ptr) MP_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return MP_OK;
+}
+
+extern "C" int mp_ipc_free(void* dev_ptr) {
+  if (dev_ptr) MP_CUDA(cudaFree(dev_ptr));
+  return MP_OK;
+}
+
 extern "C" int mp_query_grid_host(mp_mlp_t* mlp, mp_feat_t* feat, const float* feat_nchw_host, int R, int z0, int nz,
                                   const float* b_min3, const float* b_max3, const float* calib12, int projection,
                                   float z_scale, float* out_host, int mode, void* stream) {

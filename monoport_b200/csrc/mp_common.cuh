@@ -104,10 +104,17 @@ struct MpCalib {
 };
 
 // where results go
+#define MP_MAX_PEERS 8
 struct MpOutDst {
   float* out;          // MP_SRC_ROWS/GRID: [Res][ld]; value of point i, channel c at out[c*ld + i]
   long long ld;
   float* scatter_vol;  // if non-null: channel 0 is ALSO scattered to scatter_vol[nodes[i]]
+  // fused slab exchange of the z-sharded grid query (mp_query_grid_peers): channel 0 of point i is ALSO stored at
+  // peer[p][peer_off + i] for p < n_peers -- peer-memory pointers (NVLink P2P) to the full volumes of every rank, the
+  // own one included -- so the volume is assembled on every GPU while the tiles are computed, without a collective.
+  float* peer[MP_MAX_PEERS] = {};
+  long long peer_off = 0;
+  int n_peers = 0;
 };
 
 // ---------------------------------------------------------------------------------------------

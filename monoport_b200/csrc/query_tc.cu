@@ -809,7 +809,9 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
 // TMEM map: acc1 [0,512)  --drain in place-->  H1lo [0,128) | acc2 [128,384) | H1hi [384,512)
 //           --drain-->  H2 [0,128) | (free) | acc3 [384,512)
 // roofline.achieved keeps counting the ALGORITHMIC 2 363 906 FLOP/point; the hoisted layer is not executed per point.
-template <int CG>
+// PEERS: also store channel 0 into the peer volumes of dst (fused slab exchange; the default instantiation carries no
+// trace of it).
+template <int CG, bool PEERS = false>
 __global__ void __launch_bounds__(kThreads, 1)
 query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
   using C = Cfg<CG>;
@@ -1347,6 +1349,13 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
               const float val = inimg * mp_last_op(logit[r], prm.last_op);
               if (dst.out) dst.out[(long long)r * dst.ld + i] = val;
               if (dst.scatter_vol && r == 0) dst.scatter_vol[__ldg(src.nodes + i)] = val;
+              if constexpr (PEERS) {
+                if (r == 0) {
+#pragma unroll
+                  for (int p = 0; p < MP_MAX_PEERS; ++p)
+                    if (p < dst.n_peers) dst.peer[p][dst.peer_off + i] = val;      // 128 B per warp and peer over NVLink
+                }
+              }
             }
           }
         }
@@ -1706,6 +1715,7 @@ int mp_tc_prepare(mp_mlp* mlp) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(g0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG0Smem);
   if (e != cudaSuccess) {
     mp_set_error("mp_tc_prepare: cannot opt in to %d bytes of shared memory: %s", Smem::Total + 1024, cudaGetErrorString(e));
@@ -1843,6 +1853,18 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     prm.wstream2[1] = pk->w3stream2[1];
   }
   const int cg = forced == 2 ? 2 : (forced == 1 ? 1 : 1);
+  if (dst.n_peers > 0) {
+    // fused slab exchange: only the default program (v3, one CTA per tile) carries the peer stores
+    if (ver != 3 || cg != 1 || dst.n_peers > MP_MAX_PEERS) {
+      mp_set_error("peer stores need tensor-core program v3 / cta_group::1 and at most %d peers", MP_MAX_PEERS);
+      return MP_E_UNSUPPORTED;
+    }
+    const int grid = (int)(tiles < (long long)sms ? tiles : sms);
+    query_tc3_kernel<1, true><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
+    MP_CUDA(cudaGetLastError());
+    report(grid);
+    return MP_OK;
+  }
   if (cg == 1) {
     const int grid = (int)(tiles < (long long)sms ? tiles : sms);
     if (ver == 3) query_tc3_kernel<1><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);

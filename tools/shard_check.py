@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import torch, torch.distributed as dist
 from oracle import spec
 from helpers import build_net
-from monoport_b200.shard import query_grid_sharded
+from monoport_b200.shard import query_grid_sharded, query_grid_fused, PeerVolumes
 from monoport_b200.recon import marching_cubes
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -27,4 +27,23 @@ dist.all_gather(lst, t)
 if rank == 0:
     assert all(bool(x[2]) for x in lst) and all(torch.equal(x, lst[0]) for x in lst), lst
     print("shard_check OK: identical volumes and mesh topology on all %d ranks" % world)
+# fused slab exchange (peer-memory stores from the kernel epilogue instead of the all-gather): same volume, bit for bit,
+# over several frames (alternating volume sets, changing features)
+if "--fused" in sys.argv:
+    peers = PeerVolumes(R, rank, world, "cuda:%d" % local)
+    okf = True
+    for it in range(6):
+        f_it = (feat * (1.0 + 0.05 * it)).cuda()
+        vol = query_grid_fused(net, f_it, cal, R, (-1, -1, -1), (1, 1, 1), peers)
+        ref = net.query_grid(f_it, cal, R, (-1, -1, -1), (1, 1, 1))
+        okf &= bool(torch.equal(vol, ref))
+    torch.cuda.synchronize()
+    t = torch.tensor([int(okf)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    print("rank %d/%d: fused == single over 6 frames: %s" % (rank, world, okf), flush=True)
+    if rank == 0:
+        assert int(t.item()) == 1
+        print("shard_check OK (fused slab exchange)")
+    dist.barrier()
+    peers.close()
 dist.destroy_process_group()
