@@ -18,6 +18,9 @@ def _gpus():
 
 @pytest.mark.parametrize("fused", [False, True])
 def test_sharded_volume_equals_single_gpu_volume(fused):
+    if fused and os.environ.get("MONOPORT_B200_TEST_FUSED", "0") != "1":
+        pytest.skip("fused slab exchange is opt-in until it has been validated on a multi-GPU box "
+                    "(MONOPORT_B200_TEST_FUSED=1)")
     n = _gpus()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
