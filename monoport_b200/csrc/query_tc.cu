@@ -636,13 +636,13 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       }
       tc::fence_proxy_async_smem();
       // make s_zf/s_in/s_s4 visible to the epilogue role of all worker threads
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      tc::bar_sync_workers256();
       const float zf = s_zf[row];
       const float inimg = s_in[row];
       float s4[kMaxRes];
 #pragma unroll
       for (int r = 0; r < kMaxRes; ++r) s4[r] = (r < res) ? s_s4[r * kTile + row] : 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");      // everyone has read the per-point scalars
+      tc::bar_sync_workers256();      // everyone has read the per-point scalars
       warp_arrive_leader<CG>(bars + B_XREADY, lane);
       if (prof) prof[P_W_SAMPLE] += (unsigned long long)(clock64() - t_sample0);
 
@@ -1838,7 +1838,11 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
       feat->g0_owner = nullptr;
     }
     if (feat->g0_owner != (const void*)mlp || feat->g0_version != feat->version) {
+#ifndef MP_CUDA_EMU
       g0_tc_kernel<<<(unsigned)((HW + 127) / 128), kG0Threads, kG0Smem, st>>>(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s, pk->res);
+#else
+      MP_EMU_LAUNCH((unsigned)((HW + 127) / 128), kG0Threads, g0_tc_kernel(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s, pk->res));
+#endif
       MP_CUDA(cudaGetLastError());
       feat->g0_owner = (const void*)mlp;
       feat->g0_version = feat->version;
@@ -1860,19 +1864,32 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
       return MP_E_UNSUPPORTED;
     }
     const int grid = (int)(tiles < (long long)sms ? tiles : sms);
+#ifndef MP_CUDA_EMU
     query_tc3_kernel<1, true><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
+#else
+    MP_EMU_LAUNCH(grid, kThreads, (query_tc3_kernel<1, true>(prm, src, cal, dst)));
+#endif
     MP_CUDA(cudaGetLastError());
     report(grid);
     return MP_OK;
   }
   if (cg == 1) {
     const int grid = (int)(tiles < (long long)sms ? tiles : sms);
+#ifndef MP_CUDA_EMU
     if (ver == 3) query_tc3_kernel<1><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
     else query_tc_kernel<1><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
+#else
+    if (ver == 3) MP_EMU_LAUNCH(grid, kThreads, query_tc3_kernel<1>(prm, src, cal, dst));
+    else MP_EMU_LAUNCH(grid, kThreads, query_tc_kernel<1>(prm, src, cal, dst));
+#endif
     MP_CUDA(cudaGetLastError());
     report(grid);
     return MP_OK;
   }
+#ifdef MP_CUDA_EMU
+  mp_set_error("cta_group::2 is not modelled by the CPU emulation");
+  return MP_E_UNSUPPORTED;
+#else
   const long long groups = (tiles + 1) / 2;
   const long long max_clusters = sms / 2;
   const int clusters = (int)(groups < max_clusters ? groups : max_clusters);
@@ -1893,4 +1910,5 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
   else MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc_kernel<2>, prm, src, cal, dst));
   report(2 * clusters);
   return MP_OK;
+#endif
 }

@@ -5,6 +5,11 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#ifdef MP_CUDA_EMU
+// tests/emu: a functional CPU model of this layer (same names, same argument meaning) -- test infrastructure only
+#include "tc_ptx_emu.h"
+#else
+
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -55,6 +60,9 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+
+// named barrier 1 over the 256 worker threads of the v2 program (warps 4-11)
+__device__ __forceinline__ void bar_sync_workers256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -226,3 +234,5 @@ __device__ __forceinline__ void mma_commit2(uint64_t* bar) {
 }
 
 }  // namespace tc
+
+#endif  // MP_CUDA_EMU
