@@ -19,12 +19,24 @@
 
 #define MP_CUDA_EMU 1
 
+#ifdef MP_EMU_CUDA_TYPES
+// the including file has already pulled in the real <cuda_runtime.h> / <cuda_fp16.h> (host side): use their vector types
+typedef uint3 uint3_emu;
+#undef __global__
+#undef __device__
+#undef __host__
+#undef __forceinline__
+#undef __launch_bounds__
+#undef __shared__
+#undef __constant__
+#else
 struct uint3_emu { unsigned x, y, z; };
 struct dim3 {
   unsigned x, y, z;
   dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 struct uint2 { unsigned x, y; };
+#endif
 
 inline thread_local uint3_emu threadIdx, blockIdx;
 inline thread_local dim3 blockDim, gridDim;
@@ -34,7 +46,11 @@ inline thread_local dim3 blockDim, gridDim;
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#ifdef MP_EMU_EXTERN_SHARED
+#define __shared__            /* `extern __shared__ T x[]` = an array the harness defines */
+#else
 #define __shared__ static
+#endif
 #define __constant__
 
 namespace cuda_emu {
@@ -87,6 +103,24 @@ inline unsigned long long __shfl_up_sync(unsigned, unsigned long long v, int del
   return r;
 }
 
+// warp shuffles of 4- and 8-byte values (all 32 lanes take part, like every use in the kernels)
+template <class T>
+inline T emu_warp_exchange(T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle operand");
+  const int tid = cuda_emu::linear_tid(), w0 = tid & ~31;
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  cuda_emu::g_shfl[tid] = bits;
+  pthread_barrier_wait(&cuda_emu::g_warp_barrier[tid >> 5]);
+  const unsigned long long got = cuda_emu::g_shfl[w0 + (src_lane & 31)];
+  pthread_barrier_wait(&cuda_emu::g_warp_barrier[tid >> 5]);
+  T r;
+  memcpy(&r, &got, sizeof(T));
+  return r;
+}
+template <class T> inline T __shfl_sync(unsigned, T v, int src_lane) { return emu_warp_exchange(v, src_lane); }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return emu_warp_exchange(v, (cuda_emu::linear_tid() & 31) ^ lane_mask); }
+
 inline unsigned __ballot_sync(unsigned, bool pred) {
   const int tid = cuda_emu::linear_tid(), w0 = tid & ~31;
   cuda_emu::g_shfl[tid] = pred ? 1ull : 0ull;
@@ -126,3 +160,4 @@ inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 template <class T> inline T min(T a, T b) { return a < b ? a : b; }
 template <class T> inline T max(T a, T b) { return a > b ? a : b; }
+inline long long clock64() { return 0; }

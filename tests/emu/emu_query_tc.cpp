@@ -1,0 +1,154 @@
+// TEST INFRASTRUCTURE ONLY: monoport_b200/csrc/query_tc.cu -- host-side weight packing, launch logic, the per-frame G0
+// GEMM kernel and the fused tcgen05 sample+MLP kernels -- compiled UNMODIFIED for the CPU against the execution-model
+// emulation (cuda_emu.h) and the functional model of the tcgen05 / mbarrier / bulk-copy layer (tc_ptx_emu.h).
+//   emu_query_tc in.bin out.f32 program sms
+// in.bin: int32 header {C, H, W, N, has_calib, perspective, res, last_op}, float z_scale, calib[12], then fp32 arrays:
+//   feature map NCHW [C*H*W], points [3*N], for each of the 5 layers W_l [cout*cin] and b_l [cout].
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdarg.h>
+
+#define MP_EMU_CUDA_TYPES 1
+#define MP_EMU_EXTERN_SHARED 1
+#include "cuda_emu.h"
+
+// ---- device intrinsics the real headers only provide to nvcc -----------------------------------------------------------
+static inline __half2 __hfma2(__half2 a, __half2 b, __half2 c) {
+  _Float16 av[2], bv[2], cv[2], rv[2];
+  memcpy(av, &a, 4); memcpy(bv, &b, 4); memcpy(cv, &c, 4);
+  for (int i = 0; i < 2; ++i) rv[i] = (_Float16)((double)av[i] * (double)bv[i] + (double)cv[i]);   // one rounding
+  __half2 r;
+  memcpy(&r, rv, 4);
+  return r;
+}
+static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+
+// ---- the dynamic shared memory of the kernels (they run one at a time) -------------------------------------------------
+// (the kernels live in query_tc.cu's anonymous namespace, so their `extern __shared__` arrays resolve there)
+namespace {
+alignas(1024) uint8_t smem_raw[240 * 1024];
+extern uint8_t g0_smem_raw[] __attribute__((alias("_ZN12_GLOBAL__N_18smem_rawE")));
+}  // namespace
+
+// ---- a host-memory stand-in for the few CUDA runtime calls of the launcher ----------------------------------------------
+static int g_fake_sms = 148;
+extern "C" {
+cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
+  if (a == cudaDevAttrComputeCapabilityMajor) *v = 10;
+  else if (a == cudaDevAttrMaxSharedMemoryPerBlockOptin) *v = 232448;
+  else if (a == cudaDevAttrMultiProcessorCount) *v = g_fake_sms;
+  else *v = 0;
+  return cudaSuccess;
+}
+cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+}
+
+#define MP_EMU_LAUNCH(grid, block, call) cuda_emu::launch(dim3((unsigned)(grid)), dim3((unsigned)(block)), [&] { call; })
+
+static char g_err[512];
+void mp_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+template <class T> static cudaError_t cudaFuncSetAttribute(T*, cudaFuncAttribute, int) { return cudaSuccess; }
+
+#include "../../monoport_b200/csrc/query_tc.cu"
+
+int mp_launch_query_fp32(const mp_mlp*, const mp_feat*, const MpPointSrc&, const MpCalib&, const MpOutDst&, cudaStream_t) { return MP_E_UNSUPPORTED; }
+
+int main(int argc, char** argv) {
+  if (argc != 5) { fprintf(stderr, "usage: emu_query_tc in.bin out.f32 program sms\n"); return 2; }
+  const int program = atoi(argv[3]);
+  g_fake_sms = atoi(argv[4]);
+  FILE* f = fopen(argv[1], "rb");
+  if (!f) { perror(argv[1]); return 2; }
+  int32_t hd[8];
+  float zs, calib[12];
+  if (fread(hd, 4, 8, f) != 8 || fread(&zs, 4, 1, f) != 1 || fread(calib, 4, 12, f) != 12) { fprintf(stderr, "short header\n"); return 2; }
+  const int C = hd[0], H = hd[1], W = hd[2], N = hd[3], has_calib = hd[4], persp = hd[5], res = hd[6], last_op = hd[7];
+  auto rd = [&](size_t n) { std::vector<float> v(n); if (fread(v.data(), 4, n, f) != n) { fprintf(stderr, "short file\n"); exit(2); } return v; };
+  std::vector<float> nchw = rd((size_t)C * H * W), pts = rd((size_t)3 * N);
+  const int chans[6] = {C + 1, 1024, 512, 256, 128, res};
+  mp_mlp mlp;
+  memset(&mlp, 0, sizeof(mlp));
+  mlp.n_layers = 5; mlp.skip = 1; mlp.last_op = last_op;
+  std::vector<std::vector<float>> Ws(5), Bs(5);
+  for (int l = 0; l <= 5; ++l) mlp.channels[l] = chans[l];
+  for (int l = 0; l < 5; ++l) {
+    mlp.cin[l] = chans[l] + (l ? chans[0] : 0);
+    mlp.cout[l] = chans[l + 1];
+    Ws[l] = rd((size_t)mlp.cin[l] * mlp.cout[l]);
+    Bs[l] = rd(mlp.cout[l]);
+    mlp.w[l] = Ws[l].data();
+    mlp.bias[l] = Bs[l].data();
+  }
+  fclose(f);
+  tc::emu::set_smem(smem_raw, sizeof(smem_raw));
+  if (mp_tc_prepare(&mlp) != MP_OK || !mlp.tc_ok) { fprintf(stderr, "mp_tc_prepare: %s (tc_ok=%d)\n", g_err, mlp.tc_ok); return 3; }
+  if (getenv("EMU_TC_DEBUG")) {
+    const TcPack* pk = static_cast<const TcPack*>(mlp.tc);
+    fprintf(stderr, "d_bias0[0..3] = %g %g %g %g   d_wz0[0..1] = %g %g  h_bias[0]=%g\n", __half2float(pk->d_bias0[0]), __half2float(pk->d_bias0[1]),
+            __half2float(pk->d_bias0[2]), __half2float(pk->d_bias0[3]), __half2float(pk->d_wz0[0]), __half2float(pk->d_wz0[1]), pk->h_bias[0]);
+  }
+  // feature handle: channel-last copy (what nchw_to_nhwc_kernel produces)
+  std::vector<float> nhwc((size_t)C * H * W);
+  for (int c = 0; c < C; ++c)
+    for (int p = 0; p < H * W; ++p) nhwc[(size_t)p * C + c] = nchw[(size_t)c * H * W + p];
+  mp_feat feat;
+  memset(&feat, 0, sizeof(feat));
+  feat.C = C; feat.H = H; feat.W = W; feat.nhwc32 = nhwc.data(); feat.version = 1;
+  MpPointSrc src;
+  memset(&src, 0, sizeof(src));
+  src.kind = MP_SRC_ROWS;
+  src.px = pts.data(); src.py = pts.data() + N; src.pz = pts.data() + 2 * (size_t)N;
+  src.pstride = 1;
+  src.n = N;
+  MpCalib cal;
+  memset(&cal, 0, sizeof(cal));
+  cal.has = has_calib;
+  memcpy(cal.m, calib, sizeof(calib));
+  cal.perspective = persp && has_calib;
+  cal.z_scale = zs;
+  std::vector<float> out((size_t)res * N + 1, -4242.f);
+  MpOutDst dst;
+  dst.out = out.data(); dst.ld = N; dst.scatter_vol = nullptr;
+  // program 1xx: tensor-core program xx with the fused slab exchange -- three "peer volumes" (host buffers here)
+  const int n_peers = program >= 100 ? 3 : 0, peer_off = 5;
+  std::vector<std::vector<float>> peer(n_peers, std::vector<float>((size_t)N + 2 * peer_off, -4242.f));
+  for (int p = 0; p < n_peers; ++p) dst.peer[p] = peer[p].data();
+  dst.n_peers = n_peers;
+  dst.peer_off = peer_off;
+  const int rc = mp_launch_query_tc(&mlp, &feat, src, cal, dst, nullptr, program % 100);
+  if (rc != MP_OK) { fprintf(stderr, "mp_launch_query_tc: %s\n", g_err); return 3; }
+  if (out[(size_t)res * N] != -4242.f) { fprintf(stderr, "wrote past the output\n"); return 3; }
+  for (int p = 0; p < n_peers; ++p)
+    for (long long i = 0; i < (long long)peer[p].size(); ++i) {
+      const float want = (i >= peer_off && i < peer_off + N) ? out[i - peer_off] : -4242.f;
+      if (memcmp(&peer[p][i], &want, 4) != 0) { fprintf(stderr, "peer volume %d differs at %lld\n", p, i); return 3; }
+    }
+  f = fopen(argv[2], "wb");
+  fwrite(out.data(), 4, (size_t)res * N, f);
+  fclose(f);
+  if (const char* dump = getenv("EMU_TC_DUMP")) {       // per-texel products of the G0 kernel, for debugging the model
+    if (feat.g0) {
+      f = fopen(dump, "wb");
+      fwrite(feat.g0, 2, (size_t)H * W * 1024, f);
+      fwrite(feat.f16, 2, (size_t)H * W * C, f);
+      fwrite(feat.s4tex, 4, (size_t)H * W, f);
+      fclose(f);
+    }
+  }
+  mp_tc_release(&mlp);
+  return 0;
+}

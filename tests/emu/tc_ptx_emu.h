@@ -1,0 +1,323 @@
+// TEST INFRASTRUCTURE ONLY -- functional CPU model of monoport_b200/csrc/tc_ptx.cuh (included by it under MP_CUDA_EMU):
+// mbarriers with transaction counts, bulk async copies, tensor memory, tcgen05.mma (.kind::f16, cta_group::1, operands
+// from SWIZZLE_128B K-major shared-memory descriptors or packed fp16 in tensor memory), tcgen05.commit, tcgen05.ld/st.
+//
+// Asynchrony is modelled adversarially: a bulk copy or an MMA is only QUEUED when it is issued; queued operations are
+// executed (copies first, then MMAs / commits in issue order) when some thread is blocked in an mbarrier wait.  So
+//   * reading an accumulator without waiting for the commit barrier sees stale tensor memory,
+//   * overwriting a shared-memory operand (or a weight stage) before the MMA that reads it has been waited for makes
+//     that MMA consume the new bytes,
+// both of which show up as wrong results, and a broken hand-off protocol shows up as a reported deadlock (all threads
+// waiting, nothing queued) instead of a hang.  Timing, bank conflicts and memory-model subtleties are NOT modelled.
+#pragma once
+#include <chrono>
+#include <deque>
+#include <mutex>
+
+namespace tc {
+
+namespace emu {
+constexpr uint32_t kLanes = 128, kCols = 512;
+struct Op {
+  enum Kind { COPY, MMA_SS, MMA_TS, COMMIT } kind;
+  // COPY
+  uint8_t* dst; const uint8_t* src; uint32_t bytes; uint64_t* bar;
+  // MMA
+  uint32_t d_tmem, a_tmem, idesc, accumulate;
+  uint64_t a_desc, b_desc;
+};
+inline std::mutex g_mu;
+inline std::deque<Op> g_copies, g_mmas;
+inline uint32_t g_tmem[kLanes][kCols];
+inline uint8_t* g_smem = nullptr;          // base of the dynamic shared memory of the running kernel (1024-B aligned)
+inline uint32_t g_smem_bytes = 0;
+inline std::atomic<unsigned long long> g_events{0};   // bumped by every state change (deadlock watchdog)
+inline std::atomic<int> g_waiting{0};
+inline bool eager() { static const bool e = getenv("EMU_TC_EAGER") != nullptr; return e; }   // debugging aid: no deferral
+
+inline void set_smem(void* base, uint32_t bytes) {
+  if ((uintptr_t)base & 1023) { fprintf(stderr, "tc emu: shared memory base must be 1024-byte aligned\n"); abort(); }
+  g_smem = (uint8_t*)base;
+  g_smem_bytes = bytes;
+  g_copies.clear();
+  g_mmas.clear();
+  memset(g_tmem, 0xCD, sizeof(g_tmem));      // poison: uninitialised accumulators are visible
+}
+
+// ---- mbarrier word: [0,20) pending arrivals | [20,40) arrival count of a phase | [40,62) pending tx bytes | 63 phase
+inline uint32_t mb_pending(uint64_t w) { return (uint32_t)(w & 0xFFFFF); }
+inline uint32_t mb_count(uint64_t w) { return (uint32_t)((w >> 20) & 0xFFFFF); }
+inline uint32_t mb_tx(uint64_t w) { return (uint32_t)((w >> 40) & 0x3FFFFF); }
+inline uint32_t mb_phase(uint64_t w) { return (uint32_t)(w >> 63); }
+inline uint64_t mb_make(uint32_t pending, uint32_t count, uint32_t tx, uint32_t phase) {
+  return (uint64_t)pending | ((uint64_t)count << 20) | ((uint64_t)tx << 40) | ((uint64_t)phase << 63);
+}
+inline void mb_check_complete(uint64_t* bar) {
+  const uint64_t w = *bar;
+  if (mb_pending(w) == 0 && mb_tx(w) == 0) *bar = mb_make(mb_count(w), mb_count(w), 0, mb_phase(w) ^ 1u);
+  g_events++;
+}
+inline void mb_arrive_locked(uint64_t* bar) {
+  const uint64_t w = *bar;
+  if (mb_pending(w) == 0) { fprintf(stderr, "tc emu: arrival on a barrier with no pending arrivals (over-arrival)\n"); abort(); }
+  *bar = mb_make(mb_pending(w) - 1, mb_count(w), mb_tx(w), mb_phase(w));
+  mb_check_complete(bar);
+}
+
+inline float h2f(uint16_t h) { __half x; memcpy(&x, &h, 2); return __half2float(x); }
+inline uint32_t swz(uint32_t a) { return a ^ (((a >> 7) & 7u) << 4); }       // SWIZZLE_128B on the shared-memory address
+inline uint16_t smem_half(uint32_t addr) {
+  const uint32_t p = swz(addr);
+  if (p + 2 > g_smem_bytes) { fprintf(stderr, "tc emu: MMA operand address %u outside shared memory\n", p); abort(); }
+  uint16_t h;
+  memcpy(&h, g_smem + p, 2);
+  return h;
+}
+
+// D[128 x N] (+)= A[128 x 16] * B[N x 16]^T, fp16 operands, fp32 accumulation
+inline void exec_mma(const Op& op) {
+  const uint32_t M = ((op.idesc >> 24) & 0x1F) << 4, N = ((op.idesc >> 17) & 0x3F) << 3;
+  if (M != 128 || N == 0 || N > 256 || (N & 15)) { fprintf(stderr, "tc emu: unsupported MMA shape %ux%u\n", M, N); abort(); }
+  if (((op.idesc >> 4) & 3) != 1 || ((op.idesc >> 7) & 7) != 0 || ((op.idesc >> 10) & 7) != 0) { fprintf(stderr, "tc emu: idesc formats\n"); abort(); }
+  const uint32_t dcol = op.d_tmem & 0xFFFF;
+  if ((op.d_tmem >> 16) != 0 || dcol + N > kCols) { fprintf(stderr, "tc emu: bad accumulator address %08x (N=%u)\n", op.d_tmem, N); abort(); }
+  auto desc_fields = [](uint64_t d, uint32_t& start, uint32_t& sbo) {
+    start = (uint32_t)(d & 0x3FFF) << 4;
+    sbo = (uint32_t)((d >> 32) & 0x3FFF) << 4;
+    if (((d >> 61) & 7) != 2) { fprintf(stderr, "tc emu: only SWIZZLE_128B descriptors are modelled\n"); abort(); }
+  };
+  static thread_local float A[128][16], B[256][16];
+  if (op.kind == Op::MMA_SS) {
+    uint32_t st, sbo;
+    desc_fields(op.a_desc, st, sbo);
+    for (uint32_t m = 0; m < 128; ++m)
+      for (uint32_t k = 0; k < 16; ++k) A[m][k] = h2f(smem_half(st + (m >> 3) * sbo + (m & 7) * 128 + k * 2));
+  } else {
+    const uint32_t acol = op.a_tmem & 0xFFFF;
+    if ((op.a_tmem >> 16) != 0 || acol + 8 > kCols) { fprintf(stderr, "tc emu: bad A tensor-memory address\n"); abort(); }
+    for (uint32_t m = 0; m < 128; ++m)
+      for (uint32_t k = 0; k < 16; ++k) {
+        const uint32_t w = g_tmem[m][acol + (k >> 1)];
+        A[m][k] = h2f((uint16_t)((k & 1) ? (w >> 16) : (w & 0xFFFF)));
+      }
+  }
+  {
+    uint32_t st, sbo;
+    desc_fields(op.b_desc, st, sbo);
+    for (uint32_t n = 0; n < N; ++n)
+      for (uint32_t k = 0; k < 16; ++k) B[n][k] = h2f(smem_half(st + (n >> 3) * sbo + (n & 7) * 128 + k * 2));
+  }
+  {
+    static const int trace_n = getenv("EMU_TC_TRACE_MMA") ? atoi(getenv("EMU_TC_TRACE_MMA")) : 0;
+    static int seen = 0;
+    if (seen < trace_n) {
+      float amin = 1e30f, amax = -1e30f;
+      for (uint32_t m = 0; m < 128; ++m) for (uint32_t k = 0; k < 16; ++k) { amin = fminf(amin, A[m][k]); amax = fmaxf(amax, A[m][k]); }
+      fprintf(stderr, "[mma %3d] %s dcol=%3u N=%3u acc=%u  A[0][0..3]=%g %g %g %g  A range [%g, %g]  B[0][0..1]=%g %g\n", seen,
+              op.kind == Op::MMA_SS ? "SS" : "TS", dcol, N, op.accumulate, A[0][0], A[0][1], A[0][2], A[0][3], amin, amax, B[0][0], B[0][1]);
+      ++seen;
+    }
+  }
+  for (uint32_t m = 0; m < 128; ++m)
+    for (uint32_t n = 0; n < N; ++n) {
+      float acc = 0.f;
+      for (uint32_t k = 0; k < 16; ++k) acc += A[m][k] * B[n][k];
+      float d = 0.f;
+      if (op.accumulate) memcpy(&d, &g_tmem[m][dcol + n], 4);
+      d += acc;
+      memcpy(&g_tmem[m][dcol + n], &d, 4);
+    }
+}
+
+// executes ONE queued asynchronous operation; returns false when nothing is queued.  Caller holds g_mu.
+inline bool progress_locked() {
+  if (!g_copies.empty()) {
+    const Op op = g_copies.front();
+    g_copies.pop_front();
+    memcpy(op.dst, op.src, op.bytes);
+    const uint64_t w = *op.bar;
+    if (mb_tx(w) < op.bytes) { fprintf(stderr, "tc emu: complete_tx without a matching expect_tx\n"); abort(); }
+    *op.bar = mb_make(mb_pending(w), mb_count(w), mb_tx(w) - op.bytes, mb_phase(w));
+    mb_check_complete(op.bar);
+    return true;
+  }
+  if (!g_mmas.empty()) {
+    const Op op = g_mmas.front();
+    g_mmas.pop_front();
+    if (op.kind == Op::COMMIT) mb_arrive_locked(op.bar);
+    else exec_mma(op);
+    g_events++;
+    return true;
+  }
+  return false;
+}
+}  // namespace emu
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  const uintptr_t off = (uintptr_t)p - (uintptr_t)emu::g_smem;
+  if (off >= emu::g_smem_bytes) { fprintf(stderr, "tc emu: pointer is not in the kernel's shared memory\n"); abort(); }
+  return (uint32_t)off;
+}
+
+// ---------------------------------------------------------------- mbarrier
+inline void mbar_init(uint64_t* bar, uint32_t count) { std::lock_guard<std::mutex> g(emu::g_mu); *bar = emu::mb_make(count, count, 0, 0); emu::g_events++; }
+inline void fence_barrier_init() {}
+inline void mbar_arrive(uint64_t* bar) { std::lock_guard<std::mutex> g(emu::g_mu); emu::mb_arrive_locked(bar); }
+inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  std::lock_guard<std::mutex> g(emu::g_mu);
+  const uint64_t w = *bar;
+  *bar = emu::mb_make(emu::mb_pending(w), emu::mb_count(w), emu::mb_tx(w) + bytes, emu::mb_phase(w));
+  emu::mb_arrive_locked(bar);
+}
+inline bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  std::lock_guard<std::mutex> g(emu::g_mu);
+  if (emu::mb_phase(*bar) != (parity & 1u)) return true;
+  emu::progress_locked();                    // a polling thread also lets the asynchronous engines advance
+  return false;
+}
+inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  {
+    std::lock_guard<std::mutex> g(emu::g_mu);
+    if (emu::mb_phase(*bar) != (parity & 1u)) return true;
+    if (emu::progress_locked()) return emu::mb_phase(*bar) != (parity & 1u);
+  }
+  // nothing queued: somebody else has to arrive.  Deadlock watchdog: no state change anywhere for a long time.
+  const unsigned long long seen = emu::g_events.load();
+  emu::g_waiting++;
+  static thread_local std::chrono::steady_clock::time_point last_change = std::chrono::steady_clock::now();
+  static thread_local unsigned long long last_seen = ~0ull;
+  if (seen != last_seen) { last_seen = seen; last_change = std::chrono::steady_clock::now(); }
+  std::this_thread::sleep_for(std::chrono::microseconds(200));
+  emu::g_waiting--;
+  if (std::chrono::steady_clock::now() - last_change > std::chrono::seconds(20)) {
+    const uint64_t w = *bar;
+    fprintf(stderr, "tc emu: DEADLOCK -- thread %d of CTA %u waits on barrier +%u (parity %u; phase %u pending %u tx %u), nothing queued\n",
+            cuda_emu::linear_tid(), blockIdx.x, smem_u32(bar), parity, emu::mb_phase(w), emu::mb_pending(w), emu::mb_tx(w));
+    abort();
+  }
+  return false;
+}
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ---------------------------------------------------------------- bulk async copy
+inline void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  if (bytes % 16 || ((uintptr_t)smem_dst & 15) || ((uintptr_t)gmem_src & 15)) { fprintf(stderr, "tc emu: bulk copy alignment\n"); abort(); }
+  (void)smem_u32(smem_dst);
+  std::lock_guard<std::mutex> g(emu::g_mu);
+  emu::Op op{};
+  op.kind = emu::Op::COPY; op.dst = (uint8_t*)smem_dst; op.src = (const uint8_t*)gmem_src; op.bytes = bytes; op.bar = bar;
+  emu::g_copies.push_back(op);
+  if (emu::eager()) while (emu::progress_locked()) {}
+}
+
+inline void bar_sync_workers256() {
+  // warps 4..11 of the CTA: the eight per-warp barriers in sequence form a 256-thread barrier (two rounds)
+  static pthread_barrier_t b;
+  static std::once_flag once;
+  std::call_once(once, [] { pthread_barrier_init(&b, nullptr, 256); });
+  pthread_barrier_wait(&b);
+}
+
+// ---------------------------------------------------------------- fences
+inline void fence_proxy_async_smem() {}
+inline void tcgen05_fence_before() {}
+inline void tcgen05_fence_after() {}
+
+// ---------------------------------------------------------------- TMEM allocation
+inline void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+  if (ncols != 512) { fprintf(stderr, "tc emu: the model hands out all 512 columns\n"); abort(); }
+  if ((cuda_emu::linear_tid() & 31) == 0) *smem_result = 0;
+}
+inline void tmem_relinquish() {}
+inline void tmem_dealloc(uint32_t, uint32_t) {}
+
+// ---------------------------------------------------------------- descriptors (same bit layouts as tc_ptx.cuh)
+inline uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+constexpr uint32_t make_idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+
+// ---------------------------------------------------------------- MMA
+inline void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  std::lock_guard<std::mutex> g(emu::g_mu);
+  emu::Op op{};
+  op.kind = emu::Op::MMA_SS; op.d_tmem = d_tmem; op.a_desc = a_desc; op.b_desc = b_desc; op.idesc = idesc; op.accumulate = accumulate;
+  emu::g_mmas.push_back(op);
+  if (emu::eager()) while (emu::progress_locked()) {}
+}
+inline void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  std::lock_guard<std::mutex> g(emu::g_mu);
+  emu::Op op{};
+  op.kind = emu::Op::MMA_TS; op.d_tmem = d_tmem; op.a_tmem = a_tmem; op.b_desc = b_desc; op.idesc = idesc; op.accumulate = accumulate;
+  emu::g_mmas.push_back(op);
+  if (emu::eager()) while (emu::progress_locked()) {}
+}
+inline void mma_commit(uint64_t* bar) {
+  (void)smem_u32(bar);
+  std::lock_guard<std::mutex> g(emu::g_mu);
+  emu::Op op{};
+  op.kind = emu::Op::COMMIT; op.bar = bar;
+  emu::g_mmas.push_back(op);
+  if (emu::eager()) while (emu::progress_locked()) {}
+}
+
+// ---------------------------------------------------------------- TMEM <-> registers (warp w owns lanes 32*(w%4)..+31)
+inline uint32_t tmem_row_checked(uint32_t taddr) {
+  const int tid = cuda_emu::linear_tid(), warp = tid >> 5, lane = tid & 31;
+  const uint32_t lane_field = taddr >> 16;
+  if (lane_field != (uint32_t)(32 * (warp & 3))) {
+    fprintf(stderr, "tc emu: warp %d may only touch tensor-memory lanes %d..%d (address lane %u)\n", warp, 32 * (warp & 3), 32 * (warp & 3) + 31, lane_field);
+    abort();
+  }
+  return lane_field + lane;
+}
+inline void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  const uint32_t row = tmem_row_checked(taddr), col = taddr & 0xFFFF;
+  if (col + 32 > emu::kCols) { fprintf(stderr, "tc emu: tcgen05.ld beyond column 512\n"); abort(); }
+  std::lock_guard<std::mutex> g(emu::g_mu);
+  for (int j = 0; j < 32; ++j) r[j] = emu::g_tmem[row][col + j];
+}
+inline void tmem_ld_wait() {}
+inline void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  const uint32_t row = tmem_row_checked(taddr), col = taddr & 0xFFFF;
+  if (col + 16 > emu::kCols) { fprintf(stderr, "tc emu: tcgen05.st beyond column 512\n"); abort(); }
+  std::lock_guard<std::mutex> g(emu::g_mu);
+  for (int j = 0; j < 16; ++j) emu::g_tmem[row][col + j] = r[j];
+}
+inline void tmem_st_wait() {}
+
+// ---------------------------------------------------------------- operand layout helpers (as in tc_ptx.cuh)
+inline uint32_t sw128_offset(uint32_t row, uint32_t k) {
+  const uint32_t chunk = (k >> 3) ^ (row & 7u);
+  return (row >> 3) * 1024u + (row & 7u) * 128u + chunk * 16u + (k & 7u) * 2u;
+}
+inline uint32_t pack_half2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  uint32_t u;
+  memcpy(&u, &h, 4);
+  return u;
+}
+
+// ---------------------------------------------------------------- cta_group::2 / clusters: not modelled
+[[noreturn]] inline void no_cluster() { fprintf(stderr, "tc emu: cta_group::2 / clusters are not modelled\n"); abort(); }
+inline uint32_t cluster_ctarank() { return 0; }
+inline void cluster_sync_all() { no_cluster(); }
+inline void mbar_arrive_remote(uint64_t*, uint32_t) { no_cluster(); }
+inline void mbar_wait_cluster(uint64_t*, uint32_t) { no_cluster(); }
+inline void tmem_alloc2(uint32_t*, uint32_t) { no_cluster(); }
+inline void tmem_relinquish2() { no_cluster(); }
+inline void tmem_dealloc2(uint32_t, uint32_t) { no_cluster(); }
+inline void mma_ss2(uint32_t, uint64_t, uint64_t, uint32_t, uint32_t) { no_cluster(); }
+inline void mma_ts2(uint32_t, uint32_t, uint64_t, uint32_t, uint32_t) { no_cluster(); }
+inline void mma_commit2(uint64_t*) { no_cluster(); }
+
+}  // namespace tc
