@@ -82,6 +82,7 @@ struct TcPack {
   float* w4z;             // [R]
   float* b4;              // [R]
   int res;
+  int kind;               // 0 = geometry head (programs v2 / v3), 1 = colour head (query_tc3c_kernel)
 };
 
 struct TcParams {
@@ -1536,6 +1537,624 @@ g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half
   if (warp == 8) tc::tmem_dealloc(tbase, 512);
 }
 
+// ====================================================================================================================
+// Colour head: PIFuNetCMLP (filter_channels [513,1024,512,256,128,3], Tanh, heads/SurfaceClassifier.py:82-87) on the
+// 512-channel map of MonoPortNet.filter(feat_prior=...) (MonoPortNet.py:41-45), queried at the visible vertices
+// (RTL/main.py:212-249).  EXPERIMENTAL (opt-in, MONOPORT_B200_TC_NETC=1) until validated on a B200; checked on the CPU model
+// of the tcgen05 layer (tests/emu).  Same structure as program v3 (layer 0 hoisted to texels, layer 1 on all 512 TMEM
+// columns, in-place drains, A operands from TMEM) with two differences:
+//   * the skip operand X has 512 channels = 128 KB, which does not fit next to the H0 ring and the weight ring.  X keeps
+//     its 64 KB buffer and is filled in PHASES of 256 channels (A = 0..255, B = 256..511); the skip parts of the layers
+//     are issued in the order  L1:A,B  L2:B,A  L3:A,B  so that four fills per tile suffice.  The tensor pipe waits for
+//     the samplers at three of them -- acceptable for a query of 10^4..10^5 points (the dense path is the geometry head);
+//   * the per-point scalars (depth feature, in-image flag, the fp32 last-layer feature part S4[3]) are computed by the
+//     epilogue thread that owns the point instead of being passed through shared memory (no room, and no barrier).
+constexpr int kCc = 512;                                   // feature channels of the colour map
+constexpr int kResC = 3;
+constexpr int kStagesPerTileC = 32 + 16 + 8 + 8 + 4 + 2;   // L1 hidden, L1 skip (A,B), L2 hidden, L2 skip (B,A), L3 skip (A,B), L3 hidden
+
+// 16 points of one phase (256 channels starting at phase*256) of the fp16 map -> rows [pbase, pbase+16) of X
+__device__ __forceinline__ void sample_x_phase(const TcParams& prm, uint8_t* smem_x, const PointTaps& pt, int pbase, int lane, int phase) {
+  const int cbase = phase * 256 + lane * 8;
+#pragma unroll 1
+  for (int q0 = 0; q0 < 16; q0 += 4) {
+    uint4 raw[4][4];                         // [point][tap] 8 fp16 channels
+    float wgt[4][4];
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int off = __shfl_sync(0xffffffffu, pt.off[a], q0 + qq);
+        wgt[qq][a] = __shfl_sync(0xffffffffu, pt.wgt[a], q0 + qq);
+        raw[qq][a] = __ldg(reinterpret_cast<const uint4*>(prm.feat16 + (size_t)off * kCc + cbase));
+      }
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      const int p = pbase + q0 + qq;
+      float2 acc[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {                   // same accumulation order as grid_sample: nw, ne, sw, se
+        const float2 w2 = make_float2(wgt[qq][a], wgt[qq][a]);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[qq][a]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = (a == 0) ? __fmul2_rn(__half22float2(h2[j]), w2) : __ffma2_rn(__half22float2(h2[j]), w2, acc[j]);
+      }
+      uint4 packed;
+      packed.x = tc::pack_half2(acc[0].x, acc[0].y);
+      packed.y = tc::pack_half2(acc[1].x, acc[1].y);
+      packed.z = tc::pack_half2(acc[2].x, acc[2].y);
+      packed.w = tc::pack_half2(acc[3].x, acc[3].y);
+      *reinterpret_cast<uint4*>(smem_x + (lane >> 3) * 16384 + tc::sw128_offset(p, (lane & 7) * 8)) = packed;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
+  using C = Cfg<1>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::Bars);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Smem::TmemPtr);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long n = src.n;
+  if (src.count_dev) {
+    const long long c = *src.count_dev;
+    n = c < n ? c : n;
+  }
+  const long long n_tiles = (n + kTile - 1) / kTile;
+  const long long g0 = blockIdx.x, gstep = gridDim.x;
+
+  constexpr uint32_t cAcc1 = 0, cH1lo = 0, cH1hi = 384, cAcc2 = 128, cH2 = 0, cAcc3 = 384;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      tc::mbar_init(bars + B_WFULL + s, 1);
+      tc::mbar_init(bars + B_WEMPTY + s, 1);
+    }
+    constexpr int kW = 8;
+    tc::mbar_init(bars + B_XREADY, 2);             // the two sampler warps, once per phase fill
+    tc::mbar_init(bars + B_XFREE, 1);              // tcgen05.commit after the last MMA reading a fill
+    tc::mbar_init(bars + B_H0_READY0, kW);
+    tc::mbar_init(bars + B_H0_READY1, kW);
+    tc::mbar_init(bars + B_H0_FREE0, 1);
+    tc::mbar_init(bars + B_H0_FREE1, 1);
+    tc::mbar_init(bars + B_ACC1_FULL, 1);
+    tc::mbar_init(bars + B_H1_READY, kW);
+    tc::mbar_init(bars + B_ACC2_FULL, 1);
+    tc::mbar_init(bars + B_H2_READY, kW);
+    tc::mbar_init(bars + B_ACC3_FULL, 1);
+    tc::mbar_init(bars + B_TILE_DONE, 4);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) { tc::tmem_alloc(s_tmem, 512); tc::tmem_relinquish(); }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tbase = *s_tmem;
+
+  if (warp == 0) {
+    // ============================== weight producer ==============================
+    if (lane == 0) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.wstream);
+      uint32_t it = 0;
+      for (long long g = g0; g < n_tiles; g += gstep) {
+        for (int s = 0; s < kStagesPerTileC; ++s, ++it) {
+          const int slot = it % C::Stages;
+          const uint32_t use = it / C::Stages;
+          tc::mbar_wait(bars + B_WEMPTY + slot, (use & 1u) ^ 1u);
+          tc::mbar_arrive_expect_tx(bars + B_WFULL + slot, C::StageBytes);
+          tc::bulk_g2s(smem + Smem::Wr + slot * C::StageBytes, wsrc + (size_t)s * C::StageBytes, C::StageBytes, bars + B_WFULL + slot);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc128 = tc::make_idesc_f16(128, 128);
+      const uint32_t idesc256 = tc::make_idesc_f16(128, 256);
+      const uint32_t sX = tc::smem_u32(smem + Smem::X);
+      const uint32_t sH0 = tc::smem_u32(smem + Smem::H0);
+      const uint32_t sW = tc::smem_u32(smem + Smem::Wr);
+      uint32_t it = 0;
+      uint32_t c_xready = 0, c_h0ready[2] = {0, 0}, c_h1ready = 0, c_h2ready = 0, c_tiledone = 0;
+      auto next_stage = [&]() -> uint32_t {
+        const int slot = it % C::Stages;
+        tc::mbar_wait(bars + B_WFULL + slot, (it / C::Stages) & 1u);
+        tc::tcgen05_fence_after();
+        return sW + slot * C::StageBytes;
+      };
+      auto release_stage = [&]() {
+        tc::mma_commit(bars + B_WEMPTY + (it % C::Stages));
+        ++it;
+      };
+      auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool& first) {
+#pragma unroll 1
+        for (int kk = 0; kk < 4; ++kk) {
+          tc::mma_ss(d, tc::make_sdesc_sw128(a_addr + kk * 32, 1024), tc::make_sdesc_sw128(b_addr + kk * 32, 1024), idesc, first ? 0u : 1u);
+          first = false;
+        }
+      };
+      auto kblock_ts = [&](uint32_t d, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool& first) {
+#pragma unroll 1
+        for (int kk = 0; kk < 4; ++kk) {
+          tc::mma_ts(d, a_tmem + kk * 8, tc::make_sdesc_sw128(b_addr + kk * 32, 1024), idesc, first ? 0u : 1u);
+          first = false;
+        }
+      };
+      auto wait_x = [&]() {            // the next phase of X has been sampled
+        wait_bar(bars, B_XREADY, c_xready);
+        tc::tcgen05_fence_after();
+      };
+
+      for (long long g = g0; g < n_tiles; g += gstep) {
+        bool need_tile_done = g != g0;
+        bool first1[2] = {true, true};
+        // ---- layer 1, hidden part: 8 sampled layer-0 chunks x 2 K-blocks x 2 output halves
+        for (int c = 0; c < 8; ++c) {
+          const int b = c & 1;
+          wait_bar(bars, B_H0_READY0 + b, c_h0ready[b]);
+          tc::tcgen05_fence_after();
+          for (int kb = 0; kb < 2; ++kb)
+            for (int nh = 0; nh < 2; ++nh) {
+              const uint32_t w = next_stage();
+              if (nh == 1 && need_tile_done) {
+                // [384,512) holds the previous tile's acc3 until its fp32 tail has drained it
+                wait_bar(bars, B_TILE_DONE, c_tiledone);
+                tc::tcgen05_fence_after();
+                need_tile_done = false;
+              }
+              kblock_ss(tbase + cAcc1 + nh * 256, sH0 + b * 32768 + kb * 16384, w, idesc256, first1[nh]);
+              release_stage();
+            }
+          tc::mma_commit(bars + B_H0_FREE0 + b);
+        }
+        // ---- layer 1, skip part: phase A, then phase B
+        for (int ph = 0; ph < 2; ++ph) {
+          wait_x();
+          for (int kb = 0; kb < 4; ++kb)
+            for (int nh = 0; nh < 2; ++nh) {
+              const uint32_t w = next_stage();
+              kblock_ss(tbase + cAcc1 + nh * 256, sX + kb * 16384, w, idesc256, first1[nh]);
+              release_stage();
+            }
+          if (ph == 0) tc::mma_commit(bars + B_XFREE);       // phase A consumed; phase B stays for layer 2
+        }
+        tc::mma_commit(bars + B_ACC1_FULL);
+        // ---- layer 2: A = H1 from TMEM (8 K-blocks), then X phase B (resident), then phase A -> acc2 [128,384)
+        wait_bar(bars, B_H1_READY, c_h1ready);
+        tc::tcgen05_fence_after();
+        {
+          bool first = true;
+          for (int kb = 0; kb < 8; ++kb) {
+            const uint32_t w = next_stage();
+            const uint32_t a = tbase + (kb < 4 ? cH1lo + kb * 32 : cH1hi + (kb - 4) * 32);
+            kblock_ts(tbase + cAcc2, a, w, idesc256, first);
+            release_stage();
+          }
+          for (int ph = 0; ph < 2; ++ph) {
+            if (ph == 1) wait_x();                           // phase A again
+            for (int kb = 0; kb < 4; ++kb) {
+              const uint32_t w = next_stage();
+              kblock_ss(tbase + cAcc2, sX + kb * 16384, w, idesc256, first);
+              release_stage();
+            }
+            if (ph == 0) tc::mma_commit(bars + B_XFREE);     // phase B consumed
+          }
+          tc::mma_commit(bars + B_ACC2_FULL);
+        }
+        // ---- layer 3 -> acc3 [384,512): skip phase A (resident), skip phase B, hidden part
+        {
+          bool first = true;
+          for (int ph = 0; ph < 2; ++ph) {
+            if (ph == 1) wait_x();                           // phase B again
+            for (int s = 0; s < 2; ++s) {
+              const uint32_t w = next_stage();
+              kblock_ss(tbase + cAcc3, sX + (2 * s) * 16384, w, idesc128, first);
+              kblock_ss(tbase + cAcc3, sX + (2 * s + 1) * 16384, w + C::Sub, idesc128, first);
+              release_stage();
+            }
+            tc::mma_commit(bars + B_XFREE);                  // after phase B: X is dead, the next tile's phase A may be sampled
+          }
+          wait_bar(bars, B_H2_READY, c_h2ready);
+          tc::tcgen05_fence_after();
+          for (int s = 0; s < 2; ++s) {
+            const uint32_t w = next_stage();
+            kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * s) * 32, w, idesc128, first);
+            kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * s + 1) * 32, w + C::Sub, idesc128, first);
+            release_stage();
+          }
+          tc::mma_commit(bars + B_ACC3_FULL);
+        }
+      }
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ============================== samplers: four phase fills of X per tile (A, B, A, B) ==============================
+    const int sw = warp - 2;
+    uint32_t c_xfree = 0;
+    bool first_fill = true;
+    for (long long g = g0; g < n_tiles; g += gstep) {
+      const long long p0 = g * kTile;
+      for (int f = 0; f < 4; ++f) {
+        if (!first_fill) wait_bar(bars, B_XFREE, c_xfree);
+        first_fill = false;
+#pragma unroll 1
+        for (int grp = 0; grp < 4; ++grp) {
+          const int pbase = sw * 64 + grp * 16;
+          const PointTaps pt = point_taps(src, cal, prm.H, prm.W, p0 + pbase + (lane & 15), n);
+          sample_x_phase(prm, smem + Smem::X, pt, pbase, lane, f & 1);
+        }
+        tc::fence_proxy_async_smem();
+        warp_arrive_local(bars + B_XREADY, lane);
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================== workers: layer-0 chunk generators + epilogue ==============================
+    const int wk = warp - 4;
+    const int wg = wk >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    uint32_t c_h0free[2] = {0, 0}, c_acc1full = 0, c_acc2full = 0, c_acc3full = 0;
+    const int l16 = lane & 15;
+
+    auto act_pack = [&](float a, float b) -> uint32_t {
+      const __half2 h = __floats2half2_rn(a, b);
+      const __half2 r = __hmax2(h, __hmul2(h, __float2half2_rn(MP_LEAKY_SLOPE)));
+      return *reinterpret_cast<const uint32_t*>(&r);
+    };
+    // taps of this warp's 16 points (a quarter-warp per point, four points per lane), as in program v3
+    const int l8 = lane & 7, qw = lane >> 3;
+    uint32_t t_off[4][2], t_wgt[4][2], t_z[4];
+    auto compute_taps = [&](long long g) {
+      const PointTaps pt = point_taps(src, cal, prm.H, prm.W, g * kTile + wk * 16 + l16, n);
+      const uint32_t o01 = (uint32_t)pt.off[0] | ((uint32_t)pt.off[1] << 16), o23 = (uint32_t)pt.off[2] | ((uint32_t)pt.off[3] << 16);
+      const uint32_t w01 = tc::pack_half2(pt.wgt[0], pt.wgt[1]), w23 = tc::pack_half2(pt.wgt[2], pt.wgt[3]);
+      const uint32_t zz = tc::pack_half2(pt.zf, pt.zf);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int q = 4 * i + qw;
+        t_off[i][0] = __shfl_sync(0xffffffffu, o01, q);
+        t_off[i][1] = __shfl_sync(0xffffffffu, o23, q);
+        t_wgt[i][0] = __shfl_sync(0xffffffffu, w01, q);
+        t_wgt[i][1] = __shfl_sync(0xffffffffu, w23, q);
+        t_z[i] = __shfl_sync(0xffffffffu, zz, q);
+      }
+    };
+    // one sampled layer-0 chunk: h0[:, c*128 .. +128) = lrelu(lerp(G0) + b0 + w0z z) -> H0 smem buffer c&1 (packed-fp16 FMAs)
+    auto gen_chunk = [&](int c) {
+      const int b = c & 1;
+      wait_free(bars, B_H0_FREE0 + b, c_h0free[b]);
+      const int ch = c * 128 + l8 * 8;
+      __half2 b8[8], z8[8];
+      {
+        const uint4 bA = __ldg(reinterpret_cast<const uint4*>(prm.d_bias0 + ch)), bB = __ldg(reinterpret_cast<const uint4*>(prm.d_bias0 + ch + 64));
+        const uint4 zA = __ldg(reinterpret_cast<const uint4*>(prm.d_wz0 + ch)), zB = __ldg(reinterpret_cast<const uint4*>(prm.d_wz0 + ch + 64));
+        *reinterpret_cast<uint4*>(&b8[0]) = bA; *reinterpret_cast<uint4*>(&b8[4]) = bB;
+        *reinterpret_cast<uint4*>(&z8[0]) = zA; *reinterpret_cast<uint4*>(&z8[4]) = zB;
+      }
+      uint8_t* dstp = smem + Smem::H0 + b * 32768;
+      const __half2 slope2 = __float2half2_rn(MP_LEAKY_SLOPE);
+#pragma unroll
+      for (int batch = 0; batch < 2; ++batch) {
+        uint4 raw[2][4][2];                  // [point][tap][K-block]
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          const int i = batch * 2 + ps;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const uint32_t off = (a & 1) ? (t_off[i][a >> 1] >> 16) : (t_off[i][a >> 1] & 0xFFFFu);
+            const uint4* srcp = reinterpret_cast<const uint4*>(prm.g0 + (size_t)off * kL0 + ch);
+            raw[ps][a][0] = __ldg(srcp);
+            raw[ps][a][1] = __ldg(srcp + 8);      // + 64 channels
+          }
+        }
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          const int i = batch * 2 + ps;
+          const int p = wk * 16 + 4 * i + qw;
+          const __half2 zq2 = *reinterpret_cast<const __half2*>(&t_z[i]);
+          __half2 acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = __hfma2(z8[j], zq2, b8[j]);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {          // same tap order as grid_sample: nw, ne, sw, se
+            const __half2 wp = *reinterpret_cast<const __half2*>(&t_wgt[i][a >> 1]);
+            const __half2 w2 = (a & 1) ? __high2half2(wp) : __low2half2(wp);
+            const __half2* h0 = reinterpret_cast<const __half2*>(&raw[ps][a][0]);
+            const __half2* h1 = reinterpret_cast<const __half2*>(&raw[ps][a][1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[j] = __hfma2(h0[j], w2, acc[j]);
+              acc[4 + j] = __hfma2(h1[j], w2, acc[4 + j]);
+            }
+          }
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const __half2 r = __hmax2(acc[j], __hmul2(acc[j], slope2));
+            o[j] = *reinterpret_cast<const uint32_t*>(&r);
+          }
+          *reinterpret_cast<uint4*>(dstp + tc::sw128_offset(p, l8 * 8)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(dstp + 16384 + tc::sw128_offset(p, l8 * 8)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+      tc::fence_proxy_async_smem();
+      warp_arrive_local(bars + B_H0_READY0 + b, lane);
+    };
+    float zf = 0.f, inimg = 0.f;
+    float s4[kResC] = {0.f, 0.f, 0.f};
+    auto load_pre = [&](uint32_t col, int ch0, float (&o)[32]) {
+      uint32_t v[32];
+      tc::tmem_ld32(tbase + lane_base + col, v);
+      tc::tmem_ld_wait();
+      const float4* bz = reinterpret_cast<const float4*>(&prm.bias_all[ch0]);
+      const float4* wz = reinterpret_cast<const float4*>(&prm.wz_all[ch0]);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 b = bz[j4], z = wz[j4];
+        o[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + fmaf(z.x, zf, b.x);
+        o[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + fmaf(z.y, zf, b.y);
+        o[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + fmaf(z.z, zf, b.z);
+        o[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + fmaf(z.w, zf, b.w);
+      }
+    };
+    // worker loop, software-pipelined across tiles exactly like program v3 (virtual first iteration = pre-generation only)
+    for (long long g = g0 - gstep; g < n_tiles; g += gstep) {
+      const bool real = g >= g0;
+      const bool has_next = g + gstep < n_tiles;
+      const long long p0 = g * kTile;
+#pragma unroll 1
+      for (int step = 0; step < 11; ++step) {
+        int gc = -1;
+        if (step < 6) { if (real) gc = step + 2; }
+        else if (step == 7) { if (has_next) { compute_taps(g + gstep); gc = 0; } }
+        else if (step == 10) { if (has_next) gc = 1; }
+        if (gc >= 0) gen_chunk(gc);
+        if (!real) continue;
+        if (step == 6) {
+          // per-point scalars of the point this thread owns in the epilogue (TMEM lane `row`)
+          {
+            const PointTaps me = point_taps(src, cal, prm.H, prm.W, p0 + row, n);
+            zf = me.zf;
+            inimg = me.in_img ? 1.f : 0.f;
+            if (wg == 0) {
+#pragma unroll
+              for (int r = 0; r < kResC; ++r) {
+                float s = 0.f;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) s = fmaf(me.wgt[a], __ldg(prm.s4tex + (size_t)me.off[a] * kResC + r), s);
+                s4[r] = s + __ldg(prm.w4z + r) * zf + __ldg(prm.b4 + r);
+              }
+            }
+          }
+          // ---- layer 1 (512 columns) -> H1, drained in place (see program v3)
+          wait_bar(bars, B_ACC1_FULL, c_acc1full);
+          tc::tcgen05_fence_after();
+#pragma unroll 1
+          for (int gi = 0; gi < 8; ++gi) {
+            const int gq = (wg == 0) ? gi : 7 - gi;
+            const int lc = wg * 256 + gq * 32;
+            float o[32];
+            load_pre(cAcc1 + lc, side_off(1) + lc, o);
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = act_pack(o[2 * j], o[2 * j + 1]);
+            const uint32_t dcol = (wg == 0) ? (cH1lo + lc / 2) : (cH1hi + (lc - 256) / 2);
+            tc::tmem_st16(tbase + lane_base + dcol, pk);
+            tc::tmem_st_wait();
+          }
+          tc::tcgen05_fence_before();
+          warp_arrive_local(bars + B_H1_READY, lane);
+        } else if (step == 8) {
+          // ---- layer 2 -> H2 [0,128)
+          wait_bar(bars, B_ACC2_FULL, c_acc2full);
+          tc::tcgen05_fence_after();
+#pragma unroll 1
+          for (int gq = 0; gq < 4; ++gq) {
+            float o[32];
+            const int lc = wg * 128 + gq * 32;
+            load_pre(cAcc2 + lc, side_off(2) + lc, o);
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = act_pack(o[2 * j], o[2 * j + 1]);
+            tc::tmem_st16(tbase + lane_base + cH2 + lc / 2, pk);
+          }
+          tc::tmem_st_wait();
+          tc::tcgen05_fence_before();
+          warp_arrive_local(bars + B_H2_READY, lane);
+        } else if (step == 9) {
+          // ---- layer 3 + layer 4 (641 -> 3) in fp32, warpgroup 0
+          if (wg == 0) {
+            wait_bar(bars, B_ACC3_FULL, c_acc3full);
+            tc::tcgen05_fence_after();
+            float logit[kResC];
+#pragma unroll
+            for (int r = 0; r < kResC; ++r) logit[r] = s4[r];
+#pragma unroll 1
+            for (int gq = 0; gq < 4; ++gq) {
+              float o[32];
+              load_pre(cAcc3 + gq * 32, side_off(3) + gq * 32, o);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], o[j] * MP_LEAKY_SLOPE);
+#pragma unroll
+              for (int r = 0; r < kResC; ++r) {
+                const float4* wv = reinterpret_cast<const float4*>(prm.w4h + r * kL3 + gq * 32);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 w4 = __ldg(wv + j4);
+                  logit[r] = fmaf(w4.x, o[4 * j4 + 0], logit[r]);
+                  logit[r] = fmaf(w4.y, o[4 * j4 + 1], logit[r]);
+                  logit[r] = fmaf(w4.z, o[4 * j4 + 2], logit[r]);
+                  logit[r] = fmaf(w4.w, o[4 * j4 + 3], logit[r]);
+                }
+              }
+            }
+            tc::tcgen05_fence_before();
+            warp_arrive_local(bars + B_TILE_DONE, lane);
+            const long long i = p0 + row;
+            if (i < n && dst.out) {
+#pragma unroll
+              for (int r = 0; r < kResC; ++r) dst.out[(long long)r * dst.ld + i] = inimg * mp_last_op(logit[r], prm.last_op);
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tbase, 512);
+}
+
+// G0 / fp16 copy / S4 of the 512-channel colour map: as g0_tc_kernel with eight K-blocks (A staged once: 128 KB, so the B
+// ring has two 32 KB stages) and three last-layer outputs.
+constexpr int kG0cKB = kCc / 64;                       // 8 K-blocks
+constexpr int kG0cStages = 2;
+constexpr uint32_t kG0cSmemA = kG0cKB * 16384, kG0cSmemB = kG0cStages * 32768;
+constexpr uint32_t kG0cSmem = kG0cSmemA + kG0cSmemB + 1024 /*align*/ + 128 /*barriers + tmem slot*/;
+
+__global__ void __launch_bounds__(kG0Threads, 1)
+g0c_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half* __restrict__ G, int M,
+              __half* __restrict__ F16, float* __restrict__ S4, const float* __restrict__ w4s) {
+  extern __shared__ uint8_t g0_smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g0_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = base;
+  uint8_t* sB = base + kG0cSmemA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + kG0cSmemA + kG0cSmemB);
+  uint64_t* b_full = bars;                   // [2] B stage landed
+  uint64_t* b_empty = bars + 4;              // [2] B stage consumed (tcgen05.commit)
+  uint64_t* acc_full = bars + 8;             // [2] accumulator complete
+  uint64_t* acc_free = bars + 10;            // [2] accumulator drained by the 8 epilogue warps
+  uint64_t* a_ready = bars + 12;             // A staged (8 warps)
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 13);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * 128;
+  if (tid == 0) {
+    for (int i = 0; i < kG0cStages; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_free[i], 8); }
+    tc::mbar_init(a_ready, 8);
+    tc::fence_barrier_init();
+  }
+  if (warp == 8) {
+    tc::tmem_alloc(tslot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tbase = *tslot;
+  constexpr uint32_t idesc = tc::make_idesc_f16(128, kG0TileN);
+  constexpr int kTiles = kG0NT * kG0cKB;       // 32 B tiles in (nt, kb) order
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int s = 0; s < kTiles; ++s) {
+        const int slot = s % kG0cStages;
+        if (s >= kG0cStages) tc::mbar_wait(&b_empty[slot], ((s / kG0cStages) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&b_full[slot], 32768);
+        tc::bulk_g2s(sB + slot * 32768, Wt + (size_t)s * 32768, 32768, &b_full[slot]);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      tc::mbar_wait(a_ready, 0);
+      tc::tcgen05_fence_after();
+      for (int nt = 0; nt < kG0NT; ++nt) {
+        const int buf = nt & 1;
+        if (nt >= 2) { tc::mbar_wait(&acc_free[buf], ((nt >> 1) & 1) ^ 1); tc::tcgen05_fence_after(); }
+        for (int kb = 0; kb < kG0cKB; ++kb) {
+          const int s = nt * kG0cKB + kb, slot = s % kG0cStages;
+          tc::mbar_wait(&b_full[slot], (s / kG0cStages) & 1);
+          tc::tcgen05_fence_after();
+          const uint32_t a0 = tc::smem_u32(sA + kb * 16384), b0 = tc::smem_u32(sB + slot * 32768);
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16)
+            tc::mma_ss(tbase + buf * kG0TileN, tc::make_sdesc_sw128(a0 + k16 * 32, 1024), tc::make_sdesc_sw128(b0 + k16 * 32, 1024), idesc,
+                       (kb | k16) ? 1u : 0u);
+          tc::mma_commit(&b_empty[slot]);
+        }
+        tc::mma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ---- warps 0-7: stage A (thread -> row = tid / 2, 32-column half of each 64-wide K-block), then drain
+    const int row = tid >> 1, half = tid & 1;
+    const bool live = (m0 + row) < M;
+    const float* frow = F + (size_t)(live ? m0 + row : 0) * kCc + half * 32;
+    float s4acc[kResC] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int kb = 0; kb < kG0cKB; ++kb) {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = live ? __ldg(reinterpret_cast<const float4*>(frow + kb * 64) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 pk;
+        pk.x = tc::pack_half2(v[2 * j].x, v[2 * j].y);
+        pk.y = tc::pack_half2(v[2 * j].z, v[2 * j].w);
+        pk.z = tc::pack_half2(v[2 * j + 1].x, v[2 * j + 1].y);
+        pk.w = tc::pack_half2(v[2 * j + 1].z, v[2 * j + 1].w);
+        *reinterpret_cast<uint4*>(sA + kb * 16384 + tc::sw128_offset(row, half * 32 + j * 8)) = pk;
+        if (live) *reinterpret_cast<uint4*>(F16 + (size_t)(m0 + row) * kCc + kb * 64 + half * 32 + j * 8) = pk;
+      }
+#pragma unroll
+      for (int r = 0; r < kResC; ++r) {
+        const float4* wv = reinterpret_cast<const float4*>(w4s + r * kCc + kb * 64 + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w = __ldg(wv + j);
+          s4acc[r] = fmaf(w.x, v[j].x, s4acc[r]); s4acc[r] = fmaf(w.y, v[j].y, s4acc[r]);
+          s4acc[r] = fmaf(w.z, v[j].z, s4acc[r]); s4acc[r] = fmaf(w.w, v[j].w, s4acc[r]);
+        }
+      }
+    }
+    tc::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(a_ready);
+#pragma unroll
+    for (int r = 0; r < kResC; ++r) {
+      const float tot = s4acc[r] + __shfl_xor_sync(0xffffffffu, s4acc[r], 1);
+      if (live && half == 0) S4[(size_t)(m0 + row) * kResC + r] = tot;
+    }
+    const int sub = warp & 3, ch = warp >> 2;
+    const int m = m0 + sub * 32 + lane;
+#pragma unroll 1
+    for (int nt = 0; nt < kG0NT; ++nt) {
+      const int buf = nt & 1;
+      tc::mbar_wait(&acc_full[buf], (nt >> 1) & 1);
+      __syncwarp();
+      tc::tcgen05_fence_after();
+      __half* grow = G + (size_t)(m < M ? m : 0) * kL0 + nt * kG0TileN + ch * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld32(tbase + ((uint32_t)(sub * 32) << 16) + buf * kG0TileN + ch * 128 + c * 32, r);
+        tc::tmem_ld_wait();
+        if (m < M) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 pk;
+            pk.x = tc::pack_half2(__uint_as_float(r[8 * q + 0]), __uint_as_float(r[8 * q + 1]));
+            pk.y = tc::pack_half2(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3]));
+            pk.z = tc::pack_half2(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5]));
+            pk.w = tc::pack_half2(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7]));
+            *reinterpret_cast<uint4*>(grow + c * 32 + q * 8) = pk;
+          }
+        }
+      }
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_free[buf]);
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tbase, 512);
+}
+
 // --------------------------------------------------------------------------------------------------------------------
 // host side: weight packing
 // --------------------------------------------------------------------------------------------------------------------
@@ -1556,11 +2175,179 @@ bool shape_supported(const mp_mlp* m) {
   return m->channels[5] >= 1 && m->channels[5] <= kMaxRes;
 }
 
+bool colour_shape(const mp_mlp* m) {
+  if (m->n_layers != 5 || !m->skip) return false;
+  const int want[6] = {kCc + 1, 1024, 512, 256, 128, kResC};
+  for (int l = 0; l <= 5; ++l)
+    if (m->channels[l] != want[l]) return false;
+  return true;
+}
+
+// weight stream / side vectors of the colour head, in the order query_tc3c_kernel consumes them
+int tc_prepare_colour(mp_mlp* mlp) {
+  int dev = 0, major = 0, max_smem = 0;
+  MP_CUDA(cudaGetDevice(&dev));
+  MP_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  MP_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (major != 10 || max_smem < Smem::Total + 1024) return MP_OK;
+  std::vector<std::vector<float>> W(5), Bv(5);
+  for (int l = 0; l < 5; ++l) {
+    W[l].resize((size_t)mlp->cin[l] * mlp->cout[l]);
+    Bv[l].resize(mlp->cout[l]);
+    MP_CUDA(cudaMemcpy(W[l].data(), mlp->w[l], W[l].size() * sizeof(float), cudaMemcpyDeviceToHost));
+    MP_CUDA(cudaMemcpy(Bv[l].data(), mlp->bias[l], Bv[l].size() * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  const int cin1 = mlp->cin[1], cin2 = mlp->cin[2], cin3 = mlp->cin[3];
+  std::vector<uint8_t> stream((size_t)kStagesPerTileC * 32768, 0);
+  size_t st = 0;
+  auto stage_ptr = [&]() { return stream.data() + (st++) * 32768; };
+  for (int c = 0; c < 8; ++c)                                               // L1 hidden
+    for (int kb = 0; kb < 2; ++kb)
+      for (int nh = 0; nh < 2; ++nh) pack_tile(stage_ptr(), W[1].data(), cin1, nh * 256, 256, c * 128 + kb * 64);
+  for (int ph = 0; ph < 2; ++ph)                                            // L1 skip: phase A, phase B
+    for (int kb = 0; kb < 4; ++kb)
+      for (int nh = 0; nh < 2; ++nh) pack_tile(stage_ptr(), W[1].data(), cin1, nh * 256, 256, kL0 + ph * 256 + kb * 64);
+  for (int kb = 0; kb < 8; ++kb) pack_tile(stage_ptr(), W[2].data(), cin2, 0, 256, kb * 64);     // L2 hidden
+  for (int ph = 1; ph >= 0; --ph)                                           // L2 skip: phase B, phase A
+    for (int kb = 0; kb < 4; ++kb) pack_tile(stage_ptr(), W[2].data(), cin2, 0, 256, kL1 + ph * 256 + kb * 64);
+  for (int ph = 0; ph < 2; ++ph)                                            // L3 skip: phase A, phase B
+    for (int s2 = 0; s2 < 2; ++s2) {
+      uint8_t* p = stage_ptr();
+      pack_tile(p, W[3].data(), cin3, 0, 128, kL2 + ph * 256 + (2 * s2) * 64);
+      pack_tile(p + 16384, W[3].data(), cin3, 0, 128, kL2 + ph * 256 + (2 * s2 + 1) * 64);
+    }
+  for (int s2 = 0; s2 < 2; ++s2) {                                          // L3 hidden
+    uint8_t* p = stage_ptr();
+    pack_tile(p, W[3].data(), cin3, 0, 128, (2 * s2) * 64);
+    pack_tile(p + 16384, W[3].data(), cin3, 0, 128, (2 * s2 + 1) * 64);
+  }
+  if ((int)st != kStagesPerTileC) {
+    mp_set_error("internal: colour weight stream stage count mismatch");
+    return MP_E_INVALID;
+  }
+  TcPack* pk = new TcPack();
+  memset(pk, 0, sizeof(*pk));
+  pk->res = kResC;
+  pk->kind = 1;
+  mlp->tc = pk;
+  auto upload = [&](const void* src, size_t bytes, void** dptr) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dptr, bytes);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
+  };
+  cudaError_t e = upload(stream.data(), stream.size(), (void**)&pk->w3stream);
+  if (e == cudaSuccess) {   // feature part of layer 0 as fp16 SWIZZLE_128B tiles [n tile 4][K block 8][256 x 64]
+    std::vector<uint8_t> w0t((size_t)kG0NT * kG0cKB * 32768);
+    for (int nt = 0; nt < kG0NT; ++nt)
+      for (int kb = 0; kb < kG0cKB; ++kb)
+        pack_tile(w0t.data() + ((size_t)nt * kG0cKB + kb) * 32768, W[0].data(), mlp->cin[0], nt * kG0TileN, kG0TileN, kb * 64);
+    e = upload(w0t.data(), w0t.size(), (void**)&pk->d_w0t);
+  }
+  const int hid[4] = {0, kL0, kL1, kL2};
+  for (int l = 0; l < 4 && e == cudaSuccess; ++l) {
+    std::vector<float> wz(mlp->cout[l]);
+    const int zcol = hid[l] + kCc;
+    for (int co = 0; co < mlp->cout[l]; ++co) wz[co] = W[l][(size_t)co * mlp->cin[l] + zcol];
+    memcpy(pk->h_bias + side_off(l), Bv[l].data(), Bv[l].size() * sizeof(float));
+    memcpy(pk->h_wz + side_off(l), wz.data(), wz.size() * sizeof(float));
+    if (l == 0) {
+      std::vector<__half> b0h(Bv[0].size()), wz0h(wz.size());
+      for (size_t i = 0; i < b0h.size(); ++i) { b0h[i] = __float2half_rn(Bv[0][i]); wz0h[i] = __float2half_rn(wz[i]); }
+      e = upload(b0h.data(), b0h.size() * sizeof(__half), (void**)&pk->d_bias0);
+      if (e == cudaSuccess) e = upload(wz0h.data(), wz0h.size() * sizeof(__half), (void**)&pk->d_wz0);
+    }
+  }
+  if (e == cudaSuccess) {
+    const int cin4 = mlp->cin[4];
+    std::vector<float> w4h((size_t)kResC * kL3), w4s((size_t)kResC * kCc), w4z(kResC);
+    for (int r = 0; r < kResC; ++r) {
+      for (int j = 0; j < kL3; ++j) w4h[(size_t)r * kL3 + j] = W[4][(size_t)r * cin4 + j];
+      for (int j = 0; j < kCc; ++j) w4s[(size_t)r * kCc + j] = W[4][(size_t)r * cin4 + kL3 + j];
+      w4z[r] = W[4][(size_t)r * cin4 + kL3 + kCc];
+    }
+    e = upload(w4h.data(), w4h.size() * sizeof(float), (void**)&pk->w4h);
+    if (e == cudaSuccess) e = upload(w4s.data(), w4s.size() * sizeof(float), (void**)&pk->w4s);
+    if (e == cudaSuccess) e = upload(w4z.data(), w4z.size() * sizeof(float), (void**)&pk->w4z);
+    if (e == cudaSuccess) e = upload(Bv[4].data(), Bv[4].size() * sizeof(float), (void**)&pk->b4);
+  }
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(g0c_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG0cSmem);
+  if (e != cudaSuccess) {
+    mp_set_error("tc_prepare_colour: %s", cudaGetErrorString(e));
+    mp_tc_release(mlp);
+    return MP_E_CUDA;
+  }
+  mlp->tc_ok = 1;
+  return MP_OK;
+}
+
+int launch_colour(const mp_mlp* mlp, const TcPack* pk, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal, const MpOutDst& dst,
+                  cudaStream_t st) {
+  const long long HW = (long long)feat->H * feat->W;
+  if (feat->C != kCc || HW > 65536) {
+    mp_set_error("colour head: needs a %d-channel map of at most 65536 texels (got %d channels, %lld texels)", kCc, feat->C, HW);
+    return MP_E_INVALID;
+  }
+  if (dst.scatter_vol || dst.n_peers > 0 || !dst.out) {
+    mp_set_error("colour head: plain [3,N] output only");
+    return MP_E_UNSUPPORTED;
+  }
+  if (!feat->g0) {
+    MP_CUDA(cudaMalloc(&feat->g0, (size_t)HW * kL0 * sizeof(__half)));
+    if (!feat->f16) MP_CUDA(cudaMalloc(&feat->f16, (size_t)HW * kCc * sizeof(__half)));
+    if (!feat->s4tex) MP_CUDA(cudaMalloc(&feat->s4tex, (size_t)HW * kResC * sizeof(float)));
+    feat->g0_n = kL0;
+    feat->g0_owner = nullptr;
+  }
+  if (feat->g0_owner != (const void*)mlp || feat->g0_version != feat->version) {
+#ifndef MP_CUDA_EMU
+    g0c_tc_kernel<<<(unsigned)((HW + 127) / 128), kG0Threads, kG0cSmem, st>>>(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s);
+#else
+    MP_EMU_LAUNCH((unsigned)((HW + 127) / 128), kG0Threads, g0c_tc_kernel(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s));
+#endif
+    MP_CUDA(cudaGetLastError());
+    feat->g0_owner = (const void*)mlp;
+    feat->g0_version = feat->version;
+  }
+  TcParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.wstream = pk->w3stream;
+  memcpy(prm.bias_all, pk->h_bias, sizeof(prm.bias_all));
+  memcpy(prm.wz_all, pk->h_wz, sizeof(prm.wz_all));
+  prm.w4h = pk->w4h; prm.w4s = pk->w4s; prm.w4z = pk->w4z; prm.b4 = pk->b4;
+  prm.res = pk->res;
+  prm.last_op = mlp->last_op;
+  prm.H = feat->H; prm.W = feat->W;
+  prm.feat32 = feat->nhwc32;
+  prm.g0 = feat->g0;
+  prm.feat16 = feat->f16;
+  prm.s4tex = feat->s4tex;
+  prm.d_bias0 = pk->d_bias0;
+  prm.d_wz0 = pk->d_wz0;
+  int dev = 0, sms = 148;
+  MP_CUDA(cudaGetDevice(&dev));
+  MP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long tiles = (src.n + kTile - 1) / kTile;
+  const int grid = (int)(tiles < (long long)sms ? tiles : sms);
+#ifndef MP_CUDA_EMU
+  query_tc3c_kernel<<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
+#else
+  MP_EMU_LAUNCH(grid, kThreads, query_tc3c_kernel(prm, src, cal, dst));
+#endif
+  MP_CUDA(cudaGetLastError());
+  return MP_OK;
+}
+
 }  // namespace
 
 int mp_tc_prepare(mp_mlp* mlp) {
   mlp->tc = nullptr;
   mlp->tc_ok = 0;
+  if (colour_shape(mlp)) {
+    // tcgen05 program of the colour head: opt-in until it has been validated on a B200 (the fp32 kernel is the default)
+    static const int on = [] { const char* v = getenv("MONOPORT_B200_TC_NETC"); return v ? atoi(v) : 0; }();
+    return on ? tc_prepare_colour(mlp) : MP_OK;
+  }
   if (!shape_supported(mlp)) return MP_OK;
   int dev = 0, major = 0, max_smem = 0;
   MP_CUDA(cudaGetDevice(&dev));
@@ -1757,6 +2544,7 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     mp_set_error("tcgen05 path not prepared for this head");
     return MP_E_UNSUPPORTED;
   }
+  if (pk->kind == 1) return launch_colour(mlp, pk, feat, src, cal, dst, st);
   if (feat->C != kC) {
     mp_set_error("head expects %d input channels but the feature map has %d (+1 depth)", mlp->channels[0], feat->C);
     return MP_E_INVALID;

@@ -194,11 +194,11 @@ def _run_query_tc(exe, tmp_path, case, n, program, sms):
     import torch
     pts = case["points"][:, :, :n].contiguous()
     cal, feat = case["calib"], case["feat"]
-    hw = feat.shape[2]
+    hw, res = feat.shape[2], case["expected"].shape[0]
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.f32")
     with open(fin, "wb") as f:
-        f.write(struct.pack("8i", 256, hw, hw, n, 1 if cal is not None else 0, 1 if case["proj"] == "perspective" else 0, 1,
-                            spec.LAST_SIGMOID))
+        f.write(struct.pack("8i", feat.shape[1], hw, hw, n, 1 if cal is not None else 0,
+                            1 if case["proj"] == "perspective" else 0, res, case["last_op"]))
         f.write(struct.pack("f", spec.Z_SCALE))
         f.write(struct.pack("12f", *(cal[0, :3, :4].reshape(-1).tolist() if cal is not None else [0.0] * 12)))
         f.write(feat.numpy().tobytes())
@@ -206,9 +206,10 @@ def _run_query_tc(exe, tmp_path, case, n, program, sms):
         for W, b in zip(case["Ws"], case["bs"]):
             f.write(W.numpy().tobytes())
             f.write(b.numpy().tobytes())
-    r = subprocess.run([exe, fin, fout, str(program), str(sms)], capture_output=True, text=True, timeout=900)
+    env = dict(os.environ, MONOPORT_B200_TC_NETC="1")       # the colour head's tensor-core program is opt-in
+    r = subprocess.run([exe, fin, fout, str(program), str(sms)], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
-    return torch.from_numpy(np.fromfile(fout, dtype=np.float32)).reshape(1, n)
+    return torch.from_numpy(np.fromfile(fout, dtype=np.float32)).reshape(res, n)
 
 
 @pytest.mark.parametrize("name,n,program,sms", [
@@ -225,3 +226,16 @@ def test_tcgen05_kernels_match_reference_golden(emu_query_tc, tmp_path, name, n,
     got = _run_query_tc(emu_query_tc, tmp_path, case, n, program, sms)
     err = (got - case["expected"][:, :n]).abs().max().item()
     assert err <= 1e-4, err          # the GPU parity bar for the tensor-core programs (measured on the model: ~2e-5)
+
+
+def test_tcgen05_colour_head_matches_reference_golden(emu_query_tc, tmp_path):
+    """PIFuNetCMLP (513 -> 3, Tanh, 512-channel map): the phase-filled skip operand (four fills of X per tile), eight-K-block
+    G0 GEMM, three fp32 last-layer outputs; two emulated SMs so that every CTA walks several tiles."""
+    from helpers import load_query_case
+    case = load_query_case("c_rot33")
+    n = 300
+    got = _run_query_tc(emu_query_tc, tmp_path, case, n, 0, 2)
+    err = (got - case["expected"][:, :n]).abs().max().item()
+    assert err <= 1e-4, err
+    zero = case["expected"][:, :n] == 0
+    assert (got[zero] == 0).all(), "out-of-image points must be exactly 0"
