@@ -67,8 +67,23 @@ template <class T> static cudaError_t cudaFuncSetAttribute(T*, cudaFuncAttribute
 
 int mp_launch_query_fp32(const mp_mlp*, const mp_feat*, const MpPointSrc&, const MpCalib&, const MpOutDst&, cudaStream_t) { return MP_E_UNSUPPORTED; }
 
+// mp_api.cu's helper (that file holds <<<>>> launches and is not part of this build)
+static void fill_grid_geom(MpPointSrc& s, int res, int node_stride, int r_final) {
+  s.res = res;
+  s.node_stride = node_stride;
+  s.r_final = r_final;
+  s.inv_r = 1.0f / (float)r_final;
+  s.half_inv_r = (float)(1.0 / (2.0 * (double)r_final));
+  for (int a = 0; a < 3; ++a) { s.bmin[a] = -1.f; s.bext[a] = 1.f - (-1.f); }
+}
+
 int main(int argc, char** argv) {
-  if (argc != 5) { fprintf(stderr, "usage: emu_query_tc in.bin out.f32 program sms\n"); return 2; }
+  // optional point source (default: the rows of in.bin):  grid R z0 nz   |   nodes R res
+  //   grid : node centres of planes [z0, z0+nz) of an R^3 grid over [-1,1]^3, generated in-kernel (mp_query_grid)
+  //   nodes: every third node of the res^3 level of an R^3 pyramid, through an index list + a device-side count that
+  //          is smaller than the list capacity, scattered into a res^3 volume (the octree engine's fused path)
+  const char* src_kind = argc >= 6 ? argv[5] : "rows";
+  if (argc < 5) { fprintf(stderr, "usage: emu_query_tc in.bin out.f32 program sms [grid R z0 nz | nodes R res]\n"); return 2; }
   const int program = atoi(argv[3]);
   g_fake_sms = atoi(argv[4]);
   FILE* f = fopen(argv[1], "rb");
@@ -120,25 +135,53 @@ int main(int argc, char** argv) {
   memcpy(cal.m, calib, sizeof(calib));
   cal.perspective = persp && has_calib;
   cal.z_scale = zs;
-  std::vector<float> out((size_t)res * N + 1, -4242.f);
+  long long n_out = N;
+  std::vector<int32_t> nodes;
+  int32_t node_count = 0;
+  std::vector<float> scatter;
+  if (!strcmp(src_kind, "grid")) {
+    const int R = atoi(argv[6]), z0 = atoi(argv[7]), nz = atoi(argv[8]);
+    memset(&src, 0, sizeof(src));
+    src.kind = MP_SRC_GRID;
+    fill_grid_geom(src, R, 1, R);
+    src.z0 = z0;
+    src.n = (long long)nz * R * R;
+    n_out = src.n;
+  } else if (!strcmp(src_kind, "nodes")) {
+    const int R = atoi(argv[6]), lres = atoi(argv[7]);
+    for (int i = 0; i < lres * lres * lres; i += 3) nodes.push_back(i);
+    node_count = (int32_t)nodes.size();
+    nodes.resize(nodes.size() + 300, 0);            // capacity beyond the count: must not be evaluated
+    memset(&src, 0, sizeof(src));
+    src.kind = MP_SRC_NODES;
+    fill_grid_geom(src, lres, (R - 1) / (lres - 1), R);
+    src.nodes = nodes.data();
+    src.count_dev = &node_count;
+    src.n = (long long)nodes.size();
+    n_out = (long long)lres * lres * lres;
+    scatter.assign(n_out, -4242.f);
+  }
+  std::vector<float> out((size_t)res * n_out + 1, -4242.f);
   MpOutDst dst;
-  dst.out = out.data(); dst.ld = N; dst.scatter_vol = nullptr;
+  dst.out = out.data(); dst.ld = n_out; dst.scatter_vol = nullptr;
+  if (!scatter.empty()) { dst.out = nullptr; dst.ld = 0; dst.scatter_vol = scatter.data(); }
   // program 1xx: tensor-core program xx with the fused slab exchange -- three "peer volumes" (host buffers here)
   const int n_peers = program >= 100 ? 3 : 0, peer_off = 5;
-  std::vector<std::vector<float>> peer(n_peers, std::vector<float>((size_t)N + 2 * peer_off, -4242.f));
+  std::vector<std::vector<float>> peer(n_peers, std::vector<float>((size_t)n_out + 2 * peer_off, -4242.f));
   for (int p = 0; p < n_peers; ++p) dst.peer[p] = peer[p].data();
   dst.n_peers = n_peers;
   dst.peer_off = peer_off;
   const int rc = mp_launch_query_tc(&mlp, &feat, src, cal, dst, nullptr, program % 100);
   if (rc != MP_OK) { fprintf(stderr, "mp_launch_query_tc: %s\n", g_err); return 3; }
-  if (out[(size_t)res * N] != -4242.f) { fprintf(stderr, "wrote past the output\n"); return 3; }
+  if (out[(size_t)res * n_out] != -4242.f) { fprintf(stderr, "wrote past the output\n"); return 3; }
+  if (!scatter.empty()) out.assign(scatter.begin(), scatter.end());       // report the scattered volume
   for (int p = 0; p < n_peers; ++p)
     for (long long i = 0; i < (long long)peer[p].size(); ++i) {
-      const float want = (i >= peer_off && i < peer_off + N) ? out[i - peer_off] : -4242.f;
+      const float want = (i >= peer_off && i < peer_off + n_out) ? out[i - peer_off] : -4242.f;
       if (memcmp(&peer[p][i], &want, 4) != 0) { fprintf(stderr, "peer volume %d differs at %lld\n", p, i); return 3; }
     }
   f = fopen(argv[2], "wb");
-  fwrite(out.data(), 4, (size_t)res * N, f);
+  fwrite(out.data(), 4, (size_t)res * n_out, f);
   fclose(f);
   if (const char* dump = getenv("EMU_TC_DUMP")) {       // per-texel products of the G0 kernel, for debugging the model
     if (feat.g0) {

@@ -239,3 +239,60 @@ def test_tcgen05_colour_head_matches_reference_golden(emu_query_tc, tmp_path):
     assert err <= 1e-4, err
     zero = case["expected"][:, :n] == 0
     assert (got[zero] == 0).all(), "out-of-image points must be exactly 0"
+
+
+def _write_tc_input(path, case, n):
+    import struct
+    cal, feat = case["calib"], case["feat"]
+    hw = feat.shape[2]
+    with open(path, "wb") as f:
+        f.write(struct.pack("8i", feat.shape[1], hw, hw, n, 1, 0, 1, case["last_op"]))
+        f.write(struct.pack("f", spec.Z_SCALE))
+        f.write(struct.pack("12f", *cal[0, :3, :4].reshape(-1).tolist()))
+        f.write(feat.numpy().tobytes())
+        f.write(np.zeros(3 * n, np.float32).tobytes())
+        for W, b in zip(case["Ws"], case["bs"]):
+            f.write(W.numpy().tobytes())
+            f.write(b.numpy().tobytes())
+
+
+@pytest.mark.parametrize("program", [2, 3, 103])
+def test_tcgen05_kernels_grid_source(emu_query_tc, tmp_path, program):
+    """mp_query_grid's point source: node centres of a z slab generated in-kernel (103: also stored into the peer volumes
+    at the slab's offset, the fused slab exchange)."""
+    import torch
+    from helpers import load_query_case
+    case = load_query_case("g_smallmap")
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.f32")
+    _write_tc_input(fin, case, 4)
+    R, z0, nz = 13, 3, 5
+    r = subprocess.run([emu_query_tc, fin, fout, str(program), "2", "grid", str(R), str(z0), str(nz)], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = torch.from_numpy(np.fromfile(fout, dtype=np.float32))
+    pts = spec.level_points(spec._grid_coords(R, 1), R, (-1, -1, -1), (1, 1, 1))[z0 * R * R:(z0 + nz) * R * R].t().contiguous()
+    want = spec.query_ref(case["feat"], pts, case["calib"], case["Ws"], case["bs"], spec.LAST_SIGMOID)[0]
+    assert got.numel() == nz * R * R and (got - want).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("program", [2, 3])
+def test_tcgen05_kernels_node_list_source(emu_query_tc, tmp_path, program):
+    """The octree engine's fused path: an index list with a device-side count below the list capacity, values scattered
+    into the level volume; nodes that are not on the list stay untouched."""
+    import torch
+    from helpers import load_query_case
+    case = load_query_case("g_smallmap")
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.f32")
+    _write_tc_input(fin, case, 4)
+    R, res = 33, 9
+    r = subprocess.run([emu_query_tc, fin, fout, str(program), "3", "nodes", str(R), str(res)], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = torch.from_numpy(np.fromfile(fout, dtype=np.float32))
+    idx = torch.arange(0, res ** 3, 3)
+    cc = torch.stack([idx % res, (idx // res) % res, idx // (res * res)], 1) * ((R - 1) // (res - 1))
+    pts = spec.level_points(cc, R, (-1, -1, -1), (1, 1, 1)).t().contiguous()
+    want = torch.full((res ** 3,), -4242.0)
+    want[idx] = spec.query_ref(case["feat"], pts, case["calib"], case["Ws"], case["bs"], spec.LAST_SIGMOID)[0]
+    assert (got - want).abs().max().item() <= 1e-4
+    assert bool((got[want == -4242.0] == -4242.0).all())
