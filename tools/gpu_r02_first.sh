@@ -1,0 +1,27 @@
+#!/bin/bash
+# First GPU call of round 2 (1 GPU): validate what round 1 wrote against the CPU model only.
+#   1. default parity suite (must stay green)
+#   2. the same suite with the tcgen05 program of the colour head switched on (MONOPORT_B200_TC_NETC=1)
+#   3. default bench line, then the configs[2] colour frame rate with the tensor-core colour head
+#   4. per-kernel timeline of a frame (marching-cubes rewrite, scan tail)
+# Second call (gpurun --gpus 2): MONOPORT_B200_TEST_FUSED=1 python -m pytest tests/test_shard_multigpu.py -q ;
+#   torchrun ... bench.py --gpus 2 [--fused-gather]  (A/B of the fused slab exchange against the NCCL all-gather)
+mkdir -p gpurun_out
+T0=$SECONDS
+timeout 300 python -m pytest tests -x -q -m gpu --timeout 200 > gpurun_out/r02_pytest_default.log 2>&1; echo "pytest default rc=$? t=$((SECONDS-T0))s"; tail -2 gpurun_out/r02_pytest_default.log
+MONOPORT_B200_TC_NETC=1 timeout 300 python -m pytest tests -q -m gpu --timeout 200 > gpurun_out/r02_pytest_tc_netc.log 2>&1; echo "pytest tc netC rc=$? t=$((SECONDS-T0))s"; tail -5 gpurun_out/r02_pytest_tc_netc.log
+timeout 300 python bench.py > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err; echo "bench rc=$? t=$((SECONDS-T0))s"
+MONOPORT_B200_TC_NETC=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_tc_netc.json 2> gpurun_out/r02_bench_tc_netc.err; echo "bench tc netC rc=$? t=$((SECONDS-T0))s"
+python - <<'PY'
+import json
+for f in ("r02_bench_default", "r02_bench_tc_netc"):
+    try:
+        d = json.load(open("gpurun_out/%s.json" % f))
+        r = d.get("recon") or {}
+        print(f, d["value"], d["ms_per_step"], d["roofline"]["frac"], "fv fps", r.get("frames_per_s_with_forward_vertices"), "mc fps",
+              r.get("frames_per_s_with_marching_cubes"), "colour fps", r.get("frames_per_s_geometry_plus_netC_colour"))
+    except Exception as e:
+        print(f, "unreadable", e)
+PY
+timeout 120 python tools/recon_trace.py --mc 2>&1 | grep -v Warn > gpurun_out/r02_recon_trace_mc.txt; head -26 gpurun_out/r02_recon_trace_mc.txt
+MONOPORT_B200_TC_NETC=1 timeout 120 python tools/recon_trace.py --color 2>&1 | grep -v Warn > gpurun_out/r02_recon_trace_color_tc.txt; head -12 gpurun_out/r02_recon_trace_color_tc.txt
