@@ -180,6 +180,17 @@ int mp_mcubes_emit(mp_mcubes_t* h, const float* vol_dev, float iso, float* verts
 int mp_forward_vertices(const float* vol_dev, int R, int direction, int64_t* x_dev, int64_t* y_dev, float* z_dev,
                         float* norm_dev, int64_t* n_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Direct rendering of the visible surface with the colour head.  Replaces colorization (RTL/main.py:212-249): vertex i =
+ * (X[i], Y[i], R - Z[i]) of mp_forward_vertices -> world space by mat_color (:201-210) -> netC.query -> pred*0.5+0.5 ->
+ * canvas[X[i], Y[i], :]  ([R,R,3] float32, prepared by the caller), in ONE launch without intermediate tensors.
+ * Needs the tensor-core program of the colour head (opt-in, MONOPORT_B200_TC_NETC=1); MP_E_UNSUPPORTED otherwise --
+ * the binding then takes the generic mp_query_points route.
+ * ------------------------------------------------------------------------------------------- */
+int mp_colorize_surface(mp_mlp_t* mlp, mp_feat_t* feat, const int64_t* x_dev, const int64_t* y_dev, const float* z_dev,
+                        int64_t n, int R, const float* b_min3, const float* b_max3, const float* calib12, int projection,
+                        float z_scale, float* canvas_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

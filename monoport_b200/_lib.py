@@ -61,6 +61,8 @@ SIGNATURES = {
     "mp_mcubes_destroy": (c_int, [c_void_p]),
     "mp_mcubes_count": (c_int, [c_void_p, c_void_p, c_float, P(c_int64), P(c_int64), c_void_p]),
     "mp_mcubes_emit": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
+    "mp_colorize_surface": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, P(c_float), P(c_float),
+                                    P(c_float), c_int, c_float, c_void_p, c_void_p]),
     "mp_forward_vertices": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, P(c_int64),
                                     c_void_p]),
 }

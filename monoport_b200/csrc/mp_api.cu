@@ -332,6 +332,22 @@ extern "C" int mp_query_grid_peers(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0
   return mp_query_dispatch(mlp, feat, src, cal, dst, mode, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// direct rendering of the visible surface with the colour head, one launch (RTL/main.py:212-249)
+// ---------------------------------------------------------------------------------------------
+extern "C" int mp_colorize_surface(mp_mlp_t* mlp, mp_feat_t* feat, const int64_t* x_dev, const int64_t* y_dev, const float* z_dev,
+                                   int64_t n, int R, const float* b_min3, const float* b_max3, const float* calib12, int projection,
+                                   float z_scale, float* canvas_dev, void* stream) {
+  MP_REQUIRE(mlp && feat, "NULL handle");
+  MP_REQUIRE(n >= 0 && R >= 1, "bad sizes n=%lld R=%d", (long long)n, R);
+  if (n == 0) return MP_OK;
+  MP_REQUIRE(x_dev && y_dev && z_dev && canvas_dev && b_min3 && b_max3, "NULL argument");
+  MpCalib cal;
+  mp_fill_calib(cal, calib12, projection, z_scale);
+  return mp_launch_colour_surface(mlp, feat, reinterpret_cast<const long long*>(x_dev), reinterpret_cast<const long long*>(y_dev), z_dev,
+                                  n, R, b_min3, b_max3, cal, canvas_dev, (cudaStream_t)stream);
+}
+
 // Volumes that other processes of the node write into: plain cudaMalloc blocks (exportable; the caching allocators of
 // frameworks hand out sub-blocks, which legacy IPC handles cannot describe) + their 64-byte IPC handle.
 extern "C" int mp_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64) {

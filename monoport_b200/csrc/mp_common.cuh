@@ -208,6 +208,9 @@ int mp_launch_query_fp32(const mp_mlp* mlp, const mp_feat* feat, const MpPointSr
                          const MpOutDst& dst, cudaStream_t st);
 int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
                        const MpOutDst& dst, cudaStream_t st, int program /* 0 auto, 2, 3 */);
+// colour head only: vertices (X, Y, R - Z) of the visible surface -> world -> colour -> canvas[X, Y, :]   (query_tc.cu)
+int mp_launch_colour_surface(const mp_mlp* mlp, mp_feat* feat, const long long* X, const long long* Y, const float* Z, long long n,
+                             int R, const float* b_min3, const float* b_max3, const MpCalib& cal, float* canvas, cudaStream_t st);
 int mp_tc_prepare(mp_mlp* mlp);     // builds mlp->tc; sets tc_ok
 void mp_tc_release(mp_mlp* mlp);
 

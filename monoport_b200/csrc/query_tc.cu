@@ -1553,6 +1553,42 @@ constexpr int kCc = 512;                                   // feature channels o
 constexpr int kResC = 3;
 constexpr int kStagesPerTileC = 32 + 16 + 8 + 8 + 4 + 2;   // L1 hidden, L1 skip (A,B), L2 hidden, L2 skip (B,A), L3 skip (A,B), L3 hidden
 
+// Direct rendering of the visible surface (RTL/main.py:212-249) fused into the colour query: point i is the vertex
+// (X[i], Y[i], R - Z[i]) of forward_vertices mapped to world space by mat_color (RTL/main.py:201-210: diag((b_max-b_min)/R),
+// translation b_min), and its colour pred * 0.5 + 0.5 (:244) is scattered to canvas[X[i], Y[i], :] (:247-248) -- no
+// intermediate point / prediction tensors.  X == nullptr: the ordinary point sources and the [3,N] output.
+struct MpSurfaceSrc {
+  const long long* X;
+  const long long* Y;
+  const float* Z;
+  float scale[3], bmin[3];      // (b_max - b_min) / R and b_min, fp32 like torch's
+  float R;
+  float* canvas;                // [R, R, 3]
+  int canvas_R;
+};
+
+__device__ __forceinline__ PointTaps colour_taps(const MpSurfaceSrc& surf, const MpPointSrc& src, const MpCalib& cal, int H, int W,
+                                                 long long i, long long n) {
+  if (!surf.X) return point_taps(src, cal, H, W, i, n);
+  PointTaps pt;
+  float u = 0.f, v = 0.f, w = 0.f;
+  const bool valid = i < n;
+  if (valid) {
+    const float vx = (float)__ldg(surf.X + i), vy = (float)__ldg(surf.Y + i), vz = __fsub_rn(surf.R, __ldg(surf.Z + i));
+    const float x = __fadd_rn(__fmul_rn(vx, surf.scale[0]), surf.bmin[0]);
+    const float y = __fadd_rn(__fmul_rn(vy, surf.scale[1]), surf.bmin[1]);
+    const float z = __fadd_rn(__fmul_rn(vz, surf.scale[2]), surf.bmin[2]);
+    mp_project(cal, x, y, z, u, v, w);
+  }
+  pt.in_img = valid && (u >= -1.f) && (u <= 1.f) && (v >= -1.f) && (v <= 1.f);
+  const MpTaps t = mp_taps(valid ? u : 0.f, valid ? v : 0.f, H, W);
+  const bool dead = !valid || !(u == u) || !(v == v);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) { pt.off[a] = dead ? 0 : t.off[a]; pt.wgt[a] = dead ? 0.f : t.wgt[a]; }
+  pt.zf = w * cal.z_scale;
+  return pt;
+}
+
 // 16 points of one phase (256 channels starting at phase*256) of the fp16 map -> rows [pbase, pbase+16) of X
 __device__ __forceinline__ void sample_x_phase(const TcParams& prm, uint8_t* smem_x, const PointTaps& pt, int pbase, int lane, int phase) {
   const int cbase = phase * 256 + lane * 8;
@@ -1590,7 +1626,7 @@ __device__ __forceinline__ void sample_x_phase(const TcParams& prm, uint8_t* sme
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
+query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst, MpSurfaceSrc surf) {
   using C = Cfg<1>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1782,7 +1818,7 @@ query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
 #pragma unroll 1
         for (int grp = 0; grp < 4; ++grp) {
           const int pbase = sw * 64 + grp * 16;
-          const PointTaps pt = point_taps(src, cal, prm.H, prm.W, p0 + pbase + (lane & 15), n);
+          const PointTaps pt = colour_taps(surf, src, cal, prm.H, prm.W, p0 + pbase + (lane & 15), n);
           sample_x_phase(prm, smem + Smem::X, pt, pbase, lane, f & 1);
         }
         tc::fence_proxy_async_smem();
@@ -1808,7 +1844,7 @@ query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     const int l8 = lane & 7, qw = lane >> 3;
     uint32_t t_off[4][2], t_wgt[4][2], t_z[4];
     auto compute_taps = [&](long long g) {
-      const PointTaps pt = point_taps(src, cal, prm.H, prm.W, g * kTile + wk * 16 + l16, n);
+      const PointTaps pt = colour_taps(surf, src, cal, prm.H, prm.W, g * kTile + wk * 16 + l16, n);
       const uint32_t o01 = (uint32_t)pt.off[0] | ((uint32_t)pt.off[1] << 16), o23 = (uint32_t)pt.off[2] | ((uint32_t)pt.off[3] << 16);
       const uint32_t w01 = tc::pack_half2(pt.wgt[0], pt.wgt[1]), w23 = tc::pack_half2(pt.wgt[2], pt.wgt[3]);
       const uint32_t zz = tc::pack_half2(pt.zf, pt.zf);
@@ -1916,7 +1952,7 @@ query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         if (step == 6) {
           // per-point scalars of the point this thread owns in the epilogue (TMEM lane `row`)
           {
-            const PointTaps me = point_taps(src, cal, prm.H, prm.W, p0 + row, n);
+            const PointTaps me = colour_taps(surf, src, cal, prm.H, prm.W, p0 + row, n);
             zf = me.zf;
             inimg = me.in_img ? 1.f : 0.f;
             if (wg == 0) {
@@ -1994,9 +2030,16 @@ query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             tc::tcgen05_fence_before();
             warp_arrive_local(bars + B_TILE_DONE, lane);
             const long long i = p0 + row;
-            if (i < n && dst.out) {
+            if (i < n) {
+              if (surf.canvas) {
+                float* px = surf.canvas + ((size_t)__ldg(surf.X + i) * surf.canvas_R + (size_t)__ldg(surf.Y + i)) * 3;
 #pragma unroll
-              for (int r = 0; r < kResC; ++r) dst.out[(long long)r * dst.ld + i] = inimg * mp_last_op(logit[r], prm.last_op);
+                for (int r = 0; r < kResC; ++r)
+                  px[r] = __fadd_rn(__fmul_rn(inimg * mp_last_op(logit[r], prm.last_op), 0.5f), 0.5f);      // RTL/main.py:244
+              } else if (dst.out) {
+#pragma unroll
+                for (int r = 0; r < kResC; ++r) dst.out[(long long)r * dst.ld + i] = inimg * mp_last_op(logit[r], prm.last_op);
+              }
             }
           }
         }
@@ -2282,14 +2325,17 @@ int tc_prepare_colour(mp_mlp* mlp) {
 }
 
 int launch_colour(const mp_mlp* mlp, const TcPack* pk, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal, const MpOutDst& dst,
-                  cudaStream_t st) {
+                  cudaStream_t st, const MpSurfaceSrc* surf_in = nullptr) {
+  MpSurfaceSrc surf;
+  memset(&surf, 0, sizeof(surf));
+  if (surf_in) surf = *surf_in;
   const long long HW = (long long)feat->H * feat->W;
   if (feat->C != kCc || HW > 65536) {
     mp_set_error("colour head: needs a %d-channel map of at most 65536 texels (got %d channels, %lld texels)", kCc, feat->C, HW);
     return MP_E_INVALID;
   }
-  if (dst.scatter_vol || dst.n_peers > 0 || !dst.out) {
-    mp_set_error("colour head: plain [3,N] output only");
+  if (dst.scatter_vol || dst.n_peers > 0 || (!dst.out && !surf.canvas)) {
+    mp_set_error("colour head: [3,N] output or surface canvas only");
     return MP_E_UNSUPPORTED;
   }
   if (!feat->g0) {
@@ -2330,9 +2376,9 @@ int launch_colour(const mp_mlp* mlp, const TcPack* pk, mp_feat* feat, const MpPo
   const long long tiles = (src.n + kTile - 1) / kTile;
   const int grid = (int)(tiles < (long long)sms ? tiles : sms);
 #ifndef MP_CUDA_EMU
-  query_tc3c_kernel<<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
+  query_tc3c_kernel<<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst, surf);
 #else
-  MP_EMU_LAUNCH(grid, kThreads, query_tc3c_kernel(prm, src, cal, dst));
+  MP_EMU_LAUNCH(grid, kThreads, query_tc3c_kernel(prm, src, cal, dst, surf));
 #endif
   MP_CUDA(cudaGetLastError());
   return MP_OK;
@@ -2534,6 +2580,33 @@ void mp_tc_release(mp_mlp* mlp) {
   delete pk;
   mlp->tc = nullptr;
   mlp->tc_ok = 0;
+}
+
+int mp_launch_colour_surface(const mp_mlp* mlp, mp_feat* feat, const long long* X, const long long* Y, const float* Z, long long n,
+                             int R, const float* b_min3, const float* b_max3, const MpCalib& cal, float* canvas, cudaStream_t st) {
+  if (n <= 0) return MP_OK;
+  const TcPack* pk = static_cast<const TcPack*>(mlp->tc);
+  if (!pk || !mlp->tc_ok || pk->kind != 1) {
+    mp_set_error("fused surface colourisation needs the tensor-core program of the colour head (MONOPORT_B200_TC_NETC=1)");
+    return MP_E_UNSUPPORTED;
+  }
+  MpSurfaceSrc surf;
+  memset(&surf, 0, sizeof(surf));
+  surf.X = X; surf.Y = Y; surf.Z = Z;
+  for (int a = 0; a < 3; ++a) {
+    surf.scale[a] = (b_max3[a] - b_min3[a]) / (float)R;          // mat[a,a] = length / resolution  (RTL/main.py:207)
+    surf.bmin[a] = b_min3[a];
+  }
+  surf.R = (float)R;
+  surf.canvas = canvas;
+  surf.canvas_R = R;
+  MpPointSrc src;
+  memset(&src, 0, sizeof(src));
+  src.kind = MP_SRC_ROWS;
+  src.n = n;
+  MpOutDst dst;
+  dst.out = nullptr; dst.ld = 0; dst.scatter_vol = nullptr;
+  return launch_colour(mlp, pk, feat, src, cal, dst, st, &surf);
 }
 
 int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,

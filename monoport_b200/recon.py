@@ -166,7 +166,24 @@ def colorization(netC, feat_tensor_C, X, Y, Z, calib_tensor, norm=None, resoluti
     if norm is not None:
         image[X, Y, :] = ((norm + 1) / 2).clamp(0, 1)
         return image
-    from .modeling.geometry import orthogonal
+    from .modeling.geometry import orthogonal, perspective
+    head = netC.surface_classifier
+    feat = feat_tensor_C[-1][0]
+    if (netC.precision in ("auto", "tc") and not netC.training and X.is_cuda and feat.is_cuda and feat.device == device
+            and head.filter_channels[-1] == 3 and head.tc_supported()):
+        # one launch: vertices -> world (mat_color) -> netC -> pred*0.5+0.5 -> canvas  (tensor-core program of the colour head)
+        n = int(X.numel())
+        if n:
+            Xc, Yc, Zc = X.contiguous(), Y.contiguous(), Z.float().contiguous()
+            with _lib.device_guard(device):
+                fh = netC.feature_handle(feat)
+                proj = _lib.PROJ_PERSPECTIVE if netC.projection is perspective else _lib.PROJ_ORTHOGONAL
+                _lib.check(_lib.load().mp_colorize_surface(
+                    head.handle(), fh.ptr, ctypes.c_void_p(Xc.data_ptr()), ctypes.c_void_p(Yc.data_ptr()),
+                    ctypes.c_void_p(Zc.data_ptr()), n, int(resolution), _lib.f3(b_min), _lib.f3(b_max), _lib.calib12(calib_tensor),
+                    proj, ctypes.c_float(netC.normalizer.scale), ctypes.c_void_p(image.data_ptr()), _lib.stream_ptr(device)),
+                    "mp_colorize_surface")
+        return image
     verts = torch.stack([X.float(), Y.float(), resolution - Z.float()], dim=1)          # RTL/main.py:231-233
     samples = verts.unsqueeze(0).permute(0, 2, 1).contiguous()                          # [1,3,N]
     samples = orthogonal(samples, make_mat_color(resolution, b_min, b_max, device).unsqueeze(0))

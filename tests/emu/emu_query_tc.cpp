@@ -78,7 +78,7 @@ static void fill_grid_geom(MpPointSrc& s, int res, int node_stride, int r_final)
 }
 
 int main(int argc, char** argv) {
-  // optional point source (default: the rows of in.bin):  grid R z0 nz   |   nodes R res
+  // optional point source (default: the rows of in.bin):  grid R z0 nz   |   nodes R res   |   surface R
   //   grid : node centres of planes [z0, z0+nz) of an R^3 grid over [-1,1]^3, generated in-kernel (mp_query_grid)
   //   nodes: every third node of the res^3 level of an R^3 pyramid, through an index list + a device-side count that
   //          is smaller than the list capacity, scattered into a res^3 volume (the octree engine's fused path)
@@ -160,6 +160,25 @@ int main(int argc, char** argv) {
     src.n = (long long)nodes.size();
     n_out = (long long)lres * lres * lres;
     scatter.assign(n_out, -4242.f);
+  }
+  if (!strcmp(src_kind, "surface")) {
+    // surface R: the first N "points" of in.bin are visible-surface vertices (x, y integers; z float, index space);
+    // the colour head renders them into an [R,R,3] canvas of ones (mp_colorize_surface)
+    const int R = atoi(argv[6]);
+    std::vector<long long> X(N), Y(N);
+    std::vector<float> Z(N);
+    for (int i = 0; i < N; ++i) { X[i] = (long long)pts[i]; Y[i] = (long long)pts[(size_t)N + i]; Z[i] = pts[2 * (size_t)N + i]; }
+    std::vector<float> canvas((size_t)R * R * 3 + 1, 1.0f);
+    canvas[(size_t)R * R * 3] = -4242.f;
+    const float bmin[3] = {-1.f, -1.f, -1.f}, bmax[3] = {1.f, 1.f, 1.f};
+    const int rc = mp_launch_colour_surface(&mlp, &feat, X.data(), Y.data(), Z.data(), N, R, bmin, bmax, cal, canvas.data(), nullptr);
+    if (rc != MP_OK) { fprintf(stderr, "mp_launch_colour_surface: %s\n", g_err); return 3; }
+    if (canvas[(size_t)R * R * 3] != -4242.f) { fprintf(stderr, "wrote past the canvas\n"); return 3; }
+    f = fopen(argv[2], "wb");
+    fwrite(canvas.data(), 4, (size_t)R * R * 3, f);
+    fclose(f);
+    mp_tc_release(&mlp);
+    return 0;
   }
   std::vector<float> out((size_t)res * n_out + 1, -4242.f);
   MpOutDst dst;

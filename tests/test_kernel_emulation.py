@@ -296,3 +296,41 @@ def test_tcgen05_kernels_node_list_source(emu_query_tc, tmp_path, program):
     want[idx] = spec.query_ref(case["feat"], pts, case["calib"], case["Ws"], case["bs"], spec.LAST_SIGMOID)[0]
     assert (got - want).abs().max().item() <= 1e-4
     assert bool((got[want == -4242.0] == -4242.0).all())
+
+
+def test_tcgen05_colour_head_fused_surface_rendering(emu_query_tc, tmp_path):
+    """mp_colorize_surface: visible-surface vertices (X, Y, R - Z) -> world (mat_color) -> netC -> pred*0.5+0.5 -> canvas, one
+    launch, against the restatement of RTL/main.py:212-249 driven by the oracle's query."""
+    import struct
+    import torch
+    from helpers import load_query_case
+    case = load_query_case("c_rot33")
+    R, n = 65, 280
+    g = torch.Generator().manual_seed(7)
+    cols = torch.randperm(R * R, generator=g)[:n]                     # at most one vertex per (x, y) column
+    X, Y = cols // R, cols % R
+    Z = torch.rand(n, generator=g) * (R - 1)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.f32")
+    cal, feat = case["calib"], case["feat"]
+    with open(fin, "wb") as f:
+        f.write(struct.pack("8i", feat.shape[1], feat.shape[2], feat.shape[3], n, 1, 0, 3, case["last_op"]))
+        f.write(struct.pack("f", spec.Z_SCALE))
+        f.write(struct.pack("12f", *cal[0, :3, :4].reshape(-1).tolist()))
+        f.write(feat.numpy().tobytes())
+        f.write(torch.stack([X.float(), Y.float(), Z]).numpy().astype(np.float32).tobytes())
+        for W, b in zip(case["Ws"], case["bs"]):
+            f.write(W.numpy().tobytes())
+            f.write(b.numpy().tobytes())
+    r = subprocess.run([emu_query_tc, fin, fout, "0", "2", "surface", str(R)], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, MONOPORT_B200_TC_NETC="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = torch.from_numpy(np.fromfile(fout, dtype=np.float32)).reshape(R, R, 3)
+
+    def query_c(points, calib):
+        return spec.query_ref(feat, points, calib, case["Ws"], case["bs"], spec.LAST_TANH)
+
+    want = spec.colorization_ref(query_c, X, Y, Z, cal, resolution=R)
+    assert (got - want).abs().max().item() <= 1e-4
+    untouched = torch.ones(R, R, dtype=torch.bool)
+    untouched[X, Y] = False
+    assert bool((got[untouched] == 1.0).all()), "pixels without a vertex keep the canvas colour"
