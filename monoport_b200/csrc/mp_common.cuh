@@ -115,6 +115,12 @@ struct MpOutDst {
   float* peer[MP_MAX_PEERS] = {};
   long long peer_off = 0;
   int n_peers = 0;
+  // brick-ordered dense grid (opt-in experiment, tensor-core program v3 only): point i of a MP_SRC_GRID query is node
+  // (i & 7, (i >> 3) & 3, (i >> 5) & 3) of the 8 x 4 x 4 brick i >> 7 (bricks x-fastest over brick_nbx x brick_nby x ...);
+  // its value goes to the node's linear index inside the [brick_nz, R, R] slab.  A tile of 128 points then touches a
+  // few dozen texels instead of a 128-node row's ~200, so the layer-0 taps hit L1.
+  int brick = 0;
+  int brick_nbx = 0, brick_nby = 0, brick_nz = 0;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -12,9 +12,12 @@ timeout 300 python -m pytest tests -x -q -m gpu --timeout 200 > gpurun_out/r02_p
 MONOPORT_B200_TC_NETC=1 timeout 300 python -m pytest tests -q -m gpu --timeout 200 > gpurun_out/r02_pytest_tc_netc.log 2>&1; echo "pytest tc netC rc=$? t=$((SECONDS-T0))s"; tail -5 gpurun_out/r02_pytest_tc_netc.log
 timeout 300 python bench.py > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err; echo "bench rc=$? t=$((SECONDS-T0))s"
 MONOPORT_B200_TC_NETC=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_tc_netc.json 2> gpurun_out/r02_bench_tc_netc.err; echo "bench tc netC rc=$? t=$((SECONDS-T0))s"
+# A/B: brick-ordered dense grid (8x4x4 bricks per tile: layer-0 taps hit L1) against the row order, same box
+MONOPORT_B200_GRID_BRICK=1 timeout 200 python bench.py --no-recon --no-cpu-baseline > gpurun_out/r02_bench_brick.json 2> gpurun_out/r02_bench_brick.err; echo "bench brick rc=$? t=$((SECONDS-T0))s"
+MONOPORT_B200_GRID_BRICK=1 timeout 200 python -m pytest tests/test_query_gpu.py tests/test_engine_gpu.py -q -m gpu -k "grid or full_size or reconstruction or sharded" > gpurun_out/r02_pytest_brick.log 2>&1; tail -2 gpurun_out/r02_pytest_brick.log
 python - <<'PY'
 import json
-for f in ("r02_bench_default", "r02_bench_tc_netc"):
+for f in ("r02_bench_default", "r02_bench_tc_netc", "r02_bench_brick"):
     try:
         d = json.load(open("gpurun_out/%s.json" % f))
         r = d.get("recon") or {}
