@@ -15,6 +15,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 EMU = os.path.join(HERE, "emu")
 
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
+# one OS thread per CUDA thread is slow: the heaviest cases only run with MONOPORT_B200_EMU_FULL=1 (they pass; the default
+# set keeps the CPU tier at a few minutes)
+FULL = os.environ.get("MONOPORT_B200_EMU_FULL", "0") == "1"
+full_only = pytest.mark.skipif(not FULL, reason="heavy emulation case: set MONOPORT_B200_EMU_FULL=1")
 
 
 def _build(tmp, name, extra=()):
@@ -85,6 +89,7 @@ def test_ordered_scan_matches_cumsum(emu_scan, tmp_path, n, vec):
     _check_scan(emu_scan, tmp_path, n, vec)
 
 
+@full_only
 def test_ordered_scan_many_ctas(emu_scan, tmp_path):
     """More CTA totals than threads in the last CTA: every thread of it owns a run of several totals."""
     _check_scan(emu_scan, tmp_path, 2048 * 256 + 4097, 1)
@@ -123,14 +128,15 @@ def _run_octree(exe, tmp_path, mode, field, res, kpts=None):
 
 @pytest.mark.parametrize("mode,field_kind,res", [
     ("faster", "sphere", [9, 17, 33, 65]), ("faster", "two_blobs", [5, 9, 17, 33, 65]), ("faster", "ellipsoid", [9, 17, 33]),
-    ("lossless", "two_blobs", [9, 17, 33]), ("topk", "sphere", [9, 17, 33])])
+    pytest.param("lossless", "two_blobs", [9, 17, 33], marks=full_only), pytest.param("lossless", "sphere", [9, 17], marks=()),
+    pytest.param("topk", "sphere", [9, 17, 33], marks=full_only), pytest.param("topk", "sphere", [9, 17], marks=())])
 def test_octree_kernels_match_restatement(emu_octree, tmp_path, mode, field_kind, res):
     import torch
     from helpers import lookup_query
     R = res[-1]
     field = spec.analytic_volume(R, field_kind)
     fn_o, _ = lookup_query(torch.from_numpy(field))
-    kpts = [0, 1500, 5000] if mode == "topk" else None
+    kpts = [0, 1500, 5000][:len(res)] if mode == "topk" else None
     if mode == "topk":
         want, stats = spec.seg3d_topk_ref(fn_o, res, kpts, return_stats=True)
     else:
@@ -215,7 +221,7 @@ def _run_query_tc(exe, tmp_path, case, n, program, sms):
     ("g_smallmap", 300, 3, 1),      # one CTA walks three tiles: cross-tile software pipelining of the workers, ragged last tile
     ("g_smallmap", 300, 2, 2),      # self-contained program (all five layers per point)
     ("g_smallmap", 200, 103, 1),    # program v3 with the fused slab exchange (peer stores)
-    ("g_rot33", 130, 3, 148),       # 128 x 128 map: 128 CTAs of the G0 GEMM, rotated calibration, points outside the image
+    pytest.param("g_rot33", 130, 3, 148, marks=full_only),   # 128 x 128 map: 128 CTAs of the G0 GEMM, rotated calibration
     ("g_persp", 100, 2, 1),         # perspective projection
     ("g_nocalib", 150, 2, 3),       # calibs=None
 ])
