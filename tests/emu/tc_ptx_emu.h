@@ -130,8 +130,25 @@ inline void exec_mma(const Op& op) {
 }
 
 // executes ONE queued asynchronous operation; returns false when nothing is queued.  Caller holds g_mu.
+// EMU_TC_ORDER=copies (default: bulk copies before MMAs -- a weight stage overwritten too early reaches a late MMA),
+// =mmas (MMAs first), =random[:seed] (either engine; MMAs stay in issue order, copies complete in any order).
 inline bool progress_locked() {
-  if (!g_copies.empty()) {
+  static const int order = [] {
+    const char* v = getenv("EMU_TC_ORDER");
+    if (!v || !strncmp(v, "copies", 6)) return 0;
+    if (!strncmp(v, "mmas", 4)) return 1;
+    const char* c = strchr(v, ':');
+    srand(c ? (unsigned)atoi(c + 1) : 1u);
+    return 2;
+  }();
+  bool copy_first = order == 0 || (order == 2 && (rand() & 1));
+  if (copy_first && g_copies.empty()) copy_first = false;
+  if (!copy_first && g_mmas.empty() && !g_copies.empty()) copy_first = true;
+  if (copy_first && order == 2 && g_copies.size() > 1) {       // any outstanding copy may complete next
+    const size_t k = (size_t)rand() % g_copies.size();
+    std::swap(g_copies[0], g_copies[k]);
+  }
+  if (copy_first) {
     const Op op = g_copies.front();
     g_copies.pop_front();
     memcpy(op.dst, op.src, op.bytes);
