@@ -17,6 +17,10 @@ TOL = {"fp32": 2e-5, "tc": 1e-4, "tc_v2": 1e-4, "tc_v3": 1e-4}
 # stress case: features scaled x4 (N(0,16)) -- fp16 operand rounding scales with the activations; measured 1.07e-4
 # with the tensor-core path (the survey's probe predicted >1e-4 here); fp32 mode stays at 2e-5.  See DESIGN.md §precision.
 TOL_STRESS = {"fp32": 2e-5, "tc": 2e-4, "tc_v2": 2e-4, "tc_v3": 2e-4}
+# colour head on the tensor cores (opt-in, MONOPORT_B200_TC_NETC=1): the bar is 1e-4 on the rendered colour
+# pred * 0.5 + 0.5 (RTL/main.py:244), i.e. 2e-4 on the Tanh output query() returns.  Its fp16 skip operand over 512 channels
+# dominates the error (1.2e-4 worst case over 24 000 points in the torch model of the roundings, DESIGN.md precision).
+TOL_COLOUR = {"fp32": 2e-5, "tc": 2e-4, "tc_v2": 2e-4, "tc_v3": 2e-4}
 
 
 def _modes(net):
@@ -38,7 +42,8 @@ def test_query_matches_reference_golden(name):
         assert isinstance(out, list) and len(out) == 1 and out[0].shape == (1, c["expected"].shape[0], pts.shape[2])
         got = out[0][0].cpu()
         err = (got - c["expected"]).abs().max().item()
-        assert err <= (TOL_STRESS if name == "g_bigfeat" else TOL)[mode], (name, mode, err)
+        tol = TOL_STRESS if name == "g_bigfeat" else (TOL_COLOUR if c["net"] == "C" else TOL)
+        assert err <= tol[mode], (name, mode, err)
         zero = c["expected"] == 0
         assert torch.equal(got[zero], c["expected"][zero]), "out-of-image points must be exactly 0"
 
