@@ -10,6 +10,15 @@
 
 #include "../../include/monoport_b200.h"
 
+// dynamic shared memory of a kernel (tests/emu runs the kernels on the CPU, where it is an array the harness defines)
+#ifdef MP_CUDA_EMU
+#define MP_DYN_SMEM(type, name) extern type name[]
+#define MP_DYN_SMEM_ALIGNED(type, name, bytes) extern type name[]
+#else
+#define MP_DYN_SMEM(type, name) extern __shared__ type name[]
+#define MP_DYN_SMEM_ALIGNED(type, name, bytes) extern __shared__ __align__(bytes) type name[]
+#endif
+
 #define MP_LEAKY_SLOPE 0.01f   // F.leaky_relu default (heads/SurfaceClassifier.py:58)
 #define MP_MAX_LAYERS 8
 

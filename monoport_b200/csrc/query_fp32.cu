@@ -117,7 +117,7 @@ __device__ void dense_layer(const float* __restrict__ wt, const float* __restric
 template <int P>
 __global__ void __launch_bounds__(kThreads, 1)
 query_fp32_kernel(Fp32Params prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
-  extern __shared__ __align__(16) float smem[];
+  MP_DYN_SMEM_ALIGNED(float, smem, 16);
   float* sX = smem;                                  // [c0][P]
   float* sA = sX + (size_t)prm.c0 * P;               // [h_ping][P]
   float* sB = sA + (size_t)prm.h_ping * P;           // [h_pong][P]
@@ -232,7 +232,11 @@ int launch(const Fp32Params& prm, const MpPointSrc& src, const MpCalib& cal, con
   MP_CUDA(cudaFuncSetAttribute(query_fp32_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long tiles = (src.n + P - 1) / P;
   int grid = (int)(tiles < (long long)sm_count ? (tiles > 0 ? tiles : 1) : sm_count);
+#ifndef MP_CUDA_EMU
   query_fp32_kernel<P><<<grid, kThreads, smem, st>>>(prm, src, cal, dst);
+#else
+  MP_EMU_LAUNCH(grid, kThreads, query_fp32_kernel<P>(prm, src, cal, dst));      // tests/emu: CPU model of the execution model
+#endif
   MP_CUDA(cudaGetLastError());
   return MP_OK;
 }

@@ -359,7 +359,7 @@ template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
   using C = Cfg<CG>;
-  extern __shared__ uint8_t smem_raw[];
+  MP_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::Bars);
   float* s_zf = reinterpret_cast<float*>(smem + Smem::Small);
@@ -861,7 +861,7 @@ template <int CG, bool PEERS = false, bool BRICK = false>
 __global__ void __launch_bounds__(kThreads, 1)
 query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
   using C = Cfg<CG>;
-  extern __shared__ uint8_t smem_raw[];
+  MP_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::Bars);
   float* s_zf = reinterpret_cast<float*>(smem + Smem::Small);
@@ -1447,7 +1447,7 @@ constexpr uint32_t kG0Smem = kG0SmemA + kG0SmemB + 1024 /*align*/ + 128 /*barrie
 __global__ void __launch_bounds__(kG0Threads, 1)
 g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half* __restrict__ G, int M,
              __half* __restrict__ F16, float* __restrict__ S4, const float* __restrict__ w4s, int res) {
-  extern __shared__ uint8_t g0_smem_raw[];
+  MP_DYN_SMEM(uint8_t, g0_smem_raw);
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g0_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;
   uint8_t* sB = base + kG0SmemA;
@@ -1679,7 +1679,7 @@ __device__ __forceinline__ void sample_x_phase(const TcParams& prm, uint8_t* sme
 __global__ void __launch_bounds__(kThreads, 1)
 query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst, MpSurfaceSrc surf) {
   using C = Cfg<1>;
-  extern __shared__ uint8_t smem_raw[];
+  MP_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::Bars);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Smem::TmemPtr);
@@ -2113,7 +2113,7 @@ constexpr uint32_t kG0cSmem = kG0cSmemA + kG0cSmemB + 1024 /*align*/ + 128 /*bar
 __global__ void __launch_bounds__(kG0Threads, 1)
 g0c_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half* __restrict__ G, int M,
               __half* __restrict__ F16, float* __restrict__ S4, const float* __restrict__ w4s) {
-  extern __shared__ uint8_t g0_smem_raw[];
+  MP_DYN_SMEM(uint8_t, g0_smem_raw);
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g0_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;
   uint8_t* sB = base + kG0cSmemA;

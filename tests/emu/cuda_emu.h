@@ -46,11 +46,7 @@ inline thread_local dim3 blockDim, gridDim;
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#ifdef MP_EMU_EXTERN_SHARED
-#define __shared__            /* `extern __shared__ T x[]` = an array the harness defines */
-#else
-#define __shared__ static
-#endif
+#define __shared__ static      /* (dynamic shared memory goes through MP_DYN_SMEM: an array the harness defines) */
 #define __constant__
 
 namespace cuda_emu {

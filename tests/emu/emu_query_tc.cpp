@@ -9,7 +9,6 @@
 #include <stdarg.h>
 
 #define MP_EMU_CUDA_TYPES 1
-#define MP_EMU_EXTERN_SHARED 1
 #include "cuda_emu.h"
 
 // ---- device intrinsics the real headers only provide to nvcc -----------------------------------------------------------

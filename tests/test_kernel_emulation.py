@@ -357,3 +357,40 @@ def test_tcgen05_brick_ordered_grid_is_bit_identical(emu_query_tc, tmp_path, pro
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(np.fromfile(fout, dtype=np.float32))
     assert outs[0].size == 3 * 9 * 9 and np.array_equal(outs[0], outs[1])
+
+
+# ---- the exact CUDA-core kernel (query_fp32.cu): default path of the colour head, fallback for every other head shape ----
+@pytest.fixture(scope="module")
+def emu_query_fp32(tmp_path_factory):
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    return _build(str(tmp_path_factory.mktemp("emu_fp32")), "emu_query_fp32",
+                  ["-O2", "-fno-strict-aliasing", "-DMP_CUDA_EMU=1", "-I" + CUDA_INC, "-I" + EMU])
+
+
+@pytest.mark.parametrize("name,n", [("c_rot33", 200), ("c_identity", 100), ("g_persp", 150), ("g_nocalib", 77), ("g_identity", 130)])
+def test_fp32_kernel_matches_reference_golden(emu_query_fp32, tmp_path, name, n):
+    import struct
+    import torch
+    from helpers import load_query_case
+    case = load_query_case(name)
+    pts = case["points"][:, :, :n].contiguous()
+    cal, feat = case["calib"], case["feat"]
+    res = case["expected"].shape[0]
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.f32")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("8i", feat.shape[1], feat.shape[2], feat.shape[3], n, 1 if cal is not None else 0,
+                            1 if case["proj"] == "perspective" else 0, res, case["last_op"]))
+        f.write(struct.pack("f", spec.Z_SCALE))
+        f.write(struct.pack("12f", *(cal[0, :3, :4].reshape(-1).tolist() if cal is not None else [0.0] * 12)))
+        f.write(feat.numpy().tobytes())
+        f.write(pts[0].numpy().tobytes())
+        for W, b in zip(case["Ws"], case["bs"]):
+            f.write(W.numpy().tobytes())
+            f.write(b.numpy().tobytes())
+    r = subprocess.run([emu_query_fp32, fin, fout], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = torch.from_numpy(np.fromfile(fout, dtype=np.float32)).reshape(res, n)
+    want = case["expected"][:, :n]
+    assert (got - want).abs().max().item() <= 2e-5          # the GPU bar of the fp32 mode
+    assert torch.equal(got[want == 0], want[want == 0]), "out-of-image points must be exactly 0"
