@@ -11,6 +11,7 @@
 //         their up to 3 vertices + 15 face corners over the whole CTA (one short dependent chain per thread instead of
 //         one thread walking a whole cell).
 #include "mp_common.cuh"
+#include <stdlib.h>
 #include "mcubes_kernels.cuh"
 
 using namespace mcubes;
@@ -66,8 +67,10 @@ extern "C" int mp_mcubes_count(mp_mcubes_t* h, const float* vol_dev, float iso, 
                                void* stream) {
   MP_REQUIRE(h && vol_dev && n_verts && n_faces, "NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
-  classify_kernel<<<dim3((unsigned)h->D, (unsigned)((h->H + kClassRows - 1) / kClassRows)), dim3(32, kClassRows), 0, st>>>(
-      vol_dev, h->code, h->cases, h->D, h->H, h->W, iso);
+  static const int fast = [] { const char* v = getenv("MONOPORT_B200_MC_FAST"); return v ? atoi(v) : 0; }();
+  const dim3 cgrid((unsigned)h->D, (unsigned)((h->H + kClassRows - 1) / kClassRows)), cblock(32, kClassRows);
+  if (fast) classify_fast_kernel<<<cgrid, cblock, 0, st>>>(vol_dev, h->code, h->cases, h->D, h->H, h->W, iso);
+  else classify_kernel<<<cgrid, cblock, 0, st>>>(vol_dev, h->code, h->cases, h->D, h->H, h->W, iso);
   MP_CUDA(cudaGetLastError());
   CountF f{h->code};
   OffsetsEmit em{h->voff};

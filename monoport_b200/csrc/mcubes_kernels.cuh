@@ -57,6 +57,72 @@ classify_kernel(const float* __restrict__ vol, uint8_t* __restrict__ code, uint8
   }
 }
 
+// Opt-in variant (MONOPORT_B200_MC_FAST=1, to be timed on a B200): ~98 % of the 32-node chunks of an occupancy volume lie
+// entirely inside or outside the surface.  A warp first loads every node's own column of the four neighbouring rows (4
+// loads per node, plus column x0+32 by lane 0) and votes; a uniform chunk stores 32 zero code bytes and is done (its case
+// bytes are never read: no triangles).  Only mixed chunks take the full eight-corner path of classify_kernel.
+__global__ void __launch_bounds__(32 * kClassRows)
+classify_fast_kernel(const float* __restrict__ vol, uint8_t* __restrict__ code, uint8_t* __restrict__ cases, int D, int H,
+                     int W, float iso) {
+  const int z = blockIdx.x, y = blockIdx.y * kClassRows + threadIdx.y;
+  if (y >= H) return;                    // (a whole warp: blockDim.x == 32)
+  const int lane = threadIdx.x;
+  const bool yi = y + 1 < H, zi = z + 1 < D;
+  const size_t row = ((size_t)z * H + y) * W;
+  const float* r00 = vol + row;
+  const float* r01 = r00 + (yi ? (size_t)W : 0);
+  const float* r10 = r00 + (zi ? (size_t)H * W : 0);
+  const float* r11 = r10 + (yi ? (size_t)W : 0);
+  for (int x0 = 0; x0 < W; x0 += 32) {
+    const int x = x0 + lane;
+    const int xc = min(x, W - 1);                        // lanes beyond the row repeat its last node
+    const int xe = min(x0 + 32, W - 1);                  // the column after the chunk (lane 0 adds it to the vote)
+    bool any_in = false, all_in = true;
+    {
+      const bool a = __ldg(r00 + xc) > iso, b = __ldg(r01 + xc) > iso, c = __ldg(r10 + xc) > iso, d = __ldg(r11 + xc) > iso;
+      any_in = a | b | c | d;
+      all_in = a & b & c & d;
+      if (lane == 0) {
+        const bool e = __ldg(r00 + xe) > iso, f = __ldg(r01 + xe) > iso, g = __ldg(r10 + xe) > iso, h = __ldg(r11 + xe) > iso;
+        any_in |= e | f | g | h;
+        all_in &= e & f & g & h;
+      }
+    }
+    const bool uniform = !__any_sync(0xffffffffu, any_in) || __all_sync(0xffffffffu, all_in);      // warp-uniform
+    if (uniform) {
+      if (x < W) code[row + x] = 0;
+      continue;
+    }
+    if (x < W) {
+      const bool xi = x + 1 < W;
+      const int x1 = xi ? x + 1 : x;
+      const bool b000 = __ldg(r00 + x) > iso, b001 = __ldg(r00 + x1) > iso;
+      const bool b010 = __ldg(r01 + x) > iso, b011 = __ldg(r01 + x1) > iso;
+      const bool b100 = __ldg(r10 + x) > iso, b101 = __ldg(r10 + x1) > iso;
+      const bool b110 = __ldg(r11 + x) > iso, b111 = __ldg(r11 + x1) > iso;
+      uint8_t c = 0;
+      if (xi && (b001 != b000)) c |= 1;
+      if (yi && (b010 != b000)) c |= 2;
+      if (zi && (b100 != b000)) c |= 4;
+      uint8_t cs = 0;
+      if (xi && yi && zi) {
+        int k = b000 ? 1 : 0;
+        k |= b001 ? 2 : 0;
+        k |= b010 ? 4 : 0;
+        k |= b011 ? 8 : 0;
+        k |= b100 ? 16 : 0;
+        k |= b101 ? 32 : 0;
+        k |= b110 ? 64 : 0;
+        k |= b111 ? 128 : 0;
+        cs = (uint8_t)k;
+        c |= (uint8_t)(c_mc_ntri[k] << 3);
+      }
+      code[row + x] = c;
+      cases[row + x] = cs;
+    }
+  }
+}
+
 struct CountF {    // low 32: vertices owned by node i, high 32: triangles of cell i
   const uint8_t* code;       // cudaMalloc'ed (8-byte aligned)
   static constexpr bool kVec8 = true;

@@ -140,6 +140,8 @@ inline int __syncthreads_or(int pred) {
   return r;
 }
 
+inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0u; }
+inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcg(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -45,8 +45,11 @@ int main(int argc, char** argv) {
   unsigned long long total[2] = {0, 0};
 
   // ---- mp_mcubes_count
-  cuda_emu::launch(dim3((unsigned)D, (unsigned)((H + kClassRows - 1) / kClassRows)), dim3(32, kClassRows),
-                   [&] { classify_kernel(vol, code.data(), cases.data(), D, H, W, iso); });
+  const bool fast = getenv("MONOPORT_B200_MC_FAST") && atoi(getenv("MONOPORT_B200_MC_FAST"));
+  cuda_emu::launch(dim3((unsigned)D, (unsigned)((H + kClassRows - 1) / kClassRows)), dim3(32, kClassRows), [&] {
+    if (fast) classify_fast_kernel(vol, code.data(), cases.data(), D, H, W, iso);
+    else classify_kernel(vol, code.data(), cases.data(), D, H, W, iso);
+  });
   CountF f{code.data()};
   OffsetsEmit em{voff.data()};
   cuda_emu::launch(dim3(nb), dim3(mpscan::kThreads),

@@ -27,4 +27,7 @@ for f in ("r02_bench_default", "r02_bench_tc_netc", "r02_bench_brick"):
         print(f, "unreadable", e)
 PY
 timeout 120 python tools/recon_trace.py --mc 2>&1 | grep -v Warn > gpurun_out/r02_recon_trace_mc.txt; head -26 gpurun_out/r02_recon_trace_mc.txt
+# A/B: classify with the uniform-chunk fast path (MONOPORT_B200_MC_FAST=1), parity first
+MONOPORT_B200_MC_FAST=1 timeout 120 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "marching or reconstruction" > gpurun_out/r02_pytest_mc_fast.log 2>&1; tail -2 gpurun_out/r02_pytest_mc_fast.log
+MONOPORT_B200_MC_FAST=1 timeout 120 python tools/recon_trace.py --mc 2>&1 | grep -v Warn | grep -E "classify|wall" > gpurun_out/r02_recon_trace_mc_fast.txt; cat gpurun_out/r02_recon_trace_mc_fast.txt
 MONOPORT_B200_TC_NETC=1 timeout 120 python tools/recon_trace.py --color 2>&1 | grep -v Warn > gpurun_out/r02_recon_trace_color_tc.txt; head -12 gpurun_out/r02_recon_trace_color_tc.txt
