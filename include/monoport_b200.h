@@ -79,6 +79,9 @@ int mp_mlp_tc_supported(const mp_mlp_t* h);
 typedef struct mp_feat mp_feat_t;
 int mp_feat_create(int C, int H, int W, mp_feat_t** out);
 int mp_feat_upload(mp_feat_t* h, const float* nchw, int on_device, void* stream);
+/* same for a map that is already channel-last ([H,W,C] fp32, device memory -- a torch.channels_last tensor): one copy, no
+ * transposing kernel */
+int mp_feat_upload_nhwc(mp_feat_t* h, const float* nhwc_dev, void* stream);
 int mp_feat_destroy(mp_feat_t* h);
 
 /* calib: 12 host floats = rows 0..2 of the [4,4] / [3,4] calibration (R | t), or NULL for calibs=None

@@ -186,6 +186,16 @@ extern "C" int mp_feat_upload(mp_feat_t* h, const float* nchw, int on_device, vo
   return MP_OK;
 }
 
+// The map is already channel-last on the device (a torch.channels_last tensor: what a channels_last encoder emits,
+// SURVEY.md §8f-3): one device-to-device copy instead of the transposing kernel.
+extern "C" int mp_feat_upload_nhwc(mp_feat_t* h, const float* nhwc_dev, void* stream) {
+  MP_REQUIRE(h && nhwc_dev, "NULL handle or data");
+  const size_t n = (size_t)h->C * h->H * h->W;
+  MP_CUDA(cudaMemcpyAsync(h->nhwc32, nhwc_dev, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  h->version += 1;
+  return MP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // query
 // ---------------------------------------------------------------------------------------------

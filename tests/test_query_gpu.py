@@ -237,3 +237,19 @@ def test_calib_cache_follows_inplace_updates():
     assert not torch.equal(a, b)
     fresh = build_net(c).query([[feat]], pts, calibs=cal.clone())[0]
     assert torch.equal(b, fresh)
+
+
+def test_channels_last_feature_map_gives_identical_results():
+    """A torch.channels_last feature map (what a channels_last encoder emits) is taken as is -- one copy instead of the
+    transposing kernel -- and must give bit-identical outputs."""
+    c = load_query_case("g_rot33")
+    net = build_net(c)
+    pts, cal = c["points"][:, :, :3000].cuda(), c["calib"].cuda()
+    feat = c["feat"].cuda()
+    feat_cl = feat.contiguous(memory_format=torch.channels_last)
+    assert not feat_cl.is_contiguous() and torch.equal(feat_cl, feat)
+    for mode in _modes(net):
+        net.precision = mode
+        a = net.query([[feat]], pts, calibs=cal)[0].clone()
+        b = net.query([[feat_cl]], pts, calibs=cal)[0].clone()
+        assert torch.equal(a, b), mode
