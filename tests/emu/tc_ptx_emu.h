@@ -33,9 +33,22 @@ inline uint8_t* g_smem = nullptr;          // base of the dynamic shared memory 
 inline uint32_t g_smem_bytes = 0;
 inline std::atomic<unsigned long long> g_events{0};   // bumped by every state change (deadlock watchdog)
 inline std::atomic<int> g_waiting{0};
+// work counters (EMU_TC_STATS=1 prints them at exit): what the program actually executes per launch, to set against the
+// ALGORITHMIC flops the roofline is quoted on
+struct Stats { unsigned long long mma_flop = 0, mma_ops = 0, copy_bytes = 0, copies = 0, tmem_ld = 0, tmem_st = 0; };
+inline Stats g_stats;
+inline void print_stats() {
+  fprintf(stderr, "[tc emu stats] mma: %llu ops, %.3f GFLOP | bulk copies: %llu, %.3f MB | tcgen05.ld x32: %llu  tcgen05.st x16: %llu\n",
+          g_stats.mma_ops, g_stats.mma_flop * 1e-9, g_stats.copies, g_stats.copy_bytes * 1e-6, g_stats.tmem_ld, g_stats.tmem_st);
+}
+inline void stats_init() {
+  static const bool on = [] { const bool e = getenv("EMU_TC_STATS") != nullptr; if (e) atexit(print_stats); return e; }();
+  (void)on;
+}
 inline bool eager() { static const bool e = getenv("EMU_TC_EAGER") != nullptr; return e; }   // debugging aid: no deferral
 
 inline void set_smem(void* base, uint32_t bytes) {
+  stats_init();
   if ((uintptr_t)base & 1023) { fprintf(stderr, "tc emu: shared memory base must be 1024-byte aligned\n"); abort(); }
   g_smem = (uint8_t*)base;
   g_smem_bytes = bytes;
@@ -79,6 +92,8 @@ inline void exec_mma(const Op& op) {
   const uint32_t M = ((op.idesc >> 24) & 0x1F) << 4, N = ((op.idesc >> 17) & 0x3F) << 3;
   if (M != 128 || N == 0 || N > 256 || (N & 15)) { fprintf(stderr, "tc emu: unsupported MMA shape %ux%u\n", M, N); abort(); }
   if (((op.idesc >> 4) & 3) != 1 || ((op.idesc >> 7) & 7) != 0 || ((op.idesc >> 10) & 7) != 0) { fprintf(stderr, "tc emu: idesc formats\n"); abort(); }
+  g_stats.mma_ops++;
+  g_stats.mma_flop += 2ull * 128 * N * 16;
   const uint32_t dcol = op.d_tmem & 0xFFFF;
   if ((op.d_tmem >> 16) != 0 || dcol + N > kCols) { fprintf(stderr, "tc emu: bad accumulator address %08x (N=%u)\n", op.d_tmem, N); abort(); }
   auto desc_fields = [](uint64_t d, uint32_t& start, uint32_t& sbo) {
@@ -152,6 +167,8 @@ inline bool progress_locked() {
     const Op op = g_copies.front();
     g_copies.pop_front();
     memcpy(op.dst, op.src, op.bytes);
+    g_stats.copies++;
+    g_stats.copy_bytes += op.bytes;
     const uint64_t w = *op.bar;
     if (mb_tx(w) < op.bytes) { fprintf(stderr, "tc emu: complete_tx without a matching expect_tx\n"); abort(); }
     *op.bar = mb_make(mb_pending(w), mb_count(w), mb_tx(w) - op.bytes, mb_phase(w));
@@ -301,6 +318,7 @@ inline void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   const uint32_t row = tmem_row_checked(taddr), col = taddr & 0xFFFF;
   if (col + 32 > emu::kCols) { fprintf(stderr, "tc emu: tcgen05.ld beyond column 512\n"); abort(); }
   std::lock_guard<std::mutex> g(emu::g_mu);
+  if ((cuda_emu::linear_tid() & 31) == 0) emu::g_stats.tmem_ld++;
   for (int j = 0; j < 32; ++j) r[j] = emu::g_tmem[row][col + j];
 }
 inline void tmem_ld_wait() {}
@@ -308,6 +326,7 @@ inline void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   const uint32_t row = tmem_row_checked(taddr), col = taddr & 0xFFFF;
   if (col + 16 > emu::kCols) { fprintf(stderr, "tc emu: tcgen05.st beyond column 512\n"); abort(); }
   std::lock_guard<std::mutex> g(emu::g_mu);
+  if ((cuda_emu::linear_tid() & 31) == 0) emu::g_stats.tmem_st++;
   for (int j = 0; j < 16; ++j) emu::g_tmem[row][col + j] = r[j];
 }
 inline void tmem_st_wait() {}
