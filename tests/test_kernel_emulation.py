@@ -58,6 +58,15 @@ def test_mcubes_kernels_match_oracle_on_analytic_volumes(emu_mcubes, tmp_path, k
     v, f = _run_mcubes(emu_mcubes, vol, tmp_path, fast=fast)
     assert np.array_equal(f, F), "topology must be bit-exact"
     assert v.shape == V.shape and np.array_equal(v, V)
+    if kind == "sphere":
+        # independent of the restatement: the field is 0.5 + 4 (0.6 - |p|), so every vertex must sit on the sphere of radius
+        # 0.6 up to the error of interpolating |p| linearly along a grid edge (h^2 / 8r), and the mesh must be closed
+        p = (v + 0.5) / R * 2.0 - 1.0
+        assert np.abs(np.linalg.norm(p, axis=1) - 0.6).max() < (2.0 / R) ** 2 / (8 * 0.6) * 1.5
+        e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]).astype(np.int64)
+        key, rkey = e[:, 0] * len(v) + e[:, 1], e[:, 1] * len(v) + e[:, 0]
+        assert len(np.unique(key)) == len(key) and np.array_equal(np.sort(key), np.sort(rkey))       # closed, consistently oriented
+        assert len(v) - len(np.unique(np.minimum(key, rkey))) + len(f) == 2                          # Euler characteristic of a sphere
 
 
 @pytest.mark.parametrize("shape", [(20, 17, 23), (9, 40, 35), (2, 2, 2), (3, 70, 2), (3, 5, 131), (2, 3, 257), (2, 9, 128),
