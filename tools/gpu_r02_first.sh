@@ -31,3 +31,8 @@ timeout 120 python tools/recon_trace.py --mc 2>&1 | grep -v Warn > gpurun_out/r0
 MONOPORT_B200_MC_FAST=1 timeout 120 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "marching or reconstruction" > gpurun_out/r02_pytest_mc_fast.log 2>&1; tail -2 gpurun_out/r02_pytest_mc_fast.log
 MONOPORT_B200_MC_FAST=1 timeout 120 python tools/recon_trace.py --mc 2>&1 | grep -v Warn | grep -E "classify|wall" > gpurun_out/r02_recon_trace_mc_fast.txt; cat gpurun_out/r02_recon_trace_mc_fast.txt
 MONOPORT_B200_TC_NETC=1 timeout 120 python tools/recon_trace.py --color 2>&1 | grep -v Warn > gpurun_out/r02_recon_trace_color_tc.txt; head -12 gpurun_out/r02_recon_trace_color_tc.txt
+# where a dense tile's 66 k cycles go in the FINAL program v3 (in-kernel clock64 attribution + one traced tile): decides which of
+# the ideas of DESIGN.md §5 to try first
+MONOPORT_B200_TC_PROF=1 timeout 120 python tools/tc_prof.py 257 2>&1 | grep "tc prof" > gpurun_out/r02_tc_v3_final_inkernel_cycles.txt; cat gpurun_out/r02_tc_v3_final_inkernel_cycles.txt
+MONOPORT_B200_TC_TRACE=1 timeout 120 python tools/tc_prof.py 257 2>&1 | grep "tc trace" > gpurun_out/r02_tc_v3_final_trace_tile8.txt; wc -l gpurun_out/r02_tc_v3_final_trace_tile8.txt
+MONOPORT_B200_GRID_BRICK=1 MONOPORT_B200_TC_PROF=1 timeout 120 python tools/tc_prof.py 257 2>&1 | grep "tc prof" > gpurun_out/r02_tc_v3_brick_inkernel_cycles.txt; grep -E "total|h0ready|wfull" gpurun_out/r02_tc_v3_brick_inkernel_cycles.txt
