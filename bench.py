@@ -257,9 +257,9 @@ def run_ours(args):
     def step(i):
         f = feats[i % len(feats)]
         if fused:
-            query_grid_fused(net, f, cal, R, B_MIN, B_MAX, peers)
+            query_grid_fused(net, f, cal_cpu, R, B_MIN, B_MAX, peers)
             return
-        net.query_grid(f, cal, R, B_MIN, B_MAX, z0=z0, nz=nz, out=slab)
+        net.query_grid(f, cal_cpu, R, B_MIN, B_MAX, z0=z0, nz=nz, out=slab)
         if world > 1:
             gather_slabs(slab, R, rank, world, out=full)
 
@@ -279,10 +279,10 @@ def run_ours(args):
         fh = net.feature_handle(f)                 # channel-last repack kernel (part of the step)
         kev[i][0].record()
         if fused:
-            query_grid_fused(net, f, cal, R, B_MIN, B_MAX, peers)      # kernel with peer stores + barrier
+            query_grid_fused(net, f, cal_cpu, R, B_MIN, B_MAX, peers)      # kernel with peer stores + barrier
             kev[i][1].record()
         else:
-            net.query_grid(f, cal, R, B_MIN, B_MAX, z0=z0, nz=nz, out=slab)
+            net.query_grid(f, cal_cpu, R, B_MIN, B_MAX, z0=z0, nz=nz, out=slab, fh=fh)
             kev[i][1].record()
             if world > 1:
                 gather_slabs(slab, R, rank, world, out=full)

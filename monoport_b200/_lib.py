@@ -102,18 +102,61 @@ def check(rc, what=""):
 
 
 _calib_cache = threading.local()
+_scope = threading.local()
+
+# Identity-keyed caches (feature uploads, device-resident calibs) compare (data_ptr, _version).  Writes that bypass
+# the version counter (CUDA-graph static buffers, custom kernels, NCCL receives into a fixed tensor) are invisible to
+# that key, so it is only trusted (a) inside a `frame_scope()` -- one engine call, during which the caller's tensors
+# cannot legitimately change -- or (b) when the application opts in (TRUST_TENSOR_IDENTITY / env
+# MONOPORT_B200_TRUST_IDENTITY=1 / MonoPortNet.feature_cache = True).
+TRUST_TENSOR_IDENTITY = os.environ.get("MONOPORT_B200_TRUST_IDENTITY", "0") == "1"
+_scope_counter = [0]
+_scope_lock = threading.Lock()
+
+
+class frame_scope:
+    """`with frame_scope():` -- all queries issued by this thread inside the block belong to ONE frame: the first one
+    uploads the feature map / reads the calib, the others may reuse them when (data_ptr, _version) are unchanged."""
+
+    def __enter__(self):
+        with _scope_lock:
+            _scope_counter[0] += 1
+            sid = _scope_counter[0]
+        self._prev = getattr(_scope, "id", 0)
+        _scope.id = sid
+        return self
+
+    def __exit__(self, *exc):
+        _scope.id = self._prev
+        return False
+
+
+def current_scope():
+    return getattr(_scope, "id", 0)
+
+
+def tensor_identity(t):
+    """(data_ptr, version, shape, dtype) or None when the tensor has no version counter (inference-mode tensors raise
+    on `_version`): None never matches, which forces the safe path."""
+    try:
+        return (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
+    except RuntimeError:
+        return None
 
 
 def calib12(calib):
     """[1,4,4] / [4,4] / [3,4] torch tensor (any device) or None -> ctypes float[12] or None.
-    The last conversion is cached per thread: a device-resident calib costs a blocking 48-byte read-back, and the demo
-    loop passes the same tensor for many frames.  The cache holds a reference to that tensor, so its storage cannot be
-    recycled for another tensor while (data_ptr, _version) is used as the identity."""
+    A host tensor is converted on every call (microseconds).  A device-resident calib costs a blocking 48-byte
+    read-back; that one is reused only under the identity policy above (same frame scope, or opt-in), and the cache
+    keeps a reference to the tensor so its storage cannot be recycled for another tensor meanwhile."""
     if calib is None:
         return None
-    key = (calib.data_ptr(), calib._version, tuple(calib.shape), calib.dtype)
-    if getattr(_calib_cache, "key", None) == key:
-        return _calib_cache.val
+    on_dev = calib.device.type != "cpu"
+    key = tensor_identity(calib) if on_dev else None
+    if key is not None and getattr(_calib_cache, "key", None) == key:
+        sid = current_scope()
+        if TRUST_TENSOR_IDENTITY or (sid != 0 and getattr(_calib_cache, "scope", -1) == sid):
+            return _calib_cache.val
     c = calib.detach()
     if c.dim() == 3:
         if c.shape[0] != 1:
@@ -121,7 +164,8 @@ def calib12(calib):
         c = c[0]
     c = c[:3, :4].to("cpu", dtype=__import__("torch").float32).contiguous().reshape(-1).tolist()
     val = (c_float * 12)(*c)
-    _calib_cache.key, _calib_cache.ref, _calib_cache.val = key, calib, val
+    if on_dev:
+        _calib_cache.key, _calib_cache.ref, _calib_cache.val, _calib_cache.scope = key, calib, val, current_scope()
     return val
 
 

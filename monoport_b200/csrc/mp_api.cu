@@ -2,6 +2,7 @@
 // See include/monoport_b200.h for the contract of every function and the reference interface it replaces.
 #include "mp_common.cuh"
 #include <stdlib.h>
+#include <atomic>
 
 static thread_local char g_err[512] = "";
 
@@ -81,6 +82,8 @@ extern "C" int mp_mlp_create(int n_layers, const int* channels, const float* con
   h->n_layers = n_layers;
   h->skip = skip ? 1 : 0;
   h->last_op = last_op;
+  static std::atomic<unsigned long long> next_gen{1};
+  h->gen = next_gen.fetch_add(1);
   cudaGetDevice(&h->device);
   for (int l = 0; l <= n_layers; ++l) h->channels[l] = channels[l];
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -219,18 +222,6 @@ void mp_fill_grid_geom(MpPointSrc& s, int res, int node_stride, int r_final, con
   }
 }
 
-// MONOPORT_B200_GRID_BRICK=1 (opt-in experiment): dense-grid queries of the default tensor-core program walk the slab in
-// 8 x 4 x 4 bricks instead of rows (same values, same output layout; see MpOutDst)
-static void maybe_brick(const mp_mlp* mlp, int mode, MpPointSrc& src, MpOutDst& dst, int R, int nz) {
-  static const int on = [] { const char* v = getenv("MONOPORT_B200_GRID_BRICK"); return v ? atoi(v) : 0; }();
-  if (!on || !mlp->tc_ok || !(mode == MP_MODE_TC || mode == MP_MODE_AUTO || mode == MP_MODE_TC_V3)) return;
-  dst.brick = 1;
-  dst.brick_nbx = (R + 7) / 8;
-  dst.brick_nby = (R + 3) / 4;
-  dst.brick_nz = nz;
-  src.n = (long long)dst.brick_nbx * dst.brick_nby * ((nz + 3) / 4) * 128;
-}
-
 int mp_query_dispatch(mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal, const MpOutDst& dst,
                       int mode, cudaStream_t st) {
   if (mode == MP_MODE_AUTO) mode = mlp->tc_ok ? MP_MODE_TC : MP_MODE_FP32;
@@ -321,7 +312,6 @@ extern "C" int mp_query_grid(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0, int 
   mp_fill_calib(cal, calib12, projection, z_scale);
   MpOutDst dst;
   dst.out = out_dev; dst.ld = src.n; dst.scatter_vol = nullptr;
-  maybe_brick(mlp, mode, src, dst, R, nz);
   // (the tensor-core program never depends on the slab size, so a z-sharded volume is bit-identical to the single-GPU
   // volume for every rank count)
   return mp_query_dispatch(mlp, feat, src, cal, dst, mode, (cudaStream_t)stream);
@@ -353,7 +343,6 @@ extern "C" int mp_query_grid_peers(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0
   for (int p = 0; p < n_peers; ++p) dst.peer[p] = peer_vols[p];
   dst.n_peers = n_peers;
   dst.peer_off = (long long)z0 * R * R;        // the slab's position inside every full [R,R,R] volume
-  maybe_brick(mlp, mode, src, dst, R, nz);
   return mp_query_dispatch(mlp, feat, src, cal, dst, mode, (cudaStream_t)stream);
 }
 

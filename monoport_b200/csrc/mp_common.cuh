@@ -61,6 +61,7 @@ struct mp_mlp {
   void* tc;
   int tc_ok;
   int device;
+  unsigned long long gen;            // unique per mp_mlp_create (process-wide counter, never 0): keys per-feature caches
 };
 
 struct mp_feat {
@@ -70,12 +71,13 @@ struct mp_feat {
   int device;
   // layer-0 pre-activation per texel, G0 = W0[:, :C] . F  ([H*W][g0_n] fp16), built lazily by the tcgen05 v3 path
   // (bilinear sampling is linear, so sampling G0 equals applying W0 to the sampled features); valid for
-  // (g0_owner == head handle, g0_version == version)
+  // (g0_owner == generation id of the head handle, g0_version == version).  The owner is the head's generation id, not
+  // its address: a head rebuilt after a weight change may be handed the freed handle's address again.
   __half* g0;
   __half* f16;      // [H*W][C] fp16 copy of the map (X operand taps of the v3 program), same validity as g0
   float* s4tex;     // [H*W][n_out] fp32: last layer's feature part applied per texel (sampled in fp32 by the v3 program)
   int g0_n;
-  const void* g0_owner;
+  unsigned long long g0_owner;
   unsigned long long g0_version;
   unsigned long long version;   // bumped by every mp_feat_upload
 };
@@ -124,12 +126,6 @@ struct MpOutDst {
   float* peer[MP_MAX_PEERS] = {};
   long long peer_off = 0;
   int n_peers = 0;
-  // brick-ordered dense grid (opt-in experiment, tensor-core program v3 only): point i of a MP_SRC_GRID query is node
-  // (i & 7, (i >> 3) & 3, (i >> 5) & 3) of the 8 x 4 x 4 brick i >> 7 (bricks x-fastest over brick_nbx x brick_nby x ...);
-  // its value goes to the node's linear index inside the [brick_nz, R, R] slab.  A tile of 128 points then touches a
-  // few dozen texels instead of a 128-node row's ~200, so the layer-0 taps hit L1.
-  int brick = 0;
-  int brick_nbx = 0, brick_nby = 0, brick_nz = 0;
 };
 
 // ---------------------------------------------------------------------------------------------

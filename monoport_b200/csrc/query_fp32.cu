@@ -246,8 +246,8 @@ int launch(const Fp32Params& prm, const MpPointSrc& src, const MpCalib& cal, con
 int mp_launch_query_fp32(const mp_mlp* mlp, const mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
                          const MpOutDst& dst, cudaStream_t st) {
   if (src.n <= 0) return MP_OK;
-  if (dst.n_peers > 0 || dst.brick) {
-    mp_set_error("peer stores (fused slab exchange) / brick order are implemented by the tensor-core program only");
+  if (dst.n_peers > 0) {
+    mp_set_error("peer stores (fused slab exchange) are implemented by the tensor-core program only");
     return MP_E_UNSUPPORTED;
   }
   Fp32Params prm;

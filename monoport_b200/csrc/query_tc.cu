@@ -810,54 +810,9 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
 // TMEM map: acc1 [0,512)  --drain in place-->  H1lo [0,128) | acc2 [128,384) | H1hi [384,512)
 //           --drain-->  H2 [0,128) | (free) | acc3 [384,512)
 // roofline.achieved keeps counting the ALGORITHMIC 2 363 906 FLOP/point; the hoisted layer is not executed per point.
-// Brick-ordered dense grid (dst.brick, see MpOutDst): node + output index of point i.  The world coordinates use exactly
-// the arithmetic of mp_load_point's grid branch, so a value does not depend on the ordering.
-struct BrickPoint {
-  bool valid;
-  long long out;
-  float x, y, z;
-};
-__device__ __forceinline__ BrickPoint brick_point(const MpPointSrc& s, const MpOutDst& d, long long i) {
-  BrickPoint bp;
-  const long long b = i >> 7;
-  const int l = (int)(i & 127), lx = l & 7, ly = (l >> 3) & 3, lz = l >> 5;
-  const int bx = (int)(b % d.brick_nbx);
-  const long long t = b / d.brick_nbx;
-  const int by = (int)(t % d.brick_nby), bz = (int)(t / d.brick_nby);
-  const int ix = bx * 8 + lx, iy = by * 4 + ly, izl = bz * 4 + lz;          // izl: plane inside the slab
-  bp.valid = ix < s.res && iy < s.res && izl < d.brick_nz;
-  bp.out = ((long long)izl * s.res + iy) * s.res + ix;
-  const float cx = (float)(ix * s.node_stride), cy = (float)(iy * s.node_stride), cz = (float)((izl + s.z0) * s.node_stride);
-  const float R = (float)s.r_final;
-  bp.x = __fadd_rn(__fmul_rn(__fadd_rn(__fdiv_rn(cx, R), s.half_inv_r), s.bext[0]), s.bmin[0]);
-  bp.y = __fadd_rn(__fmul_rn(__fadd_rn(__fdiv_rn(cy, R), s.half_inv_r), s.bext[1]), s.bmin[1]);
-  bp.z = __fadd_rn(__fmul_rn(__fadd_rn(__fdiv_rn(cz, R), s.half_inv_r), s.bext[2]), s.bmin[2]);
-  return bp;
-}
-template <bool BRICK>
-__device__ __forceinline__ PointTaps taps_of(const MpPointSrc& src, const MpOutDst& dst, const MpCalib& cal, int H, int W, long long i,
-                                             long long n) {
-  if constexpr (!BRICK) {
-    return point_taps(src, cal, H, W, i, n);
-  } else {
-    PointTaps pt;
-    float u = 0.f, v = 0.f, w = 0.f;
-    const BrickPoint bp = brick_point(src, dst, i);
-    const bool valid = i < n && bp.valid;
-    if (valid) mp_project(cal, bp.x, bp.y, bp.z, u, v, w);
-    pt.in_img = valid && (u >= -1.f) && (u <= 1.f) && (v >= -1.f) && (v <= 1.f);
-    const MpTaps t = mp_taps(valid ? u : 0.f, valid ? v : 0.f, H, W);
-    const bool dead = !valid || !(u == u) || !(v == v);
-#pragma unroll
-    for (int a = 0; a < 4; ++a) { pt.off[a] = dead ? 0 : t.off[a]; pt.wgt[a] = dead ? 0.f : t.wgt[a]; }
-    pt.zf = w * cal.z_scale;
-    return pt;
-  }
-}
-
-// PEERS: also store channel 0 into the peer volumes of dst (fused slab exchange).  BRICK: brick-ordered dense grid.  The
-// default instantiation carries no trace of either.
-template <int CG, bool PEERS = false, bool BRICK = false>
+// PEERS: also store channel 0 into the peer volumes of dst (fused slab exchange); the default instantiation carries no
+// trace of it.
+template <int CG, bool PEERS = false>
 __global__ void __launch_bounds__(kThreads, 1)
 query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
   using C = Cfg<CG>;
@@ -1135,7 +1090,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
 #pragma unroll 1
       for (int grp = 0; grp < 4; ++grp) {
         const int pbase = sw * 64 + grp * 16;
-        PointTaps pt = taps_of<BRICK>(src, dst, cal, prm.H, prm.W, p0 + pbase + (lane & 15), n);
+        PointTaps pt = point_taps(src, cal, prm.H, prm.W, p0 + pbase + (lane & 15), n);
         if (prm.exp & 4) { pt.off[0] = pt.off[1] = pt.off[2] = pt.off[3] = 0; }
         sample_x_group16(prm, smem + Smem::X, s_zf, s_in, s_s4, pt, pbase, lane);
       }
@@ -1170,7 +1125,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     uint32_t t_off[4][2], t_wgt[4][2], t_z[4];
     int gtr = -1;                              // trace slot base for the chunk being generated (-1: off)
     auto compute_taps = [&](long long g) {
-      const PointTaps pt = taps_of<BRICK>(src, dst, cal, prm.H, prm.W, (g * CG + rank) * kTile + wk * 16 + l16, n);
+      const PointTaps pt = point_taps(src, cal, prm.H, prm.W, (g * CG + rank) * kTile + wk * 16 + l16, n);
       const uint32_t o01 = (uint32_t)pt.off[0] | ((uint32_t)pt.off[1] << 16), o23 = (uint32_t)pt.off[2] | ((uint32_t)pt.off[3] << 16);
       const uint32_t w01 = tc::pack_half2(pt.wgt[0], pt.wgt[1]), w23 = tc::pack_half2(pt.wgt[2], pt.wgt[3]);
       const uint32_t zz = tc::pack_half2(pt.zf, pt.zf);
@@ -1387,14 +1342,8 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         warp_arrive_local(bars + B_TILE_DONE, lane);
         PROF_ADD(P_W_DRAIN3);
         TRACE(tr, tb + 16);
-        long long i = p0 + row;
-        bool live = i < n;
-        if constexpr (BRICK) {          // the node's place in the slab instead of the point's place in the brick order
-          const BrickPoint bp = brick_point(src, dst, i);
-          live = live && bp.valid;
-          i = bp.out;
-        }
-        if (live) {
+        const long long i = p0 + row;
+        if (i < n) {
 #pragma unroll
           for (int r = 0; r < kMaxRes; ++r) {
             if (r < res) {
@@ -2394,16 +2343,16 @@ int launch_colour(const mp_mlp* mlp, const TcPack* pk, mp_feat* feat, const MpPo
     if (!feat->f16) MP_CUDA(cudaMalloc(&feat->f16, (size_t)HW * kCc * sizeof(__half)));
     if (!feat->s4tex) MP_CUDA(cudaMalloc(&feat->s4tex, (size_t)HW * kResC * sizeof(float)));
     feat->g0_n = kL0;
-    feat->g0_owner = nullptr;
+    feat->g0_owner = 0;
   }
-  if (feat->g0_owner != (const void*)mlp || feat->g0_version != feat->version) {
+  if (feat->g0_owner != mlp->gen || feat->g0_version != feat->version) {
 #ifndef MP_CUDA_EMU
     g0c_tc_kernel<<<(unsigned)((HW + 127) / 128), kG0Threads, kG0cSmem, st>>>(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s);
 #else
     MP_EMU_LAUNCH((unsigned)((HW + 127) / 128), kG0Threads, g0c_tc_kernel(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s));
 #endif
     MP_CUDA(cudaGetLastError());
-    feat->g0_owner = (const void*)mlp;
+    feat->g0_owner = mlp->gen;
     feat->g0_version = feat->version;
   }
   TcParams prm;
@@ -2440,11 +2389,7 @@ int launch_colour(const mp_mlp* mlp, const TcPack* pk, mp_feat* feat, const MpPo
 int mp_tc_prepare(mp_mlp* mlp) {
   mlp->tc = nullptr;
   mlp->tc_ok = 0;
-  if (colour_shape(mlp)) {
-    // tcgen05 program of the colour head: opt-in until it has been validated on a B200 (the fp32 kernel is the default)
-    static const int on = [] { const char* v = getenv("MONOPORT_B200_TC_NETC"); return v ? atoi(v) : 0; }();
-    return on ? tc_prepare_colour(mlp) : MP_OK;
-  }
+  if (colour_shape(mlp)) return tc_prepare_colour(mlp);     // tcgen05 program of the colour head (validated on B200, round 2)
   if (!shape_supported(mlp)) return MP_OK;
   int dev = 0, major = 0, max_smem = 0;
   MP_CUDA(cudaGetDevice(&dev));
@@ -2600,8 +2545,6 @@ int mp_tc_prepare(mp_mlp* mlp) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(g0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG0Smem);
   if (e != cudaSuccess) {
     mp_set_error("mp_tc_prepare: cannot opt in to %d bytes of shared memory: %s", Smem::Total + 1024, cudaGetErrorString(e));
@@ -2749,16 +2692,16 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
       if (!feat->f16) MP_CUDA(cudaMalloc(&feat->f16, (size_t)HW * kC * sizeof(__half)));
       if (!feat->s4tex) MP_CUDA(cudaMalloc(&feat->s4tex, (size_t)HW * kMaxRes * sizeof(float)));
       feat->g0_n = kL0;
-      feat->g0_owner = nullptr;
+      feat->g0_owner = 0;
     }
-    if (feat->g0_owner != (const void*)mlp || feat->g0_version != feat->version) {
+    if (feat->g0_owner != mlp->gen || feat->g0_version != feat->version) {
 #ifndef MP_CUDA_EMU
       g0_tc_kernel<<<(unsigned)((HW + 127) / 128), kG0Threads, kG0Smem, st>>>(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s, pk->res);
 #else
       MP_EMU_LAUNCH((unsigned)((HW + 127) / 128), kG0Threads, g0_tc_kernel(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s, pk->res));
 #endif
       MP_CUDA(cudaGetLastError());
-      feat->g0_owner = (const void*)mlp;
+      feat->g0_owner = mlp->gen;
       feat->g0_version = feat->version;
     }
     prm.g0 = feat->g0;
@@ -2771,21 +2714,17 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     prm.wstream2[1] = pk->w3stream2[1];
   }
   const int cg = forced == 2 ? 2 : (forced == 1 ? 1 : 1);
-  if (dst.n_peers > 0 || dst.brick) {
-    // fused slab exchange / brick-ordered grid: only the default program (v3, one CTA per tile) has these variants
-    if (ver != 3 || cg != 1 || dst.n_peers > MP_MAX_PEERS || (dst.brick && (src.kind != MP_SRC_GRID || dst.scatter_vol))) {
-      mp_set_error("peer stores / brick order need tensor-core program v3, cta_group::1, a grid query and at most %d peers", MP_MAX_PEERS);
+  if (dst.n_peers > 0) {
+    // fused slab exchange: only the default program (v3, one CTA per tile) has this variant
+    if (ver != 3 || cg != 1 || dst.n_peers > MP_MAX_PEERS) {
+      mp_set_error("peer stores need tensor-core program v3, cta_group::1 and at most %d peers", MP_MAX_PEERS);
       return MP_E_UNSUPPORTED;
     }
     const int grid = (int)(tiles < (long long)sms ? tiles : sms);
 #ifndef MP_CUDA_EMU
-    if (dst.brick && dst.n_peers > 0) query_tc3_kernel<1, true, true><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
-    else if (dst.brick) query_tc3_kernel<1, false, true><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
-    else query_tc3_kernel<1, true><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
+    query_tc3_kernel<1, true><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
 #else
-    if (dst.brick && dst.n_peers > 0) MP_EMU_LAUNCH(grid, kThreads, (query_tc3_kernel<1, true, true>(prm, src, cal, dst)));
-    else if (dst.brick) MP_EMU_LAUNCH(grid, kThreads, (query_tc3_kernel<1, false, true>(prm, src, cal, dst)));
-    else MP_EMU_LAUNCH(grid, kThreads, (query_tc3_kernel<1, true>(prm, src, cal, dst)));
+    MP_EMU_LAUNCH(grid, kThreads, (query_tc3_kernel<1, true>(prm, src, cal, dst)));
 #endif
     MP_CUDA(cudaGetLastError());
     report(grid);

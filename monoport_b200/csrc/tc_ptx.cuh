@@ -235,4 +235,43 @@ __device__ __forceinline__ void mma_commit2(uint64_t* bar) {
 
 }  // namespace tc
 
+
+// ---------------------------------------------------------------- tensor-map TMA (cp.async.bulk.tensor, SASS UTMALDG)
+namespace tc {
+
+// 2-D tile load global -> shared through a CUtensorMap (box = the map's box, coordinates in elements: c0 innermost).
+// Completion (bytes) is signalled on `bar` of this CTA.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// cta_group::2 flavour, executed by BOTH CTAs of the pair (each loads its own box into its own shared memory): the
+// completion bytes of both land on the LEADER's barrier (shared::cluster address of `bar` with the CTA-rank bit cleared),
+// so the MMA issuer waits on one barrier and nobody has to forward anything.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+// plain (non-release) remote arrive: the data the arrival publishes has been made visible by the caller
+// (fence.proxy.async / tcgen05.fence::before_thread_sync + fence.acq_rel.cluster where generic-proxy data is involved)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+
+}  // namespace tc
+
 #endif  // MP_CUDA_EMU

@@ -84,9 +84,11 @@ class _Seg3dBase(nn.Module):
         if device.type != "cuda":
             raise RuntimeError("monoport_b200 engines run on CUDA only (call .to('cuda:0') like RTL/main.py:195)")
         net = getattr(self.query_func, "__monoport_fused__", None)
-        if net is not None and set(kwargs) == {"im_feat_list", "calib_tensor"}:
-            return self._forward_fused(net, device, **kwargs)
-        return self._forward_generic(device, **kwargs)
+        # one engine call = one frame: its per-level queries may reuse the frame's uploaded features / calib
+        with _lib.frame_scope():
+            if net is not None and set(kwargs) == {"im_feat_list", "calib_tensor"}:
+                return self._forward_fused(net, device, **kwargs)
+            return self._forward_generic(device, **kwargs)
 
     def _new_volume(self, device):
         R = self.resolutions[-1]

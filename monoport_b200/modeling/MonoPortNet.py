@@ -31,12 +31,16 @@ class FeatureHandle:
             _lib.check(_lib.load().mp_feat_create(C, H, W, ctypes.byref(self.ptr)), "mp_feat_create")
         self.key = None
         self._src = None
+        self._scope = 0
 
-    def upload(self, feat):
-        # identity of the uploaded frame = (storage address, version counter).  `_src` keeps that tensor alive so the
-        # caching allocator cannot hand its address to the NEXT frame's features (which would look "unchanged").
-        key = (feat.data_ptr(), feat._version, feat.dtype)
-        if key == self.key:
+    def upload(self, feat, trust_identity=False):
+        """Repack `feat` into the handle.  The upload is skipped only when (storage address, version counter) are
+        unchanged AND that identity may be trusted: inside one `_lib.frame_scope()` (the levels of one engine call) or
+        when the application opted in (`MonoPortNet.feature_cache = True`).  Writes that bypass the version counter
+        (CUDA-graph static buffers, custom kernels, NCCL receives) are otherwise re-uploaded: ~11 us repack + ~26 us G0."""
+        key = _lib.tensor_identity(feat)          # None for inference-mode tensors: never matches
+        sid = _lib.current_scope()
+        if key is not None and key == self.key and (trust_identity or _lib.TRUST_TENSOR_IDENTITY or (sid != 0 and sid == self._scope)):
             return
         f = feat.detach()
         if (f.dtype == torch.float32 and f.shape[1] > 1 and not f.is_contiguous()
@@ -44,15 +48,17 @@ class FeatureHandle:
             # a channels_last encoder already emits [H,W,C]: copy, do not transpose
             _lib.check(_lib.load().mp_feat_upload_nhwc(self.ptr, ctypes.c_void_p(f.data_ptr()), _lib.stream_ptr(self.device)),
                        "mp_feat_upload_nhwc")
-            self.key = key
-            self._src = feat
-            return
-        if f.dtype != torch.float32 or not f.is_contiguous():
-            f = f.to(torch.float32).contiguous()
-        _lib.check(_lib.load().mp_feat_upload(self.ptr, ctypes.c_void_p(f.data_ptr()), 1, _lib.stream_ptr(self.device)),
-                   "mp_feat_upload")
-        self.key = key
-        self._src = feat
+        else:
+            if f.dtype != torch.float32 or not f.is_contiguous():
+                f = f.to(torch.float32).contiguous()
+            _lib.check(_lib.load().mp_feat_upload(self.ptr, ctypes.c_void_p(f.data_ptr()), 1, _lib.stream_ptr(self.device)),
+                       "mp_feat_upload")
+        # `_src` keeps the tensor alive so the caching allocator cannot hand its address to the NEXT frame's features
+        self.key, self._src, self._scope = key, feat, sid
+
+    def invalidate(self):
+        self.key = None
+        self._src = None
 
     def __del__(self):
         try:
@@ -74,6 +80,9 @@ class MonoPortNet(nn.Module):
         self.normalizer = globals()[opt_net.normalizer.IMF](opt_net.normalizer)
         # arithmetic of the fused kernel: "auto" (tcgen05 when supported), "tc", "fp32"; "tc_v2"/"tc_v3" pin the tensor-core program
         self.precision = os.environ.get("MONOPORT_B200_MODE", "auto")
+        # True: skip the per-call feature upload when the tensor's (address, version) are unchanged (see FeatureHandle.upload
+        # for what that identity cannot see); default off -- every query()/query_grid()/engine call uploads its frame
+        self.feature_cache = os.environ.get("MONOPORT_B200_FEATURE_CACHE", "0") == "1"
         self._feat_handles = {}
 
     # ---- encoder: stays PyTorch ---------------------------------------------------------------------------
@@ -97,8 +106,13 @@ class MonoPortNet(nn.Module):
         h = self._feat_handles.get(key)
         if h is None:
             h = self._feat_handles[key] = FeatureHandle(C, H, W, feat.device)
-        h.upload(feat)
+        h.upload(feat, trust_identity=self.feature_cache)
         return h
+
+    def invalidate_features(self):
+        """Forget every uploaded frame (call after writing into a feature tensor behind PyTorch's back)."""
+        for h in self._feat_handles.values():
+            h.invalidate()
 
     def _mode(self):
         try:
@@ -146,14 +160,16 @@ class MonoPortNet(nn.Module):
                 _lib.stream_ptr(feat.device)), "mp_query_points")
         return [out]
 
-    def query_grid(self, feat, calibs, resolution, b_min, b_max, z0=0, nz=None, out=None):
-        """Dense occupancy slab [nz,R,R] of an R^3 grid over [b_min,b_max] (points generated in-kernel)."""
+    def query_grid(self, feat, calibs, resolution, b_min, b_max, z0=0, nz=None, out=None, fh=None):
+        """Dense occupancy slab [nz,R,R] of an R^3 grid over [b_min,b_max] (points generated in-kernel).
+        `fh`: a handle already uploaded for this frame (`feature_handle(feat)`), to skip the upload here."""
         R = int(resolution)
         nz = R - z0 if nz is None else int(nz)
         if out is None:
             out = torch.empty((nz, R, R), dtype=torch.float32, device=feat.device)
         with _lib.device_guard(feat.device):
-            fh = self.feature_handle(feat)
+            if fh is None:
+                fh = self.feature_handle(feat)
             proj = _lib.PROJ_PERSPECTIVE if self.projection is perspective else _lib.PROJ_ORTHOGONAL
             _lib.check(_lib.load().mp_query_grid(
                 self.surface_classifier.handle(), fh.ptr, R, int(z0), nz, _lib.f3(b_min), _lib.f3(b_max),

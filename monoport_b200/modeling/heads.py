@@ -48,12 +48,17 @@ class SurfaceClassifier(nn.Module):
         raise NotImplementedError("last_op %r" % (self.last_op,))
 
     def _key(self):
-        return tuple((p.data_ptr(), p._version, p.device) for p in self.parameters())
+        def ver(p):
+            try:
+                return p._version
+            except RuntimeError:          # inference-mode tensors carry no version counter
+                return None
+        return tuple((p.data_ptr(), ver(p), p.device) for p in self.parameters())
 
     def handle(self):
         """mp_mlp_t* for the current parameters (rebuilt when they change: load_state_dict, .to(), optimizer step)."""
         key = self._key()
-        if self._handle is not None and key == self._handle_key:
+        if self._handle is not None and key == self._handle_key and not any(k[1] is None for k in key):
             return self._handle
         self.release()
         lib = _lib.load()

@@ -138,10 +138,8 @@ int main(int argc, char** argv) {
   std::vector<int32_t> nodes;
   int32_t node_count = 0;
   std::vector<float> scatter;
-  int brick_R = 0, brick_nz = 0;
-  if (!strcmp(src_kind, "grid") || !strcmp(src_kind, "gridb")) {
+  if (!strcmp(src_kind, "grid")) {
     const int R = atoi(argv[6]), z0 = atoi(argv[7]), nz = atoi(argv[8]);
-    if (!strcmp(src_kind, "gridb")) { brick_R = R; brick_nz = nz; }        // brick-ordered walk of the same slab
     memset(&src, 0, sizeof(src));
     src.kind = MP_SRC_GRID;
     fill_grid_geom(src, R, 1, R);
@@ -185,13 +183,6 @@ int main(int argc, char** argv) {
   MpOutDst dst;
   dst.out = out.data(); dst.ld = n_out; dst.scatter_vol = nullptr;
   if (!scatter.empty()) { dst.out = nullptr; dst.ld = 0; dst.scatter_vol = scatter.data(); }
-  if (brick_R) {                                       // what mp_api.cu's maybe_brick sets up
-    dst.brick = 1;
-    dst.brick_nbx = (brick_R + 7) / 8;
-    dst.brick_nby = (brick_R + 3) / 4;
-    dst.brick_nz = brick_nz;
-    src.n = (long long)dst.brick_nbx * dst.brick_nby * ((brick_nz + 3) / 4) * 128;
-  }
   // program 1xx: tensor-core program xx with the fused slab exchange -- three "peer volumes" (host buffers here)
   const int n_peers = program >= 100 ? 3 : 0, peer_off = 5;
   std::vector<std::vector<float>> peer(n_peers, std::vector<float>((size_t)n_out + 2 * peer_off, -4242.f));

@@ -352,24 +352,6 @@ def test_tcgen05_colour_head_fused_surface_rendering(emu_query_tc, tmp_path):
     assert bool((got[untouched] == 1.0).all()), "pixels without a vertex keep the canvas colour"
 
 
-@pytest.mark.parametrize("program", [3, 103])
-def test_tcgen05_brick_ordered_grid_is_bit_identical(emu_query_tc, tmp_path, program):
-    """MONOPORT_B200_GRID_BRICK: the slab walked in 8 x 4 x 4 bricks (partial bricks on every axis for R = 9, nz = 3) gives
-    the same volume, bit for bit, as the row-ordered walk (103: also in the peer volumes)."""
-    from helpers import load_query_case
-    case = load_query_case("g_smallmap")
-    fin = str(tmp_path / "in.bin")
-    _write_tc_input(fin, case, 4)
-    outs = []
-    for kind in ("grid", "gridb"):
-        fout = str(tmp_path / (kind + ".f32"))
-        r = subprocess.run([emu_query_tc, fin, fout, str(program), "3", kind, "9", "2", "3"], capture_output=True, text=True,
-                           timeout=900)
-        assert r.returncode == 0, r.stderr[-2000:]
-        outs.append(np.fromfile(fout, dtype=np.float32))
-    assert outs[0].size == 3 * 9 * 9 and np.array_equal(outs[0], outs[1])
-
-
 # ---- the exact CUDA-core kernel (query_fp32.cu): default path of the colour head, fallback for every other head shape ----
 @pytest.fixture(scope="module")
 def emu_query_fp32(tmp_path_factory):

@@ -197,7 +197,7 @@ def test_concurrent_queries_from_threads():
             errs.append(repr(ex))
 
     tg = threading.Thread(target=run, args=(netG, fg, pg, calg, cg["expected"], 1e-4, 20))
-    tcol = threading.Thread(target=run, args=(netC, fc, pc, calc, cc["expected"], 2e-5, 20))
+    tcol = threading.Thread(target=run, args=(netC, fc, pc, calc, cc["expected"], TOL_COLOUR["tc"], 20))     # netC "auto" = tensor-core program
     tg.start(); tcol.start(); tg.join(); tcol.join()
     assert not errs, errs
 
@@ -253,3 +253,52 @@ def test_channels_last_feature_map_gives_identical_results():
         a = net.query([[feat]], pts, calibs=cal)[0].clone()
         b = net.query([[feat_cl]], pts, calibs=cal)[0].clone()
         assert torch.equal(a, b), mode
+
+
+def test_head_weight_change_invalidates_per_feature_cache():
+    """the per-feature-map cache of the tensor-core program (G0 / S4 per texel) is keyed on the head's
+    generation id.  Query, load new weights into the SAME module (the rebuilt handle may get the freed handle's address),
+    query the same feature tensor again: must equal a fresh net with the new weights."""
+    Wa, ba = spec.make_weights(spec.G_CHANNELS, 21)
+    Wb, bb = spec.make_weights(spec.G_CHANNELS, 22)
+    feat = spec.make_feat(256, 64, 64, 5).cuda()
+    cal = spec.scene_calib(10, 20).cuda()
+    pts = spec.make_points(3000, 3).cuda()
+    net = build_net("G", Wa, ba)
+    net.feature_cache = True                       # worst case: the feature upload is skipped on the second query
+    for mode in _modes(net):
+        net.surface_classifier.load_state_dict({**{"filters.%d.weight" % l: W[:, :, None] for l, W in enumerate(Wa)},
+                                                **{"filters.%d.bias" % l: b for l, b in enumerate(ba)}})
+        net.precision = mode
+        a = net.query([[feat]], pts, calibs=cal)[0]
+        net.surface_classifier.load_state_dict({**{"filters.%d.weight" % l: W[:, :, None] for l, W in enumerate(Wb)},
+                                                **{"filters.%d.bias" % l: b for l, b in enumerate(bb)}})
+        b = net.query([[feat]], pts, calibs=cal)[0]
+        fresh = build_net("G", Wb, bb)
+        fresh.precision = mode
+        want = fresh.query([[feat]], pts, calibs=cal)[0]
+        assert torch.equal(b, want), mode
+        assert not torch.equal(a, b)
+
+
+def test_out_of_band_feature_writes_and_inference_tensors():
+    """by default every query uploads its frame, so a write that bypasses the tensor's version counter (a
+    CUDA-graph static buffer, a custom kernel) is seen; inference-mode tensors (no version counter) work."""
+    c = load_query_case("g_rot33")
+    net = build_net(c)
+    net.precision = "fp32"
+    cal, pts = c["calib"].cuda(), c["points"][:, :, :2000].cuda()
+    buf = c["feat"].cuda().clone()
+    a = net.query([[buf]], pts, calibs=cal)[0]
+    other = spec.make_feat(256, buf.shape[2], buf.shape[3], 99).cuda()
+    v0 = buf._version
+    buf.untyped_storage().copy_(other.untyped_storage())     # storage-level copy: same data_ptr, same _version
+    assert buf._version == v0
+    b = net.query([[buf]], pts, calibs=cal)[0]
+    want = net.query([[other]], pts, calibs=cal)[0]
+    assert torch.equal(b, want) and not torch.equal(a, b)
+    with torch.inference_mode():
+        f_inf = c["feat"].cuda() * 1.0
+        cal_inf = c["calib"].cuda() * 1.0
+    d = net.query([[f_inf]], pts, calibs=cal_inf)[0]
+    assert torch.equal(d, a)
