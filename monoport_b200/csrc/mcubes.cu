@@ -3,13 +3,13 @@
 // HBM-bound byte/integer work.  Indexed, watertight mesh with deterministic ids:
 //   vertex id = rank of (node, axis) among active owned edges (every grid edge is owned by its lower node);
 //   face order = (cell linear index, table order).
-// count:  classify_kernel (1 read of the volume, rows walked by warps, no divisions: per node 3 owned-edge bits + the
-//         triangle count of its cell packed in one byte, + the cell's case byte)  ->  ordered scan of (verts, tris)
-//         packed in one uint64 (8-byte loads of the code bytes); the emit half of the scan stores the exclusive vertex
-//         offset of the nodes that own a vertex (sparse: faces look up nothing else)  -> totals.
-// emit :  mesh_emit_kernel re-runs the block-local scan, queues the block's active nodes in shared memory and spreads
-//         their up to 3 vertices + 15 face corners over the whole CTA (one short dependent chain per thread instead of
-//         one thread walking a whole cell).
+// count:  bits_kernel (THE read of the volume: 4 B per node in, one occupancy bit per node out, streaming) ->
+//         classify_words_kernel (one thread per 32-node word of the bit volume: edge masks + triangle count; words with no
+//         surface inside leave after a dozen cached loads) -> ordered scan of (verts, tris) per word packed in one
+//         uint64 -> exclusive prefix per word -> totals.
+// emit :  mesh_emit_kernel, a warp per word with a surface inside, a lane per node: vertices from the volume (two loads
+//         per vertex), faces from the table; the vertex id behind a face corner is the owning word's prefix + popcounts.
+// Workspace: 1 bit + 24 B per 32 nodes (15 MB at 257^3; the round-1 byte-per-node design took 102 MB).
 #include "mp_common.cuh"
 #include <stdlib.h>
 #include "mcubes_kernels.cuh"
@@ -19,10 +19,10 @@ using namespace mcubes;
 
 struct mp_mcubes {
   int D, H, W;
-  long long n;
-  uint8_t* code;
-  uint8_t* cases;
-  uint32_t* voff;
+  long long n, n_words;
+  uint32_t* bits;
+  WordInfo* info;
+  unsigned long long* prefix;
   unsigned long long* sums;
   unsigned long long* total;
   long long nv, nf;
@@ -31,9 +31,9 @@ struct mp_mcubes {
 
 extern "C" int mp_mcubes_destroy(mp_mcubes_t* h) {
   if (!h) return MP_OK;
-  if (h->code) cudaFree(h->code);
-  if (h->cases) cudaFree(h->cases);
-  if (h->voff) cudaFree(h->voff);
+  if (h->bits) cudaFree(h->bits);
+  if (h->info) cudaFree(h->info);
+  if (h->prefix) cudaFree(h->prefix);
   if (h->sums) cudaFree(h->sums);
   if (h->total) cudaFree(h->total);
   delete h;
@@ -43,15 +43,18 @@ extern "C" int mp_mcubes_destroy(mp_mcubes_t* h) {
 extern "C" int mp_mcubes_create(int D, int H, int W, mp_mcubes_t** out) {
   MP_REQUIRE(out != nullptr, "out is NULL");
   *out = nullptr;
-  MP_REQUIRE(D >= 2 && H >= 2 && W >= 2 && (long long)D * H * W < (1ll << 31) && H <= kClassRows * 65535, "bad volume shape %dx%dx%d", D, H, W);
+  MP_REQUIRE(D >= 2 && H >= 2 && W >= 2 && (long long)D * H * W < (1ll << 31), "bad volume shape %dx%dx%d", D, H, W);
   mp_mcubes* h = new mp_mcubes();
   memset(h, 0, sizeof(*h));
   h->D = D; h->H = H; h->W = W;
   h->n = (long long)D * H * W;
-  cudaError_t e = cudaMalloc(&h->code, h->n);
-  if (e == cudaSuccess) e = cudaMalloc(&h->cases, h->n);
-  if (e == cudaSuccess) e = cudaMalloc(&h->voff, h->n * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&h->sums, (size_t)(mpscan::num_blocks(h->n) + 1) * sizeof(unsigned long long));
+  h->n_words = (h->n + 31) >> 5;
+  const size_t bit_words = (size_t)(h->n_words + bits_pad_words(H, W));
+  cudaError_t e = cudaMalloc(&h->bits, bit_words * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(h->bits, 0, bit_words * sizeof(uint32_t));     // the padding stays zero for ever
+  if (e == cudaSuccess) e = cudaMalloc(&h->info, (size_t)h->n_words * sizeof(WordInfo));
+  if (e == cudaSuccess) e = cudaMalloc(&h->prefix, (size_t)h->n_words * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&h->sums, (size_t)(mpscan::num_blocks(h->n_words) + 1) * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&h->total, 2 * sizeof(unsigned long long));                 // [0] total, [1] scan ticket
   if (e == cudaSuccess) e = cudaMemset(h->total, 0, 2 * sizeof(unsigned long long));
   if (e != cudaSuccess) {
@@ -63,18 +66,31 @@ extern "C" int mp_mcubes_create(int D, int H, int W, mp_mcubes_t** out) {
   return MP_OK;
 }
 
+static int sm_count() {
+  static const int sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  return sms;
+}
+
 extern "C" int mp_mcubes_count(mp_mcubes_t* h, const float* vol_dev, float iso, int64_t* n_verts, int64_t* n_faces,
                                void* stream) {
   MP_REQUIRE(h && vol_dev && n_verts && n_faces, "NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
-  static const int fast = [] { const char* v = getenv("MONOPORT_B200_MC_FAST"); return v ? atoi(v) : 1; }();   // measured 59.6 vs 71.0 us at 257^3 (profiles/r02_call1_*)
-  const dim3 cgrid((unsigned)h->D, (unsigned)((h->H + kClassRows - 1) / kClassRows)), cblock(32, kClassRows);
-  if (fast) classify_fast_kernel<<<cgrid, cblock, 0, st>>>(vol_dev, h->code, h->cases, h->D, h->H, h->W, iso);
-  else classify_kernel<<<cgrid, cblock, 0, st>>>(vol_dev, h->code, h->cases, h->D, h->H, h->W, iso);
+  {
+    // a multiple of the SM count, 8 CTAs of 256 threads resident per SM: 8 x 128 B loads in flight per warp
+    const long long warps_needed = (h->n_words + kBitsUnroll - 1) / kBitsUnroll;
+    const long long blocks_needed = (warps_needed + kBitsThreads / 32 - 1) / (kBitsThreads / 32);
+    const long long cap = (long long)sm_count() * 8;
+    bits_kernel<<<(unsigned)(blocks_needed < cap ? blocks_needed : cap), kBitsThreads, 0, st>>>(vol_dev, h->bits, h->n, iso);
+  }
+  classify_words_kernel<<<(unsigned)((h->n_words + 255) / 256), 256, 0, st>>>(h->bits, h->info, h->n, h->D, h->H, h->W);
   MP_CUDA(cudaGetLastError());
-  CountF f{h->code};
-  OffsetsEmit em{h->voff};
-  MP_CUDA(mpscan::scan_emit(f, em, h->n, h->sums, h->total, st));
+  WordCountF f{h->info};
+  PrefixEmit em{h->prefix};
+  MP_CUDA(mpscan::scan_emit(f, em, h->n_words, h->sums, h->total, st));
   unsigned long long tot = 0;
   MP_CUDA(cudaMemcpyAsync(&tot, h->total, sizeof(tot), cudaMemcpyDeviceToHost, st));
   MP_CUDA(cudaStreamSynchronize(st));
@@ -93,9 +109,11 @@ extern "C" int mp_mcubes_emit(mp_mcubes_t* h, const float* vol_dev, float iso, f
   if (h->nv == 0 && h->nf == 0) return MP_OK;
   MP_REQUIRE(verts_dev && faces_dev, "NULL output buffers");
   cudaStream_t st = (cudaStream_t)stream;
-  // block offsets in h->sums are still valid from the count pass: only the emit launch is needed
-  mesh_emit_kernel<<<mpscan::num_blocks(h->n), mpscan::kThreads, 0, st>>>(vol_dev, h->code, h->cases, h->voff, h->sums, verts_dev,
-                                                                         faces_dev, h->H, h->W, h->n, iso);
+  const long long n_groups = (h->n_words + 31) >> 5;
+  const long long blocks_needed = (n_groups + kEmitThreads / 32 - 1) / (kEmitThreads / 32);
+  const long long cap = (long long)sm_count() * 8;
+  mesh_emit_kernel<<<(unsigned)(blocks_needed < cap ? blocks_needed : cap), kEmitThreads, 0, st>>>(
+      vol_dev, h->bits, h->info, h->prefix, verts_dev, faces_dev, h->D, h->H, h->W, h->n, iso);
   MP_CUDA(cudaGetLastError());
   return MP_OK;
 }

@@ -1,5 +1,10 @@
 // Device code of F3 marching cubes (see mcubes.cu for the pipeline).  Kept free of host API calls and of CUDA runtime
 // types so that tests/emu can run these kernels unmodified on the CPU emulation layer of the build container.
+//
+// Everything after the first pass works on a BIT VOLUME: one occupancy bit (value > iso) per node in linear node order,
+// word w = nodes 32w .. 32w+31 (a word may straddle rows).  At 257^3 that is 2.1 MB instead of 68 MB, so the volume is
+// read from HBM exactly once (bits_kernel, streaming); neighbour lookups become funnel shifts of L1/L2-resident words, and
+// the ~95 % of words whose eight shifted copies agree (no surface inside) cost a dozen loads and seven XORs.
 #pragma once
 #include <stdint.h>
 #include "mp_scan.cuh"
@@ -7,214 +12,205 @@
 
 namespace mcubes {
 
+constexpr int kBitsThreads = 256;
+constexpr int kBitsUnroll = 8;      // words (= 128 B lines of the volume) a warp has in flight per iteration
 
-// per node byte: bits 0..2 = owned +x/+y/+z edge active; bits 3..5 = triangle count of the cell whose corner 0 is
-// this node (0 when the node is on the +face of the grid).
-// Block (32, 8) = eight rows of one z plane, a warp walks its row 32 nodes at a time (coalesced); grid (D, ceil(H/8)).
-// Eight loads per node, four of which hit the lines the neighbouring lane just fetched.  (A variant that loads every
-// value once and derives the x+1 neighbours from warp ballots measured SLOWER on B200 -- 100 us instead of 70 us at
-// 257^3: the kernel is instruction-bound, not load-bound; profiles/r01_final3_recon_trace_ballot_classify.txt.)
-constexpr int kClassRows = 8;
-__global__ void __launch_bounds__(32 * kClassRows)
-classify_kernel(const float* __restrict__ vol, uint8_t* __restrict__ code, uint8_t* __restrict__ cases, int D, int H,
-                int W, float iso) {
-  const int z = blockIdx.x, y = blockIdx.y * kClassRows + threadIdx.y;
-  if (y >= H) return;
-  const bool yi = y + 1 < H, zi = z + 1 < D;
-  const size_t row = ((size_t)z * H + y) * W;
-  // neighbour rows; a missing neighbour aliases the row itself (its bits are masked by yi / zi below)
-  const float* r00 = vol + row;
-  const float* r01 = r00 + (yi ? (size_t)W : 0);
-  const float* r10 = r00 + (zi ? (size_t)H * W : 0);
-  const float* r11 = r10 + (yi ? (size_t)W : 0);
-#pragma unroll 2
-  for (int x = threadIdx.x; x < W; x += 32) {
-    const bool xi = x + 1 < W;
-    const int x1 = xi ? x + 1 : x;
-    const bool b000 = __ldg(r00 + x) > iso, b001 = __ldg(r00 + x1) > iso;
-    const bool b010 = __ldg(r01 + x) > iso, b011 = __ldg(r01 + x1) > iso;
-    const bool b100 = __ldg(r10 + x) > iso, b101 = __ldg(r10 + x1) > iso;
-    const bool b110 = __ldg(r11 + x) > iso, b111 = __ldg(r11 + x1) > iso;
-    uint8_t c = 0;
-    if (xi && (b001 != b000)) c |= 1;
-    if (yi && (b010 != b000)) c |= 2;
-    if (zi && (b100 != b000)) c |= 4;
-    uint8_t cs = 0;
-    if (xi && yi && zi) {
-      int k = b000 ? 1 : 0;
-      k |= b001 ? 2 : 0;
-      k |= b010 ? 4 : 0;
-      k |= b011 ? 8 : 0;
-      k |= b100 ? 16 : 0;
-      k |= b101 ? 32 : 0;
-      k |= b110 ? 64 : 0;
-      k |= b111 ? 128 : 0;
-      cs = (uint8_t)k;
-      c |= (uint8_t)(c_mc_ntri[k] << 3);
-    }
-    code[row + x] = c;
-    cases[row + x] = cs;
-  }
-}
+// zero words the bit volume carries behind the last node so that neighbour reads (+1, +W, +H*W and their sums) of the
+// last words never leave the allocation
+__host__ __device__ inline long long bits_pad_words(int H, int W) { return ((long long)H * W + W + 1) / 32 + 3; }
 
-// Opt-in variant (MONOPORT_B200_MC_FAST=1, to be timed on a B200): ~98 % of the 32-node chunks of an occupancy volume lie
-// entirely inside or outside the surface.  A warp first loads every node's own column of the four neighbouring rows (4
-// loads per node, plus column x0+32 by lane 0) and votes; a uniform chunk stores 32 zero code bytes and is done (its case
-// bytes are never read: no triangles).  Only mixed chunks take the full eight-corner path of classify_kernel.
-__global__ void __launch_bounds__(32 * kClassRows)
-classify_fast_kernel(const float* __restrict__ vol, uint8_t* __restrict__ code, uint8_t* __restrict__ cases, int D, int H,
-                     int W, float iso) {
-  const int z = blockIdx.x, y = blockIdx.y * kClassRows + threadIdx.y;
-  if (y >= H) return;                    // (a whole warp: blockDim.x == 32)
-  const int lane = threadIdx.x;
-  const bool yi = y + 1 < H, zi = z + 1 < D;
-  const size_t row = ((size_t)z * H + y) * W;
-  const float* r00 = vol + row;
-  const float* r01 = r00 + (yi ? (size_t)W : 0);
-  const float* r10 = r00 + (zi ? (size_t)H * W : 0);
-  const float* r11 = r10 + (yi ? (size_t)W : 0);
-  for (int x0 = 0; x0 < W; x0 += 32) {
-    const int x = x0 + lane;
-    const int xc = min(x, W - 1);                        // lanes beyond the row repeat its last node
-    const int xe = min(x0 + 32, W - 1);                  // the column after the chunk (lane 0 adds it to the vote)
-    bool any_in = false, all_in = true;
-    {
-      const bool a = __ldg(r00 + xc) > iso, b = __ldg(r01 + xc) > iso, c = __ldg(r10 + xc) > iso, d = __ldg(r11 + xc) > iso;
-      any_in = a | b | c | d;
-      all_in = a & b & c & d;
-      if (lane == 0) {
-        const bool e = __ldg(r00 + xe) > iso, f = __ldg(r01 + xe) > iso, g = __ldg(r10 + xe) > iso, h = __ldg(r11 + xe) > iso;
-        any_in |= e | f | g | h;
-        all_in &= e & f & g & h;
-      }
+// ---- pass 1: volume -> bits.  HBM-bound: 4 B read per node, 1 bit written.
+__global__ void __launch_bounds__(kBitsThreads)
+bits_kernel(const float* __restrict__ vol, uint32_t* __restrict__ bits, long long n, float iso) {
+  const long long n_words = (n + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (kBitsThreads / 32) + (threadIdx.x >> 5);
+  const long long n_warps = (long long)gridDim.x * (kBitsThreads / 32);
+  for (long long w0 = warp0 * kBitsUnroll; w0 < n_words; w0 += n_warps * kBitsUnroll) {     // (warp-uniform trip count)
+    float v[kBitsUnroll];
+#pragma unroll
+    for (int j = 0; j < kBitsUnroll; ++j) {
+      const long long i = (w0 + j) * 32 + lane;
+      v[j] = i < n ? __ldg(vol + i) : iso;                  // (iso > iso is false: nodes past the end read as outside)
     }
-    const bool uniform = !__any_sync(0xffffffffu, any_in) || __all_sync(0xffffffffu, all_in);      // warp-uniform
-    if (uniform) {
-      if (x < W) code[row + x] = 0;
-      continue;
-    }
-    if (x < W) {
-      const bool xi = x + 1 < W;
-      const int x1 = xi ? x + 1 : x;
-      const bool b000 = __ldg(r00 + x) > iso, b001 = __ldg(r00 + x1) > iso;
-      const bool b010 = __ldg(r01 + x) > iso, b011 = __ldg(r01 + x1) > iso;
-      const bool b100 = __ldg(r10 + x) > iso, b101 = __ldg(r10 + x1) > iso;
-      const bool b110 = __ldg(r11 + x) > iso, b111 = __ldg(r11 + x1) > iso;
-      uint8_t c = 0;
-      if (xi && (b001 != b000)) c |= 1;
-      if (yi && (b010 != b000)) c |= 2;
-      if (zi && (b100 != b000)) c |= 4;
-      uint8_t cs = 0;
-      if (xi && yi && zi) {
-        int k = b000 ? 1 : 0;
-        k |= b001 ? 2 : 0;
-        k |= b010 ? 4 : 0;
-        k |= b011 ? 8 : 0;
-        k |= b100 ? 16 : 0;
-        k |= b101 ? 32 : 0;
-        k |= b110 ? 64 : 0;
-        k |= b111 ? 128 : 0;
-        cs = (uint8_t)k;
-        c |= (uint8_t)(c_mc_ntri[k] << 3);
-      }
-      code[row + x] = c;
-      cases[row + x] = cs;
+#pragma unroll
+    for (int j = 0; j < kBitsUnroll; ++j) {
+      const uint32_t m = __ballot_sync(0xffffffffu, v[j] > iso);
+      if (lane == j && w0 + j < n_words) bits[w0 + j] = m;  // lanes 0..7 store eight consecutive words: one 32 B segment
     }
   }
 }
 
-struct CountF {    // low 32: vertices owned by node i, high 32: triangles of cell i
-  const uint8_t* code;       // cudaMalloc'ed (8-byte aligned)
-  static constexpr bool kVec8 = true;
-  static __device__ __forceinline__ unsigned long long counts(uint32_t c) {
-    return (unsigned long long)__popc(c & 7u) | ((unsigned long long)(c >> 3) << 32);
-  }
-  __device__ unsigned long long operator()(long long i) const { return counts(code[i]); }
-  __device__ void load8(long long i, unsigned long long (&v)[8]) const {
-    uint32_t b[8];
-    mpscan::load_bytes8(code, i, b);
+// bits of nodes 32w + s .. 32w + s + 31
+__device__ __forceinline__ uint32_t shifted_word(const uint32_t* __restrict__ bits, long long w, long long s) {
+  const long long i = 32 * w + s;
+  const long long q = i >> 5;
+  return __funnelshift_r(__ldg(bits + q), __ldg(bits + q + 1), (uint32_t)(i & 31));
+}
+
+// the eight corner bit-vectors of the cells whose corner 0 is a node of word w: index c = dx | dy << 1 | dz << 2
+__device__ __forceinline__ void corner_words(const uint32_t* __restrict__ bits, long long w, int H, int W, uint32_t (&v)[8]) {
+  const long long sy = W, sz = (long long)H * W;
+  v[0] = __ldg(bits + w);
+  v[1] = shifted_word(bits, w, 1);
+  v[2] = shifted_word(bits, w, sy);
+  v[3] = shifted_word(bits, w, sy + 1);
+  v[4] = shifted_word(bits, w, sz);
+  v[5] = shifted_word(bits, w, sz + 1);
+  v[6] = shifted_word(bits, w, sz + sy);
+  v[7] = shifted_word(bits, w, sz + sy + 1);
+}
+
+__device__ __forceinline__ int case_of(const uint32_t (&v)[8], int b) {
+  int k = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = counts(b[j]);
-  }
+  for (int c = 0; c < 8; ++c) k |= (int)((v[c] >> b) & 1u) << c;
+  return k;
+}
+
+// per word: x / y / z edge masks (bit b: node 32w+b owns an active +x / +y / +z edge) and the triangle count of its cells
+struct WordInfo {
+  uint32_t ex, ey, ez, nt;
 };
 
-// Stores the exclusive vertex offset of the nodes that own at least one vertex.  Faces look offsets up by node, but only
-// for nodes owning the active edge in question, so the other entries of the dense array are never read (and never
-// written: 80 k stores instead of 17 M at 257^3).
-struct OffsetsEmit {
-  uint32_t* voff;
-  __device__ void operator()(long long i, unsigned long long v, unsigned long long pre) const {
-    if ((uint32_t)v) voff[i] = (uint32_t)pre;
-  }
-};
-
-// Emission.  Phase 1 = the emit half of the ordered scan (block offsets come from the count pass): every active node
-// (owning a vertex or a triangle) is queued in shared memory with its exclusive (vertex, triangle) offsets; the order
-// inside the queue is irrelevant because every entry carries its own output positions.  Phase 2 spreads the queue's
-// work items -- 3 candidate vertices + MC_MAX_TRI * 3 face corners per entry -- over the CTA.
-constexpr int kItemsPerNode = 3 + 3 * MC_MAX_TRI;
-
-__global__ void __launch_bounds__(mpscan::kThreads)
-mesh_emit_kernel(const float* __restrict__ vol, const uint8_t* __restrict__ code, const uint8_t* __restrict__ cases,
-                 const uint32_t* __restrict__ voff, const unsigned long long* __restrict__ block_offsets,
-                 float* __restrict__ verts, int32_t* __restrict__ faces, int H, int W, long long n, float iso) {
-  __shared__ int q_node[mpscan::kChunk];
-  __shared__ uint32_t q_voff[mpscan::kChunk];
-  __shared__ uint32_t q_foff[mpscan::kChunk];
-  __shared__ int q_n;
-  if (threadIdx.x == 0) q_n = 0;        // (published by the barriers inside block_excl_scan)
-  const long long base = (long long)blockIdx.x * mpscan::kChunk + (long long)threadIdx.x * mpscan::kItems;
-  unsigned long long v[mpscan::kItems];
-  const CountF f{code};
-  mpscan::load_items(f, base, n, v);
-  unsigned long long s = 0;
+// ---- pass 2: one thread per word.  Uniform words (all eight shifted copies equal) leave at once.
+__global__ void __launch_bounds__(256)
+classify_words_kernel(const uint32_t* __restrict__ bits, WordInfo* __restrict__ info, long long n, int D, int H, int W) {
+  const long long n_words = (n + 31) >> 5;
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  uint32_t v[8];
+  corner_words(bits, w, H, W, v);
+  uint32_t mixed = 0;
 #pragma unroll
-  for (int j = 0; j < mpscan::kItems; ++j) s += v[j];
-  unsigned long long run = block_offsets[blockIdx.x] + mpscan::block_excl_scan(s, nullptr);
-#pragma unroll
-  for (int j = 0; j < mpscan::kItems; ++j) {
-    if (v[j]) {
-      const int slot = atomicAdd(&q_n, 1);
-      q_node[slot] = (int)(base + j);
-      q_voff[slot] = (uint32_t)run;
-      q_foff[slot] = (uint32_t)(run >> 32);
+  for (int c = 1; c < 8; ++c) mixed |= v[0] ^ v[c];
+  WordInfo wi{0u, 0u, 0u, 0u};
+  if (mixed) {
+    // which nodes of the word have a +x / +y / +z neighbour (a word may straddle rows and planes)
+    uint32_t xi = 0, yi = 0, zi = 0;
+    const long long i0 = 32 * w;
+    int x = (int)(i0 % W);
+    const long long t = i0 / W;
+    int y = (int)(t % H), z = (int)(t / H);
+    for (int b = 0; b < 32 && i0 + b < n; ++b) {
+      if (x + 1 < W) xi |= 1u << b;
+      if (y + 1 < H) yi |= 1u << b;
+      if (z + 1 < D) zi |= 1u << b;
+      if (++x == W) { x = 0; if (++y == H) { y = 0; ++z; } }
     }
-    run += v[j];
+    wi.ex = (v[0] ^ v[1]) & xi;
+    wi.ey = (v[0] ^ v[2]) & yi;
+    wi.ez = (v[0] ^ v[4]) & zi;
+    uint32_t cm = mixed & xi & yi & zi;
+    while (cm) {
+      const int b = __ffs((int)cm) - 1;
+      cm &= cm - 1;
+      wi.nt += c_mc_ntri[case_of(v, b)];
+    }
   }
-  __syncthreads();
-  const int items = q_n * kItemsPerNode;
+  info[w] = wi;
+}
+
+struct WordCountF {    // low 32: vertices owned by the word's nodes, high 32: triangles of its cells
+  const WordInfo* info;
+  static constexpr bool kVec8 = false;
+  __device__ unsigned long long operator()(long long w) const {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(info + w));
+    return (unsigned long long)(__popc(q.x) + __popc(q.y) + __popc(q.z)) | ((unsigned long long)q.w << 32);
+  }
+};
+
+struct PrefixEmit {    // exclusive (vertex, triangle) prefix of every word
+  unsigned long long* prefix;
+  __device__ void operator()(long long w, unsigned long long, unsigned long long pre) const { prefix[w] = pre; }
+};
+
+// id of the vertex on the +`axis` edge owned by node i (the edge must be active)
+__device__ __forceinline__ int32_t vertex_id(const WordInfo* __restrict__ info, const unsigned long long* __restrict__ prefix,
+                                             long long i, int axis) {
+  const long long w = i >> 5;
+  const int b = (int)(i & 31);
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(info + w));
+  const uint32_t below = (1u << b) - 1u;
+  uint32_t id = (uint32_t)__ldg(prefix + w) + __popc(q.x & below) + __popc(q.y & below) + __popc(q.z & below);
+  if (axis >= 1) id += (q.x >> b) & 1u;
+  if (axis == 2) id += (q.y >> b) & 1u;
+  return (int32_t)id;
+}
+
+// ---- pass 4: emission.  A warp takes 32 words at a time, keeps those with vertices or triangles, and handles each of
+// them with one lane per node: up to three vertices (vertex id = rank of (node, axis) in node order) and up to
+// MC_MAX_TRI triangles (face order = (cell linear index, table order); their offsets come from a warp scan).
+constexpr int kEmitThreads = 256;
+__global__ void __launch_bounds__(kEmitThreads)
+mesh_emit_kernel(const float* __restrict__ vol, const uint32_t* __restrict__ bits, const WordInfo* __restrict__ info,
+                 const unsigned long long* __restrict__ prefix, float* __restrict__ verts, int32_t* __restrict__ faces, int D,
+                 int H, int W, long long n, float iso) {
+  const long long n_words = (n + 31) >> 5;
+  const long long n_groups = (n_words + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (kEmitThreads / 32) + (threadIdx.x >> 5);
+  const long long n_warps = (long long)gridDim.x * (kEmitThreads / 32);
   const int plane = H * W;
-  for (int w = threadIdx.x; w < items; w += mpscan::kThreads) {
-    const int e = w / kItemsPerNode, sub = w - e * kItemsPerNode;
-    const int i = q_node[e];
-    const uint32_t c = __ldg(code + i);
-    if (sub < 3) {
-      // vertex on the owned edge along axis `sub`
-      if (!((c >> sub) & 1u)) continue;
-      const uint32_t vi = q_voff[e] + __popc(c & ((1u << sub) - 1u));
-      const int z = i / plane, r = i - z * plane, y = r / W, x = r - y * W;
-      const int step = sub == 0 ? 1 : (sub == 1 ? W : plane);
-      const float va = __ldg(vol + i), vb = __ldg(vol + i + step);
-      const float t = __fdiv_rn(__fsub_rn(iso, va), __fsub_rn(vb, va));
-      float p[3] = {(float)x, (float)y, (float)z};
-      p[sub] = __fadd_rn(p[sub], t);
-      float* o = verts + 3ll * vi;
-      o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
-    } else {
-      const int corner = sub - 3, t = corner / 3;
-      if (t >= (int)(c >> 3)) continue;
-      const int k = __ldg(cases + i);
-      const int ed = g_mc_tri[k][corner];
-      // edge -> owning node + axis.  edges 0-3 along x at (y,z) offsets, 4-7 along y at (x,z), 8-11 along z at (x,y)
-      const int axis = ed >> 2, q = ed & 3;
-      int ox = 0, oy = 0, oz = 0;
-      if (axis == 0) { oy = q & 1; oz = q >> 1; }
-      else if (axis == 1) { ox = q & 1; oz = q >> 1; }
-      else { ox = q & 1; oy = q >> 1; }
-      const int node = i + (oz * H + oy) * W + ox;
-      const uint32_t cn = __ldg(code + node) & 7u;
-      const uint32_t rank = __popc(cn & ((1u << axis) - 1u));
-      faces[3ll * (q_foff[e] + t) + (corner - 3 * t)] = (int32_t)(__ldg(voff + node) + rank);
+  for (long long g = warp0; g < n_groups; g += n_warps) {                       // (warp-uniform trip count)
+    const long long wl = g * 32 + lane;
+    uint4 mine = make_uint4(0u, 0u, 0u, 0u);
+    unsigned long long mypre = 0;
+    if (wl < n_words) {
+      mine = __ldg(reinterpret_cast<const uint4*>(info + wl));
+      mypre = __ldg(prefix + wl);
+    }
+    uint32_t active = __ballot_sync(0xffffffffu, (mine.x | mine.y | mine.z | mine.w) != 0u);
+    while (active) {                                                            // (warp-uniform)
+      const int src = __ffs((int)active) - 1;
+      active &= active - 1;
+      const long long w = g * 32 + src;
+      const uint32_t ex = __shfl_sync(0xffffffffu, mine.x, src), ey = __shfl_sync(0xffffffffu, mine.y, src);
+      const uint32_t ez = __shfl_sync(0xffffffffu, mine.z, src), nt = __shfl_sync(0xffffffffu, mine.w, src);
+      const unsigned long long pre = __shfl_sync(0xffffffffu, mypre, src);
+      const long long i = 32 * w + lane;                                        // this lane's node
+      const int z = (int)(i / plane), r = (int)(i - (long long)z * plane), y = r / W, x = r - y * W;
+      // ---- vertices on the owned edges
+      const uint32_t below = (1u << lane) - 1u;
+      const uint32_t code = ((ex >> lane) & 1u) | (((ey >> lane) & 1u) << 1) | (((ez >> lane) & 1u) << 2);
+      if (code) {
+        uint32_t vi = (uint32_t)pre + __popc(ex & below) + __popc(ey & below) + __popc(ez & below);
+        const float va = __ldg(vol + i);
+#pragma unroll
+        for (int axis = 0; axis < 3; ++axis) {
+          if (!((code >> axis) & 1u)) continue;
+          const long long step = axis == 0 ? 1 : (axis == 1 ? W : plane);
+          const float vb = __ldg(vol + i + step);
+          const float t = __fdiv_rn(__fsub_rn(iso, va), __fsub_rn(vb, va));
+          float p[3] = {(float)x, (float)y, (float)z};
+          p[axis] = __fadd_rn(p[axis], t);
+          float* o = verts + 3ll * vi;
+          o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+          ++vi;
+        }
+      }
+      // ---- triangles of the cell whose corner 0 is this node
+      if (nt) {                                                                 // (warp-uniform)
+        uint32_t v[8];
+        corner_words(bits, w, H, W, v);
+        const bool cell = i < n && x + 1 < W && y + 1 < H && z + 1 < D;
+        const int k = cell ? case_of(v, lane) : 0;
+        const int mytri = c_mc_ntri[k];
+        // exclusive warp scan of the triangle counts
+        unsigned long long incl = mpscan::warp_incl_scan((unsigned long long)mytri, lane);
+        const uint32_t foff = (uint32_t)(pre >> 32) + (uint32_t)incl - (uint32_t)mytri;
+        for (int corner = 0; corner < 3 * mytri; ++corner) {
+          const int ed = g_mc_tri[k][corner];
+          // edge -> owning node + axis.  edges 0-3 along x at (y,z) offsets, 4-7 along y at (x,z), 8-11 along z at (x,y)
+          const int axis = ed >> 2, q = ed & 3;
+          int ox = 0, oy = 0, oz = 0;
+          if (axis == 0) { oy = q & 1; oz = q >> 1; }
+          else if (axis == 1) { ox = q & 1; oz = q >> 1; }
+          else { ox = q & 1; oy = q >> 1; }
+          const long long node = i + ((long long)oz * H + oy) * W + ox;
+          faces[3ll * foff + corner] = vertex_id(info, prefix, node, axis);
+        }
+      }
     }
   }
 }

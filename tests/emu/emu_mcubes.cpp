@@ -37,38 +37,52 @@ int main(int argc, char** argv) {
   if ((long long)raw.size() != n * 4) { fprintf(stderr, "volume size mismatch\n"); return 2; }
   const float* vol = reinterpret_cast<const float*>(raw.data());
 
-  // workspace of mp_mcubes_create; the offset array is poisoned: only entries of vertex-owning nodes may be read
-  std::vector<uint8_t> code(n + 64, 0xEE), cases(n + 64, 0xEE);
-  std::vector<uint32_t> voff(n, 0xDEADBEEFu);
-  const int nb = mpscan::num_blocks(n);
+  // workspace of mp_mcubes_create (guard words behind every array)
+  const long long n_words = (n + 31) >> 5;
+  const long long pad = bits_pad_words(H, W);
+  std::vector<uint32_t> bits(n_words + pad, 0u);
+  std::vector<WordInfo> info(n_words + 4, WordInfo{0xEEEEEEEEu, 0xEEEEEEEEu, 0xEEEEEEEEu, 0xEEEEEEEEu});
+  std::vector<unsigned long long> prefix(n_words + 4, 0xDEADBEEFDEADBEEFull);
+  const int nb = mpscan::num_blocks(n_words);
   std::vector<unsigned long long> sums(nb + 1, 0);
   unsigned long long total[2] = {0, 0};
 
   // ---- mp_mcubes_count
-  const bool fast = getenv("MONOPORT_B200_MC_FAST") && atoi(getenv("MONOPORT_B200_MC_FAST"));
-  cuda_emu::launch(dim3((unsigned)D, (unsigned)((H + kClassRows - 1) / kClassRows)), dim3(32, kClassRows), [&] {
-    if (fast) classify_fast_kernel(vol, code.data(), cases.data(), D, H, W, iso);
-    else classify_kernel(vol, code.data(), cases.data(), D, H, W, iso);
-  });
-  CountF f{code.data()};
-  OffsetsEmit em{voff.data()};
+  {
+    const long long warps_needed = (n_words + kBitsUnroll - 1) / kBitsUnroll;
+    long long blocks = (warps_needed + kBitsThreads / 32 - 1) / (kBitsThreads / 32);
+    if (blocks > 3) blocks = 3;                       // force the grid-stride loop
+    cuda_emu::launch(dim3((unsigned)blocks), dim3(kBitsThreads), [&] { bits_kernel(vol, bits.data(), n, iso); });
+  }
+  for (long long w = n_words; w < n_words + pad; ++w)
+    if (bits[w] != 0u) { fprintf(stderr, "wrote into the bit padding\n"); return 3; }
+  cuda_emu::launch(dim3((unsigned)((n_words + 255) / 256)), dim3(256),
+                   [&] { classify_words_kernel(bits.data(), info.data(), n, D, H, W); });
+  WordCountF f{info.data()};
+  PrefixEmit em{prefix.data()};
   cuda_emu::launch(dim3(nb), dim3(mpscan::kThreads),
-                   [&] { mpscan::block_sums_kernel<CountF, mpscan::NoPost>(f, n, sums.data(), nb, total, mpscan::NoPost()); });
+                   [&] { mpscan::block_sums_kernel<WordCountF, mpscan::NoPost>(f, n_words, sums.data(), nb, total, mpscan::NoPost()); });
   cuda_emu::launch(dim3(nb), dim3(mpscan::kThreads),
-                   [&] { mpscan::emit_kernel<CountF, OffsetsEmit>(f, em, n, sums.data()); });
+                   [&] { mpscan::emit_kernel<WordCountF, PrefixEmit>(f, em, n_words, sums.data()); });
   if (total[1] != 0) { fprintf(stderr, "scan ticket not reset\n"); return 3; }
   const long long nv = (long long)(total[0] & 0xffffffffull), nf = (long long)(total[0] >> 32);
 
   // ---- mp_mcubes_emit
   std::vector<float> verts((size_t)nv * 3 + 1, -12345.f);
   std::vector<int32_t> faces((size_t)nf * 3 + 1, -7);
-  if (nv || nf)
-    cuda_emu::launch(dim3(nb), dim3(mpscan::kThreads), [&] {
-      mesh_emit_kernel(vol, code.data(), cases.data(), voff.data(), sums.data(), verts.data(), faces.data(), H, W, n, iso);
+  if (nv || nf) {
+    const long long n_groups = (n_words + 31) >> 5;
+    long long blocks = (n_groups + kEmitThreads / 32 - 1) / (kEmitThreads / 32);
+    if (blocks > 2) blocks = 2;
+    cuda_emu::launch(dim3((unsigned)blocks), dim3(kEmitThreads), [&] {
+      mesh_emit_kernel(vol, bits.data(), info.data(), prefix.data(), verts.data(), faces.data(), D, H, W, n, iso);
     });
+  }
   if (verts[(size_t)nv * 3] != -12345.f || faces[(size_t)nf * 3] != -7) { fprintf(stderr, "wrote past the outputs\n"); return 3; }
-  for (long long i = n; i < n + 64; ++i)
-    if (code[i] != 0xEE || cases[i] != 0xEE) { fprintf(stderr, "wrote past the code volume\n"); return 3; }
+  for (long long w = n_words; w < n_words + 4; ++w)
+    if (info[w].ex != 0xEEEEEEEEu || prefix[w] != 0xDEADBEEFDEADBEEFull) { fprintf(stderr, "wrote past the word arrays\n"); return 3; }
+  for (long long k = 0; k < nf * 3; ++k)
+    if (faces[k] < 0 || faces[k] >= nv) { fprintf(stderr, "face index out of range\n"); return 3; }
   write_file(argv[6], verts.data(), (size_t)nv * 3 * sizeof(float));
   write_file(argv[7], faces.data(), (size_t)nf * 3 * sizeof(int32_t));
   printf("%lld %lld\n", nv, nf);

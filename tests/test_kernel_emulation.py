@@ -35,13 +35,12 @@ def emu_mcubes(tmp_path_factory):
     return _build(str(tmp_path_factory.mktemp("emu")), "emu_mcubes")
 
 
-def _run_mcubes(exe, vol, tmp_path, iso=0.5, fast=False):
+def _run_mcubes(exe, vol, tmp_path, iso=0.5):
     D, H, W = vol.shape
     vin, vout, fout = (str(tmp_path / n) for n in ("vol.f32", "verts.f32", "faces.i32"))
     np.ascontiguousarray(vol, dtype=np.float32).tofile(vin)
-    env = dict(os.environ, MONOPORT_B200_MC_FAST="1" if fast else "0")      # opt-in classify with the uniform-chunk fast path
     r = subprocess.run([exe, str(D), str(H), str(W), repr(float(iso)), vin, vout, fout], capture_output=True, text=True,
-                       timeout=600, env=env)
+                       timeout=600)
     assert r.returncode == 0, r.stderr
     nv, nf = (int(x) for x in r.stdout.split())
     v = np.fromfile(vout, dtype=np.float32).reshape(-1, 3)
@@ -50,12 +49,11 @@ def _run_mcubes(exe, vol, tmp_path, iso=0.5, fast=False):
     return v, f
 
 
-@pytest.mark.parametrize("fast", [False, True])
 @pytest.mark.parametrize("kind,R", [("sphere", 33), ("ellipsoid", 40), ("two_blobs", 49)])
-def test_mcubes_kernels_match_oracle_on_analytic_volumes(emu_mcubes, tmp_path, kind, R, fast):
+def test_mcubes_kernels_match_oracle_on_analytic_volumes(emu_mcubes, tmp_path, kind, R):
     vol = spec.analytic_volume(R, kind)
     V, F = spec.marching_cubes_ref(vol)
-    v, f = _run_mcubes(emu_mcubes, vol, tmp_path, fast=fast)
+    v, f = _run_mcubes(emu_mcubes, vol, tmp_path)
     assert np.array_equal(f, F), "topology must be bit-exact"
     assert v.shape == V.shape and np.array_equal(v, V)
     if kind == "sphere":
@@ -77,7 +75,7 @@ def test_mcubes_kernels_match_oracle_on_noise(emu_mcubes, tmp_path, shape):
     row tiles hanging over H, scan chunks hanging over n)."""
     vol = np.random.default_rng(sum(shape)).random(shape, dtype=np.float32)
     V, F = spec.marching_cubes_ref(vol)
-    v, f = _run_mcubes(emu_mcubes, vol, tmp_path, fast=(sum(shape) % 2 == 0))
+    v, f = _run_mcubes(emu_mcubes, vol, tmp_path)
     assert np.array_equal(f, F.reshape(-1, 3))
     assert v.shape == V.shape and np.array_equal(v, V)
 
