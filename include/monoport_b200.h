@@ -33,6 +33,7 @@ extern "C" {
 #define MP_E_UNSUPPORTED (-3) /* shape / mode not supported by this kernel   */
 #define MP_E_CAPACITY (-4)  /* caller-provided output buffer too small       */
 #define MP_E_NOMEM (-5)
+#define MP_E_RANGE (-6)     /* inputs outside the validated range of the requested fast path; use the exact one */
 
 /* last_op of the head: heads/SurfaceClassifier.py:68-69 (None / nn.Sigmoid / nn.Tanh) */
 #define MP_LAST_NONE 0
@@ -47,9 +48,8 @@ extern "C" {
 #define MP_MODE_FP32 0   /* CUDA-core fp32 everywhere (|err| ~1e-6 vs the reference)                 */
 #define MP_MODE_TC 1     /* tcgen05 fp16 operands / fp32 TMEM accumulators, last layer fp32 (<=1e-4)   */
 #define MP_MODE_AUTO 2   /* TC when the head/feature shape is supported by the tcgen05 kernel, else FP32 */
-/* MP_MODE_TC picks the tensor-core program by query size; these two pin it (tests / benchmarks):                    */
-#define MP_MODE_TC_V2 3  /* all five layers per point (layer 0 recomputed for the second half of layer 1)            */
-#define MP_MODE_TC_V3 4  /* layer 0 hoisted to texels (per-frame W0.F product, sampled per point); default >= 2^20 pts */
+/* 3 was MP_MODE_TC_V2 (the self-contained tensor-core program, removed in round 2: 335 vs 485 Mpoints/s); rejected now */
+#define MP_MODE_TC_V3 4  /* alias of MP_MODE_TC: the one tensor-core program (layer 0 hoisted to texels)                     */
 
 const char* mp_last_error(void);
 int mp_version(void);
@@ -70,6 +70,12 @@ int mp_mlp_create(int n_layers, const int* channels, const float* const* weights
 int mp_mlp_destroy(mp_mlp_t* h);
 /* 1 if MP_MODE_TC is available for this head on this device */
 int mp_mlp_tc_supported(const mp_mlp_t* h);
+/* Validated range of the tensor-core program (no reference counterpart: the reference computes in fp32 throughout,
+ * MonoPortNet.py:86-89).  MP_MODE_TC / MP_MODE_AUTO evaluate a frame on the tensor cores only while its largest
+ * |feature| stays under `limit` (defaults: 12 geometry head, 8 colour head -- both keep |error| <= 1e-4 on what query()
+ * returns); frames above it take the exact fp32 kernel.  The choice is made on the device from the frame itself.
+ * +infinity disables the guard. */
+int mp_mlp_set_tc_feature_limit(mp_mlp_t* h, float limit);
 
 /* ---------------------------------------------------------------------------------------------
  * Feature volume.  Replaces the tensor index() samples (geometry.py:4-16): one [C,H,W] fp32 NCHW map
@@ -187,8 +193,9 @@ int mp_forward_vertices(const float* vol_dev, int R, int direction, int64_t* x_d
  * Direct rendering of the visible surface with the colour head.  Replaces colorization (RTL/main.py:212-249): vertex i =
  * (X[i], Y[i], R - Z[i]) of mp_forward_vertices -> world space by mat_color (:201-210) -> netC.query -> pred*0.5+0.5 ->
  * canvas[X[i], Y[i], :]  ([R,R,3] float32, prepared by the caller), in ONE launch without intermediate tensors.
- * Needs the tensor-core program of the colour head (opt-in, MONOPORT_B200_TC_NETC=1); MP_E_UNSUPPORTED otherwise --
- * the binding then takes the generic mp_query_points route.
+ * Needs the tensor-core program of the colour head (MP_E_UNSUPPORTED otherwise) and a frame inside its validated feature
+ * range (MP_E_RANGE otherwise, see mp_mlp_set_tc_feature_limit) -- the binding then takes the generic mp_query_points
+ * route.
  * ------------------------------------------------------------------------------------------- */
 int mp_colorize_surface(mp_mlp_t* mlp, mp_feat_t* feat, const int64_t* x_dev, const int64_t* y_dev, const float* z_dev,
                         int64_t n, int R, const float* b_min3, const float* b_max3, const float* calib12, int projection,

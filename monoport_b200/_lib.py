@@ -11,7 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmonoport_b200.so")
 
 MP_OK = 0
-MODE_FP32, MODE_TC, MODE_AUTO, MODE_TC_V2, MODE_TC_V3 = 0, 1, 2, 3, 4
+MP_E_RANGE = -6
+MODE_FP32, MODE_TC, MODE_AUTO, MODE_TC_V3 = 0, 1, 2, 4
 LAST_NONE, LAST_SIGMOID, LAST_TANH = 0, 1, 2
 PROJ_ORTHOGONAL, PROJ_PERSPECTIVE = 0, 1
 
@@ -32,6 +33,7 @@ SIGNATURES = {
     "mp_mlp_create": (c_int, [c_int, P(c_int), P(c_void_p), P(c_void_p), c_int, c_int, c_int, P(c_void_p)]),
     "mp_mlp_destroy": (c_int, [c_void_p]),
     "mp_mlp_tc_supported": (c_int, [c_void_p]),
+    "mp_mlp_set_tc_feature_limit": (c_int, [c_void_p, c_float]),
     "mp_feat_create": (c_int, [c_int, c_int, c_int, P(c_void_p)]),
     "mp_feat_upload": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "mp_feat_upload_nhwc": (c_int, [c_void_p, c_void_p, c_void_p]),

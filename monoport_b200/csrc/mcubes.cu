@@ -111,8 +111,9 @@ extern "C" int mp_mcubes_emit(mp_mcubes_t* h, const float* vol_dev, float iso, f
   cudaStream_t st = (cudaStream_t)stream;
   const long long n_groups = (h->n_words + 31) >> 5;
   const long long blocks_needed = (n_groups + kEmitThreads / 32 - 1) / (kEmitThreads / 32);
-  const long long cap = (long long)sm_count() * 8;
-  mesh_emit_kernel<<<(unsigned)(blocks_needed < cap ? blocks_needed : cap), kEmitThreads, 0, st>>>(
+  // one warp per 32 words: every warp that finds a surface inside its words works through a chain of dependent L2
+  // accesses, so the more warps the better (no grid cap: 2 073 CTAs at 257^3)
+  mesh_emit_kernel<<<(unsigned)blocks_needed, kEmitThreads, 0, st>>>(
       vol_dev, h->bits, h->info, h->prefix, verts_dev, faces_dev, h->D, h->H, h->W, h->n, iso);
   MP_CUDA(cudaGetLastError());
   return MP_OK;

@@ -105,7 +105,7 @@ classify_words_kernel(const uint32_t* __restrict__ bits, WordInfo* __restrict__ 
     while (cm) {
       const int b = __ffs((int)cm) - 1;
       cm &= cm - 1;
-      wi.nt += c_mc_ntri[case_of(v, b)];
+      wi.nt += (uint32_t)__ldg(&g_mc_tri[case_of(v, b)][15]);      // byte 15 of a table row = its triangle count
     }
   }
   info[w] = wi;
@@ -195,21 +195,34 @@ mesh_emit_kernel(const float* __restrict__ vol, const uint32_t* __restrict__ bit
         corner_words(bits, w, H, W, v);
         const bool cell = i < n && x + 1 < W && y + 1 < H && z + 1 < D;
         const int k = cell ? case_of(v, lane) : 0;
-        const int mytri = c_mc_ntri[k];
+        // one 16-byte load: bytes 0..14 = edge ids of the cell's triangles, byte 15 = their number
+        const uint4 row = __ldg(reinterpret_cast<const uint4*>(&g_mc_tri[k][0]));
+        const uint32_t rw[4] = {row.x, row.y, row.z, row.w};
+        const int mytri = (int)(row.w >> 24);
         // exclusive warp scan of the triangle counts
         unsigned long long incl = mpscan::warp_incl_scan((unsigned long long)mytri, lane);
         const uint32_t foff = (uint32_t)(pre >> 32) + (uint32_t)incl - (uint32_t)mytri;
-        for (int corner = 0; corner < 3 * mytri; ++corner) {
-          const int ed = g_mc_tri[k][corner];
-          // edge -> owning node + axis.  edges 0-3 along x at (y,z) offsets, 4-7 along y at (x,z), 8-11 along z at (x,y)
-          const int axis = ed >> 2, q = ed & 3;
-          int ox = 0, oy = 0, oz = 0;
-          if (axis == 0) { oy = q & 1; oz = q >> 1; }
-          else if (axis == 1) { ox = q & 1; oz = q >> 1; }
-          else { ox = q & 1; oy = q >> 1; }
-          const long long node = i + ((long long)oz * H + oy) * W + ox;
-          faces[3ll * foff + corner] = vertex_id(info, prefix, node, axis);
+        // all vertex-id lookups of the cell are issued before the first store (independent loads in flight instead of
+        // one L2 round trip per face corner)
+        int32_t ids[3 * MC_MAX_TRI];
+#pragma unroll
+        for (int corner = 0; corner < 3 * MC_MAX_TRI; ++corner) {
+          ids[corner] = 0;
+          if (corner < 3 * mytri) {
+            const int ed = (int)((rw[corner >> 2] >> (8 * (corner & 3))) & 0xFFu);
+            // edge -> owning node + axis.  edges 0-3 along x at (y,z) offsets, 4-7 along y at (x,z), 8-11 along z at (x,y)
+            const int axis = ed >> 2, q = ed & 3;
+            int ox = 0, oy = 0, oz = 0;
+            if (axis == 0) { oy = q & 1; oz = q >> 1; }
+            else if (axis == 1) { ox = q & 1; oz = q >> 1; }
+            else { ox = q & 1; oy = q >> 1; }
+            const long long node = i + ((long long)oz * H + oy) * W + ox;
+            ids[corner] = vertex_id(info, prefix, node, axis);
+          }
         }
+#pragma unroll
+        for (int corner = 0; corner < 3 * MC_MAX_TRI; ++corner)
+          if (corner < 3 * mytri) faces[3ll * foff + corner] = ids[corner];
       }
     }
   }

@@ -3,6 +3,7 @@
 #include "mp_common.cuh"
 #include <stdlib.h>
 #include <atomic>
+#include <math.h>
 
 static thread_local char g_err[512] = "";
 
@@ -84,6 +85,13 @@ extern "C" int mp_mlp_create(int n_layers, const int* channels, const float* con
   h->last_op = last_op;
   static std::atomic<unsigned long long> next_gen{1};
   h->gen = next_gen.fetch_add(1);
+  {
+    // validated feature range of the tensor-core programs (precision): measured error ~2.7e-5 x (max|feature| / 5)
+    // for the geometry head, 5.6e-5 x (max|feature| / 5) for the colour head; the limits keep both under 1e-4 with margin
+    const bool colour = channels[n_layers] == 3;
+    const char* v = getenv("MONOPORT_B200_TC_FEATURE_LIMIT");
+    h->tc_amax_limit = v ? (float)atof(v) : (colour ? 8.0f : 12.0f);
+  }
   cudaGetDevice(&h->device);
   for (int l = 0; l <= n_layers; ++l) h->channels[l] = channels[l];
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -121,6 +129,13 @@ extern "C" int mp_mlp_create(int n_layers, const int* channels, const float* con
 
 extern "C" int mp_mlp_tc_supported(const mp_mlp_t* h) { return h ? h->tc_ok : 0; }
 
+extern "C" int mp_mlp_set_tc_feature_limit(mp_mlp_t* h, float limit) {
+  MP_REQUIRE(h, "NULL handle");
+  MP_REQUIRE(limit > 0.f, "the limit must be positive (+inf disables the guard)");
+  h->tc_amax_limit = limit;
+  return MP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // feature volume: NCHW fp32 -> NHWC fp32 (channel-last: one bilinear tap = one contiguous vector)
 // ---------------------------------------------------------------------------------------------
@@ -148,6 +163,7 @@ extern "C" int mp_feat_destroy(mp_feat_t* h) {
   if (h->g0) cudaFree(h->g0);
   if (h->f16) cudaFree(h->f16);
   if (h->s4tex) cudaFree(h->s4tex);
+  if (h->amax) cudaFree(h->amax);
   delete h;
   return MP_OK;
 }
@@ -163,6 +179,8 @@ extern "C" int mp_feat_create(int C, int H, int W, mp_feat_t** out) {
   const size_t n = (size_t)C * H * W;
   cudaError_t e = cudaMalloc(&h->nhwc32, n * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&h->staging, n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&h->amax, sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(h->amax, 0, sizeof(unsigned));
   if (e != cudaSuccess) {
     mp_set_error("mp_feat_create: %s", cudaGetErrorString(e));
     mp_feat_destroy(h);
@@ -185,6 +203,7 @@ extern "C" int mp_feat_upload(mp_feat_t* h, const float* nchw, int on_device, vo
   dim3 grid((HW + 31) / 32, (h->C + 31) / 32), block(32, 8);
   nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(src, h->nhwc32, h->C, HW);
   MP_CUDA(cudaGetLastError());
+  MP_CUDA(cudaMemsetAsync(h->amax, 0, sizeof(unsigned), st));
   h->version += 1;
   return MP_OK;
 }
@@ -195,6 +214,7 @@ extern "C" int mp_feat_upload_nhwc(mp_feat_t* h, const float* nhwc_dev, void* st
   MP_REQUIRE(h && nhwc_dev, "NULL handle or data");
   const size_t n = (size_t)h->C * h->H * h->W;
   MP_CUDA(cudaMemcpyAsync(h->nhwc32, nhwc_dev, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  MP_CUDA(cudaMemsetAsync(h->amax, 0, sizeof(unsigned), (cudaStream_t)stream));
   h->version += 1;
   return MP_OK;
 }
@@ -224,16 +244,25 @@ void mp_fill_grid_geom(MpPointSrc& s, int res, int node_stride, int r_final, con
 
 int mp_query_dispatch(mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal, const MpOutDst& dst,
                       int mode, cudaStream_t st) {
-  if (mode == MP_MODE_AUTO) mode = mlp->tc_ok ? MP_MODE_TC : MP_MODE_FP32;
-  if (mode == MP_MODE_TC || mode == MP_MODE_TC_V2 || mode == MP_MODE_TC_V3) {
+  // the tensor-core program covers maps of at most 65536 texels (16-bit texel indices in registers)
+  const bool tc_can = mlp->tc_ok && (long long)feat->H * feat->W <= 65536;
+  if (mode == MP_MODE_AUTO) mode = tc_can ? MP_MODE_TC : MP_MODE_FP32;
+  if (mode == MP_MODE_TC || mode == MP_MODE_TC_V3) {
     if (!mlp->tc_ok) {
       mp_set_error("MP_MODE_TC requested but the tcgen05 kernel does not support this head/device");
       return MP_E_UNSUPPORTED;
     }
-    return mp_launch_query_tc(mlp, feat, src, cal, dst, st, mode == MP_MODE_TC_V2 ? 2 : (mode == MP_MODE_TC_V3 ? 3 : 0));
+    // Range guard: the tensor-core program is validated (<= 1e-4 on what query() returns) for frames whose largest
+    // |feature| stays under the head's limit.  The decision is taken on the device, per launch, from the frame's own
+    // maximum (no host synchronisation, graph-capturable): the tensor-core launch runs when the frame is in range, the
+    // exact fp32 launch when it is not; the other one returns at once.  Peer stores exist in the tensor-core kernel only.
+    const bool guarded = isfinite(mlp->tc_amax_limit) && dst.n_peers == 0;
+    int rc = mp_launch_query_tc(mlp, feat, src, cal, dst, st, guarded ? MP_GUARD_IN_RANGE : MP_GUARD_NONE);
+    if (rc != MP_OK || !guarded) return rc;
+    return mp_launch_query_fp32(mlp, feat, src, cal, dst, st, MP_GUARD_OUT_OF_RANGE);
   }
   if (mode != MP_MODE_FP32) {
-    mp_set_error("bad mode %d", mode);
+    mp_set_error("bad mode %d (3 was the removed MP_MODE_TC_V2)", mode);
     return MP_E_INVALID;
   }
   return mp_launch_query_fp32(mlp, feat, src, cal, dst, st);

@@ -62,6 +62,9 @@ struct mp_mlp {
   int tc_ok;
   int device;
   unsigned long long gen;            // unique per mp_mlp_create (process-wide counter, never 0): keys per-feature caches
+  // validated range of the tensor-core program: frames whose largest |feature| exceeds this limit are evaluated by the
+  // exact fp32 kernel instead (decided on the DEVICE, per launch; see mp_query_dispatch).  +inf disables the guard.
+  float tc_amax_limit;
 };
 
 struct mp_feat {
@@ -80,6 +83,9 @@ struct mp_feat {
   unsigned long long g0_owner;
   unsigned long long g0_version;
   unsigned long long version;   // bumped by every mp_feat_upload
+  // max |feature| of the current frame as float bits (non-negative floats order like unsigned integers): zeroed by every
+  // upload, raised by the staging pass of the per-frame G0 kernels; read by the range guard of the query kernels
+  unsigned* amax;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -215,10 +221,19 @@ __device__ __forceinline__ float mp_last_op(float v, int last_op) {
 __device__ __forceinline__ float mp_lrelu(float v) { return v > 0.f ? v : v * MP_LEAKY_SLOPE; }
 
 // host-side launchers implemented in the kernel files
+// `guard`: the launch is conditional on the frame's feature range (feat->amax vs mlp->tc_amax_limit), evaluated on the device:
+//   MP_GUARD_NONE always run, MP_GUARD_IN_RANGE run when max|feature| <= limit, MP_GUARD_OUT_OF_RANGE run when it is above.
+enum { MP_GUARD_NONE = 0, MP_GUARD_IN_RANGE = 1, MP_GUARD_OUT_OF_RANGE = 2 };
 int mp_launch_query_fp32(const mp_mlp* mlp, const mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
-                         const MpOutDst& dst, cudaStream_t st);
+                         const MpOutDst& dst, cudaStream_t st, int guard = MP_GUARD_NONE);
 int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
-                       const MpOutDst& dst, cudaStream_t st, int program /* 0 auto, 2, 3 */);
+                       const MpOutDst& dst, cudaStream_t st, int guard = MP_GUARD_NONE);
+// device-side predicate shared by the kernels: true = this launch must do nothing
+__device__ __forceinline__ bool mp_guard_skips(const unsigned* amax, float limit, int guard) {
+  if (guard == MP_GUARD_NONE || amax == nullptr) return false;
+  const bool above = __uint_as_float(*amax) > limit;
+  return guard == MP_GUARD_IN_RANGE ? above : !above;
+}
 // colour head only: vertices (X, Y, R - Z) of the visible surface -> world -> colour -> canvas[X, Y, :]   (query_tc.cu)
 int mp_launch_colour_surface(const mp_mlp* mlp, mp_feat* feat, const long long* X, const long long* Y, const float* Z, long long n,
                              int R, const float* b_min3, const float* b_max3, const MpCalib& cal, float* canvas, cudaStream_t st);

@@ -36,6 +36,9 @@ struct Fp32Params {
   int last_op;
   int h_ping, h_pong;
   const float* feat;            // NHWC fp32
+  const unsigned* amax;         // range guard (see mp_guard_skips)
+  float amax_limit;
+  int guard;
 };
 
 // acc[j][p] += w_j * act[p]
@@ -124,6 +127,7 @@ query_fp32_kernel(Fp32Params prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
   float* sMeta = sB + (size_t)prm.h_pong * P;        // [8][P]: in_img, u, v, z_feat, (4 spare)
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  if (mp_guard_skips(prm.amax, prm.amax_limit, prm.guard)) return;      // (uniform over the grid)
 
   long long n = src.n;
   if (src.count_dev) {
@@ -244,7 +248,7 @@ int launch(const Fp32Params& prm, const MpPointSrc& src, const MpCalib& cal, con
 }  // namespace
 
 int mp_launch_query_fp32(const mp_mlp* mlp, const mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
-                         const MpOutDst& dst, cudaStream_t st) {
+                         const MpOutDst& dst, cudaStream_t st, int guard) {
   if (src.n <= 0) return MP_OK;
   if (dst.n_peers > 0) {
     mp_set_error("peer stores (fused slab exchange) are implemented by the tensor-core program only");
@@ -279,6 +283,7 @@ int mp_launch_query_fp32(const mp_mlp* mlp, const mp_feat* feat, const MpPointSr
   prm.last_op = mlp->last_op;
   prm.h_ping = ping; prm.h_pong = pong;
   prm.feat = feat->nhwc32;
+  prm.amax = feat->amax; prm.amax_limit = mlp->tc_amax_limit; prm.guard = guard;
   int dev = 0, sms = 148, max_smem = 0;
   MP_CUDA(cudaGetDevice(&dev));
   MP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

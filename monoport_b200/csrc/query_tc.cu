@@ -7,33 +7,21 @@
 // bias of every layer are applied in fp32 in the epilogue (so K is exactly 256-aligned, no padding); the last layer
 // (385 -> R) runs in fp32 on CUDA cores from the fp32 layer-3 accumulators and the fp32-sampled features.
 //
-// One persistent CTA per SM, a tile = 128 points = the M dimension of every MMA (one TMEM lane per point):
-//   X  [128 x 256] fp16 sampled features, K-major SWIZZLE_128B, resident in smem for the whole tile (skip operand of
-//      every layer; the skip-concat is just extra K-blocks of the same accumulation);
-//   weights stream L2 -> smem through a 3-stage ring of 32 KB tiles filled by cp.async.bulk (TMA engine), pre-packed on
-//      the host in exactly the order the MMA warp consumes them;
-//   layer 0 is produced in 8 chunks of 128 channels: acc0 (TMEM) -> epilogue (bias, z, leaky-relu, fp16) -> smem H0
-//      chunk -> immediately consumed as a K-chunk of layer 1, so the 1024-wide activation never exists in full;
-//   TMEM (512 columns) cannot hold layer 1's 512 accumulators next to a layer-0 chunk, so layer 1 is evaluated in two
-//      halves of 256 outputs and layer 0 is recomputed for the second half (+22% MMA work, documented in DESIGN.md);
-//   H1, H2 are written back to TMEM as packed fp16 and consumed by the next layer as the A operand straight from
-//      TMEM (tcgen05.mma with A in tensor memory), so they never touch shared memory.
-// TMEM map: [0,256)   acc1-half, later acc2
-//           [256,384) acc0 buffer 0, later H1 (ch 256..511), later acc3
-//           [384,512) acc0 buffer 1 during the FIRST half only (double-buffered layer-0 chunks), then H1 (ch 0..255), later H2
+// One persistent CTA per SM, a tile = 128 points = the M dimension of every MMA (one TMEM lane per point).  Layer 0 is
+// hoisted from points to texels (g0_tc_kernel builds G0 = W0f . F per frame on the tensor cores and the main kernel SAMPLES
+// the 1024-channel layer-0 pre-activation, see "program v3" below); layer 1 owns all 512 TMEM columns and is drained in
+// place; H1, H2 feed the next layer as the A operand from TMEM; weights stream L2 -> smem through a 3-stage ring of 32 KB
+// tiles filled by cp.async.bulk (TMA engine), pre-packed on the host in exactly the order the MMA warp consumes them.
 //
-// Two variants of the same kernel (template parameter CG):
-//   CG = 1  one CTA per tile, tcgen05.mma.cta_group::1 (M = 128), weight ring 3 x 32 KB;
-//   CG = 2  a 2-CTA cluster (one TPC) runs cta_group::2 MMAs with M = 256 = 128 points of each CTA; every weight tile is
-//           split between the two CTAs' shared memories, so each SM ingests (and reads) only half of the weight bytes
-//           per point -- the weight stream is the bottleneck of the CG = 1 kernel (ncu: tensor pipe 35% active, the MMA
-//           warp spends its time waiting for weight stages).  Ring 6 x 16 KB per CTA.  The leader CTA (rank 0) issues all
-//           MMAs; cross-CTA hand-offs (operands ready / accumulators drained) are mbarrier arrivals on the leader's
-//           barriers (mapa + mbarrier.arrive.release.cluster), MMA completions are multicast to both CTAs by
-//           tcgen05.commit.multicast.
+// Round 2 removed two variants that had been kept selectable: the self-contained program v2 (all five layers per point,
+// layer 0 recomputed for the second half of layer 1: 335 vs 485 Mpoints/s) and the cta_group::2 flavour (a CTA pair
+// sharing every weight tile).  tools/tc_rate.cu measures why the pair does not pay on this chip: a 128x256x16 fp16 MMA
+// issued back to back from shared-memory operands takes 246 cycles with one CTA and 247.6 cycles for the M = 256 pair
+// instruction -- the same per-SM rate -- and the pair loses 40 more cycles per MMA to cluster-scope waits once the
+// weights stream (profiles/r02_call2_tc_rate_probe.txt).
 //
-// Warp roles (384 threads): warp 0 weight producer, warp 1 MMA issuer (one lane), warp 2 TMEM allocator, warps 4-11
-// workers: all eight sample the tile's X, then act as two epilogue warpgroups (each drains half of the columns).
+// Warp roles (384 threads): warp 0 weight producer, warp 1 MMA issuer (one lane), warps 2-3 samplers (X operand, one tile
+// ahead; warp 2 also owns the TMEM allocation), warps 4-11 workers: layer-0 chunk generators, then two epilogue warpgroups.
 #include "mp_common.cuh"
 #include "tc_ptx.cuh"
 #include <stdlib.h>
@@ -44,32 +32,24 @@ constexpr int kC = 256;                 // feature channels
 constexpr int kTile = 128;              // points per tile
 constexpr int kThreads = 384;
 
-template <int CG> struct Cfg {
-  static constexpr int Stages = 3 * CG;
-  static constexpr int StageBytes = 32768 / CG;
+struct Cfg {                                        // weight ring: 3 stages of 32 KB
+  static constexpr int Stages = 3;
+  static constexpr int StageBytes = 32768;
   static constexpr int Sub = StageBytes / 2;       // second K-block of a two-K-block (128-row tile) stage
 };
-constexpr int kStages = 6;                          // barrier slots reserved (max over variants)
+constexpr int kStages = 3;                          // weight-ring barrier slots
 constexpr int kRingBytes = 98304;
 constexpr int kL0 = 1024, kL1 = 512, kL2 = 256, kL3 = 128;
 constexpr int kMaxRes = 1;             // output channels handled by the fp32 tail (PIFuNetGMLP: 1)
 
 // per-tile weight stream (32 KB stages), in MMA consumption order
-constexpr int kStagesPerHalf = 16 + 16 + 4;                       // L0 (8 chunks x 2) + L1 hidden (8 x 2) + L1 skip
-constexpr int kStagesPerTile = 2 * kStagesPerHalf + 12 + 4;       // + L2 (8 hidden + 4 skip) + L3 (2 hidden + 2 skip)
-constexpr int kStagesPerTile3 = 32 + 8 + 12 + 4;                  // v3: L1 hidden (8 chunks x 2 K-blocks x 2 N-halves) + L1 skip + L2 + L3
-
-// TMEM columns
-constexpr uint32_t kColAcc1 = 0, kColAcc0 = 256, kColH1lo = 384, kColH1hi = 256, kColH2 = 384, kColAcc3 = 256;
+constexpr int kStagesPerTile3 = 32 + 8 + 12 + 4;                  // L1 hidden (8 chunks x 2 K-blocks x 2 N-halves) + L1 skip + L2 + L3
 
 constexpr int kSideFloats = kL0 + kL1 + kL2 + kL3;      // 1920 hidden output channels over layers 0..3
 __host__ __device__ constexpr int side_off(int l) { return l == 0 ? 0 : l == 1 ? kL0 : l == 2 ? kL0 + kL1 : kL0 + kL1 + kL2; }
 
 struct TcPack {
-  __half* wstream;        // CG=1: kStagesPerTile * 32 KB
-  __half* wstream2[2];    // CG=2: per cluster rank, kStagesPerTile * 16 KB
-  __half* w3stream;       // v3 (layer 0 hoisted to texels): kStagesPerTile3 * 32 KB
-  __half* w3stream2[2];   // v3, CG=2
+  __half* w3stream;       // stage stream of a tile: kStagesPerTile3 (geometry) / kStagesPerTileC (colour) x 32 KB
   __half* d_bias0;        // fp16 device copies of the layer-0 bias / depth column for per-lane channel access (v3 H0 generation)
   __half* d_wz0;
   uint8_t* d_w0t;         // the same as fp16 SWIZZLE_128B tiles [n tile 4][K block 4][256 x 64] for g0_tc_kernel
@@ -87,7 +67,6 @@ struct TcPack {
 
 struct TcParams {
   const __half* wstream;
-  const __half* wstream2[2];
   // per-channel bias and depth-column weight of layers 0..3, carried in the kernel parameter (constant) bank: the
   // epilogue reads them with warp-uniform indices, so they cost no load instructions and no shared memory
   alignas(16) float bias_all[kSideFloats];
@@ -110,11 +89,14 @@ struct TcParams {
   int exp;                    // timing experiments only (MONOPORT_B200_TC_EXP bitmask; results are WRONG when set):
                               // 1 = weights not re-streamed, 2 = layer-0 gathers all hit texel 0, 4 = X taps all hit texel 0
   unsigned long long* trace;  // optional [128] absolute clock64 stamps of CTA 0's tile kTraceTile (MONOPORT_B200_TC_TRACE=1)
+  const unsigned* amax;       // range guard (see mp_guard_skips): max |feature| of the frame, limit of this head, sense
+  float amax_limit;
+  int guard;
 };
 constexpr int kTraceTile = 8;
 // v3 event ids: MMA issuer 0..31, worker warp 4 at 32.., worker warp 8 at 64.., sampler warp 2 at 96..
 #define TRACE(cond, id) do { if (prm.trace && (cond)) prm.trace[id] = (unsigned long long)clock64(); } while (0)
-enum Prof { P_TOTAL = 0, P_XREADY, P_ACC0FREE, P_WFULL, P_WPEER, P_H0READY, P_ACC1DRAINED, P_H1READY, P_H2READY,
+enum Prof { P_TOTAL = 0, P_XREADY, P_ACC0FREE, P_WFULL, P_UNUSED4, P_H0READY, P_ACC1DRAINED, P_H1READY, P_H2READY,
             P_W_SAMPLE = 16, P_W_ACC0FULL, P_W_H0FREE, P_W_ACC1FULL, P_W_ACC2FULL, P_W_ACC3FULL, P_W_DRAIN0, P_W_DRAIN1,
             P_W_DRAIN2, P_W_DRAIN3, P_W_XFREE };
 #define PROF_T0() const long long _t0 = prof ? clock64() : 0
@@ -127,14 +109,13 @@ struct Smem {
   static constexpr int Wr = H0 + 65536;                         // kStages x 32 KB
   static constexpr int Small = Wr + kRingBytes;                 // zf[128], inimg[128], s4[kMaxRes][128]
   static constexpr int Bars = Small + (2 + kMaxRes) * kTile * 4;
-  static constexpr int NumBars = 3 * kStages + 20;
+  static constexpr int NumBars = 2 * kStages + 14;
   static constexpr int TmemPtr = Bars + NumBars * 8;
   static constexpr int Total = TmemPtr + 16;
 };
-enum Bar { B_WFULL = 0, B_WEMPTY = kStages, B_WPEER = 2 * kStages, B_XREADY = 3 * kStages, B_ACC0_FULL0, B_ACC0_FULL1, B_H0_READY0, B_H0_READY1,
-           B_H0_FREE0, B_H0_FREE1, B_ACC1_FULL, B_H1_READY, B_ACC2_FULL, B_H2_READY, B_ACC3_FULL, B_TILE_DONE, B_XFREE,
-           B_P_H0_0, B_P_H0_1, B_P_X, B_P_H1, B_P_H2, B_P_TD };   // v3 / cta_group::2: events forwarded by the peer CTA's relay
-static_assert(B_P_TD + 1 == Smem::NumBars, "barrier count");
+enum Bar { B_WFULL = 0, B_WEMPTY = kStages, B_XREADY = 2 * kStages, B_ACC0_FULL0, B_ACC0_FULL1, B_H0_READY0, B_H0_READY1,
+           B_H0_FREE0, B_H0_FREE1, B_ACC1_FULL, B_H1_READY, B_ACC2_FULL, B_H2_READY, B_ACC3_FULL, B_TILE_DONE, B_XFREE };
+static_assert(B_XFREE + 1 == Smem::NumBars, "barrier count");
 static_assert(Smem::Total + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
 
 __device__ __forceinline__ void wait_bar(uint64_t* bars, int which, uint32_t& count) {
@@ -176,106 +157,9 @@ __device__ __forceinline__ PointTaps point_taps(const MpPointSrc& src, const MpC
   return pt;
 }
 
-// Transposing warp reduction: every lane holds 16 partial sums (one per point); afterwards lane L (< 16) holds the total of
-// point L over all 32 lanes.  16+8+4+2+1 = 31 shuffles instead of 16 x 5.
-__device__ __forceinline__ float warp_reduce16(const float (&part)[16], int lane) {
-  float v16[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) v16[j] = part[j] + __shfl_xor_sync(0xffffffffu, part[j], 16);
-  float v8[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const bool up = lane & 8;
-    const float keep = up ? v16[j + 8] : v16[j], send = up ? v16[j] : v16[j + 8];
-    v8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-  float v4[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const bool up = lane & 4;
-    const float keep = up ? v8[j + 4] : v8[j], send = up ? v8[j] : v8[j + 4];
-    v4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  float v2[2];
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const bool up = lane & 2;
-    const float keep = up ? v4[j + 2] : v4[j], send = up ? v4[j] : v4[j + 2];
-    v2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  const bool up = lane & 1;
-  const float keep = up ? v2[1] : v2[0], send = up ? v2[0] : v2[1];
-  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
-}
-
 // Whole warp: sample the 16 points whose taps sit in lanes 0..15 (`pt`, duplicated in lanes 16..31) into rows
-// [pbase, pbase+16) of the fp16 X tile (K-major SWIZZLE_128B, 4 K-blocks of 64 channels; lane covers 8 channels; the
-// taps are read from the fp32 map and the interpolated value is rounded to fp16 exactly once) and
-// publish the per-point scalars: depth feature, in-image flag and the fp32 skip part of the last layer
-// sum_c w4[128 + c] * x_c + w4z * z + b4 (computed from the fp32 samples, before they are rounded to fp16).
-__device__ __forceinline__ void sample_x_group(const TcParams& prm, uint8_t* smem_x, float* s_zf, float* s_in, float* s_s4,
-                                               const PointTaps& pt, int pbase, int lane, const float (&w4s)[kMaxRes][8]) {
-  const int cbase = lane * 8;
-  float s4part[kMaxRes][16];
-#pragma unroll
-  for (int q0 = 0; q0 < 16; q0 += 2) {
-    float4 raw[2][4][2];                     // [point][tap][8 fp32 channels]
-    float wgt[2][4];
-#pragma unroll
-    for (int qq = 0; qq < 2; ++qq)
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int off = __shfl_sync(0xffffffffu, pt.off[a], q0 + qq);
-        wgt[qq][a] = __shfl_sync(0xffffffffu, pt.wgt[a], q0 + qq);
-        const float4* src4 = reinterpret_cast<const float4*>(prm.feat32 + (size_t)off * kC + cbase);
-        raw[qq][a][0] = __ldg(src4);
-        raw[qq][a][1] = __ldg(src4 + 1);
-      }
-#pragma unroll
-    for (int qq = 0; qq < 2; ++qq) {
-      const int p = pbase + q0 + qq;
-      float2 acc[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {                   // same accumulation order as grid_sample: nw, ne, sw, se
-        const float2 w2 = make_float2(wgt[qq][a], wgt[qq][a]);
-        const float2 f[4] = {make_float2(raw[qq][a][0].x, raw[qq][a][0].y), make_float2(raw[qq][a][0].z, raw[qq][a][0].w),
-                             make_float2(raw[qq][a][1].x, raw[qq][a][1].y), make_float2(raw[qq][a][1].z, raw[qq][a][1].w)};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = (a == 0) ? __fmul2_rn(f[j], w2) : __ffma2_rn(f[j], w2, acc[j]);
-      }
-      uint4 packed;
-      packed.x = tc::pack_half2(acc[0].x, acc[0].y);
-      packed.y = tc::pack_half2(acc[1].x, acc[1].y);
-      packed.z = tc::pack_half2(acc[2].x, acc[2].y);
-      packed.w = tc::pack_half2(acc[3].x, acc[3].y);
-      *reinterpret_cast<uint4*>(smem_x + (lane >> 3) * 16384 + tc::sw128_offset(p, (lane & 7) * 8)) = packed;
-#pragma unroll
-      for (int r = 0; r < kMaxRes; ++r) {
-        float sacc = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          sacc = fmaf(w4s[r][2 * j], acc[j].x, sacc);
-          sacc = fmaf(w4s[r][2 * j + 1], acc[j].y, sacc);
-        }
-        s4part[r][q0 + qq] = sacc;
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < kMaxRes; ++r) {
-    if (r < prm.res) {
-      const float tot = warp_reduce16(s4part[r], lane);
-      if (lane < 16) s_s4[r * kTile + pbase + lane] = tot + __ldg(prm.w4z + r) * pt.zf + __ldg(prm.b4 + r);
-    }
-  }
-  if (lane < 16) {
-    s_zf[pbase + lane] = pt.zf;
-    s_in[pbase + lane] = pt.in_img ? 1.f : 0.f;
-  }
-}
-
-// Program v3 variant: the X operand is sampled from the fp16 copy of the map (half the bytes through L1), four points per
-// batch; the last layer's direct feature access is NOT derived from these samples but from S4 (fp32, per texel), which
+// [pbase, pbase+16) of the fp16 X tile (K-major SWIZZLE_128B, 4 K-blocks of 64 channels; lane covers 8 channels) from the
+// fp16 copy of the map, four points per batch; the last layer's direct feature access is NOT derived from these samples but from S4 (fp32, per texel), which
 // the lane owning the point interpolates in fp32.
 __device__ __forceinline__ void sample_x_group16(const TcParams& prm, uint8_t* smem_x, float* s_zf, float* s_in, float* s_s4,
                                                  PointTaps pt, int pbase, int lane) {
@@ -328,474 +212,19 @@ __device__ __forceinline__ void sample_x_group16(const TcParams& prm, uint8_t* s
 }
 
 // --------------------------------------------------------------------------------------------------------------------
-// hand-off helpers.  Producers of operands (workers) signal the MMA issuer, which lives in the leader CTA (rank 0):
-// one elected lane per warp arrives after __syncwarp(); every lane has already executed its own proxy / tcgen05 fence.
-template <int CG>
-__device__ __forceinline__ void warp_arrive_leader(uint64_t* bar, int lane) {
-  __syncwarp();
-  if (lane == 0) {
-    if constexpr (CG == 1) tc::mbar_arrive(bar);
-    else tc::mbar_arrive_remote(bar, 0);
-  }
-}
+// hand-off helper: one elected lane per warp arrives after __syncwarp(); every lane has already executed its own
+// proxy / tcgen05 fence.
 __device__ __forceinline__ void warp_arrive_local(uint64_t* bar, int lane) {
   __syncwarp();
   if (lane == 0) tc::mbar_arrive(bar);
 }
-template <int CG>
-__device__ __forceinline__ void wait_leader(uint64_t* bars, int which, uint32_t& count, bool free_type = false) {
-  const uint32_t par = (count & 1u) ^ (free_type ? 1u : 0u);
-  if constexpr (CG == 1) tc::mbar_wait(bars + which, par);
-  else tc::mbar_wait_cluster(bars + which, par);
-  ++count;
-}
-template <int CG>
-__device__ __forceinline__ void commit(uint64_t* bar) {
-  if constexpr (CG == 1) tc::mma_commit(bar);
-  else tc::mma_commit2(bar);
-}
-
-template <int CG>
-__global__ void __launch_bounds__(kThreads, 1)
-query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
-  using C = Cfg<CG>;
-  MP_DYN_SMEM(uint8_t, smem_raw);
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::Bars);
-  float* s_zf = reinterpret_cast<float*>(smem + Smem::Small);
-  float* s_in = s_zf + kTile;
-  float* s_s4 = s_in + kTile;                                    // [res][128]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Smem::TmemPtr);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  unsigned long long* prof = prm.prof ? prm.prof + (size_t)blockIdx.x * 32 : nullptr;
-  const uint32_t rank = (CG == 2) ? tc::cluster_ctarank() : 0u;
-  const bool leader = rank == 0;
-
-  long long n = src.n;
-  if (src.count_dev) {
-    const long long c = *src.count_dev;
-    n = c < n ? c : n;
-  }
-  const long long n_tiles = (n + kTile - 1) / kTile;
-  // the unit of scheduling is a group of CG tiles (one per CTA of the cluster); every CTA of a cluster runs the same
-  // number of iterations, a CTA whose tile lies beyond n_tiles computes on masked-out points
-  const long long n_groups = (n_tiles + CG - 1) / CG;
-  const long long g0 = blockIdx.x / CG, gstep = gridDim.x / CG;
-
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      tc::mbar_init(bars + B_WFULL + s, 1);
-      tc::mbar_init(bars + B_WEMPTY + s, 1);
-      tc::mbar_init(bars + B_WPEER + s, 1);
-    }
-    constexpr int kW = 8 * CG;                        // one arrival per worker warp of every CTA in the cluster
-    tc::mbar_init(bars + B_XREADY, kW);
-    tc::mbar_init(bars + B_ACC0_FULL0, 1);
-    tc::mbar_init(bars + B_ACC0_FULL1, 1);
-    tc::mbar_init(bars + B_XFREE, 1);
-    tc::mbar_init(bars + B_H0_READY0, kW);
-    tc::mbar_init(bars + B_H0_READY1, kW);
-    tc::mbar_init(bars + B_H0_FREE0, 1);
-    tc::mbar_init(bars + B_H0_FREE1, 1);
-    tc::mbar_init(bars + B_ACC1_FULL, 1);
-    tc::mbar_init(bars + B_H1_READY, kW);
-    tc::mbar_init(bars + B_ACC2_FULL, 1);
-    tc::mbar_init(bars + B_H2_READY, kW);
-    tc::mbar_init(bars + B_ACC3_FULL, 1);
-    tc::mbar_init(bars + B_TILE_DONE, 4 * CG);
-    tc::fence_barrier_init();
-  }
-  if (warp == 2) {
-    if constexpr (CG == 1) { tc::tmem_alloc(s_tmem, 512); tc::tmem_relinquish(); }
-    else { tc::tmem_alloc2(s_tmem, 512); tc::tmem_relinquish2(); }
-  }
-  tc::tcgen05_fence_before();
-  if constexpr (CG == 1) __syncthreads(); else tc::cluster_sync_all();
-  tc::tcgen05_fence_after();
-  const uint32_t tbase = *s_tmem;
-
-  if (warp == 0) {
-    // ============================== weight producer (every CTA streams its own part of every tile) ===========
-    if (lane == 0) {
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(CG == 2 ? prm.wstream2[rank] : prm.wstream);
-      uint32_t it = 0;
-      for (long long g = g0; g < n_groups; g += gstep) {
-        for (int s = 0; s < kStagesPerTile; ++s, ++it) {
-          const int slot = it % C::Stages;
-          const uint32_t use = it / C::Stages;
-          tc::mbar_wait(bars + B_WEMPTY + slot, (use & 1u) ^ 1u);
-          tc::mbar_arrive_expect_tx(bars + B_WFULL + slot, C::StageBytes);
-          tc::bulk_g2s(smem + Smem::Wr + slot * C::StageBytes,
-                       wsrc + (size_t)s * C::StageBytes, C::StageBytes,
-                       bars + B_WFULL + slot);
-        }
-      }
-    }
-  } else if (warp == 1 && !leader) {
-    // ============================== peer CTA: tell the leader when our half of a weight stage has landed ========
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (long long g = g0; g < n_groups; g += gstep) {
-        for (int s = 0; s < kStagesPerTile; ++s, ++it) {
-          const int slot = it % C::Stages;
-          tc::mbar_wait(bars + B_WFULL + slot, (it / C::Stages) & 1u);
-          tc::mbar_arrive_remote(bars + B_WPEER + slot, 0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ============================== MMA issuer (leader CTA, one lane) ==============================
-    if (lane == 0) {
-      const uint32_t idesc128 = tc::make_idesc_f16(128 * CG, 128);
-      const uint32_t idesc256 = tc::make_idesc_f16(128 * CG, 256);
-      const uint32_t sX = tc::smem_u32(smem + Smem::X);
-      const uint32_t sH0 = tc::smem_u32(smem + Smem::H0);
-      const uint32_t sW = tc::smem_u32(smem + Smem::Wr);
-      uint32_t it = 0;                                  // weight stage counter (mirrors the producers)
-      uint32_t c_xready = 0, c_h0ready[2] = {0, 0}, c_h1ready = 0, c_h2ready = 0, c_tiledone = 0;
-
-      const long long t_begin = prof ? clock64() : 0;
-      auto next_stage = [&]() -> uint32_t {
-        const int slot = it % C::Stages;
-        const uint32_t par = (it / C::Stages) & 1u;
-        { PROF_T0(); tc::mbar_wait(bars + B_WFULL + slot, par); PROF_ADD(P_WFULL); }
-        if constexpr (CG == 2) { PROF_T0(); tc::mbar_wait_cluster(bars + B_WPEER + slot, par); PROF_ADD(P_WPEER); }
-        tc::tcgen05_fence_after();
-        return sW + slot * C::StageBytes;
-      };
-      auto release_stage = [&]() {
-        commit<CG>(bars + B_WEMPTY + (it % C::Stages));
-        ++it;
-      };
-      auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool& first) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t ad = tc::make_sdesc_sw128(a_addr + kk * 32, 1024), bd = tc::make_sdesc_sw128(b_addr + kk * 32, 1024);
-          if constexpr (CG == 1) tc::mma_ss(d, ad, bd, idesc, first ? 0u : 1u);
-          else tc::mma_ss2(d, ad, bd, idesc, first ? 0u : 1u);
-          first = false;
-        }
-      };
-      auto kblock_ts = [&](uint32_t d, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool& first) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t bd = tc::make_sdesc_sw128(b_addr + kk * 32, 1024);
-          if constexpr (CG == 1) tc::mma_ts(d, a_tmem + kk * 8, bd, idesc, first ? 0u : 1u);
-          else tc::mma_ts2(d, a_tmem + kk * 8, bd, idesc, first ? 0u : 1u);
-          first = false;
-        }
-      };
-
-      for (long long g = g0; g < n_groups; g += gstep) {
-        { PROF_T0(); wait_leader<CG>(bars, B_XREADY, c_xready); PROF_ADD(P_XREADY); }
-        tc::tcgen05_fence_after();
-        // acc0 buffer 0 = [256,384) held acc3 of the previous tile: wait until its fp32 tail has drained it
-        if (g != g0) {
-          PROF_T0();
-          wait_leader<CG>(bars, B_TILE_DONE, c_tiledone);
-          PROF_ADD(P_ACC1DRAINED);
-          tc::tcgen05_fence_after();
-        }
-        for (int h = 0; h < 2; ++h) {
-          bool first1 = true;
-          // Layer-0 chunk c goes to acc0 buffer (h == 0 ? c & 1 : 0).  In the first half [384,512) is still free, so the
-          // chunks are double-buffered and the tensor pipe never waits for a drain; in the second half that region holds
-          // H1 and chunk c+1 has to wait until chunk c has been drained ("drained" and "H0 smem buffer written" are the
-          // same event, B_H0_READY).  Buffer 1 held H2 of the previous tile: its last readers (layer-3 hidden MMAs) were
-          // issued earlier by this thread and MMAs execute in order, so overwriting it is safe.
-          auto issue_l0 = [&](int c) {
-            const int ab = (h == 0) ? (c & 1) : 0;
-            bool first0 = true;
-            for (int s = 0; s < 2; ++s) {
-              const uint32_t w = next_stage();
-              kblock_ss(tbase + kColAcc0 + ab * 128, sX + (2 * s) * 16384, w, idesc128, first0);
-              kblock_ss(tbase + kColAcc0 + ab * 128, sX + (2 * s + 1) * 16384, w + C::Sub, idesc128, first0);
-              release_stage();
-            }
-            commit<CG>(bars + B_ACC0_FULL0 + ab);
-          };
-          auto wait_chunk = [&](int c, int slot) {      // chunk c drained + its H0 smem buffer written
-            const int b = c & 1;
-            PROF_T0();
-            wait_leader<CG>(bars, B_H0_READY0 + b, c_h0ready[b]);
-            if (prof) prof[slot] += (unsigned long long)(clock64() - _t0);
-            tc::tcgen05_fence_after();
-          };
-          auto issue_l1 = [&](int c) {
-            const int b = c & 1;
-            if (c == 0 && h == 1) {
-              // the first layer-1 MMA of the second half overwrites [0,256): the first half must have been drained.
-              // (For h == 0 the region held acc2 of the previous tile, drained before its B_H2_READY, already waited.)
-              PROF_T0();
-              wait_leader<CG>(bars, B_H1_READY, c_h1ready);
-              PROF_ADD(P_ACC1DRAINED);
-              tc::tcgen05_fence_after();
-            }
-            for (int kb = 0; kb < 2; ++kb) {
-              const uint32_t w = next_stage();
-              kblock_ss(tbase + kColAcc1, sH0 + b * 32768 + kb * 16384, w, idesc256, first1);
-              release_stage();
-            }
-            commit<CG>(bars + B_H0_FREE0 + b);
-          };
-          if (h == 0) {
-            issue_l0(0);
-            issue_l0(1);
-            for (int c = 0; c < 8; ++c) {
-              wait_chunk(c, P_ACC0FREE);
-              issue_l1(c);
-              if (c + 2 < 8) issue_l0(c + 2);
-            }
-          } else {
-            issue_l0(0);
-            for (int c = 0; c < 7; ++c) {
-              wait_chunk(c, P_ACC0FREE);
-              issue_l0(c + 1);
-              issue_l1(c);
-            }
-            wait_chunk(7, P_H0READY);
-            issue_l1(7);
-          }
-          for (int kb = 0; kb < 4; ++kb) {                       // skip part of layer 1: A = X
-            const uint32_t w = next_stage();
-            kblock_ss(tbase + kColAcc1, sX + kb * 16384, w, idesc256, first1);
-            release_stage();
-          }
-          commit<CG>(bars + B_ACC1_FULL);
-        }
-        // ---- layer 2: A = H1 from TMEM (8 K-blocks) + X (4 K-blocks) -> acc2 [0,256)
-        { PROF_T0(); wait_leader<CG>(bars, B_H1_READY, c_h1ready); PROF_ADD(P_H1READY); }
-        tc::tcgen05_fence_after();
-        {
-          bool first = true;
-          for (int kb = 0; kb < 8; ++kb) {
-            const uint32_t w = next_stage();
-            const uint32_t a = tbase + (kb < 4 ? kColH1lo + kb * 32 : kColH1hi + (kb - 4) * 32);
-            kblock_ts(tbase + kColAcc1, a, w, idesc256, first);
-            release_stage();
-          }
-          for (int kb = 0; kb < 4; ++kb) {
-            const uint32_t w = next_stage();
-            kblock_ss(tbase + kColAcc1, sX + kb * 16384, w, idesc256, first);
-            release_stage();
-          }
-          commit<CG>(bars + B_ACC2_FULL);
-        }
-        // ---- layer 3 -> acc3 [256,384) (H1hi's columns: their last readers, the layer-2 MMAs, are already issued).
-        //      The skip part (A = X) goes FIRST: it does not depend on the layer-2 epilogue, and once it has completed X
-        //      is dead, so the workers can start sampling the next tile while layer 3 and the fp32 tail still run.
-        {
-          bool first = true;
-          for (int s = 0; s < 2; ++s) {
-            const uint32_t w = next_stage();
-            kblock_ss(tbase + kColAcc3, sX + (2 * s) * 16384, w, idesc128, first);
-            kblock_ss(tbase + kColAcc3, sX + (2 * s + 1) * 16384, w + C::Sub, idesc128, first);
-            release_stage();
-          }
-          commit<CG>(bars + B_XFREE);
-          { PROF_T0(); wait_leader<CG>(bars, B_H2_READY, c_h2ready); PROF_ADD(P_H2READY); }
-          tc::tcgen05_fence_after();
-          for (int s = 0; s < 2; ++s) {
-            const uint32_t w = next_stage();
-            kblock_ts(tbase + kColAcc3, tbase + kColH2 + (2 * s) * 32, w, idesc128, first);
-            kblock_ts(tbase + kColAcc3, tbase + kColH2 + (2 * s + 1) * 32, w + C::Sub, idesc128, first);
-            release_stage();
-          }
-          commit<CG>(bars + B_ACC3_FULL);
-        }
-      }
-      if (prof) prof[P_TOTAL] = (unsigned long long)(clock64() - t_begin);
-    }
-  } else if (warp >= 4) {
-    // ============================== workers: sampler + epilogue ==============================
-    const int wk = warp - 4;                     // 0..7
-    const int wg = wk >> 2;                      // epilogue warpgroup: column half
-    const int quarter = warp & 3;                // TMEM lane quarter this warp may touch
-    const int row = quarter * 32 + lane;         // the point (TMEM lane) this thread owns in the epilogue
-    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    uint32_t c_acc0full[2] = {0, 0}, c_xfree = 0, c_h0free[2] = {0, 0}, c_acc1full = 0, c_acc2full = 0, c_acc3full = 0;
-    const int res = prm.res;
-    if (!(warp == 4 && lane == 0)) prof = nullptr;      // one worker thread records
-
-    for (long long g = g0; g < n_groups; g += gstep) {
-      const long long tile = g * CG + rank;
-      const long long p0 = tile * kTile;
-      // ---- X is free once the previous tile's last MMAs (layer-3 skip) have completed
-      if (g != g0) { wait_bar(bars, B_XFREE, c_xfree); }
-      const long long t_sample0 = prof ? clock64() : 0;
-      // ---- sampling: warp wk handles points wk*16 .. +15.  Lane q (< 16) projects point q and builds its bilinear
-      //      taps once; the taps are then broadcast and every lane gathers 8 consecutive channels (16 B) per tap.
-      {
-        float w4s[kMaxRes][8];
-#pragma unroll
-        for (int r = 0; r < kMaxRes; ++r)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) w4s[r][j] = (r < res) ? __ldg(prm.w4s + r * kC + lane * 8 + j) : 0.f;
-        const PointTaps pt = point_taps(src, cal, prm.H, prm.W, p0 + wk * 16 + (lane & 15), n);
-        sample_x_group(prm, smem + Smem::X, s_zf, s_in, s_s4, pt, wk * 16, lane, w4s);
-      }
-      tc::fence_proxy_async_smem();
-      // make s_zf/s_in/s_s4 visible to the epilogue role of all worker threads
-      tc::bar_sync_workers256();
-      const float zf = s_zf[row];
-      const float inimg = s_in[row];
-      float s4[kMaxRes];
-#pragma unroll
-      for (int r = 0; r < kMaxRes; ++r) s4[r] = (r < res) ? s_s4[r * kTile + row] : 0.f;
-      tc::bar_sync_workers256();      // everyone has read the per-point scalars
-      warp_arrive_leader<CG>(bars + B_XREADY, lane);
-      if (prof) prof[P_W_SAMPLE] += (unsigned long long)(clock64() - t_sample0);
-
-      // ---- epilogue helper: acc columns [col0, col0+32) of this thread's row -> activated fp32 values
-      // pre-activation = accumulator + bias[ch] + wz[ch] * z_feat (fp32); `ch0` is warp-uniform -> constant-bank operands
-      auto load_pre = [&](uint32_t col, int ch0, float (&o)[32]) {
-        uint32_t v[32];
-        tc::tmem_ld32(tbase + lane_base + col, v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          o[j] = __uint_as_float(v[j]) + fmaf(prm.wz_all[ch0 + j], zf, prm.bias_all[ch0 + j]);
-      };
-      auto load_act = [&](uint32_t col, int ch0, float (&o)[32]) {
-        load_pre(col, ch0, o);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], o[j] * MP_LEAKY_SLOPE);      // leaky-relu, slope in (0,1)
-      };
-      // fp16 pair with leaky-relu applied on the packed value (max(h, 0.01 h) in half2: 2 instructions per pair)
-      auto act_pack = [&](float a, float b) -> uint32_t {
-        const __half2 h = __floats2half2_rn(a, b);
-        const __half2 r = __hmax2(h, __hmul2(h, __float2half2_rn(MP_LEAKY_SLOPE)));
-        return *reinterpret_cast<const uint32_t*>(&r);
-      };
-
-      for (int h = 0; h < 2; ++h) {
-        // ---- layer-0 chunks -> H0 buffers (smem, A operand of layer 1)
-        for (int c = 0; c < 8; ++c) {
-          const int b = c & 1;
-          const int ab = (h == 0) ? b : 0;                        // acc0 buffer (double-buffered in the first half)
-          { PROF_T0(); wait_bar(bars, B_ACC0_FULL0 + ab, c_acc0full[ab]); PROF_ADD(P_W_ACC0FULL); }
-          { PROF_T0(); wait_free(bars, B_H0_FREE0 + b, c_h0free[b]); PROF_ADD(P_W_H0FREE); }
-          tc::tcgen05_fence_after();
-          PROF_T0();
-          // this warpgroup drains columns [wg*64, wg*64+64) == K-block `wg` of the chunk
-#pragma unroll
-          for (int gq = 0; gq < 2; ++gq) {
-            float o[32];
-            const int ch0 = c * 128 + wg * 64 + gq * 32;
-            load_pre(kColAcc0 + ab * 128 + wg * 64 + gq * 32, side_off(0) + ch0, o);
-            uint8_t* dstp = smem + Smem::H0 + b * 32768 + wg * 16384;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 pk;
-              pk.x = act_pack(o[8 * q + 0], o[8 * q + 1]);
-              pk.y = act_pack(o[8 * q + 2], o[8 * q + 3]);
-              pk.z = act_pack(o[8 * q + 4], o[8 * q + 5]);
-              pk.w = act_pack(o[8 * q + 6], o[8 * q + 7]);
-              *reinterpret_cast<uint4*>(dstp + tc::sw128_offset(row, gq * 32 + q * 8)) = pk;
-            }
-          }
-          tc::fence_proxy_async_smem();
-          tc::tcgen05_fence_before();
-          warp_arrive_leader<CG>(bars + B_H0_READY0 + b, lane);      // also means "acc0 drained"
-          PROF_ADD(P_W_DRAIN0);
-        }
-        // ---- layer-1 half -> H1 (packed fp16 in TMEM, A operand of layer 2)
-        { PROF_T0(); wait_bar(bars, B_ACC1_FULL, c_acc1full); PROF_ADD(P_W_ACC1FULL); }
-        tc::tcgen05_fence_after();
-        {
-          PROF_T0();
-          const uint32_t hcol = (h == 0) ? kColH1lo : kColH1hi;
-#pragma unroll 1
-          for (int gq = 0; gq < 4; ++gq) {
-            float o[32];
-            const int lc = wg * 128 + gq * 32;                    // column inside the 256-wide half
-            load_pre(kColAcc1 + lc, side_off(1) + h * 256 + lc, o);
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = act_pack(o[2 * j], o[2 * j + 1]);
-            tc::tmem_st16(tbase + lane_base + hcol + lc / 2, pk);
-          }
-          tc::tmem_st_wait();
-          tc::tcgen05_fence_before();
-          warp_arrive_leader<CG>(bars + B_H1_READY, lane);
-          PROF_ADD(P_W_DRAIN1);
-        }
-      }
-      // ---- layer 2 -> H2 (packed fp16 in TMEM)
-      { PROF_T0(); wait_bar(bars, B_ACC2_FULL, c_acc2full); PROF_ADD(P_W_ACC2FULL); }
-      tc::tcgen05_fence_after();
-      {
-        PROF_T0();
-#pragma unroll 1
-        for (int gq = 0; gq < 4; ++gq) {
-          float o[32];
-          const int lc = wg * 128 + gq * 32;
-          load_pre(kColAcc1 + lc, side_off(2) + lc, o);
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = act_pack(o[2 * j], o[2 * j + 1]);
-          tc::tmem_st16(tbase + lane_base + kColH2 + lc / 2, pk);
-        }
-        tc::tmem_st_wait();
-        tc::tcgen05_fence_before();
-        warp_arrive_leader<CG>(bars + B_H2_READY, lane);
-        PROF_ADD(P_W_DRAIN2);
-      }
-      // ---- layer 3 (fp32 accumulators) + layer 4 in fp32 on CUDA cores, warpgroup 0 only
-      if (wg == 0) {
-        { PROF_T0(); wait_bar(bars, B_ACC3_FULL, c_acc3full); PROF_ADD(P_W_ACC3FULL); }
-        tc::tcgen05_fence_after();
-        PROF_T0();
-        float logit[kMaxRes];
-#pragma unroll
-        for (int r = 0; r < kMaxRes; ++r) logit[r] = s4[r];
-#pragma unroll 1
-        for (int gq = 0; gq < 4; ++gq) {
-          float o[32];
-          load_act(kColAcc3 + gq * 32, side_off(3) + gq * 32, o);
-#pragma unroll
-          for (int r = 0; r < kMaxRes; ++r) {
-            if (r < res) {
-              const float4* wv = reinterpret_cast<const float4*>(prm.w4h + r * kL3 + gq * 32);
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 w4 = __ldg(wv + j4);
-                logit[r] = fmaf(w4.x, o[4 * j4 + 0], logit[r]);
-                logit[r] = fmaf(w4.y, o[4 * j4 + 1], logit[r]);
-                logit[r] = fmaf(w4.z, o[4 * j4 + 2], logit[r]);
-                logit[r] = fmaf(w4.w, o[4 * j4 + 3], logit[r]);
-              }
-            }
-          }
-        }
-        tc::tcgen05_fence_before();
-        warp_arrive_leader<CG>(bars + B_TILE_DONE, lane);
-        PROF_ADD(P_W_DRAIN3);
-        const long long i = p0 + row;
-        if (i < n) {
-#pragma unroll
-          for (int r = 0; r < kMaxRes; ++r) {
-            if (r < res) {
-              const float val = inimg * mp_last_op(logit[r], prm.last_op);      // MonoPortNet.py:89
-              if (dst.out) dst.out[(long long)r * dst.ld + i] = val;
-              if (dst.scatter_vol && r == 0) dst.scatter_vol[__ldg(src.nodes + i)] = val;
-            }
-          }
-        }
-      }
-    }
-  }
-  // ---- teardown (reconverge the single-lane roles first: the barriers below are .aligned)
+// Barrier wait of a warp whose control flow is warp-uniform (the MMA issuers): ONE lane -- the elected one, which also
+// issues the tcgen05 instructions -- polls, the others are released by __syncwarp().  All 32 lanes polling would be
+// equivalent on the hardware (they execute try_wait in lock step) but lets a lagging lane sleep through a whole phase when
+// lanes are scheduled independently (the CPU model of tests/emu runs one OS thread per lane).
+__device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity) {
+  if (tc::elect_one()) tc::mbar_wait(bar, parity);
   __syncwarp();
-  tc::tcgen05_fence_before();
-  if constexpr (CG == 1) {
-    __syncthreads();
-    if (warp == 2) tc::tmem_dealloc(tbase, 512);
-  } else {
-    tc::cluster_sync_all();
-    if (warp == 2) tc::tmem_dealloc2(tbase, 512);
-  }
 }
 
 // ====================================================================================================================
@@ -812,10 +241,10 @@ query_tc_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
 // roofline.achieved keeps counting the ALGORITHMIC 2 363 906 FLOP/point; the hoisted layer is not executed per point.
 // PEERS: also store channel 0 into the peer volumes of dst (fused slab exchange); the default instantiation carries no
 // trace of it.
-template <int CG, bool PEERS = false>
+template <bool PEERS = false>
 __global__ void __launch_bounds__(kThreads, 1)
 query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
-  using C = Cfg<CG>;
+  using C = Cfg;
   MP_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::Bars);
@@ -825,9 +254,8 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Smem::TmemPtr);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (mp_guard_skips(prm.amax, prm.amax_limit, prm.guard)) return;      // (uniform over the grid: nothing is allocated yet)
   unsigned long long* prof = prm.prof ? prm.prof + (size_t)blockIdx.x * 32 : nullptr;
-  const uint32_t rank = (CG == 2) ? tc::cluster_ctarank() : 0u;
-  const bool leader = rank == 0;
 
   long long n = src.n;
   if (src.count_dev) {
@@ -835,8 +263,8 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     n = c < n ? c : n;
   }
   const long long n_tiles = (n + kTile - 1) / kTile;
-  const long long n_groups = (n_tiles + CG - 1) / CG;
-  const long long g0 = blockIdx.x / CG, gstep = gridDim.x / CG;
+  const long long n_groups = n_tiles;
+  const long long g0 = blockIdx.x, gstep = gridDim.x;
 
   constexpr uint32_t cAcc1 = 0, cH1lo = 0, cH1hi = 384, cAcc2 = 128, cH2 = 0, cAcc3 = 384;
 
@@ -844,13 +272,8 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     for (int s = 0; s < kStages; ++s) {
       tc::mbar_init(bars + B_WFULL + s, 1);
       tc::mbar_init(bars + B_WEMPTY + s, 1);
-      tc::mbar_init(bars + B_WPEER + s, 1);
     }
-    // hand-off barriers are CTA-local (workers never touch the peer CTA: a cluster-scope release from 8 warps per event
-    // costs far more than one forwarded arrival); with cta_group::2 the peer's relay thread forwards every event to the
-    // leader's B_P_* barriers
     constexpr int kW = 8;
-    for (int i = B_P_H0_0; i <= B_P_TD; ++i) tc::mbar_init(bars + i, 1);
     tc::mbar_init(bars + B_XREADY, 2);             // the two sampler warps
     tc::mbar_init(bars + B_H0_READY0, kW);
     tc::mbar_init(bars + B_H0_READY1, kW);
@@ -868,18 +291,18 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     tc::fence_barrier_init();
   }
   if (warp == 2) {
-    if constexpr (CG == 1) { tc::tmem_alloc(s_tmem, 512); tc::tmem_relinquish(); }
-    else { tc::tmem_alloc2(s_tmem, 512); tc::tmem_relinquish2(); }
+    tc::tmem_alloc(s_tmem, 512);
+    tc::tmem_relinquish();
   }
   tc::tcgen05_fence_before();
-  if constexpr (CG == 1) __syncthreads(); else tc::cluster_sync_all();
+  __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tbase = *s_tmem;
 
   if (warp == 0) {
     // ============================== weight producer ==============================
     if (lane == 0) {
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(CG == 2 ? prm.wstream2[rank] : prm.wstream);
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.wstream);
       uint32_t it = 0;
       for (long long g = g0; g < n_groups; g += gstep) {
         for (int s = 0; s < kStagesPerTile3; ++s, ++it) {
@@ -893,90 +316,60 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         }
       }
     }
-  } else if (warp == 1 && !leader) {
-    // ============================== peer CTA relay ==============================
-    // One thread forwards to the leader (a) "our half of weight stage s has landed" and (b) every operand hand-off of
-    // this CTA's workers, polling the local barriers without blocking so that neither stream delays the other.
-    if (lane == 0) {
-      uint32_t it = 0;                        // weight stages forwarded
-      const uint32_t total_stages = (uint32_t)(((n_groups - g0 + gstep - 1) / gstep) * kStagesPerTile3);
-      // per-tile event sequence (the order in which the leader consumes them)
-      constexpr int kEvents = 12;
-      const int ev_local[kEvents] = {B_H0_READY0, B_H0_READY1, B_H0_READY0, B_H0_READY1, B_H0_READY0, B_H0_READY1,
-                                     B_H0_READY0, B_H0_READY1, B_XREADY, B_H1_READY, B_H2_READY, B_TILE_DONE};
-      const int ev_peer[kEvents] = {B_P_H0_0, B_P_H0_1, B_P_H0_0, B_P_H0_1, B_P_H0_0, B_P_H0_1, B_P_H0_0, B_P_H0_1,
-                                    B_P_X, B_P_H1, B_P_H2, B_P_TD};
-      uint32_t cnt[Smem::NumBars];
-      for (int i = 0; i < Smem::NumBars; ++i) cnt[i] = 0;
-      const long long n_my_tiles = (n_groups - g0 + gstep - 1) / gstep;
-      long long tile_i = 0;
-      int ev = 0;
-      while (it < total_stages || tile_i < n_my_tiles) {
-        if (it < total_stages) {
-          const int slot = it % C::Stages;
-          if (tc::mbar_test_wait(bars + B_WFULL + slot, (it / C::Stages) & 1u)) {
-            tc::mbar_arrive_remote(bars + B_WPEER + slot, 0);
-            ++it;
-          }
-        }
-        if (tile_i < n_my_tiles) {
-          const int lb = ev_local[ev];
-          if (tc::mbar_test_wait(bars + lb, cnt[lb] & 1u)) {
-            ++cnt[lb];
-            tc::tcgen05_fence_after();
-            tc::tcgen05_fence_before();
-            tc::mbar_arrive_remote(bars + ev_peer[ev], 0);
-            if (++ev == kEvents) { ev = 0; ++tile_i; }
-          }
-        }
-      }
-    }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      const uint32_t idesc128 = tc::make_idesc_f16(128 * CG, 128);
-      const uint32_t idesc256 = tc::make_idesc_f16(128 * CG, 256);
+    // The WHOLE warp runs the control flow (barrier waits, stage counters, descriptor arithmetic: all warp-uniform, so the
+    // compiler keeps them in uniform registers); only the tcgen05 instructions themselves are predicated on one elected
+    // lane.  Issuing from inside `if (lane == 0)` cost ~20 extra instructions per MMA (an elect / R2UR loop to move the
+    // operands to uniform registers) and made the ISSUE rate the bound of every MMA phase: tools/tc_rate.cu measures 246
+    // cycles per 128x256x16 MMA that way against 163 with unrolled K-steps (profiles/r02_call4_tc_rate_issue_patterns.txt).
+    {
+      unsigned long long* const prof_all = prof;
+      prof = (lane == 0) ? prof_all : nullptr;           // one lane records the in-kernel timers
+      const uint32_t idesc128 = tc::make_idesc_f16(128, 128);
+      const uint32_t idesc256 = tc::make_idesc_f16(128, 256);
       const uint32_t sX = tc::smem_u32(smem + Smem::X);
       const uint32_t sH0 = tc::smem_u32(smem + Smem::H0);
       const uint32_t sW = tc::smem_u32(smem + Smem::Wr);
       uint32_t it = 0;
       uint32_t c_xready = 0, c_h0ready[2] = {0, 0}, c_h1ready = 0, c_h2ready = 0, c_tiledone = 0;
       const long long t_begin = prof ? clock64() : 0;
-      // an operand is ready when this CTA's workers (local barrier) and, with cta_group::2, the peer's (forwarded) are
-      auto wait_both = [&](int local_bar, int peer_bar, uint32_t& count) {
-        tc::mbar_wait(bars + local_bar, count & 1u);
-        if constexpr (CG == 2) tc::mbar_wait_cluster(bars + peer_bar, count & 1u);
+      auto wait_both = [&](int local_bar, int, uint32_t& count) {
+        warp_wait(bars + local_bar, count & 1u);
         ++count;
       };
       auto next_stage = [&]() -> uint32_t {
         const int slot = it % C::Stages;
         const uint32_t par = (it / C::Stages) & 1u;
-        { PROF_T0(); tc::mbar_wait(bars + B_WFULL + slot, par); PROF_ADD(P_WFULL); }
-        if constexpr (CG == 2) { PROF_T0(); tc::mbar_wait_cluster(bars + B_WPEER + slot, par); PROF_ADD(P_WPEER); }
+        { PROF_T0(); warp_wait(bars + B_WFULL + slot, par); PROF_ADD(P_WFULL); }
         tc::tcgen05_fence_after();
         return sW + slot * C::StageBytes;
       };
       auto release_stage = [&]() {
-        commit<CG>(bars + B_WEMPTY + (it % C::Stages));
+        if (tc::elect_one()) tc::mma_commit(bars + B_WEMPTY + (it % C::Stages));
         ++it;
       };
+      auto commit_one = [&](int which) {
+        if (tc::elect_one()) tc::mma_commit(bars + which);
+      };
+      // one K-block (64 channels = four K = 16 steps): descriptors advance by 32 B (+2 in the address field)
       auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool& first) {
-#pragma unroll 1
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t ad = tc::make_sdesc_sw128(a_addr + kk * 32, 1024), bd = tc::make_sdesc_sw128(b_addr + kk * 32, 1024);
-          if constexpr (CG == 1) tc::mma_ss(d, ad, bd, idesc, first ? 0u : 1u);
-          else tc::mma_ss2(d, ad, bd, idesc, first ? 0u : 1u);
-          first = false;
+        const uint64_t ad0 = tc::make_sdesc_sw128(a_addr, 1024), bd0 = tc::make_sdesc_sw128(b_addr, 1024);
+        const uint32_t acc0 = first ? 0u : 1u;
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc::mma_ss(d, ad0 + 2 * kk, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
         }
+        first = false;
       };
       auto kblock_ts = [&](uint32_t d, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool& first) {
-#pragma unroll 1
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t bd = tc::make_sdesc_sw128(b_addr + kk * 32, 1024);
-          if constexpr (CG == 1) tc::mma_ts(d, a_tmem + kk * 8, bd, idesc, first ? 0u : 1u);
-          else tc::mma_ts2(d, a_tmem + kk * 8, bd, idesc, first ? 0u : 1u);
-          first = false;
+        const uint64_t bd0 = tc::make_sdesc_sw128(b_addr, 1024);
+        const uint32_t acc0 = first ? 0u : 1u;
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc::mma_ts(d, a_tmem + kk * 8, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
         }
+        first = false;
       };
 
       for (long long g = g0; g < n_groups; g += gstep) {
@@ -984,13 +377,13 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         // B_H2_READY, waited) and acc3 (drained by the fp32 tail: B_TILE_DONE)
         bool need_tile_done = g != g0;
         bool first1[2] = {true, true};
-        const bool tr = blockIdx.x == 0 && (g - g0) / gstep == kTraceTile;
+        const bool tr = blockIdx.x == 0 && lane == 0 && (g - g0) / gstep == kTraceTile;
         TRACE(tr, 0);
         const long long t_ph0 = prof ? clock64() : 0;
         // ---- layer 1, hidden part: 8 sampled layer-0 chunks x 2 K-blocks x 2 output halves
         for (int c = 0; c < 8; ++c) {
           const int b = c & 1;
-          { PROF_T0(); wait_both(B_H0_READY0 + b, B_P_H0_0 + b, c_h0ready[b]); PROF_ADD(P_H0READY); }
+          { PROF_T0(); wait_both(B_H0_READY0 + b, 0, c_h0ready[b]); PROF_ADD(P_H0READY); }
           TRACE(tr, 1 + c);
           tc::tcgen05_fence_after();
           for (int kb = 0; kb < 2; ++kb)
@@ -1000,7 +393,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
                 // [384,512) holds the previous tile's acc3 until its fp32 tail has drained it; the lower half of acc1
                 // does not overlap it, so only the first MMA into [256,512) has to wait
                 PROF_T0();
-                wait_both(B_TILE_DONE, B_P_TD, c_tiledone);
+                wait_both(B_TILE_DONE, 0, c_tiledone);
                 PROF_ADD(P_ACC1DRAINED);
                 tc::tcgen05_fence_after();
                 need_tile_done = false;
@@ -1008,12 +401,12 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
               kblock_ss(tbase + cAcc1 + nh * 256, sH0 + b * 32768 + kb * 16384, w, idesc256, first1[nh]);
               release_stage();
             }
-          commit<CG>(bars + B_H0_FREE0 + b);
+          commit_one(B_H0_FREE0 + b);
         }
         if (prof) prof[9] += (unsigned long long)(clock64() - t_ph0);
         TRACE(tr, 9);
         // ---- layer 1, skip part: A = X
-        { PROF_T0(); wait_both(B_XREADY, B_P_X, c_xready); PROF_ADD(P_XREADY); }
+        { PROF_T0(); wait_both(B_XREADY, 0, c_xready); PROF_ADD(P_XREADY); }
         TRACE(tr, 10);
         const long long t_ph1 = prof ? clock64() : 0;
         tc::tcgen05_fence_after();
@@ -1023,11 +416,11 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             kblock_ss(tbase + cAcc1 + nh * 256, sX + kb * 16384, w, idesc256, first1[nh]);
             release_stage();
           }
-        commit<CG>(bars + B_ACC1_FULL);
+        commit_one(B_ACC1_FULL);
         if (prof) prof[10] += (unsigned long long)(clock64() - t_ph1);
         TRACE(tr, 11);
         // ---- layer 2: A = H1 from TMEM (8 K-blocks) + X (4 K-blocks) -> acc2 [128,384)
-        { PROF_T0(); wait_both(B_H1_READY, B_P_H1, c_h1ready); PROF_ADD(P_H1READY); }
+        { PROF_T0(); wait_both(B_H1_READY, 0, c_h1ready); PROF_ADD(P_H1READY); }
         TRACE(tr, 12);
         tc::tcgen05_fence_after();
         {
@@ -1045,7 +438,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             kblock_ss(tbase + cAcc2, sX + kb * 16384, w, idesc256, first);
             release_stage();
           }
-          commit<CG>(bars + B_ACC2_FULL);
+          commit_one(B_ACC2_FULL);
           TRACE(tr, 13);
         }
         // ---- layer 3 -> acc3 [384,512); skip part first, then X is dead
@@ -1057,9 +450,9 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             kblock_ss(tbase + cAcc3, sX + (2 * s + 1) * 16384, w + C::Sub, idesc128, first);
             release_stage();
           }
-          commit<CG>(bars + B_XFREE);
+          commit_one(B_XFREE);
           TRACE(tr, 14);
-          { PROF_T0(); wait_both(B_H2_READY, B_P_H2, c_h2ready); PROF_ADD(P_H2READY); }
+          { PROF_T0(); wait_both(B_H2_READY, 0, c_h2ready); PROF_ADD(P_H2READY); }
           TRACE(tr, 15);
           tc::tcgen05_fence_after();
           for (int s = 0; s < 2; ++s) {
@@ -1068,7 +461,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * s + 1) * 32, w + C::Sub, idesc128, first);
             release_stage();
           }
-          commit<CG>(bars + B_ACC3_FULL);
+          commit_one(B_ACC3_FULL);
           TRACE(tr, 16);
         }
       }
@@ -1081,7 +474,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     const int res = prm.res;
     uint32_t c_xfree = 0;
     for (long long g = g0; g < n_groups; g += gstep) {
-      const long long tile = g * CG + rank;
+      const long long tile = g;
       const long long p0 = tile * kTile;
       const bool tr = blockIdx.x == 0 && sw == 0 && lane == 0 && (g - g0) / gstep == kTraceTile;
       TRACE(tr, 96);
@@ -1125,7 +518,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     uint32_t t_off[4][2], t_wgt[4][2], t_z[4];
     int gtr = -1;                              // trace slot base for the chunk being generated (-1: off)
     auto compute_taps = [&](long long g) {
-      const PointTaps pt = point_taps(src, cal, prm.H, prm.W, (g * CG + rank) * kTile + wk * 16 + l16, n);
+      const PointTaps pt = point_taps(src, cal, prm.H, prm.W, g * kTile + wk * 16 + l16, n);
       const uint32_t o01 = (uint32_t)pt.off[0] | ((uint32_t)pt.off[1] << 16), o23 = (uint32_t)pt.off[2] | ((uint32_t)pt.off[3] << 16);
       const uint32_t w01 = tc::pack_half2(pt.wgt[0], pt.wgt[1]), w23 = tc::pack_half2(pt.wgt[2], pt.wgt[3]);
       const uint32_t zz = tc::pack_half2(pt.zf, pt.zf);
@@ -1239,7 +632,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       for (long long g = g0 - gstep; g < n_groups; g += gstep) {
         const bool real = g >= g0;
         const bool has_next = g + gstep < n_groups;
-        const long long p0 = (g * CG + rank) * kTile;
+        const long long p0 = g * kTile;
         const bool tr = blockIdx.x == 0 && real && (wk & 3) == 0 && lane == 0 && (g - g0) / gstep == kTraceTile;
         const int tb = 32 + wg * 32;
 #pragma unroll 1
@@ -1368,13 +761,8 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
   }
   __syncwarp();
   tc::tcgen05_fence_before();
-  if constexpr (CG == 1) {
-    __syncthreads();
-    if (warp == 2) tc::tmem_dealloc(tbase, 512);
-  } else {
-    tc::cluster_sync_all();
-    if (warp == 2) tc::tmem_dealloc2(tbase, 512);
-  }
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tbase, 512);
 }
 
 // G0[texel][n] = sum_k F[texel][k] * W0f[n][k] on the tensor cores: fp16 operands (F rounded once while staging, W0f
@@ -1395,7 +783,7 @@ constexpr uint32_t kG0Smem = kG0SmemA + kG0SmemB + 1024 /*align*/ + 128 /*barrie
 
 __global__ void __launch_bounds__(kG0Threads, 1)
 g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half* __restrict__ G, int M,
-             __half* __restrict__ F16, float* __restrict__ S4, const float* __restrict__ w4s, int res) {
+             __half* __restrict__ F16, float* __restrict__ S4, const float* __restrict__ w4s, int res, unsigned* __restrict__ amax) {
   MP_DYN_SMEM(uint8_t, g0_smem_raw);
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g0_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;
@@ -1436,25 +824,25 @@ g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half
       }
     }
   } else if (warp == 9) {
-    // ---- MMA issuer
-    if (lane == 0) {
-      tc::mbar_wait(a_ready, 0);
+    // ---- MMA issuer (whole warp, one elected lane per tcgen05 instruction)
+    {
+      warp_wait(a_ready, 0);
       tc::tcgen05_fence_after();
       for (int nt = 0; nt < kG0NT; ++nt) {
         const int buf = nt & 1;
-        if (nt >= 2) { tc::mbar_wait(&acc_free[buf], ((nt >> 1) & 1) ^ 1); tc::tcgen05_fence_after(); }
+        if (nt >= 2) { warp_wait(&acc_free[buf], ((nt >> 1) & 1) ^ 1); tc::tcgen05_fence_after(); }
         for (int kb = 0; kb < 4; ++kb) {
           const int s = nt * 4 + kb, slot = s % kG0Stages;
-          tc::mbar_wait(&b_full[slot], (s / kG0Stages) & 1);
+          warp_wait(&b_full[slot], (s / kG0Stages) & 1);
           tc::tcgen05_fence_after();
-          const uint32_t a0 = tc::smem_u32(sA + kb * 16384), b0 = tc::smem_u32(sB + slot * 32768);
+          const uint64_t ad0 = tc::make_sdesc_sw128(tc::smem_u32(sA + kb * 16384), 1024), bd0 = tc::make_sdesc_sw128(tc::smem_u32(sB + slot * 32768), 1024);
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16)
-            tc::mma_ss(tbase + buf * kG0TileN, tc::make_sdesc_sw128(a0 + k16 * 32, 1024), tc::make_sdesc_sw128(b0 + k16 * 32, 1024), idesc,
-                       (kb | k16) ? 1u : 0u);
-          tc::mma_commit(&b_empty[slot]);
+            for (int k16 = 0; k16 < 4; ++k16) tc::mma_ss(tbase + buf * kG0TileN, ad0 + 2 * k16, bd0 + 2 * k16, idesc, (kb | k16) ? 1u : 0u);
+            tc::mma_commit(&b_empty[slot]);
+          }
         }
-        tc::mma_commit(&acc_full[buf]);
+        if (tc::elect_one()) tc::mma_commit(&acc_full[buf]);
       }
     }
   } else {
@@ -1463,6 +851,7 @@ g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half
     const bool live = (m0 + row) < M;
     const float* frow = F + (size_t)(live ? m0 + row : 0) * kC + half * 32;
     float s4acc[kMaxRes];
+    float fmax_abs = 0.f;             // range guard: the largest |feature| this thread stages
 #pragma unroll
     for (int r = 0; r < kMaxRes; ++r) s4acc[r] = 0.f;
 #pragma unroll 1
@@ -1470,6 +859,8 @@ g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half
       float4 v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = live ? __ldg(reinterpret_cast<const float4*>(frow + kb * 64) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fmax_abs = fmaxf(fmax_abs, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 pk;
@@ -1495,6 +886,11 @@ g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half
     tc::fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(a_ready);
+    if (amax) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) fmax_abs = fmaxf(fmax_abs, __shfl_xor_sync(0xffffffffu, fmax_abs, o));
+      if (lane == 0) atomicMax(amax, __float_as_uint(fmax_abs));       // non-negative floats order like their bit patterns
+    }
 #pragma unroll
     for (int r = 0; r < kMaxRes; ++r) {
       const float tot = s4acc[r] + __shfl_xor_sync(0xffffffffu, s4acc[r], 1);
@@ -1548,10 +944,13 @@ g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half
 //     are issued in the order  L1:A,B  L2:B,A  L3:A,B  so that four fills per tile suffice.  The tensor pipe waits for
 //     the samplers at three of them -- acceptable for a query of 10^4..10^5 points (the dense path is the geometry head);
 //   * the per-point scalars (depth feature, in-image flag, the fp32 last-layer feature part S4[3]) are computed by the
-//     epilogue thread that owns the point instead of being passed through shared memory (no room, and no barrier).
+//     epilogue thread that owns the point instead of being passed through shared memory (no room, and no barrier);
+//   * layer 3 multiplies by W3 as an fp16 PAIR (hi + lo, two MMAs per K-step on the same A operand): the Tanh output is four
+//     times as sensitive to the logit as the geometry head's Sigmoid, and tools/precision_budget.py shows the rounding of
+//     W3 to be the largest single term of the error (1.0e-4 -> 5.6e-5 on what query() returns; +6 % MMAs of this program).
 constexpr int kCc = 512;                                   // feature channels of the colour map
 constexpr int kResC = 3;
-constexpr int kStagesPerTileC = 32 + 16 + 8 + 8 + 4 + 2;   // L1 hidden, L1 skip (A,B), L2 hidden, L2 skip (B,A), L3 skip (A,B), L3 hidden
+constexpr int kStagesPerTileC = 32 + 16 + 8 + 8 + 8 + 4;   // L1 hidden, L1 skip (A,B), L2 hidden, L2 skip (B,A), L3 skip (A,B) x (hi,lo), L3 hidden x (hi,lo)
 
 // Direct rendering of the visible surface (RTL/main.py:212-249) fused into the colour query: point i is the vertex
 // (X[i], Y[i], R - Z[i]) of forward_vertices mapped to world space by mat_color (RTL/main.py:201-210: diag((b_max-b_min)/R),
@@ -1627,13 +1026,14 @@ __device__ __forceinline__ void sample_x_phase(const TcParams& prm, uint8_t* sme
 
 __global__ void __launch_bounds__(kThreads, 1)
 query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst, MpSurfaceSrc surf) {
-  using C = Cfg<1>;
+  using C = Cfg;
   MP_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::Bars);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Smem::TmemPtr);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (mp_guard_skips(prm.amax, prm.amax_limit, prm.guard)) return;      // (uniform over the grid: nothing is allocated yet)
   long long n = src.n;
   if (src.count_dev) {
     const long long c = *src.count_dev;
@@ -1686,8 +1086,8 @@ query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst, MpSur
       }
     }
   } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // ============================== MMA issuer (whole warp, one elected lane per tcgen05 instruction: see program v3) ======
+    {
       const uint32_t idesc128 = tc::make_idesc_f16(128, 128);
       const uint32_t idesc256 = tc::make_idesc_f16(128, 256);
       const uint32_t sX = tc::smem_u32(smem + Smem::X);
@@ -1697,30 +1097,38 @@ query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst, MpSur
       uint32_t c_xready = 0, c_h0ready[2] = {0, 0}, c_h1ready = 0, c_h2ready = 0, c_tiledone = 0;
       auto next_stage = [&]() -> uint32_t {
         const int slot = it % C::Stages;
-        tc::mbar_wait(bars + B_WFULL + slot, (it / C::Stages) & 1u);
+        warp_wait(bars + B_WFULL + slot, (it / C::Stages) & 1u);
         tc::tcgen05_fence_after();
         return sW + slot * C::StageBytes;
       };
       auto release_stage = [&]() {
-        tc::mma_commit(bars + B_WEMPTY + (it % C::Stages));
+        if (tc::elect_one()) tc::mma_commit(bars + B_WEMPTY + (it % C::Stages));
         ++it;
       };
+      auto commit_one = [&](int which) {
+        if (tc::elect_one()) tc::mma_commit(bars + which);
+      };
       auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool& first) {
-#pragma unroll 1
-        for (int kk = 0; kk < 4; ++kk) {
-          tc::mma_ss(d, tc::make_sdesc_sw128(a_addr + kk * 32, 1024), tc::make_sdesc_sw128(b_addr + kk * 32, 1024), idesc, first ? 0u : 1u);
-          first = false;
+        const uint64_t ad0 = tc::make_sdesc_sw128(a_addr, 1024), bd0 = tc::make_sdesc_sw128(b_addr, 1024);
+        const uint32_t acc0 = first ? 0u : 1u;
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc::mma_ss(d, ad0 + 2 * kk, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
         }
+        first = false;
       };
       auto kblock_ts = [&](uint32_t d, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool& first) {
-#pragma unroll 1
-        for (int kk = 0; kk < 4; ++kk) {
-          tc::mma_ts(d, a_tmem + kk * 8, tc::make_sdesc_sw128(b_addr + kk * 32, 1024), idesc, first ? 0u : 1u);
-          first = false;
+        const uint64_t bd0 = tc::make_sdesc_sw128(b_addr, 1024);
+        const uint32_t acc0 = first ? 0u : 1u;
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc::mma_ts(d, a_tmem + kk * 8, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
         }
+        first = false;
       };
       auto wait_x = [&]() {            // the next phase of X has been sampled
-        wait_bar(bars, B_XREADY, c_xready);
+        warp_wait(bars + B_XREADY, c_xready & 1u);
+        ++c_xready;
         tc::tcgen05_fence_after();
       };
 
@@ -1730,21 +1138,23 @@ query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst, MpSur
         // ---- layer 1, hidden part: 8 sampled layer-0 chunks x 2 K-blocks x 2 output halves
         for (int c = 0; c < 8; ++c) {
           const int b = c & 1;
-          wait_bar(bars, B_H0_READY0 + b, c_h0ready[b]);
+          warp_wait(bars + B_H0_READY0 + b, c_h0ready[b] & 1u);
+          ++c_h0ready[b];
           tc::tcgen05_fence_after();
           for (int kb = 0; kb < 2; ++kb)
             for (int nh = 0; nh < 2; ++nh) {
               const uint32_t w = next_stage();
               if (nh == 1 && need_tile_done) {
                 // [384,512) holds the previous tile's acc3 until its fp32 tail has drained it
-                wait_bar(bars, B_TILE_DONE, c_tiledone);
+                warp_wait(bars + B_TILE_DONE, c_tiledone & 1u);
+                ++c_tiledone;
                 tc::tcgen05_fence_after();
                 need_tile_done = false;
               }
               kblock_ss(tbase + cAcc1 + nh * 256, sH0 + b * 32768 + kb * 16384, w, idesc256, first1[nh]);
               release_stage();
             }
-          tc::mma_commit(bars + B_H0_FREE0 + b);
+          commit_one(B_H0_FREE0 + b);
         }
         // ---- layer 1, skip part: phase A, then phase B
         for (int ph = 0; ph < 2; ++ph) {
@@ -1755,11 +1165,12 @@ query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst, MpSur
               kblock_ss(tbase + cAcc1 + nh * 256, sX + kb * 16384, w, idesc256, first1[nh]);
               release_stage();
             }
-          if (ph == 0) tc::mma_commit(bars + B_XFREE);       // phase A consumed; phase B stays for layer 2
+          if (ph == 0) commit_one(B_XFREE);       // phase A consumed; phase B stays for layer 2
         }
-        tc::mma_commit(bars + B_ACC1_FULL);
+        commit_one(B_ACC1_FULL);
         // ---- layer 2: A = H1 from TMEM (8 K-blocks), then X phase B (resident), then phase A -> acc2 [128,384)
-        wait_bar(bars, B_H1_READY, c_h1ready);
+        warp_wait(bars + B_H1_READY, c_h1ready & 1u);
+        ++c_h1ready;
         tc::tcgen05_fence_after();
         {
           bool first = true;
@@ -1776,32 +1187,33 @@ query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst, MpSur
               kblock_ss(tbase + cAcc2, sX + kb * 16384, w, idesc256, first);
               release_stage();
             }
-            if (ph == 0) tc::mma_commit(bars + B_XFREE);     // phase B consumed
+            if (ph == 0) commit_one(B_XFREE);     // phase B consumed
           }
-          tc::mma_commit(bars + B_ACC2_FULL);
+          commit_one(B_ACC2_FULL);
         }
         // ---- layer 3 -> acc3 [384,512): skip phase A (resident), skip phase B, hidden part
         {
           bool first = true;
           for (int ph = 0; ph < 2; ++ph) {
             if (ph == 1) wait_x();                           // phase B again
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < 4; ++s) {                    // stages 0,1: hi(W3) of K-blocks (0,1) (2,3); stages 2,3: lo(W3), same A
               const uint32_t w = next_stage();
-              kblock_ss(tbase + cAcc3, sX + (2 * s) * 16384, w, idesc128, first);
-              kblock_ss(tbase + cAcc3, sX + (2 * s + 1) * 16384, w + C::Sub, idesc128, first);
+              kblock_ss(tbase + cAcc3, sX + (2 * (s & 1)) * 16384, w, idesc128, first);
+              kblock_ss(tbase + cAcc3, sX + (2 * (s & 1) + 1) * 16384, w + C::Sub, idesc128, first);
               release_stage();
             }
-            tc::mma_commit(bars + B_XFREE);                  // after phase B: X is dead, the next tile's phase A may be sampled
+            commit_one(B_XFREE);                  // after phase B: X is dead, the next tile's phase A may be sampled
           }
-          wait_bar(bars, B_H2_READY, c_h2ready);
+          warp_wait(bars + B_H2_READY, c_h2ready & 1u);
+          ++c_h2ready;
           tc::tcgen05_fence_after();
-          for (int s = 0; s < 2; ++s) {
+          for (int s = 0; s < 4; ++s) {                      // hi(W3) stages, then lo(W3) stages
             const uint32_t w = next_stage();
-            kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * s) * 32, w, idesc128, first);
-            kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * s + 1) * 32, w + C::Sub, idesc128, first);
+            kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * (s & 1)) * 32, w, idesc128, first);
+            kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * (s & 1) + 1) * 32, w + C::Sub, idesc128, first);
             release_stage();
           }
-          tc::mma_commit(bars + B_ACC3_FULL);
+          commit_one(B_ACC3_FULL);
         }
       }
     }
@@ -2061,7 +1473,7 @@ constexpr uint32_t kG0cSmem = kG0cSmemA + kG0cSmemB + 1024 /*align*/ + 128 /*bar
 
 __global__ void __launch_bounds__(kG0Threads, 1)
 g0c_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half* __restrict__ G, int M,
-              __half* __restrict__ F16, float* __restrict__ S4, const float* __restrict__ w4s) {
+              __half* __restrict__ F16, float* __restrict__ S4, const float* __restrict__ w4s, unsigned* __restrict__ amax) {
   MP_DYN_SMEM(uint8_t, g0_smem_raw);
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g0_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;
@@ -2102,24 +1514,25 @@ g0c_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __hal
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
-      tc::mbar_wait(a_ready, 0);
+    // ---- MMA issuer (whole warp, one elected lane per tcgen05 instruction)
+    {
+      warp_wait(a_ready, 0);
       tc::tcgen05_fence_after();
       for (int nt = 0; nt < kG0NT; ++nt) {
         const int buf = nt & 1;
-        if (nt >= 2) { tc::mbar_wait(&acc_free[buf], ((nt >> 1) & 1) ^ 1); tc::tcgen05_fence_after(); }
+        if (nt >= 2) { warp_wait(&acc_free[buf], ((nt >> 1) & 1) ^ 1); tc::tcgen05_fence_after(); }
         for (int kb = 0; kb < kG0cKB; ++kb) {
           const int s = nt * kG0cKB + kb, slot = s % kG0cStages;
-          tc::mbar_wait(&b_full[slot], (s / kG0cStages) & 1);
+          warp_wait(&b_full[slot], (s / kG0cStages) & 1);
           tc::tcgen05_fence_after();
-          const uint32_t a0 = tc::smem_u32(sA + kb * 16384), b0 = tc::smem_u32(sB + slot * 32768);
+          const uint64_t ad0 = tc::make_sdesc_sw128(tc::smem_u32(sA + kb * 16384), 1024), bd0 = tc::make_sdesc_sw128(tc::smem_u32(sB + slot * 32768), 1024);
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16)
-            tc::mma_ss(tbase + buf * kG0TileN, tc::make_sdesc_sw128(a0 + k16 * 32, 1024), tc::make_sdesc_sw128(b0 + k16 * 32, 1024), idesc,
-                       (kb | k16) ? 1u : 0u);
-          tc::mma_commit(&b_empty[slot]);
+            for (int k16 = 0; k16 < 4; ++k16) tc::mma_ss(tbase + buf * kG0TileN, ad0 + 2 * k16, bd0 + 2 * k16, idesc, (kb | k16) ? 1u : 0u);
+            tc::mma_commit(&b_empty[slot]);
+          }
         }
-        tc::mma_commit(&acc_full[buf]);
+        if (tc::elect_one()) tc::mma_commit(&acc_full[buf]);
       }
     }
   } else {
@@ -2128,11 +1541,14 @@ g0c_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __hal
     const bool live = (m0 + row) < M;
     const float* frow = F + (size_t)(live ? m0 + row : 0) * kCc + half * 32;
     float s4acc[kResC] = {0.f, 0.f, 0.f};
+    float fmax_abs = 0.f;             // range guard: the largest |feature| this thread stages
 #pragma unroll 1
     for (int kb = 0; kb < kG0cKB; ++kb) {
       float4 v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = live ? __ldg(reinterpret_cast<const float4*>(frow + kb * 64) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fmax_abs = fmaxf(fmax_abs, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 pk;
@@ -2157,6 +1573,11 @@ g0c_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __hal
     tc::fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(a_ready);
+    if (amax) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) fmax_abs = fmaxf(fmax_abs, __shfl_xor_sync(0xffffffffu, fmax_abs, o));
+      if (lane == 0) atomicMax(amax, __float_as_uint(fmax_abs));       // non-negative floats order like their bit patterns
+    }
 #pragma unroll
     for (int r = 0; r < kResC; ++r) {
       const float tot = s4acc[r] + __shfl_xor_sync(0xffffffffu, s4acc[r], 1);
@@ -2202,10 +1623,13 @@ g0c_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __hal
 // host side: weight packing
 // --------------------------------------------------------------------------------------------------------------------
 // writes the [nrows x 64] fp16 K-major SWIZZLE_128B image of W[row0.., col0..col0+64) (W row-major [cout][cin])
-void pack_tile(uint8_t* dst, const float* W, int cin, int row0, int nrows, int col0) {
+// (lo = true: the fp16 rounding of what the first rounding lost, W - float(half(W)): the low half of an fp16 pair)
+void pack_tile(uint8_t* dst, const float* W, int cin, int row0, int nrows, int col0, bool lo = false) {
   for (int r = 0; r < nrows; ++r)
     for (int k = 0; k < 64; ++k) {
-      const __half h = __float2half_rn(W[(size_t)(row0 + r) * cin + col0 + k]);
+      const float w = W[(size_t)(row0 + r) * cin + col0 + k];
+      __half h = __float2half_rn(w);
+      if (lo) h = __float2half_rn(w - __half2float(h));
       memcpy(dst + tc::sw128_offset(r, k), &h, 2);
     }
 }
@@ -2253,17 +1677,19 @@ int tc_prepare_colour(mp_mlp* mlp) {
   for (int kb = 0; kb < 8; ++kb) pack_tile(stage_ptr(), W[2].data(), cin2, 0, 256, kb * 64);     // L2 hidden
   for (int ph = 1; ph >= 0; --ph)                                           // L2 skip: phase B, phase A
     for (int kb = 0; kb < 4; ++kb) pack_tile(stage_ptr(), W[2].data(), cin2, 0, 256, kL1 + ph * 256 + kb * 64);
-  for (int ph = 0; ph < 2; ++ph)                                            // L3 skip: phase A, phase B
+  for (int ph = 0; ph < 2; ++ph)                                            // L3 skip: phase A, phase B; each hi(W3), then lo(W3)
+    for (int part = 0; part < 2; ++part)
+      for (int s2 = 0; s2 < 2; ++s2) {
+        uint8_t* p = stage_ptr();
+        pack_tile(p, W[3].data(), cin3, 0, 128, kL2 + ph * 256 + (2 * s2) * 64, part == 1);
+        pack_tile(p + 16384, W[3].data(), cin3, 0, 128, kL2 + ph * 256 + (2 * s2 + 1) * 64, part == 1);
+      }
+  for (int part = 0; part < 2; ++part)                                      // L3 hidden: hi(W3), then lo(W3)
     for (int s2 = 0; s2 < 2; ++s2) {
       uint8_t* p = stage_ptr();
-      pack_tile(p, W[3].data(), cin3, 0, 128, kL2 + ph * 256 + (2 * s2) * 64);
-      pack_tile(p + 16384, W[3].data(), cin3, 0, 128, kL2 + ph * 256 + (2 * s2 + 1) * 64);
+      pack_tile(p, W[3].data(), cin3, 0, 128, (2 * s2) * 64, part == 1);
+      pack_tile(p + 16384, W[3].data(), cin3, 0, 128, (2 * s2 + 1) * 64, part == 1);
     }
-  for (int s2 = 0; s2 < 2; ++s2) {                                          // L3 hidden
-    uint8_t* p = stage_ptr();
-    pack_tile(p, W[3].data(), cin3, 0, 128, (2 * s2) * 64);
-    pack_tile(p + 16384, W[3].data(), cin3, 0, 128, (2 * s2 + 1) * 64);
-  }
   if ((int)st != kStagesPerTileC) {
     mp_set_error("internal: colour weight stream stage count mismatch");
     return MP_E_INVALID;
@@ -2325,7 +1751,7 @@ int tc_prepare_colour(mp_mlp* mlp) {
 }
 
 int launch_colour(const mp_mlp* mlp, const TcPack* pk, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal, const MpOutDst& dst,
-                  cudaStream_t st, const MpSurfaceSrc* surf_in = nullptr) {
+                  cudaStream_t st, const MpSurfaceSrc* surf_in = nullptr, int guard = MP_GUARD_NONE) {
   MpSurfaceSrc surf;
   memset(&surf, 0, sizeof(surf));
   if (surf_in) surf = *surf_in;
@@ -2347,16 +1773,30 @@ int launch_colour(const mp_mlp* mlp, const TcPack* pk, mp_feat* feat, const MpPo
   }
   if (feat->g0_owner != mlp->gen || feat->g0_version != feat->version) {
 #ifndef MP_CUDA_EMU
-    g0c_tc_kernel<<<(unsigned)((HW + 127) / 128), kG0Threads, kG0cSmem, st>>>(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s);
+    g0c_tc_kernel<<<(unsigned)((HW + 127) / 128), kG0Threads, kG0cSmem, st>>>(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s, feat->amax);
 #else
-    MP_EMU_LAUNCH((unsigned)((HW + 127) / 128), kG0Threads, g0c_tc_kernel(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s));
+    MP_EMU_LAUNCH((unsigned)((HW + 127) / 128), kG0Threads, g0c_tc_kernel(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s, feat->amax));
 #endif
     MP_CUDA(cudaGetLastError());
     feat->g0_owner = mlp->gen;
     feat->g0_version = feat->version;
   }
+  if (surf_in && isfinite(mlp->tc_amax_limit)) {
+    // the fused rendering has no exact-kernel twin: check the frame's feature range on the host (one 4-byte read-back per
+    // frame) and let the caller take the unfused path when it is outside the validated range
+    unsigned bits = 0;
+    MP_CUDA(cudaMemcpyAsync(&bits, feat->amax, sizeof(bits), cudaMemcpyDeviceToHost, st));
+    MP_CUDA(cudaStreamSynchronize(st));
+    float a;
+    memcpy(&a, &bits, sizeof(a));
+    if (a > mlp->tc_amax_limit) {
+      mp_set_error("feature magnitude %.3g is outside the validated range of the tensor-core colour program (limit %.3g)", a, mlp->tc_amax_limit);
+      return MP_E_RANGE;
+    }
+  }
   TcParams prm;
   memset(&prm, 0, sizeof(prm));
+  prm.amax = feat->amax; prm.amax_limit = mlp->tc_amax_limit; prm.guard = guard;
   prm.wstream = pk->w3stream;
   memcpy(prm.bias_all, pk->h_bias, sizeof(prm.bias_all));
   memcpy(prm.wz_all, pk->h_wz, sizeof(prm.wz_all));
@@ -2405,57 +1845,9 @@ int mp_tc_prepare(mp_mlp* mlp) {
     MP_CUDA(cudaMemcpy(W[l].data(), mlp->w[l], W[l].size() * sizeof(float), cudaMemcpyDeviceToHost));
     MP_CUDA(cudaMemcpy(Bv[l].data(), mlp->bias[l], Bv[l].size() * sizeof(float), cudaMemcpyDeviceToHost));
   }
-  // one weight stream per (variant, cluster rank): CG=1 -> 32 KB stages with full tiles; CG=2 -> 16 KB stages holding
-  // this rank's half of the rows of every tile (tcgen05.mma.cta_group::2 reads B rows [r*N/2, (r+1)*N/2) from CTA r)
-  auto build_stream = [&](int cg, int r, std::vector<uint8_t>& stream) -> bool {
-    const int stage_bytes = 32768 / cg, sub = stage_bytes / 2;
-    stream.assign((size_t)kStagesPerTile * stage_bytes, 0);
-    size_t st = 0;
-    auto stage_ptr = [&]() { return stream.data() + (st++) * stage_bytes; };
-    const int n128 = 128 / cg, n256 = 256 / cg;            // rows of a 128- / 256-row tile held by this rank
-    const int cin0 = mlp->cin[0], cin1 = mlp->cin[1], cin2 = mlp->cin[2], cin3 = mlp->cin[3];
-    for (int h = 0; h < 2; ++h) {
-      auto l0 = [&](int c) {
-        for (int s2 = 0; s2 < 2; ++s2) {
-          uint8_t* p = stage_ptr();
-          pack_tile(p, W[0].data(), cin0, c * 128 + r * n128, n128, (2 * s2) * 64);
-          pack_tile(p + sub, W[0].data(), cin0, c * 128 + r * n128, n128, (2 * s2 + 1) * 64);
-        }
-      };
-      auto l1 = [&](int c) {
-        for (int kb = 0; kb < 2; ++kb) pack_tile(stage_ptr(), W[1].data(), cin1, h * 256 + r * n256, n256, c * 128 + kb * 64);
-      };
-      if (h == 0) {            // double-buffered chunk order (mirrors the MMA issuer)
-        l0(0); l0(1);
-        for (int c = 0; c < 8; ++c) { l1(c); if (c + 2 < 8) l0(c + 2); }
-      } else {
-        l0(0);
-        for (int c = 0; c < 7; ++c) { l0(c + 1); l1(c); }
-        l1(7);
-      }
-      for (int kb = 0; kb < 4; ++kb) pack_tile(stage_ptr(), W[1].data(), cin1, h * 256 + r * n256, n256, kL0 + kb * 64);
-    }
-    for (int kb = 0; kb < 8; ++kb) pack_tile(stage_ptr(), W[2].data(), cin2, r * n256, n256, kb * 64);
-    for (int kb = 0; kb < 4; ++kb) pack_tile(stage_ptr(), W[2].data(), cin2, r * n256, n256, kL1 + kb * 64);
-    for (int s2 = 0; s2 < 2; ++s2) {         // layer 3: skip part first
-      uint8_t* p = stage_ptr();
-      pack_tile(p, W[3].data(), cin3, r * n128, n128, kL2 + (2 * s2) * 64);
-      pack_tile(p + sub, W[3].data(), cin3, r * n128, n128, kL2 + (2 * s2 + 1) * 64);
-    }
-    for (int s2 = 0; s2 < 2; ++s2) {
-      uint8_t* p = stage_ptr();
-      pack_tile(p, W[3].data(), cin3, r * n128, n128, (2 * s2) * 64);
-      pack_tile(p + sub, W[3].data(), cin3, r * n128, n128, (2 * s2 + 1) * 64);
-    }
-    return (int)st == kStagesPerTile;
-  };
-  std::vector<uint8_t> stream, stream2[2];
-  if (!build_stream(1, 0, stream) || !build_stream(2, 0, stream2[0]) || !build_stream(2, 1, stream2[1])) {
-    mp_set_error("internal: weight stream stage count mismatch");
-    return MP_E_INVALID;
-  }
   // v3 program (layer 0 hoisted): layer 1 over all 512 outputs as two 256-row tiles per K-block, then layers 2, 3
-  auto build_stream3 = [&](int cg, int r, std::vector<uint8_t>& out) -> bool {
+  auto build_stream3 = [&](std::vector<uint8_t>& out) -> bool {
+    const int cg = 1, r = 0;
     const int stage_bytes = 32768 / cg, sub = stage_bytes / 2;
     out.assign((size_t)kStagesPerTile3 * stage_bytes, 0);
     size_t st = 0;
@@ -2481,8 +1873,8 @@ int mp_tc_prepare(mp_mlp* mlp) {
     }
     return (int)st == kStagesPerTile3;
   };
-  std::vector<uint8_t> s3, s3b[2];
-  if (!build_stream3(1, 0, s3) || !build_stream3(2, 0, s3b[0]) || !build_stream3(2, 1, s3b[1])) {
+  std::vector<uint8_t> s3;
+  if (!build_stream3(s3)) {
     mp_set_error("internal: v3 weight stream stage count mismatch");
     return MP_E_INVALID;
   }
@@ -2495,10 +1887,7 @@ int mp_tc_prepare(mp_mlp* mlp) {
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
   };
-  cudaError_t e = upload(stream.data(), stream.size(), (void**)&pk->wstream);
-  for (int r = 0; r < 2 && e == cudaSuccess; ++r) e = upload(stream2[r].data(), stream2[r].size(), (void**)&pk->wstream2[r]);
-  if (e == cudaSuccess) e = upload(s3.data(), s3.size(), (void**)&pk->w3stream);
-  for (int r = 0; r < 2 && e == cudaSuccess; ++r) e = upload(s3b[r].data(), s3b[r].size(), (void**)&pk->w3stream2[r]);
+  cudaError_t e = upload(s3.data(), s3.size(), (void**)&pk->w3stream);
   {   // feature part of layer 0 as fp16 SWIZZLE_128B tiles, operand of the per-texel G0 GEMM
     if (e == cudaSuccess) {
       std::vector<uint8_t> w0t((size_t)(kL0 / kG0TileN) * 4 * 32768);
@@ -2540,11 +1929,8 @@ int mp_tc_prepare(mp_mlp* mlp) {
     mp_tc_release(mlp);
     return MP_E_CUDA;
   }
-  e = cudaFuncSetAttribute(query_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+  e = cudaFuncSetAttribute(query_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(g0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG0Smem);
   if (e != cudaSuccess) {
     mp_set_error("mp_tc_prepare: cannot opt in to %d bytes of shared memory: %s", Smem::Total + 1024, cudaGetErrorString(e));
@@ -2558,10 +1944,7 @@ int mp_tc_prepare(mp_mlp* mlp) {
 void mp_tc_release(mp_mlp* mlp) {
   TcPack* pk = static_cast<TcPack*>(mlp->tc);
   if (!pk) return;
-  if (pk->wstream) cudaFree(pk->wstream);
-  for (int r = 0; r < 2; ++r) if (pk->wstream2[r]) cudaFree(pk->wstream2[r]);
   if (pk->w3stream) cudaFree(pk->w3stream);
-  for (int r = 0; r < 2; ++r) if (pk->w3stream2[r]) cudaFree(pk->w3stream2[r]);
   if (pk->d_bias0) cudaFree(pk->d_bias0);
   if (pk->d_wz0) cudaFree(pk->d_wz0);
   if (pk->d_w0t) cudaFree(pk->d_w0t);
@@ -2606,23 +1989,26 @@ int mp_launch_colour_surface(const mp_mlp* mlp, mp_feat* feat, const long long* 
 }
 
 int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
-                       const MpOutDst& dst, cudaStream_t st, int program) {
+                       const MpOutDst& dst, cudaStream_t st, int guard) {
   if (src.n <= 0) return MP_OK;
   const TcPack* pk = static_cast<const TcPack*>(mlp->tc);
   if (!pk || !mlp->tc_ok) {
     mp_set_error("tcgen05 path not prepared for this head");
     return MP_E_UNSUPPORTED;
   }
-  if (pk->kind == 1) return launch_colour(mlp, pk, feat, src, cal, dst, st);
+  if (pk->kind == 1) return launch_colour(mlp, pk, feat, src, cal, dst, st, nullptr, guard);
   if (feat->C != kC) {
     mp_set_error("head expects %d input channels but the feature map has %d (+1 depth)", mlp->channels[0], feat->C);
     return MP_E_INVALID;
   }
+  const long long HW = (long long)feat->H * feat->W;
+  if (HW > 65536) {      // texel indices travel as 16-bit pairs in registers
+    mp_set_error("the tensor-core program handles feature maps of at most 65536 texels (got %d x %d); use MP_MODE_FP32", feat->H, feat->W);
+    return MP_E_UNSUPPORTED;
+  }
   TcParams prm;
   memset(&prm, 0, sizeof(prm));
-  prm.wstream = pk->wstream;
-  prm.wstream2[0] = pk->wstream2[0];
-  prm.wstream2[1] = pk->wstream2[1];
+  prm.amax = feat->amax; prm.amax_limit = mlp->tc_amax_limit; prm.guard = guard;
   memcpy(prm.bias_all, pk->h_bias, sizeof(prm.bias_all));
   memcpy(prm.wz_all, pk->h_wz, sizeof(prm.wz_all));
   prm.w4h = pk->w4h; prm.w4s = pk->w4s; prm.w4z = pk->w4z; prm.b4 = pk->b4;
@@ -2666,106 +2052,53 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     std::vector<unsigned long long> h((size_t)sms * 32);
     cudaMemcpy(h.data(), d_prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(d_prof);
-    static const char* names[32] = {"total", "xready", "acc0free", "wfull", "wpeer", "h0ready", "acc1drained", "h1ready", "h2ready",
-                                    "ph_L1hid(32st)", "ph_L1skip(8st)", "ph_L2_TS(4st)", 0, 0, 0, 0, "w_sample", "w_acc0full", "w_h0free", "w_acc1full", "w_acc2full", "w_acc3full",
-                                    "w_drain0", "w_drain1", "w_drain2", "w_drain3", 0, 0, 0, 0, 0, 0};
+    static const char* names[32] = {"total", "xready", 0, "wfull", 0, "h0ready", "acc1drained", "h1ready", "h2ready",
+                                    "ph_L1hid(32st)", "ph_L1skip(8st)", "ph_L2_TS(4st)", 0, 0, 0, 0, 0, 0, "w_h0free", "w_acc1full", "w_acc2full", "w_acc3full",
+                                    "w_drain0", "w_drain1", "w_drain2", "w_drain3", "w_xfree", 0, 0, 0, 0, 0};
     const long long tiles_per_cta = (tiles + grid - 1) / grid;
     fprintf(stderr, "[tc prof] grid=%d tiles/cta~%lld  (cycles per tile, CTA 0 | CTA 1)\n", grid, tiles_per_cta);
     for (int k = 0; k < 32; ++k)
       if (names[k]) fprintf(stderr, "[tc prof] %-12s %10.0f | %10.0f\n", names[k], (double)h[k] / tiles_per_cta, (double)h[32 + k] / tiles_per_cta);
   };
-  // variant: CTA group.  MONOPORT_B200_TC_CG=1|2 overrides.  Default: 1 for the v2 program (its layer-0 chunk hand-off
-  // is on the critical path and every cross-CTA arrival adds latency to it), see below for v3.
-  static const int forced = [] { const char* v = getenv("MONOPORT_B200_TC_CG"); return v ? atoi(v) : 0; }();
-  // program: v3 (layer 0 hoisted to texels; the per-frame G0 GEMM runs on the tensor cores in ~15 us, so it pays off for
-  // octree-sized queries too); v2 stays selectable (MP_MODE_TC_V2 / MONOPORT_B200_TC_VER=2) as the self-contained variant.
-  static const int forced_ver = [] { const char* v = getenv("MONOPORT_B200_TC_VER"); return v ? atoi(v) : 0; }();
-  const int want = program ? program : forced_ver;
-  // (v3 keeps texel indices as 16-bit pairs in registers: maps above 65536 texels take the self-contained program)
-  const int ver = (want == 2 || (long long)feat->H * feat->W > 65536) ? 2 : 3;
-  if (ver == 3) {
-    const long long HW = (long long)feat->H * feat->W;
-    if (!feat->g0 || feat->g0_n != kL0) {
-      if (feat->g0) cudaFree(feat->g0);
-      feat->g0 = nullptr;
-      MP_CUDA(cudaMalloc(&feat->g0, (size_t)HW * kL0 * sizeof(__half)));
-      if (!feat->f16) MP_CUDA(cudaMalloc(&feat->f16, (size_t)HW * kC * sizeof(__half)));
-      if (!feat->s4tex) MP_CUDA(cudaMalloc(&feat->s4tex, (size_t)HW * kMaxRes * sizeof(float)));
-      feat->g0_n = kL0;
-      feat->g0_owner = 0;
-    }
-    if (feat->g0_owner != mlp->gen || feat->g0_version != feat->version) {
-#ifndef MP_CUDA_EMU
-      g0_tc_kernel<<<(unsigned)((HW + 127) / 128), kG0Threads, kG0Smem, st>>>(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s, pk->res);
-#else
-      MP_EMU_LAUNCH((unsigned)((HW + 127) / 128), kG0Threads, g0_tc_kernel(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s, pk->res));
-#endif
-      MP_CUDA(cudaGetLastError());
-      feat->g0_owner = mlp->gen;
-      feat->g0_version = feat->version;
-    }
-    prm.g0 = feat->g0;
-    prm.feat16 = feat->f16;
-    prm.s4tex = feat->s4tex;
-    prm.d_bias0 = pk->d_bias0;
-    prm.d_wz0 = pk->d_wz0;
-    prm.wstream = pk->w3stream;
-    prm.wstream2[0] = pk->w3stream2[0];
-    prm.wstream2[1] = pk->w3stream2[1];
+  // the per-frame per-texel products of this head: G0 (layer-0 pre-activation), the fp16 copy of the map, S4
+  if (!feat->g0 || feat->g0_n != kL0) {
+    if (feat->g0) cudaFree(feat->g0);
+    feat->g0 = nullptr;
+    MP_CUDA(cudaMalloc(&feat->g0, (size_t)HW * kL0 * sizeof(__half)));
+    if (!feat->f16) MP_CUDA(cudaMalloc(&feat->f16, (size_t)HW * kC * sizeof(__half)));
+    if (!feat->s4tex) MP_CUDA(cudaMalloc(&feat->s4tex, (size_t)HW * kMaxRes * sizeof(float)));
+    feat->g0_n = kL0;
+    feat->g0_owner = 0;
   }
-  const int cg = forced == 2 ? 2 : (forced == 1 ? 1 : 1);
-  if (dst.n_peers > 0) {
-    // fused slab exchange: only the default program (v3, one CTA per tile) has this variant
-    if (ver != 3 || cg != 1 || dst.n_peers > MP_MAX_PEERS) {
-      mp_set_error("peer stores need tensor-core program v3, cta_group::1 and at most %d peers", MP_MAX_PEERS);
-      return MP_E_UNSUPPORTED;
-    }
-    const int grid = (int)(tiles < (long long)sms ? tiles : sms);
+  if (feat->g0_owner != mlp->gen || feat->g0_version != feat->version) {
 #ifndef MP_CUDA_EMU
-    query_tc3_kernel<1, true><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
+    g0_tc_kernel<<<(unsigned)((HW + 127) / 128), kG0Threads, kG0Smem, st>>>(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s, pk->res, feat->amax);
 #else
-    MP_EMU_LAUNCH(grid, kThreads, (query_tc3_kernel<1, true>(prm, src, cal, dst)));
+    MP_EMU_LAUNCH((unsigned)((HW + 127) / 128), kG0Threads, g0_tc_kernel(feat->nhwc32, pk->d_w0t, feat->g0, (int)HW, feat->f16, feat->s4tex, pk->w4s, pk->res, feat->amax));
 #endif
     MP_CUDA(cudaGetLastError());
-    report(grid);
-    return MP_OK;
+    feat->g0_owner = mlp->gen;
+    feat->g0_version = feat->version;
   }
-  if (cg == 1) {
-    const int grid = (int)(tiles < (long long)sms ? tiles : sms);
+  prm.g0 = feat->g0;
+  prm.feat16 = feat->f16;
+  prm.s4tex = feat->s4tex;
+  prm.d_bias0 = pk->d_bias0;
+  prm.d_wz0 = pk->d_wz0;
+  prm.wstream = pk->w3stream;
+  if (dst.n_peers > MP_MAX_PEERS) {
+    mp_set_error("at most %d peer volumes", MP_MAX_PEERS);
+    return MP_E_UNSUPPORTED;
+  }
+  const int grid = (int)(tiles < (long long)sms ? tiles : sms);
 #ifndef MP_CUDA_EMU
-    if (ver == 3) query_tc3_kernel<1><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
-    else query_tc_kernel<1><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
+  if (dst.n_peers > 0) query_tc3_kernel<true><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);      // fused slab exchange
+  else query_tc3_kernel<false><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
 #else
-    if (ver == 3) MP_EMU_LAUNCH(grid, kThreads, query_tc3_kernel<1>(prm, src, cal, dst));
-    else MP_EMU_LAUNCH(grid, kThreads, query_tc_kernel<1>(prm, src, cal, dst));
+  if (dst.n_peers > 0) MP_EMU_LAUNCH(grid, kThreads, (query_tc3_kernel<true>(prm, src, cal, dst)));
+  else MP_EMU_LAUNCH(grid, kThreads, (query_tc3_kernel<false>(prm, src, cal, dst)));
 #endif
-    MP_CUDA(cudaGetLastError());
-    report(grid);
-    return MP_OK;
-  }
-#ifdef MP_CUDA_EMU
-  mp_set_error("cta_group::2 is not modelled by the CPU emulation");
-  return MP_E_UNSUPPORTED;
-#else
-  const long long groups = (tiles + 1) / 2;
-  const long long max_clusters = sms / 2;
-  const int clusters = (int)(groups < max_clusters ? groups : max_clusters);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = Smem::Total + 1024;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (ver == 3) MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc3_kernel<2>, prm, src, cal, dst));
-  else MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc_kernel<2>, prm, src, cal, dst));
-  report(2 * clusters);
+  MP_CUDA(cudaGetLastError());
+  report(grid);
   return MP_OK;
-#endif
 }

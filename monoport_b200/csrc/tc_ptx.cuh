@@ -261,6 +261,20 @@ __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const void* tmap
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
+// One lane of the (converged) warp: `if (elect_one()) tcgen05.mma ...` keeps the surrounding control flow and the operand
+// arithmetic WARP-UNIFORM, so the compiler holds descriptors in uniform registers and emits the MMA directly.  Issuing from
+// inside an `if (lane == 0)` region instead makes every operand a per-thread value that has to be moved to uniform
+// registers through an elect / R2UR loop per instruction (~20 extra instructions: the issue rate, not the tensor pipe,
+// then bounds a chain of MMAs -- tools/tc_rate.cu: 246 vs 163 cycles per 128x256x16 MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // plain (non-release) remote arrive: the data the arrival publishes has been made visible by the caller
 // (fence.proxy.async / tcgen05.fence::before_thread_sync + fence.acq_rel.cluster where generic-proxy data is involved)
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {

@@ -17,7 +17,7 @@ from .normalizers import DepthNormalizer, PIFuNomalizer  # noqa: F401
 from .backbones import HGFilter, PIFuHGFilters, ResnetFilter, PIFuResBlkFilters  # noqa: F401
 from .heads import SurfaceClassifier, PIFuNetGMLP, PIFuNetCMLP  # noqa: F401
 
-_MODES = {"fp32": _lib.MODE_FP32, "tc": _lib.MODE_TC, "auto": _lib.MODE_AUTO, "tc_v2": _lib.MODE_TC_V2, "tc_v3": _lib.MODE_TC_V3}
+_MODES = {"fp32": _lib.MODE_FP32, "tc": _lib.MODE_TC, "auto": _lib.MODE_AUTO, "tc_v3": _lib.MODE_TC_V3}
 
 
 class FeatureHandle:
@@ -78,7 +78,7 @@ class MonoPortNet(nn.Module):
         self.surface_classifier = globals()[opt_net.head.IMF](opt_net.head)
         self.projection = globals()[opt_net.projection]
         self.normalizer = globals()[opt_net.normalizer.IMF](opt_net.normalizer)
-        # arithmetic of the fused kernel: "auto" (tcgen05 when supported), "tc", "fp32"; "tc_v2"/"tc_v3" pin the tensor-core program
+        # arithmetic of the fused kernel: "auto" (tcgen05 when supported), "tc" (= "tc_v3"), "fp32"
         self.precision = os.environ.get("MONOPORT_B200_MODE", "auto")
         # True: skip the per-call feature upload when the tensor's (address, version) are unchanged (see FeatureHandle.upload
         # for what that identity cannot see); default off -- every query()/query_grid()/engine call uploads its frame

@@ -27,6 +27,9 @@ class SurfaceClassifier(nn.Module):
             self.filters.append(nn.Conv1d(cin, filter_channels[l + 1], 1))
         self._handle = None
         self._handle_key = None
+        # largest |feature| a frame may have for the tensor-core program to be used (None = the library default: 12 for the
+        # geometry head, 8 for the colour head; float("inf") disables the guard); larger frames take the exact fp32 kernel
+        self.tc_feature_limit = None
 
     # ---- autograd / stand-alone module forward (training scaffolding, not the hot path) ----------------
     def forward(self, feature):
@@ -59,7 +62,7 @@ class SurfaceClassifier(nn.Module):
         """mp_mlp_t* for the current parameters (rebuilt when they change: load_state_dict, .to(), optimizer step)."""
         key = self._key()
         if self._handle is not None and key == self._handle_key and not any(k[1] is None for k in key):
-            return self._handle
+            return self._with_limit(self._handle)
         self.release()
         lib = _lib.load()
         dev = self.filters[0].weight.device
@@ -77,6 +80,14 @@ class SurfaceClassifier(nn.Module):
             _lib.check(lib.mp_mlp_create(n, chans, wp, bp, 0 if self.no_residual else 1, self.last_op_code(), 1,
                                          ctypes.byref(h)), "mp_mlp_create")
         self._handle, self._handle_key = h, key
+        self._applied_limit = None
+        return self._with_limit(h)
+
+    def _with_limit(self, h):
+        if self.tc_feature_limit is not None and self.tc_feature_limit != self._applied_limit:
+            _lib.check(_lib.load().mp_mlp_set_tc_feature_limit(h, ctypes.c_float(float(self.tc_feature_limit))),
+                       "mp_mlp_set_tc_feature_limit")
+            self._applied_limit = self.tc_feature_limit
         return h
 
     def tc_supported(self):

@@ -173,17 +173,22 @@ def colorization(netC, feat_tensor_C, X, Y, Z, calib_tensor, norm=None, resoluti
             and head.filter_channels[-1] == 3 and head.tc_supported()):
         # one launch: vertices -> world (mat_color) -> netC -> pred*0.5+0.5 -> canvas  (tensor-core program of the colour head)
         n = int(X.numel())
+        rc = _lib.MP_OK
         if n:
             Xc, Yc, Zc = X.contiguous(), Y.contiguous(), Z.float().contiguous()
             with _lib.device_guard(device):
                 fh = netC.feature_handle(feat)
                 proj = _lib.PROJ_PERSPECTIVE if netC.projection is perspective else _lib.PROJ_ORTHOGONAL
-                _lib.check(_lib.load().mp_colorize_surface(
+                rc = _lib.load().mp_colorize_surface(
                     head.handle(), fh.ptr, ctypes.c_void_p(Xc.data_ptr()), ctypes.c_void_p(Yc.data_ptr()),
                     ctypes.c_void_p(Zc.data_ptr()), n, int(resolution), _lib.f3(b_min), _lib.f3(b_max), _lib.calib12(calib_tensor),
-                    proj, ctypes.c_float(netC.normalizer.scale), ctypes.c_void_p(image.data_ptr()), _lib.stream_ptr(device)),
-                    "mp_colorize_surface")
-        return image
+                    proj, ctypes.c_float(netC.normalizer.scale), ctypes.c_void_p(image.data_ptr()), _lib.stream_ptr(device))
+                if rc != _lib.MP_E_RANGE:
+                    _lib.check(rc, "mp_colorize_surface")
+        if rc != _lib.MP_E_RANGE:
+            return image
+        # features outside the validated range of the tensor-core colour program: the generic route below (its query()
+        # takes the exact fp32 kernel for such a frame)
     verts = torch.stack([X.float(), Y.float(), resolution - Z.float()], dim=1)          # RTL/main.py:231-233
     samples = verts.unsqueeze(0).permute(0, 2, 1).contiguous()                          # [1,3,N]
     samples = orthogonal(samples, make_mat_color(resolution, b_min, b_max, device).unsqueeze(0))

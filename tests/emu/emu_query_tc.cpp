@@ -9,6 +9,7 @@
 #include <stdarg.h>
 
 #define MP_EMU_CUDA_TYPES 1
+#include <math.h>
 #include "cuda_emu.h"
 
 // ---- device intrinsics the real headers only provide to nvcc -----------------------------------------------------------
@@ -37,6 +38,7 @@ cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) /
 cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
   if (a == cudaDevAttrComputeCapabilityMajor) *v = 10;
@@ -64,7 +66,7 @@ template <class T> static cudaError_t cudaFuncSetAttribute(T*, cudaFuncAttribute
 
 #include "../../monoport_b200/csrc/query_tc.cu"
 
-int mp_launch_query_fp32(const mp_mlp*, const mp_feat*, const MpPointSrc&, const MpCalib&, const MpOutDst&, cudaStream_t) { return MP_E_UNSUPPORTED; }
+int mp_launch_query_fp32(const mp_mlp*, const mp_feat*, const MpPointSrc&, const MpCalib&, const MpOutDst&, cudaStream_t, int) { return MP_E_UNSUPPORTED; }
 
 // mp_api.cu's helper (that file holds <<<>>> launches and is not part of this build)
 static void fill_grid_geom(MpPointSrc& s, int res, int node_stride, int r_final) {
@@ -97,6 +99,9 @@ int main(int argc, char** argv) {
   mp_mlp mlp;
   memset(&mlp, 0, sizeof(mlp));
   mlp.n_layers = 5; mlp.skip = 1; mlp.last_op = last_op;
+  mlp.gen = 1;
+  mlp.tc_amax_limit = getenv("EMU_TC_LIMIT") ? (float)atof(getenv("EMU_TC_LIMIT")) : INFINITY;      // range guard (see mp_query_dispatch)
+  const int guard = getenv("EMU_TC_GUARD") ? atoi(getenv("EMU_TC_GUARD")) : MP_GUARD_NONE;
   std::vector<std::vector<float>> Ws(5), Bs(5);
   for (int l = 0; l <= 5; ++l) mlp.channels[l] = chans[l];
   for (int l = 0; l < 5; ++l) {
@@ -122,6 +127,8 @@ int main(int argc, char** argv) {
   mp_feat feat;
   memset(&feat, 0, sizeof(feat));
   feat.C = C; feat.H = H; feat.W = W; feat.nhwc32 = nhwc.data(); feat.version = 1;
+  unsigned amax_word = 0;
+  feat.amax = &amax_word;
   MpPointSrc src;
   memset(&src, 0, sizeof(src));
   src.kind = MP_SRC_ROWS;
@@ -189,7 +196,9 @@ int main(int argc, char** argv) {
   for (int p = 0; p < n_peers; ++p) dst.peer[p] = peer[p].data();
   dst.n_peers = n_peers;
   dst.peer_off = peer_off;
-  const int rc = mp_launch_query_tc(&mlp, &feat, src, cal, dst, nullptr, program % 100);
+  if (program % 100 != 3 && program % 100 != 0) { fprintf(stderr, "unknown program %d (3 = the tensor-core program, 103 = with peer stores)\n", program); return 2; }
+  const int rc = mp_launch_query_tc(&mlp, &feat, src, cal, dst, nullptr, guard);
+  if (getenv("EMU_TC_AMAX")) { float a; memcpy(&a, &amax_word, 4); fprintf(stderr, "amax %.9g\n", a); }
   if (rc != MP_OK) { fprintf(stderr, "mp_launch_query_tc: %s\n", g_err); return 3; }
   if (out[(size_t)res * n_out] != -4242.f) { fprintf(stderr, "wrote past the output\n"); return 3; }
   if (!scatter.empty()) out.assign(scatter.begin(), scatter.end());       // report the scattered volume

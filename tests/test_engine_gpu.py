@@ -221,7 +221,7 @@ def test_frame_pipeline_overlap_equals_sequential():
         W2, b2, f, _ = spec.heightfield_person(Ws, bs, base * (1.0 + 0.1 * k), channel=0)
         feats.append(f.cuda())
     net = build_net("G", W2, b2)
-    net.precision = "tc_v2"
+    net.precision = "tc"
     cal = spec.scene_calib(20, 33).cuda()
     b = np.array([[-1.0, -1.0, -1.0]], dtype=np.float32)
     eng = Seg3dLossless(make_query_func(net), b, -b, [17, 33, 65], balance_value=0.5, faster=True).to("cuda")

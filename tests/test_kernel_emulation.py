@@ -228,11 +228,11 @@ def _run_query_tc(exe, tmp_path, case, n, program, sms):
 
 @pytest.mark.parametrize("name,n,program,sms", [
     ("g_smallmap", 300, 3, 1),      # one CTA walks three tiles: cross-tile software pipelining of the workers, ragged last tile
-    ("g_smallmap", 300, 2, 2),      # self-contained program (all five layers per point)
+    ("g_smallmap", 300, 3, 2),      # two CTAs
     ("g_smallmap", 200, 103, 1),    # program v3 with the fused slab exchange (peer stores)
     pytest.param("g_rot33", 130, 3, 148, marks=full_only),   # 128 x 128 map: 128 CTAs of the G0 GEMM, rotated calibration
-    ("g_persp", 100, 2, 1),         # perspective projection
-    ("g_nocalib", 150, 2, 3),       # calibs=None
+    ("g_persp", 100, 3, 1),         # perspective projection
+    ("g_nocalib", 150, 3, 3),       # calibs=None
 ])
 def test_tcgen05_kernels_match_reference_golden(emu_query_tc, tmp_path, name, n, program, sms):
     from helpers import load_query_case
@@ -270,7 +270,7 @@ def _write_tc_input(path, case, n):
             f.write(b.numpy().tobytes())
 
 
-@pytest.mark.parametrize("program", [2, 3, 103])
+@pytest.mark.parametrize("program", [3, 103])
 def test_tcgen05_kernels_grid_source(emu_query_tc, tmp_path, program):
     """mp_query_grid's point source: node centres of a z slab generated in-kernel (103: also stored into the peer volumes
     at the slab's offset, the fused slab exchange)."""
@@ -289,7 +289,7 @@ def test_tcgen05_kernels_grid_source(emu_query_tc, tmp_path, program):
     assert got.numel() == nz * R * R and (got - want).abs().max().item() <= 1e-4
 
 
-@pytest.mark.parametrize("program", [2, 3])
+@pytest.mark.parametrize("program", [3])
 def test_tcgen05_kernels_node_list_source(emu_query_tc, tmp_path, program):
     """The octree engine's fused path: an index list with a device-side count below the list capacity, values scattered
     into the level volume; nodes that are not on the list stay untouched."""

@@ -149,17 +149,13 @@ def write_inc(path):
     with open(path, "w") as f:
         f.write("// GENERATED by tools/gen_mc_table.py -- do not edit.  See that file for the derivation.\n")
         f.write("#define MC_MAX_TRI %d\n" % maxt)
-        f.write("static __constant__ unsigned char c_mc_ntri[256] = {%s};\n" %
-                ",".join(str(int(v)) for v in ntri))
-        f.write("static __constant__ signed char c_mc_tri[256][%d] = {\n" % (maxt * 3))
-        for c in range(256):
-            f.write("  {%s},\n" % ",".join(str(int(v)) for v in tri[c]))
-        f.write("};\n")
-        # the same table in global memory, rows padded to 16 bytes: divergent per-lane lookups (one case per active cell)
-        # go through L1 instead of serialising on the constant cache
+        # one 16-byte row per case in global memory: bytes 0..14 the edge ids of up to five triangles (-1 padded), byte 15
+        # the triangle count.  Per-lane lookups (one case per active cell) go through L1 as ONE 16-byte load instead of
+        # serialising on the constant cache.
+        assert tri.shape[1] == 15
         f.write("static __device__ const signed char g_mc_tri[256][16] = {\n")
         for c in range(256):
-            f.write("  {%s},\n" % ",".join([str(int(v)) for v in tri[c]] + ["-1"] * (16 - tri.shape[1])))
+            f.write("  {%s},\n" % ",".join([str(int(v)) for v in tri[c]] + [str(int(ntri[c]))]))
         f.write("};\n")
     return maxt
 

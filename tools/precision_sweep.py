@@ -15,7 +15,7 @@ for seed in range(12):
     want = spec.query_ref(feat, pts, cal, Ws, bs, spec.LAST_SIGMOID)[0]
     net = build_net("G", Ws, bs)
     row = []
-    for mode in ("tc_v2", "tc_v3"):
+    for mode in ("tc",):
         net.precision = mode
         got = net.query([[feat.cuda()]], pts.cuda(), calibs=cal.cuda())[0][0, 0].cpu()
         e = (got - want).abs()

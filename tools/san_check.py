@@ -14,12 +14,12 @@ Ws, bs, feat, _ = spec.heightfield_person(Ws, bs, feat)
 net = build_net("G", Ws, bs)
 cal = spec.scene_calib(20, 33).cuda()
 pts = spec.make_points(700, 1).cuda()
-for mode in ("fp32", "tc_v2", "tc_v3"):
+for mode in ("fp32", "tc"):
     net.precision = mode
     out = net.query([[feat.cuda()]], pts, calibs=cal)[0]
     torch.cuda.synchronize()
     print(mode, float(out.sum()))
-net.precision = "tc_v2"
+net.precision = "tc"
 b = np.array([[-1.0, -1.0, -1.0]], dtype=np.float32)
 for faster in (True, False):
     eng = Seg3dLossless(make_query_func(net), b, -b, [9, 17, 33], balance_value=0.5, faster=faster).to("cuda")

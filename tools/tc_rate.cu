@@ -8,6 +8,9 @@
 //                                                 4 = A operand from tensor memory (the layer-2 / layer-3 hidden parts)
 //                                                 8 = weights by tensor-map TMA (cp.async.bulk.tensor) instead of 1-D bulk copies
 //                                                     (cg 2: completion of both CTAs' halves lands on the leader's barrier)
+//                                                 16 = N = 128 instead of 256          32 = alternate the accumulator every MMA
+//                                                 64 = fully unrolled issue loop       128 = a second issuing warp (no streaming:
+//                                                      each warp issues half of the MMAs into its own accumulator)
 // Prints cycles per MMA (min / mean over the CTAs that issue) and the implied fraction of the 128-cycle floor.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -lineinfo -o tc_rate tools/tc_rate.cu -lcuda
 #include <cuda.h>
@@ -52,7 +55,10 @@ __global__ void __launch_bounds__(kThreads, 1) rate_kernel(const __grid_constant
   const uint32_t rank = CG == 2 ? tc::cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   const int flags = prm.flags, n_stages = prm.stages;
+  int n_stages_half = n_stages;
   const bool f_stream = flags & 1, f_workers = flags & 2, f_ts = flags & 4, f_tmap = flags & 8;
+  const bool f_n128 = flags & 16, f_alt = flags & 32, f_unroll = flags & 64, f_two = flags & 128, f_noacc = flags & 256;   // 256: never accumulate (D is not read)
+  const bool f_uniform = flags & 512;   // 512: warp-uniform issue loop, one elected lane per MMA (no streaming / workers)
 
   for (int i = tid; i < (Off::Wr + 98304) / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
@@ -99,14 +105,41 @@ __global__ void __launch_bounds__(kThreads, 1) rate_kernel(const __grid_constant
         }
       }
     }
+  } else if (warp == 1 && leader && f_uniform) {
+    // ---- the whole warp runs the loop; only the tcgen05 instructions are predicated on one elected lane
+    const uint32_t idesc = tc::make_idesc_f16(128 * CG, f_n128 ? 128 : 256);
+    const uint32_t sX = tc::smem_u32(smem + Off::X), sW = tc::smem_u32(smem + Off::Wr);
+    for (int sl = 0; sl < Stages; ++sl) tc::mbar_wait(bars + B_FULL + sl, 0);
+    tc::tcgen05_fence_after();
+    const long long t0 = clock64();
+    for (int it = 0; it < n_stages; ++it) {
+      const int slot = it % Stages;
+      if (f_stream && it >= Stages) { tc::mbar_wait(bars + B_FULL + slot, (it / Stages) & 1); tc::tcgen05_fence_after(); }
+      const uint64_t ad0 = tc::make_sdesc_sw128(sX + (it & 3) * 16384, 1024), bd0 = tc::make_sdesc_sw128(sW + slot * StageBytes, 1024);
+      const uint32_t d = tbase + (it & 1) * 256;
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if constexpr (CG == 1) tc::mma_ss(d, ad0 + 2 * kk, bd0 + 2 * kk, idesc, (it < 2 && kk == 0) ? 0u : 1u);
+          else tc::mma_ss2(d, ad0 + 2 * kk, bd0 + 2 * kk, idesc, (it < 2 && kk == 0) ? 0u : 1u);
+        }
+        if (f_stream) { if constexpr (CG == 1) tc::mma_commit(bars + B_EMPTY + slot); else tc::mma_commit2(bars + B_EMPTY + slot); }
+      }
+      __syncwarp();
+    }
+    if (tc::elect_one()) { if constexpr (CG == 1) tc::mma_commit(bars + B_DONE); else tc::mma_commit2(bars + B_DONE); }
+    __syncwarp();
+    tc::mbar_wait(bars + B_DONE, 0);
+    if (lane == 0) prm.cycles[blockIdx.x] = (unsigned long long)(clock64() - t0);
   } else if (warp == 1 && leader) {
     if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_f16(128 * CG, 256);
+      const uint32_t idesc = tc::make_idesc_f16(128 * CG, f_n128 ? 128 : 256);
+      if (f_two) n_stages_half = n_stages / 2;
       const uint32_t sX = tc::smem_u32(smem + Off::X), sH0 = tc::smem_u32(smem + Off::H0), sW = tc::smem_u32(smem + Off::Wr);
       uint32_t c_ready[2] = {0, 0};
       const long long t0 = clock64();
       bool first = true;
-      for (int it = 0; it < n_stages; ++it) {
+      for (int it = 0; it < n_stages_half; ++it) {
         const int chunk = it >> 2, b = chunk & 1, kb = (it >> 1) & 1;       // 4 stages (2 K-blocks x 2 N-halves) per chunk
         if (f_workers && (it & 3) == 0) {
           tc::mbar_wait_cluster(bars + B_READY0 + b, c_ready[b] & 1u);
@@ -122,6 +155,17 @@ __global__ void __launch_bounds__(kThreads, 1) rate_kernel(const __grid_constant
         }
         const uint32_t w = sW + slot * StageBytes;
         const uint32_t d = tbase + (it & 1) * 256;
+        if (f_unroll) {
+          const uint32_t a = sX + (it & 3) * 16384;
+          const uint64_t ad0 = tc::make_sdesc_sw128(a, 1024), bd0 = tc::make_sdesc_sw128(w, 1024);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t dd = f_alt ? tbase + (kk & 1) * 256 : d;
+            if constexpr (CG == 1) tc::mma_ss(dd, ad0 + 2 * kk, bd0 + 2 * kk, idesc, first ? 0u : 1u);
+            else tc::mma_ss2(dd, ad0 + 2 * kk, bd0 + 2 * kk, idesc, first ? 0u : 1u);
+            if (kk >= 1) first = false;
+          }
+        } else
 #pragma unroll 1
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t bd = tc::make_sdesc_sw128(w + kk * 32, 1024);
@@ -132,10 +176,11 @@ __global__ void __launch_bounds__(kThreads, 1) rate_kernel(const __grid_constant
           } else {
             const uint32_t a = f_workers ? sH0 + b * 32768 + kb * 16384 : sX + (it & 3) * 16384;
             const uint64_t ad = tc::make_sdesc_sw128(a + kk * 32, 1024);
-            if constexpr (CG == 1) tc::mma_ss(d, ad, bd, idesc, first ? 0u : 1u);
-            else tc::mma_ss2(d, ad, bd, idesc, first ? 0u : 1u);
+            const uint32_t dd = f_alt ? tbase + (kk & 1) * 256 : d;
+            if constexpr (CG == 1) tc::mma_ss(dd, ad, bd, idesc, ((first && kk < 2) || f_noacc) ? 0u : 1u);
+            else tc::mma_ss2(dd, ad, bd, idesc, ((first && kk < 2) || f_noacc) ? 0u : 1u);
           }
-          first = false;
+          if (kk >= 1) first = false;
         }
         if (f_stream) { if constexpr (CG == 1) tc::mma_commit(bars + B_EMPTY + slot); else tc::mma_commit2(bars + B_EMPTY + slot); }
         if (f_workers && (it & 3) == 3) { if constexpr (CG == 1) tc::mma_commit(bars + B_FREE0 + b); else tc::mma_commit2(bars + B_FREE0 + b); }
@@ -143,6 +188,24 @@ __global__ void __launch_bounds__(kThreads, 1) rate_kernel(const __grid_constant
       if constexpr (CG == 1) tc::mma_commit(bars + B_DONE); else tc::mma_commit2(bars + B_DONE);
       tc::mbar_wait(bars + B_DONE, 0);
       prm.cycles[blockIdx.x] = (unsigned long long)(clock64() - t0);
+    }
+  } else if (warp == 3 && f_two && CG == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_f16(128, f_n128 ? 128 : 256);
+      const uint32_t sX = tc::smem_u32(smem + Off::X), sW = tc::smem_u32(smem + Off::Wr);
+      tc::mbar_wait(bars + B_FULL + 2, 0);
+      tc::tcgen05_fence_after();
+      bool first = true;
+      for (int it = 0; it < n_stages / 2; ++it) {
+        const uint32_t w = sW + 2 * 32768;
+#pragma unroll 1
+        for (int kk = 0; kk < 4; ++kk) {
+          tc::mma_ss(tbase + 256, tc::make_sdesc_sw128(sX + (it & 3) * 16384 + kk * 32, 1024), tc::make_sdesc_sw128(w + kk * 32, 1024), idesc,
+                     first ? 0u : 1u);
+          first = false;
+        }
+      }
+      tc::mma_commit(bars + B_READY0);
     }
   } else if (warp >= 4 && f_workers) {
     // ---- workers: rewrite the 32 KB chunk buffer (what the sampled layer-0 chunk generation stores) and hand it over
