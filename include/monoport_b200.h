@@ -112,16 +112,25 @@ int mp_query_points_host(mp_mlp_t* mlp, mp_feat_t* feat, const float* feat_nchw_
  * across GPUs calls this with a different [z0,nz) per rank. */
 int mp_query_grid(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0, int nz, const float* b_min3, const float* b_max3,
                   const float* calib12, int projection, float z_scale, float* out_dev, int mode, void* stream);
+/* The same for any contiguous range [lin0, lin0+n) of the grid's z-major linear node order (a z slab is the range
+ * [z0*R*R, (z0+nz)*R*R)): balanced sharding over GPUs whose boundaries need not fall on plane boundaries (257 = 8*32+1:
+ * with whole planes one rank carries 33 planes and the others 32).  out_dev receives n values. */
+int mp_query_grid_range(mp_mlp_t* mlp, mp_feat_t* feat, int R, int64_t lin0, int64_t n, const float* b_min3,
+                        const float* b_max3, const float* calib12, int projection, float z_scale, float* out_dev, int mode,
+                        void* stream);
 
 /* Fused slab exchange (instead of the all-gather): the slab [z0, z0+nz) is evaluated like mp_query_grid,
  * but every value is stored straight into the FULL [R,R,R] volumes of all n_peers ranks (peer_vols: host array of
  * device pointers, the caller's own volume included; peers' volumes are peer-memory mappings obtained through
  * mp_ipc_open) while the tiles are computed -- compute and transfer in ONE kernel over NVLink.  The caller synchronises
  * the ranks afterwards (any barrier ordered after this call on `stream`); with two alternating volume sets one barrier
- * per frame suffices.  MP_MODE_TC / AUTO only (tensor-core program v3); n_peers <= 8. */
+ * per frame suffices.  n_peers <= 8.  mp_query_grid_range_peers: the same for a range of the linear node order. */
 int mp_query_grid_peers(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0, int nz, const float* b_min3, const float* b_max3,
                         const float* calib12, int projection, float z_scale, float* const* peer_vols, int n_peers,
                         int mode, void* stream);
+int mp_query_grid_range_peers(mp_mlp_t* mlp, mp_feat_t* feat, int R, int64_t lin0, int64_t n, const float* b_min3,
+                              const float* b_max3, const float* calib12, int projection, float z_scale,
+                              float* const* peer_vols, int n_peers, int mode, void* stream);
 /* Exportable device memory for such volumes: cudaMalloc + the 64-byte cudaIpcMemHandle_t to hand to the other ranks
  * (one process per GPU), which map it with mp_ipc_open (enables peer access) and unmap it with mp_ipc_close. */
 int mp_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
@@ -168,6 +177,18 @@ int mp_octree_finish(mp_octree_t* h, float* out_dev, int* nonempty, void* stream
  * Synchronises once at the end (to report nonempty/stats). */
 int mp_octree_run_fused(mp_octree_t* h, mp_mlp_t* mlp, mp_feat_t* feat, const float* calib12, int projection,
                         float z_scale, int mode, float* out_dev, int* nonempty, int64_t* stats_host, void* stream);
+/* Multi-GPU list sharding of mp_octree_run_fused (one process per GPU, one handle per rank, same ctor
+ * arguments).  Every rank keeps the whole pyramid and runs the volume passes itself -- identical inputs give identical
+ * node lists, the lossless conflict loop included -- and evaluates only its window of each level's ordered node list
+ * (balanced to one 128-point tile); the fused kernel stores the values into the value lists of ALL ranks over NVLink peer
+ * memory and a flag barrier between the ranks' streams replaces the collective.  Every rank ends up with the full volume.
+ *   mp_octree_shard_export : 3 x 64-byte IPC handles (two value lists, the barrier flags) to hand to the other ranks;
+ *   mp_octree_shard_set    : rank / world and, per rank, the peer mappings of those three blocks (mp_ipc_open; entry
+ *                            [rank] is ignored).  world == 1 switches sharding off.  All ranks must then call
+ *                            mp_octree_run_fused the same number of times with the same inputs. */
+int mp_octree_shard_export(mp_octree_t* h, unsigned char* handles192);
+int mp_octree_shard_set(mp_octree_t* h, int rank, int world, float* const* vals0, float* const* vals1,
+                        uint32_t* const* flags);
 
 /* ---------------------------------------------------------------------------------------------
  * Marching cubes (absent from the reference; PIFu-style reconstruction() asked for by the north star).

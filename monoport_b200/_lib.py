@@ -46,6 +46,10 @@ SIGNATURES = {
                               c_float, c_void_p, c_int, c_void_p]),
     "mp_query_grid_peers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, P(c_float), P(c_float), P(c_float), c_int,
                                     c_float, P(c_void_p), c_int, c_int, c_void_p]),
+    "mp_query_grid_range": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, P(c_float), P(c_float), P(c_float), c_int,
+                                    c_float, c_void_p, c_int, c_void_p]),
+    "mp_query_grid_range_peers": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, P(c_float), P(c_float), P(c_float),
+                                          c_int, c_float, P(c_void_p), c_int, c_int, c_void_p]),
     "mp_ipc_alloc": (c_int, [ctypes.c_size_t, P(c_void_p), ctypes.c_char_p]),
     "mp_ipc_open": (c_int, [ctypes.c_char_p, P(c_void_p)]),
     "mp_ipc_close": (c_int, [c_void_p]),
@@ -60,6 +64,8 @@ SIGNATURES = {
     "mp_octree_finish": (c_int, [c_void_p, c_void_p, P(c_int), c_void_p]),
     "mp_octree_run_fused": (c_int, [c_void_p, c_void_p, c_void_p, P(c_float), c_int, c_float, c_int, c_void_p,
                                     P(c_int), P(c_int64), c_void_p]),
+    "mp_octree_shard_export": (c_int, [c_void_p, ctypes.c_char_p]),
+    "mp_octree_shard_set": (c_int, [c_void_p, c_int, c_int, P(c_void_p), P(c_void_p), P(c_void_p)]),
     "mp_mcubes_create": (c_int, [c_int, c_int, c_int, P(c_void_p)]),
     "mp_mcubes_destroy": (c_int, [c_void_p]),
     "mp_mcubes_count": (c_int, [c_void_p, c_void_p, c_float, P(c_int64), P(c_int64), c_void_p]),

@@ -255,8 +255,8 @@ int mp_query_dispatch(mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, const M
     // Range guard: the tensor-core program is validated (<= 1e-4 on what query() returns) for frames whose largest
     // |feature| stays under the head's limit.  The decision is taken on the device, per launch, from the frame's own
     // maximum (no host synchronisation, graph-capturable): the tensor-core launch runs when the frame is in range, the
-    // exact fp32 launch when it is not; the other one returns at once.  Peer stores exist in the tensor-core kernel only.
-    const bool guarded = isfinite(mlp->tc_amax_limit) && dst.n_peers == 0;
+    // exact fp32 launch when it is not; the other one returns at once.
+    const bool guarded = isfinite(mlp->tc_amax_limit);
     int rc = mp_launch_query_tc(mlp, feat, src, cal, dst, st, guarded ? MP_GUARD_IN_RANGE : MP_GUARD_NONE);
     if (rc != MP_OK || !guarded) return rc;
     return mp_launch_query_fp32(mlp, feat, src, cal, dst, st, MP_GUARD_OUT_OF_RANGE);
@@ -323,56 +323,67 @@ extern "C" int mp_query_points_host(mp_mlp_t* mlp, mp_feat_t* feat, const float*
   return rc;
 }
 
-extern "C" int mp_query_grid(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0, int nz, const float* b_min3, const float* b_max3,
-                             const float* calib12, int projection, float z_scale, float* out_dev, int mode, void* stream) {
+// One implementation behind the four grid entry points: nodes [lin0, lin0 + n) of the R^3 grid in z-major linear order
+// (a z slab is the range [z0*R*R, (z0+nz)*R*R)), values to out_dev[0..n) and / or to every peer volume at offset lin0.
+static int query_grid_range(mp_mlp_t* mlp, mp_feat_t* feat, int R, long long lin0, long long n, const float* b_min3,
+                            const float* b_max3, const float* calib12, int projection, float z_scale, float* out_dev,
+                            float* const* peer_vols, int n_peers, int mode, void* stream) {
   MP_REQUIRE(mlp && feat, "NULL handle");
-  MP_REQUIRE(R >= 1 && z0 >= 0 && nz >= 0 && z0 + nz <= R, "bad slab R=%d z0=%d nz=%d", R, z0, nz);
+  MP_REQUIRE(R >= 1 && lin0 >= 0 && n >= 0 && lin0 + n <= (long long)R * R * R, "bad range R=%d lin0=%lld n=%lld", R, lin0, n);
   MP_REQUIRE(b_min3 && b_max3, "NULL bounds");
-  MP_REQUIRE(mlp->cout[mlp->n_layers - 1] == 1, "mp_query_grid needs a single-channel head");
-  if (nz == 0) return MP_OK;
-  MP_REQUIRE(out_dev, "NULL out");
+  MP_REQUIRE(mlp->cout[mlp->n_layers - 1] == 1, "grid queries need a single-channel head");
+  MP_REQUIRE(n_peers >= 0 && n_peers <= MP_MAX_PEERS && (n_peers == 0 || peer_vols), "n_peers=%d out of range [0,%d]", n_peers, MP_MAX_PEERS);
+  for (int p = 0; p < n_peers; ++p) MP_REQUIRE(peer_vols[p] != nullptr, "peer volume %d is NULL", p);
+  if (n == 0) return MP_OK;
+  MP_REQUIRE(out_dev || n_peers > 0, "NULL out");
   MpPointSrc src;
   memset(&src, 0, sizeof(src));
   src.kind = MP_SRC_GRID;
   mp_fill_grid_geom(src, R, 1, R, b_min3, b_max3);
-  src.z0 = z0;
-  src.n = (long long)nz * R * R;
+  src.lin0 = lin0;
+  src.n = n;
   MpCalib cal;
   mp_fill_calib(cal, calib12, projection, z_scale);
   MpOutDst dst;
-  dst.out = out_dev; dst.ld = src.n; dst.scatter_vol = nullptr;
-  // (the tensor-core program never depends on the slab size, so a z-sharded volume is bit-identical to the single-GPU
-  // volume for every rank count)
+  dst.out = out_dev; dst.ld = n; dst.scatter_vol = nullptr;
+  for (int p = 0; p < n_peers; ++p) dst.peer[p] = peer_vols[p];
+  dst.n_peers = n_peers;
+  dst.peer_off = lin0;        // the range's position inside every full [R,R,R] volume
+  // (the value of a node never depends on the range it is evaluated in, so a sharded volume is bit-identical to the
+  // single-GPU volume for every rank count)
   return mp_query_dispatch(mlp, feat, src, cal, dst, mode, (cudaStream_t)stream);
 }
 
+extern "C" int mp_query_grid(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0, int nz, const float* b_min3, const float* b_max3,
+                             const float* calib12, int projection, float z_scale, float* out_dev, int mode, void* stream) {
+  MP_REQUIRE(R >= 1 && z0 >= 0 && nz >= 0 && z0 + nz <= R, "bad slab R=%d z0=%d nz=%d", R, z0, nz);
+  return query_grid_range(mlp, feat, R, (long long)z0 * R * R, (long long)nz * R * R, b_min3, b_max3, calib12, projection, z_scale,
+                          out_dev, nullptr, 0, mode, stream);
+}
+
+extern "C" int mp_query_grid_range(mp_mlp_t* mlp, mp_feat_t* feat, int R, int64_t lin0, int64_t n, const float* b_min3,
+                                   const float* b_max3, const float* calib12, int projection, float z_scale, float* out_dev,
+                                   int mode, void* stream) {
+  return query_grid_range(mlp, feat, R, lin0, n, b_min3, b_max3, calib12, projection, z_scale, out_dev, nullptr, 0, mode, stream);
+}
+
 // ---------------------------------------------------------------------------------------------
-// fused slab exchange (multi-GPU z-slab sharding without a data collective)
+// fused slab exchange (multi-GPU sharding of the grid without a data collective)
 // ---------------------------------------------------------------------------------------------
 extern "C" int mp_query_grid_peers(mp_mlp_t* mlp, mp_feat_t* feat, int R, int z0, int nz, const float* b_min3,
                                    const float* b_max3, const float* calib12, int projection, float z_scale,
                                    float* const* peer_vols, int n_peers, int mode, void* stream) {
-  MP_REQUIRE(mlp && feat, "NULL handle");
   MP_REQUIRE(R >= 1 && z0 >= 0 && nz >= 0 && z0 + nz <= R, "bad slab R=%d z0=%d nz=%d", R, z0, nz);
-  MP_REQUIRE(b_min3 && b_max3, "NULL bounds");
-  MP_REQUIRE(mlp->cout[mlp->n_layers - 1] == 1, "mp_query_grid_peers needs a single-channel head");
-  MP_REQUIRE(peer_vols && n_peers >= 1 && n_peers <= MP_MAX_PEERS, "n_peers=%d out of range [1,%d]", n_peers, MP_MAX_PEERS);
-  for (int p = 0; p < n_peers; ++p) MP_REQUIRE(peer_vols[p] != nullptr, "peer volume %d is NULL", p);
-  if (nz == 0) return MP_OK;
-  MpPointSrc src;
-  memset(&src, 0, sizeof(src));
-  src.kind = MP_SRC_GRID;
-  mp_fill_grid_geom(src, R, 1, R, b_min3, b_max3);
-  src.z0 = z0;
-  src.n = (long long)nz * R * R;
-  MpCalib cal;
-  mp_fill_calib(cal, calib12, projection, z_scale);
-  MpOutDst dst;
-  dst.out = nullptr; dst.ld = src.n; dst.scatter_vol = nullptr;
-  for (int p = 0; p < n_peers; ++p) dst.peer[p] = peer_vols[p];
-  dst.n_peers = n_peers;
-  dst.peer_off = (long long)z0 * R * R;        // the slab's position inside every full [R,R,R] volume
-  return mp_query_dispatch(mlp, feat, src, cal, dst, mode, (cudaStream_t)stream);
+  MP_REQUIRE(peer_vols && n_peers >= 1, "n_peers=%d out of range [1,%d]", n_peers, MP_MAX_PEERS);
+  return query_grid_range(mlp, feat, R, (long long)z0 * R * R, (long long)nz * R * R, b_min3, b_max3, calib12, projection, z_scale,
+                          nullptr, peer_vols, n_peers, mode, stream);
+}
+
+extern "C" int mp_query_grid_range_peers(mp_mlp_t* mlp, mp_feat_t* feat, int R, int64_t lin0, int64_t n, const float* b_min3,
+                                         const float* b_max3, const float* calib12, int projection, float z_scale,
+                                         float* const* peer_vols, int n_peers, int mode, void* stream) {
+  MP_REQUIRE(peer_vols && n_peers >= 1, "n_peers=%d out of range [1,%d]", n_peers, MP_MAX_PEERS);
+  return query_grid_range(mlp, feat, R, lin0, n, b_min3, b_max3, calib12, projection, z_scale, nullptr, peer_vols, n_peers, mode, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

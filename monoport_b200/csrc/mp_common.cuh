@@ -107,7 +107,12 @@ struct MpPointSrc {
   int res;          // nodes per axis of the (level) grid
   int node_stride;  // index-space stride of a node (final-resolution units)
   int r_final;      // final resolution (divisor of the world mapping)
-  int z0;           // first plane (MP_SRC_GRID slab)
+  int z0;           // (host-side bookkeeping only: first plane of a MP_SRC_GRID slab; the kernels use lin0)
+  long long lin0;   // MP_SRC_GRID: linear index (z slowest) of the node point 0 stands for -- a z slab starts at z0*res*res,
+                    // a balanced shard anywhere (contiguous z-major ranges need not end on plane boundaries)
+  // list sharding (multi-GPU): of the n points (after the device-side count) this launch evaluates only the window
+  // [rank * per, rank * per + per) with per = ceil(n / world) rounded up to a multiple of 128; 0/1 = everything
+  int shard_rank, shard_world;
   float inv_r, half_inv_r;    // 1/r_final, 1/(2 r_final) rounded to fp32
   float bmin[3], bext[3];     // b_min, (b_max - b_min)
   long long n;
@@ -147,8 +152,9 @@ __device__ __forceinline__ void mp_load_point(const MpPointSrc& s, long long i, 
   int ix, iy, iz;
   if (s.kind == MP_SRC_GRID) {
     const long long plane = (long long)s.res * s.res;
-    iz = (int)(i / plane) + s.z0;
-    const int r = (int)(i % plane);
+    const long long li = i + s.lin0;
+    iz = (int)(li / plane);
+    const int r = (int)(li % plane);
     iy = r / s.res;
     ix = r - iy * s.res;
   } else {
@@ -166,6 +172,19 @@ __device__ __forceinline__ void mp_load_point(const MpPointSrc& s, long long i, 
   x = __fadd_rn(__fmul_rn(__fadd_rn(__fdiv_rn(cx, R), s.half_inv_r), s.bext[0]), s.bmin[0]);
   y = __fadd_rn(__fmul_rn(__fadd_rn(__fdiv_rn(cy, R), s.half_inv_r), s.bext[1]), s.bmin[1]);
   z = __fadd_rn(__fmul_rn(__fadd_rn(__fdiv_rn(cz, R), s.half_inv_r), s.bext[2]), s.bmin[2]);
+}
+
+// the window [i0, i1) of a query's n points that this launch evaluates (see MpPointSrc::shard_rank)
+__device__ __forceinline__ void mp_shard_window(const MpPointSrc& s, long long n, long long& i0, long long& i1) {
+  i0 = 0; i1 = n;
+  if (s.shard_world > 1) {
+    long long per = (n + s.shard_world - 1) / s.shard_world;
+    per = (per + 127) / 128 * 128;
+    i0 = per * s.shard_rank;
+    i1 = i0 + per;
+    if (i0 > n) i0 = n;
+    if (i1 > n) i1 = n;
+  }
 }
 
 // geometry.py:19-34 / :37-55

@@ -33,6 +33,31 @@ __global__ void node_points_kernel(MpPointSrc src, float* __restrict__ pts) {
 // per-level evaluated-node counters [MP_MAX_LAYERS + 4] + one slot for the non-empty flag
 constexpr int kStatSlots = MP_MAX_LAYERS + 5;
 
+// ---- multi-GPU list sharding: every rank keeps the whole pyramid state and runs the cheap volume passes
+// itself (identical inputs => identical node lists on every rank, including the lossless conflict loop, which can walk
+// across any slab boundary); only the expensive part -- the MLP evaluation of a level's node list -- is split: rank r
+// evaluates the r-th window of the ordered list (balanced to one 128-point tile) and its kernel stores each value into the
+// value lists of ALL ranks over NVLink peer memory.  What is left of the exchange is this barrier between the ranks'
+// streams: thread p publishes "rank `rank` has finished epoch e" in peer p's flag array and waits for peer p's flag.
+struct XBarrier {
+  uint32_t* peer[MP_MAX_PEERS];   // flag arrays of all ranks ([MP_MAX_PEERS] words each), peer-mapped
+  uint32_t* mine;
+  int rank, world;
+  uint32_t epoch;
+};
+__global__ void xgpu_barrier_kernel(XBarrier b) {
+  const int p = threadIdx.x;
+  if (p < b.world) {
+    // (the peer stores of the preceding kernels of this stream have completed; the fence orders them before the flag)
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(b.peer[p] + b.rank), "r"(b.epoch) : "memory");
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(b.mine + p) : "memory");
+    } while ((int32_t)(v - b.epoch) < 0);
+  }
+}
+
 inline int grid_for(long long n, int threads = 256, int cap = 148 * 8) {
   long long b = (n + threads - 1) / threads;
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
@@ -59,7 +84,16 @@ struct mp_octree {
   uint8_t* conflict;
   int32_t* idx;
   float* points;              // [cap,3]
-  float* vals;                // [cap] scratch (fused path conflict detection)
+  float* vals;                // [cap] scratch (fused path conflict detection); == vals2[0]
+  // list sharding: two alternating value lists (a rank may already receive the next list while it still scatters this
+  // one), the flag array of the cross-GPU barrier, and the peer mappings of all ranks' (own included)
+  float* vals2[2];
+  uint32_t* flags;
+  float* peer_vals[2][MP_MAX_PEERS];
+  uint32_t* peer_flags[MP_MAX_PEERS];
+  int shard_rank, shard_world;
+  uint32_t epoch;
+  int vsel;
   unsigned long long* sums;   // scan block sums
   unsigned long long* total;  // scan total
   int32_t* count;             // device count of the current node list
@@ -88,6 +122,8 @@ extern "C" int mp_octree_destroy(mp_octree_t* h) {
   if (h->idx) cudaFree(h->idx);
   if (h->points) cudaFree(h->points);
   if (h->vals) cudaFree(h->vals);
+  if (h->vals2[1]) cudaFree(h->vals2[1]);
+  if (h->flags) cudaFree(h->flags);
   if (h->sums) cudaFree(h->sums);
   if (h->total) cudaFree(h->total);
   if (h->count) cudaFree(h->count);
@@ -158,7 +194,72 @@ extern "C" int mp_octree_create(int n_levels, const int* resolutions, const floa
     mp_octree_destroy(h);
     return MP_E_NOMEM;
   }
+  h->vals2[0] = h->vals;
+  h->shard_world = 1;
   *out = h;
+  return MP_OK;
+}
+
+// ---- list sharding over the GPUs of a node --------------------------------------------------------
+extern "C" int mp_octree_shard_export(mp_octree_t* h, unsigned char* handles192) {
+  MP_REQUIRE(h && handles192, "NULL argument");
+  if (!h->vals2[1]) MP_CUDA(cudaMalloc(&h->vals2[1], h->cap * sizeof(float)));
+  if (!h->flags) {
+    MP_CUDA(cudaMalloc(&h->flags, MP_MAX_PEERS * sizeof(uint32_t)));
+    MP_CUDA(cudaMemset(h->flags, 0, MP_MAX_PEERS * sizeof(uint32_t)));
+  }
+  void* ptrs[3] = {h->vals2[0], h->vals2[1], h->flags};
+  for (int k = 0; k < 3; ++k) {
+    cudaIpcMemHandle_t ih;
+    MP_CUDA(cudaIpcGetMemHandle(&ih, ptrs[k]));
+    memcpy(handles192 + 64 * k, &ih, 64);
+  }
+  return MP_OK;
+}
+
+extern "C" int mp_octree_shard_set(mp_octree_t* h, int rank, int world, float* const* vals0, float* const* vals1,
+                                   uint32_t* const* flags) {
+  MP_REQUIRE(h, "NULL handle");
+  MP_REQUIRE(world >= 1 && world <= MP_MAX_PEERS && rank >= 0 && rank < world, "bad rank %d of %d (at most %d ranks)", rank, world, MP_MAX_PEERS);
+  if (world == 1) { h->shard_world = 1; h->shard_rank = 0; return MP_OK; }
+  MP_REQUIRE(vals0 && vals1 && flags, "NULL pointer arrays");
+  MP_REQUIRE(h->vals2[1] && h->flags, "mp_octree_shard_export must run first");
+  for (int p = 0; p < world; ++p) {
+    h->peer_vals[0][p] = (p == rank) ? h->vals2[0] : vals0[p];
+    h->peer_vals[1][p] = (p == rank) ? h->vals2[1] : vals1[p];
+    h->peer_flags[p] = (p == rank) ? h->flags : flags[p];
+    MP_REQUIRE(h->peer_vals[0][p] && h->peer_vals[1][p] && h->peer_flags[p], "peer %d: NULL mapping", p);
+  }
+  h->shard_rank = rank;
+  h->shard_world = world;
+  h->epoch = 0;
+  h->vsel = 0;
+  return MP_OK;
+}
+
+// evaluate `src` (this rank's window of it) into the value lists of all ranks, wait for everybody; returns the list to
+// scatter from
+static int sharded_query(mp_octree* h, mp_mlp_t* mlp, mp_feat_t* feat, MpPointSrc src, const MpCalib& cal, int mode,
+                         cudaStream_t st, const float** vals_out) {
+  src.shard_rank = h->shard_rank;
+  src.shard_world = h->shard_world;
+  MpOutDst dst;
+  dst.out = nullptr; dst.ld = 0; dst.scatter_vol = nullptr;
+  for (int p = 0; p < h->shard_world; ++p) dst.peer[p] = h->peer_vals[h->vsel][p];
+  dst.n_peers = h->shard_world;
+  dst.peer_off = 0;
+  int rc = mp_query_dispatch(mlp, feat, src, cal, dst, mode, st);
+  if (rc != MP_OK) return rc;
+  XBarrier b;
+  for (int p = 0; p < MP_MAX_PEERS; ++p) b.peer[p] = p < h->shard_world ? h->peer_flags[p] : nullptr;
+  b.mine = h->flags;
+  b.rank = h->shard_rank;
+  b.world = h->shard_world;
+  b.epoch = ++h->epoch;
+  xgpu_barrier_kernel<<<1, 32, 0, st>>>(b);
+  MP_CUDA(cudaGetLastError());
+  *vals_out = h->vals2[h->vsel];
+  h->vsel ^= 1;
   return MP_OK;
 }
 
@@ -373,10 +474,17 @@ static int run_fused_levels(mp_octree* h, mp_mlp_t* mlp, mp_feat_t* feat, const 
     src.kind = MP_SRC_GRID;
     mp_fill_grid_geom(src, r0, (h->R - 1) / (r0 - 1), h->R, h->bmin, h->bmax);
     src.n = n;
-    MpOutDst dst;
-    dst.out = h->vol[h->cur]; dst.ld = n; dst.scatter_vol = nullptr;
-    rc = mp_query_dispatch(mlp, feat, src, cal, dst, mode, st);
-    if (rc != MP_OK) return rc;
+    if (h->shard_world > 1) {
+      const float* vals = nullptr;
+      rc = sharded_query(h, mlp, feat, src, cal, mode, st, &vals);
+      if (rc != MP_OK) return rc;
+      MP_CUDA(cudaMemcpyAsync(h->vol[h->cur], vals, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+      MpOutDst dst;
+      dst.out = h->vol[h->cur]; dst.ld = n; dst.scatter_vol = nullptr;
+      rc = mp_query_dispatch(mlp, feat, src, cal, dst, mode, st);
+      if (rc != MP_OK) return rc;
+    }
     set_u8_kernel<<<grid_for(n), 256, 0, st>>>(h->known[h->cur], n, 1);
     any_gt_kernel<<<grid_for(n), 256, 0, st>>>(h->vol[h->cur], n, h->balance, h->nonempty);
     const long long n0 = n;
@@ -401,17 +509,24 @@ static int run_fused_levels(mp_octree* h, mp_mlp_t* mlp, mp_feat_t* feat, const 
         src.count_dev = nullptr;
         MP_CUDA(cudaMemcpyAsync(h->stats + level, &k, sizeof(long long), cudaMemcpyHostToDevice, st));
       }
-      MpOutDst dst;
-      dst.out = nullptr; dst.ld = 0; dst.scatter_vol = h->vol[h->cur];
-      if (lossless) {
-        // keep the interpolated values, evaluate into vals, then scatter+conflict-detect
-        dst.out = h->vals; dst.ld = h->cap; dst.scatter_vol = nullptr;
+      const float* vals = h->vals;
+      const bool via_vals = lossless || h->shard_world > 1;
+      if (h->shard_world > 1) {
+        rc = sharded_query(h, mlp, feat, src, cal, mode, st, &vals);
+        if (rc != MP_OK) return rc;
+      } else {
+        MpOutDst dst;
+        dst.out = nullptr; dst.ld = 0; dst.scatter_vol = h->vol[h->cur];
+        if (lossless) {
+          // keep the interpolated values, evaluate into vals, then scatter+conflict-detect
+          dst.out = h->vals; dst.ld = h->cap; dst.scatter_vol = nullptr;
+        }
+        rc = mp_query_dispatch(mlp, feat, src, cal, dst, mode, st);
+        if (rc != MP_OK) return rc;
       }
-      rc = mp_query_dispatch(mlp, feat, src, cal, dst, mode, st);
-      if (rc != MP_OK) return rc;
       scatter_kernel<<<grid_for(h->cap > 1 << 20 ? 1 << 20 : h->cap), 256, 0, st>>>(
-          h->idx, src.count_dev, src.n, lossless ? h->vals : h->vol[h->cur], h->vol[h->cur],
-          h->use_topk ? nullptr : h->known[h->cur], lossless ? h->conflict : nullptr, h->balance, lossless);
+          h->idx, src.count_dev, src.n, via_vals ? vals : h->vol[h->cur], h->vol[h->cur],
+          h->use_topk ? nullptr : h->known[h->cur], lossless ? h->conflict : nullptr, h->balance, via_vals);
       MP_CUDA(cudaGetLastError());
       if (!lossless) break;
       rc = build_conflict_list(h, level, st);

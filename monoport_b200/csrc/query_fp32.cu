@@ -134,10 +134,13 @@ query_fp32_kernel(Fp32Params prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     const long long c = *src.count_dev;
     n = c < n ? c : n;
   }
-  const long long n_tiles = (n + P - 1) / P;
+  long long win0, win1;
+  mp_shard_window(src, n, win0, win1);
+  n = win1;                                          // points >= n are padding; the first evaluated one is win0
+  const long long n_tiles = (win1 - win0 + P - 1) / P;
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long p0 = tile * P;
+    const long long p0 = win0 + tile * P;
     // ---- 1. projection, mask, taps ------------------------------------------------------------
     __shared__ int sOff[4][P];
     __shared__ float sWgt[4][P];
@@ -221,6 +224,8 @@ query_fp32_kernel(Fp32Params prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
             v = sMeta[p] * v;                                                              // MonoPortNet.py:89
             if (dst.out) dst.out[(long long)r * dst.ld + i] = v;
             if (dst.scatter_vol && r == 0) dst.scatter_vol[__ldg(src.nodes + i)] = v;
+            if (r == 0)
+              for (int pp = 0; pp < dst.n_peers; ++pp) dst.peer[pp][dst.peer_off + i] = v;      // peer-memory stores (NVLink)
           }
         }
       }
@@ -250,10 +255,6 @@ int launch(const Fp32Params& prm, const MpPointSrc& src, const MpCalib& cal, con
 int mp_launch_query_fp32(const mp_mlp* mlp, const mp_feat* feat, const MpPointSrc& src, const MpCalib& cal,
                          const MpOutDst& dst, cudaStream_t st, int guard) {
   if (src.n <= 0) return MP_OK;
-  if (dst.n_peers > 0) {
-    mp_set_error("peer stores (fused slab exchange) are implemented by the tensor-core program only");
-    return MP_E_UNSUPPORTED;
-  }
   Fp32Params prm;
   memset(&prm, 0, sizeof(prm));
   prm.n_layers = mlp->n_layers;

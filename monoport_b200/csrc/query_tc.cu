@@ -262,7 +262,10 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     const long long c = *src.count_dev;
     n = c < n ? c : n;
   }
-  const long long n_tiles = (n + kTile - 1) / kTile;
+  long long win0, win1;
+  mp_shard_window(src, n, win0, win1);
+  n = win1;                                          // points >= n are padding; tile 0 starts at point win0
+  const long long n_tiles = (win1 - win0 + kTile - 1) / kTile;
   const long long n_groups = n_tiles;
   const long long g0 = blockIdx.x, gstep = gridDim.x;
 
@@ -475,7 +478,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     uint32_t c_xfree = 0;
     for (long long g = g0; g < n_groups; g += gstep) {
       const long long tile = g;
-      const long long p0 = tile * kTile;
+      const long long p0 = win0 + tile * kTile;
       const bool tr = blockIdx.x == 0 && sw == 0 && lane == 0 && (g - g0) / gstep == kTraceTile;
       TRACE(tr, 96);
       if (g != g0) wait_bar(bars, B_XFREE, c_xfree);
@@ -518,7 +521,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     uint32_t t_off[4][2], t_wgt[4][2], t_z[4];
     int gtr = -1;                              // trace slot base for the chunk being generated (-1: off)
     auto compute_taps = [&](long long g) {
-      const PointTaps pt = point_taps(src, cal, prm.H, prm.W, g * kTile + wk * 16 + l16, n);
+      const PointTaps pt = point_taps(src, cal, prm.H, prm.W, win0 + g * kTile + wk * 16 + l16, n);
       const uint32_t o01 = (uint32_t)pt.off[0] | ((uint32_t)pt.off[1] << 16), o23 = (uint32_t)pt.off[2] | ((uint32_t)pt.off[3] << 16);
       const uint32_t w01 = tc::pack_half2(pt.wgt[0], pt.wgt[1]), w23 = tc::pack_half2(pt.wgt[2], pt.wgt[3]);
       const uint32_t zz = tc::pack_half2(pt.zf, pt.zf);
@@ -632,7 +635,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       for (long long g = g0 - gstep; g < n_groups; g += gstep) {
         const bool real = g >= g0;
         const bool has_next = g + gstep < n_groups;
-        const long long p0 = g * kTile;
+        const long long p0 = win0 + g * kTile;
         const bool tr = blockIdx.x == 0 && real && (wk & 3) == 0 && lane == 0 && (g - g0) / gstep == kTraceTile;
         const int tb = 32 + wg * 32;
 #pragma unroll 1

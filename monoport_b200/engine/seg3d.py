@@ -53,6 +53,8 @@ class _Seg3dBase(nn.Module):
         self.register_buffer("b_min", torch.from_numpy(_as3(b_min)).view(1, 1, 3))
         self.register_buffer("b_max", torch.from_numpy(_as3(b_max)).view(1, 1, 3))
         self._handles = {}
+        self._mapped = []
+        self._sharded = None
         self.last_stats = None
 
     # one engine workspace per (device, calling thread)
@@ -73,10 +75,57 @@ class _Seg3dBase(nn.Module):
 
     def __del__(self):
         try:
+            self.unshard()
             for h in self._handles.values():
                 _lib.load().mp_octree_destroy(h)
         except Exception:
             pass
+
+    # ---- multi-GPU list sharding ------------------------------------------------------------
+    def shard(self, rank, world_size, group=None):
+        """Collective: split the MLP evaluations of every level's node list over the ranks of `group` (one process per
+        GPU of one node).  Every rank keeps the whole pyramid (the volume passes are replicated: identical inputs give
+        identical node lists, the lossless conflict loop included), evaluates its window of each list, and the fused
+        kernel stores the values into all ranks' value lists over NVLink peer memory.  Afterwards every rank calls the
+        engine with the same features / calib and receives the full volume, bit-identical to the single-GPU volume.
+        Applies to the calling thread's workspace and to the fused drive mode (`make_query_func(net)`)."""
+        import torch.distributed as dist
+        lib = _lib.load()
+        device = self.b_min.device
+        if device.type != "cuda":
+            raise RuntimeError("call .to('cuda:N') before shard()")
+        self.unshard()
+        h = self._handle(device)
+        if world_size == 1:
+            return self
+        with _lib.device_guard(device):
+            blob = ctypes.create_string_buffer(192)
+            _lib.check(lib.mp_octree_shard_export(h, blob), "mp_octree_shard_export")
+            blobs = [None] * world_size
+            dist.all_gather_object(blobs, blob.raw, group=group)
+            arrs = [(ctypes.c_void_p * world_size)() for _ in range(3)]
+            for r in range(world_size):
+                if r == rank:
+                    continue
+                for k in range(3):
+                    p = ctypes.c_void_p()
+                    _lib.check(lib.mp_ipc_open(blobs[r][64 * k:64 * (k + 1)], ctypes.byref(p)), "mp_ipc_open")
+                    self._mapped.append(p)
+                    arrs[k][r] = p.value
+            _lib.check(lib.mp_octree_shard_set(h, int(rank), int(world_size), arrs[0], arrs[1], arrs[2]), "mp_octree_shard_set")
+        self._sharded = (int(rank), int(world_size))
+        if group is not None or dist.is_initialized():
+            dist.barrier(group=group)        # nobody starts storing into a peer before every mapping exists
+        return self
+
+    def unshard(self):
+        for p in getattr(self, "_mapped", []):
+            _lib.load().mp_ipc_close(p)
+        self._mapped = []
+        if getattr(self, "_sharded", None):
+            for h in self._handles.values():
+                _lib.load().mp_octree_shard_set(h, 0, 1, None, None, None)
+        self._sharded = None
 
     @torch.no_grad()
     def forward(self, **kwargs):
@@ -114,6 +163,9 @@ class _Seg3dBase(nn.Module):
         return out if nonempty.value else None
 
     def _forward_generic(self, device, **kwargs):
+        if self._sharded:
+            raise RuntimeError("a sharded engine needs the fused drive mode: query_func = make_query_func(net), called "
+                               "with im_feat_list= and calib_tensor=")
         lib = _lib.load()
         h = self._handle(device)
         stats = [0] * len(self.resolutions)

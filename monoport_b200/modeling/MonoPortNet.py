@@ -177,6 +177,24 @@ class MonoPortNet(nn.Module):
                 self._mode(), _lib.stream_ptr(feat.device)), "mp_query_grid")
         return out
 
+    def query_grid_range(self, feat, calibs, resolution, b_min, b_max, lin0, n, out=None, fh=None):
+        """Occupancy of nodes [lin0, lin0+n) of the R^3 grid's z-major linear order (balanced multi-GPU sharding, see
+        shard.range_bounds); `out` = a float32 CUDA buffer of at least n elements."""
+        R, lin0, n = int(resolution), int(lin0), int(n)
+        if out is None:
+            out = torch.empty(n, dtype=torch.float32, device=feat.device)
+        if n == 0:
+            return out
+        with _lib.device_guard(feat.device):
+            if fh is None:
+                fh = self.feature_handle(feat)
+            proj = _lib.PROJ_PERSPECTIVE if self.projection is perspective else _lib.PROJ_ORTHOGONAL
+            _lib.check(_lib.load().mp_query_grid_range(
+                self.surface_classifier.handle(), fh.ptr, R, lin0, n, _lib.f3(b_min), _lib.f3(b_max),
+                _lib.calib12(calibs), proj, ctypes.c_float(self.normalizer.scale), ctypes.c_void_p(out.data_ptr()),
+                self._mode(), _lib.stream_ptr(feat.device)), "mp_query_grid_range")
+        return out
+
     # ---- training scaffolding kept for API parity ---------------------------------------------------------
     def get_loss(self, pred_stages, labels):
         fn = {"MSE": F.mse_loss, "L1": F.l1_loss}.get(self.opt.loss.IMF)

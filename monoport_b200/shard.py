@@ -1,6 +1,9 @@
 """z-slab sharding of the query grid over GPUs: one process per GPU (torch.distributed / NCCL),
-every rank evaluates its contiguous slab of z planes with the fused kernel, then ONE all-gather of the occupancy
-volume over NVLink so every rank holds the full [R,R,R] volume for marching cubes.  No other collective."""
+every rank evaluates a contiguous range of the z-major node order (a z slab whose boundaries need not fall on plane
+boundaries, so the ranks are balanced to within one 128-point tile) with the fused kernel, then ONE all-gather of the
+occupancy volume over NVLink -- in place, inside a persistent buffer -- so every rank holds the full [R,R,R] volume for
+marching cubes.  No other collective.  `PeerVolumes` / `query_grid_fused` replace even that by peer-memory stores from the
+kernel epilogue."""
 import torch
 
 
@@ -45,14 +48,54 @@ def gather_slabs(slab, R, rank, world_size, group=None, out=None):
     return out
 
 
-def query_grid_sharded(net, feat, calibs, R, b_min, b_max, rank, world_size, group=None, gather=True):
-    """Dense R^3 occupancy volume evaluated slab-wise across ranks; returns the full volume (gather=True) or the
-    local slab."""
-    z0, nz = slab_bounds(R, world_size)[rank]
-    slab = net.query_grid(feat, calibs, R, b_min, b_max, z0=z0, nz=nz)
+def range_bounds(R, world_size):
+    """Balanced sharding of the R^3 grid: rank r evaluates nodes [r*per, r*per + n_r) of the z-major linear node order,
+    per = ceil(R^3 / world) rounded up to a whole number of 128-point tiles.  The ranges are z slabs whose boundaries need
+    not fall on plane boundaries (257 = 8*32+1: with whole planes one rank carries 33 planes, the others 32).
+    Returns ([(lin0, n)] per rank, per)."""
+    total = int(R) ** 3
+    per = -(-total // int(world_size))
+    per = -(-per // 128) * 128
+    out = []
+    for r in range(int(world_size)):
+        lin0 = min(r * per, total)
+        out.append((lin0, max(0, min(per, total - lin0))))
+    return out, per
+
+
+class ShardedVolume:
+    """Persistent buffers of the sharded dense grid: ONE flat [world * per] float32 buffer whose first R^3 elements are the
+    volume.  `query()` lets the fused kernel write this rank's range straight into its segment of that buffer; `gather()` is
+    one in-place all_gather_into_tensor over it -- no padding copies, no reassembly copies, no allocation per frame.
+    `.volume` is the [R,R,R] view every rank reads after `gather()`."""
+
+    def __init__(self, R, rank, world_size, device, group=None):
+        self.R, self.rank, self.world, self.group = int(R), int(rank), int(world_size), group
+        self.bounds, self.per = range_bounds(R, world_size)
+        self.flat = torch.empty(self.world * self.per, dtype=torch.float32, device=device)
+        self.volume = self.flat[:self.R ** 3].view(self.R, self.R, self.R)
+        self.segment = self.flat[self.rank * self.per:(self.rank + 1) * self.per]
+
+    def query(self, net, feat, calibs, b_min, b_max, fh=None):
+        lin0, n = self.bounds[self.rank]
+        net.query_grid_range(feat, calibs, self.R, b_min, b_max, lin0, n, out=self.segment, fh=fh)
+        return self.segment
+
+    def gather(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.flat, self.segment, group=self.group)     # in place: segment r lives at r*per
+        return self.volume
+
+
+def query_grid_sharded(net, feat, calibs, R, b_min, b_max, rank, world_size, group=None, gather=True, buffers=None):
+    """Dense R^3 occupancy volume evaluated range-wise across ranks; returns the full volume (gather=True) or the local
+    segment.  Pass a `ShardedVolume` as `buffers` to reuse its memory from frame to frame."""
+    sv = buffers if buffers is not None else ShardedVolume(R, rank, world_size, feat.device, group)
+    seg = sv.query(net, feat, calibs, b_min, b_max)
     if not gather:
-        return slab
-    return gather_slabs(slab, R, rank, world_size, group)
+        return seg[:sv.bounds[rank][1]]
+    return sv.gather()
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -125,7 +168,7 @@ class PeerVolumes:
         self._own = []
 
 
-def query_grid_fused(net, feat, calibs, R, b_min, b_max, peers):
+def query_grid_fused(net, feat, calibs, R, b_min, b_max, peers, fh=None):
     """Dense R^3 occupancy volume, z-slab sharded over the ranks of `peers` (a PeerVolumes): ONE kernel per rank computes
     its slab and stores it into every rank's volume; returns this rank's full [R,R,R] volume (valid on the current
     stream after the trailing barrier).  Consumers must be ordered on the same stream (the two alternating volume sets
@@ -134,14 +177,15 @@ def query_grid_fused(net, feat, calibs, R, b_min, b_max, peers):
     from . import _lib
     from .modeling.geometry import perspective
     assert R == peers.R
-    z0, nz = slab_bounds(R, peers.world)[peers.rank]
+    lin0, n = range_bounds(R, peers.world)[0][peers.rank]          # balanced ranges of the linear node order
     ptrs, local = peers.next_set()
     with _lib.device_guard(feat.device):
-        fh = net.feature_handle(feat)
+        if fh is None:
+            fh = net.feature_handle(feat)
         proj = _lib.PROJ_PERSPECTIVE if net.projection is perspective else _lib.PROJ_ORTHOGONAL
-        _lib.check(_lib.load().mp_query_grid_peers(
-            net.surface_classifier.handle(), fh.ptr, int(R), int(z0), int(nz), _lib.f3(b_min), _lib.f3(b_max),
+        _lib.check(_lib.load().mp_query_grid_range_peers(
+            net.surface_classifier.handle(), fh.ptr, int(R), int(lin0), int(n), _lib.f3(b_min), _lib.f3(b_max),
             _lib.calib12(calibs), proj, ctypes.c_float(net.normalizer.scale), ptrs, peers.world, net._mode(),
-            _lib.stream_ptr(feat.device)), "mp_query_grid_peers")
+            _lib.stream_ptr(feat.device)), "mp_query_grid_range_peers")
     peers.barrier()
     return local

@@ -197,14 +197,24 @@ int main(int argc, char** argv) {
   dst.n_peers = n_peers;
   dst.peer_off = peer_off;
   if (program % 100 != 3 && program % 100 != 0) { fprintf(stderr, "unknown program %d (3 = the tensor-core program, 103 = with peer stores)\n", program); return 2; }
-  const int rc = mp_launch_query_tc(&mlp, &feat, src, cal, dst, nullptr, guard);
+  // EMU_SHARD_WORLD=W: the query is evaluated as W launches, launch r taking the r-th window of the point list (what W
+  // GPUs do with list sharding; here they share the output buffers, so together they must reproduce the unsharded result)
+  const int shard_world = getenv("EMU_SHARD_WORLD") ? atoi(getenv("EMU_SHARD_WORLD")) : 1;
+  int rc = MP_OK;
+  for (int r = 0; r < shard_world && rc == MP_OK; ++r) {
+    src.shard_rank = r;
+    src.shard_world = shard_world;
+    rc = mp_launch_query_tc(&mlp, &feat, src, cal, dst, nullptr, guard);
+  }
   if (getenv("EMU_TC_AMAX")) { float a; memcpy(&a, &amax_word, 4); fprintf(stderr, "amax %.9g\n", a); }
   if (rc != MP_OK) { fprintf(stderr, "mp_launch_query_tc: %s\n", g_err); return 3; }
   if (out[(size_t)res * n_out] != -4242.f) { fprintf(stderr, "wrote past the output\n"); return 3; }
   if (!scatter.empty()) out.assign(scatter.begin(), scatter.end());       // report the scattered volume
   for (int p = 0; p < n_peers; ++p)
     for (long long i = 0; i < (long long)peer[p].size(); ++i) {
-      const float want = (i >= peer_off && i < peer_off + n_out) ? out[i - peer_off] : -4242.f;
+      float want = -4242.f;
+      if (scatter.empty()) { if (i >= peer_off && i < peer_off + n_out) want = out[i - peer_off]; }
+      else if (i >= peer_off && i < peer_off + node_count) want = scatter[nodes[i - peer_off]];     // peers receive the value LIST
       if (memcmp(&peer[p][i], &want, 4) != 0) { fprintf(stderr, "peer volume %d differs at %lld\n", p, i); return 3; }
     }
   f = fopen(argv[2], "wb");

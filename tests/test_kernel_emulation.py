@@ -312,6 +312,26 @@ def test_tcgen05_kernels_node_list_source(emu_query_tc, tmp_path, program):
     assert bool((got[want == -4242.0] == -4242.0).all())
 
 
+@pytest.mark.parametrize("kind,world", [("nodes", 2), ("nodes", 3), ("grid", 2)])
+def test_tcgen05_list_sharding_is_bit_identical(emu_query_tc, tmp_path, kind, world):
+    """Multi-GPU list sharding of a query (octree levels, balanced dense ranges): `world` launches, launch r evaluating the
+    r-th 128-aligned window of the point list -- also through the peer stores -- reproduce the unsharded launch bit for
+    bit (243 nodes over 2 / 3 windows incl. an empty one; 5*13*13 grid nodes over 2)."""
+    from helpers import load_query_case
+    case = load_query_case("g_smallmap")
+    fin = str(tmp_path / "in.bin")
+    _write_tc_input(fin, case, 4)
+    args = ["nodes", "33", "9"] if kind == "nodes" else ["grid", "13", "3", "5"]
+    outs = []
+    for w in (1, world):
+        fout = str(tmp_path / ("w%d.f32" % w))
+        r = subprocess.run([emu_query_tc, fin, fout, "103", "2"] + args, capture_output=True, text=True, timeout=900,
+                           env=dict(os.environ, EMU_SHARD_WORLD=str(w)))
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.fromfile(fout, dtype=np.float32))
+    assert outs[0].size > 0 and np.array_equal(outs[0], outs[1])
+
+
 def test_tcgen05_colour_head_fused_surface_rendering(emu_query_tc, tmp_path):
     """mp_colorize_surface: visible-surface vertices (X, Y, R - Z) -> world (mat_color) -> netC -> pred*0.5+0.5 -> canvas, one
     launch, against the restatement of RTL/main.py:212-249 driven by the oracle's query (32 x 32 colour map)."""

@@ -36,6 +36,16 @@ def _worker(rank, world, port, R, q):
         slab = _field(R)[z0:z0 + nz].contiguous()          # what net.query_grid(z0=z0, nz=nz) would return
         full = gather_slabs(slab, R, rank, world)
         ok = torch.equal(full, _field(R))
+        # balanced ranges of the linear node order + ONE in-place all-gather inside the persistent buffer (ShardedVolume)
+        from monoport_b200.shard import ShardedVolume, range_bounds
+        bounds, per = range_bounds(R, world)
+        assert per % 128 == 0 and sum(n for _, n in bounds) == R ** 3 and all(b[0] == r * per or b[1] == 0 for r, b in enumerate(bounds))
+        sv = ShardedVolume(R, rank, world, "cpu")
+        for frame in range(2):                              # the buffers are reused from frame to frame
+            lin0, n = bounds[rank]
+            sv.segment[:n] = (_field(R) + frame).reshape(-1)[lin0:lin0 + n]     # what net.query_grid_range(...) would write
+            vol = sv.gather()
+            ok = ok and torch.equal(vol, _field(R) + frame) and vol.data_ptr() == sv.flat.data_ptr()
         q.put((rank, bool(ok), tuple(full.shape)))
     finally:
         dist.destroy_process_group()

@@ -18,17 +18,15 @@ def _gpus():
 
 @pytest.mark.parametrize("fused", [False, True])
 def test_sharded_volume_equals_single_gpu_volume(fused):
-    if fused and os.environ.get("MONOPORT_B200_TEST_FUSED", "0") != "1":
-        pytest.skip("fused slab exchange is opt-in until it has been validated on a multi-GPU box "
-                    "(MONOPORT_B200_TEST_FUSED=1)")
     n = _gpus()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     world = 2 if n < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
-           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "shard_check.py")] + (["--fused"] if fused else [])
+           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "shard_check.py")] + (["--fused", "--octree"] if fused else [])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "shard_check OK: identical volumes" in r.stdout
     if fused:
         assert "shard_check OK (fused slab exchange)" in r.stdout
+        assert "shard_check OK (list-sharded octree engines)" in r.stdout

@@ -46,4 +46,46 @@ if "--fused" in sys.argv:
         print("shard_check OK (fused slab exchange)")
     dist.barrier()
     peers.close()
+# list-sharded coarse-to-fine engines (mp_octree_shard_*): the volume every rank receives == the single-GPU engine's volume,
+# bit for bit, in the `faster` mode of RTL/main.py:195, in lossless mode (conflict loop) and for top-k
+if "--octree" in sys.argv:
+    import numpy as np, time
+    from monoport_b200.engine import Seg3dLossless, Seg3dTopk, make_query_func
+    b = np.array([[-1.0, -1.0, -1.0]], dtype=np.float32)
+    res = [17, 33, 65, 129]
+    dev = "cuda:%d" % local
+    oko = True
+    for name, make in (("faster", lambda: Seg3dLossless(make_query_func(net), b, -b, res, balance_value=0.5, faster=True)),
+                       ("lossless", lambda: Seg3dLossless(make_query_func(net), b, -b, res, balance_value=0.5, faster=False)),
+                       ("topk", lambda: Seg3dTopk(make_query_func(net), b, -b, res, num_points=[None, 3000, 9000, 30000]))):
+        single = make().to(dev)
+        ref = single(im_feat_list=[[feat.cuda()]], calib_tensor=cal)
+        sharded = make().to(dev).shard(rank, world)
+        for it in range(3):                       # several frames through the same mappings (alternating value lists)
+            f_it = (feat * (1.0 + 0.05 * it)).cuda()
+            got = sharded(im_feat_list=[[f_it]], calib_tensor=cal)
+            want = single(im_feat_list=[[f_it]], calib_tensor=cal)
+            same = (got is None and want is None) or bool(torch.equal(got, want))
+            oko &= same and list(sharded.last_stats) == list(single.last_stats)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for it in range(10):
+            sharded(im_feat_list=[[feat.cuda()]], calib_tensor=cal)
+        torch.cuda.synchronize()
+        ts = (time.perf_counter() - t0) / 10
+        t0 = time.perf_counter()
+        for it in range(10):
+            single(im_feat_list=[[feat.cuda()]], calib_tensor=cal)
+        torch.cuda.synchronize()
+        t1 = (time.perf_counter() - t0) / 10
+        print("rank %d/%d: octree %s sharded == single: %s ; %.0f us sharded vs %.0f us single ; evaluated %s"
+              % (rank, world, name, oko, ts * 1e6, t1 * 1e6, sharded.last_stats), flush=True)
+        dist.barrier()
+        sharded.unshard()
+        assert ref is not None
+    t = torch.tensor([int(oko)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        assert int(t.item()) == 1
+        print("shard_check OK (list-sharded octree engines)")
 dist.destroy_process_group()
