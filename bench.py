@@ -9,7 +9,9 @@ A "step" = one pass of the hot path over one synthetic frame: upload-free channe
 feature map + the fused sample+MLP kernel over the dense 257^3 node grid ("256^3", RTL/main.py:187), z-slab
 sharded over the ranks, + ONE all-gather of the occupancy volume (N>1).  `value` = whole-job Mpoints/s with inputs
 resident in HBM; `e2e` = the same through the C-ABI host-buffer entry point (feature map H2D + volume D2H inside the
-timed region).  `recon` reports BASELINE configs[1]: coarse-to-fine (Seg3dLossless, faster=True) recon frames/s.
+timed region; at N > 1 the all-gather too).  `recon` reports BASELINE configs[1..3] (coarse-to-fine recon frames/s, with the
+netC colour pass, and the image stream with the PyTorch encoder as CUDA-graph captured frame steps), `configs4_dense513`
+BASELINE configs[4].  At N > 1 the line also asserts that the gathered volume equals the single-GPU volume bit for bit.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -27,6 +29,9 @@ if ROOT not in sys.path:
 
 R_GRID = 257
 FLOP_PER_POINT = 2363906          # 2*(257*1024+1281*512+769*256+513*128+385*1)  
+# DRAM bytes of one query_tc3_kernel launch over the dense 257^3 grid, from an `ncu --set full` capture (not re-measured by a
+# bench run: profiling and timing never share a run).  Updated by hand from profiles/ when the kernel changes.
+TRAFFIC_NCU = {"bytes": 84.44e6, "source": "profiles/r01_final_ncu_tc_summary.txt: 45.55 MB read + 38.89 MB written"}
 B_MIN, B_MAX = (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0)
 
 
@@ -206,13 +211,23 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _person_hook(height):
+    """Stream workload: the encoder's last-stage map with channel 0 replaced by a synthetic body height map, so that the
+    frame (points evaluated, vertices) is the same in every run -- the random-init encoder alone gives a noise surface."""
+    def hook(f):
+        f = f.clone()
+        f[:, 0] = height
+        return f
+    return hook
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     from monoport_b200 import _lib
     from monoport_b200.modeling import PIFuNetG
-    from monoport_b200.shard import slab_bounds, gather_slabs, PeerVolumes, query_grid_fused
+    from monoport_b200.shard import ShardedVolume, PeerVolumes, query_grid_fused, range_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -227,6 +242,7 @@ def run_ours(args):
 
     R = args.res
     chans, Ws, bs, feats_cpu = synthetic(n_feat=4)
+    torch.manual_seed(0)                       # the encoder's random init (stream workload) is the same in every run
     net = PIFuNetG()
     net.surface_classifier.load_state_dict(
         {**{"filters.%d.weight" % l: W[:, :, None] for l, W in enumerate(Ws)},
@@ -240,11 +256,11 @@ def run_ours(args):
     cal_cpu = scene_calib()
     cal = cal_cpu.to(dev)
     feats = [f.to(dev) for f in feats_cpu]
-    z0, nz = slab_bounds(R, world)[rank]
     n_pts_total = R ** 3
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
-    slab = torch.empty((nz, R, R), dtype=torch.float32, device=dev)
-    full = torch.empty((R, R, R), dtype=torch.float32, device=dev)
+    # balanced ranges of the z-major node order (z slabs whose boundaries need not fall on planes), ONE in-place all-gather
+    sv = ShardedVolume(R, rank, world, dev)
+    lin0, my_pts = sv.bounds[rank]
 
     fused = bool(args.fused_gather and world > 1)
     peers = PeerVolumes(R, rank, world, dev) if fused else None
@@ -254,17 +270,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i):
+    def step(i, fh=None):
         f = feats[i % len(feats)]
         if fused:
-            query_grid_fused(net, f, cal_cpu, R, B_MIN, B_MAX, peers)
-            return
-        net.query_grid(f, cal_cpu, R, B_MIN, B_MAX, z0=z0, nz=nz, out=slab)
-        if world > 1:
-            gather_slabs(slab, R, rank, world, out=full)
+            return query_grid_fused(net, f, cal_cpu, R, B_MIN, B_MAX, peers, fh=fh)
+        sv.query(net, f, cal_cpu, B_MIN, B_MAX, fh=fh)
+        return None
 
     for i in range(args.warmup):
         step(i)
+        if not fused:
+            sv.gather()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -272,20 +288,17 @@ def run_ours(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    vol = None
     for i in range(args.steps):
         flush.fill_(float(i))                      # L2 flush between timed iterations (not timed)
         f = feats[i % len(feats)]
         ev[i][0].record()
         fh = net.feature_handle(f)                 # channel-last repack kernel (part of the step)
         kev[i][0].record()
-        if fused:
-            query_grid_fused(net, f, cal_cpu, R, B_MIN, B_MAX, peers)      # kernel with peer stores + barrier
-            kev[i][1].record()
-        else:
-            net.query_grid(f, cal_cpu, R, B_MIN, B_MAX, z0=z0, nz=nz, out=slab, fh=fh)
-            kev[i][1].record()
-            if world > 1:
-                gather_slabs(slab, R, rank, world, out=full)
+        vol = step(i, fh)                          # fused: kernel with peer stores + barrier
+        kev[i][1].record()
+        if not fused:
+            vol = sv.gather()                      # N > 1: one in-place all-gather inside the persistent buffer
         ev[i][1].record()
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -297,10 +310,33 @@ def run_ours(args):
     t_ms, k_ms = tt.tolist()
     value = n_pts_total * args.steps / (t_ms * 1e-3) / 1e6
 
-    # ---- e2e through the C-ABI with HOST buffers (pinned), rank-local slab ---------------------------------
+    # ---- what was timed is right: the volume every rank holds == the volume ONE GPU computes, bit for bit; and the
+    #      tensor-core values agree with the exact fp32 kernel on a sample of the same grid -------------------------
+    f_last = feats[(args.steps - 1) % len(feats)]
+    single = net.query_grid(f_last, cal_cpu, R, B_MIN, B_MAX) if world > 1 else vol
+    same = torch.tensor([int(torch.equal(vol, single))], device=dev)
+    if world > 1:
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    volume_ok = bool(same.item())
+    checksum = float(vol.double().sum().item())
+    g = torch.Generator().manual_seed(17)
+    lin = torch.randint(0, R ** 3, (16384,), generator=g)
+    parity = None
+    if mode_used == "tc":
+        R_f = float(R)
+        xyz = torch.stack([(lin % R).float(), ((lin // R) % R).float(), (lin // (R * R)).float()], 0)
+        pts = (((xyz / R_f) + 1.0 / (2.0 * R_f)) * 2.0 - 1.0)[None].to(dev)          # node centres, [1,3,N]
+        net.precision = "fp32"
+        exact = net.query([[f_last]], pts, calibs=cal_cpu)[0]
+        net.precision = args.mode
+        parity = float((vol.reshape(-1)[lin.to(dev)] - exact[0, 0]).abs().max().item())
+    del single
+
+    # ---- e2e through the C-ABI with HOST buffers (pinned): feature map H2D, this rank's range of the volume D2H, and --
+    #      at N > 1 -- the all-gather in between (the job's result is the assembled volume) ---------------------------
     lib = _lib.load()
     feat_pinned = [f.pin_memory() for f in feats_cpu]
-    out_host = torch.empty((nz, R, R), dtype=torch.float32).pin_memory()
+    out_host = torch.empty(max(my_pts, 1), dtype=torch.float32).pin_memory()
     fh = net.feature_handle(feats[0])
     cal12 = _lib.calib12(cal_cpu)
     st = _lib.stream_ptr(dev)
@@ -308,9 +344,18 @@ def run_ours(args):
 
     def e2e_step(i):
         f = feat_pinned[i % len(feat_pinned)]
-        _lib.check(lib.mp_query_grid_host(net.surface_classifier.handle(), fh.ptr, ctypes.c_void_p(f.data_ptr()), R, z0, nz,
-                                          _lib.f3(B_MIN), _lib.f3(B_MAX), cal12, 0, ctypes.c_float(net.normalizer.scale),
-                                          ctypes.c_void_p(out_host.data_ptr()), mode_code, st))
+        if world == 1:
+            _lib.check(lib.mp_query_grid_host(net.surface_classifier.handle(), fh.ptr, ctypes.c_void_p(f.data_ptr()), R, 0, R,
+                                              _lib.f3(B_MIN), _lib.f3(B_MAX), cal12, 0, ctypes.c_float(net.normalizer.scale),
+                                              ctypes.c_void_p(out_host.data_ptr()), mode_code, st))
+            return
+        _lib.check(lib.mp_feat_upload(fh.ptr, ctypes.c_void_p(f.data_ptr()), 0, st))                      # H2D + repack
+        _lib.check(lib.mp_query_grid_range(net.surface_classifier.handle(), fh.ptr, R, lin0, my_pts, _lib.f3(B_MIN), _lib.f3(B_MAX),
+                                           cal12, 0, ctypes.c_float(net.normalizer.scale), ctypes.c_void_p(sv.segment.data_ptr()),
+                                           mode_code, st))
+        sv.gather()
+        out_host[:my_pts].copy_(sv.segment[:my_pts], non_blocking=True)                                     # D2H
+        torch.cuda.current_stream().synchronize()
     e2e_steps = max(3, min(args.steps, 10))
     e2e_step(0)
     barrier()
@@ -325,86 +370,32 @@ def run_ours(args):
     e2e_value = n_pts_total * e2e_steps / te.item() / 1e6
     fh.key = None
 
-    # ---- configs[1]: coarse-to-fine recon frames/s (rank 0, N=1 only) ---------------------------------------
+    # ---- configs[1..3]: coarse-to-fine recon frames/s -------------------------------------------------------------
     recon = None
-    if rank == 0 and world == 1 and not args.no_recon and R == R_GRID:
-        from monoport_b200.engine import Seg3dLossless, make_query_func
-        from monoport_b200.recon import forward_vertices, marching_cubes
-        b = np.array([B_MIN], dtype=np.float32)
-        eng = Seg3dLossless(make_query_func(net), b, -b, [17, 33, 65, 129, 257], balance_value=0.5, faster=True).to(dev)
-        for i in range(3):                                  # warm-up: engine, surface kernel, marching cubes
-            sdf = eng(im_feat_list=[[feats[i % 4]]], calib_tensor=cal)
-            X, Y, Z, nrm = forward_vertices(sdf, "front")
-            v, fcs = marching_cubes(sdf[0, 0])
-        torch.cuda.synchronize()
-        nfr = 20
-        t0 = time.perf_counter()
-        for i in range(nfr):
-            sdf = eng(im_feat_list=[[feats[i % 4]]], calib_tensor=cal)
-            X, Y, Z, nrm = forward_vertices(sdf, "front")
-        torch.cuda.synchronize()
-        fps_fv = nfr / (time.perf_counter() - t0)
-        t0 = time.perf_counter()
-        for i in range(nfr):
-            sdf = eng(im_feat_list=[[feats[i % 4]]], calib_tensor=cal)
-            v, fcs = marching_cubes(sdf[0, 0])
-        torch.cuda.synchronize()
-        fps_mc = nfr / (time.perf_counter() - t0)
-        recon_stats = list(eng.last_stats)
-        # configs[2]: geometry + colour -- netC (513-wide head, fp32 fused kernel) queried at the visible vertices
-        from monoport_b200.modeling import PIFuNetC
-        from monoport_b200.recon import colorization
-        netC = PIFuNetC()
-        netC.surface_classifier.to(dev)
-        netC.eval()
-        gC = torch.Generator().manual_seed(11)
-        featC = [[(torch.randn(1, 512, 128, 128, generator=gC) * 0.5).to(dev)]]
-        img = colorization(netC, featC, X, Y, Z, cal)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(nfr):
-            sdf = eng(im_feat_list=[[feats[i % 4]]], calib_tensor=cal)
-            X, Y, Z, nrm = forward_vertices(sdf, "front")
-            img = colorization(netC, featC, X, Y, Z, cal)
-        torch.cuda.synchronize()
-        fps_color = nfr / (time.perf_counter() - t0)
-        # configs[3]-style image stream on one GPU: synthetic 512x512 frames -> HG encoder (PyTorch, fp32) -> coarse-to-fine
-        # recon -> visible surface, frames overlapped by FramePipeline (1 lane = sequential, 2 lanes = overlapped)
-        from monoport_b200.pipeline import FramePipeline
-        net.image_filter.to(dev)
-        gI = torch.Generator().manual_seed(5)
-        frames = [(torch.rand(1, 3, 512, 512, generator=gI) * 2 - 1).to(dev) for _ in range(4)]
-
-        def stage_encode(img):
-            return net.filter(img)
-
-        def stage_recon(fs):
-            return eng(im_feat_list=fs, calib_tensor=cal)
-
-        def stage_surface(sdf_):
-            return forward_vertices(sdf_, "front")
-
-        stream_fps = {}
-        with torch.no_grad():
-            for lanes in (1, 2):
-                pipe = FramePipeline([stage_encode, stage_recon, stage_surface], dev, n_lanes=lanes)
-                list(pipe.run(frames[i % 4] for i in range(4)))               # warm-up (cudnn autotune, handles)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                nst = 24
-                outs = list(pipe.run(frames[i % 4] for i in range(nst)))
-                torch.cuda.synchronize()
-                stream_fps[lanes] = nst / (time.perf_counter() - t0)
-                pipe.close()
-        recon = {"workload": "configs[1]: netG 256^3 Seg3dLossless(faster=True) from resident features, per frame",
-                 "frames_per_s_stream_with_pytorch_encoder": {
-                     "1_lane": stream_fps[1], "2_lanes": stream_fps[2],
-                     "note": "512x512 frame -> HGFilter (PyTorch fp32, random init => noise field, %d points/frame) -> recon -> "
-                             "forward_vertices; lanes = overlapped frames (FramePipeline)" % int(sum(eng.last_stats))},
-                 "frames_per_s_geometry_plus_netC_colour": fps_color,
-                 "frames_per_s_with_forward_vertices": fps_fv, "frames_per_s_with_marching_cubes": fps_mc,
-                 "points_evaluated_per_frame": int(sum(recon_stats)), "per_level": recon_stats,
-                 "visible_vertices": int(X.numel()), "mesh_vertices": int(v.shape[0]), "mesh_faces": int(fcs.shape[0])}
+    if not args.no_recon and R == R_GRID:
+        recon = bench_recon(args, net, feats, cal, cal_cpu, dev, rank, world, barrier)
+    # ---- configs[4]: dense 513^3 ("512^3") through the same sharded step, a few steps ------------------------------
+    c4 = None
+    if not args.no_recon and R == R_GRID:
+        R5 = 513
+        sv5 = ShardedVolume(R5, rank, world, dev)
+        for i in range(1):
+            sv5.query(net, feats[0], cal_cpu, B_MIN, B_MAX); sv5.gather()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n5 = 3
+        e0.record()
+        for i in range(n5):
+            sv5.query(net, feats[i % 4], cal_cpu, B_MIN, B_MAX); v5 = sv5.gather()
+        e1.record()
+        barrier()
+        t5 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        c4 = {"workload": "configs[4]: netG dense 513^3 (135 005 697 points), range-sharded over %d GPU(s) + 1 all-gather (540 MB volume)" % world,
+              "ms_per_volume": t5.item() / n5, "mpoints_per_s": R5 ** 3 * n5 / (t5.item() * 1e-3) / 1e6,
+              "occupied_fraction": float((v5 > 0.5).float().mean().item())}
+        del sv5, v5
 
     # ---- CPU baseline (reported, not the target): the oracle port on a bounded sample, rank 0, N=1 only ----
     cpu = None
@@ -415,18 +406,20 @@ def run_ours(args):
         cores = best_threads(lambda: spec.query_ref(feats_cpu[0], pts[:, :16384], cal_cpu, Ws, bs, spec.LAST_SIGMOID))
         t0 = time.perf_counter()
         reps = 0
+        ref = None
         while time.perf_counter() - t0 < 10.0 or reps < 1:
-            spec.query_ref(feats_cpu[0], pts, cal_cpu, Ws, bs, spec.LAST_SIGMOID)
+            ref = spec.query_ref(feats_cpu[0], pts, cal_cpu, Ws, bs, spec.LAST_SIGMOID)
             reps += 1
         dt = time.perf_counter() - t0
+        ours64 = net.query([[feats[0]]], pts[None].to(dev), calibs=cal_cpu)[0][0].cpu()
         cpu = {"value": S ** 3 * reps / dt / 1e6, "unit": "Mpoints/s", "cores": cores, "kind": "port",
-               "sample": "dense 64^3 = 262144 points x %d reps (%.1f s), torch CPU fp32 oracle port of MonoPortNet.query" % (reps, dt)}
+               "sample": "dense 64^3 = 262144 points x %d reps (%.1f s), torch CPU fp32 oracle port of MonoPortNet.query" % (reps, dt),
+               "parity_max_abs_vs_oracle": float((ours64 - ref).abs().max().item())}
 
-    my_pts = nz * R * R
     if rank == 0:
         pk = peaks()
-        # nchw_to_nhwc repack + (tensor-core program v3, every query size: per-texel layer-0 GEMM g0_tc_kernel) + fused query kernel
-        launches_per_step = 3 if mode_used == "tc" else 2
+        # nchw_to_nhwc repack + per-texel layer-0 GEMM (g0_tc_kernel) + fused query kernel + the range guard's (empty) exact-kernel launch
+        launches_per_step = 4 if mode_used == "tc" else 2
         k_avg_s = k_ms * 1e-3 / args.steps
         achieved_tf = FLOP_PER_POINT * my_pts / k_avg_s / 1e12
         peak_tf = pk["tf_sustained"]
@@ -435,21 +428,22 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f16" if mode_used == "tc" else "f32", "data": "synthetic",
             "config": {"workload": "netG dense %d^3 grid query (%d points/step), [1,256,128,128] features, scene calib "
-                                   "yaw20/pitch33, z-slab sharded over %d GPU(s) + %s" % (R, n_pts_total, world, "peer-memory stores from the kernel epilogue + 1 barrier" if fused else "1 all-gather"),
+                                   "yaw20/pitch33, balanced z-major ranges over %d GPU(s) + %s" % (R, n_pts_total, world, "peer-memory stores from the kernel epilogue + 1 barrier" if fused else "1 in-place all-gather"),
                        "kernel_mode": mode_used, "l2_flush_between_steps": True, "grid": R,
                        "accumulate": "fp32", "last_layer": "fp32"},
+            "volume_matches_single_gpu": volume_ok, "volume_checksum": checksum,
+            "parity_max_abs": parity, "parity_note": "tensor-core volume vs the exact fp32 kernel on 16384 random nodes of this grid (bar 1e-4); cpu_baseline.parity_max_abs_vs_oracle: vs the oracle on the 64^3 sample",
             "e2e": {"value": e2e_value, "unit": "Mpoints/s", "h2d_bytes_per_step": 256 * 128 * 128 * 4 + 48,
-                    "d2h_bytes_per_step": nz * R * R * 4, "steps": e2e_steps,
-                    "api": "mp_query_grid_host (pinned host feature map in, host occupancy slab out)"},
+                    "d2h_bytes_per_step": my_pts * 4, "steps": e2e_steps,
+                    "api": "mp_query_grid_host (pinned host feature map in, host occupancy volume out)" if world == 1 else
+                           "mp_feat_upload(host) + mp_query_grid_range + all-gather + D2H of this rank's range"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from profiles/r01_final_ncu_tc_summary.txt
-                         # (ncu --set full, 257^3, N=1, final code of round 1): 45.55 MB + 38.89 MB per launch
-                         "traffic": (84.44e6 if (launches_per_step == 3 and world == 1 and R == R_GRID) else None),
-                         "traffic_unit": "bytes/launch (ncu capture r01, not re-measured in this run)",
-                         "kernel": ("query_tc3_kernel (+ g0_tc_kernel, the per-frame per-texel layer-0 GEMM, 26 us)" if launches_per_step == 3
-                                    else "query_%s_kernel" % mode_used),
+                         "traffic": (TRAFFIC_NCU["bytes"] if (mode_used == "tc" and world == 1 and R == R_GRID) else None),
+                         "traffic_unit": "bytes/launch, dram__bytes_read.sum + dram__bytes_write.sum of query_tc3_kernel (%s)" % TRAFFIC_NCU["source"],
+                         "kernel": ("query_tc3_kernel (+ g0_tc_kernel, the per-frame per-texel layer-0 GEMM, 26 us)" if mode_used == "tc"
+                                    else "query_fp32_kernel"),
                          "kernel_ms": 1e3 * k_avg_s, "peak_source": pk["source"] + " bf16 sustained (cuBLAS loop)",
                          "frac_of_burst": achieved_tf / pk["tf_burst"],
                          "algorithmic_flop_per_point": FLOP_PER_POINT},
@@ -459,12 +453,132 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if recon:
             line["recon"] = recon
+        if c4:
+            line["configs4_dense513"] = c4
         print(json.dumps(line))
     if peers is not None:
         barrier()
         peers.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_recon(args, net, feats, cal, cal_cpu, dev, rank, world, barrier):
+    """configs[1] (coarse-to-fine recon, one image), configs[2] (+ netC colour), configs[3] (image stream) -- per rank at N = 1,
+    and at N > 1: frame-parallel replicas (every rank reconstructs its own frames) and the list-sharded engine."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from monoport_b200.engine import Seg3dLossless, make_query_func
+    from monoport_b200.recon import forward_vertices, marching_cubes, colorization
+    from monoport_b200.pipeline import FrameGraph, FrameGraphRing
+    b = np.array([B_MIN], dtype=np.float32)
+    res = [17, 33, 65, 129, 257]
+    eng = Seg3dLossless(make_query_func(net), b, -b, res, balance_value=0.5, faster=True).to(dev)
+    out = {"workload": "netG 256^3 Seg3dLossless(faster=True) on a body-like height field, per frame"}
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(n):
+            fn(i)
+        torch.cuda.synchronize()
+        return n / (time.perf_counter() - t0)
+
+    nfr = 20
+    if world == 1:
+        for i in range(3):                                  # warm-up: engine, surface kernel, marching cubes
+            sdf = eng(im_feat_list=[[feats[i % 4]]], calib_tensor=cal_cpu)
+            X, Y, Z, nrm = forward_vertices(sdf, "front")
+            v, fcs = marching_cubes(sdf[0, 0])
+        state = {}
+
+        def fv(i):
+            state["sdf"] = eng(im_feat_list=[[feats[i % 4]]], calib_tensor=cal_cpu)
+            state["fv"] = forward_vertices(state["sdf"], "front")
+
+        def mc(i):
+            sdf_ = eng(im_feat_list=[[feats[i % 4]]], calib_tensor=cal_cpu)
+            state["mesh"] = marching_cubes(sdf_[0, 0])
+        out["frames_per_s_with_forward_vertices"] = timed(fv, nfr)
+        out["frames_per_s_with_marching_cubes"] = timed(mc, nfr)
+        recon_stats = list(eng.last_stats)
+        X, Y, Z, nrm = state["fv"]
+        v, fcs = state["mesh"]
+        # the same frame as ONE CUDA-graph launch (pipeline.FrameGraph), one and two lanes
+        for lanes in (1, 2):
+            ring = FrameGraphRing(lambda: FrameGraph(net, eng, cal_cpu, "front", with_encoder=False), n_lanes=lanes)
+            list(ring.run(feats[i % 4] for i in range(4)))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_g = 60
+            for r_ in ring.run(feats[i % 4] for i in range(n_g)):
+                pass
+            torch.cuda.synchronize()
+            out["frames_per_s_frame_graph_%d_lane%s" % (lanes, "s" if lanes > 1 else "")] = n_g / (time.perf_counter() - t0)
+            ring.close()
+        # configs[2]: geometry + colour -- netC queried at the visible vertices, fused direct rendering (tensor-core colour program)
+        from monoport_b200.modeling import PIFuNetC
+        netC = PIFuNetC()
+        netC.surface_classifier.to(dev)
+        netC.eval()
+        gC = torch.Generator().manual_seed(11)
+        featC = [[(torch.randn(1, 512, 128, 128, generator=gC) * 0.5).to(dev)]]
+        colorization(netC, featC, X, Y, Z, cal)
+
+        def col(i):
+            sdf_ = eng(im_feat_list=[[feats[i % 4]]], calib_tensor=cal_cpu)
+            X_, Y_, Z_, _n = forward_vertices(sdf_, "front")
+            state["img"] = colorization(netC, featC, X_, Y_, Z_, cal)
+        out["frames_per_s_geometry_plus_netC_colour"] = timed(col, nfr)
+        out.update({"points_evaluated_per_frame": int(sum(recon_stats)), "per_level": recon_stats,
+                    "visible_vertices": int(X.numel()), "mesh_vertices": int(v.shape[0]), "mesh_faces": int(fcs.shape[0])})
+    # configs[3]: image stream -- synthetic 512x512 frames -> HG encoder (PyTorch fp32) -> recon -> visible surface, every frame
+    # one CUDA-graph launch, two lanes in flight per GPU; at N > 1 the ranks work on different frames (frame-parallel replicas)
+    net.image_filter.to(dev)
+    gI = torch.Generator().manual_seed(5 + rank)
+    frames = [(torch.rand(1, 3, 512, 512, generator=gI) * 2 - 1).to(dev) for _ in range(4)]
+    hook = _person_hook(feats[0][:, 0].clone())
+    stream = {}
+    for lanes in (1, 2):
+        ring = FrameGraphRing(lambda: FrameGraph(net, eng, cal_cpu, "front", with_encoder=True, feature_hook=hook), n_lanes=lanes)
+        list(ring.run(frames[i % 4] for i in range(4)))
+        barrier()
+        t0 = time.perf_counter()
+        nst = 40
+        for r_ in ring.run(frames[i % 4] for i in range(nst)):
+            pass
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        stream["%d_lane%s" % (lanes, "s" if lanes > 1 else "")] = world * nst / dt.item()
+        pts_frame = int(sum(ring.lanes[0].last_stats))
+        ring.close()
+    out["configs3_stream_frames_per_s"] = dict(stream, note="512x512 frame -> HGFilter (PyTorch fp32, seeded random init; channel 0 of its map carries the synthetic "
+                                               "body height field, %d points evaluated per frame) -> recon -> forward_vertices; one CUDA-graph launch per frame "
+                                               "(pipeline.FrameGraph); %d GPU(s) = frame-parallel replicas" % (pts_frame, world))
+    if world > 1:
+        # the list-sharded engine: ONE frame at a time over all GPUs (MLP evaluations split, volume passes replicated)
+        sh = Seg3dLossless(make_query_func(net), b, -b, res, balance_value=0.5, faster=True).to(dev).shard(rank, world)
+        for i in range(3):
+            sdf = sh(im_feat_list=[[feats[i % 4]]], calib_tensor=cal_cpu)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(nfr):
+            sdf = sh(im_feat_list=[[feats[i % 4]]], calib_tensor=cal_cpu)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        single = eng(im_feat_list=[[feats[(nfr - 1) % 4]]], calib_tensor=cal_cpu)
+        okv = torch.tensor([int(torch.equal(sdf, single))], device=dev)
+        dist.all_reduce(okv, op=dist.ReduceOp.MIN)
+        out["list_sharded_engine"] = {"frames_per_s": nfr / dt.item(), "volume_matches_single_gpu": bool(okv.item()),
+                                      "note": "every level's node list evaluated in %d windows (one per GPU), values exchanged by peer-memory stores; "
+                                              "at 256^3 a frame is latency-bound (one tile per SM per level), so this does not scale -- see configs3 replicas" % world}
+        barrier()
+        sh.unshard()
+    return out if rank == 0 else None
 
 
 if __name__ == "__main__":

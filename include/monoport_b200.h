@@ -186,6 +186,12 @@ int mp_octree_run_fused(mp_octree_t* h, mp_mlp_t* mlp, mp_feat_t* feat, const fl
  *   mp_octree_shard_set    : rank / world and, per rank, the peer mappings of those three blocks (mp_ipc_open; entry
  *                            [rank] is ignored).  world == 1 switches sharding off.  All ranks must then call
  *                            mp_octree_run_fused the same number of times with the same inputs. */
+/* The fused run in two halves for CUDA-graph captured frame steps: _async only enqueues (no host memory is read, no
+ * synchronisation: capturable; engines without a conflict loop, i.e. faster != 0 or top-k), mp_octree_fetch reads the
+ * non-empty flag and the per-level counts back afterwards (synchronises). */
+int mp_octree_run_fused_async(mp_octree_t* h, mp_mlp_t* mlp, mp_feat_t* feat, const float* calib12, int projection,
+                              float z_scale, int mode, float* out_dev, void* stream);
+int mp_octree_fetch(mp_octree_t* h, int* nonempty, int64_t* stats_host, void* stream);
 int mp_octree_shard_export(mp_octree_t* h, unsigned char* handles192);
 int mp_octree_shard_set(mp_octree_t* h, int rank, int world, float* const* vals0, float* const* vals1,
                         uint32_t* const* flags);
@@ -209,6 +215,12 @@ int mp_mcubes_emit(mp_mcubes_t* h, const float* vol_dev, float iso, float* verts
  * ------------------------------------------------------------------------------------------- */
 int mp_forward_vertices(const float* vol_dev, int R, int direction, int64_t* x_dev, int64_t* y_dev, float* z_dev,
                         float* norm_dev, int64_t* n_out, void* stream);
+/* Enqueue-only variant for CUDA-graph captured frame steps (the reference overlaps its stages with one
+ * Python thread per processor, RTL/dataloader.py:734-751): no allocation, no host read-back.  scratch_dev: at least
+ * mp_forward_vertices_scratch_bytes(R) bytes of device memory; count_dev: one int64 on the device. */
+int64_t mp_forward_vertices_scratch_bytes(int R);
+int mp_forward_vertices_async(const float* vol_dev, int R, int direction, int64_t* x_dev, int64_t* y_dev, float* z_dev,
+                              float* norm_dev, int64_t* count_dev, void* scratch_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Direct rendering of the visible surface with the colour head.  Replaces colorization (RTL/main.py:212-249): vertex i =

@@ -64,6 +64,8 @@ SIGNATURES = {
     "mp_octree_finish": (c_int, [c_void_p, c_void_p, P(c_int), c_void_p]),
     "mp_octree_run_fused": (c_int, [c_void_p, c_void_p, c_void_p, P(c_float), c_int, c_float, c_int, c_void_p,
                                     P(c_int), P(c_int64), c_void_p]),
+    "mp_octree_run_fused_async": (c_int, [c_void_p, c_void_p, c_void_p, P(c_float), c_int, c_float, c_int, c_void_p, c_void_p]),
+    "mp_octree_fetch": (c_int, [c_void_p, P(c_int), P(c_int64), c_void_p]),
     "mp_octree_shard_export": (c_int, [c_void_p, ctypes.c_char_p]),
     "mp_octree_shard_set": (c_int, [c_void_p, c_int, c_int, P(c_void_p), P(c_void_p), P(c_void_p)]),
     "mp_mcubes_create": (c_int, [c_int, c_int, c_int, P(c_void_p)]),
@@ -74,6 +76,9 @@ SIGNATURES = {
                                     P(c_float), c_int, c_float, c_void_p, c_void_p]),
     "mp_forward_vertices": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, P(c_int64),
                                     c_void_p]),
+    "mp_forward_vertices_scratch_bytes": (c_int64, [c_int]),
+    "mp_forward_vertices_async": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p]),
 }
 
 _lib = None

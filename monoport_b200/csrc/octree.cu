@@ -314,8 +314,7 @@ static int build_level_list(mp_octree* h, int level, cudaStream_t st) {
     TopkEmit em{h->idx, h->sel};
     MP_CUDA(mpscan::scan_emit(f, em, nf, h->sums, h->total, st));
     // count = k exactly
-    const int32_t kk = (int32_t)k;
-    MP_CUDA(cudaMemcpyAsync(h->count, &kk, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    set_i32_kernel<<<1, 1, 0, st>>>(h->count, (int32_t)k);
     return MP_OK;
   }
   if (interp_only) {
@@ -488,7 +487,7 @@ static int run_fused_levels(mp_octree* h, mp_mlp_t* mlp, mp_feat_t* feat, const 
     set_u8_kernel<<<grid_for(n), 256, 0, st>>>(h->known[h->cur], n, 1);
     any_gt_kernel<<<grid_for(n), 256, 0, st>>>(h->vol[h->cur], n, h->balance, h->nonempty);
     const long long n0 = n;
-    MP_CUDA(cudaMemcpyAsync(h->stats, &n0, sizeof(long long), cudaMemcpyHostToDevice, st));
+    set_i64_kernel<<<1, 1, 0, st>>>(h->stats, n0);
   }
   for (int level = 1; level < h->n_levels; ++level) {
     h->level = level;
@@ -507,7 +506,7 @@ static int run_fused_levels(mp_octree* h, mp_mlp_t* mlp, mp_feat_t* feat, const 
         if (k <= 0) break;
         src.n = k;
         src.count_dev = nullptr;
-        MP_CUDA(cudaMemcpyAsync(h->stats + level, &k, sizeof(long long), cudaMemcpyHostToDevice, st));
+        set_i64_kernel<<<1, 1, 0, st>>>(h->stats + level, k);
       }
       const float* vals = h->vals;
       const bool via_vals = lossless || h->shard_world > 1;
@@ -538,6 +537,44 @@ static int run_fused_levels(mp_octree* h, mp_mlp_t* mlp, mp_feat_t* feat, const 
     }
   }
   h->level = h->n_levels - 1;
+  return MP_OK;
+}
+
+// The enqueue half of the fused run: everything is stream-ordered and no host memory is read, so the call can be captured
+// into a CUDA graph (engines without a conflict loop: `faster` and top-k).  Results (non-empty flag, per-level counts) stay
+// on the device until mp_octree_fetch.
+extern "C" int mp_octree_run_fused_async(mp_octree_t* h, mp_mlp_t* mlp, mp_feat_t* feat, const float* calib12, int projection,
+                                         float z_scale, int mode, float* out_dev, void* stream) {
+  MP_REQUIRE(h && mlp && feat && out_dev, "NULL argument");
+  MP_REQUIRE(mlp->cout[mlp->n_layers - 1] == 1, "the occupancy engine needs a single-channel head");
+  MP_REQUIRE(h->use_topk || h->faster, "the lossless engine's conflict loop reads counts on the host; use mp_octree_run_fused");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = reset_run(h, st);
+  if (rc != MP_OK) return rc;
+  MpCalib cal;
+  mp_fill_calib(cal, calib12, projection, z_scale);
+  const int final_buf = (h->n_levels - 1) & 1;
+  float* const own_buf = h->vol[final_buf];
+  h->vol[final_buf] = out_dev;          // the last level lands in the caller's volume (see mp_octree_run_fused)
+  rc = run_fused_levels(h, mlp, feat, cal, mode, st);
+  const bool in_place = h->cur == final_buf;
+  const float* result = h->vol[h->cur];
+  h->vol[final_buf] = own_buf;
+  if (rc != MP_OK) return rc;
+  if (!in_place) MP_CUDA(cudaMemcpyAsync(out_dev, result, h->vol_elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  h->phase = 2;
+  return MP_OK;
+}
+
+// The read-back half: non-empty flag and per-level evaluated-node counts of the last (async) run.  Synchronises.
+extern "C" int mp_octree_fetch(mp_octree_t* h, int* nonempty, int64_t* stats_host, void* stream) {
+  MP_REQUIRE(h && nonempty, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long stats[kStatSlots];
+  MP_CUDA(cudaMemcpyAsync(stats, h->stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
+  MP_CUDA(cudaStreamSynchronize(st));
+  *nonempty = *reinterpret_cast<const int*>(stats + kStatSlots - 1);
+  if (stats_host) for (int l = 0; l < h->n_levels; ++l) stats_host[l] = stats[l];
   return MP_OK;
 }
 

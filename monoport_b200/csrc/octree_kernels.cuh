@@ -154,6 +154,10 @@ __global__ void iota_kernel(int32_t* idx, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) idx[i] = i;
 }
 
+// a scalar parameter -> device memory (instead of a host-to-device copy from a stack variable: graph-capturable)
+__global__ void set_i32_kernel(int32_t* p, int32_t v) { *p = v; }
+__global__ void set_i64_kernel(long long* p, long long v) { *p = v; }
+
 __global__ void set_u8_kernel(uint8_t* p, long long n, uint8_t v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }

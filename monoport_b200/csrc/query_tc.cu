@@ -25,6 +25,7 @@
 #include "mp_common.cuh"
 #include "tc_ptx.cuh"
 #include <stdlib.h>
+#include <cuda.h>          // CUtensorMap (the encoder itself is fetched from the driver at run time)
 
 namespace {
 
@@ -32,12 +33,15 @@ constexpr int kC = 256;                 // feature channels
 constexpr int kTile = 128;              // points per tile
 constexpr int kThreads = 384;
 
-struct Cfg {                                        // weight ring: 3 stages of 32 KB
-  static constexpr int Stages = 3;
-  static constexpr int StageBytes = 32768;
+// weight ring: 96 KB.  One CTA per tile (CG = 1): 3 stages of 32 KB = whole weight tiles.  CTA pair (CG = 2, see
+// query_tc3_kernel): every CTA holds HALF of the rows of each tile, 6 stages of 16 KB -- the ring covers twice as many MMAs.
+template <int CG> struct CfgT {
+  static constexpr int Stages = 3 * CG;
+  static constexpr int StageBytes = 32768 / CG;
   static constexpr int Sub = StageBytes / 2;       // second K-block of a two-K-block (128-row tile) stage
 };
-constexpr int kStages = 3;                          // weight-ring barrier slots
+using Cfg = CfgT<1>;
+constexpr int kStages = 6;                          // weight-ring barrier slots (max over the variants)
 constexpr int kRingBytes = 98304;
 constexpr int kL0 = 1024, kL1 = 512, kL2 = 256, kL3 = 128;
 constexpr int kMaxRes = 1;             // output channels handled by the fp32 tail (PIFuNetGMLP: 1)
@@ -50,6 +54,9 @@ __host__ __device__ constexpr int side_off(int l) { return l == 0 ? 0 : l == 1 ?
 
 struct TcPack {
   __half* w3stream;       // stage stream of a tile: kStagesPerTile3 (geometry) / kStagesPerTileC (colour) x 32 KB
+  __half* w3pair[2];      // CTA-pair variant: per cluster rank, kStagesPerTile3 x 16 KB (this rank's half of the rows of every tile)
+  CUtensorMap tmap_pair[2];   // 2-D tensor maps over w3pair[r]: [rows][64 fp16], box = one 16 KB stage (128 rows)
+  int pair_ok;
   __half* d_bias0;        // fp16 device copies of the layer-0 bias / depth column for per-lane channel access (v3 H0 generation)
   __half* d_wz0;
   uint8_t* d_w0t;         // the same as fp16 SWIZZLE_128B tiles [n tile 4][K block 4][256 x 64] for g0_tc_kernel
@@ -92,6 +99,7 @@ struct TcParams {
   const unsigned* amax;       // range guard (see mp_guard_skips): max |feature| of the frame, limit of this head, sense
   float amax_limit;
   int guard;
+  alignas(64) CUtensorMap tmap_pair[2];     // CTA-pair variant: the two ranks' halves of the weight stream
 };
 constexpr int kTraceTile = 8;
 // v3 event ids: MMA issuer 0..31, worker warp 4 at 32.., worker warp 8 at 64.., sampler warp 2 at 96..
@@ -226,6 +234,10 @@ __device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity) {
   if (tc::elect_one()) tc::mbar_wait(bar, parity);
   __syncwarp();
 }
+__device__ __forceinline__ void warp_wait_cluster(uint64_t* bar, uint32_t parity) {      // arrivals may come from the peer CTA
+  if (tc::elect_one()) tc::mbar_wait_cluster(bar, parity);
+  __syncwarp();
+}
 
 // ====================================================================================================================
 // v3: layer 0 hoisted from points to texels.
@@ -241,10 +253,19 @@ __device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity) {
 // roofline.achieved keeps counting the ALGORITHMIC 2 363 906 FLOP/point; the hoisted layer is not executed per point.
 // PEERS: also store channel 0 into the peer volumes of dst (fused slab exchange); the default instantiation carries no
 // trace of it.
-template <bool PEERS = false>
+//
+// CG = 2 (opt-in, MONOPORT_B200_TC_CG=2; measured 2.4 % slower than CG = 1, see mp_launch_query_tc): a CTA PAIR (2-CTA cluster
+// on one TPC) works on two tiles at once with tcgen05.mma.cta_group::2 (M = 256 = the 128 points of each CTA).  Every weight tile is split between the two shared memories (each CTA streams half of its rows by
+// tensor-map TMA, both halves completing on the leader's barrier), so each SM ingests half of the weight bytes per point
+// and the 96 KB ring covers twice as many MMAs.  That matters since the MMAs are issued at the tensor pipe's rate: the
+// one-CTA kernel then waits 16.5 k of 69 k cycles per tile for weight stages (profiles/r02_call6_*), the L2 -> SM stream
+// being the bound.  Everything per tile -- operands in shared / tensor memory, samplers, workers, epilogue -- stays local
+// to its CTA; the leader (rank 0) issues all MMAs, operand hand-offs are remote mbarrier arrivals on the leader's
+// barriers, MMA completions are multicast to both CTAs by tcgen05.commit.
+template <bool PEERS = false, int CG = 1>
 __global__ void __launch_bounds__(kThreads, 1)
-query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
-  using C = Cfg;
+query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
+  using C = CfgT<CG>;
   MP_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::Bars);
@@ -266,8 +287,12 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
   mp_shard_window(src, n, win0, win1);
   n = win1;                                          // points >= n are padding; tile 0 starts at point win0
   const long long n_tiles = (win1 - win0 + kTile - 1) / kTile;
-  const long long n_groups = n_tiles;
-  const long long g0 = blockIdx.x, gstep = gridDim.x;
+  // the unit of scheduling is a group of CG tiles (one per CTA of the pair); both CTAs run the same number of iterations, a
+  // CTA whose tile lies beyond n_tiles computes on masked-out points
+  const long long n_groups = (n_tiles + CG - 1) / CG;
+  const long long g0 = blockIdx.x / CG, gstep = gridDim.x / CG;
+  const uint32_t rank = (CG == 2) ? tc::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
 
   constexpr uint32_t cAcc1 = 0, cH1lo = 0, cH1hi = 384, cAcc2 = 128, cH2 = 0, cAcc3 = 384;
 
@@ -276,8 +301,10 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       tc::mbar_init(bars + B_WFULL + s, 1);
       tc::mbar_init(bars + B_WEMPTY + s, 1);
     }
-    constexpr int kW = 8;
-    tc::mbar_init(bars + B_XREADY, 2);             // the two sampler warps
+    // operand hand-offs to the MMA issuer count one arrival per producing warp of EVERY CTA of the pair (they all arrive on
+    // the leader's barriers); what the issuer hands back (tcgen05.commit) reaches both CTAs' own barriers
+    constexpr int kW = 8 * CG;
+    tc::mbar_init(bars + B_XREADY, 2 * CG);        // the two sampler warps
     tc::mbar_init(bars + B_H0_READY0, kW);
     tc::mbar_init(bars + B_H0_READY1, kW);
     tc::mbar_init(bars + B_H0_FREE0, 1);
@@ -287,23 +314,34 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     tc::mbar_init(bars + B_ACC2_FULL, 1);
     tc::mbar_init(bars + B_H2_READY, kW);
     tc::mbar_init(bars + B_ACC3_FULL, 1);
-    tc::mbar_init(bars + B_TILE_DONE, 4);
+    tc::mbar_init(bars + B_TILE_DONE, 4 * CG);
     tc::mbar_init(bars + B_XFREE, 1);
     tc::mbar_init(bars + B_ACC0_FULL0, 2);         // v3: "per-point scalars of this tile are in smem" (CTA-local)
     tc::mbar_init(bars + B_ACC0_FULL1, 1);
     tc::fence_barrier_init();
+#ifndef MP_CUDA_EMU
+    if constexpr (CG == 2) tc::tma_prefetch_desc(&prm.tmap_pair[rank]);
+#endif
   }
   if (warp == 2) {
-    tc::tmem_alloc(s_tmem, 512);
-    tc::tmem_relinquish();
+    if constexpr (CG == 1) { tc::tmem_alloc(s_tmem, 512); tc::tmem_relinquish(); }
+    else { tc::tmem_alloc2(s_tmem, 512); tc::tmem_relinquish2(); }
   }
   tc::tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CG == 1) __syncthreads(); else tc::cluster_sync_all();
   tc::tcgen05_fence_after();
   const uint32_t tbase = *s_tmem;
+  // an operand hand-off of a producing warp to the MMA issuer (which lives in the leader CTA)
+  auto arrive_issuer = [&](int which) {
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (CG == 1) tc::mbar_arrive(bars + which);
+      else tc::mbar_arrive_remote(bars + which, 0);
+    }
+  };
 
   if (warp == 0) {
-    // ============================== weight producer ==============================
+    // ============================== weight producer (every CTA streams its own part of every tile) ===============
     if (lane == 0) {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.wstream);
       uint32_t it = 0;
@@ -312,13 +350,24 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           const int slot = it % C::Stages;
           const uint32_t use = it / C::Stages;
           tc::mbar_wait(bars + B_WEMPTY + slot, (use & 1u) ^ 1u);
-          if ((prm.exp & 1) && it >= (uint32_t)C::Stages) { tc::mbar_arrive(bars + B_WFULL + slot); continue; }
-          tc::mbar_arrive_expect_tx(bars + B_WFULL + slot, C::StageBytes);
-          tc::bulk_g2s(smem + Smem::Wr + slot * C::StageBytes, wsrc + (size_t)s * C::StageBytes, C::StageBytes,
-                       bars + B_WFULL + slot);
+          if constexpr (CG == 1) {
+            if ((prm.exp & 1) && it >= (uint32_t)C::Stages) { tc::mbar_arrive(bars + B_WFULL + slot); continue; }
+            tc::mbar_arrive_expect_tx(bars + B_WFULL + slot, C::StageBytes);
+            tc::bulk_g2s(smem + Smem::Wr + slot * C::StageBytes, wsrc + (size_t)s * C::StageBytes, C::StageBytes,
+                         bars + B_WFULL + slot);
+          } else {
+#ifndef MP_CUDA_EMU
+            // both halves of the stage complete on the LEADER's barrier (the leader arms it for 2 x 16 KB)
+            if (leader) tc::mbar_arrive_expect_tx(bars + B_WFULL + slot, 2 * C::StageBytes);
+            tc::tma_load_2d_cg2(smem + Smem::Wr + slot * C::StageBytes, &prm.tmap_pair[rank], 0, s * (C::StageBytes / 128),
+                                bars + B_WFULL + slot);
+#endif
+          }
         }
       }
     }
+  } else if (warp == 1 && !leader) {
+    // (the peer CTA's warp 1 has nothing to do: the leader issues the MMAs of both tiles)
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     // The WHOLE warp runs the control flow (barrier waits, stage counters, descriptor arithmetic: all warp-uniform, so the
@@ -329,48 +378,94 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     {
       unsigned long long* const prof_all = prof;
       prof = (lane == 0) ? prof_all : nullptr;           // one lane records the in-kernel timers
-      const uint32_t idesc128 = tc::make_idesc_f16(128, 128);
-      const uint32_t idesc256 = tc::make_idesc_f16(128, 256);
+      const uint32_t idesc128 = tc::make_idesc_f16(128 * CG, 128);
+      const uint32_t idesc256 = tc::make_idesc_f16(128 * CG, 256);
       const uint32_t sX = tc::smem_u32(smem + Smem::X);
       const uint32_t sH0 = tc::smem_u32(smem + Smem::H0);
       const uint32_t sW = tc::smem_u32(smem + Smem::Wr);
       uint32_t it = 0;
       uint32_t c_xready = 0, c_h0ready[2] = {0, 0}, c_h1ready = 0, c_h2ready = 0, c_tiledone = 0;
       const long long t_begin = prof ? clock64() : 0;
+      // (with a CTA pair the arrivals and the weight bytes partly come from the peer CTA: cluster-scope acquire)
       auto wait_both = [&](int local_bar, int, uint32_t& count) {
-        warp_wait(bars + local_bar, count & 1u);
+        if constexpr (CG == 1) warp_wait(bars + local_bar, count & 1u);
+        else warp_wait_cluster(bars + local_bar, count & 1u);
         ++count;
       };
       auto next_stage = [&]() -> uint32_t {
         const int slot = it % C::Stages;
         const uint32_t par = (it / C::Stages) & 1u;
-        { PROF_T0(); warp_wait(bars + B_WFULL + slot, par); PROF_ADD(P_WFULL); }
+        {
+          PROF_T0();
+          if constexpr (CG == 1) warp_wait(bars + B_WFULL + slot, par);
+          else warp_wait_cluster(bars + B_WFULL + slot, par);
+          PROF_ADD(P_WFULL);
+        }
         tc::tcgen05_fence_after();
         return sW + slot * C::StageBytes;
       };
+      auto commit_bar = [&](uint64_t* bar) {
+        if constexpr (CG == 1) tc::mma_commit(bar);
+        else tc::mma_commit2(bar);
+      };
       auto release_stage = [&]() {
-        if (tc::elect_one()) tc::mma_commit(bars + B_WEMPTY + (it % C::Stages));
+        if (tc::elect_one()) commit_bar(bars + B_WEMPTY + (it % C::Stages));
         ++it;
       };
       auto commit_one = [&](int which) {
-        if (tc::elect_one()) tc::mma_commit(bars + which);
+        if (tc::elect_one()) commit_bar(bars + which);
       };
       // one K-block (64 channels = four K = 16 steps): descriptors advance by 32 B (+2 in the address field)
+      // (MONOPORT_B200_TC_EXP bit 8: the round-1 issue pattern -- one lane builds the descriptors per MMA inside a divergent
+      // branch, which costs ~20 instructions per MMA -- kept selectable for the A/B of profiles/r02_call8_*)
+      const bool slow_issue = (prm.exp & 8) != 0;
       auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool& first) {
+        if (slow_issue) {
+          if (lane == 0) {
+#pragma unroll 1
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = tc::make_sdesc_sw128(a_addr + kk * 32, 1024), bd = tc::make_sdesc_sw128(b_addr + kk * 32, 1024);
+              if constexpr (CG == 1) tc::mma_ss(d, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
+              else tc::mma_ss2(d, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
+            }
+          }
+          __syncwarp();
+          first = false;
+          return;
+        }
         const uint64_t ad0 = tc::make_sdesc_sw128(a_addr, 1024), bd0 = tc::make_sdesc_sw128(b_addr, 1024);
         const uint32_t acc0 = first ? 0u : 1u;
         if (tc::elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc::mma_ss(d, ad0 + 2 * kk, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
+          for (int kk = 0; kk < 4; ++kk) {
+            if constexpr (CG == 1) tc::mma_ss(d, ad0 + 2 * kk, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
+            else tc::mma_ss2(d, ad0 + 2 * kk, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
+          }
         }
         first = false;
       };
       auto kblock_ts = [&](uint32_t d, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool& first) {
+        if (slow_issue) {
+          if (lane == 0) {
+#pragma unroll 1
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t bd = tc::make_sdesc_sw128(b_addr + kk * 32, 1024);
+              if constexpr (CG == 1) tc::mma_ts(d, a_tmem + kk * 8, bd, idesc, (first && kk == 0) ? 0u : 1u);
+              else tc::mma_ts2(d, a_tmem + kk * 8, bd, idesc, (first && kk == 0) ? 0u : 1u);
+            }
+          }
+          __syncwarp();
+          first = false;
+          return;
+        }
         const uint64_t bd0 = tc::make_sdesc_sw128(b_addr, 1024);
         const uint32_t acc0 = first ? 0u : 1u;
         if (tc::elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc::mma_ts(d, a_tmem + kk * 8, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
+          for (int kk = 0; kk < 4; ++kk) {
+            if constexpr (CG == 1) tc::mma_ts(d, a_tmem + kk * 8, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
+            else tc::mma_ts2(d, a_tmem + kk * 8, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
+          }
         }
         first = false;
       };
@@ -477,7 +572,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     const int res = prm.res;
     uint32_t c_xfree = 0;
     for (long long g = g0; g < n_groups; g += gstep) {
-      const long long tile = g;
+      const long long tile = g * CG + rank;
       const long long p0 = win0 + tile * kTile;
       const bool tr = blockIdx.x == 0 && sw == 0 && lane == 0 && (g - g0) / gstep == kTraceTile;
       TRACE(tr, 96);
@@ -493,7 +588,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       tc::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(bars + B_ACC0_FULL0);        // scalars ready (CTA-local, release)
-      warp_arrive_local(bars + B_XREADY, lane);
+      arrive_issuer(B_XREADY);
       TRACE(tr, 98);
     }
   } else if (warp >= 4) {
@@ -521,7 +616,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
     uint32_t t_off[4][2], t_wgt[4][2], t_z[4];
     int gtr = -1;                              // trace slot base for the chunk being generated (-1: off)
     auto compute_taps = [&](long long g) {
-      const PointTaps pt = point_taps(src, cal, prm.H, prm.W, win0 + g * kTile + wk * 16 + l16, n);
+      const PointTaps pt = point_taps(src, cal, prm.H, prm.W, win0 + (g * CG + rank) * kTile + wk * 16 + l16, n);
       const uint32_t o01 = (uint32_t)pt.off[0] | ((uint32_t)pt.off[1] << 16), o23 = (uint32_t)pt.off[2] | ((uint32_t)pt.off[3] << 16);
       const uint32_t w01 = tc::pack_half2(pt.wgt[0], pt.wgt[1]), w23 = tc::pack_half2(pt.wgt[2], pt.wgt[3]);
       const uint32_t zz = tc::pack_half2(pt.zf, pt.zf);
@@ -604,7 +699,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           TRACE(gtr >= 0, gtr + 3 + 2 * batch);
         }
         tc::fence_proxy_async_smem();
-        warp_arrive_local(bars + B_H0_READY0 + b, lane);
+        arrive_issuer(B_H0_READY0 + b);
         TRACE(gtr >= 0, gtr + 6);
         PROF_ADD(P_W_DRAIN0);
       };
@@ -635,7 +730,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
       for (long long g = g0 - gstep; g < n_groups; g += gstep) {
         const bool real = g >= g0;
         const bool has_next = g + gstep < n_groups;
-        const long long p0 = win0 + g * kTile;
+        const long long p0 = win0 + (g * CG + rank) * kTile;
         const bool tr = blockIdx.x == 0 && real && (wk & 3) == 0 && lane == 0 && (g - g0) / gstep == kTraceTile;
         const int tb = 32 + wg * 32;
 #pragma unroll 1
@@ -676,7 +771,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           tc::tmem_st_wait();
         }
         tc::tcgen05_fence_before();
-        warp_arrive_local(bars + B_H1_READY, lane);
+        arrive_issuer(B_H1_READY);
         PROF_ADD(P_W_DRAIN1);
         TRACE(tr, tb + 12);
       }
@@ -699,7 +794,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
         }
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
-        warp_arrive_local(bars + B_H2_READY, lane);
+        arrive_issuer(B_H2_READY);
         PROF_ADD(P_W_DRAIN2);
         TRACE(tr, tb + 14);
       }
@@ -735,7 +830,7 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
           }
         }
         tc::tcgen05_fence_before();
-        warp_arrive_local(bars + B_TILE_DONE, lane);
+        arrive_issuer(B_TILE_DONE);
         PROF_ADD(P_W_DRAIN3);
         TRACE(tr, tb + 16);
         const long long i = p0 + row;
@@ -764,8 +859,13 @@ query_tc3_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
   }
   __syncwarp();
   tc::tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 2) tc::tmem_dealloc(tbase, 512);
+  if constexpr (CG == 1) {
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tbase, 512);
+  } else {
+    tc::cluster_sync_all();
+    if (warp == 2) tc::tmem_dealloc2(tbase, 512);
+  }
 }
 
 // G0[texel][n] = sum_k F[texel][k] * W0f[n][k] on the tensor cores: fp16 operands (F rounded once while staging, W0f
@@ -1849,8 +1949,9 @@ int mp_tc_prepare(mp_mlp* mlp) {
     MP_CUDA(cudaMemcpy(Bv[l].data(), mlp->bias[l], Bv[l].size() * sizeof(float), cudaMemcpyDeviceToHost));
   }
   // v3 program (layer 0 hoisted): layer 1 over all 512 outputs as two 256-row tiles per K-block, then layers 2, 3
-  auto build_stream3 = [&](std::vector<uint8_t>& out) -> bool {
-    const int cg = 1, r = 0;
+  // cg = 1: 32 KB stages holding whole tiles; cg = 2 (CTA pair): 16 KB stages holding rank r's half of the rows of every
+  // tile (tcgen05.mma.cta_group::2 reads B rows [r*N/2, (r+1)*N/2) from CTA r)
+  auto build_stream3 = [&](int cg, int r, std::vector<uint8_t>& out) -> bool {
     const int stage_bytes = 32768 / cg, sub = stage_bytes / 2;
     out.assign((size_t)kStagesPerTile3 * stage_bytes, 0);
     size_t st = 0;
@@ -1876,8 +1977,8 @@ int mp_tc_prepare(mp_mlp* mlp) {
     }
     return (int)st == kStagesPerTile3;
   };
-  std::vector<uint8_t> s3;
-  if (!build_stream3(s3)) {
+  std::vector<uint8_t> s3, s3p[2];
+  if (!build_stream3(1, 0, s3) || !build_stream3(2, 0, s3p[0]) || !build_stream3(2, 1, s3p[1])) {
     mp_set_error("internal: v3 weight stream stage count mismatch");
     return MP_E_INVALID;
   }
@@ -1891,6 +1992,31 @@ int mp_tc_prepare(mp_mlp* mlp) {
     return cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
   };
   cudaError_t e = upload(s3.data(), s3.size(), (void**)&pk->w3stream);
+#ifndef MP_CUDA_EMU
+  for (int r = 0; r < 2 && e == cudaSuccess; ++r) e = upload(s3p[r].data(), s3p[r].size(), (void**)&pk->w3pair[r]);
+  if (e == cudaSuccess) {
+    // tensor maps over the two half streams: [rows][64 fp16] with 128-byte rows, box = one 16 KB stage (the tiles are
+    // stored pre-swizzled, so the copy itself is a plain 2-D box: no swizzle, no interleave)
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    EncodeFn encode = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &qres) == cudaSuccess && encode) {
+      pk->pair_ok = 1;
+      for (int r = 0; r < 2; ++r) {
+        const cuuint64_t gdim[2] = {64, (cuuint64_t)kStagesPerTile3 * 128};
+        const cuuint64_t gstr[1] = {128};
+        const cuuint32_t box[2] = {64, 128};
+        const cuuint32_t estr[2] = {1, 1};
+        if (encode(&pk->tmap_pair[r], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, pk->w3pair[r], gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          pk->pair_ok = 0;
+      }
+    }
+  }
+#endif
   {   // feature part of layer 0 as fp16 SWIZZLE_128B tiles, operand of the per-texel G0 GEMM
     if (e == cudaSuccess) {
       std::vector<uint8_t> w0t((size_t)(kL0 / kG0TileN) * 4 * 32768);
@@ -1932,8 +2058,12 @@ int mp_tc_prepare(mp_mlp* mlp) {
     mp_tc_release(mlp);
     return MP_E_CUDA;
   }
-  e = cudaFuncSetAttribute(query_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+  e = cudaFuncSetAttribute(query_tc3_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+#ifndef MP_CUDA_EMU
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+#endif
   if (e == cudaSuccess) e = cudaFuncSetAttribute(g0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG0Smem);
   if (e != cudaSuccess) {
     mp_set_error("mp_tc_prepare: cannot opt in to %d bytes of shared memory: %s", Smem::Total + 1024, cudaGetErrorString(e));
@@ -1948,6 +2078,7 @@ void mp_tc_release(mp_mlp* mlp) {
   TcPack* pk = static_cast<TcPack*>(mlp->tc);
   if (!pk) return;
   if (pk->w3stream) cudaFree(pk->w3stream);
+  for (int r = 0; r < 2; ++r) if (pk->w3pair[r]) cudaFree(pk->w3pair[r]);
   if (pk->d_bias0) cudaFree(pk->d_bias0);
   if (pk->d_wz0) cudaFree(pk->d_wz0);
   if (pk->d_w0t) cudaFree(pk->d_w0t);
@@ -2093,13 +2224,44 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     mp_set_error("at most %d peer volumes", MP_MAX_PEERS);
     return MP_E_UNSUPPORTED;
   }
+#ifndef MP_CUDA_EMU
+  // One CTA per tile by default.  MONOPORT_B200_TC_CG=2 selects the CTA-pair kernel (validated: the whole GPU suite passes
+  // with it) -- same box, same run: 486 Mpoints/s against 498 (profiles/r02_call8_ab_issue_pattern_x_cta_group.txt).  The
+  // pair halves the weight bytes per SM, but a 2-CTA MMA runs at the same per-SM rate (tools/tc_rate.cu) and every operand
+  // hand-off and weight-stage release crosses the cluster, which costs more than the halved stream gains.
+  static const int forced_cg = [] { const char* v = getenv("MONOPORT_B200_TC_CG"); return v ? atoi(v) : 0; }();
+  if (pk->pair_ok && forced_cg == 2 && sms >= 2) {
+    prm.tmap_pair[0] = pk->tmap_pair[0];
+    prm.tmap_pair[1] = pk->tmap_pair[1];
+    const long long groups = (tiles + 1) / 2;
+    const long long max_pairs = sms / 2;
+    const int pairs = (int)(groups < max_pairs ? groups : max_pairs);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Smem::Total + 1024;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (dst.n_peers > 0) MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc3_kernel<true, 2>, prm, src, cal, dst));
+    else MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc3_kernel<false, 2>, prm, src, cal, dst));
+    report(2 * pairs);
+    return MP_OK;
+  }
+#endif
   const int grid = (int)(tiles < (long long)sms ? tiles : sms);
 #ifndef MP_CUDA_EMU
-  if (dst.n_peers > 0) query_tc3_kernel<true><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);      // fused slab exchange
-  else query_tc3_kernel<false><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
+  if (dst.n_peers > 0) query_tc3_kernel<true, 1><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);      // fused slab exchange
+  else query_tc3_kernel<false, 1><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
 #else
-  if (dst.n_peers > 0) MP_EMU_LAUNCH(grid, kThreads, (query_tc3_kernel<true>(prm, src, cal, dst)));
-  else MP_EMU_LAUNCH(grid, kThreads, (query_tc3_kernel<false>(prm, src, cal, dst)));
+  if (dst.n_peers > 0) MP_EMU_LAUNCH(grid, kThreads, (query_tc3_kernel<true, 1>(prm, src, cal, dst)));
+  else MP_EMU_LAUNCH(grid, kThreads, (query_tc3_kernel<false, 1>(prm, src, cal, dst)));
 #endif
   MP_CUDA(cudaGetLastError());
   report(grid);

@@ -57,20 +57,24 @@ class _Seg3dBase(nn.Module):
         self._sharded = None
         self.last_stats = None
 
+    def _new_handle(self, device):
+        """A fresh engine workspace (mp_octree_t) with this engine's parameters."""
+        n = len(self.resolutions)
+        res = (ctypes.c_int * n)(*self.resolutions)
+        topk = None if self.topk_points is None else (ctypes.c_int * n)(*self.topk_points)
+        h = ctypes.c_void_p()
+        with _lib.device_guard(device):
+            _lib.check(_lib.load().mp_octree_create(
+                n, res, _lib.f3(self.b_min), _lib.f3(self.b_max), ctypes.c_float(self.balance_value),
+                1 if self.faster else 0, topk, ctypes.byref(h)), "mp_octree_create")
+        return h
+
     # one engine workspace per (device, calling thread)
     def _handle(self, device):
         key = (device.index if device.index is not None else torch.cuda.current_device(), threading.get_ident())
         h = self._handles.get(key)
         if h is None:
-            n = len(self.resolutions)
-            res = (ctypes.c_int * n)(*self.resolutions)
-            topk = None if self.topk_points is None else (ctypes.c_int * n)(*self.topk_points)
-            h = ctypes.c_void_p()
-            with _lib.device_guard(device):
-                _lib.check(_lib.load().mp_octree_create(
-                    n, res, _lib.f3(self.b_min), _lib.f3(self.b_max), ctypes.c_float(self.balance_value),
-                    1 if self.faster else 0, topk, ctypes.byref(h)), "mp_octree_create")
-            self._handles[key] = h
+            h = self._handles[key] = self._new_handle(device)
         return h
 
     def __del__(self):

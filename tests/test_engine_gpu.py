@@ -240,3 +240,63 @@ def test_frame_pipeline_overlap_equals_sequential():
     assert len(par) == len(seq) == 9
     for a, c in zip(seq, par):
         assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1]) and torch.equal(a[3], c[3])
+
+
+def test_frame_graph_equals_eager_frames():
+    """the CUDA-graph captured frame step (features -> coarse-to-fine engine -> visible surface, one graph
+    launch per frame, two lanes in flight) returns exactly what the eager calls return, frame after frame, including an
+    empty frame (engine -> None) between full ones; and with the PyTorch encoder inside the captured step."""
+    from monoport_b200.engine import Seg3dLossless, make_query_func
+    from monoport_b200.pipeline import FrameGraph, FrameGraphRing
+    from monoport_b200.recon import forward_vertices
+    Ws, bs = spec.make_weights(spec.G_CHANNELS, 3)
+    base = spec.make_feat(256, 128, 128, 4, 0.5)
+    feats = []
+    for k in range(3):
+        W2, b2, f, _ = spec.heightfield_person(Ws, bs, base * (1.0 + 0.1 * k), channel=0)
+        feats.append(f.cuda())
+    empty = feats[0].clone()
+    empty[0, 0] = -5.0                                   # height map far below every node: nothing occupied
+    frames = [feats[0], feats[1], empty, feats[2], feats[0]]
+    net = build_net("G", W2, b2)
+    cal = spec.scene_calib(20, 33)
+    b = np.array([[-1.0, -1.0, -1.0]], dtype=np.float32)
+    eng = Seg3dLossless(make_query_func(net), b, -b, [17, 33, 65], balance_value=0.5, faster=True).to("cuda")
+    want = []
+    for f in frames:
+        sdf = eng(im_feat_list=[[f]], calib_tensor=cal.cuda())
+        X, Y, Z, n = forward_vertices(sdf, "front")
+        want.append((None if sdf is None else sdf.clone(), X, Y, Z, n, list(eng.last_stats)))
+    assert want[2][0] is None and want[0][0] is not None
+    ring = FrameGraphRing(lambda: FrameGraph(net, eng, cal, "front", with_encoder=False), n_lanes=2)
+    got = []
+    for sdf, X, Y, Z, n in ring.run(iter(frames)):
+        got.append((None if sdf is None else sdf.clone(), None if X is None else X.clone(), None if Z is None else Z.clone(),
+                    None if n is None else n.clone()))
+    assert len(got) == len(want)
+    for w, g in zip(want, got):
+        if w[0] is None:
+            assert g[0] is None
+            continue
+        assert torch.equal(w[0], g[0]) and torch.equal(w[1], g[1]) and torch.equal(w[3], g[2]) and torch.equal(w[4], g[3])
+    assert ring.lanes[0].last_stats == want[4][5]
+    ring.close()
+    # with the encoder inside the captured step: same volume as filter() + engine() run eagerly on the same image
+    torch.manual_seed(0)
+    net.image_filter.cuda()
+    img = (torch.rand(1, 3, 512, 512, generator=torch.Generator().manual_seed(5)) * 2 - 1).cuda()
+
+    def hook(f):                                          # deterministic body-like field: channel 0 carries the height map
+        f = f.clone()
+        f[:, 0] = feats[0][:, 0]
+        return f
+    with torch.no_grad():
+        fe = hook(net.filter(img)[-1][0])
+        sdf = eng(im_feat_list=[[fe]], calib_tensor=cal.cuda())
+    fg = FrameGraph(net, eng, cal, "front", with_encoder=True, feature_hook=hook)
+    for _ in range(2):
+        out = fg.launch(img).result()
+        assert out[0] is not None and sdf is not None
+        # cudnn may pick another algorithm under capture: the encoder output agrees to float noise, the mask to a few nodes
+        assert ((out[0] > 0.5) != (sdf > 0.5)).sum().item() <= 64
+    fg.close()
