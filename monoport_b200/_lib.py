@@ -175,8 +175,13 @@ def calib12(calib):
         if c.shape[0] != 1:
             raise ValueError("batch size must be 1 (RTL/main.py:175)")
         c = c[0]
-    c = c[:3, :4].to("cpu", dtype=__import__("torch").float32).contiguous().reshape(-1).tolist()
-    val = (c_float * 12)(*c)
+    if on_dev:
+        c = c[:3, :4].to("cpu", dtype=__import__("torch").float32).contiguous().reshape(-1).tolist()
+        val = (c_float * 12)(*c)
+    else:
+        import numpy as np
+        a = np.ascontiguousarray(c.numpy()[:3, :4], dtype=np.float32)
+        val = (c_float * 12).from_buffer_copy(a)
     if on_dev:
         _calib_cache.key, _calib_cache.ref, _calib_cache.val, _calib_cache.scope = key, calib, val, current_scope()
     return val

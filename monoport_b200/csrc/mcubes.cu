@@ -78,6 +78,7 @@ static int sm_count() {
 extern "C" int mp_mcubes_count(mp_mcubes_t* h, const float* vol_dev, float iso, int64_t* n_verts, int64_t* n_faces,
                                void* stream) {
   MP_REQUIRE(h && vol_dev && n_verts && n_faces, "NULL argument");
+  MpRange nvtx("monoport_b200: F3 marching cubes (count)");
   cudaStream_t st = (cudaStream_t)stream;
   {
     // a multiple of the SM count, 8 CTAs of 256 threads resident per SM: 8 x 128 B loads in flight per warp
@@ -108,6 +109,7 @@ extern "C" int mp_mcubes_emit(mp_mcubes_t* h, const float* vol_dev, float iso, f
   MP_REQUIRE(h->counted, "mp_mcubes_count must run first");
   if (h->nv == 0 && h->nf == 0) return MP_OK;
   MP_REQUIRE(verts_dev && faces_dev, "NULL output buffers");
+  MpRange nvtx("monoport_b200: F3 marching cubes (emit)");
   cudaStream_t st = (cudaStream_t)stream;
   const long long n_groups = (h->n_words + 31) >> 5;
   const long long blocks_needed = (n_groups + kEmitThreads / 32 - 1) / (kEmitThreads / 32);

@@ -192,6 +192,7 @@ extern "C" int mp_feat_create(int C, int H, int W, mp_feat_t** out) {
 
 extern "C" int mp_feat_upload(mp_feat_t* h, const float* nchw, int on_device, void* stream) {
   MP_REQUIRE(h && nchw, "NULL handle or data");
+  MpRange nvtx("monoport_b200: feature upload (channel-last repack)");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)h->C * h->H * h->W;
   const float* src = nchw;
@@ -244,6 +245,7 @@ void mp_fill_grid_geom(MpPointSrc& s, int res, int node_stride, int r_final, con
 
 int mp_query_dispatch(mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, const MpCalib& cal, const MpOutDst& dst,
                       int mode, cudaStream_t st) {
+  MpRange nvtx("monoport_b200: F1 fused sample+MLP query");
   // the tensor-core program covers maps of at most 65536 texels (16-bit texel indices in registers)
   const bool tc_can = mlp->tc_ok && (long long)feat->H * feat->W <= 65536;
   if (mode == MP_MODE_AUTO) mode = tc_can ? MP_MODE_TC : MP_MODE_FP32;

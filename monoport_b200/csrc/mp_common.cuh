@@ -19,6 +19,20 @@
 #define MP_DYN_SMEM_ALIGNED(type, name, bytes) extern __shared__ __align__(bytes) type name[]
 #endif
 
+// NVTX ranges around the entry points of the hot path (F1 query, F2 octree, F3 marching cubes / visible surface): header-only
+// NVTX3, a no-op unless a profiler (nsys / ncu --nvtx) is attached
+#ifndef MP_CUDA_EMU
+#include <nvtx3/nvToolsExt.h>
+struct MpRange {
+  explicit MpRange(const char* name) { nvtxRangePushA(name); }
+  ~MpRange() { nvtxRangePop(); }
+};
+#else
+struct MpRange {
+  explicit MpRange(const char*) {}
+};
+#endif
+
 #define MP_LEAKY_SLOPE 0.01f   // F.leaky_relu default (heads/SurfaceClassifier.py:58)
 #define MP_MAX_LAYERS 8
 

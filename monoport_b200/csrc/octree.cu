@@ -548,6 +548,7 @@ extern "C" int mp_octree_run_fused_async(mp_octree_t* h, mp_mlp_t* mlp, mp_feat_
   MP_REQUIRE(h && mlp && feat && out_dev, "NULL argument");
   MP_REQUIRE(mlp->cout[mlp->n_layers - 1] == 1, "the occupancy engine needs a single-channel head");
   MP_REQUIRE(h->use_topk || h->faster, "the lossless engine's conflict loop reads counts on the host; use mp_octree_run_fused");
+  MpRange nvtx("monoport_b200: F2 coarse-to-fine engine (enqueue)");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = reset_run(h, st);
   if (rc != MP_OK) return rc;
@@ -583,6 +584,7 @@ extern "C" int mp_octree_run_fused(mp_octree_t* h, mp_mlp_t* mlp, mp_feat_t* fea
                                    void* stream) {
   MP_REQUIRE(h && mlp && feat && out_dev && nonempty, "NULL argument");
   MP_REQUIRE(mlp->cout[mlp->n_layers - 1] == 1, "the occupancy engine needs a single-channel head");
+  MpRange nvtx("monoport_b200: F2 coarse-to-fine engine");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = reset_run(h, st);
   if (rc != MP_OK) return rc;

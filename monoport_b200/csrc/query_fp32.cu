@@ -238,7 +238,14 @@ template <int P>
 int launch(const Fp32Params& prm, const MpPointSrc& src, const MpCalib& cal, const MpOutDst& dst, cudaStream_t st,
            int sm_count) {
   const size_t smem = Fp32Smem<P>::bytes(prm.c0, prm.h_ping, prm.h_pong);
-  MP_CUDA(cudaFuncSetAttribute(query_fp32_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // (the opt-in is sticky per device: raising it again for every launch costs a driver call per query)
+  static thread_local size_t opted[64] = {};
+  int dev_ = 0;
+  MP_CUDA(cudaGetDevice(&dev_));
+  if (dev_ < 0 || dev_ >= 64 || opted[dev_] < smem) {
+    MP_CUDA(cudaFuncSetAttribute(query_fp32_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev_ >= 0 && dev_ < 64) opted[dev_] = smem;
+  }
   long long tiles = (src.n + P - 1) / P;
   int grid = (int)(tiles < (long long)sm_count ? (tiles > 0 ? tiles : 1) : sm_count);
 #ifndef MP_CUDA_EMU
@@ -287,8 +294,15 @@ int mp_launch_query_fp32(const mp_mlp* mlp, const mp_feat* feat, const MpPointSr
   prm.amax = feat->amax; prm.amax_limit = mlp->tc_amax_limit; prm.guard = guard;
   int dev = 0, sms = 148, max_smem = 0;
   MP_CUDA(cudaGetDevice(&dev));
-  MP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  MP_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  {
+    static thread_local int c_sms[64] = {}, c_smem[64] = {};
+    if (dev >= 0 && dev < 64 && c_sms[dev]) { sms = c_sms[dev]; max_smem = c_smem[dev]; }
+    else {
+      MP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      MP_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+      if (dev >= 0 && dev < 64) { c_sms[dev] = sms; c_smem[dev] = max_smem; }
+    }
+  }
   if (Fp32Smem<32>::bytes(prm.c0, ping, pong) + 2048 <= (size_t)max_smem) return launch<32>(prm, src, cal, dst, st, sms);
   if (Fp32Smem<16>::bytes(prm.c0, ping, pong) + 2048 <= (size_t)max_smem) return launch<16>(prm, src, cal, dst, st, sms);
   if (Fp32Smem<8>::bytes(prm.c0, ping, pong) + 2048 <= (size_t)max_smem) return launch<8>(prm, src, cal, dst, st, sms);

@@ -25,6 +25,7 @@ extern "C" int mp_forward_vertices_async(const float* vol_dev, int R, int direct
   MP_REQUIRE(vol_dev && x_dev && y_dev && z_dev && norm_dev && count_dev && scratch_dev, "NULL argument");
   MP_REQUIRE(R >= 2 && R <= 2048, "bad R=%d", R);
   MP_REQUIRE(direction >= 0 && direction <= 3, "bad direction %d", direction);
+  MpRange nvtx("monoport_b200: F3' visible surface");
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = (long long)R * R;
   size_t sums_off = 0;
@@ -46,26 +47,19 @@ extern "C" int mp_forward_vertices(const float* vol_dev, int R, int direction, i
                                    float* z_dev, float* norm_dev, int64_t* n_out, void* stream) {
   MP_REQUIRE(vol_dev && x_dev && y_dev && z_dev && norm_dev && n_out, "NULL argument");
   MP_REQUIRE(R >= 2 && R <= 2048, "bad R=%d", R);
-  MP_REQUIRE(direction >= 0 && direction <= 3, "bad direction %d", direction);
   cudaStream_t st = (cudaStream_t)stream;
-  const long long n = (long long)R * R;
-  int32_t* first_t = nullptr;
-  unsigned long long* sums = nullptr;
+  uint8_t* scratch = nullptr;
   mp_ensure_pool();
-  MP_CUDA(cudaMallocAsync(&first_t, n * sizeof(int32_t), st));
-  MP_CUDA(cudaMallocAsync(&sums, (size_t)(mpscan::num_blocks(n) + 3) * sizeof(unsigned long long), st));
-  unsigned long long* total = sums + mpscan::num_blocks(n) + 1;
-  cudaMemsetAsync(total + 1, 0, sizeof(unsigned long long), st);   // ticket counter of the scan
-  const int grid = (int)((n + 255) / 256);
-  first_hit_kernel<<<grid, 256, 0, st>>>(vol_dev, R, direction, first_t);
-  HitF f{first_t};
-  HitEmit em{vol_dev, first_t, R, direction, (long long*)x_dev, (long long*)y_dev, z_dev, norm_dev};
-  cudaError_t e = mpscan::scan_emit(f, em, n, sums, total, st);
-  unsigned long long tot = 0;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&tot, total, sizeof(tot), cudaMemcpyDeviceToHost, st);
-  cudaFreeAsync(first_t, st);
-  cudaFreeAsync(sums, st);
+  const size_t bytes = scratch_layout(R, nullptr) + 16;       // + the device-side count
+  MP_CUDA(cudaMallocAsync(&scratch, bytes, st));
+  int64_t* count_dev = reinterpret_cast<int64_t*>(scratch + bytes - 16);
+  int rc = mp_forward_vertices_async(vol_dev, R, direction, x_dev, y_dev, z_dev, norm_dev, count_dev, scratch, stream);
+  long long tot = 0;
+  cudaError_t e = cudaSuccess;
+  if (rc == MP_OK) e = cudaMemcpyAsync(&tot, count_dev, sizeof(tot), cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(scratch, st);                                  // (freed on every path)
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (rc != MP_OK) return rc;
   if (e != cudaSuccess) {
     mp_set_error("mp_forward_vertices: %s", cudaGetErrorString(e));
     return MP_E_CUDA;

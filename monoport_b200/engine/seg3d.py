@@ -57,6 +57,11 @@ class _Seg3dBase(nn.Module):
         self._sharded = None
         self.last_stats = None
 
+    def __getstate__(self):          # engine workspaces / peer mappings are native and per-thread: a copy starts without them
+        d = dict(self.__dict__)
+        d["_handles"], d["_mapped"], d["_sharded"] = {}, [], None
+        return d
+
     def _new_handle(self, device):
         """A fresh engine workspace (mp_octree_t) with this engine's parameters."""
         n = len(self.resolutions)

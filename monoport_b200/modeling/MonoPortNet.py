@@ -85,6 +85,11 @@ class MonoPortNet(nn.Module):
         self.feature_cache = os.environ.get("MONOPORT_B200_FEATURE_CACHE", "0") == "1"
         self._feat_handles = {}
 
+    def __getstate__(self):          # feature handles are native, per-thread scratch: a copy starts without them
+        d = dict(self.__dict__)
+        d["_feat_handles"] = {}
+        return d
+
     # ---- encoder: stays PyTorch ---------------------------------------------------------------------------
     def filter(self, images, feat_prior=None):
         feats_stages = self.image_filter(images)

@@ -90,6 +90,14 @@ class SurfaceClassifier(nn.Module):
             self._applied_limit = self.tc_feature_limit
         return h
 
+    # native handles never travel with a copy: deepcopy / pickle / copy.copy drop them (rebuilt lazily on first use);
+    # sharing the pointer would end in two mp_mlp_destroy calls on it
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_handle"], d["_handle_key"] = None, None
+        d.pop("_applied_limit", None)
+        return d
+
     def tc_supported(self):
         return bool(_lib.load().mp_mlp_tc_supported(self.handle()))
 

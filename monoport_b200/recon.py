@@ -113,6 +113,10 @@ def reconstruction(net, cuda, calib_tensor, resolution, b_min, b_max, use_octree
     b_min_t = torch.as_tensor(np.asarray(b_min, dtype=np.float32)).view(3)
     b_max_t = torch.as_tensor(np.asarray(b_max, dtype=np.float32)).view(3)
     if use_octree:
+        if engine is None and (R < 3 or (R - 1) & (R - 2)):
+            raise ValueError("use_octree=True needs a resolution of 2^k+1 nodes per axis (17, 33, ..., 257, 513: RTL/main.py:187); "
+                             "got %d -- use %d, or the dense path (use_octree=False), which takes any resolution"
+                             % (R, (1 << max(1, (R - 1).bit_length())) + 1))
         if engine is None:
             from .engine import Seg3dLossless, make_query_func
             res = [R]

@@ -1,5 +1,6 @@
 """CPU: host-side logic -- drop-in import surface, encoder/state-dict compatibility, slab partition, MC table and
 octree oracle properties."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -179,3 +180,59 @@ def test_bench_reference_arm_contract():
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None and "workload" in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_binary_ply_round_trip(tmp_path):
+    """binary PLY dump of reconstruction() output; float32 coordinates and topology round-trip exactly."""
+    from monoport_b200.mesh_util import save_ply_mesh, load_ply_mesh
+    rng = np.random.default_rng(3)
+    V = rng.random((57, 3), dtype=np.float32) * 2 - 1
+    Fc = rng.integers(0, 57, size=(101, 3)).astype(np.int32)
+    C = rng.random((57, 3), dtype=np.float32)
+    p = str(tmp_path / "m.ply")
+    save_ply_mesh(p, torch.from_numpy(V), torch.from_numpy(Fc))
+    v, f, c = load_ply_mesh(p)
+    assert np.array_equal(v, V) and np.array_equal(f, Fc) and c is None
+    save_ply_mesh(p, V, Fc, C)
+    v, f, c = load_ply_mesh(p)
+    assert np.array_equal(v, V) and np.array_equal(f, Fc) and np.array_equal(c, np.rint(C * 255).astype(np.uint8))
+    assert open(p, "rb").read(3) == b"ply" and os.path.getsize(p) < 57 * 15 + 101 * 13 + 400
+    save_ply_mesh(p, np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32))        # empty mesh
+    v, f, c = load_ply_mesh(p)
+    assert v.shape == (0, 3) and f.shape == (0, 3)
+
+
+def test_modules_with_native_handles_copy_and_pickle():
+    """nn.Modules that cache ctypes handles must survive copy.deepcopy / pickle (the handles are dropped and
+    rebuilt lazily) and copy.copy must not share a handle that two __del__ calls would free twice."""
+    import copy
+    import pickle
+    from monoport_b200.modeling import PIFuNetG
+    from monoport_b200.engine import Seg3dLossless, make_query_func
+    net = PIFuNetG()
+    head = net.surface_classifier
+    head._handle, head._handle_key = object(), ("fake",)            # pretend a native handle exists (no GPU here)
+    net._feat_handles[("k",)] = object()
+    for clone in (copy.deepcopy(net), pickle.loads(pickle.dumps(net))):
+        assert clone.surface_classifier._handle is None and clone.surface_classifier._handle_key is None
+        assert clone._feat_handles == {}
+        assert torch.equal(clone.surface_classifier.filters[0].weight, head.filters[0].weight)
+    shallow_head = copy.copy(head)               # a NEW object: it must not carry the pointer the original will free
+    assert shallow_head._handle is None and shallow_head.filters is head.filters
+    assert copy.copy(net)._feat_handles == {}
+    head._handle, head._handle_key = None, None
+    net._feat_handles.clear()
+    b = np.array([[-1.0, -1.0, -1.0]], dtype=np.float32)
+    eng = Seg3dLossless(lambda **kw: None, b, -b, [9, 17], balance_value=0.5)
+    eng._handles[("k",)] = object()
+    c2 = copy.copy(eng)
+    assert c2._handles == {} and c2.resolutions == [9, 17]
+    eng._handles.clear()
+
+
+def test_reconstruction_rejects_even_octree_resolution():
+    """the coarse-to-fine pyramid needs 2^k+1 nodes per axis; an even resolution gets a clear error up front
+    instead of an assertion from inside the engine (the dense branch accepts any resolution)."""
+    from monoport_b200.recon import reconstruction
+    with pytest.raises(ValueError, match="2\\^k\\+1"):
+        reconstruction(object(), "cuda:0", None, 256, (-1, -1, -1), (1, 1, 1), use_octree=True, feats=[[torch.zeros(1, 1, 2, 2)]])

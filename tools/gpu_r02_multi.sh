@@ -1,13 +1,18 @@
 #!/bin/bash
-# Round 2, multi-GPU call (gpurun --gpus 2, then --gpus 8): the fused slab exchange against the NCCL all-gather.
-#   usage: bash tools/gpu_r02_multi.sh N
+# Round 2, multi-GPU call (gpurun --gpus N): range-sharded dense grid through the in-place NCCL all-gather and through the
+# fused peer-memory exchange, list-sharded octree engines; bench at N GPUs with both exchanges.   usage: bash tools/gpu_r02_multi.sh N
 N=${1:-2}
 mkdir -p gpurun_out
 T0=$SECONDS
-MONOPORT_B200_TEST_FUSED=1 timeout 400 python -m pytest tests/test_shard_multigpu.py -q -m gpu > gpurun_out/r02_pytest_multigpu.log 2>&1; echo "pytest multi-gpu rc=$? t=$((SECONDS-T0))s"; tail -3 gpurun_out/r02_pytest_multigpu.log
+timeout 600 python -m pytest tests/test_shard_multigpu.py -q -m gpu > gpurun_out/r02_pytest_multigpu_n${N}.log 2>&1; echo "pytest multi-gpu rc=$? t=$((SECONDS-T0))s"; tail -12 gpurun_out/r02_pytest_multigpu_n${N}.log
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 tools/shard_check.py --fused --octree 2>&1 | grep -E "rank 0|OK|Error|error" | tee gpurun_out/r02_shard_check_n${N}.txt
 for flag in "" "--fused-gather"; do
   tag=$([ -z "$flag" ] && echo nccl || echo fused)
-  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 10 --warmup 3 $flag \
-    > gpurun_out/r02_bench_n${N}_${tag}.json 2> gpurun_out/r02_bench_n${N}_${tag}.err; echo "bench N=$N $tag rc=$? t=$((SECONDS-T0))s"
-  python -c "import json; d=json.load(open('gpurun_out/r02_bench_n${N}_${tag}.json')); print('$tag', d['value'], d['ms_per_step'], d['e2e']['value'])" 2>/dev/null || tail -3 gpurun_out/r02_bench_n${N}_${tag}.err
+  timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 10 --warmup 3 $flag \
+    > gpurun_out/r02_bench_n${N}_${tag}.raw 2> gpurun_out/r02_bench_n${N}_${tag}.err; echo "bench N=$N $tag rc=$? t=$((SECONDS-T0))s"
+  grep '^{' gpurun_out/r02_bench_n${N}_${tag}.raw | tail -1 > gpurun_out/r02_bench_n${N}_${tag}.json
+  python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_n${N}_${tag}.json'))
+print('$tag', round(d['value'],1), round(d['ms_per_step'],3), 'kernel_ms', round(d['roofline']['kernel_ms'],3), 'e2e', round(d['e2e']['value'],1), 'vol ok', d['volume_matches_single_gpu'], 'parity', d['parity_max_abs'])
+print(json.dumps(d.get('recon'))[:1500]); print(d.get('configs4_dense513'))" 2>/dev/null || tail -5 gpurun_out/r02_bench_n${N}_${tag}.err
 done

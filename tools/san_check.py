@@ -30,4 +30,12 @@ sdf = eng(im_feat_list=[[feat.cuda()]], calib_tensor=cal)
 X, Y, Z, n = forward_vertices(sdf, "front")
 v, f = marching_cubes(sdf[0, 0])
 torch.cuda.synchronize()
-print("ok", X.numel(), v.shape, f.shape)
+# the colour head's tensor-core program incl. the fused direct rendering, and a frame outside the range guard's limit
+from monoport_b200.recon import colorization
+cW, cb = spec.make_weights(spec.C_CHANNELS, 5)
+netC = build_net("C", cW, cb)
+featC = spec.make_feat(512, 128, 128, 6, 0.5).cuda()
+img = colorization(netC, [[featC]], X, Y, Z, cal, resolution=33)
+big = net.query([[feat.cuda() * 60.0]], pts, calibs=cal)[0]
+torch.cuda.synchronize()
+print("ok", X.numel(), v.shape, f.shape, float(img.sum()), float(big.sum()))
