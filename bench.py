@@ -43,9 +43,11 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("MONOPORT_B200_MODE", "auto"), choices=["auto", "tc", "fp32"])
     ap.add_argument("--res", type=int, default=R_GRID)
-    ap.add_argument("--fused-gather", action="store_true", default=os.environ.get("MONOPORT_B200_FUSED_GATHER", "0") == "1",
-                    help="N>1: store the slab into every rank's volume from the kernel epilogue (peer memory) instead of "
-                         "the NCCL all-gather (experimental, opt-in)")
+    ap.add_argument("--exchange", default=os.environ.get("MONOPORT_B200_EXCHANGE", "auto"), choices=["auto", "nccl", "fused"],
+                    help="N>1, how the ranks' ranges become the volume on every rank: 'nccl' = one in-place all-gather, 'fused' = "
+                         "peer-memory stores from the kernel epilogue + a barrier; 'auto' = fused from 4 GPUs on (measured: 2 GPUs "
+                         "990 vs 977 Mpoints/s in favour of NCCL, 8 GPUs 4133 vs 4246 in favour of the fused exchange)")
+    ap.add_argument("--fused-gather", action="store_true", help="same as --exchange fused")
     ap.add_argument("--no-recon", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -262,7 +264,10 @@ def run_ours(args):
     sv = ShardedVolume(R, rank, world, dev)
     lin0, my_pts = sv.bounds[rank]
 
-    fused = bool(args.fused_gather and world > 1)
+    exchange = "fused" if args.fused_gather else args.exchange
+    if exchange == "auto":
+        exchange = "fused" if world >= 4 else "nccl"
+    fused = bool(exchange == "fused" and world > 1)
     peers = PeerVolumes(R, rank, world, dev) if fused else None
 
     def barrier():
@@ -506,7 +511,7 @@ def bench_recon(args, net, feats, cal, cal_cpu, dev, rank, world, barrier):
         X, Y, Z, nrm = state["fv"]
         v, fcs = state["mesh"]
         # the same frame as ONE CUDA-graph launch (pipeline.FrameGraph), one and two lanes
-        for lanes in (1, 2):
+        for lanes in (1, 2, 4):
             ring = FrameGraphRing(lambda: FrameGraph(net, eng, cal_cpu, "front", with_encoder=False), n_lanes=lanes)
             list(ring.run(feats[i % 4] for i in range(4)))
             torch.cuda.synchronize()
@@ -540,7 +545,7 @@ def bench_recon(args, net, feats, cal, cal_cpu, dev, rank, world, barrier):
     frames = [(torch.rand(1, 3, 512, 512, generator=gI) * 2 - 1).to(dev) for _ in range(4)]
     hook = _person_hook(feats[0][:, 0].clone())
     stream = {}
-    for lanes in (1, 2):
+    for lanes in (1, 2, 3):
         ring = FrameGraphRing(lambda: FrameGraph(net, eng, cal_cpu, "front", with_encoder=True, feature_hook=hook), n_lanes=lanes)
         list(ring.run(frames[i % 4] for i in range(4)))
         barrier()

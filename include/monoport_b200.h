@@ -87,6 +87,10 @@ int mp_feat_create(int C, int H, int W, mp_feat_t** out);
 int mp_feat_upload(mp_feat_t* h, const float* nchw, int on_device, void* stream);
 /* same for a map that is already channel-last ([H,W,C] fp32, device memory -- a torch.channels_last tensor): one copy, no
  * transposing kernel */
+/* Zero-copy variant: the handle reads the caller's channel-last [H,W,C] fp32 device map IN PLACE for this frame (what a
+ * channels_last encoder emits, HGFilters.py:158-159 / RTL/main.py:382-387: no repack kernel, no copy).  The memory must stay
+ * valid and unchanged until the frame's queries have completed; the next upload / bind replaces the binding. */
+int mp_feat_bind_nhwc(mp_feat_t* h, const float* nhwc_dev, void* stream);
 int mp_feat_upload_nhwc(mp_feat_t* h, const float* nhwc_dev, void* stream);
 int mp_feat_destroy(mp_feat_t* h);
 

@@ -37,6 +37,7 @@ SIGNATURES = {
     "mp_feat_create": (c_int, [c_int, c_int, c_int, P(c_void_p)]),
     "mp_feat_upload": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "mp_feat_upload_nhwc": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "mp_feat_bind_nhwc": (c_int, [c_void_p, c_void_p, c_void_p]),
     "mp_feat_destroy": (c_int, [c_void_p]),
     "mp_query_points": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, P(c_float), c_int, c_float,
                                 c_void_p, c_int64, c_int, c_void_p]),

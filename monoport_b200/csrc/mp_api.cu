@@ -158,7 +158,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restr
 
 extern "C" int mp_feat_destroy(mp_feat_t* h) {
   if (!h) return MP_OK;
-  if (h->nhwc32) cudaFree(h->nhwc32);
+  if (h->nhwc_own) cudaFree(h->nhwc_own);
   if (h->staging) cudaFree(h->staging);
   if (h->g0) cudaFree(h->g0);
   if (h->f16) cudaFree(h->f16);
@@ -177,7 +177,8 @@ extern "C" int mp_feat_create(int C, int H, int W, mp_feat_t** out) {
   h->C = C; h->H = H; h->W = W;
   cudaGetDevice(&h->device);
   const size_t n = (size_t)C * H * W;
-  cudaError_t e = cudaMalloc(&h->nhwc32, n * sizeof(float));
+  cudaError_t e = cudaMalloc(&h->nhwc_own, n * sizeof(float));
+  h->nhwc32 = h->nhwc_own;
   if (e == cudaSuccess) e = cudaMalloc(&h->staging, n * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&h->amax, sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMemset(h->amax, 0, sizeof(unsigned));
@@ -202,6 +203,7 @@ extern "C" int mp_feat_upload(mp_feat_t* h, const float* nchw, int on_device, vo
   }
   const int HW = h->H * h->W;
   dim3 grid((HW + 31) / 32, (h->C + 31) / 32), block(32, 8);
+  h->nhwc32 = h->nhwc_own;
   nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(src, h->nhwc32, h->C, HW);
   MP_CUDA(cudaGetLastError());
   MP_CUDA(cudaMemsetAsync(h->amax, 0, sizeof(unsigned), st));
@@ -214,7 +216,19 @@ extern "C" int mp_feat_upload(mp_feat_t* h, const float* nchw, int on_device, vo
 extern "C" int mp_feat_upload_nhwc(mp_feat_t* h, const float* nhwc_dev, void* stream) {
   MP_REQUIRE(h && nhwc_dev, "NULL handle or data");
   const size_t n = (size_t)h->C * h->H * h->W;
+  h->nhwc32 = h->nhwc_own;
   MP_CUDA(cudaMemcpyAsync(h->nhwc32, nhwc_dev, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  MP_CUDA(cudaMemsetAsync(h->amax, 0, sizeof(unsigned), (cudaStream_t)stream));
+  h->version += 1;
+  return MP_OK;
+}
+
+// Zero-copy hand-off: the kernels read the caller's channel-last map in place -- no repack, no copy.  The
+// memory must stay valid and unchanged until the queries of this frame have completed (the binding keeps the tensor alive).
+extern "C" int mp_feat_bind_nhwc(mp_feat_t* h, const float* nhwc_dev, void* stream) {
+  MP_REQUIRE(h && nhwc_dev, "NULL handle or data");
+  MP_REQUIRE((reinterpret_cast<uintptr_t>(nhwc_dev) & 15) == 0, "the channel-last map must be 16-byte aligned");
+  h->nhwc32 = const_cast<float*>(nhwc_dev);
   MP_CUDA(cudaMemsetAsync(h->amax, 0, sizeof(unsigned), (cudaStream_t)stream));
   h->version += 1;
   return MP_OK;

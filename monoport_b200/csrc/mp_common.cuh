@@ -83,7 +83,9 @@ struct mp_mlp {
 
 struct mp_feat {
   int C, H, W;
-  float* nhwc32;    // [H][W][C] fp32 (one bilinear tap = one contiguous C*4-byte vector)
+  float* nhwc32;    // [H][W][C] fp32 (one bilinear tap = one contiguous C*4-byte vector): the CURRENT map -- the handle's own
+                    // repacked copy (nhwc_own) or, after mp_feat_bind_nhwc, the caller's channel-last tensor itself
+  float* nhwc_own;
   float* staging;   // [C][H][W] device staging for host uploads
   int device;
   // layer-0 pre-activation per texel, G0 = W0[:, :C] . F  ([H*W][g0_n] fp16), built lazily by the tcgen05 v3 path

@@ -45,9 +45,10 @@ class FeatureHandle:
         f = feat.detach()
         if (f.dtype == torch.float32 and f.shape[1] > 1 and not f.is_contiguous()
                 and f.is_contiguous(memory_format=torch.channels_last)):
-            # a channels_last encoder already emits [H,W,C]: copy, do not transpose
-            _lib.check(_lib.load().mp_feat_upload_nhwc(self.ptr, ctypes.c_void_p(f.data_ptr()), _lib.stream_ptr(self.device)),
-                       "mp_feat_upload_nhwc")
+            # a channels_last encoder already emits [H,W,C]: the kernels read it in place -- no repack, no copy (SURVEY.md
+            # §8f-3).  `_src` below keeps the tensor alive for the frame.
+            _lib.check(_lib.load().mp_feat_bind_nhwc(self.ptr, ctypes.c_void_p(f.data_ptr()), _lib.stream_ptr(self.device)),
+                       "mp_feat_bind_nhwc")
         else:
             if f.dtype != torch.float32 or not f.is_contiguous():
                 f = f.to(torch.float32).contiguous()

@@ -151,6 +151,7 @@ int main(int argc, char** argv) {
     src.kind = MP_SRC_GRID;
     fill_grid_geom(src, R, 1, R);
     src.z0 = z0;
+    src.lin0 = (long long)z0 * R * R;      // (what mp_api.cu's query_grid_range sets up)
     src.n = (long long)nz * R * R;
     n_out = src.n;
   } else if (!strcmp(src_kind, "nodes")) {

@@ -247,6 +247,25 @@ def test_channels_last_feature_map_gives_identical_results():
         a = net.query([[feat]], pts, calibs=cal)[0].clone()
         b = net.query([[feat_cl]], pts, calibs=cal)[0].clone()
         assert torch.equal(a, b), mode
+        # ... and against the reference's golden output, not only against the other CUDA path
+        tol = TOL[mode]
+        assert (b[0].cpu() - c["expected"][:, :3000]).abs().max().item() <= tol, mode
+    # the channel-last map is read IN PLACE (mp_feat_bind_nhwc): a write into it is seen by the next query without any upload
+    net.precision = "fp32"
+    net.feature_cache = True
+    before = net.query([[feat_cl]], pts, calibs=cal)[0].clone()
+    feat_cl.mul_(0.5)
+    torch.cuda.synchronize()
+    net.invalidate_features()
+    after = net.query([[feat_cl]], pts, calibs=cal)[0]
+    want = net.query([[(feat * 0.5)]], pts, calibs=cal)[0]
+    assert torch.equal(after, want) and not torch.equal(before, after)
+    # an encoder converted to channels_last hands its last-stage map over in that layout
+    net.image_filter.cuda().to(memory_format=torch.channels_last)
+    with torch.no_grad():
+        img = torch.rand(1, 3, 512, 512, device="cuda").contiguous(memory_format=torch.channels_last)
+        fmap = net.filter(img)[-1][0]
+    assert fmap.is_contiguous(memory_format=torch.channels_last) and not fmap.is_contiguous()
 
 
 def test_head_weight_change_invalidates_per_feature_cache():
