@@ -7,7 +7,7 @@
 //         classify_words_kernel (one thread per 32-node word of the bit volume: edge masks + triangle count; words with no
 //         surface inside leave after a dozen cached loads) -> ordered scan of (verts, tris) per word packed in one
 //         uint64 -> exclusive prefix per word -> totals.
-// emit :  mesh_emit_kernel, a warp per word with a surface inside, a lane per node: vertices from the volume (two loads
+// emit :  mesh_emit_kernel, a warp per word with a surface inside (an unordered active list left by the scan), a lane per node: vertices from the volume (two loads
 //         per vertex), faces from the table; the vertex id behind a face corner is the owning word's prefix + popcounts.
 // Workspace: 1 bit + 24 B per 32 nodes (15 MB at 257^3; the round-1 byte-per-node design took 102 MB).
 #include "mp_common.cuh"
@@ -23,6 +23,9 @@ struct mp_mcubes {
   uint32_t* bits;
   WordInfo* info;
   unsigned long long* prefix;
+  uint32_t* active;            // words with a surface inside (unordered), filled by the scan's emit half
+  uint32_t* n_active_dev;
+  uint32_t n_active;
   unsigned long long* sums;
   unsigned long long* total;
   long long nv, nf;
@@ -34,6 +37,8 @@ extern "C" int mp_mcubes_destroy(mp_mcubes_t* h) {
   if (h->bits) cudaFree(h->bits);
   if (h->info) cudaFree(h->info);
   if (h->prefix) cudaFree(h->prefix);
+  if (h->active) cudaFree(h->active);
+  if (h->n_active_dev) cudaFree(h->n_active_dev);
   if (h->sums) cudaFree(h->sums);
   if (h->total) cudaFree(h->total);
   delete h;
@@ -54,6 +59,8 @@ extern "C" int mp_mcubes_create(int D, int H, int W, mp_mcubes_t** out) {
   if (e == cudaSuccess) e = cudaMemset(h->bits, 0, bit_words * sizeof(uint32_t));     // the padding stays zero for ever
   if (e == cudaSuccess) e = cudaMalloc(&h->info, (size_t)h->n_words * sizeof(WordInfo));
   if (e == cudaSuccess) e = cudaMalloc(&h->prefix, (size_t)h->n_words * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&h->active, (size_t)h->n_words * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->n_active_dev, sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->sums, (size_t)(mpscan::num_blocks(h->n_words) + 1) * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&h->total, 2 * sizeof(unsigned long long));                 // [0] total, [1] scan ticket
   if (e == cudaSuccess) e = cudaMemset(h->total, 0, 2 * sizeof(unsigned long long));
@@ -89,11 +96,13 @@ extern "C" int mp_mcubes_count(mp_mcubes_t* h, const float* vol_dev, float iso, 
   }
   classify_words_kernel<<<(unsigned)((h->n_words + 255) / 256), 256, 0, st>>>(h->bits, h->info, h->n, h->D, h->H, h->W);
   MP_CUDA(cudaGetLastError());
+  MP_CUDA(cudaMemsetAsync(h->n_active_dev, 0, sizeof(uint32_t), st));
   WordCountF f{h->info};
-  PrefixEmit em{h->prefix};
+  PrefixEmit em{h->prefix, h->active, h->n_active_dev};
   MP_CUDA(mpscan::scan_emit(f, em, h->n_words, h->sums, h->total, st));
   unsigned long long tot = 0;
   MP_CUDA(cudaMemcpyAsync(&tot, h->total, sizeof(tot), cudaMemcpyDeviceToHost, st));
+  MP_CUDA(cudaMemcpyAsync(&h->n_active, h->n_active_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   MP_CUDA(cudaStreamSynchronize(st));
   h->nv = (long long)(tot & 0xffffffffull);
   h->nf = (long long)(tot >> 32);
@@ -111,12 +120,11 @@ extern "C" int mp_mcubes_emit(mp_mcubes_t* h, const float* vol_dev, float iso, f
   MP_REQUIRE(verts_dev && faces_dev, "NULL output buffers");
   MpRange nvtx("monoport_b200: F3 marching cubes (emit)");
   cudaStream_t st = (cudaStream_t)stream;
-  const long long n_groups = (h->n_words + 31) >> 5;
-  const long long blocks_needed = (n_groups + kEmitThreads / 32 - 1) / (kEmitThreads / 32);
-  // one warp per 32 words: every warp that finds a surface inside its words works through a chain of dependent L2
-  // accesses, so the more warps the better (no grid cap: 2 073 CTAs at 257^3)
-  mesh_emit_kernel<<<(unsigned)blocks_needed, kEmitThreads, 0, st>>>(
-      vol_dev, h->bits, h->info, h->prefix, verts_dev, faces_dev, h->D, h->H, h->W, h->n, iso);
+  // one warp per word with a surface inside (the active list the count pass left behind)
+  const long long blocks_needed = ((long long)h->n_active + kEmitThreads / 32 - 1) / (kEmitThreads / 32);
+  if (blocks_needed > 0)
+    mesh_emit_kernel<<<(unsigned)blocks_needed, kEmitThreads, 0, st>>>(vol_dev, h->bits, h->info, h->prefix, h->active, h->n_active,
+                                                                     verts_dev, faces_dev, h->D, h->H, h->W, h->n, iso);
   MP_CUDA(cudaGetLastError());
   return MP_OK;
 }

@@ -120,9 +120,17 @@ struct WordCountF {    // low 32: vertices owned by the word's nodes, high 32: t
   }
 };
 
-struct PrefixEmit {    // exclusive (vertex, triangle) prefix of every word
+// exclusive (vertex, triangle) prefix of every word; words with a surface inside are also appended to the ACTIVE LIST the
+// emission walks (one warp per entry).  The list's order is whatever the atomics give -- it does not matter: every word
+// carries its own output offsets, so the mesh is the same for any order.
+struct PrefixEmit {
   unsigned long long* prefix;
-  __device__ void operator()(long long w, unsigned long long, unsigned long long pre) const { prefix[w] = pre; }
+  uint32_t* active;            // [n_words] word indices
+  uint32_t* n_active;          // zeroed before the scan
+  __device__ void operator()(long long w, unsigned long long v, unsigned long long pre) const {
+    prefix[w] = pre;
+    if (v) active[atomicAdd(n_active, 1u)] = (uint32_t)w;
+  }
 };
 
 // id of the vertex on the +`axis` edge owned by node i (the edge must be active)
@@ -138,92 +146,79 @@ __device__ __forceinline__ int32_t vertex_id(const WordInfo* __restrict__ info, 
   return (int32_t)id;
 }
 
-// ---- pass 4: emission.  A warp takes 32 words at a time, keeps those with vertices or triangles, and handles each of
-// them with one lane per node: up to three vertices (vertex id = rank of (node, axis) in node order) and up to
-// MC_MAX_TRI triangles (face order = (cell linear index, table order); their offsets come from a warp scan).
+// ---- pass 4: emission.  One warp per word with a surface inside (the active list), one lane per node: up to three
+// vertices (vertex id = rank of (node, axis) in node order) and up to MC_MAX_TRI triangles (face order = (cell linear
+// index, table order); their offsets come from a warp scan).  Walking 32 consecutive words per warp instead left most warps
+// with nothing and a few with a dozen dependent chains in a row (63 us at 257^3).
 constexpr int kEmitThreads = 256;
 __global__ void __launch_bounds__(kEmitThreads)
 mesh_emit_kernel(const float* __restrict__ vol, const uint32_t* __restrict__ bits, const WordInfo* __restrict__ info,
-                 const unsigned long long* __restrict__ prefix, float* __restrict__ verts, int32_t* __restrict__ faces, int D,
-                 int H, int W, long long n, float iso) {
-  const long long n_words = (n + 31) >> 5;
-  const long long n_groups = (n_words + 31) >> 5;
+                 const unsigned long long* __restrict__ prefix, const uint32_t* __restrict__ active, uint32_t n_active,
+                 float* __restrict__ verts, int32_t* __restrict__ faces, int D, int H, int W, long long n, float iso) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (kEmitThreads / 32) + (threadIdx.x >> 5);
   const long long n_warps = (long long)gridDim.x * (kEmitThreads / 32);
   const int plane = H * W;
-  for (long long g = warp0; g < n_groups; g += n_warps) {                       // (warp-uniform trip count)
-    const long long wl = g * 32 + lane;
-    uint4 mine = make_uint4(0u, 0u, 0u, 0u);
-    unsigned long long mypre = 0;
-    if (wl < n_words) {
-      mine = __ldg(reinterpret_cast<const uint4*>(info + wl));
-      mypre = __ldg(prefix + wl);
+  for (long long e = warp0; e < (long long)n_active; e += n_warps) {             // (warp-uniform trip count)
+    const long long w = (long long)__ldg(active + e);
+    const uint4 wi = __ldg(reinterpret_cast<const uint4*>(info + w));
+    const uint32_t ex = wi.x, ey = wi.y, ez = wi.z, nt = wi.w;
+    const unsigned long long pre = __ldg(prefix + w);
+    const long long i = 32 * w + lane;                                          // this lane's node
+    const int z = (int)(i / plane), r = (int)(i - (long long)z * plane), y = r / W, x = r - y * W;
+    // ---- vertices on the owned edges
+    const uint32_t below = (1u << lane) - 1u;
+    const uint32_t code = ((ex >> lane) & 1u) | (((ey >> lane) & 1u) << 1) | (((ez >> lane) & 1u) << 2);
+    if (code) {
+      uint32_t vi = (uint32_t)pre + __popc(ex & below) + __popc(ey & below) + __popc(ez & below);
+      const float va = __ldg(vol + i);
+#pragma unroll
+      for (int axis = 0; axis < 3; ++axis) {
+        if (!((code >> axis) & 1u)) continue;
+        const long long step = axis == 0 ? 1 : (axis == 1 ? W : plane);
+        const float vb = __ldg(vol + i + step);
+        const float t = __fdiv_rn(__fsub_rn(iso, va), __fsub_rn(vb, va));
+        float p[3] = {(float)x, (float)y, (float)z};
+        p[axis] = __fadd_rn(p[axis], t);
+        float* o = verts + 3ll * vi;
+        o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+        ++vi;
+      }
     }
-    uint32_t active = __ballot_sync(0xffffffffu, (mine.x | mine.y | mine.z | mine.w) != 0u);
-    while (active) {                                                            // (warp-uniform)
-      const int src = __ffs((int)active) - 1;
-      active &= active - 1;
-      const long long w = g * 32 + src;
-      const uint32_t ex = __shfl_sync(0xffffffffu, mine.x, src), ey = __shfl_sync(0xffffffffu, mine.y, src);
-      const uint32_t ez = __shfl_sync(0xffffffffu, mine.z, src), nt = __shfl_sync(0xffffffffu, mine.w, src);
-      const unsigned long long pre = __shfl_sync(0xffffffffu, mypre, src);
-      const long long i = 32 * w + lane;                                        // this lane's node
-      const int z = (int)(i / plane), r = (int)(i - (long long)z * plane), y = r / W, x = r - y * W;
-      // ---- vertices on the owned edges
-      const uint32_t below = (1u << lane) - 1u;
-      const uint32_t code = ((ex >> lane) & 1u) | (((ey >> lane) & 1u) << 1) | (((ez >> lane) & 1u) << 2);
-      if (code) {
-        uint32_t vi = (uint32_t)pre + __popc(ex & below) + __popc(ey & below) + __popc(ez & below);
-        const float va = __ldg(vol + i);
+    // ---- triangles of the cell whose corner 0 is this node
+    if (nt) {                                                                   // (warp-uniform)
+      uint32_t v[8];
+      corner_words(bits, w, H, W, v);
+      const bool cell = i < n && x + 1 < W && y + 1 < H && z + 1 < D;
+      const int k = cell ? case_of(v, lane) : 0;
+      // one 16-byte load: bytes 0..14 = edge ids of the cell's triangles, byte 15 = their number
+      const uint4 row = __ldg(reinterpret_cast<const uint4*>(&g_mc_tri[k][0]));
+      const uint32_t rw[4] = {row.x, row.y, row.z, row.w};
+      const int mytri = (int)(row.w >> 24);
+      // exclusive warp scan of the triangle counts
+      unsigned long long incl = mpscan::warp_incl_scan((unsigned long long)mytri, lane);
+      const uint32_t foff = (uint32_t)(pre >> 32) + (uint32_t)incl - (uint32_t)mytri;
+      // all vertex-id lookups of the cell are issued before the first store (independent loads in flight instead of
+      // one L2 round trip per face corner)
+      int32_t ids[3 * MC_MAX_TRI];
 #pragma unroll
-        for (int axis = 0; axis < 3; ++axis) {
-          if (!((code >> axis) & 1u)) continue;
-          const long long step = axis == 0 ? 1 : (axis == 1 ? W : plane);
-          const float vb = __ldg(vol + i + step);
-          const float t = __fdiv_rn(__fsub_rn(iso, va), __fsub_rn(vb, va));
-          float p[3] = {(float)x, (float)y, (float)z};
-          p[axis] = __fadd_rn(p[axis], t);
-          float* o = verts + 3ll * vi;
-          o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
-          ++vi;
+      for (int corner = 0; corner < 3 * MC_MAX_TRI; ++corner) {
+        ids[corner] = 0;
+        if (corner < 3 * mytri) {
+          const int ed = (int)((rw[corner >> 2] >> (8 * (corner & 3))) & 0xFFu);
+          // edge -> owning node + axis.  edges 0-3 along x at (y,z) offsets, 4-7 along y at (x,z), 8-11 along z at (x,y)
+          const int axis = ed >> 2, q = ed & 3;
+          int ox = 0, oy = 0, oz = 0;
+          if (axis == 0) { oy = q & 1; oz = q >> 1; }
+          else if (axis == 1) { ox = q & 1; oz = q >> 1; }
+          else { ox = q & 1; oy = q >> 1; }
+          const long long node = i + ((long long)oz * H + oy) * W + ox;
+          ids[corner] = vertex_id(info, prefix, node, axis);
         }
       }
-      // ---- triangles of the cell whose corner 0 is this node
-      if (nt) {                                                                 // (warp-uniform)
-        uint32_t v[8];
-        corner_words(bits, w, H, W, v);
-        const bool cell = i < n && x + 1 < W && y + 1 < H && z + 1 < D;
-        const int k = cell ? case_of(v, lane) : 0;
-        // one 16-byte load: bytes 0..14 = edge ids of the cell's triangles, byte 15 = their number
-        const uint4 row = __ldg(reinterpret_cast<const uint4*>(&g_mc_tri[k][0]));
-        const uint32_t rw[4] = {row.x, row.y, row.z, row.w};
-        const int mytri = (int)(row.w >> 24);
-        // exclusive warp scan of the triangle counts
-        unsigned long long incl = mpscan::warp_incl_scan((unsigned long long)mytri, lane);
-        const uint32_t foff = (uint32_t)(pre >> 32) + (uint32_t)incl - (uint32_t)mytri;
-        // all vertex-id lookups of the cell are issued before the first store (independent loads in flight instead of
-        // one L2 round trip per face corner)
-        int32_t ids[3 * MC_MAX_TRI];
 #pragma unroll
-        for (int corner = 0; corner < 3 * MC_MAX_TRI; ++corner) {
-          ids[corner] = 0;
-          if (corner < 3 * mytri) {
-            const int ed = (int)((rw[corner >> 2] >> (8 * (corner & 3))) & 0xFFu);
-            // edge -> owning node + axis.  edges 0-3 along x at (y,z) offsets, 4-7 along y at (x,z), 8-11 along z at (x,y)
-            const int axis = ed >> 2, q = ed & 3;
-            int ox = 0, oy = 0, oz = 0;
-            if (axis == 0) { oy = q & 1; oz = q >> 1; }
-            else if (axis == 1) { ox = q & 1; oz = q >> 1; }
-            else { ox = q & 1; oy = q >> 1; }
-            const long long node = i + ((long long)oz * H + oy) * W + ox;
-            ids[corner] = vertex_id(info, prefix, node, axis);
-          }
-        }
-#pragma unroll
-        for (int corner = 0; corner < 3 * MC_MAX_TRI; ++corner)
-          if (corner < 3 * mytri) faces[3ll * foff + corner] = ids[corner];
-      }
+      for (int corner = 0; corner < 3 * MC_MAX_TRI; ++corner)
+        if (corner < 3 * mytri) faces[3ll * foff + corner] = ids[corner];
     }
   }
 }

@@ -58,8 +58,10 @@ int main(int argc, char** argv) {
     if (bits[w] != 0u) { fprintf(stderr, "wrote into the bit padding\n"); return 3; }
   cuda_emu::launch(dim3((unsigned)((n_words + 255) / 256)), dim3(256),
                    [&] { classify_words_kernel(bits.data(), info.data(), n, D, H, W); });
+  std::vector<uint32_t> active(n_words + 4, 0xABABABABu);
+  uint32_t n_active = 0;
   WordCountF f{info.data()};
-  PrefixEmit em{prefix.data()};
+  PrefixEmit em{prefix.data(), active.data(), &n_active};
   cuda_emu::launch(dim3(nb), dim3(mpscan::kThreads),
                    [&] { mpscan::block_sums_kernel<WordCountF, mpscan::NoPost>(f, n_words, sums.data(), nb, total, mpscan::NoPost()); });
   cuda_emu::launch(dim3(nb), dim3(mpscan::kThreads),
@@ -71,13 +73,15 @@ int main(int argc, char** argv) {
   std::vector<float> verts((size_t)nv * 3 + 1, -12345.f);
   std::vector<int32_t> faces((size_t)nf * 3 + 1, -7);
   if (nv || nf) {
-    const long long n_groups = (n_words + 31) >> 5;
-    long long blocks = (n_groups + kEmitThreads / 32 - 1) / (kEmitThreads / 32);
-    if (blocks > 2) blocks = 2;
-    cuda_emu::launch(dim3((unsigned)blocks), dim3(kEmitThreads), [&] {
-      mesh_emit_kernel(vol, bits.data(), info.data(), prefix.data(), verts.data(), faces.data(), D, H, W, n, iso);
-    });
+    long long blocks = ((long long)n_active + kEmitThreads / 32 - 1) / (kEmitThreads / 32);
+    if (blocks > 2) blocks = 2;                       // force the grid-stride loop
+    if (blocks > 0)
+      cuda_emu::launch(dim3((unsigned)blocks), dim3(kEmitThreads), [&] {
+        mesh_emit_kernel(vol, bits.data(), info.data(), prefix.data(), active.data(), n_active, verts.data(), faces.data(), D, H, W, n, iso);
+      });
   }
+  for (long long w = n_words; w < n_words + 4; ++w)
+    if (active[w] != 0xABABABABu) { fprintf(stderr, "wrote past the active list\n"); return 3; }
   if (verts[(size_t)nv * 3] != -12345.f || faces[(size_t)nf * 3] != -7) { fprintf(stderr, "wrote past the outputs\n"); return 3; }
   for (long long w = n_words; w < n_words + 4; ++w)
     if (info[w].ex != 0xEEEEEEEEu || prefix[w] != 0xDEADBEEFDEADBEEFull) { fprintf(stderr, "wrote past the word arrays\n"); return 3; }
