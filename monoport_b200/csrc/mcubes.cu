@@ -4,11 +4,12 @@
 //   vertex id = rank of (node, axis) among active owned edges (every grid edge is owned by its lower node);
 //   face order = (cell linear index, table order).
 // count:  bits_kernel (THE read of the volume: 4 B per node in, one occupancy bit per node out, streaming) ->
-//         classify_words_kernel (one thread per 32-node word of the bit volume: edge masks + triangle count; words with no
-//         surface inside leave after a dozen cached loads) -> ordered scan of (verts, tris) per word packed in one
-//         uint64 -> exclusive prefix per word -> totals.
-// emit :  mesh_emit_kernel, a warp per word with a surface inside (an unordered active list left by the scan), a lane per node: vertices from the volume (two loads
-//         per vertex), faces from the table; the vertex id behind a face corner is the owning word's prefix + popcounts.
+//         ordered scan over the 32-node words of the bit volume, (verts, tris) packed in one uint64.  Its first pass
+//         CLASSIFIES each word on the way (classify_word: edge masks + triangle count; words with no surface inside leave
+//         after a dozen cached loads), its second pass leaves the exclusive prefix per word, the totals, and an unordered
+//         list of the words with a surface inside.
+// emit :  mesh_emit_kernel, a warp per listed word, a lane per node: vertices from the volume (two loads per vertex), faces
+//         from the table; the ids of the vertices on a cell's 12 edges are popcounts over warp-uniform (info, prefix) words.
 // Workspace: 1 bit + 24 B per 32 nodes (15 MB at 257^3; the round-1 byte-per-node design took 102 MB).
 #include "mp_common.cuh"
 #include <stdlib.h>
@@ -94,12 +95,12 @@ extern "C" int mp_mcubes_count(mp_mcubes_t* h, const float* vol_dev, float iso, 
     const long long cap = (long long)sm_count() * 8;
     bits_kernel<<<(unsigned)(blocks_needed < cap ? blocks_needed : cap), kBitsThreads, 0, st>>>(vol_dev, h->bits, h->n, iso);
   }
-  classify_words_kernel<<<(unsigned)((h->n_words + 255) / 256), 256, 0, st>>>(h->bits, h->info, h->n, h->D, h->H, h->W);
   MP_CUDA(cudaGetLastError());
   MP_CUDA(cudaMemsetAsync(h->n_active_dev, 0, sizeof(uint32_t), st));
-  WordCountF f{h->info};
+  ClassifyCountF f1{h->bits, h->info, h->n, h->D, h->H, h->W};
+  WordCountF f2{h->info};
   PrefixEmit em{h->prefix, h->active, h->n_active_dev};
-  MP_CUDA(mpscan::scan_emit(f, em, h->n_words, h->sums, h->total, st));
+  MP_CUDA(mpscan::scan_emit2(f1, f2, em, h->n_words, h->sums, h->total, st));
   unsigned long long tot = 0;
   MP_CUDA(cudaMemcpyAsync(&tot, h->total, sizeof(tot), cudaMemcpyDeviceToHost, st));
   MP_CUDA(cudaMemcpyAsync(&h->n_active, h->n_active_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

@@ -73,12 +73,9 @@ struct WordInfo {
   uint32_t ex, ey, ez, nt;
 };
 
-// ---- pass 2: one thread per word.  Uniform words (all eight shifted copies equal) leave at once.
-__global__ void __launch_bounds__(256)
-classify_words_kernel(const uint32_t* __restrict__ bits, WordInfo* __restrict__ info, long long n, int D, int H, int W) {
-  const long long n_words = (n + 31) >> 5;
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= n_words) return;
+// ---- pass 2 (runs inside the scan's first pass): edge masks + triangle count of one word.  Uniform words (all eight
+// shifted copies equal) leave at once.
+__device__ __forceinline__ WordInfo classify_word(const uint32_t* __restrict__ bits, long long w, long long n, int D, int H, int W) {
   uint32_t v[8];
   corner_words(bits, w, H, W, v);
   uint32_t mixed = 0;
@@ -108,15 +105,34 @@ classify_words_kernel(const uint32_t* __restrict__ bits, WordInfo* __restrict__ 
       wi.nt += (uint32_t)__ldg(&g_mc_tri[case_of(v, b)][15]);      // byte 15 of a table row = its triangle count
     }
   }
-  info[w] = wi;
+  return wi;
 }
 
+__device__ __forceinline__ unsigned long long word_counts(const uint4 q) {
+  return (unsigned long long)(__popc(q.x) + __popc(q.y) + __popc(q.z)) | ((unsigned long long)q.w << 32);
+}
+
+// functor of the scan's FIRST pass: classifies the word, stores its info and returns its (vertex, triangle) counts
+struct ClassifyCountF {
+  const uint32_t* bits;
+  WordInfo* info;
+  long long n;
+  int D, H, W;
+  static constexpr bool kVec8 = false;
+  __device__ unsigned long long operator()(long long w) const {
+    const WordInfo wi = classify_word(bits, w, n, D, H, W);
+    *reinterpret_cast<uint4*>(info + w) = make_uint4(wi.ex, wi.ey, wi.ez, wi.nt);
+    return word_counts(make_uint4(wi.ex, wi.ey, wi.ez, wi.nt));
+  }
+};
+
+// functor of the scan's SECOND pass (and of everything after it): the stored info
 struct WordCountF {    // low 32: vertices owned by the word's nodes, high 32: triangles of its cells
   const WordInfo* info;
   static constexpr bool kVec8 = false;
   __device__ unsigned long long operator()(long long w) const {
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(info + w));
-    return (unsigned long long)(__popc(q.x) + __popc(q.y) + __popc(q.z)) | ((unsigned long long)q.w << 32);
+    // (plain load, not __ldg: the first pass of the same scan wrote it)
+    return word_counts(*reinterpret_cast<const uint4*>(info + w));
   }
 };
 
@@ -133,19 +149,6 @@ struct PrefixEmit {
   }
 };
 
-// id of the vertex on the +`axis` edge owned by node i (the edge must be active)
-__device__ __forceinline__ int32_t vertex_id(const WordInfo* __restrict__ info, const unsigned long long* __restrict__ prefix,
-                                             long long i, int axis) {
-  const long long w = i >> 5;
-  const int b = (int)(i & 31);
-  const uint4 q = __ldg(reinterpret_cast<const uint4*>(info + w));
-  const uint32_t below = (1u << b) - 1u;
-  uint32_t id = (uint32_t)__ldg(prefix + w) + __popc(q.x & below) + __popc(q.y & below) + __popc(q.z & below);
-  if (axis >= 1) id += (q.x >> b) & 1u;
-  if (axis == 2) id += (q.y >> b) & 1u;
-  return (int32_t)id;
-}
-
 // ---- pass 4: emission.  One warp per word with a surface inside (the active list), one lane per node: up to three
 // vertices (vertex id = rank of (node, axis) in node order) and up to MC_MAX_TRI triangles (face order = (cell linear
 // index, table order); their offsets come from a warp scan).  Walking 32 consecutive words per warp instead left most warps
@@ -155,6 +158,7 @@ __global__ void __launch_bounds__(kEmitThreads)
 mesh_emit_kernel(const float* __restrict__ vol, const uint32_t* __restrict__ bits, const WordInfo* __restrict__ info,
                  const unsigned long long* __restrict__ prefix, const uint32_t* __restrict__ active, uint32_t n_active,
                  float* __restrict__ verts, int32_t* __restrict__ faces, int D, int H, int W, long long n, float iso) {
+  __shared__ int32_t s_ids[kEmitThreads / 32][12][32];
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (kEmitThreads / 32) + (threadIdx.x >> 5);
   const long long n_warps = (long long)gridDim.x * (kEmitThreads / 32);
@@ -198,27 +202,44 @@ mesh_emit_kernel(const float* __restrict__ vol, const uint32_t* __restrict__ bit
       // exclusive warp scan of the triangle counts
       unsigned long long incl = mpscan::warp_incl_scan((unsigned long long)mytri, lane);
       const uint32_t foff = (uint32_t)(pre >> 32) + (uint32_t)incl - (uint32_t)mytri;
-      // all vertex-id lookups of the cell are issued before the first store (independent loads in flight instead of
-      // one L2 round trip per face corner)
-      int32_t ids[3 * MC_MAX_TRI];
+      // ---- ids of the vertices on the cell's 12 edges.  They live on 7 nodes in 4 node rows (dy, dz); the 32 cells of the
+      // warp take each row from at most two consecutive words, so (info, prefix) of those words are WARP-UNIFORM loads and
+      // every id is a few popcounts on registers -- not a 24-byte lookup per face corner.  The ids go through shared memory
+      // ([edge][lane], conflict-free) because the face corners index them by a run-time edge number.
+      int32_t* my_ids = s_ids[threadIdx.x >> 5][0];
+      const long long last_word = ((n + 31) >> 5) - 1;
 #pragma unroll
-      for (int corner = 0; corner < 3 * MC_MAX_TRI; ++corner) {
-        ids[corner] = 0;
-        if (corner < 3 * mytri) {
-          const int ed = (int)((rw[corner >> 2] >> (8 * (corner & 3))) & 0xFFu);
-          // edge -> owning node + axis.  edges 0-3 along x at (y,z) offsets, 4-7 along y at (x,z), 8-11 along z at (x,y)
-          const int axis = ed >> 2, q = ed & 3;
-          int ox = 0, oy = 0, oz = 0;
-          if (axis == 0) { oy = q & 1; oz = q >> 1; }
-          else if (axis == 1) { ox = q & 1; oz = q >> 1; }
-          else { ox = q & 1; oy = q >> 1; }
-          const long long node = i + ((long long)oz * H + oy) * W + ox;
-          ids[corner] = vertex_id(info, prefix, node, axis);
+      for (int rw4 = 0; rw4 < 4; ++rw4) {
+        const int oy = rw4 & 1, oz = rw4 >> 1;
+        const long long base = 32 * w + ((long long)oz * H + oy) * W;            // node of lane 0 in this row
+        const long long wa = min(base >> 5, last_word), wb = min((base >> 5) + 1, last_word);
+        const int sft = (int)(base & 31);
+        const uint4 qa = __ldg(reinterpret_cast<const uint4*>(info + wa)), qb = __ldg(reinterpret_cast<const uint4*>(info + wb));
+        const uint32_t pa = (uint32_t)__ldg(prefix + wa), pb = (uint32_t)__ldg(prefix + wb);
+#pragma unroll
+        for (int ox = 0; ox < 2; ++ox) {
+          if (ox == 1 && rw4 == 3) continue;                                     // node (1,1,1) owns none of the cell's edges
+          const int nb = sft + lane + ox;
+          const bool hi = nb >= 32;
+          const int bb = nb & 31;
+          const uint32_t qx = hi ? qb.x : qa.x, qy = hi ? qb.y : qa.y, qz = hi ? qb.z : qa.z;
+          const uint32_t bel = (1u << bb) - 1u;
+          const uint32_t r0 = (hi ? pb : pa) + __popc(qx & bel) + __popc(qy & bel) + __popc(qz & bel);   // id of its +x vertex
+          const uint32_t bx = (qx >> bb) & 1u, by = (qy >> bb) & 1u;
+          // edges 0-3: along x at (dy, dz); 4-7: along y at (dx, dz); 8-11: along z at (dx, dy)
+          if (ox == 0) my_ids[(0 + oy + 2 * oz) * 32 + lane] = (int32_t)r0;
+          if (oy == 0) my_ids[(4 + ox + 2 * oz) * 32 + lane] = (int32_t)(r0 + bx);
+          if (oz == 0) my_ids[(8 + ox + 2 * oy) * 32 + lane] = (int32_t)(r0 + bx + by);
         }
       }
+      __syncwarp();
 #pragma unroll
       for (int corner = 0; corner < 3 * MC_MAX_TRI; ++corner)
-        if (corner < 3 * mytri) faces[3ll * foff + corner] = ids[corner];
+        if (corner < 3 * mytri) {
+          const int ed = (int)((rw[corner >> 2] >> (8 * (corner & 3))) & 0xFFu);
+          faces[3ll * foff + corner] = my_ids[ed * 32 + lane];
+        }
+      __syncwarp();                                                              // (the next entry overwrites the ids)
     }
   }
 }

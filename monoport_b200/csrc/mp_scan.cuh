@@ -147,6 +147,16 @@ inline cudaError_t scan_emit(F f, E emit, long long n, unsigned long long* sums,
   if (n > 0) emit_kernel<F, E><<<nb, kThreads, 0, st>>>(f, emit, n, sums);
   return cudaGetLastError();
 }
+// The same with a different functor per pass: `first` may be expensive and may have side effects (it runs exactly once per
+// element), `second` must return the same values (typically it reads back what `first` stored).
+template <class F1, class F2, class E>
+inline cudaError_t scan_emit2(F1 first, F2 second, E emit, long long n, unsigned long long* sums, unsigned long long* total,
+                              cudaStream_t st) {
+  const int nb = num_blocks(n > 0 ? n : 1);
+  block_sums_kernel<F1, NoPost><<<nb, kThreads, 0, st>>>(first, n > 0 ? n : 0, sums, nb, total, NoPost());
+  if (n > 0) emit_kernel<F2, E><<<nb, kThreads, 0, st>>>(second, emit, n, sums);
+  return cudaGetLastError();
+}
 #endif  // __CUDACC__
 
 }  // namespace mpscan

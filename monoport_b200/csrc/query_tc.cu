@@ -262,9 +262,17 @@ __device__ __forceinline__ void warp_wait_cluster(uint64_t* bar, uint32_t parity
 // being the bound.  Everything per tile -- operands in shared / tensor memory, samplers, workers, epilogue -- stays local
 // to its CTA; the leader (rank 0) issues all MMAs, operand hand-offs are remote mbarrier arrivals on the leader's
 // barriers, MMA completions are multicast to both CTAs by tcgen05.commit.
-template <bool PEERS = false, int CG = 1>
+//
+// WM (opt-in, MONOPORT_B200_TC_WM=1; CG = 1 only): two INDEPENDENT one-CTA programs launched as a 2-CTA cluster that share
+// the weight stream: each CTA fetches half of every 32 KB stage and multicasts it into both shared memories
+// (cp.async.bulk ... .multicast::cluster), so the L2 serves each weight byte once per pair.  Everything else is CTA-local
+// (cta_group::1 MMAs); the only coupling is the ring: a slot is refilled when BOTH issuers have released it
+// (tcgen05.commit multicast onto both CTAs' "empty" barriers), so the two CTAs drift by at most the ring's three stages.
+template <bool PEERS = false, int CG = 1, bool WM = false>
 __global__ void __launch_bounds__(kThreads, 1)
 query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
+  static_assert(!(WM && CG == 2), "weight multicast is a variant of the one-CTA program");
+  constexpr int TP = (CG == 2 || WM) ? 2 : 1;          // tiles (CTAs) per scheduling group
   using C = CfgT<CG>;
   MP_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -289,17 +297,17 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
   const long long n_tiles = (win1 - win0 + kTile - 1) / kTile;
   // the unit of scheduling is a group of CG tiles (one per CTA of the pair); both CTAs run the same number of iterations, a
   // CTA whose tile lies beyond n_tiles computes on masked-out points
-  const long long n_groups = (n_tiles + CG - 1) / CG;
-  const long long g0 = blockIdx.x / CG, gstep = gridDim.x / CG;
-  const uint32_t rank = (CG == 2) ? tc::cluster_ctarank() : 0u;
-  const bool leader = rank == 0;
+  const long long n_groups = (n_tiles + TP - 1) / TP;
+  const long long g0 = blockIdx.x / TP, gstep = gridDim.x / TP;
+  const uint32_t rank = (TP == 2) ? tc::cluster_ctarank() : 0u;
+  const bool leader = CG == 1 || rank == 0;            // (who issues the MMAs: every CTA unless the pair shares them)
 
   constexpr uint32_t cAcc1 = 0, cH1lo = 0, cH1hi = 384, cAcc2 = 128, cH2 = 0, cAcc3 = 384;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       tc::mbar_init(bars + B_WFULL + s, 1);
-      tc::mbar_init(bars + B_WEMPTY + s, 1);
+      tc::mbar_init(bars + B_WEMPTY + s, WM ? 2 : 1);      // WM: released by both issuers of the pair
     }
     // operand hand-offs to the MMA issuer count one arrival per producing warp of EVERY CTA of the pair (they all arrive on
     // the leader's barriers); what the issuer hands back (tcgen05.commit) reaches both CTAs' own barriers
@@ -328,7 +336,7 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
     else { tc::tmem_alloc2(s_tmem, 512); tc::tmem_relinquish2(); }
   }
   tc::tcgen05_fence_before();
-  if constexpr (CG == 1) __syncthreads(); else tc::cluster_sync_all();
+  if constexpr (TP == 1) __syncthreads(); else tc::cluster_sync_all();
   tc::tcgen05_fence_after();
   const uint32_t tbase = *s_tmem;
   // an operand hand-off of a producing warp to the MMA issuer (which lives in the leader CTA)
@@ -349,6 +357,17 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
         for (int s = 0; s < kStagesPerTile3; ++s, ++it) {
           const int slot = it % C::Stages;
           const uint32_t use = it / C::Stages;
+          if constexpr (WM) {
+#ifndef MP_CUDA_EMU
+            // my half of the stage, into both CTAs; my barrier expects the whole stage (the other half comes from the peer)
+            tc::mbar_wait_cluster(bars + B_WEMPTY + slot, (use & 1u) ^ 1u);
+            tc::mbar_arrive_expect_tx(bars + B_WFULL + slot, C::StageBytes);
+            tc::bulk_g2s_multicast(smem + Smem::Wr + slot * C::StageBytes + rank * (C::StageBytes / 2),
+                                   wsrc + (size_t)s * C::StageBytes + rank * (C::StageBytes / 2), C::StageBytes / 2,
+                                   bars + B_WFULL + slot, (uint16_t)3);
+#endif
+            continue;
+          }
           tc::mbar_wait(bars + B_WEMPTY + slot, (use & 1u) ^ 1u);
           if constexpr (CG == 1) {
             if ((prm.exp & 1) && it >= (uint32_t)C::Stages) { tc::mbar_arrive(bars + B_WFULL + slot); continue; }
@@ -397,7 +416,7 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
         const uint32_t par = (it / C::Stages) & 1u;
         {
           PROF_T0();
-          if constexpr (CG == 1) warp_wait(bars + B_WFULL + slot, par);
+          if constexpr (CG == 1 && !WM) warp_wait(bars + B_WFULL + slot, par);
           else warp_wait_cluster(bars + B_WFULL + slot, par);
           PROF_ADD(P_WFULL);
         }
@@ -409,7 +428,10 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
         else tc::mma_commit2(bar);
       };
       auto release_stage = [&]() {
-        if (tc::elect_one()) commit_bar(bars + B_WEMPTY + (it % C::Stages));
+        if (tc::elect_one()) {
+          if constexpr (WM) tc::mma_commit_pair(bars + B_WEMPTY + (it % C::Stages));
+          else commit_bar(bars + B_WEMPTY + (it % C::Stages));
+        }
         ++it;
       };
       auto commit_one = [&](int which) {
@@ -572,7 +594,7 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
     const int res = prm.res;
     uint32_t c_xfree = 0;
     for (long long g = g0; g < n_groups; g += gstep) {
-      const long long tile = g * CG + rank;
+      const long long tile = g * TP + rank;
       const long long p0 = win0 + tile * kTile;
       const bool tr = blockIdx.x == 0 && sw == 0 && lane == 0 && (g - g0) / gstep == kTraceTile;
       TRACE(tr, 96);
@@ -616,7 +638,7 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
     uint32_t t_off[4][2], t_wgt[4][2], t_z[4];
     int gtr = -1;                              // trace slot base for the chunk being generated (-1: off)
     auto compute_taps = [&](long long g) {
-      const PointTaps pt = point_taps(src, cal, prm.H, prm.W, win0 + (g * CG + rank) * kTile + wk * 16 + l16, n);
+      const PointTaps pt = point_taps(src, cal, prm.H, prm.W, win0 + (g * TP + rank) * kTile + wk * 16 + l16, n);
       const uint32_t o01 = (uint32_t)pt.off[0] | ((uint32_t)pt.off[1] << 16), o23 = (uint32_t)pt.off[2] | ((uint32_t)pt.off[3] << 16);
       const uint32_t w01 = tc::pack_half2(pt.wgt[0], pt.wgt[1]), w23 = tc::pack_half2(pt.wgt[2], pt.wgt[3]);
       const uint32_t zz = tc::pack_half2(pt.zf, pt.zf);
@@ -730,7 +752,7 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
       for (long long g = g0 - gstep; g < n_groups; g += gstep) {
         const bool real = g >= g0;
         const bool has_next = g + gstep < n_groups;
-        const long long p0 = win0 + (g * CG + rank) * kTile;
+        const long long p0 = win0 + (g * TP + rank) * kTile;
         const bool tr = blockIdx.x == 0 && real && (wk & 3) == 0 && lane == 0 && (g - g0) / gstep == kTraceTile;
         const int tb = 32 + wg * 32;
 #pragma unroll 1
@@ -860,7 +882,8 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
   __syncwarp();
   tc::tcgen05_fence_before();
   if constexpr (CG == 1) {
-    __syncthreads();
+    if constexpr (WM) tc::cluster_sync_all();      // (the peer's last stage releases arrive on this CTA's barriers)
+    else __syncthreads();
     if (warp == 2) tc::tmem_dealloc(tbase, 512);
   } else {
     tc::cluster_sync_all();
@@ -2061,6 +2084,7 @@ int mp_tc_prepare(mp_mlp* mlp) {
   e = cudaFuncSetAttribute(query_tc3_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
 #ifndef MP_CUDA_EMU
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
 #endif
@@ -2251,6 +2275,31 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     cfg.numAttrs = 1;
     if (dst.n_peers > 0) MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc3_kernel<true, 2>, prm, src, cal, dst));
     else MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc3_kernel<false, 2>, prm, src, cal, dst));
+    report(2 * pairs);
+    return MP_OK;
+  }
+#endif
+#ifndef MP_CUDA_EMU
+  // MONOPORT_B200_TC_WM=1: the one-CTA program in 2-CTA clusters that share (multicast) the weight stream
+  static const int forced_wm = [] { const char* v = getenv("MONOPORT_B200_TC_WM"); return v ? atoi(v) : 0; }();
+  if (forced_wm == 1 && dst.n_peers == 0 && sms >= 2 && tiles >= 2) {
+    const long long groups = (tiles + 1) / 2;
+    const long long max_pairs = sms / 2;
+    const int pairs = (int)(groups < max_pairs ? groups : max_pairs);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Smem::Total + 1024;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc3_kernel<false, 1, true>, prm, src, cal, dst));
     report(2 * pairs);
     return MP_OK;
   }

@@ -34,8 +34,8 @@ extern "C" int mp_forward_vertices_async(const float* vol_dev, int R, int direct
   unsigned long long* sums = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(scratch_dev) + sums_off);
   unsigned long long* total = sums + mpscan::num_blocks(n) + 1;
   MP_CUDA(cudaMemsetAsync(total + 1, 0, sizeof(unsigned long long), st));   // ticket counter of the scan
-  const int grid = (int)((n + 255) / 256);
-  first_hit_kernel<<<grid, 256, 0, st>>>(vol_dev, R, direction, first_t);
+  const int grid = (int)((n + kHitCols - 1) / kHitCols);
+  first_hit_kernel<<<grid, kHitCols * kHitSlices, 0, st>>>(vol_dev, R, direction, first_t);
   HitF f{first_t};
   HitEmit em{vol_dev, first_t, R, direction, (long long*)x_dev, (long long*)y_dev, z_dev, norm_dev};
   MP_CUDA(mpscan::scan_emit(f, em, n, sums, total, st));

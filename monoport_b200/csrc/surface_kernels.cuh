@@ -25,28 +25,44 @@ __device__ __forceinline__ void column_walk(int dir, int R, int x, int y, long l
   stride = a_index(dir, R, x, y, 1) - base;
 }
 
-__global__ void __launch_bounds__(256)
+// 32 columns x 8 depth slices per block: every thread walks ONE slice of its column (R/8 nodes, in batches of independent
+// loads), the block keeps the first slice with a hit.  One thread per whole column made an empty column a chain of R/16
+// dependent memory round trips (17 at R = 257: 24 us); here it is ceil(R/8/17) = 2.  For front/back the 32 lanes of a warp
+// walk 32 consecutive x (coalesced); for left/right k is the contiguous axis and a thread reads 17 consecutive floats.
+constexpr int kHitCols = 32, kHitSlices = 8, kHitBatch = 17;
+__global__ void __launch_bounds__(kHitCols * kHitSlices)
 first_hit_kernel(const float* __restrict__ vol, int R, int dir, int32_t* __restrict__ first_t) {
-  // thread -> column; for front/back consecutive threads walk consecutive x (coalesced); for left/right consecutive
-  // threads walk consecutive y rows of the same (x) plane -- k is then the contiguous axis, handled per thread.
-  // The column is read in batches of 16 unconditional loads (independent, so they overlap) and tested afterwards:
-  // a serial load-test-break chain costs one memory round trip per node, ~100 us for R = 257.
-  constexpr int kBatch = 16;
+  __shared__ int s_hit[kHitSlices][kHitCols];
   const int n = R * R;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
-    const int x = c % R, y = c / R;
-    long long base, stride;
-    column_walk(dir, R, x, y, base, stride);
+  const int cx = threadIdx.x % kHitCols, sl = threadIdx.x / kHitCols;
+  const int len = (R + kHitSlices - 1) / kHitSlices;
+  for (int c0 = blockIdx.x * kHitCols; c0 < n; c0 += gridDim.x * kHitCols) {     // (block-uniform trip count)
+    const int c = c0 + cx;
     int hit = -1;
-    for (int k0 = 0; k0 < R && hit < 0; k0 += kBatch) {
-      float v[kBatch];
+    if (c < n) {
+      const int x = c % R, y = c / R;
+      long long base, stride;
+      column_walk(dir, R, x, y, base, stride);
+      const int k_end = min(R, (sl + 1) * len);
+      for (int k0 = sl * len; k0 < k_end && hit < 0; k0 += kHitBatch) {
+        float v[kHitBatch];
 #pragma unroll
-      for (int j = 0; j < kBatch; ++j) v[j] = (k0 + j < R) ? __ldg(vol + base + (long long)(k0 + j) * stride) : 0.f;
+        for (int j = 0; j < kHitBatch; ++j) v[j] = (k0 + j < k_end) ? __ldg(vol + base + (long long)(k0 + j) * stride) : 0.f;
 #pragma unroll
-      for (int j = kBatch - 1; j >= 0; --j)
-        if (v[j] > 0.5f) hit = k0 + j;
+        for (int j = kHitBatch - 1; j >= 0; --j)
+          if (v[j] > 0.5f) hit = k0 + j;
+      }
     }
-    first_t[x * R + y] = hit;    // transposed: scan order is x-major
+    s_hit[sl][cx] = hit;
+    __syncthreads();
+    if (sl == 0 && c < n) {
+      int h = -1;
+#pragma unroll
+      for (int q = kHitSlices - 1; q >= 0; --q)
+        if (s_hit[q][cx] >= 0) h = s_hit[q][cx];
+      first_t[(c % R) * R + c / R] = h;    // transposed: scan order is x-major
+    }
+    __syncthreads();
   }
 }
 

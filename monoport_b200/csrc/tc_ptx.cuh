@@ -61,6 +61,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
+// the same copy delivered to the same shared-memory offset of every CTA in `cta_mask` of the cluster; each destination's
+// barrier (same offset) receives the complete_tx for the bytes it got
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+
 // named barrier 1 over the 256 worker threads of the v2 program (warps 4-11)
 __device__ __forceinline__ void bar_sync_workers256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -226,6 +235,13 @@ __device__ __forceinline__ void mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64
       : "memory");
 }
 // completion of all prior MMAs arrives on the barrier at this smem offset in BOTH CTAs of the pair
+// one-CTA MMAs, completion signalled on the barrier at the same offset in BOTH CTAs of a pair
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit2(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),

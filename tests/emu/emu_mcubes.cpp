@@ -56,14 +56,14 @@ int main(int argc, char** argv) {
   }
   for (long long w = n_words; w < n_words + pad; ++w)
     if (bits[w] != 0u) { fprintf(stderr, "wrote into the bit padding\n"); return 3; }
-  cuda_emu::launch(dim3((unsigned)((n_words + 255) / 256)), dim3(256),
-                   [&] { classify_words_kernel(bits.data(), info.data(), n, D, H, W); });
+  
   std::vector<uint32_t> active(n_words + 4, 0xABABABABu);
   uint32_t n_active = 0;
+  ClassifyCountF f1{bits.data(), info.data(), n, D, H, W};
   WordCountF f{info.data()};
   PrefixEmit em{prefix.data(), active.data(), &n_active};
   cuda_emu::launch(dim3(nb), dim3(mpscan::kThreads),
-                   [&] { mpscan::block_sums_kernel<WordCountF, mpscan::NoPost>(f, n_words, sums.data(), nb, total, mpscan::NoPost()); });
+                   [&] { mpscan::block_sums_kernel<ClassifyCountF, mpscan::NoPost>(f1, n_words, sums.data(), nb, total, mpscan::NoPost()); });
   cuda_emu::launch(dim3(nb), dim3(mpscan::kThreads),
                    [&] { mpscan::emit_kernel<WordCountF, PrefixEmit>(f, em, n_words, sums.data()); });
   if (total[1] != 0) { fprintf(stderr, "scan ticket not reset\n"); return 3; }

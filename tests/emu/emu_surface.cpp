@@ -23,7 +23,7 @@ int main(int argc, char** argv) {
   std::vector<float> Z(n, -1.f), N(3 * n, -1.f);
   const float* vp = vol.data();
   int32_t* ft = first_t.data();
-  cuda_emu::launch(dim3((unsigned)((n + 255) / 256)), dim3(256), [&] { first_hit_kernel(vp, R, dir, ft); });
+  cuda_emu::launch(dim3((unsigned)std::min<long long>((n + kHitCols - 1) / kHitCols, 37)), dim3(kHitCols * kHitSlices), [&] { first_hit_kernel(vp, R, dir, ft); });
   HitF hf{ft};
   HitEmit em{vp, ft, R, dir, X.data(), Y.data(), Z.data(), N.data()};
   cuda_emu::launch(dim3(nb), dim3(mpscan::kThreads),

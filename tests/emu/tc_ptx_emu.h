@@ -355,6 +355,8 @@ inline void tmem_dealloc2(uint32_t, uint32_t) { no_cluster(); }
 inline void mma_ss2(uint32_t, uint64_t, uint64_t, uint32_t, uint32_t) { no_cluster(); }
 inline void mma_ts2(uint32_t, uint32_t, uint64_t, uint32_t, uint32_t) { no_cluster(); }
 inline void mma_commit2(uint64_t*) { no_cluster(); }
+inline void mma_commit_pair(uint64_t*) { no_cluster(); }
+inline void bulk_g2s_multicast(void*, const void*, uint32_t, uint64_t*, uint16_t) { no_cluster(); }
 // elect.sync: the same lane for the same (full) member mask
 inline bool elect_one() { return (cuda_emu::linear_tid() & 31) == 0; }
 

@@ -126,6 +126,31 @@ def test_host_buffer_entry_point():
     lib.mp_feat_destroy(fh)
 
 
+def test_grid_host_entry_point_equals_device_path():
+    """mp_query_grid_host (host feature map in, host volume out; large slabs read back in z-chunks that overlap the evaluation)
+    returns exactly what the device-side grid query leaves in HBM -- for a small volume (one chunk) and for one above the
+    chunking threshold, full volume and a slab of it."""
+    from monoport_b200 import _lib
+    c = load_query_case("g_smallmap")
+    net = build_net(c)
+    lib = _lib.load()
+    feat = c["feat"].contiguous()
+    hw = feat.shape[2]
+    cal = c["calib"]
+    for R, z0, nz in ((21, 0, 21), (165, 0, 165), (165, 7, 150)):
+        want = net.query_grid(feat.cuda(), cal.cuda(), R, (-1, -1, -1), (1, 1, 1), z0=z0, nz=nz).cpu()
+        fh = ctypes.c_void_p()
+        _lib.check(lib.mp_feat_create(256, hw, hw, ctypes.byref(fh)))
+        out = torch.full((nz, R, R), float("nan"), dtype=torch.float32).pin_memory()
+        mode = _lib.MODE_TC if net.surface_classifier.tc_supported() else _lib.MODE_FP32
+        _lib.check(lib.mp_query_grid_host(net.surface_classifier.handle(), fh, ctypes.c_void_p(feat.data_ptr()), R, z0, nz,
+                                          _lib.f3((-1, -1, -1)), _lib.f3((1, 1, 1)), _lib.calib12(cal), 0,
+                                          ctypes.c_float(spec.Z_SCALE), ctypes.c_void_p(out.data_ptr()), mode,
+                                          _lib.stream_ptr(torch.device("cuda:0"))))
+        lib.mp_feat_destroy(fh)
+        assert torch.equal(out, want), "R=%d z0=%d nz=%d" % (R, z0, nz)
+
+
 def test_errors_are_reported_not_swallowed():
     c = load_query_case("g_smallmap")
     net = build_net(c)
