@@ -5,11 +5,12 @@
 //   face order = (cell linear index, table order).
 // count:  bits_kernel (THE read of the volume: 4 B per node in, one occupancy bit per node out, streaming) ->
 //         ordered scan over the 32-node words of the bit volume, (verts, tris) packed in one uint64.  Its first pass
-//         CLASSIFIES each word on the way (classify_word: edge masks + triangle count; words with no surface inside leave
-//         after a dozen cached loads), its second pass leaves the exclusive prefix per word, the totals, and an unordered
-//         list of the words with a surface inside.
-// emit :  mesh_emit_kernel, a warp per listed word, a lane per node: vertices from the volume (two loads per vertex), faces
-//         from the table; the ids of the vertices on a cell's 12 edges are popcounts over warp-uniform (info, prefix) words.
+//         (classify_sums_kernel) CLASSIFIES each word on the way (edge masks + triangle count; words with no surface inside
+//         leave after a dozen cached loads), its second pass leaves the exclusive prefix per word, the totals, and an
+//         unordered list of the words with a surface inside.
+// emit :  mesh_emit_kernel, a warp per listed word, a lane per node: vertices from the volume (two loads per vertex); the
+//         cells' triangles go through a shared-memory queue and are resolved one thread per face corner (edge -> owning
+//         node -> id = the owning word's prefix + popcounts).
 // Workspace: 1 bit + 24 B per 32 nodes (15 MB at 257^3; the round-1 byte-per-node design took 102 MB).
 #include "mp_common.cuh"
 #include <stdlib.h>
@@ -97,10 +98,14 @@ extern "C" int mp_mcubes_count(mp_mcubes_t* h, const float* vol_dev, float iso, 
   }
   MP_CUDA(cudaGetLastError());
   MP_CUDA(cudaMemsetAsync(h->n_active_dev, 0, sizeof(uint32_t), st));
-  ClassifyCountF f1{h->bits, h->info, h->n, h->D, h->H, h->W};
+  // the ordered scan over the words, first pass = classify_sums_kernel (classification + chunk totals), second pass = the
+  // generic emit half reading the stored info
+  const int nb = mpscan::num_blocks(h->n_words);
+  classify_sums_kernel<<<nb, kClassifyThreads, 0, st>>>(h->bits, h->info, h->n, h->D, h->H, h->W, h->sums, nb, h->total);
   WordCountF f2{h->info};
   PrefixEmit em{h->prefix, h->active, h->n_active_dev};
-  MP_CUDA(mpscan::scan_emit2(f1, f2, em, h->n_words, h->sums, h->total, st));
+  mpscan::emit_kernel<WordCountF, PrefixEmit><<<nb, mpscan::kThreads, 0, st>>>(f2, em, h->n_words, h->sums);
+  MP_CUDA(cudaGetLastError());
   unsigned long long tot = 0;
   MP_CUDA(cudaMemcpyAsync(&tot, h->total, sizeof(tot), cudaMemcpyDeviceToHost, st));
   MP_CUDA(cudaMemcpyAsync(&h->n_active, h->n_active_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

@@ -112,19 +112,43 @@ __device__ __forceinline__ unsigned long long word_counts(const uint4 q) {
   return (unsigned long long)(__popc(q.x) + __popc(q.y) + __popc(q.z)) | ((unsigned long long)q.w << 32);
 }
 
-// functor of the scan's FIRST pass: classifies the word, stores its info and returns its (vertex, triangle) counts
-struct ClassifyCountF {
-  const uint32_t* bits;
-  WordInfo* info;
-  long long n;
-  int D, H, W;
-  static constexpr bool kVec8 = false;
-  __device__ unsigned long long operator()(long long w) const {
-    const WordInfo wi = classify_word(bits, w, n, D, H, W);
-    *reinterpret_cast<uint4*>(info + w) = make_uint4(wi.ex, wi.ey, wi.ez, wi.nt);
-    return word_counts(make_uint4(wi.ex, wi.ey, wi.ez, wi.nt));
+// The scan's first pass, specialised: one thread per word classifies it (coalesced, 2 words per thread of a 1024-thread
+// CTA = one 2048-word chunk of mp_scan), stores its info, and the CTA reduces the (vertex, triangle) counts to the chunk
+// total; the last CTA turns the totals into offsets (mpscan::finish_block_sums).  A functor inside block_sums_kernel had one
+// thread classify eight consecutive words in a row (23.6 us against 11.0 + 6.6 for classify + sums as two launches).
+constexpr int kClassifyThreads = 1024;
+static_assert(mpscan::kChunk == 2 * kClassifyThreads, "one CTA = one chunk of the ordered scan");
+__global__ void __launch_bounds__(kClassifyThreads)
+classify_sums_kernel(const uint32_t* __restrict__ bits, WordInfo* __restrict__ info, long long n, int D, int H, int W,
+                     unsigned long long* __restrict__ sums, int nb, unsigned long long* __restrict__ total) {
+  const long long n_words = (n + 31) >> 5;
+  unsigned long long s = 0;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const long long w = (long long)blockIdx.x * mpscan::kChunk + j * kClassifyThreads + threadIdx.x;
+    if (w < n_words) {
+      const WordInfo wi = classify_word(bits, w, n, D, H, W);
+      const uint4 q = make_uint4(wi.ex, wi.ey, wi.ez, wi.nt);
+      *reinterpret_cast<uint4*>(info + w) = q;
+      s += word_counts(q);
+    }
   }
-};
+  // CTA total: warp shuffles, then one warp over the 32 warp totals
+  __shared__ unsigned long long s_warp[kClassifyThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) s_warp[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long t = s_warp[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) s_warp[0] = t;
+  }
+  __syncthreads();
+  mpscan::finish_block_sums<kClassifyThreads>(s_warp[0], sums, nb, total, mpscan::NoPost());
+}
 
 // functor of the scan's SECOND pass (and of everything after it): the stored info
 struct WordCountF {    // low 32: vertices owned by the word's nodes, high 32: triangles of its cells
@@ -149,98 +173,116 @@ struct PrefixEmit {
   }
 };
 
-// ---- pass 4: emission.  One warp per word with a surface inside (the active list), one lane per node: up to three
-// vertices (vertex id = rank of (node, axis) in node order) and up to MC_MAX_TRI triangles (face order = (cell linear
-// index, table order); their offsets come from a warp scan).  Walking 32 consecutive words per warp instead left most warps
-// with nothing and a few with a dozen dependent chains in a row (63 us at 257^3).
+// id of the vertex on the +`axis` edge owned by node i (the edge must be active)
+__device__ __forceinline__ int32_t vertex_id(const WordInfo* __restrict__ info, const unsigned long long* __restrict__ prefix,
+                                             uint32_t i, int axis) {
+  const uint32_t w = i >> 5;
+  const int b = (int)(i & 31u);
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(info + w));
+  const uint32_t below = (1u << b) - 1u;
+  uint32_t id = (uint32_t)__ldg(prefix + w) + __popc(q.x & below) + __popc(q.y & below) + __popc(q.z & below);
+  if (axis >= 1) id += (q.x >> b) & 1u;
+  if (axis == 2) id += (q.y >> b) & 1u;
+  return (int32_t)id;
+}
+
+// ---- pass 4: emission, two phases per round of a CTA.
+// (a) one warp per word with a surface inside (the active list), one lane per node: up to three vertices (vertex id = rank of
+//     (node, axis) in node order), and the cell's triangles are QUEUED in shared memory -- (corner-0 node, triangle index,
+//     its three edge numbers); triangle index = the word's prefix + a warp scan, i.e. face order = (cell linear index, table
+//     order).
+// (b) the whole CTA walks the queue densely, one thread per face corner: edge -> owning node -> vertex id (the owning
+//     word's prefix + popcounts) -> faces.
+// Only about one cell in ten of an active word has triangles: resolving the corners in phase (a) made every warp run the
+// 15-corner loop for its few cells (27-63 us at 257^3); walking 32 consecutive words per warp instead of a list left most
+// warps empty and a few with a dozen dependent chains.  Node indices are 32-bit (mp_mcubes_create bounds the volume).
 constexpr int kEmitThreads = 256;
+constexpr int kEmitWarps = kEmitThreads / 32;
+constexpr int kEmitQueue = kEmitWarps * 32 * MC_MAX_TRI;
 __global__ void __launch_bounds__(kEmitThreads)
 mesh_emit_kernel(const float* __restrict__ vol, const uint32_t* __restrict__ bits, const WordInfo* __restrict__ info,
                  const unsigned long long* __restrict__ prefix, const uint32_t* __restrict__ active, uint32_t n_active,
                  float* __restrict__ verts, int32_t* __restrict__ faces, int D, int H, int W, long long n, float iso) {
-  __shared__ int32_t s_ids[kEmitThreads / 32][12][32];
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * (kEmitThreads / 32) + (threadIdx.x >> 5);
-  const long long n_warps = (long long)gridDim.x * (kEmitThreads / 32);
-  const int plane = H * W;
-  for (long long e = warp0; e < (long long)n_active; e += n_warps) {             // (warp-uniform trip count)
-    const long long w = (long long)__ldg(active + e);
-    const uint4 wi = __ldg(reinterpret_cast<const uint4*>(info + w));
-    const uint32_t ex = wi.x, ey = wi.y, ez = wi.z, nt = wi.w;
-    const unsigned long long pre = __ldg(prefix + w);
-    const long long i = 32 * w + lane;                                          // this lane's node
-    const int z = (int)(i / plane), r = (int)(i - (long long)z * plane), y = r / W, x = r - y * W;
-    // ---- vertices on the owned edges
-    const uint32_t below = (1u << lane) - 1u;
-    const uint32_t code = ((ex >> lane) & 1u) | (((ey >> lane) & 1u) << 1) | (((ez >> lane) & 1u) << 2);
-    if (code) {
-      uint32_t vi = (uint32_t)pre + __popc(ex & below) + __popc(ey & below) + __popc(ez & below);
-      const float va = __ldg(vol + i);
+  __shared__ uint32_t q_node[kEmitQueue], q_tri[kEmitQueue], q_edges[kEmitQueue];
+  __shared__ uint32_t q_count;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t plane = (uint32_t)H * (uint32_t)W;
+  const uint32_t per_round = gridDim.x * kEmitWarps;
+  const uint32_t rounds = (n_active + per_round - 1) / per_round;                 // (uniform over the grid)
+  for (uint32_t round = 0; round < rounds; ++round) {
+    if (threadIdx.x == 0) q_count = 0;
+    __syncthreads();
+    const uint32_t e = (round * gridDim.x + blockIdx.x) * kEmitWarps + warp;
+    if (e < n_active) {                                                           // (warp-uniform)
+      const uint32_t w = __ldg(active + e);
+      const uint4 wi = __ldg(reinterpret_cast<const uint4*>(info + w));
+      const uint32_t ex = wi.x, ey = wi.y, ez = wi.z, nt = wi.w;
+      const unsigned long long pre = __ldg(prefix + w);
+      const uint32_t i = 32u * w + (uint32_t)lane;                                // this lane's node
+      const uint32_t z = i / plane, r = i - z * plane, y = r / (uint32_t)W, x = r - y * (uint32_t)W;
+      // ---- vertices on the owned edges
+      const uint32_t below = (1u << lane) - 1u;
+      const uint32_t code = ((ex >> lane) & 1u) | (((ey >> lane) & 1u) << 1) | (((ez >> lane) & 1u) << 2);
+      if (code) {
+        uint32_t vi = (uint32_t)pre + __popc(ex & below) + __popc(ey & below) + __popc(ez & below);
+        const float va = __ldg(vol + i);
 #pragma unroll
-      for (int axis = 0; axis < 3; ++axis) {
-        if (!((code >> axis) & 1u)) continue;
-        const long long step = axis == 0 ? 1 : (axis == 1 ? W : plane);
-        const float vb = __ldg(vol + i + step);
-        const float t = __fdiv_rn(__fsub_rn(iso, va), __fsub_rn(vb, va));
-        float p[3] = {(float)x, (float)y, (float)z};
-        p[axis] = __fadd_rn(p[axis], t);
-        float* o = verts + 3ll * vi;
-        o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
-        ++vi;
-      }
-    }
-    // ---- triangles of the cell whose corner 0 is this node
-    if (nt) {                                                                   // (warp-uniform)
-      uint32_t v[8];
-      corner_words(bits, w, H, W, v);
-      const bool cell = i < n && x + 1 < W && y + 1 < H && z + 1 < D;
-      const int k = cell ? case_of(v, lane) : 0;
-      // one 16-byte load: bytes 0..14 = edge ids of the cell's triangles, byte 15 = their number
-      const uint4 row = __ldg(reinterpret_cast<const uint4*>(&g_mc_tri[k][0]));
-      const uint32_t rw[4] = {row.x, row.y, row.z, row.w};
-      const int mytri = (int)(row.w >> 24);
-      // exclusive warp scan of the triangle counts
-      unsigned long long incl = mpscan::warp_incl_scan((unsigned long long)mytri, lane);
-      const uint32_t foff = (uint32_t)(pre >> 32) + (uint32_t)incl - (uint32_t)mytri;
-      // ---- ids of the vertices on the cell's 12 edges.  They live on 7 nodes in 4 node rows (dy, dz); the 32 cells of the
-      // warp take each row from at most two consecutive words, so (info, prefix) of those words are WARP-UNIFORM loads and
-      // every id is a few popcounts on registers -- not a 24-byte lookup per face corner.  The ids go through shared memory
-      // ([edge][lane], conflict-free) because the face corners index them by a run-time edge number.
-      int32_t* my_ids = s_ids[threadIdx.x >> 5][0];
-      const long long last_word = ((n + 31) >> 5) - 1;
-#pragma unroll
-      for (int rw4 = 0; rw4 < 4; ++rw4) {
-        const int oy = rw4 & 1, oz = rw4 >> 1;
-        const long long base = 32 * w + ((long long)oz * H + oy) * W;            // node of lane 0 in this row
-        const long long wa = min(base >> 5, last_word), wb = min((base >> 5) + 1, last_word);
-        const int sft = (int)(base & 31);
-        const uint4 qa = __ldg(reinterpret_cast<const uint4*>(info + wa)), qb = __ldg(reinterpret_cast<const uint4*>(info + wb));
-        const uint32_t pa = (uint32_t)__ldg(prefix + wa), pb = (uint32_t)__ldg(prefix + wb);
-#pragma unroll
-        for (int ox = 0; ox < 2; ++ox) {
-          if (ox == 1 && rw4 == 3) continue;                                     // node (1,1,1) owns none of the cell's edges
-          const int nb = sft + lane + ox;
-          const bool hi = nb >= 32;
-          const int bb = nb & 31;
-          const uint32_t qx = hi ? qb.x : qa.x, qy = hi ? qb.y : qa.y, qz = hi ? qb.z : qa.z;
-          const uint32_t bel = (1u << bb) - 1u;
-          const uint32_t r0 = (hi ? pb : pa) + __popc(qx & bel) + __popc(qy & bel) + __popc(qz & bel);   // id of its +x vertex
-          const uint32_t bx = (qx >> bb) & 1u, by = (qy >> bb) & 1u;
-          // edges 0-3: along x at (dy, dz); 4-7: along y at (dx, dz); 8-11: along z at (dx, dy)
-          if (ox == 0) my_ids[(0 + oy + 2 * oz) * 32 + lane] = (int32_t)r0;
-          if (oy == 0) my_ids[(4 + ox + 2 * oz) * 32 + lane] = (int32_t)(r0 + bx);
-          if (oz == 0) my_ids[(8 + ox + 2 * oy) * 32 + lane] = (int32_t)(r0 + bx + by);
+        for (int axis = 0; axis < 3; ++axis) {
+          if (!((code >> axis) & 1u)) continue;
+          const uint32_t step = axis == 0 ? 1u : (axis == 1 ? (uint32_t)W : plane);
+          const float vb = __ldg(vol + i + step);
+          const float t = __fdiv_rn(__fsub_rn(iso, va), __fsub_rn(vb, va));
+          float p[3] = {(float)x, (float)y, (float)z};
+          p[axis] = __fadd_rn(p[axis], t);
+          float* o = verts + 3ull * vi;
+          o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+          ++vi;
         }
       }
-      __syncwarp();
+      // ---- triangles of the cell whose corner 0 is this node: queue them
+      if (nt) {                                                                   // (warp-uniform)
+        uint32_t v[8];
+        corner_words(bits, w, H, W, v);
+        const bool cell = (long long)i < n && x + 1 < (uint32_t)W && y + 1 < (uint32_t)H && z + 1 < (uint32_t)D;
+        const int k = cell ? case_of(v, lane) : 0;
+        // one 16-byte load: bytes 0..14 = edge numbers of the cell's triangles, byte 15 = their number
+        const uint4 row = __ldg(reinterpret_cast<const uint4*>(&g_mc_tri[k][0]));
+        const uint32_t rw[4] = {row.x, row.y, row.z, row.w};
+        const uint32_t mytri = row.w >> 24;
+        const uint32_t incl = (uint32_t)mpscan::warp_incl_scan((unsigned long long)mytri, lane);
+        const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&q_count, warp_total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t slot = base + incl - mytri, tri0 = (uint32_t)(pre >> 32) + incl - mytri;
 #pragma unroll
-      for (int corner = 0; corner < 3 * MC_MAX_TRI; ++corner)
-        if (corner < 3 * mytri) {
-          const int ed = (int)((rw[corner >> 2] >> (8 * (corner & 3))) & 0xFFu);
-          faces[3ll * foff + corner] = my_ids[ed * 32 + lane];
-        }
-      __syncwarp();                                                              // (the next entry overwrites the ids)
+        for (int t = 0; t < MC_MAX_TRI; ++t)
+          if ((uint32_t)t < mytri) {
+            uint32_t ed3 = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) ed3 |= ((rw[(3 * t + c) >> 2] >> (8 * ((3 * t + c) & 3))) & 0xFFu) << (8 * c);
+            q_node[slot + t] = i;
+            q_tri[slot + t] = tri0 + (uint32_t)t;
+            q_edges[slot + t] = ed3;
+          }
+      }
     }
+    __syncthreads();
+    // ---- phase (b): one thread per face corner of the queued triangles
+    const uint32_t corners = 3u * q_count;
+    for (uint32_t idx = threadIdx.x; idx < corners; idx += kEmitThreads) {
+      const uint32_t tq = idx / 3u, c = idx - 3u * tq;
+      const int ed = (int)((q_edges[tq] >> (8 * c)) & 0xFFu);
+      // edge -> owning node + axis.  edges 0-3 along x at (y,z) offsets, 4-7 along y at (x,z), 8-11 along z at (x,y)
+      const int axis = ed >> 2, q = ed & 3;
+      uint32_t ox = 0, oy = 0, oz = 0;
+      if (axis == 0) { oy = q & 1; oz = q >> 1; }
+      else if (axis == 1) { ox = q & 1; oz = q >> 1; }
+      else { ox = q & 1; oy = q >> 1; }
+      const uint32_t node = q_node[tq] + (oz * (uint32_t)H + oy) * (uint32_t)W + ox;
+      faces[3ull * q_tri[tq] + c] = vertex_id(info, prefix, node, axis);
+    }
+    __syncthreads();
   }
 }
 

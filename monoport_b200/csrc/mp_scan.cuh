@@ -26,16 +26,17 @@ __device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long 
   return v;
 }
 
-// exclusive scan of one value per thread across the CTA; returns exclusive prefix, *total = CTA sum
+// exclusive scan of one value per thread across the CTA (of NT threads); returns exclusive prefix, *total = CTA sum
+template <int NT = kThreads>
 __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long v, unsigned long long* total) {
-  __shared__ unsigned long long warp_sums[kThreads / 32];
+  __shared__ unsigned long long warp_sums[NT / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long incl = warp_incl_scan(v, lane);
   if (lane == 31) warp_sums[warp] = incl;
   __syncthreads();
   unsigned long long base = 0, tot = 0;
 #pragma unroll
-  for (int w = 0; w < kThreads / 32; ++w) {
+  for (int w = 0; w < NT / 32; ++w) {
     const unsigned long long s = warp_sums[w];
     if (w < warp) base += s;
     tot += s;
@@ -74,19 +75,12 @@ __device__ __forceinline__ void load_bytes8(const uint8_t* p, long long i, uint3
   }
 }
 
-// sums[0..nb) <- exclusive scan of the CTA totals, total[0] <- grand total.  total[1] is the ticket counter: zero on entry
-// (zero-initialised once by the owner of the workspace), reset to zero by the last CTA.
-template <class F, class P>
-__global__ void __launch_bounds__(kThreads) block_sums_kernel(F f, long long n, unsigned long long* __restrict__ sums, int nb,
-                                                              unsigned long long* __restrict__ total, P post) {
-  const long long base = (long long)blockIdx.x * kChunk + (long long)threadIdx.x * kItems;
-  unsigned long long v[kItems];
-  load_items(f, base, n, v);
-  unsigned long long s = 0;
-#pragma unroll
-  for (int j = 0; j < kItems; ++j) s += v[j];
-  unsigned long long tot;
-  block_excl_scan(s, &tot);
+// Tail of a scan's first pass, called by ALL threads of every CTA with the CTA's total `tot`: sums[0..nb) <- exclusive scan of
+// the CTA totals, total[0] <- grand total.  total[1] is the ticket counter: zero on entry (zero-initialised once by the owner
+// of the workspace), reset to zero by the last CTA.  NT = threads per CTA.
+template <int NT = kThreads, class P>
+__device__ __forceinline__ void finish_block_sums(unsigned long long tot, unsigned long long* __restrict__ sums, int nb,
+                                                  unsigned long long* __restrict__ total, P post) {
   __shared__ bool is_last;
   if (threadIdx.x == 0) {
     sums[blockIdx.x] = tot;
@@ -98,12 +92,12 @@ __global__ void __launch_bounds__(kThreads) block_sums_kernel(F f, long long n, 
   __threadfence();
   // the last CTA turns the nb CTA totals into exclusive offsets: thread t owns the contiguous run [t*per, (t+1)*per)
   // (two independent passes over L2-resident values + ONE block scan, instead of a block scan per 256 entries)
-  const int per = (nb + kThreads - 1) / kThreads;
-  const int b0 = (int)threadIdx.x * per, b1 = min(b0 + per, nb);
+  const int per = (nb + NT - 1) / NT;
+  const int b0 = min((int)threadIdx.x * per, nb), b1 = min(b0 + per, nb);
   unsigned long long local = 0;
   for (int i = b0; i < b1; ++i) local += __ldcg(sums + i);
   unsigned long long grand;
-  unsigned long long run = block_excl_scan(local, &grand);
+  unsigned long long run = block_excl_scan<NT>(local, &grand);
   for (int i = b0; i < b1; ++i) {
     const unsigned long long v = __ldcg(sums + i);
     sums[i] = run;
@@ -114,6 +108,20 @@ __global__ void __launch_bounds__(kThreads) block_sums_kernel(F f, long long n, 
     total[1] = 0;
     post(grand);
   }
+}
+
+template <class F, class P>
+__global__ void __launch_bounds__(kThreads) block_sums_kernel(F f, long long n, unsigned long long* __restrict__ sums, int nb,
+                                                              unsigned long long* __restrict__ total, P post) {
+  const long long base = (long long)blockIdx.x * kChunk + (long long)threadIdx.x * kItems;
+  unsigned long long v[kItems];
+  load_items(f, base, n, v);
+  unsigned long long s = 0;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) s += v[j];
+  unsigned long long tot;
+  block_excl_scan(s, &tot);
+  finish_block_sums<kThreads>(tot, sums, nb, total, post);
 }
 
 template <class F, class E>
@@ -145,16 +153,6 @@ inline cudaError_t scan_emit(F f, E emit, long long n, unsigned long long* sums,
   const int nb = num_blocks(n > 0 ? n : 1);
   block_sums_kernel<F, P><<<nb, kThreads, 0, st>>>(f, n > 0 ? n : 0, sums, nb, total, post);
   if (n > 0) emit_kernel<F, E><<<nb, kThreads, 0, st>>>(f, emit, n, sums);
-  return cudaGetLastError();
-}
-// The same with a different functor per pass: `first` may be expensive and may have side effects (it runs exactly once per
-// element), `second` must return the same values (typically it reads back what `first` stored).
-template <class F1, class F2, class E>
-inline cudaError_t scan_emit2(F1 first, F2 second, E emit, long long n, unsigned long long* sums, unsigned long long* total,
-                              cudaStream_t st) {
-  const int nb = num_blocks(n > 0 ? n : 1);
-  block_sums_kernel<F1, NoPost><<<nb, kThreads, 0, st>>>(first, n > 0 ? n : 0, sums, nb, total, NoPost());
-  if (n > 0) emit_kernel<F2, E><<<nb, kThreads, 0, st>>>(second, emit, n, sums);
   return cudaGetLastError();
 }
 #endif  // __CUDACC__

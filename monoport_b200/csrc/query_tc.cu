@@ -263,7 +263,9 @@ __device__ __forceinline__ void warp_wait_cluster(uint64_t* bar, uint32_t parity
 // to its CTA; the leader (rank 0) issues all MMAs, operand hand-offs are remote mbarrier arrivals on the leader's
 // barriers, MMA completions are multicast to both CTAs by tcgen05.commit.
 //
-// WM (opt-in, MONOPORT_B200_TC_WM=1; CG = 1 only): two INDEPENDENT one-CTA programs launched as a 2-CTA cluster that share
+// WM (opt-in, MONOPORT_B200_TC_WM=1; CG = 1 only; validated: the query suite passes with it; same box, same run 487 against
+// 490 Mpoints/s -- 72.5 k cycles per tile instead of 66 k at a higher clock, profiles/r02_call14_wm_ab.txt): two
+// INDEPENDENT one-CTA programs launched as a 2-CTA cluster that share
 // the weight stream: each CTA fetches half of every 32 KB stage and multicasts it into both shared memories
 // (cp.async.bulk ... .multicast::cluster), so the L2 serves each weight byte once per pair.  Everything else is CTA-local
 // (cta_group::1 MMAs); the only coupling is the ring: a slot is refilled when BOTH issuers have released it
@@ -2280,7 +2282,9 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
   }
 #endif
 #ifndef MP_CUDA_EMU
-  // MONOPORT_B200_TC_WM=1: the one-CTA program in 2-CTA clusters that share (multicast) the weight stream
+  // MONOPORT_B200_TC_WM=1: the one-CTA program in 2-CTA clusters that share (multicast) the weight stream.  Halves the L2 -> SM
+  // weight bytes like the CTA pair above without touching the MMAs; the coupled ring costs 10 % more cycles per tile and the
+  // power saved buys back all but 0.7 % of it (profiles/r02_call14_wm_ab.txt): opt-in.
   static const int forced_wm = [] { const char* v = getenv("MONOPORT_B200_TC_WM"); return v ? atoi(v) : 0; }();
   if (forced_wm == 1 && dst.n_peers == 0 && sms >= 2 && tiles >= 2) {
     const long long groups = (tiles + 1) / 2;

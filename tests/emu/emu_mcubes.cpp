@@ -59,11 +59,10 @@ int main(int argc, char** argv) {
   
   std::vector<uint32_t> active(n_words + 4, 0xABABABABu);
   uint32_t n_active = 0;
-  ClassifyCountF f1{bits.data(), info.data(), n, D, H, W};
   WordCountF f{info.data()};
   PrefixEmit em{prefix.data(), active.data(), &n_active};
-  cuda_emu::launch(dim3(nb), dim3(mpscan::kThreads),
-                   [&] { mpscan::block_sums_kernel<ClassifyCountF, mpscan::NoPost>(f1, n_words, sums.data(), nb, total, mpscan::NoPost()); });
+  cuda_emu::launch(dim3(nb), dim3(kClassifyThreads),
+                   [&] { classify_sums_kernel(bits.data(), info.data(), n, D, H, W, sums.data(), nb, total); });
   cuda_emu::launch(dim3(nb), dim3(mpscan::kThreads),
                    [&] { mpscan::emit_kernel<WordCountF, PrefixEmit>(f, em, n_words, sums.data()); });
   if (total[1] != 0) { fprintf(stderr, "scan ticket not reset\n"); return 3; }
