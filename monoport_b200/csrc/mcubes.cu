@@ -40,7 +40,6 @@ extern "C" int mp_mcubes_destroy(mp_mcubes_t* h) {
   if (h->info) cudaFree(h->info);
   if (h->prefix) cudaFree(h->prefix);
   if (h->active) cudaFree(h->active);
-  if (h->n_active_dev) cudaFree(h->n_active_dev);
   if (h->sums) cudaFree(h->sums);
   if (h->total) cudaFree(h->total);
   delete h;
@@ -62,8 +61,9 @@ extern "C" int mp_mcubes_create(int D, int H, int W, mp_mcubes_t** out) {
   if (e == cudaSuccess) e = cudaMalloc(&h->info, (size_t)h->n_words * sizeof(WordInfo));
   if (e == cudaSuccess) e = cudaMalloc(&h->prefix, (size_t)h->n_words * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&h->active, (size_t)h->n_words * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&h->n_active_dev, sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&h->sums, (size_t)(mpscan::num_blocks(h->n_words) + 1) * sizeof(unsigned long long));
+  // chunk totals of the scan + (last entry) the length of the active list: zeroed together before every count
+  if (e == cudaSuccess) e = cudaMalloc(&h->sums, (size_t)(mpscan::num_blocks(h->n_words) + 2) * sizeof(unsigned long long));
+  if (e == cudaSuccess) h->n_active_dev = reinterpret_cast<uint32_t*>(h->sums + mpscan::num_blocks(h->n_words) + 1);
   if (e == cudaSuccess) e = cudaMalloc(&h->total, 2 * sizeof(unsigned long long));                 // [0] total, [1] scan ticket
   if (e == cudaSuccess) e = cudaMemset(h->total, 0, 2 * sizeof(unsigned long long));
   if (e != cudaSuccess) {
@@ -97,11 +97,12 @@ extern "C" int mp_mcubes_count(mp_mcubes_t* h, const float* vol_dev, float iso, 
     bits_kernel<<<(unsigned)(blocks_needed < cap ? blocks_needed : cap), kBitsThreads, 0, st>>>(vol_dev, h->bits, h->n, iso);
   }
   MP_CUDA(cudaGetLastError());
-  MP_CUDA(cudaMemsetAsync(h->n_active_dev, 0, sizeof(uint32_t), st));
   // the ordered scan over the words, first pass = classify_sums_kernel (classification + chunk totals), second pass = the
   // generic emit half reading the stored info
   const int nb = mpscan::num_blocks(h->n_words);
-  classify_sums_kernel<<<nb, kClassifyThreads, 0, st>>>(h->bits, h->info, h->n, h->D, h->H, h->W, h->sums, nb, h->total);
+  MP_CUDA(cudaMemsetAsync(h->sums, 0, (size_t)(nb + 2) * sizeof(unsigned long long), st));
+  const unsigned n_ctas = (unsigned)((h->n_words + kClassifyWords - 1) / kClassifyWords);
+  classify_sums_kernel<<<n_ctas, kClassifyThreads, 0, st>>>(h->bits, h->info, h->n, h->D, h->H, h->W, h->sums, nb, h->total);
   WordCountF f2{h->info};
   PrefixEmit em{h->prefix, h->active, h->n_active_dev};
   mpscan::emit_kernel<WordCountF, PrefixEmit><<<nb, mpscan::kThreads, 0, st>>>(f2, em, h->n_words, h->sums);

@@ -75,7 +75,9 @@ struct WordInfo {
 
 // ---- pass 2 (runs inside the scan's first pass): edge masks + triangle count of one word.  Uniform words (all eight
 // shifted copies equal) leave at once.
-__device__ __forceinline__ WordInfo classify_word(const uint32_t* __restrict__ bits, long long w, long long n, int D, int H, int W) {
+// `ntri`: the 256 triangle counts (byte 15 of the table rows), staged in shared memory by the caller
+__device__ __forceinline__ WordInfo classify_word(const uint32_t* __restrict__ bits, long long w, long long n, int D, int H, int W,
+                                                  const uint8_t* ntri) {
   uint32_t v[8];
   corner_words(bits, w, H, W, v);
   uint32_t mixed = 0;
@@ -86,9 +88,10 @@ __device__ __forceinline__ WordInfo classify_word(const uint32_t* __restrict__ b
     // which nodes of the word have a +x / +y / +z neighbour (a word may straddle rows and planes)
     uint32_t xi = 0, yi = 0, zi = 0;
     const long long i0 = 32 * w;
-    int x = (int)(i0 % W);
-    const long long t = i0 / W;
-    int y = (int)(t % H), z = (int)(t / H);
+    const uint32_t i0u = (uint32_t)i0;                              // (the volume has fewer than 2^31 nodes)
+    const uint32_t t = i0u / (uint32_t)W;
+    int x = (int)(i0u - t * (uint32_t)W);
+    int z = (int)(t / (uint32_t)H), y = (int)(t - (uint32_t)z * (uint32_t)H);
     for (int b = 0; b < 32 && i0 + b < n; ++b) {
       if (x + 1 < W) xi |= 1u << b;
       if (y + 1 < H) yi |= 1u << b;
@@ -102,7 +105,7 @@ __device__ __forceinline__ WordInfo classify_word(const uint32_t* __restrict__ b
     while (cm) {
       const int b = __ffs((int)cm) - 1;
       cm &= cm - 1;
-      wi.nt += (uint32_t)__ldg(&g_mc_tri[case_of(v, b)][15]);      // byte 15 of a table row = its triangle count
+      wi.nt += (uint32_t)ntri[case_of(v, b)];
     }
   }
   return wi;
@@ -112,42 +115,51 @@ __device__ __forceinline__ unsigned long long word_counts(const uint4 q) {
   return (unsigned long long)(__popc(q.x) + __popc(q.y) + __popc(q.z)) | ((unsigned long long)q.w << 32);
 }
 
-// The scan's first pass, specialised: one thread per word classifies it (coalesced, 2 words per thread of a 1024-thread
-// CTA = one 2048-word chunk of mp_scan), stores its info, and the CTA reduces the (vertex, triangle) counts to the chunk
-// total; the last CTA turns the totals into offsets (mpscan::finish_block_sums).  A functor inside block_sums_kernel had one
-// thread classify eight consecutive words in a row (23.6 us against 11.0 + 6.6 for classify + sums as two launches).
-constexpr int kClassifyThreads = 1024;
-static_assert(mpscan::kChunk == 2 * kClassifyThreads, "one CTA = one chunk of the ordered scan");
+// The scan's first pass, specialised: one thread per word classifies it (coalesced), stores its info, and the CTA reduces the
+// (vertex, triangle) counts.  A CTA covers a QUARTER of a 2048-word chunk of mp_scan (256 threads x 2 words) and adds its total
+// into the chunk's slot: the words with a surface cluster in a few z ranges, and with whole chunks per CTA (1024 threads) the
+// few CTAs that got them set the kernel's time (19.4 us; the classification as its own 256-thread kernel + a sums pass took
+// 11.0 + 6.6).  The last CTA turns the chunk totals into offsets (mpscan::finish_block_sums).  sums[] must be zero on entry.
+// A functor inside the generic block_sums_kernel was slower still (23.6 us: one thread classified eight consecutive words).
+constexpr int kClassifyThreads = 256;
+constexpr int kClassifyWords = 2 * kClassifyThreads;                  // words per CTA
+constexpr int kClassifySplit = mpscan::kChunk / kClassifyWords;       // CTAs per chunk of the ordered scan
+static_assert(mpscan::kChunk % kClassifyWords == 0, "a CTA must not straddle two chunks of the ordered scan");
 __global__ void __launch_bounds__(kClassifyThreads)
 classify_sums_kernel(const uint32_t* __restrict__ bits, WordInfo* __restrict__ info, long long n, int D, int H, int W,
                      unsigned long long* __restrict__ sums, int nb, unsigned long long* __restrict__ total) {
+  // the triangle counts of the 256 cases: a word with a surface inside looks up one per mixed cell, back to back
+  __shared__ uint8_t s_ntri[256];
+  if (threadIdx.x < 256) s_ntri[threadIdx.x] = g_mc_tri[threadIdx.x][15];
+  __syncthreads();
   const long long n_words = (n + 31) >> 5;
   unsigned long long s = 0;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    const long long w = (long long)blockIdx.x * mpscan::kChunk + j * kClassifyThreads + threadIdx.x;
+    const long long w = (long long)blockIdx.x * kClassifyWords + j * kClassifyThreads + threadIdx.x;
     if (w < n_words) {
-      const WordInfo wi = classify_word(bits, w, n, D, H, W);
+      const WordInfo wi = classify_word(bits, w, n, D, H, W, s_ntri);
       const uint4 q = make_uint4(wi.ex, wi.ey, wi.ez, wi.nt);
       *reinterpret_cast<uint4*>(info + w) = q;
       s += word_counts(q);
     }
   }
-  // CTA total: warp shuffles, then one warp over the 32 warp totals
-  __shared__ unsigned long long s_warp[kClassifyThreads / 32];
+  // CTA total: warp shuffles, then one warp over the warp totals
+  __shared__ unsigned long long s_warp[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) s_warp[warp] = s;
   __syncthreads();
   if (warp == 0) {
-    unsigned long long t = s_warp[lane];
+    unsigned long long t = lane < kClassifyThreads / 32 ? s_warp[lane] : 0ull;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     if (lane == 0) s_warp[0] = t;
   }
   __syncthreads();
-  mpscan::finish_block_sums<kClassifyThreads>(s_warp[0], sums, nb, total, mpscan::NoPost());
+  mpscan::finish_block_sums<kClassifyThreads>(s_warp[0], sums, nb, total, mpscan::NoPost(), (int)(blockIdx.x / kClassifySplit),
+                                              (int)gridDim.x, true);
 }
 
 // functor of the scan's SECOND pass (and of everything after it): the stored info

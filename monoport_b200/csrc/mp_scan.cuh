@@ -76,21 +76,24 @@ __device__ __forceinline__ void load_bytes8(const uint8_t* p, long long i, uint3
 }
 
 // Tail of a scan's first pass, called by ALL threads of every CTA with the CTA's total `tot`: sums[0..nb) <- exclusive scan of
-// the CTA totals, total[0] <- grand total.  total[1] is the ticket counter: zero on entry (zero-initialised once by the owner
-// of the workspace), reset to zero by the last CTA.  NT = threads per CTA.
+// the chunk totals, total[0] <- grand total.  total[1] is the ticket counter: zero on entry (zero-initialised once by the owner
+// of the workspace), reset to zero by the last CTA.  NT = threads per CTA.  By default one CTA = one chunk (slot = blockIdx.x,
+// n_ctas = nb); with `accumulate` several CTAs add their totals into one chunk's slot (sums[] must then be zero on entry).
 template <int NT = kThreads, class P>
 __device__ __forceinline__ void finish_block_sums(unsigned long long tot, unsigned long long* __restrict__ sums, int nb,
-                                                  unsigned long long* __restrict__ total, P post) {
+                                                  unsigned long long* __restrict__ total, P post, int slot, int n_ctas,
+                                                  bool accumulate) {
   __shared__ bool is_last;
   if (threadIdx.x == 0) {
-    sums[blockIdx.x] = tot;
+    if (accumulate) atomicAdd(&sums[slot], tot);
+    else sums[slot] = tot;
     __threadfence();
-    is_last = atomicAdd(&total[1], 1ull) == (unsigned long long)(nb - 1);
+    is_last = atomicAdd(&total[1], 1ull) == (unsigned long long)(n_ctas - 1);
   }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // the last CTA turns the nb CTA totals into exclusive offsets: thread t owns the contiguous run [t*per, (t+1)*per)
+  // the last CTA turns the nb chunk totals into exclusive offsets: thread t owns the contiguous run [t*per, (t+1)*per)
   // (two independent passes over L2-resident values + ONE block scan, instead of a block scan per 256 entries)
   const int per = (nb + NT - 1) / NT;
   const int b0 = min((int)threadIdx.x * per, nb), b1 = min(b0 + per, nb);
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(kThreads) block_sums_kernel(F f, long long n, 
   for (int j = 0; j < kItems; ++j) s += v[j];
   unsigned long long tot;
   block_excl_scan(s, &tot);
-  finish_block_sums<kThreads>(tot, sums, nb, total, post);
+  finish_block_sums<kThreads>(tot, sums, nb, total, post, (int)blockIdx.x, nb, false);
 }
 
 template <class F, class E>

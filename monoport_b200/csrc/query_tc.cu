@@ -103,12 +103,13 @@ struct TcParams {
 };
 constexpr int kTraceTile = 8;
 // v3 event ids: MMA issuer 0..31, worker warp 4 at 32.., worker warp 8 at 64.., sampler warp 2 at 96..
-#define TRACE(cond, id) do { if (prm.trace && (cond)) prm.trace[id] = (unsigned long long)clock64(); } while (0)
+// (all of these compile to nothing unless the kernel is instantiated with PROF: `kProf` is a constant of its scope)
+#define TRACE(cond, id) do { if (kProf && prm.trace && (cond)) prm.trace[id] = (unsigned long long)clock64(); } while (0)
 enum Prof { P_TOTAL = 0, P_XREADY, P_ACC0FREE, P_WFULL, P_UNUSED4, P_H0READY, P_ACC1DRAINED, P_H1READY, P_H2READY,
             P_W_SAMPLE = 16, P_W_ACC0FULL, P_W_H0FREE, P_W_ACC1FULL, P_W_ACC2FULL, P_W_ACC3FULL, P_W_DRAIN0, P_W_DRAIN1,
             P_W_DRAIN2, P_W_DRAIN3, P_W_XFREE };
-#define PROF_T0() const long long _t0 = prof ? clock64() : 0
-#define PROF_ADD(slot) do { if (prof) prof[slot] += (unsigned long long)(clock64() - _t0); } while (0)
+#define PROF_T0() const long long _t0 = (kProf && prof) ? clock64() : 0
+#define PROF_ADD(slot) do { if (kProf && prof) prof[slot] += (unsigned long long)(clock64() - _t0); } while (0)
 
 struct Smem {
   // offsets inside the 1024-aligned dynamic shared memory block
@@ -270,9 +271,12 @@ __device__ __forceinline__ void warp_wait_cluster(uint64_t* bar, uint32_t parity
 // (cp.async.bulk ... .multicast::cluster), so the L2 serves each weight byte once per pair.  Everything else is CTA-local
 // (cta_group::1 MMAs); the only coupling is the ring: a slot is refilled when BOTH issuers have released it
 // (tcgen05.commit multicast onto both CTAs' "empty" barriers), so the two CTAs drift by at most the ring's three stages.
-template <bool PEERS = false, int CG = 1, bool WM = false>
+// PROF: the in-kernel cycle attribution / trace (MONOPORT_B200_TC_PROF, MONOPORT_B200_TC_TRACE) as its own instantiation: the
+// shipped kernels carry no trace of it (the issue loop is sensitive to every instruction, see the issuer below).
+template <bool PEERS = false, int CG = 1, bool WM = false, bool PROF = false>
 __global__ void __launch_bounds__(kThreads, 1)
 query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst) {
+  constexpr bool kProf = PROF;
   static_assert(!(WM && CG == 2), "weight multicast is a variant of the one-CTA program");
   constexpr int TP = (CG == 2 || WM) ? 2 : 1;          // tiles (CTAs) per scheduling group
   using C = CfgT<CG>;
@@ -286,7 +290,7 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (mp_guard_skips(prm.amax, prm.amax_limit, prm.guard)) return;      // (uniform over the grid: nothing is allocated yet)
-  unsigned long long* prof = prm.prof ? prm.prof + (size_t)blockIdx.x * 32 : nullptr;
+  unsigned long long* prof = (kProf && prm.prof) ? prm.prof + (size_t)blockIdx.x * 32 : nullptr;
 
   long long n = src.n;
   if (src.count_dev) {
@@ -391,203 +395,176 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
     // (the peer CTA's warp 1 has nothing to do: the leader issues the MMAs of both tiles)
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    // The WHOLE warp runs the control flow (barrier waits, stage counters, descriptor arithmetic: all warp-uniform, so the
-    // compiler keeps them in uniform registers); only the tcgen05 instructions themselves are predicated on one elected
-    // lane.  Issuing from inside `if (lane == 0)` cost ~20 extra instructions per MMA (an elect / R2UR loop to move the
-    // operands to uniform registers) and made the ISSUE rate the bound of every MMA phase: tools/tc_rate.cu measures 246
-    // cycles per 128x256x16 MMA that way against 163 with unrolled K-steps (profiles/r02_call4_tc_rate_issue_patterns.txt).
+    // The WHOLE warp runs the control flow -- ring position, phase counters, descriptor bases: all warp-uniform, so the
+    // compiler keeps them in uniform registers -- and ONE elected lane executes, per sampled chunk / per phase, a single
+    // region with everything that has to happen in order: barrier waits, fences, the tcgen05.mma instructions and their
+    // commits.  How the issue loop is written decides the rate of the tensor pipe (tools/tc_rate.cu, cycles per 128x256x16
+    // MMA inside this pipeline, weights streaming + worker hand-offs):  issuing from inside `if (lane == 0)` 246 (the
+    // operands become per-thread values and reach the uniform registers through an elect / R2UR loop per instruction);
+    // warp-uniform loop with separate elected regions for every wait, the MMAs and the commit 187;  one elected region per
+    // weight stage 161;  one region per two stages 147;  the bare loop without hand-offs 128 = the pipe's floor
+    // (profiles/r02_call17_*, r02_call18_*).  Hence: one region per CHUNK (four stages, 16 MMAs) / per phase.
     {
-      unsigned long long* const prof_all = prof;
-      prof = (lane == 0) ? prof_all : nullptr;           // one lane records the in-kernel timers
+      [[maybe_unused]] unsigned long long* const prof_el = prof;   // (PROF builds: the elected lane records the in-kernel timers)
       const uint32_t idesc128 = tc::make_idesc_f16(128 * CG, 128);
       const uint32_t idesc256 = tc::make_idesc_f16(128 * CG, 256);
-      const uint32_t sX = tc::smem_u32(smem + Smem::X);
-      const uint32_t sH0 = tc::smem_u32(smem + Smem::H0);
-      const uint32_t sW = tc::smem_u32(smem + Smem::Wr);
-      uint32_t it = 0;
-      uint32_t c_xready = 0, c_h0ready[2] = {0, 0}, c_h1ready = 0, c_h2ready = 0, c_tiledone = 0;
-      const long long t_begin = prof ? clock64() : 0;
-      // (with a CTA pair the arrivals and the weight bytes partly come from the peer CTA: cluster-scope acquire)
-      auto wait_both = [&](int local_bar, int, uint32_t& count) {
-        if constexpr (CG == 1) warp_wait(bars + local_bar, count & 1u);
-        else warp_wait_cluster(bars + local_bar, count & 1u);
-        ++count;
+      // descriptor bases; inside the regions only compile-time multiples are added (address field = bytes >> 4)
+      const uint64_t dX = tc::make_sdesc_sw128(tc::smem_u32(smem + Smem::X), 1024);
+      const uint64_t dH0 = tc::make_sdesc_sw128(tc::smem_u32(smem + Smem::H0), 1024);
+      const uint64_t dW = tc::make_sdesc_sw128(tc::smem_u32(smem + Smem::Wr), 1024);
+      constexpr uint64_t kKb = 16384 >> 4;                 // one K-block of an A operand (128 rows x 64 channels)
+      constexpr uint64_t kStage = C::StageBytes >> 4;      // one ring slot
+      constexpr uint64_t kSub = C::Sub >> 4;               // second K-block of a two-K-block (128-row tile) stage
+      uint32_t slot = 0, wpar = 0;                         // ring slot of the next stage and the parity of its "full" phase
+      uint32_t c_xready = 0, n_chunks = 0, c_h1ready = 0, c_h2ready = 0, c_tiledone = 0;
+      const long long t_begin = (kProf && prof) ? clock64() : 0;
+      // ---- (all of these run inside an elected region: one lane)
+      auto wait_b = [&](int which, uint32_t par, [[maybe_unused]] int prof_slot) {
+        [[maybe_unused]] long long t0 = 0;
+        if constexpr (kProf) t0 = prof_el ? clock64() : 0;
+        if constexpr (CG == 1 && !WM) tc::mbar_wait(bars + which, par);
+        else tc::mbar_wait_cluster(bars + which, par);       // (arrivals / bytes partly come from the peer CTA)
+        if constexpr (kProf) { if (prof_el && prof_slot >= 0) prof_el[prof_slot] += (unsigned long long)(clock64() - t0); }
       };
-      auto next_stage = [&]() -> uint32_t {
-        const int slot = it % C::Stages;
-        const uint32_t par = (it / C::Stages) & 1u;
-        {
-          PROF_T0();
-          if constexpr (CG == 1 && !WM) warp_wait(bars + B_WFULL + slot, par);
-          else warp_wait_cluster(bars + B_WFULL + slot, par);
-          PROF_ADD(P_WFULL);
-        }
-        tc::tcgen05_fence_after();
-        return sW + slot * C::StageBytes;
+      auto commit_b = [&](int which) {
+        if constexpr (CG == 1) tc::mma_commit(bars + which);
+        else tc::mma_commit2(bars + which);
       };
-      auto commit_bar = [&](uint64_t* bar) {
-        if constexpr (CG == 1) tc::mma_commit(bar);
-        else tc::mma_commit2(bar);
-      };
-      auto release_stage = [&]() {
-        if (tc::elect_one()) {
-          if constexpr (WM) tc::mma_commit_pair(bars + B_WEMPTY + (it % C::Stages));
-          else commit_bar(bars + B_WEMPTY + (it % C::Stages));
-        }
-        ++it;
-      };
-      auto commit_one = [&](int which) {
-        if (tc::elect_one()) commit_bar(bars + which);
+      auto release = [&](uint32_t sl) {                      // the stage's MMAs done -> its ring slot may be refilled
+        if constexpr (WM) tc::mma_commit_pair(bars + B_WEMPTY + sl);
+        else commit_b(B_WEMPTY + (int)sl);
       };
       // one K-block (64 channels = four K = 16 steps): descriptors advance by 32 B (+2 in the address field)
-      // (MONOPORT_B200_TC_EXP bit 8: the round-1 issue pattern -- one lane builds the descriptors per MMA inside a divergent
-      // branch, which costs ~20 instructions per MMA -- kept selectable for the A/B of profiles/r02_call8_*)
-      const bool slow_issue = (prm.exp & 8) != 0;
-      auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool& first) {
-        if (slow_issue) {
-          if (lane == 0) {
-#pragma unroll 1
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ad = tc::make_sdesc_sw128(a_addr + kk * 32, 1024), bd = tc::make_sdesc_sw128(b_addr + kk * 32, 1024);
-              if constexpr (CG == 1) tc::mma_ss(d, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
-              else tc::mma_ss2(d, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
-            }
-          }
-          __syncwarp();
-          first = false;
-          return;
-        }
-        const uint64_t ad0 = tc::make_sdesc_sw128(a_addr, 1024), bd0 = tc::make_sdesc_sw128(b_addr, 1024);
-        const uint32_t acc0 = first ? 0u : 1u;
-        if (tc::elect_one()) {
+      auto kblock_ss = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc0) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            if constexpr (CG == 1) tc::mma_ss(d, ad0 + 2 * kk, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
-            else tc::mma_ss2(d, ad0 + 2 * kk, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
-          }
+        for (int kk = 0; kk < 4; ++kk) {
+          if constexpr (CG == 1) tc::mma_ss(d, ad + 2 * kk, bd + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
+          else tc::mma_ss2(d, ad + 2 * kk, bd + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
         }
-        first = false;
       };
-      auto kblock_ts = [&](uint32_t d, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool& first) {
-        if (slow_issue) {
-          if (lane == 0) {
-#pragma unroll 1
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t bd = tc::make_sdesc_sw128(b_addr + kk * 32, 1024);
-              if constexpr (CG == 1) tc::mma_ts(d, a_tmem + kk * 8, bd, idesc, (first && kk == 0) ? 0u : 1u);
-              else tc::mma_ts2(d, a_tmem + kk * 8, bd, idesc, (first && kk == 0) ? 0u : 1u);
-            }
-          }
-          __syncwarp();
-          first = false;
-          return;
-        }
-        const uint64_t bd0 = tc::make_sdesc_sw128(b_addr, 1024);
-        const uint32_t acc0 = first ? 0u : 1u;
-        if (tc::elect_one()) {
+      auto kblock_ts = [&](uint32_t d, uint32_t a_tmem, uint64_t bd, uint32_t idesc, uint32_t acc0) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            if constexpr (CG == 1) tc::mma_ts(d, a_tmem + kk * 8, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
-            else tc::mma_ts2(d, a_tmem + kk * 8, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
-          }
+        for (int kk = 0; kk < 4; ++kk) {
+          if constexpr (CG == 1) tc::mma_ts(d, a_tmem + kk * 8, bd + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
+          else tc::mma_ts2(d, a_tmem + kk * 8, bd + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
         }
-        first = false;
+      };
+      // ---- (uniform, all lanes) the ring positions of the next N stages
+      auto take = [&](uint32_t (&sl)[12], uint32_t (&pr)[12], int n_take) {
+#pragma unroll
+        for (int q = 0; q < 12; ++q)
+          if (q < n_take) {
+            sl[q] = slot; pr[q] = wpar;
+            if (++slot == (uint32_t)C::Stages) { slot = 0; wpar ^= 1u; }
+          }
       };
 
       for (long long g = g0; g < n_groups; g += gstep) {
         // acc1 = [0,512) overlaps the previous tile's H2 (readers already issued, in order), acc2 (drained before
         // B_H2_READY, waited) and acc3 (drained by the fp32 tail: B_TILE_DONE)
-        bool need_tile_done = g != g0;
-        bool first1[2] = {true, true};
-        const bool tr = blockIdx.x == 0 && lane == 0 && (g - g0) / gstep == kTraceTile;
-        TRACE(tr, 0);
-        const long long t_ph0 = prof ? clock64() : 0;
-        // ---- layer 1, hidden part: 8 sampled layer-0 chunks x 2 K-blocks x 2 output halves
+        const bool later_tile = g != g0;
+        uint32_t sl[12], pr[12];
+        const long long t_ph0 = (kProf && prof) ? clock64() : 0;
+        // ---- layer 1, hidden part: 8 sampled layer-0 chunks x (2 K-blocks x 2 output halves = 4 stages)
+#pragma unroll 1
         for (int c = 0; c < 8; ++c) {
           const int b = c & 1;
-          { PROF_T0(); wait_both(B_H0_READY0 + b, 0, c_h0ready[b]); PROF_ADD(P_H0READY); }
-          TRACE(tr, 1 + c);
-          tc::tcgen05_fence_after();
-          for (int kb = 0; kb < 2; ++kb)
-            for (int nh = 0; nh < 2; ++nh) {
-              const uint32_t w = next_stage();
-              if (nh == 1 && need_tile_done) {
-                // [384,512) holds the previous tile's acc3 until its fp32 tail has drained it; the lower half of acc1
-                // does not overlap it, so only the first MMA into [256,512) has to wait
-                PROF_T0();
-                wait_both(B_TILE_DONE, 0, c_tiledone);
-                PROF_ADD(P_ACC1DRAINED);
-                tc::tcgen05_fence_after();
-                need_tile_done = false;
-              }
-              kblock_ss(tbase + cAcc1 + nh * 256, sH0 + b * 32768 + kb * 16384, w, idesc256, first1[nh]);
-              release_stage();
+          const uint32_t p_h0 = (n_chunks >> 1) & 1u;          // the two chunk buffers alternate strictly: use (n_chunks / 2) of buffer b
+          ++n_chunks;
+          take(sl, pr, 4);
+          // [384,512) holds the previous tile's acc3 until its fp32 tail has drained it; the lower half of acc1 does not
+          // overlap it, so only the first MMA into [256,512) has to wait
+          const bool wait_td = later_tile && c == 0;
+          const uint32_t p_td = c_tiledone & 1u;
+          if (wait_td) ++c_tiledone;
+          const uint32_t acc_first = c == 0 ? 0u : 1u;
+          if (tc::elect_one()) {
+            wait_b(B_H0_READY0 + b, p_h0, P_H0READY);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int kb = q >> 1, nh = q & 1;
+              wait_b(B_WFULL + (int)sl[q], pr[q], P_WFULL);
+              if (q == 1 && wait_td) wait_b(B_TILE_DONE, p_td, P_ACC1DRAINED);
+              tc::tcgen05_fence_after();
+              kblock_ss(tbase + cAcc1 + nh * 256, dH0 + (uint64_t)(b * 2 + kb) * kKb, dW + sl[q] * kStage, idesc256,
+                        kb == 0 ? acc_first : 1u);
+              release(sl[q]);
             }
-          commit_one(B_H0_FREE0 + b);
-        }
-        if (prof) prof[9] += (unsigned long long)(clock64() - t_ph0);
-        TRACE(tr, 9);
-        // ---- layer 1, skip part: A = X
-        { PROF_T0(); wait_both(B_XREADY, 0, c_xready); PROF_ADD(P_XREADY); }
-        TRACE(tr, 10);
-        const long long t_ph1 = prof ? clock64() : 0;
-        tc::tcgen05_fence_after();
-        for (int kb = 0; kb < 4; ++kb)
-          for (int nh = 0; nh < 2; ++nh) {
-            const uint32_t w = next_stage();
-            kblock_ss(tbase + cAcc1 + nh * 256, sX + kb * 16384, w, idesc256, first1[nh]);
-            release_stage();
+            commit_b(B_H0_FREE0 + b);
           }
-        commit_one(B_ACC1_FULL);
-        if (prof) prof[10] += (unsigned long long)(clock64() - t_ph1);
-        TRACE(tr, 11);
+        }
+        if constexpr (kProf) { if (prof && lane == 0) prof[9] += (unsigned long long)(clock64() - t_ph0); }
+        // ---- layer 1, skip part: A = X (4 K-blocks x 2 output halves)
+        {
+          const uint32_t p_x = c_xready & 1u;
+          ++c_xready;
+          take(sl, pr, 8);
+          const long long t_ph1 = (kProf && prof) ? clock64() : 0;
+          if (tc::elect_one()) {
+            wait_b(B_XREADY, p_x, P_XREADY);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int kb = q >> 1, nh = q & 1;
+              wait_b(B_WFULL + (int)sl[q], pr[q], P_WFULL);
+              tc::tcgen05_fence_after();
+              kblock_ss(tbase + cAcc1 + nh * 256, dX + (uint64_t)kb * kKb, dW + sl[q] * kStage, idesc256, 1u);
+              release(sl[q]);
+            }
+            commit_b(B_ACC1_FULL);
+          }
+          if constexpr (kProf) { if (prof && lane == 0) prof[10] += (unsigned long long)(clock64() - t_ph1); }
+        }
         // ---- layer 2: A = H1 from TMEM (8 K-blocks) + X (4 K-blocks) -> acc2 [128,384)
-        { PROF_T0(); wait_both(B_H1_READY, 0, c_h1ready); PROF_ADD(P_H1READY); }
-        TRACE(tr, 12);
-        tc::tcgen05_fence_after();
         {
-          const long long t_ph2 = prof ? clock64() : 0;
-          bool first = true;
-          for (int kb = 0; kb < 8; ++kb) {
-            if (prof && kb == 4) prof[11] += (unsigned long long)(clock64() - t_ph2);   // first 4 TS K-blocks (16 MMAs N=256)
-            const uint32_t w = next_stage();
-            const uint32_t a = tbase + (kb < 4 ? cH1lo + kb * 32 : cH1hi + (kb - 4) * 32);
-            kblock_ts(tbase + cAcc2, a, w, idesc256, first);
-            release_stage();
+          const uint32_t p_h1 = c_h1ready & 1u;
+          ++c_h1ready;
+          take(sl, pr, 12);
+          if (tc::elect_one()) {
+            wait_b(B_H1_READY, p_h1, P_H1READY);
+            [[maybe_unused]] long long t_ph2 = 0;
+            if constexpr (kProf) t_ph2 = prof_el ? clock64() : 0;
+#pragma unroll
+            for (int q = 0; q < 12; ++q) {
+              if constexpr (kProf) { if (prof_el && q == 4) prof_el[11] += (unsigned long long)(clock64() - t_ph2); }   // first 4 TS K-blocks
+              wait_b(B_WFULL + (int)sl[q], pr[q], P_WFULL);
+              tc::tcgen05_fence_after();
+              if (q < 8) kblock_ts(tbase + cAcc2, tbase + (q < 4 ? cH1lo + q * 32 : cH1hi + (q - 4) * 32), dW + sl[q] * kStage, idesc256,
+                                   q == 0 ? 0u : 1u);
+              else kblock_ss(tbase + cAcc2, dX + (uint64_t)(q - 8) * kKb, dW + sl[q] * kStage, idesc256, 1u);
+              release(sl[q]);
+            }
+            commit_b(B_ACC2_FULL);
           }
-          for (int kb = 0; kb < 4; ++kb) {
-            const uint32_t w = next_stage();
-            kblock_ss(tbase + cAcc2, sX + kb * 16384, w, idesc256, first);
-            release_stage();
-          }
-          commit_one(B_ACC2_FULL);
-          TRACE(tr, 13);
         }
-        // ---- layer 3 -> acc3 [384,512); skip part first, then X is dead
+        // ---- layer 3 -> acc3 [384,512): skip part first (then X is dead), then H2 from TMEM; two K-blocks per stage
         {
-          bool first = true;
-          for (int s = 0; s < 2; ++s) {
-            const uint32_t w = next_stage();
-            kblock_ss(tbase + cAcc3, sX + (2 * s) * 16384, w, idesc128, first);
-            kblock_ss(tbase + cAcc3, sX + (2 * s + 1) * 16384, w + C::Sub, idesc128, first);
-            release_stage();
+          const uint32_t p_h2 = c_h2ready & 1u;
+          ++c_h2ready;
+          take(sl, pr, 4);
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              wait_b(B_WFULL + (int)sl[q], pr[q], P_WFULL);
+              tc::tcgen05_fence_after();
+              kblock_ss(tbase + cAcc3, dX + (uint64_t)(2 * q) * kKb, dW + sl[q] * kStage, idesc128, q == 0 ? 0u : 1u);
+              kblock_ss(tbase + cAcc3, dX + (uint64_t)(2 * q + 1) * kKb, dW + sl[q] * kStage + kSub, idesc128, 1u);
+              release(sl[q]);
+            }
+            commit_b(B_XFREE);
+            wait_b(B_H2_READY, p_h2, P_H2READY);
+#pragma unroll
+            for (int q = 2; q < 4; ++q) {
+              wait_b(B_WFULL + (int)sl[q], pr[q], P_WFULL);
+              tc::tcgen05_fence_after();
+              kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * (q - 2)) * 32, dW + sl[q] * kStage, idesc128, 1u);
+              kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * (q - 2) + 1) * 32, dW + sl[q] * kStage + kSub, idesc128, 1u);
+              release(sl[q]);
+            }
+            commit_b(B_ACC3_FULL);
           }
-          commit_one(B_XFREE);
-          TRACE(tr, 14);
-          { PROF_T0(); wait_both(B_H2_READY, 0, c_h2ready); PROF_ADD(P_H2READY); }
-          TRACE(tr, 15);
-          tc::tcgen05_fence_after();
-          for (int s = 0; s < 2; ++s) {
-            const uint32_t w = next_stage();
-            kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * s) * 32, w, idesc128, first);
-            kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * s + 1) * 32, w + C::Sub, idesc128, first);
-            release_stage();
-          }
-          commit_one(B_ACC3_FULL);
-          TRACE(tr, 16);
         }
       }
-      if (prof) prof[P_TOTAL] = (unsigned long long)(clock64() - t_begin);
+      if constexpr (kProf) { if (prof && lane == 0) prof[P_TOTAL] = (unsigned long long)(clock64() - t_begin); }
     }
   } else if (warp == 2 || warp == 3) {
     // ============================== samplers: X (skip operand) + per-point scalars ==============================
@@ -2088,7 +2065,7 @@ int mp_tc_prepare(mp_mlp* mlp) {
 #ifndef MP_CUDA_EMU
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(query_tc3_kernel<false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::Total + 1024);
 #endif
   if (e == cudaSuccess) e = cudaFuncSetAttribute(g0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG0Smem);
   if (e != cudaSuccess) {
@@ -2182,7 +2159,7 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
   const long long tiles = (src.n + kTile - 1) / kTile;
   static const int do_prof = [] { const char* v = getenv("MONOPORT_B200_TC_PROF"); return v ? atoi(v) : 0; }();
   unsigned long long* d_prof = nullptr;
-  if (do_prof && tiles >= 2 * sms) {
+  if (do_prof && (tiles >= 2 * sms || do_prof >= 2)) {        // (=2: also launches of a wave or less)
     MP_CUDA(cudaMalloc(&d_prof, (size_t)sms * 32 * sizeof(unsigned long long)));
     MP_CUDA(cudaMemset(d_prof, 0, (size_t)sms * 32 * sizeof(unsigned long long)));
     prm.prof = d_prof;
@@ -2256,7 +2233,7 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
   // pair halves the weight bytes per SM, but a 2-CTA MMA runs at the same per-SM rate (tools/tc_rate.cu) and every operand
   // hand-off and weight-stage release crosses the cluster, which costs more than the halved stream gains.
   static const int forced_cg = [] { const char* v = getenv("MONOPORT_B200_TC_CG"); return v ? atoi(v) : 0; }();
-  if (pk->pair_ok && forced_cg == 2 && sms >= 2) {
+  if (pk->pair_ok && forced_cg == 2 && sms >= 2 && dst.n_peers == 0) {
     prm.tmap_pair[0] = pk->tmap_pair[0];
     prm.tmap_pair[1] = pk->tmap_pair[1];
     const long long groups = (tiles + 1) / 2;
@@ -2275,8 +2252,7 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (dst.n_peers > 0) MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc3_kernel<true, 2>, prm, src, cal, dst));
-    else MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc3_kernel<false, 2>, prm, src, cal, dst));
+    MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc3_kernel<false, 2>, prm, src, cal, dst));
     report(2 * pairs);
     return MP_OK;
   }
@@ -2311,6 +2287,7 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
   const int grid = (int)(tiles < (long long)sms ? tiles : sms);
 #ifndef MP_CUDA_EMU
   if (dst.n_peers > 0) query_tc3_kernel<true, 1><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);      // fused slab exchange
+  else if (prm.prof || prm.trace) query_tc3_kernel<false, 1, false, true><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
   else query_tc3_kernel<false, 1><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);
 #else
   if (dst.n_peers > 0) MP_EMU_LAUNCH(grid, kThreads, (query_tc3_kernel<true, 1>(prm, src, cal, dst)));

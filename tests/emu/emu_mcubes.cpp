@@ -61,7 +61,8 @@ int main(int argc, char** argv) {
   uint32_t n_active = 0;
   WordCountF f{info.data()};
   PrefixEmit em{prefix.data(), active.data(), &n_active};
-  cuda_emu::launch(dim3(nb), dim3(kClassifyThreads),
+  std::fill(sums.begin(), sums.end(), 0ull);            // (mp_mcubes_count zeroes the chunk totals: the CTAs accumulate)
+  cuda_emu::launch(dim3((unsigned)((n_words + kClassifyWords - 1) / kClassifyWords)), dim3(kClassifyThreads),
                    [&] { classify_sums_kernel(bits.data(), info.data(), n, D, H, W, sums.data(), nb, total); });
   cuda_emu::launch(dim3(nb), dim3(mpscan::kThreads),
                    [&] { mpscan::emit_kernel<WordCountF, PrefixEmit>(f, em, n_words, sums.data()); });

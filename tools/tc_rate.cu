@@ -11,6 +11,8 @@
 //                                                 16 = N = 128 instead of 256          32 = alternate the accumulator every MMA
 //                                                 64 = fully unrolled issue loop       128 = a second issuing warp (no streaming:
 //                                                      each warp issues half of the MMAs into its own accumulator)
+//                                                 512 = warp-uniform issue loop, one elected lane per MMA (the shipped pattern);
+//                                                      combines with 1, 2, 4, 8, 16      1024 = (with 2) the workers store 4x the bytes
 // Prints cycles per MMA (min / mean over the CTAs that issue) and the implied fraction of the 128-cycle floor.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -lineinfo -o tc_rate tools/tc_rate.cu -lcuda
 #include <cuda.h>
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(kThreads, 1) rate_kernel(const __grid_constant
   int n_stages_half = n_stages;
   const bool f_stream = flags & 1, f_workers = flags & 2, f_ts = flags & 4, f_tmap = flags & 8;
   const bool f_n128 = flags & 16, f_alt = flags & 32, f_unroll = flags & 64, f_two = flags & 128, f_noacc = flags & 256;   // 256: never accumulate (D is not read)
-  const bool f_uniform = flags & 512;   // 512: warp-uniform issue loop, one elected lane per MMA (no streaming / workers)
+  const bool f_uniform = flags & 512;   // 512: warp-uniform issue loop, one elected lane per MMA (combines with 1, 2, 4, 8, 16)
 
   for (int i = tid; i < (Off::Wr + 98304) / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
@@ -112,20 +114,93 @@ __global__ void __launch_bounds__(kThreads, 1) rate_kernel(const __grid_constant
     for (int sl = 0; sl < Stages; ++sl) tc::mbar_wait(bars + B_FULL + sl, 0);
     tc::tcgen05_fence_after();
     const long long t0 = clock64();
-    for (int it = 0; it < n_stages; ++it) {
-      const int slot = it % Stages;
-      if (f_stream && it >= Stages) { tc::mbar_wait(bars + B_FULL + slot, (it / Stages) & 1); tc::tcgen05_fence_after(); }
-      const uint64_t ad0 = tc::make_sdesc_sw128(sX + (it & 3) * 16384, 1024), bd0 = tc::make_sdesc_sw128(sW + slot * StageBytes, 1024);
-      const uint32_t d = tbase + (it & 1) * 256;
-      if (tc::elect_one()) {
+    const uint32_t sH0u = tc::smem_u32(smem + Off::H0);
+    const bool f_poll_all = flags & 2048;     // every lane polls the barriers (no elected poll + __syncwarp)
+    const bool f_one_region = flags & 4096;   // ONE elected region per stage: waits, fence, 4 MMAs, commits
+    const bool f_two_stages = flags & 8192;   // (with 4096) two stages per elected region
+    const bool f_no_sync = flags & 16384;     // (with 4096) no __syncwarp after the region
+    uint32_t c_ready_u[2] = {0, 0};
+    // everything one stage needs, computed by ALL lanes (warp-uniform values, so the tcgen05 operands stay uniform)
+    struct St { uint64_t ad0, bd0; uint32_t d, par_ready, par_full, acc0; int slot, b; bool w_ready, w_full, w_free; };
+    auto prep = [&](int it) -> St {
+      St q;
+      q.slot = it % Stages;
+      const int chunk = it >> 2, kb = (it >> 1) & 1;                          // 4 stages (2 K-blocks x 2 N-halves) per chunk
+      q.b = chunk & 1;
+      const uint32_t a_addr = f_workers ? sH0u + q.b * 32768 + kb * 16384 : sX + (it & 3) * 16384;
+      q.ad0 = tc::make_sdesc_sw128(a_addr, 1024);
+      q.bd0 = tc::make_sdesc_sw128(sW + q.slot * StageBytes, 1024);
+      q.d = tbase + (it & 1) * 256;
+      q.w_ready = f_workers && (it & 3) == 0;
+      q.w_full = f_stream && it >= Stages;
+      q.w_free = f_workers && (it & 3) == 3;
+      q.par_ready = c_ready_u[q.b] & 1u;
+      q.par_full = (it / Stages) & 1;
+      q.acc0 = it < 2 ? 0u : 1u;
+      if (q.w_ready) ++c_ready_u[q.b];
+      return q;
+    };
+    auto mmas = [&](const St& q) {                                              // (inside an elected region)
+      if (f_ts) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          if constexpr (CG == 1) tc::mma_ss(d, ad0 + 2 * kk, bd0 + 2 * kk, idesc, (it < 2 && kk == 0) ? 0u : 1u);
-          else tc::mma_ss2(d, ad0 + 2 * kk, bd0 + 2 * kk, idesc, (it < 2 && kk == 0) ? 0u : 1u);
-        }
-        if (f_stream) { if constexpr (CG == 1) tc::mma_commit(bars + B_EMPTY + slot); else tc::mma_commit2(bars + B_EMPTY + slot); }
+        for (int kk = 0; kk < 4; ++kk) tc::mma_ts(q.d, tbase + kk * 8, q.bd0 + 2 * kk, idesc, kk == 0 ? q.acc0 : 1u);
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) tc::mma_ss(q.d, q.ad0 + 2 * kk, q.bd0 + 2 * kk, idesc, kk == 0 ? q.acc0 : 1u);
       }
-      __syncwarp();
+      if (f_stream) tc::mma_commit(bars + B_EMPTY + q.slot);
+      if (q.w_free) tc::mma_commit(bars + B_FREE0 + q.b);
+    };
+    auto all_in_one = [&](const St& q) {                                        // (inside an elected region)
+      if (q.w_ready) tc::mbar_wait(bars + B_READY0 + q.b, q.par_ready);
+      if (q.w_full) tc::mbar_wait(bars + B_FULL + q.slot, q.par_full);
+      tc::tcgen05_fence_after();
+      mmas(q);
+    };
+    if (flags & 32768) {      // the minimal loop of profiles/r02_call5_* (streaming only: every lane polls), kept as the control
+    for (int it = 0; it < n_stages; ++it) {
+        const int slot = it % Stages;
+        if (f_stream && it >= Stages) { tc::mbar_wait(bars + B_FULL + slot, (it / Stages) & 1); tc::tcgen05_fence_after(); }
+        const uint64_t ad0 = tc::make_sdesc_sw128(sX + (it & 3) * 16384, 1024), bd0 = tc::make_sdesc_sw128(sW + slot * StageBytes, 1024);
+        const uint32_t d = tbase + (it & 1) * 256;
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            if constexpr (CG == 1) tc::mma_ss(d, ad0 + 2 * kk, bd0 + 2 * kk, idesc, (it < 2 && kk == 0) ? 0u : 1u);
+            else tc::mma_ss2(d, ad0 + 2 * kk, bd0 + 2 * kk, idesc, (it < 2 && kk == 0) ? 0u : 1u);
+          }
+          if (f_stream) { if constexpr (CG == 1) tc::mma_commit(bars + B_EMPTY + slot); else tc::mma_commit2(bars + B_EMPTY + slot); }
+        }
+        __syncwarp();
+      }
+    } else if (CG == 2 || !f_one_region) {
+      for (int it = 0; it < n_stages; ++it) {
+        const St q = prep(it);
+        // separate regions: waits (elected poll + __syncwarp, or all lanes), then the MMAs + commits
+        if (q.w_ready) {
+          if (f_poll_all) tc::mbar_wait(bars + B_READY0 + q.b, q.par_ready);
+          else { if (tc::elect_one()) tc::mbar_wait(bars + B_READY0 + q.b, q.par_ready); __syncwarp(); }
+        }
+        if (q.w_full) {
+          if (f_poll_all) tc::mbar_wait(bars + B_FULL + q.slot, q.par_full);
+          else { if (tc::elect_one()) tc::mbar_wait(bars + B_FULL + q.slot, q.par_full); __syncwarp(); }
+        }
+        tc::tcgen05_fence_after();
+        if (tc::elect_one()) mmas(q);
+        __syncwarp();
+      }
+    } else if (!f_two_stages) {
+      for (int it = 0; it < n_stages; ++it) {
+        const St q = prep(it);
+        if (tc::elect_one()) all_in_one(q);
+        if (!f_no_sync) __syncwarp();
+      }
+    } else {
+      for (int it = 0; it < n_stages; it += 2) {
+        const St q0 = prep(it), q1 = prep(it + 1);
+        if (tc::elect_one()) { all_in_one(q0); all_in_one(q1); }
+        if (!f_no_sync) __syncwarp();
+      }
     }
     if (tc::elect_one()) { if constexpr (CG == 1) tc::mma_commit(bars + B_DONE); else tc::mma_commit2(bars + B_DONE); }
     __syncwarp();
@@ -218,12 +293,14 @@ __global__ void __launch_bounds__(kThreads, 1) rate_kernel(const __grid_constant
       ++c_free[b];
       uint8_t* dst = smem + Off::H0 + b * 32768;
       // 16 rows per warp, 2 K-blocks x 128 B per row: 2 x uint4 per lane per row pair (same store count as gen_chunk)
+      for (int rep = 0; rep < ((flags & 1024) ? 4 : 1); ++rep) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int p = wk * 16 + 4 * i + (lane >> 3);
-        const uint4 v = make_uint4(c, i, lane, wk);
-        *reinterpret_cast<uint4*>(dst + tc::sw128_offset(p, (lane & 7) * 8)) = v;
-        *reinterpret_cast<uint4*>(dst + 16384 + tc::sw128_offset(p, (lane & 7) * 8)) = v;
+        for (int i = 0; i < 4; ++i) {
+          const int p = wk * 16 + 4 * i + (lane >> 3);
+          const uint4 v = make_uint4(c, i + rep, lane, wk);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(tc::smem_u32(dst + tc::sw128_offset(p, (lane & 7) * 8))), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(tc::smem_u32(dst + 16384 + tc::sw128_offset(p, (lane & 7) * 8))), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
