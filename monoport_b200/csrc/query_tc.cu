@@ -227,19 +227,6 @@ __device__ __forceinline__ void warp_arrive_local(uint64_t* bar, int lane) {
   __syncwarp();
   if (lane == 0) tc::mbar_arrive(bar);
 }
-// Barrier wait of a warp whose control flow is warp-uniform (the MMA issuers): ONE lane -- the elected one, which also
-// issues the tcgen05 instructions -- polls, the others are released by __syncwarp().  All 32 lanes polling would be
-// equivalent on the hardware (they execute try_wait in lock step) but lets a lagging lane sleep through a whole phase when
-// lanes are scheduled independently (the CPU model of tests/emu runs one OS thread per lane).
-__device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity) {
-  if (tc::elect_one()) tc::mbar_wait(bar, parity);
-  __syncwarp();
-}
-__device__ __forceinline__ void warp_wait_cluster(uint64_t* bar, uint32_t parity) {      // arrivals may come from the peer CTA
-  if (tc::elect_one()) tc::mbar_wait_cluster(bar, parity);
-  __syncwarp();
-}
-
 // ====================================================================================================================
 // v3: layer 0 hoisted from points to texels.
 // Bilinear sampling is linear, so  W0[:, :256] . sample(F)(u,v) == sample(W0[:, :256] . F)(u,v).  G0 = W0f . F is built once
@@ -264,13 +251,12 @@ __device__ __forceinline__ void warp_wait_cluster(uint64_t* bar, uint32_t parity
 // to its CTA; the leader (rank 0) issues all MMAs, operand hand-offs are remote mbarrier arrivals on the leader's
 // barriers, MMA completions are multicast to both CTAs by tcgen05.commit.
 //
-// WM (opt-in, MONOPORT_B200_TC_WM=1; CG = 1 only; validated: the query suite passes with it; same box, same run 487 against
-// 490 Mpoints/s -- 72.5 k cycles per tile instead of 66 k at a higher clock, profiles/r02_call14_wm_ab.txt): two
-// INDEPENDENT one-CTA programs launched as a 2-CTA cluster that share
-// the weight stream: each CTA fetches half of every 32 KB stage and multicasts it into both shared memories
-// (cp.async.bulk ... .multicast::cluster), so the L2 serves each weight byte once per pair.  Everything else is CTA-local
-// (cta_group::1 MMAs); the only coupling is the ring: a slot is refilled when BOTH issuers have released it
-// (tcgen05.commit multicast onto both CTAs' "empty" barriers), so the two CTAs drift by at most the ring's three stages.
+// WM (CG = 1 only; the default for launches of several waves, see mp_launch_query_tc; MONOPORT_B200_TC_WM=0 / 1): two
+// INDEPENDENT one-CTA programs launched as a 2-CTA cluster that share the weight stream: each CTA fetches half of every 32 KB
+// stage and multicasts it into both shared memories (cp.async.bulk ... .multicast::cluster), so the L2 serves each weight
+// byte once per pair.  Everything else is CTA-local (cta_group::1 MMAs); the only coupling is the ring: a slot is refilled
+// when BOTH issuers have released it (tcgen05.commit multicast onto both CTAs' "empty" barriers), so the two CTAs drift by at
+// most the ring's three stages.
 // PROF: the in-kernel cycle attribution / trace (MONOPORT_B200_TC_PROF, MONOPORT_B200_TC_TRACE) as its own instantiation: the
 // shipped kernels carry no trace of it (the issue loop is sensitive to every instruction, see the issuer below).
 template <bool PEERS = false, int CG = 1, bool WM = false, bool PROF = false>
@@ -929,25 +915,29 @@ g0_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __half
       }
     }
   } else if (warp == 9) {
-    // ---- MMA issuer (whole warp, one elected lane per tcgen05 instruction)
+    // ---- MMA issuer: the whole warp runs the (uniform) control flow, one elected lane executes ONE region per output tile --
+    //      waits, fences, MMAs, commits (see the issuer of query_tc3_kernel)
     {
-      warp_wait(a_ready, 0);
-      tc::tcgen05_fence_after();
+      const uint64_t dA = tc::make_sdesc_sw128(tc::smem_u32(sA), 1024), dB = tc::make_sdesc_sw128(tc::smem_u32(sB), 1024);
+#pragma unroll 1
       for (int nt = 0; nt < kG0NT; ++nt) {
         const int buf = nt & 1;
-        if (nt >= 2) { warp_wait(&acc_free[buf], ((nt >> 1) & 1) ^ 1); tc::tcgen05_fence_after(); }
-        for (int kb = 0; kb < 4; ++kb) {
-          const int s = nt * 4 + kb, slot = s % kG0Stages;
-          warp_wait(&b_full[slot], (s / kG0Stages) & 1);
-          tc::tcgen05_fence_after();
-          const uint64_t ad0 = tc::make_sdesc_sw128(tc::smem_u32(sA + kb * 16384), 1024), bd0 = tc::make_sdesc_sw128(tc::smem_u32(sB + slot * 32768), 1024);
-          if (tc::elect_one()) {
+        if (tc::elect_one()) {
+          if (nt == 0) tc::mbar_wait(a_ready, 0);
+          if (nt >= 2) tc::mbar_wait(&acc_free[buf], ((nt >> 1) & 1) ^ 1);
 #pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16) tc::mma_ss(tbase + buf * kG0TileN, ad0 + 2 * k16, bd0 + 2 * k16, idesc, (kb | k16) ? 1u : 0u);
+          for (int kb = 0; kb < 4; ++kb) {
+            const int s = nt * 4 + kb, slot = s % kG0Stages;
+            tc::mbar_wait(&b_full[slot], (s / kG0Stages) & 1);
+            tc::tcgen05_fence_after();
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16)
+              tc::mma_ss(tbase + buf * kG0TileN, dA + (uint64_t)kb * (16384 >> 4) + 2 * k16, dB + (uint64_t)slot * (32768 >> 4) + 2 * k16, idesc,
+                         (kb | k16) ? 1u : 0u);
             tc::mma_commit(&b_empty[slot]);
           }
+          tc::mma_commit(&acc_full[buf]);
         }
-        if (tc::elect_one()) tc::mma_commit(&acc_full[buf]);
       }
     }
   } else {
@@ -1191,134 +1181,155 @@ query_tc3c_kernel(TcParams prm, MpPointSrc src, MpCalib cal, MpOutDst dst, MpSur
       }
     }
   } else if (warp == 1) {
-    // ============================== MMA issuer (whole warp, one elected lane per tcgen05 instruction: see program v3) ======
+    // ============================== MMA issuer: one elected region per chunk / phase (see program v3) ==============================
     {
       const uint32_t idesc128 = tc::make_idesc_f16(128, 128);
       const uint32_t idesc256 = tc::make_idesc_f16(128, 256);
-      const uint32_t sX = tc::smem_u32(smem + Smem::X);
-      const uint32_t sH0 = tc::smem_u32(smem + Smem::H0);
-      const uint32_t sW = tc::smem_u32(smem + Smem::Wr);
-      uint32_t it = 0;
-      uint32_t c_xready = 0, c_h0ready[2] = {0, 0}, c_h1ready = 0, c_h2ready = 0, c_tiledone = 0;
-      auto next_stage = [&]() -> uint32_t {
-        const int slot = it % C::Stages;
-        warp_wait(bars + B_WFULL + slot, (it / C::Stages) & 1u);
-        tc::tcgen05_fence_after();
-        return sW + slot * C::StageBytes;
-      };
-      auto release_stage = [&]() {
-        if (tc::elect_one()) tc::mma_commit(bars + B_WEMPTY + (it % C::Stages));
-        ++it;
-      };
-      auto commit_one = [&](int which) {
-        if (tc::elect_one()) tc::mma_commit(bars + which);
-      };
-      auto kblock_ss = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool& first) {
-        const uint64_t ad0 = tc::make_sdesc_sw128(a_addr, 1024), bd0 = tc::make_sdesc_sw128(b_addr, 1024);
-        const uint32_t acc0 = first ? 0u : 1u;
-        if (tc::elect_one()) {
+      const uint64_t dX = tc::make_sdesc_sw128(tc::smem_u32(smem + Smem::X), 1024);
+      const uint64_t dH0 = tc::make_sdesc_sw128(tc::smem_u32(smem + Smem::H0), 1024);
+      const uint64_t dW = tc::make_sdesc_sw128(tc::smem_u32(smem + Smem::Wr), 1024);
+      constexpr uint64_t kKb = 16384 >> 4, kStage = C::StageBytes >> 4, kSub = C::Sub >> 4;
+      uint32_t slot = 0, wpar = 0;                         // ring slot of the next stage and the parity of its "full" phase
+      uint32_t c_xready = 0, n_chunks = 0, c_h1ready = 0, c_h2ready = 0, c_tiledone = 0;
+      // ---- (inside an elected region: one lane)
+      auto wait_b = [&](int which, uint32_t par) { tc::mbar_wait(bars + which, par); };
+      auto kblock_ss = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc0) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc::mma_ss(d, ad0 + 2 * kk, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
-        }
-        first = false;
+        for (int kk = 0; kk < 4; ++kk) tc::mma_ss(d, ad + 2 * kk, bd + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
       };
-      auto kblock_ts = [&](uint32_t d, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool& first) {
-        const uint64_t bd0 = tc::make_sdesc_sw128(b_addr, 1024);
-        const uint32_t acc0 = first ? 0u : 1u;
-        if (tc::elect_one()) {
+      auto kblock_ts = [&](uint32_t d, uint32_t a_tmem, uint64_t bd, uint32_t idesc, uint32_t acc0) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc::mma_ts(d, a_tmem + kk * 8, bd0 + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
-        }
-        first = false;
+        for (int kk = 0; kk < 4; ++kk) tc::mma_ts(d, a_tmem + kk * 8, bd + 2 * kk, idesc, kk == 0 ? acc0 : 1u);
       };
-      auto wait_x = [&]() {            // the next phase of X has been sampled
-        warp_wait(bars + B_XREADY, c_xready & 1u);
-        ++c_xready;
-        tc::tcgen05_fence_after();
+      // ---- (uniform, all lanes) the ring positions of the next N stages / the parity of the next X phase
+      auto take = [&](uint32_t (&sl)[8], uint32_t (&pr)[8], int n_take) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q < n_take) {
+            sl[q] = slot; pr[q] = wpar;
+            if (++slot == (uint32_t)C::Stages) { slot = 0; wpar ^= 1u; }
+          }
       };
+      auto next_x = [&]() -> uint32_t { const uint32_t p = c_xready & 1u; ++c_xready; return p; };
 
       for (long long g = g0; g < n_tiles; g += gstep) {
-        bool need_tile_done = g != g0;
-        bool first1[2] = {true, true};
-        // ---- layer 1, hidden part: 8 sampled layer-0 chunks x 2 K-blocks x 2 output halves
+        const bool later_tile = g != g0;
+        uint32_t sl[8], pr[8];
+        // ---- layer 1, hidden part: 8 sampled layer-0 chunks x (2 K-blocks x 2 output halves = 4 stages)
+#pragma unroll 1
         for (int c = 0; c < 8; ++c) {
           const int b = c & 1;
-          warp_wait(bars + B_H0_READY0 + b, c_h0ready[b] & 1u);
-          ++c_h0ready[b];
-          tc::tcgen05_fence_after();
-          for (int kb = 0; kb < 2; ++kb)
-            for (int nh = 0; nh < 2; ++nh) {
-              const uint32_t w = next_stage();
-              if (nh == 1 && need_tile_done) {
-                // [384,512) holds the previous tile's acc3 until its fp32 tail has drained it
-                warp_wait(bars + B_TILE_DONE, c_tiledone & 1u);
-                ++c_tiledone;
-                tc::tcgen05_fence_after();
-                need_tile_done = false;
-              }
-              kblock_ss(tbase + cAcc1 + nh * 256, sH0 + b * 32768 + kb * 16384, w, idesc256, first1[nh]);
-              release_stage();
+          const uint32_t p_h0 = (n_chunks >> 1) & 1u;
+          ++n_chunks;
+          take(sl, pr, 4);
+          // [384,512) holds the previous tile's acc3 until its fp32 tail has drained it
+          const bool wait_td = later_tile && c == 0;
+          const uint32_t p_td = c_tiledone & 1u;
+          if (wait_td) ++c_tiledone;
+          const uint32_t acc_first = c == 0 ? 0u : 1u;
+          if (tc::elect_one()) {
+            wait_b(B_H0_READY0 + b, p_h0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int kb = q >> 1, nh = q & 1;
+              wait_b(B_WFULL + (int)sl[q], pr[q]);
+              if (q == 1 && wait_td) wait_b(B_TILE_DONE, p_td);
+              tc::tcgen05_fence_after();
+              kblock_ss(tbase + cAcc1 + nh * 256, dH0 + (uint64_t)(b * 2 + kb) * kKb, dW + sl[q] * kStage, idesc256,
+                        kb == 0 ? acc_first : 1u);
+              tc::mma_commit(bars + B_WEMPTY + sl[q]);
             }
-          commit_one(B_H0_FREE0 + b);
+            tc::mma_commit(bars + B_H0_FREE0 + b);
+          }
         }
-        // ---- layer 1, skip part: phase A, then phase B
+        // ---- layer 1, skip part: phase A, then phase B (8 stages each)
+#pragma unroll 1
         for (int ph = 0; ph < 2; ++ph) {
-          wait_x();
-          for (int kb = 0; kb < 4; ++kb)
-            for (int nh = 0; nh < 2; ++nh) {
-              const uint32_t w = next_stage();
-              kblock_ss(tbase + cAcc1 + nh * 256, sX + kb * 16384, w, idesc256, first1[nh]);
-              release_stage();
+          const uint32_t p_x = next_x();
+          take(sl, pr, 8);
+          if (tc::elect_one()) {
+            wait_b(B_XREADY, p_x);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int kb = q >> 1, nh = q & 1;
+              wait_b(B_WFULL + (int)sl[q], pr[q]);
+              tc::tcgen05_fence_after();
+              kblock_ss(tbase + cAcc1 + nh * 256, dX + (uint64_t)kb * kKb, dW + sl[q] * kStage, idesc256, 1u);
+              tc::mma_commit(bars + B_WEMPTY + sl[q]);
             }
-          if (ph == 0) commit_one(B_XFREE);       // phase A consumed; phase B stays for layer 2
+            if (ph == 0) tc::mma_commit(bars + B_XFREE);       // phase A consumed; phase B stays for layer 2
+            else tc::mma_commit(bars + B_ACC1_FULL);
+          }
         }
-        commit_one(B_ACC1_FULL);
         // ---- layer 2: A = H1 from TMEM (8 K-blocks), then X phase B (resident), then phase A -> acc2 [128,384)
-        warp_wait(bars + B_H1_READY, c_h1ready & 1u);
-        ++c_h1ready;
-        tc::tcgen05_fence_after();
         {
-          bool first = true;
-          for (int kb = 0; kb < 8; ++kb) {
-            const uint32_t w = next_stage();
-            const uint32_t a = tbase + (kb < 4 ? cH1lo + kb * 32 : cH1hi + (kb - 4) * 32);
-            kblock_ts(tbase + cAcc2, a, w, idesc256, first);
-            release_stage();
-          }
-          for (int ph = 0; ph < 2; ++ph) {
-            if (ph == 1) wait_x();                           // phase A again
-            for (int kb = 0; kb < 4; ++kb) {
-              const uint32_t w = next_stage();
-              kblock_ss(tbase + cAcc2, sX + kb * 16384, w, idesc256, first);
-              release_stage();
+          const uint32_t p_h1 = c_h1ready & 1u;
+          ++c_h1ready;
+          take(sl, pr, 8);
+          if (tc::elect_one()) {
+            wait_b(B_H1_READY, p_h1);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              wait_b(B_WFULL + (int)sl[q], pr[q]);
+              tc::tcgen05_fence_after();
+              kblock_ts(tbase + cAcc2, tbase + (q < 4 ? cH1lo + q * 32 : cH1hi + (q - 4) * 32), dW + sl[q] * kStage, idesc256,
+                        q == 0 ? 0u : 1u);
+              tc::mma_commit(bars + B_WEMPTY + sl[q]);
             }
-            if (ph == 0) commit_one(B_XFREE);     // phase B consumed
           }
-          commit_one(B_ACC2_FULL);
+#pragma unroll 1
+          for (int ph = 0; ph < 2; ++ph) {
+            const uint32_t p_x = ph == 1 ? next_x() : 0u;      // phase A again
+            take(sl, pr, 4);
+            if (tc::elect_one()) {
+              if (ph == 1) wait_b(B_XREADY, p_x);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                wait_b(B_WFULL + (int)sl[q], pr[q]);
+                tc::tcgen05_fence_after();
+                kblock_ss(tbase + cAcc2, dX + (uint64_t)q * kKb, dW + sl[q] * kStage, idesc256, 1u);
+                tc::mma_commit(bars + B_WEMPTY + sl[q]);
+              }
+              if (ph == 0) tc::mma_commit(bars + B_XFREE);     // phase B consumed
+              else tc::mma_commit(bars + B_ACC2_FULL);
+            }
+          }
         }
-        // ---- layer 3 -> acc3 [384,512): skip phase A (resident), skip phase B, hidden part
-        {
-          bool first = true;
-          for (int ph = 0; ph < 2; ++ph) {
-            if (ph == 1) wait_x();                           // phase B again
-            for (int s = 0; s < 4; ++s) {                    // stages 0,1: hi(W3) of K-blocks (0,1) (2,3); stages 2,3: lo(W3), same A
-              const uint32_t w = next_stage();
-              kblock_ss(tbase + cAcc3, sX + (2 * (s & 1)) * 16384, w, idesc128, first);
-              kblock_ss(tbase + cAcc3, sX + (2 * (s & 1) + 1) * 16384, w + C::Sub, idesc128, first);
-              release_stage();
+        // ---- layer 3 -> acc3 [384,512): skip phase A (resident), skip phase B, hidden part; every part multiplies by W3 as an
+        //      fp16 pair: stages 0,1 = hi(W3) of K-blocks (0,1) (2,3), stages 2,3 = lo(W3), same A
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ++ph) {
+          const uint32_t p_x = ph == 1 ? next_x() : 0u;        // phase B again
+          take(sl, pr, 4);
+          if (tc::elect_one()) {
+            if (ph == 1) wait_b(B_XREADY, p_x);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              wait_b(B_WFULL + (int)sl[q], pr[q]);
+              tc::tcgen05_fence_after();
+              kblock_ss(tbase + cAcc3, dX + (uint64_t)(2 * (q & 1)) * kKb, dW + sl[q] * kStage, idesc128, (ph == 0 && q == 0) ? 0u : 1u);
+              kblock_ss(tbase + cAcc3, dX + (uint64_t)(2 * (q & 1) + 1) * kKb, dW + sl[q] * kStage + kSub, idesc128, 1u);
+              tc::mma_commit(bars + B_WEMPTY + sl[q]);
             }
-            commit_one(B_XFREE);                  // after phase B: X is dead, the next tile's phase A may be sampled
+            tc::mma_commit(bars + B_XFREE);                    // after phase B: X is dead, the next tile's phase A may be sampled
           }
-          warp_wait(bars + B_H2_READY, c_h2ready & 1u);
+        }
+        {
+          const uint32_t p_h2 = c_h2ready & 1u;
           ++c_h2ready;
-          tc::tcgen05_fence_after();
-          for (int s = 0; s < 4; ++s) {                      // hi(W3) stages, then lo(W3) stages
-            const uint32_t w = next_stage();
-            kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * (s & 1)) * 32, w, idesc128, first);
-            kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * (s & 1) + 1) * 32, w + C::Sub, idesc128, first);
-            release_stage();
+          take(sl, pr, 4);
+          if (tc::elect_one()) {
+            wait_b(B_H2_READY, p_h2);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                      // hi(W3) stages, then lo(W3) stages
+              wait_b(B_WFULL + (int)sl[q], pr[q]);
+              tc::tcgen05_fence_after();
+              kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * (q & 1)) * 32, dW + sl[q] * kStage, idesc128, 1u);
+              kblock_ts(tbase + cAcc3, tbase + cH2 + (2 * (q & 1) + 1) * 32, dW + sl[q] * kStage + kSub, idesc128, 1u);
+              tc::mma_commit(bars + B_WEMPTY + sl[q]);
+            }
+            tc::mma_commit(bars + B_ACC3_FULL);
           }
-          commit_one(B_ACC3_FULL);
         }
       }
     }
@@ -1619,25 +1630,28 @@ g0c_tc_kernel(const float* __restrict__ F, const uint8_t* __restrict__ Wt, __hal
       }
     }
   } else if (warp == 9) {
-    // ---- MMA issuer (whole warp, one elected lane per tcgen05 instruction)
+    // ---- MMA issuer: one elected region per output tile (see g0_tc_kernel)
     {
-      warp_wait(a_ready, 0);
-      tc::tcgen05_fence_after();
+      const uint64_t dA = tc::make_sdesc_sw128(tc::smem_u32(sA), 1024), dB = tc::make_sdesc_sw128(tc::smem_u32(sB), 1024);
+#pragma unroll 1
       for (int nt = 0; nt < kG0NT; ++nt) {
         const int buf = nt & 1;
-        if (nt >= 2) { warp_wait(&acc_free[buf], ((nt >> 1) & 1) ^ 1); tc::tcgen05_fence_after(); }
-        for (int kb = 0; kb < kG0cKB; ++kb) {
-          const int s = nt * kG0cKB + kb, slot = s % kG0cStages;
-          warp_wait(&b_full[slot], (s / kG0cStages) & 1);
-          tc::tcgen05_fence_after();
-          const uint64_t ad0 = tc::make_sdesc_sw128(tc::smem_u32(sA + kb * 16384), 1024), bd0 = tc::make_sdesc_sw128(tc::smem_u32(sB + slot * 32768), 1024);
-          if (tc::elect_one()) {
+        if (tc::elect_one()) {
+          if (nt == 0) tc::mbar_wait(a_ready, 0);
+          if (nt >= 2) tc::mbar_wait(&acc_free[buf], ((nt >> 1) & 1) ^ 1);
 #pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16) tc::mma_ss(tbase + buf * kG0TileN, ad0 + 2 * k16, bd0 + 2 * k16, idesc, (kb | k16) ? 1u : 0u);
+          for (int kb = 0; kb < kG0cKB; ++kb) {
+            const int s = nt * kG0cKB + kb, slot = s % kG0cStages;
+            tc::mbar_wait(&b_full[slot], (s / kG0cStages) & 1);
+            tc::tcgen05_fence_after();
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16)
+              tc::mma_ss(tbase + buf * kG0TileN, dA + (uint64_t)kb * (16384 >> 4) + 2 * k16, dB + (uint64_t)slot * (32768 >> 4) + 2 * k16, idesc,
+                         (kb | k16) ? 1u : 0u);
             tc::mma_commit(&b_empty[slot]);
           }
+          tc::mma_commit(&acc_full[buf]);
         }
-        if (tc::elect_one()) tc::mma_commit(&acc_full[buf]);
       }
     }
   } else {
@@ -2258,11 +2272,16 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
   }
 #endif
 #ifndef MP_CUDA_EMU
-  // MONOPORT_B200_TC_WM=1: the one-CTA program in 2-CTA clusters that share (multicast) the weight stream.  Halves the L2 -> SM
-  // weight bytes like the CTA pair above without touching the MMAs; the coupled ring costs 10 % more cycles per tile and the
-  // power saved buys back all but 0.7 % of it (profiles/r02_call14_wm_ab.txt): opt-in.
-  static const int forced_wm = [] { const char* v = getenv("MONOPORT_B200_TC_WM"); return v ? atoi(v) : 0; }();
-  if (forced_wm == 1 && dst.n_peers == 0 && sms >= 2 && tiles >= 2) {
+  // Weight multicast: the one-CTA program in 2-CTA clusters that share the weight stream (halves the L2 -> SM weight requests
+  // like the CTA pair above without touching the MMAs).  With the round-1..mid-round-2 issuer it lost 0.7 % (the coupled ring
+  // cost more cycles than the saved power bought back, profiles/r02_call14_wm_ab.txt); with the issuer at the pipe's rate the
+  // weight ring is what the issuer waits for, and the same box measures 569.5 / 565.5 against 556.7 / 559.0 Mpoints/s
+  // (CTA pair: 540.5 / 542.4; profiles/r02_call20_weight_halving_ab.txt).  Default for launches of several waves (a launch
+  // of a wave or less is bound by the latency of one tile, which the coupling can only lengthen);
+  // MONOPORT_B200_TC_WM=0 / 1 forces it off / on.
+  static const int forced_wm = [] { const char* v = getenv("MONOPORT_B200_TC_WM"); return v ? atoi(v) : -1; }();
+  const bool use_wm = forced_wm == 1 || (forced_wm < 0 && tiles >= 4ll * sms);
+  if (use_wm && dst.n_peers == 0 && sms >= 2 && tiles >= 2 && !prm.prof && !prm.trace) {
     const long long groups = (tiles + 1) / 2;
     const long long max_pairs = sms / 2;
     const int pairs = (int)(groups < max_pairs ? groups : max_pairs);
