@@ -118,13 +118,13 @@ struct Smem {
   static constexpr int Wr = H0 + 65536;                         // kStages x 32 KB
   static constexpr int Small = Wr + kRingBytes;                 // zf[128], inimg[128], s4[kMaxRes][128]
   static constexpr int Bars = Small + (2 + kMaxRes) * kTile * 4;
-  static constexpr int NumBars = 2 * kStages + 14;
+  static constexpr int NumBars = 2 * kStages + 15;
   static constexpr int TmemPtr = Bars + NumBars * 8;
   static constexpr int Total = TmemPtr + 16;
 };
 enum Bar { B_WFULL = 0, B_WEMPTY = kStages, B_XREADY = 2 * kStages, B_ACC0_FULL0, B_ACC0_FULL1, B_H0_READY0, B_H0_READY1,
-           B_H0_FREE0, B_H0_FREE1, B_ACC1_FULL, B_H1_READY, B_ACC2_FULL, B_H2_READY, B_ACC3_FULL, B_TILE_DONE, B_XFREE };
-static_assert(B_XFREE + 1 == Smem::NumBars, "barrier count");
+           B_H0_FREE0, B_H0_FREE1, B_ACC1_FULL, B_H1_READY, B_ACC2_FULL, B_H2_READY, B_ACC3_FULL, B_TILE_DONE, B_XFREE, B_PART_READY };
+static_assert(B_PART_READY + 1 == Smem::NumBars, "barrier count");
 static_assert(Smem::Total + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
 
 __device__ __forceinline__ void wait_bar(uint64_t* bars, int which, uint32_t& count) {
@@ -314,8 +314,9 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
     tc::mbar_init(bars + B_ACC2_FULL, 1);
     tc::mbar_init(bars + B_H2_READY, kW);
     tc::mbar_init(bars + B_ACC3_FULL, 1);
-    tc::mbar_init(bars + B_TILE_DONE, 4 * CG);
+    tc::mbar_init(bars + B_TILE_DONE, 8 * CG);         // both warpgroups read acc3 (fp32 tail)
     tc::mbar_init(bars + B_XFREE, 1);
+    tc::mbar_init(bars + B_PART_READY, 4);         // v3 fp32 tail: warpgroup 1's partial dot products are in smem (CTA-local)
     tc::mbar_init(bars + B_ACC0_FULL0, 2);         // v3: "per-point scalars of this tile are in smem" (CTA-local)
     tc::mbar_init(bars + B_ACC0_FULL1, 1);
     tc::fence_barrier_init();
@@ -585,7 +586,7 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    uint32_t c_sready = 0, c_h0free[2] = {0, 0}, c_acc1full = 0, c_acc2full = 0, c_acc3full = 0;
+    uint32_t c_sready = 0, c_h0free[2] = {0, 0}, c_acc1full = 0, c_acc2full = 0, c_acc3full = 0, c_part = 0;
     const int res = prm.res;
     if (!(warp == 4 && lane == 0)) prof = nullptr;
     const int l16 = lane & 15;
@@ -786,19 +787,27 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
         TRACE(tr, tb + 14);
       }
           } else if (step == 9) {
-      // ---- layer 3 + layer 4 in fp32, warpgroup 0
-      if (wg == 0) {
+      // ---- layer 3 + layer 4 in fp32.  Each warpgroup takes HALF of acc3's 128 columns (its warp of a quarter owns the same 32
+      //      rows in both groups): the tail is on the issuer's critical path -- [384,512) is the next tile's layer-1 accumulator,
+      //      B_TILE_DONE -- and with one warpgroup it took 4.8 k cycles per tile.  TMEM is released as soon as a warp's last
+      //      column group is in registers; warpgroup 1 passes its partial dot product through the (idle) second chunk buffer.
+      {
         { PROF_T0(); wait_bar(bars, B_ACC3_FULL, c_acc3full); PROF_ADD(P_W_ACC3FULL); }
         TRACE(tr, tb + 15);
         tc::tcgen05_fence_after();
         PROF_T0();
         float logit[kMaxRes];
 #pragma unroll
-        for (int r = 0; r < kMaxRes; ++r) logit[r] = s4[r];
+        for (int r = 0; r < kMaxRes; ++r) logit[r] = wg == 0 ? s4[r] : 0.f;
 #pragma unroll 1
-        for (int gq = 0; gq < 4; ++gq) {
+        for (int h = 0; h < 2; ++h) {
+          const int gq = 2 * wg + h;
           float o[32];
           load_pre(cAcc3 + gq * 32, side_off(3) + gq * 32, o);
+          if (h == 1) {                               // this warp has read all it needs of acc3
+            tc::tcgen05_fence_before();
+            arrive_issuer(B_TILE_DONE);
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], o[j] * MP_LEAKY_SLOPE);
 #pragma unroll
@@ -816,10 +825,25 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
             }
           }
         }
-        tc::tcgen05_fence_before();
-        arrive_issuer(B_TILE_DONE);
+        // the second chunk buffer is idle here (its last reader was this tile's layer 1; the next tile's chunk 1 is generated
+        // at step 10): rows [16 q, 16 q + 16) of it are what warpgroup 0's warp of quarter q overwrites next, and nobody else
+        // (hand-off: a CTA-local mbarrier, one arrival per warp of warpgroup 1)
+        float* s_part = reinterpret_cast<float*>(smem + Smem::H0 + 32768 + quarter * 16 * 128);
+        if (wg == 1) {
+#pragma unroll
+          for (int r = 0; r < kMaxRes; ++r) s_part[r * 32 + lane] = logit[r];
+        }
+        if (wg == 1) {
+          warp_arrive_local(bars + B_PART_READY, lane);
+        } else {
+          wait_bar(bars, B_PART_READY, c_part);
+#pragma unroll
+          for (int r = 0; r < kMaxRes; ++r) logit[r] += s_part[r * 32 + lane];
+          __syncwarp();        // every lane has its partial before any lane of this warp overwrites these rows (chunk 1, step 10)
+        }
         PROF_ADD(P_W_DRAIN3);
         TRACE(tr, tb + 16);
+        if (wg == 0) {
         const long long i = p0 + row;
         if (i < n) {
 #pragma unroll
@@ -837,6 +861,7 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
               }
             }
           }
+        }
         }
       }
           }
