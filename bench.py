@@ -31,7 +31,7 @@ R_GRID = 257
 FLOP_PER_POINT = 2363906          # 2*(257*1024+1281*512+769*256+513*128+385*1)  
 # DRAM bytes of one query_tc3_kernel launch over the dense 257^3 grid, from an `ncu --set full` capture (not re-measured by a
 # bench run: profiling and timing never share a run).  Updated by hand from profiles/ when the kernel changes.
-TRAFFIC_NCU = {"bytes": 84.43e6, "source": "profiles/r02_final_ncu_tc_summary.txt: 45.34 MB read + 39.09 MB written (ncu --set full pass of tools/gpu_r02_final.sh)"}
+TRAFFIC_NCU = {"bytes": 84.95e6, "source": "profiles/r02_final_ncu_tc_summary.txt: 45.74 MB read + 39.21 MB written (ncu --set full pass of tools/gpu_r02_final.sh)"}
 B_MIN, B_MAX = (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0)
 
 
@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--exchange", default=os.environ.get("MONOPORT_B200_EXCHANGE", "auto"), choices=["auto", "nccl", "fused"],
                     help="N>1, how the ranks' ranges become the volume on every rank: 'nccl' = one in-place all-gather, 'fused' = "
                          "peer-memory stores from the kernel epilogue + a barrier; 'auto' = fused from 4 GPUs on (measured: 2 GPUs "
-                         "990 vs 977 Mpoints/s in favour of NCCL, 8 GPUs 4133 vs 4246 in favour of the fused exchange)")
+                         "1101 vs 1086 Mpoints/s in favour of NCCL, 8 GPUs 4647 vs 4733 in favour of the fused exchange)")
     ap.add_argument("--fused-gather", action="store_true", help="same as --exchange fused")
     ap.add_argument("--no-recon", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -447,7 +447,7 @@ def run_ours(args):
                          "frac": achieved_tf / peak_tf,
                          "traffic": (TRAFFIC_NCU["bytes"] if (mode_used == "tc" and world == 1 and R == R_GRID) else None),
                          "traffic_unit": "bytes/launch, dram__bytes_read.sum + dram__bytes_write.sum of query_tc3_kernel (%s)" % TRAFFIC_NCU["source"],
-                         "kernel": ("query_tc3_kernel (+ g0_tc_kernel, the per-frame per-texel layer-0 GEMM, 26 us)" if mode_used == "tc"
+                         "kernel": ("query_tc3_kernel (+ g0_tc_kernel, the per-frame per-texel layer-0 GEMM, 25 us)" if mode_used == "tc"
                                     else "query_fp32_kernel"),
                          "kernel_ms": 1e3 * k_avg_s, "peak_source": pk["source"] + " bf16 sustained (cuBLAS loop)",
                          "frac_of_burst": achieved_tf / pk["tf_burst"],
