@@ -2305,7 +2305,9 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
   // of a wave or less is bound by the latency of one tile, which the coupling can only lengthen);
   // MONOPORT_B200_TC_WM=0 / 1 forces it off / on.
   static const int forced_wm = [] { const char* v = getenv("MONOPORT_B200_TC_WM"); return v ? atoi(v) : -1; }();
-  const bool use_wm = forced_wm == 1 || (forced_wm < 0 && tiles >= 4ll * sms);
+  // (node lists with a device-side count -- the coarse-to-fine levels -- are latency-bound whatever their capacity: plain launch,
+  // 259.1 vs 265.8 us of F1 per frame, profiles/r02_call27_*, r02_call22_*)
+  const bool use_wm = forced_wm == 1 || (forced_wm < 0 && tiles >= 4ll * sms && src.count_dev == nullptr);
   if (use_wm && dst.n_peers == 0 && sms >= 2 && tiles >= 2 && !prm.prof && !prm.trace) {
     const long long groups = (tiles + 1) / 2;
     const long long max_pairs = sms / 2;
