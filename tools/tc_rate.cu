@@ -13,6 +13,11 @@
 //                                                      each warp issues half of the MMAs into its own accumulator)
 //                                                 512 = warp-uniform issue loop, one elected lane per MMA (the shipped pattern);
 //                                                      combines with 1, 2, 4, 8, 16      1024 = (with 2) the workers store 4x the bytes
+//                                                 structure of the uniform loop inside the pipeline (with 512): 2048 = every lane
+//                                                      polls the barriers (default: an elected poll + __syncwarp); 4096 = ONE elected
+//                                                      region per stage (waits, fence, 4 MMAs, commits); 8192 = (with 4096) two stages
+//                                                      per region; 16384 = (with 4096) no __syncwarp after it; 32768 = the minimal
+//                                                      control loop (streaming only) that reaches the floor
 // Prints cycles per MMA (min / mean over the CTAs that issue) and the implied fraction of the 128-cycle floor.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -lineinfo -o tc_rate tools/tc_rate.cu -lcuda
 #include <cuda.h>
