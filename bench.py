@@ -31,7 +31,7 @@ R_GRID = 257
 FLOP_PER_POINT = 2363906          # 2*(257*1024+1281*512+769*256+513*128+385*1)  
 # DRAM bytes of one query_tc3_kernel launch over the dense 257^3 grid, from an `ncu --set full` capture (not re-measured by a
 # bench run: profiling and timing never share a run).  Updated by hand from profiles/ when the kernel changes.
-TRAFFIC_NCU = {"bytes": 84.95e6, "source": "profiles/r02_final_ncu_tc_summary.txt: 45.74 MB read + 39.21 MB written (ncu --set full pass of tools/gpu_r02_final.sh)"}
+TRAFFIC_NCU = {"bytes": 82.69e6, "source": "profiles/r02_final_ncu_tc_summary.txt: 44.79 MB read + 37.90 MB written (ncu --set full pass of tools/gpu_r02_final.sh)"}
 B_MIN, B_MAX = (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0)
 
 

@@ -4,6 +4,7 @@
 mkdir -p gpurun_out
 T0=$SECONDS
 timeout 400 python -m pytest tests -x -q -m gpu --timeout 300 > gpurun_out/r02f_pytest.log 2>&1; echo "pytest rc=$? t=$((SECONDS-T0))s"; tail -3 gpurun_out/r02f_pytest.log
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02f_smoke.log 2>&1; echo "smoke rc=$? t=$((SECONDS-T0))s"; tail -2 gpurun_out/r02f_smoke.log
 timeout 400 python bench.py > gpurun_out/r02f_bench.json 2> gpurun_out/r02f_bench.err; echo "bench rc=$? t=$((SECONDS-T0))s"
 python - <<'PY'
 import json
