@@ -10,10 +10,12 @@
 
 #include "../../include/monoport_b200.h"
 
-// dynamic shared memory of a kernel (tests/emu runs the kernels on the CPU, where it is an array the harness defines)
+// dynamic shared memory of a kernel (tests/emu runs the kernels on the CPU, where it is a buffer the harness hands out --
+// one per CTA of a cluster)
 #ifdef MP_CUDA_EMU
-#define MP_DYN_SMEM(type, name) extern type name[]
-#define MP_DYN_SMEM_ALIGNED(type, name, bytes) extern type name[]
+void* mp_emu_dyn_smem();
+#define MP_DYN_SMEM(type, name) type* const name = static_cast<type*>(mp_emu_dyn_smem())
+#define MP_DYN_SMEM_ALIGNED(type, name, bytes) type* const name = static_cast<type*>(mp_emu_dyn_smem())
 #else
 #define MP_DYN_SMEM(type, name) extern __shared__ type name[]
 #define MP_DYN_SMEM_ALIGNED(type, name, bytes) extern __shared__ __align__(bytes) type name[]

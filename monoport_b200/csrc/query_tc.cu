@@ -351,14 +351,12 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
           const int slot = it % C::Stages;
           const uint32_t use = it / C::Stages;
           if constexpr (WM) {
-#ifndef MP_CUDA_EMU
             // my half of the stage, into both CTAs; my barrier expects the whole stage (the other half comes from the peer)
             tc::mbar_wait_cluster(bars + B_WEMPTY + slot, (use & 1u) ^ 1u);
             tc::mbar_arrive_expect_tx(bars + B_WFULL + slot, C::StageBytes);
             tc::bulk_g2s_multicast(smem + Smem::Wr + slot * C::StageBytes + rank * (C::StageBytes / 2),
                                    wsrc + (size_t)s * C::StageBytes + rank * (C::StageBytes / 2), C::StageBytes / 2,
                                    bars + B_WFULL + slot, (uint16_t)3);
-#endif
             continue;
           }
           tc::mbar_wait(bars + B_WEMPTY + slot, (use & 1u) ^ 1u);
@@ -2296,7 +2294,6 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     return MP_OK;
   }
 #endif
-#ifndef MP_CUDA_EMU
   // Weight multicast: the one-CTA program in 2-CTA clusters that share the weight stream (halves the L2 -> SM weight requests
   // like the CTA pair above without touching the MMAs).  With the round-1..mid-round-2 issuer it lost 0.7 % (the coupled ring
   // cost more cycles than the saved power bought back, profiles/r02_call14_wm_ab.txt); with the issuer at the pipe's rate the
@@ -2312,6 +2309,7 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     const long long groups = (tiles + 1) / 2;
     const long long max_pairs = sms / 2;
     const int pairs = (int)(groups < max_pairs ? groups : max_pairs);
+#ifndef MP_CUDA_EMU
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * pairs);
@@ -2326,10 +2324,12 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc3_kernel<false, 1, true>, prm, src, cal, dst));
+#else
+    MP_EMU_LAUNCH_CLUSTER2(2 * pairs, kThreads, (query_tc3_kernel<false, 1, true>(prm, src, cal, dst)));     // (the CPU model runs the two CTAs of a cluster side by side)
+#endif
     report(2 * pairs);
     return MP_OK;
   }
-#endif
   const int grid = (int)(tiles < (long long)sms ? tiles : sms);
 #ifndef MP_CUDA_EMU
   if (dst.n_peers > 0) query_tc3_kernel<true, 1><<<grid, kThreads, Smem::Total + 1024, st>>>(prm, src, cal, dst);      // fused slab exchange

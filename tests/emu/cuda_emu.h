@@ -53,38 +53,58 @@ inline thread_local dim3 blockDim, gridDim;
 
 namespace cuda_emu {
 constexpr int kMaxThreads = 1024;
-inline pthread_barrier_t g_cta_barrier;
-inline pthread_barrier_t g_warp_barrier[kMaxThreads / 32];
-inline unsigned long long g_shfl[kMaxThreads];
+// A launch runs one CTA at a time -- or, for a 2-CTA cluster launch, the two CTAs of one cluster at a time: every CTA of the
+// cluster has its own barriers / exchange buffers, selected by the thread's rank in the cluster.
+inline thread_local int t_rank = 0;                 // %cluster_ctarank of the calling thread
+inline int g_cluster = 1;                           // CTAs per cluster of the running launch
+inline pthread_barrier_t g_cta_barrier_r[2];
+inline pthread_barrier_t g_warp_barrier_r[2][kMaxThreads / 32];
+inline unsigned long long g_shfl_r[2][kMaxThreads];
+inline pthread_barrier_t g_cluster_barrier;         // all threads of the cluster
+#define g_cta_barrier g_cta_barrier_r[cuda_emu::t_rank]
+#define g_warp_barrier g_warp_barrier_r[cuda_emu::t_rank]
+#define g_shfl g_shfl_r[cuda_emu::t_rank]
 inline int linear_tid() { return (int)(threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)); }
 
 // run `body` once per CUDA thread of a grid x block launch.  The CTA's threads are created once per launch and walk the
 // grid together (one barrier between CTAs, so the static "shared memory" is never reused while a thread is still in
-// the previous CTA).
+// the previous CTA).  cluster = 2 (1-D grids, even size): the two CTAs of a cluster run concurrently, clusters one after
+// the other; `__shared__` statics would be shared by the pair, so kernels launched this way must only use MP_DYN_SMEM.
 template <class Body>
-void launch(dim3 grid, dim3 block, Body body) {
+void launch(dim3 grid, dim3 block, Body body, int cluster = 1) {
   const int nt = (int)(block.x * block.y * block.z);
   if (nt > kMaxThreads || nt % 32 != 0) { fprintf(stderr, "cuda_emu: block of %d threads unsupported\n", nt); abort(); }
-  pthread_barrier_init(&g_cta_barrier, nullptr, nt);
-  for (int w = 0; w < nt / 32; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, 32);
+  if (cluster != 1 && (cluster != 2 || grid.y != 1 || grid.z != 1 || grid.x % 2)) { fprintf(stderr, "cuda_emu: unsupported cluster launch\n"); abort(); }
+  g_cluster = cluster;
+  for (int r = 0; r < cluster; ++r) {
+    pthread_barrier_init(&g_cta_barrier_r[r], nullptr, nt);
+    for (int w = 0; w < nt / 32; ++w) pthread_barrier_init(&g_warp_barrier_r[r][w], nullptr, 32);
+  }
+  pthread_barrier_init(&g_cluster_barrier, nullptr, nt * cluster);
   std::vector<std::thread> th;
-  th.reserve(nt);
-  for (int t = 0; t < nt; ++t)
+  th.reserve((size_t)nt * cluster);
+  for (int tt = 0; tt < nt * cluster; ++tt)
     th.emplace_back([=] {
+      const int rank = tt / nt, t = tt % nt;
+      t_rank = rank;
       threadIdx = {(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
       blockDim = block;
       gridDim = grid;
       for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
-          for (unsigned bx = 0; bx < grid.x; ++bx) {
-            blockIdx = {bx, by, bz};
+          for (unsigned bx = 0; bx < grid.x; bx += (unsigned)cluster) {
+            blockIdx = {bx + (unsigned)rank, by, bz};
             body();
-            pthread_barrier_wait(&g_cta_barrier);
+            pthread_barrier_wait(&g_cluster_barrier);
           }
     });
   for (auto& x : th) x.join();
-  pthread_barrier_destroy(&g_cta_barrier);
-  for (int w = 0; w < nt / 32; ++w) pthread_barrier_destroy(&g_warp_barrier[w]);
+  for (int r = 0; r < cluster; ++r) {
+    pthread_barrier_destroy(&g_cta_barrier_r[r]);
+    for (int w = 0; w < nt / 32; ++w) pthread_barrier_destroy(&g_warp_barrier_r[r][w]);
+  }
+  pthread_barrier_destroy(&g_cluster_barrier);
+  g_cluster = 1;
 }
 }  // namespace cuda_emu
 

@@ -7,9 +7,8 @@
 #define MP_EMU_CUDA_TYPES 1
 #include "cuda_emu.h"
 
-namespace {
-alignas(1024) float smem[240 * 1024 / 4];        // the kernel's `extern __shared__ float smem[]`
-}
+alignas(1024) static float g_dyn_smem[240 * 1024 / 4];        // the kernel's dynamic shared memory
+void* mp_emu_dyn_smem() { return g_dyn_smem; }
 
 extern "C" {
 cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }

@@ -24,12 +24,9 @@ static inline __half2 __hfma2(__half2 a, __half2 b, __half2 c) {
 static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 
-// ---- the dynamic shared memory of the kernels (they run one at a time) -------------------------------------------------
-// (the kernels live in query_tc.cu's anonymous namespace, so their `extern __shared__` arrays resolve there)
-namespace {
-alignas(1024) uint8_t smem_raw[240 * 1024];
-extern uint8_t g0_smem_raw[] __attribute__((alias("_ZN12_GLOBAL__N_18smem_rawE")));
-}  // namespace
+// ---- the dynamic shared memory of the kernels: one buffer per CTA of a (2-CTA) cluster; CTAs / clusters run one at a time ---
+alignas(1024) static uint8_t g_dyn_smem[2][240 * 1024];
+void* mp_emu_dyn_smem() { return g_dyn_smem[cuda_emu::t_rank]; }
 
 // ---- a host-memory stand-in for the few CUDA runtime calls of the launcher ----------------------------------------------
 static int g_fake_sms = 148;
@@ -54,6 +51,7 @@ const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 }
 
 #define MP_EMU_LAUNCH(grid, block, call) cuda_emu::launch(dim3((unsigned)(grid)), dim3((unsigned)(block)), [&] { call; })
+#define MP_EMU_LAUNCH_CLUSTER2(grid, block, call) cuda_emu::launch(dim3((unsigned)(grid)), dim3((unsigned)(block)), [&] { call; }, 2)
 
 static char g_err[512];
 void mp_set_error(const char* fmt, ...) {
@@ -113,7 +111,7 @@ int main(int argc, char** argv) {
     mlp.bias[l] = Bs[l].data();
   }
   fclose(f);
-  tc::emu::set_smem(smem_raw, sizeof(smem_raw));
+  tc::emu::set_smem(g_dyn_smem[0], sizeof(g_dyn_smem[0]), g_dyn_smem[1]);
   if (mp_tc_prepare(&mlp) != MP_OK || !mlp.tc_ok) { fprintf(stderr, "mp_tc_prepare: %s (tc_ok=%d)\n", g_err, mlp.tc_ok); return 3; }
   if (getenv("EMU_TC_DEBUG")) {
     const TcPack* pk = static_cast<const TcPack*>(mlp.tc);

@@ -1,6 +1,9 @@
 // TEST INFRASTRUCTURE ONLY -- functional CPU model of monoport_b200/csrc/tc_ptx.cuh (included by it under MP_CUDA_EMU):
 // mbarriers with transaction counts, bulk async copies, tensor memory, tcgen05.mma (.kind::f16, cta_group::1, operands
-// from SWIZZLE_128B K-major shared-memory descriptors or packed fp16 in tensor memory), tcgen05.commit, tcgen05.ld/st.
+// from SWIZZLE_128B K-major shared-memory descriptors or packed fp16 in tensor memory), tcgen05.commit, tcgen05.ld/st;
+// and, for launches of 2-CTA clusters (cuda_emu::launch(..., 2): each CTA has its own shared and tensor memory), the
+// cluster rank, cluster barriers, remote mbarrier arrivals, multicast bulk copies and multicast commits.  cta_group::2
+// MMAs (one instruction over both CTAs) are NOT modelled.
 //
 // Asynchrony is modelled adversarially: a bulk copy or an MMA is only QUEUED when it is issued; queued operations are
 // executed (copies first, then MMAs / commits in issue order) when some thread is blocked in an mbarrier wait.  So
@@ -25,12 +28,15 @@ struct Op {
   // MMA
   uint32_t d_tmem, a_tmem, idesc, accumulate;
   uint64_t a_desc, b_desc;
+  int rank;                                  // the issuing CTA: whose shared / tensor memory the operands live in
 };
 inline std::mutex g_mu;
 inline std::deque<Op> g_copies, g_mmas;
-inline uint32_t g_tmem[kLanes][kCols];
-inline uint8_t* g_smem = nullptr;          // base of the dynamic shared memory of the running kernel (1024-B aligned)
+inline uint32_t g_tmem_r[2][kLanes][kCols];
+inline uint8_t* g_smem_r[2] = {nullptr, nullptr};   // base of the dynamic shared memory of each CTA of the cluster (1024-B aligned)
 inline uint32_t g_smem_bytes = 0;
+#define g_tmem g_tmem_r[cuda_emu::t_rank]
+#define g_smem g_smem_r[cuda_emu::t_rank]
 inline std::atomic<unsigned long long> g_events{0};   // bumped by every state change (deadlock watchdog)
 inline std::atomic<int> g_waiting{0};
 // work counters (EMU_TC_STATS=1 prints them at exit): what the program actually executes per launch, to set against the
@@ -47,23 +53,38 @@ inline void stats_init() {
 }
 inline bool eager() { static const bool e = getenv("EMU_TC_EAGER") != nullptr; return e; }   // debugging aid: no deferral
 
-inline void set_smem(void* base, uint32_t bytes) {
+// `base1`: the shared memory of the second CTA of a cluster (same size; may be null when no cluster launch follows)
+inline void set_smem(void* base, uint32_t bytes, void* base1 = nullptr) {
   stats_init();
-  if ((uintptr_t)base & 1023) { fprintf(stderr, "tc emu: shared memory base must be 1024-byte aligned\n"); abort(); }
-  g_smem = (uint8_t*)base;
+  if (((uintptr_t)base | (uintptr_t)base1) & 1023) { fprintf(stderr, "tc emu: shared memory base must be 1024-byte aligned\n"); abort(); }
+  g_smem_r[0] = (uint8_t*)base;
+  g_smem_r[1] = (uint8_t*)base1;
   g_smem_bytes = bytes;
   g_copies.clear();
   g_mmas.clear();
-  memset(g_tmem, 0xCD, sizeof(g_tmem));      // poison: uninitialised accumulators are visible
+  memset(g_tmem_r, 0xCD, sizeof(g_tmem_r));  // poison: uninitialised accumulators are visible
+}
+// which CTA of the cluster owns a shared-memory pointer (-1: none), and the same offset in CTA `rank`
+inline int smem_rank_of(const void* p) {
+  for (int r = 0; r < 2; ++r)
+    if (g_smem_r[r] && (uintptr_t)p >= (uintptr_t)g_smem_r[r] && (uintptr_t)p < (uintptr_t)g_smem_r[r] + g_smem_bytes) return r;
+  return -1;
+}
+template <class T> inline T* smem_in_cta(T* p, int rank) {
+  const int own = smem_rank_of(p);
+  if (own < 0 || rank < 0 || rank >= cuda_emu::g_cluster || !g_smem_r[rank]) { fprintf(stderr, "tc emu: bad cluster address translation\n"); abort(); }
+  return reinterpret_cast<T*>(g_smem_r[rank] + ((uintptr_t)p - (uintptr_t)g_smem_r[own]));
 }
 
-// ---- mbarrier word: [0,20) pending arrivals | [20,40) arrival count of a phase | [40,62) pending tx bytes | 63 phase
+// ---- mbarrier word: [0,20) pending arrivals | [20,40) arrival count of a phase | [40,62) pending tx bytes (SIGNED: in a
+//      cluster the peer's multicast bytes may complete before this CTA's expect_tx of the same phase) | 63 phase
 inline uint32_t mb_pending(uint64_t w) { return (uint32_t)(w & 0xFFFFF); }
 inline uint32_t mb_count(uint64_t w) { return (uint32_t)((w >> 20) & 0xFFFFF); }
-inline uint32_t mb_tx(uint64_t w) { return (uint32_t)((w >> 40) & 0x3FFFFF); }
+inline int32_t mb_tx(uint64_t w) { const uint32_t v = (uint32_t)((w >> 40) & 0x3FFFFF); return (v & 0x200000u) ? (int32_t)v - 0x400000 : (int32_t)v; }
 inline uint32_t mb_phase(uint64_t w) { return (uint32_t)(w >> 63); }
-inline uint64_t mb_make(uint32_t pending, uint32_t count, uint32_t tx, uint32_t phase) {
-  return (uint64_t)pending | ((uint64_t)count << 20) | ((uint64_t)tx << 40) | ((uint64_t)phase << 63);
+inline uint64_t mb_make(uint32_t pending, uint32_t count, int32_t tx, uint32_t phase) {
+  if (tx < -0x200000 || tx >= 0x200000) { fprintf(stderr, "tc emu: mbarrier tx-count out of range\n"); abort(); }
+  return (uint64_t)pending | ((uint64_t)count << 20) | ((uint64_t)((uint32_t)tx & 0x3FFFFFu) << 40) | ((uint64_t)phase << 63);
 }
 inline void mb_check_complete(uint64_t* bar) {
   const uint64_t w = *bar;
@@ -79,11 +100,11 @@ inline void mb_arrive_locked(uint64_t* bar) {
 
 inline float h2f(uint16_t h) { __half x; memcpy(&x, &h, 2); return __half2float(x); }
 inline uint32_t swz(uint32_t a) { return a ^ (((a >> 7) & 7u) << 4); }       // SWIZZLE_128B on the shared-memory address
-inline uint16_t smem_half(uint32_t addr) {
+inline uint16_t smem_half(uint32_t addr, int rank) {
   const uint32_t p = swz(addr);
   if (p + 2 > g_smem_bytes) { fprintf(stderr, "tc emu: MMA operand address %u outside shared memory\n", p); abort(); }
   uint16_t h;
-  memcpy(&h, g_smem + p, 2);
+  memcpy(&h, g_smem_r[rank] + p, 2);
   return h;
 }
 
@@ -106,13 +127,13 @@ inline void exec_mma(const Op& op) {
     uint32_t st, sbo;
     desc_fields(op.a_desc, st, sbo);
     for (uint32_t m = 0; m < 128; ++m)
-      for (uint32_t k = 0; k < 16; ++k) A[m][k] = h2f(smem_half(st + (m >> 3) * sbo + (m & 7) * 128 + k * 2));
+      for (uint32_t k = 0; k < 16; ++k) A[m][k] = h2f(smem_half(st + (m >> 3) * sbo + (m & 7) * 128 + k * 2, op.rank));
   } else {
     const uint32_t acol = op.a_tmem & 0xFFFF;
     if ((op.a_tmem >> 16) != 0 || acol + 8 > kCols) { fprintf(stderr, "tc emu: bad A tensor-memory address\n"); abort(); }
     for (uint32_t m = 0; m < 128; ++m)
       for (uint32_t k = 0; k < 16; ++k) {
-        const uint32_t w = g_tmem[m][acol + (k >> 1)];
+        const uint32_t w = g_tmem_r[op.rank][m][acol + (k >> 1)];
         A[m][k] = h2f((uint16_t)((k & 1) ? (w >> 16) : (w & 0xFFFF)));
       }
   }
@@ -120,7 +141,7 @@ inline void exec_mma(const Op& op) {
     uint32_t st, sbo;
     desc_fields(op.b_desc, st, sbo);
     for (uint32_t n = 0; n < N; ++n)
-      for (uint32_t k = 0; k < 16; ++k) B[n][k] = h2f(smem_half(st + (n >> 3) * sbo + (n & 7) * 128 + k * 2));
+      for (uint32_t k = 0; k < 16; ++k) B[n][k] = h2f(smem_half(st + (n >> 3) * sbo + (n & 7) * 128 + k * 2, op.rank));
   }
   {
     static const int trace_n = getenv("EMU_TC_TRACE_MMA") ? atoi(getenv("EMU_TC_TRACE_MMA")) : 0;
@@ -138,9 +159,9 @@ inline void exec_mma(const Op& op) {
       float acc = 0.f;
       for (uint32_t k = 0; k < 16; ++k) acc += A[m][k] * B[n][k];
       float d = 0.f;
-      if (op.accumulate) memcpy(&d, &g_tmem[m][dcol + n], 4);
+      if (op.accumulate) memcpy(&d, &g_tmem_r[op.rank][m][dcol + n], 4);
       d += acc;
-      memcpy(&g_tmem[m][dcol + n], &d, 4);
+      memcpy(&g_tmem_r[op.rank][m][dcol + n], &d, 4);
     }
 }
 
@@ -170,8 +191,9 @@ inline bool progress_locked() {
     g_stats.copies++;
     g_stats.copy_bytes += op.bytes;
     const uint64_t w = *op.bar;
-    if (mb_tx(w) < op.bytes) { fprintf(stderr, "tc emu: complete_tx without a matching expect_tx\n"); abort(); }
-    *op.bar = mb_make(mb_pending(w), mb_count(w), mb_tx(w) - op.bytes, mb_phase(w));
+    // (inside one CTA a complete_tx never precedes its expect_tx -- the copy is issued after it; across a cluster it may)
+    if (mb_tx(w) < (int32_t)op.bytes && cuda_emu::g_cluster == 1) { fprintf(stderr, "tc emu: complete_tx without a matching expect_tx\n"); abort(); }
+    *op.bar = mb_make(mb_pending(w), mb_count(w), mb_tx(w) - (int32_t)op.bytes, mb_phase(w));
     mb_check_complete(op.bar);
     return true;
   }
@@ -187,9 +209,10 @@ inline bool progress_locked() {
 }
 }  // namespace emu
 
+// shared::cta address of a pointer into the CALLING CTA's shared memory
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   const uintptr_t off = (uintptr_t)p - (uintptr_t)emu::g_smem;
-  if (off >= emu::g_smem_bytes) { fprintf(stderr, "tc emu: pointer is not in the kernel's shared memory\n"); abort(); }
+  if (off >= emu::g_smem_bytes) { fprintf(stderr, "tc emu: pointer is not in this CTA's shared memory\n"); abort(); }
   return (uint32_t)off;
 }
 
@@ -200,7 +223,7 @@ inline void mbar_arrive(uint64_t* bar) { std::lock_guard<std::mutex> g(emu::g_mu
 inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   std::lock_guard<std::mutex> g(emu::g_mu);
   const uint64_t w = *bar;
-  *bar = emu::mb_make(emu::mb_pending(w), emu::mb_count(w), emu::mb_tx(w) + bytes, emu::mb_phase(w));
+  *bar = emu::mb_make(emu::mb_pending(w), emu::mb_count(w), emu::mb_tx(w) + (int32_t)bytes, emu::mb_phase(w));
   emu::mb_arrive_locked(bar);
 }
 inline bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
@@ -225,7 +248,7 @@ inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   emu::g_waiting--;
   if (std::chrono::steady_clock::now() - last_change > std::chrono::seconds(20)) {
     const uint64_t w = *bar;
-    fprintf(stderr, "tc emu: DEADLOCK -- thread %d of CTA %u waits on barrier +%u (parity %u; phase %u pending %u tx %u), nothing queued\n",
+    fprintf(stderr, "tc emu: DEADLOCK -- thread %d of CTA %u waits on barrier +%u (parity %u; phase %u pending %u tx %d), nothing queued\n",
             cuda_emu::linear_tid(), blockIdx.x, smem_u32(bar), parity, emu::mb_phase(w), emu::mb_pending(w), emu::mb_tx(w));
     abort();
   }
@@ -285,6 +308,7 @@ inline void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t i
   std::lock_guard<std::mutex> g(emu::g_mu);
   emu::Op op{};
   op.kind = emu::Op::MMA_SS; op.d_tmem = d_tmem; op.a_desc = a_desc; op.b_desc = b_desc; op.idesc = idesc; op.accumulate = accumulate;
+  op.rank = cuda_emu::t_rank;
   emu::g_mmas.push_back(op);
   if (emu::eager()) while (emu::progress_locked()) {}
 }
@@ -292,6 +316,7 @@ inline void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t i
   std::lock_guard<std::mutex> g(emu::g_mu);
   emu::Op op{};
   op.kind = emu::Op::MMA_TS; op.d_tmem = d_tmem; op.a_tmem = a_tmem; op.b_desc = b_desc; op.idesc = idesc; op.accumulate = accumulate;
+  op.rank = cuda_emu::t_rank;
   emu::g_mmas.push_back(op);
   if (emu::eager()) while (emu::progress_locked()) {}
 }
@@ -343,20 +368,51 @@ inline uint32_t pack_half2(float lo, float hi) {
   return u;
 }
 
-// ---------------------------------------------------------------- cta_group::2 / clusters: not modelled
-[[noreturn]] inline void no_cluster() { fprintf(stderr, "tc emu: cta_group::2 / clusters are not modelled\n"); abort(); }
-inline uint32_t cluster_ctarank() { return 0; }
-inline void cluster_sync_all() { no_cluster(); }
-inline void mbar_arrive_remote(uint64_t*, uint32_t) { no_cluster(); }
-inline void mbar_wait_cluster(uint64_t*, uint32_t) { no_cluster(); }
+// ---------------------------------------------------------------- 2-CTA clusters (cuda_emu::launch(..., 2))
+inline uint32_t cluster_ctarank() { return (uint32_t)cuda_emu::t_rank; }
+inline void cluster_sync_all() {
+  if (cuda_emu::g_cluster == 1) { __syncthreads(); return; }
+  pthread_barrier_wait(&cuda_emu::g_cluster_barrier);
+}
+// arrive on the barrier at the same offset in CTA `rank`
+inline void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  std::lock_guard<std::mutex> g(emu::g_mu);
+  emu::mb_arrive_locked(emu::smem_in_cta(bar, (int)rank));
+}
+inline void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+// one copy per CTA of `cta_mask`, to the same offsets (data and barrier) in each
+inline void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  if (bytes % 16 || ((uintptr_t)smem_dst & 15) || ((uintptr_t)gmem_src & 15)) { fprintf(stderr, "tc emu: bulk copy alignment\n"); abort(); }
+  (void)smem_u32(smem_dst);
+  std::lock_guard<std::mutex> g(emu::g_mu);
+  for (int r = 0; r < 2; ++r) {
+    if (!((cta_mask >> r) & 1)) continue;
+    emu::Op op{};
+    op.kind = emu::Op::COPY; op.dst = emu::smem_in_cta((uint8_t*)smem_dst, r); op.src = (const uint8_t*)gmem_src; op.bytes = bytes;
+    op.bar = emu::smem_in_cta(bar, r);
+    emu::g_copies.push_back(op);
+  }
+  if (emu::eager()) while (emu::progress_locked()) {}
+}
+// completion of this CTA's MMAs so far, signalled on the barrier at the same offset in BOTH CTAs
+inline void mma_commit_pair(uint64_t* bar) {
+  (void)smem_u32(bar);
+  std::lock_guard<std::mutex> g(emu::g_mu);
+  for (int r = 0; r < 2; ++r) {
+    emu::Op op{};
+    op.kind = emu::Op::COMMIT; op.bar = emu::smem_in_cta(bar, r);
+    emu::g_mmas.push_back(op);
+  }
+  if (emu::eager()) while (emu::progress_locked()) {}
+}
+// cta_group::2 (one MMA over both CTAs' tensor memories, operands split over both shared memories): not modelled
+[[noreturn]] inline void no_cluster() { fprintf(stderr, "tc emu: cta_group::2 instructions are not modelled\n"); abort(); }
 inline void tmem_alloc2(uint32_t*, uint32_t) { no_cluster(); }
 inline void tmem_relinquish2() { no_cluster(); }
 inline void tmem_dealloc2(uint32_t, uint32_t) { no_cluster(); }
 inline void mma_ss2(uint32_t, uint64_t, uint64_t, uint32_t, uint32_t) { no_cluster(); }
 inline void mma_ts2(uint32_t, uint32_t, uint64_t, uint32_t, uint32_t) { no_cluster(); }
 inline void mma_commit2(uint64_t*) { no_cluster(); }
-inline void mma_commit_pair(uint64_t*) { no_cluster(); }
-inline void bulk_g2s_multicast(void*, const void*, uint32_t, uint64_t*, uint16_t) { no_cluster(); }
 // elect.sync: the same lane for the same (full) member mask
 inline bool elect_one() { return (cuda_emu::linear_tid() & 31) == 0; }
 

@@ -203,7 +203,7 @@ def emu_query_tc(tmp_path_factory):
                   ["-O3", "-march=native", "-fno-strict-aliasing", "-DMP_CUDA_EMU=1", "-I" + CUDA_INC, "-I" + EMU])
 
 
-def _run_query_tc(exe, tmp_path, case, n, program, sms):
+def _run_query_tc(exe, tmp_path, case, n, program, sms, extra_env=None):
     import struct
     import torch
     pts = case["points"][:, :, :n].contiguous()
@@ -221,6 +221,7 @@ def _run_query_tc(exe, tmp_path, case, n, program, sms):
             f.write(W.numpy().tobytes())
             f.write(b.numpy().tobytes())
     env = dict(os.environ, MONOPORT_B200_TC_NETC="1")       # the colour head's tensor-core program is opt-in
+    env.update(extra_env or {})
     r = subprocess.run([exe, fin, fout, str(program), str(sms)], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     return torch.from_numpy(np.fromfile(fout, dtype=np.float32)).reshape(res, n)
@@ -240,6 +241,22 @@ def test_tcgen05_kernels_match_reference_golden(emu_query_tc, tmp_path, name, n,
     got = _run_query_tc(emu_query_tc, tmp_path, case, n, program, sms)
     err = (got - case["expected"][:, :n]).abs().max().item()
     assert err <= 1e-4, err          # the GPU parity bar for the tensor-core programs (measured on the model: ~2e-5)
+
+
+@pytest.mark.parametrize("n,sms", [(300, 2), (600, 4)])
+def test_tcgen05_weight_multicast_clusters_match_reference_golden(emu_query_tc, tmp_path, n, sms):
+    """The default launch of multi-wave grids: 2-CTA clusters whose CTAs each fetch half of every weight stage and multicast it
+    into both shared memories, ring slots released by both issuers (tcgen05.commit multicast).  The CPU model runs the two CTAs
+    of a cluster side by side, each with its own shared / tensor memory.  300 points = 3 tiles on one cluster (the second CTA's
+    last tile is padding); 600 points = 5 tiles on two clusters."""
+    import torch
+    from helpers import load_query_case
+    case = load_query_case("g_smallmap")
+    got = _run_query_tc(emu_query_tc, tmp_path, case, n, 3, sms, {"MONOPORT_B200_TC_WM": "1"})
+    want = _run_query_tc(emu_query_tc, tmp_path, case, n, 3, sms, {"MONOPORT_B200_TC_WM": "0"})
+    assert torch.equal(got, want), "the cluster launch must reproduce the plain launch bit for bit"
+    err = (got - case["expected"][:, :n]).abs().max().item()
+    assert err <= 1e-4, err
 
 
 def test_tcgen05_colour_head_matches_reference_golden(emu_query_tc, tmp_path):
