@@ -320,9 +320,7 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
     tc::mbar_init(bars + B_ACC0_FULL0, 2);         // v3: "per-point scalars of this tile are in smem" (CTA-local)
     tc::mbar_init(bars + B_ACC0_FULL1, 1);
     tc::fence_barrier_init();
-#ifndef MP_CUDA_EMU
     if constexpr (CG == 2) tc::tma_prefetch_desc(&prm.tmap_pair[rank]);
-#endif
   }
   if (warp == 2) {
     if constexpr (CG == 1) { tc::tmem_alloc(s_tmem, 512); tc::tmem_relinquish(); }
@@ -366,12 +364,10 @@ query_tc3_kernel(const __grid_constant__ TcParams prm, MpPointSrc src, MpCalib c
             tc::bulk_g2s(smem + Smem::Wr + slot * C::StageBytes, wsrc + (size_t)s * C::StageBytes, C::StageBytes,
                          bars + B_WFULL + slot);
           } else {
-#ifndef MP_CUDA_EMU
             // both halves of the stage complete on the LEADER's barrier (the leader arms it for 2 x 16 KB)
             if (leader) tc::mbar_arrive_expect_tx(bars + B_WFULL + slot, 2 * C::StageBytes);
             tc::tma_load_2d_cg2(smem + Smem::Wr + slot * C::StageBytes, &prm.tmap_pair[rank], 0, s * (C::StageBytes / 128),
                                 bars + B_WFULL + slot);
-#endif
           }
         }
       }
@@ -2031,8 +2027,14 @@ int mp_tc_prepare(mp_mlp* mlp) {
     return cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
   };
   cudaError_t e = upload(s3.data(), s3.size(), (void**)&pk->w3stream);
-#ifndef MP_CUDA_EMU
   for (int r = 0; r < 2 && e == cudaSuccess; ++r) e = upload(s3p[r].data(), s3p[r].size(), (void**)&pk->w3pair[r]);
+#ifdef MP_CUDA_EMU
+  // (the CPU model's "tensor map" is the base pointer of the [rows][64 fp16] array, see tests/emu/tc_ptx_emu.h)
+  if (e == cudaSuccess) {
+    pk->pair_ok = 1;
+    for (int r = 0; r < 2; ++r) memcpy(&pk->tmap_pair[r], &pk->w3pair[r], sizeof(void*));
+  }
+#else
   if (e == cudaSuccess) {
     // tensor maps over the two half streams: [rows][64 fp16] with 128-byte rows, box = one 16 KB stage (the tiles are
     // stored pre-swizzled, so the copy itself is a plain 2-D box: no swizzle, no interleave)
@@ -2264,7 +2266,6 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     mp_set_error("at most %d peer volumes", MP_MAX_PEERS);
     return MP_E_UNSUPPORTED;
   }
-#ifndef MP_CUDA_EMU
   // One CTA per tile by default.  MONOPORT_B200_TC_CG=2 selects the CTA-pair kernel (validated: the whole GPU suite passes
   // with it) -- same box, same run: 486 Mpoints/s against 498 (profiles/r02_call8_ab_issue_pattern_x_cta_group.txt).  The
   // pair halves the weight bytes per SM, but a 2-CTA MMA runs at the same per-SM rate (tools/tc_rate.cu) and every operand
@@ -2276,6 +2277,7 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     const long long groups = (tiles + 1) / 2;
     const long long max_pairs = sms / 2;
     const int pairs = (int)(groups < max_pairs ? groups : max_pairs);
+#ifndef MP_CUDA_EMU
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * pairs);
@@ -2290,10 +2292,12 @@ int mp_launch_query_tc(const mp_mlp* mlp, mp_feat* feat, const MpPointSrc& src, 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     MP_CUDA(cudaLaunchKernelEx(&cfg, query_tc3_kernel<false, 2>, prm, src, cal, dst));
+#else
+    MP_EMU_LAUNCH_CLUSTER2(2 * pairs, kThreads, (query_tc3_kernel<false, 2>(prm, src, cal, dst)));
+#endif
     report(2 * pairs);
     return MP_OK;
   }
-#endif
   // Weight multicast: the one-CTA program in 2-CTA clusters that share the weight stream (halves the L2 -> SM weight requests
   // like the CTA pair above without touching the MMAs).  With the round-1..mid-round-2 issuer it lost 0.7 % (the coupled ring
   // cost more cycles than the saved power bought back, profiles/r02_call14_wm_ab.txt); with the issuer at the pipe's rate the

@@ -2,8 +2,10 @@
 // mbarriers with transaction counts, bulk async copies, tensor memory, tcgen05.mma (.kind::f16, cta_group::1, operands
 // from SWIZZLE_128B K-major shared-memory descriptors or packed fp16 in tensor memory), tcgen05.commit, tcgen05.ld/st;
 // and, for launches of 2-CTA clusters (cuda_emu::launch(..., 2): each CTA has its own shared and tensor memory), the
-// cluster rank, cluster barriers, remote mbarrier arrivals, multicast bulk copies and multicast commits.  cta_group::2
-// MMAs (one instruction over both CTAs) are NOT modelled.
+// cluster rank, cluster barriers, remote mbarrier arrivals, multicast bulk copies and multicast commits, and
+// tcgen05.mma.cta_group::2 (M = 256: rows [0,128) are the leader CTA's, [128,256) the peer's -- A operand and accumulator of
+// each half in that CTA's shared / tensor memory; the N rows of B are split between the two shared memories) with plain
+// 2-D tensor-map copies completing on the leader's barrier.
 //
 // Asynchrony is modelled adversarially: a bulk copy or an MMA is only QUEUED when it is issued; queued operations are
 // executed (copies first, then MMAs / commits in issue order) when some thread is blocked in an mbarrier wait.  So
@@ -29,6 +31,7 @@ struct Op {
   uint32_t d_tmem, a_tmem, idesc, accumulate;
   uint64_t a_desc, b_desc;
   int rank;                                  // the issuing CTA: whose shared / tensor memory the operands live in
+  int cg;                                    // 1, or 2: one instruction over both CTAs of the pair (issued by rank 0)
 };
 inline std::mutex g_mu;
 inline std::deque<Op> g_copies, g_mmas;
@@ -108,13 +111,16 @@ inline uint16_t smem_half(uint32_t addr, int rank) {
   return h;
 }
 
-// D[128 x N] (+)= A[128 x 16] * B[N x 16]^T, fp16 operands, fp32 accumulation
+// D[128 x N] (+)= A[128 x 16] * B[N x 16]^T, fp16 operands, fp32 accumulation.  cta_group::2: M = 256 -- for each CTA h of the
+// pair D_h[128 x N] (+)= A_h * B^T with A_h and D_h in CTA h's memories and B = rows [0, N/2) from CTA 0's shared memory followed
+// by rows [N/2, N) from CTA 1's (same descriptor in both).
 inline void exec_mma(const Op& op) {
   const uint32_t M = ((op.idesc >> 24) & 0x1F) << 4, N = ((op.idesc >> 17) & 0x3F) << 3;
-  if (M != 128 || N == 0 || N > 256 || (N & 15)) { fprintf(stderr, "tc emu: unsupported MMA shape %ux%u\n", M, N); abort(); }
+  if (M != 128u * (uint32_t)op.cg || N == 0 || N > 256 || (N & 15)) { fprintf(stderr, "tc emu: unsupported MMA shape %ux%u (cta_group::%d)\n", M, N, op.cg); abort(); }
   if (((op.idesc >> 4) & 3) != 1 || ((op.idesc >> 7) & 7) != 0 || ((op.idesc >> 10) & 7) != 0) { fprintf(stderr, "tc emu: idesc formats\n"); abort(); }
+  if (op.cg == 2 && (op.rank != 0 || cuda_emu::g_cluster != 2)) { fprintf(stderr, "tc emu: cta_group::2 MMAs are issued by the leader of a 2-CTA cluster\n"); abort(); }
   g_stats.mma_ops++;
-  g_stats.mma_flop += 2ull * 128 * N * 16;
+  g_stats.mma_flop += 2ull * M * N * 16;
   const uint32_t dcol = op.d_tmem & 0xFFFF;
   if ((op.d_tmem >> 16) != 0 || dcol + N > kCols) { fprintf(stderr, "tc emu: bad accumulator address %08x (N=%u)\n", op.d_tmem, N); abort(); }
   auto desc_fields = [](uint64_t d, uint32_t& start, uint32_t& sbo) {
@@ -123,46 +129,56 @@ inline void exec_mma(const Op& op) {
     if (((d >> 61) & 7) != 2) { fprintf(stderr, "tc emu: only SWIZZLE_128B descriptors are modelled\n"); abort(); }
   };
   static thread_local float A[128][16], B[256][16];
-  if (op.kind == Op::MMA_SS) {
-    uint32_t st, sbo;
-    desc_fields(op.a_desc, st, sbo);
-    for (uint32_t m = 0; m < 128; ++m)
-      for (uint32_t k = 0; k < 16; ++k) A[m][k] = h2f(smem_half(st + (m >> 3) * sbo + (m & 7) * 128 + k * 2, op.rank));
-  } else {
-    const uint32_t acol = op.a_tmem & 0xFFFF;
-    if ((op.a_tmem >> 16) != 0 || acol + 8 > kCols) { fprintf(stderr, "tc emu: bad A tensor-memory address\n"); abort(); }
-    for (uint32_t m = 0; m < 128; ++m)
-      for (uint32_t k = 0; k < 16; ++k) {
-        const uint32_t w = g_tmem_r[op.rank][m][acol + (k >> 1)];
-        A[m][k] = h2f((uint16_t)((k & 1) ? (w >> 16) : (w & 0xFFFF)));
-      }
-  }
   {
     uint32_t st, sbo;
     desc_fields(op.b_desc, st, sbo);
-    for (uint32_t n = 0; n < N; ++n)
-      for (uint32_t k = 0; k < 16; ++k) B[n][k] = h2f(smem_half(st + (n >> 3) * sbo + (n & 7) * 128 + k * 2, op.rank));
-  }
-  {
-    static const int trace_n = getenv("EMU_TC_TRACE_MMA") ? atoi(getenv("EMU_TC_TRACE_MMA")) : 0;
-    static int seen = 0;
-    if (seen < trace_n) {
-      float amin = 1e30f, amax = -1e30f;
-      for (uint32_t m = 0; m < 128; ++m) for (uint32_t k = 0; k < 16; ++k) { amin = fminf(amin, A[m][k]); amax = fmaxf(amax, A[m][k]); }
-      fprintf(stderr, "[mma %3d] %s dcol=%3u N=%3u acc=%u  A[0][0..3]=%g %g %g %g  A range [%g, %g]  B[0][0..1]=%g %g\n", seen,
-              op.kind == Op::MMA_SS ? "SS" : "TS", dcol, N, op.accumulate, A[0][0], A[0][1], A[0][2], A[0][3], amin, amax, B[0][0], B[0][1]);
-      ++seen;
+    if (op.cg == 1) {
+      for (uint32_t n = 0; n < N; ++n)
+        for (uint32_t k = 0; k < 16; ++k) B[n][k] = h2f(smem_half(st + (n >> 3) * sbo + (n & 7) * 128 + k * 2, op.rank));
+    } else {
+      for (uint32_t n = 0; n < N; ++n) {
+        const uint32_t nl = n % (N / 2);
+        for (uint32_t k = 0; k < 16; ++k) B[n][k] = h2f(smem_half(st + (nl >> 3) * sbo + (nl & 7) * 128 + k * 2, (int)(n / (N / 2))));
+      }
     }
   }
-  for (uint32_t m = 0; m < 128; ++m)
-    for (uint32_t n = 0; n < N; ++n) {
-      float acc = 0.f;
-      for (uint32_t k = 0; k < 16; ++k) acc += A[m][k] * B[n][k];
-      float d = 0.f;
-      if (op.accumulate) memcpy(&d, &g_tmem_r[op.rank][m][dcol + n], 4);
-      d += acc;
-      memcpy(&g_tmem_r[op.rank][m][dcol + n], &d, 4);
+  for (int h = 0; h < op.cg; ++h) {
+    const int cta = op.cg == 1 ? op.rank : h;
+    if (op.kind == Op::MMA_SS) {
+      uint32_t st, sbo;
+      desc_fields(op.a_desc, st, sbo);
+      for (uint32_t m = 0; m < 128; ++m)
+        for (uint32_t k = 0; k < 16; ++k) A[m][k] = h2f(smem_half(st + (m >> 3) * sbo + (m & 7) * 128 + k * 2, cta));
+    } else {
+      const uint32_t acol = op.a_tmem & 0xFFFF;
+      if ((op.a_tmem >> 16) != 0 || acol + 8 > kCols) { fprintf(stderr, "tc emu: bad A tensor-memory address\n"); abort(); }
+      for (uint32_t m = 0; m < 128; ++m)
+        for (uint32_t k = 0; k < 16; ++k) {
+          const uint32_t w = g_tmem_r[cta][m][acol + (k >> 1)];
+          A[m][k] = h2f((uint16_t)((k & 1) ? (w >> 16) : (w & 0xFFFF)));
+        }
     }
+    if (h == 0) {
+      static const int trace_n = getenv("EMU_TC_TRACE_MMA") ? atoi(getenv("EMU_TC_TRACE_MMA")) : 0;
+      static int seen = 0;
+      if (seen < trace_n) {
+        float amin = 1e30f, amax = -1e30f;
+        for (uint32_t m = 0; m < 128; ++m) for (uint32_t k = 0; k < 16; ++k) { amin = fminf(amin, A[m][k]); amax = fmaxf(amax, A[m][k]); }
+        fprintf(stderr, "[mma %3d] %s dcol=%3u N=%3u acc=%u  A[0][0..3]=%g %g %g %g  A range [%g, %g]  B[0][0..1]=%g %g\n", seen,
+                op.kind == Op::MMA_SS ? "SS" : "TS", dcol, N, op.accumulate, A[0][0], A[0][1], A[0][2], A[0][3], amin, amax, B[0][0], B[0][1]);
+        ++seen;
+      }
+    }
+    for (uint32_t m = 0; m < 128; ++m)
+      for (uint32_t n = 0; n < N; ++n) {
+        float acc = 0.f;
+        for (uint32_t k = 0; k < 16; ++k) acc += A[m][k] * B[n][k];
+        float d = 0.f;
+        if (op.accumulate) memcpy(&d, &g_tmem_r[cta][m][dcol + n], 4);
+        d += acc;
+        memcpy(&g_tmem_r[cta][m][dcol + n], &d, 4);
+      }
+  }
 }
 
 // executes ONE queued asynchronous operation; returns false when nothing is queued.  Caller holds g_mu.
@@ -308,7 +324,7 @@ inline void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t i
   std::lock_guard<std::mutex> g(emu::g_mu);
   emu::Op op{};
   op.kind = emu::Op::MMA_SS; op.d_tmem = d_tmem; op.a_desc = a_desc; op.b_desc = b_desc; op.idesc = idesc; op.accumulate = accumulate;
-  op.rank = cuda_emu::t_rank;
+  op.rank = cuda_emu::t_rank; op.cg = 1;
   emu::g_mmas.push_back(op);
   if (emu::eager()) while (emu::progress_locked()) {}
 }
@@ -316,7 +332,7 @@ inline void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t i
   std::lock_guard<std::mutex> g(emu::g_mu);
   emu::Op op{};
   op.kind = emu::Op::MMA_TS; op.d_tmem = d_tmem; op.a_tmem = a_tmem; op.b_desc = b_desc; op.idesc = idesc; op.accumulate = accumulate;
-  op.rank = cuda_emu::t_rank;
+  op.rank = cuda_emu::t_rank; op.cg = 1;
   emu::g_mmas.push_back(op);
   if (emu::eager()) while (emu::progress_locked()) {}
 }
@@ -405,14 +421,44 @@ inline void mma_commit_pair(uint64_t* bar) {
   }
   if (emu::eager()) while (emu::progress_locked()) {}
 }
-// cta_group::2 (one MMA over both CTAs' tensor memories, operands split over both shared memories): not modelled
-[[noreturn]] inline void no_cluster() { fprintf(stderr, "tc emu: cta_group::2 instructions are not modelled\n"); abort(); }
-inline void tmem_alloc2(uint32_t*, uint32_t) { no_cluster(); }
-inline void tmem_relinquish2() { no_cluster(); }
-inline void tmem_dealloc2(uint32_t, uint32_t) { no_cluster(); }
-inline void mma_ss2(uint32_t, uint64_t, uint64_t, uint32_t, uint32_t) { no_cluster(); }
-inline void mma_ts2(uint32_t, uint32_t, uint64_t, uint32_t, uint32_t) { no_cluster(); }
-inline void mma_commit2(uint64_t*) { no_cluster(); }
+// ---- cta_group::2: allocation, MMAs over the pair, commits to both CTAs, tensor-map copies completing on the leader's barrier
+inline void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) { tmem_alloc(smem_result, ncols); }
+inline void tmem_relinquish2() {}
+inline void tmem_dealloc2(uint32_t, uint32_t) {}
+inline void mma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  std::lock_guard<std::mutex> g(emu::g_mu);
+  emu::Op op{};
+  op.kind = emu::Op::MMA_SS; op.d_tmem = d_tmem; op.a_desc = a_desc; op.b_desc = b_desc; op.idesc = idesc; op.accumulate = accumulate;
+  op.rank = cuda_emu::t_rank; op.cg = 2;
+  emu::g_mmas.push_back(op);
+  if (emu::eager()) while (emu::progress_locked()) {}
+}
+inline void mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  std::lock_guard<std::mutex> g(emu::g_mu);
+  emu::Op op{};
+  op.kind = emu::Op::MMA_TS; op.d_tmem = d_tmem; op.a_tmem = a_tmem; op.b_desc = b_desc; op.idesc = idesc; op.accumulate = accumulate;
+  op.rank = cuda_emu::t_rank; op.cg = 2;
+  emu::g_mmas.push_back(op);
+  if (emu::eager()) while (emu::progress_locked()) {}
+}
+inline void mma_commit2(uint64_t* bar) { mma_commit_pair(bar); }
+// The model's "tensor map": the first 8 bytes of the 128-byte object hold the base of a [rows][64 fp16] array (what
+// mp_tc_prepare stores under MP_CUDA_EMU); a copy is one plain 2-D box of 128 rows x 128 bytes at row c1, landing in the
+// CALLING CTA's shared memory and completing on the LEADER's barrier (cta_group::2 form).
+inline void tma_load_2d_cg2(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  if (c0 != 0 || c1 < 0) { fprintf(stderr, "tc emu: tensor-map copy coordinates\n"); abort(); }
+  (void)smem_u32(smem_dst);
+  const uint8_t* base;
+  memcpy(&base, tmap, sizeof(base));
+  std::lock_guard<std::mutex> g(emu::g_mu);
+  emu::Op op{};
+  op.kind = emu::Op::COPY; op.dst = (uint8_t*)smem_dst; op.src = base + (size_t)c1 * 128; op.bytes = 128 * 128;
+  op.bar = emu::smem_in_cta(bar, 0);
+  emu::g_copies.push_back(op);
+  if (emu::eager()) while (emu::progress_locked()) {}
+}
+inline void tma_load_2d(void*, const void*, int, int, uint64_t*) { fprintf(stderr, "tc emu: cta_group::1 tensor-map copies are not modelled\n"); abort(); }
+inline void tma_prefetch_desc(const void*) {}
 // elect.sync: the same lane for the same (full) member mask
 inline bool elect_one() { return (cuda_emu::linear_tid() & 31) == 0; }
 

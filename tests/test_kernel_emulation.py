@@ -259,6 +259,21 @@ def test_tcgen05_weight_multicast_clusters_match_reference_golden(emu_query_tc, 
     assert err <= 1e-4, err
 
 
+@pytest.mark.parametrize("n,sms", [(300, 2), (600, 4)])
+def test_tcgen05_cta_pair_kernel_matches_reference_golden(emu_query_tc, tmp_path, n, sms):
+    """The opt-in CTA-pair flavour (MONOPORT_B200_TC_CG=2): tcgen05.mma.cta_group::2 with M = 256 over the two CTAs of a
+    cluster -- the leader issues for both tiles, every weight tile is split over the two shared memories (tensor-map copies
+    completing on the leader's barrier), operand hand-offs are remote arrivals, completions are multicast commits."""
+    import torch
+    from helpers import load_query_case
+    case = load_query_case("g_smallmap")
+    got = _run_query_tc(emu_query_tc, tmp_path, case, n, 3, sms, {"MONOPORT_B200_TC_CG": "2"})
+    want = _run_query_tc(emu_query_tc, tmp_path, case, n, 3, sms, {"MONOPORT_B200_TC_WM": "0"})
+    assert torch.equal(got, want), "the CTA-pair kernel must reproduce the one-CTA kernel bit for bit"
+    err = (got - case["expected"][:, :n]).abs().max().item()
+    assert err <= 1e-4, err
+
+
 def test_tcgen05_colour_head_matches_reference_golden(emu_query_tc, tmp_path):
     """PIFuNetCMLP (513 -> 3, Tanh, 512-channel map): the phase-filled skip operand (four fills of X per tile), eight-K-block
     G0 GEMM, three fp32 last-layer outputs; one emulated SM walks both tiles."""
