@@ -274,6 +274,21 @@ def test_tcgen05_cta_pair_kernel_matches_reference_golden(emu_query_tc, tmp_path
     assert err <= 1e-4, err
 
 
+@pytest.mark.parametrize("flavour", ["plain", "multicast", "pair"])
+@pytest.mark.parametrize("order", ["mmas", "random:1", "random:2"])
+def test_tcgen05_handoffs_survive_other_completion_orders(emu_query_tc, tmp_path, flavour, order):
+    """The model completes queued asynchronous operations in an adversarial but fixed order (bulk copies before MMAs).  The
+    hand-off protocols must not depend on that: MMAs first, and random interleavings (copies in any order), give the same bits
+    for the one-CTA launch, the weight-multicast clusters and the CTA-pair kernel."""
+    import torch
+    from helpers import load_query_case
+    case = load_query_case("g_smallmap")
+    env = {"plain": {"MONOPORT_B200_TC_WM": "0"}, "multicast": {"MONOPORT_B200_TC_WM": "1"}, "pair": {"MONOPORT_B200_TC_CG": "2"}}[flavour]
+    want = _run_query_tc(emu_query_tc, tmp_path, case, 300, 3, 2, {"MONOPORT_B200_TC_WM": "0"})
+    got = _run_query_tc(emu_query_tc, tmp_path, case, 300, 3, 2, dict(env, EMU_TC_ORDER=order))
+    assert torch.equal(got, want)
+
+
 def test_tcgen05_colour_head_matches_reference_golden(emu_query_tc, tmp_path):
     """PIFuNetCMLP (513 -> 3, Tanh, 512-channel map): the phase-filled skip operand (four fills of X per tile), eight-K-block
     G0 GEMM, three fp32 last-layer outputs; one emulated SM walks both tiles."""
