@@ -289,13 +289,15 @@ def test_tcgen05_handoffs_survive_other_completion_orders(emu_query_tc, tmp_path
     assert torch.equal(got, want)
 
 
-def test_tcgen05_colour_head_matches_reference_golden(emu_query_tc, tmp_path):
+@pytest.mark.parametrize("order", ["copies", "random:3"])
+def test_tcgen05_colour_head_matches_reference_golden(emu_query_tc, tmp_path, order):
     """PIFuNetCMLP (513 -> 3, Tanh, 512-channel map): the phase-filled skip operand (four fills of X per tile), eight-K-block
-    G0 GEMM, three fp32 last-layer outputs; one emulated SM walks both tiles."""
+    G0 GEMM, three fp32 last-layer outputs; one emulated SM walks both tiles (default completion order of the asynchronous
+    engines and a random one)."""
     from helpers import load_query_case
     case = load_query_case("c_rot33")
     n = 200
-    got = _run_query_tc(emu_query_tc, tmp_path, case, n, 0, 1)
+    got = _run_query_tc(emu_query_tc, tmp_path, case, n, 0, 1, {"EMU_TC_ORDER": order})
     err = (got - case["expected"][:, :n]).abs().max().item()
     assert err <= 1e-4, err
     zero = case["expected"][:, :n] == 0
