@@ -143,7 +143,9 @@ int mp_ipc_close(void* dev_ptr);
 int mp_ipc_free(void* dev_ptr);
 
 /* mp_query_grid with HOST buffers: uploads the NCHW fp32 feature map (NULL = reuse), evaluates the slab, copies
- * the [nz,R,R] result to out_host, synchronises.  bench.py's e2e leg. */
+ * the [nz,R,R] result to out_host, synchronises.  Slabs of 4 M nodes or more are evaluated and read back in four z-chunks,
+ * the copy of one chunk (internal copy stream) overlapping the evaluation of the next: pin out_host to get the overlap.
+ * bench.py's e2e leg. */
 int mp_query_grid_host(mp_mlp_t* mlp, mp_feat_t* feat, const float* feat_nchw_host, int R, int z0, int nz,
                        const float* b_min3, const float* b_max3, const float* calib12, int projection, float z_scale,
                        float* out_host, int mode, void* stream);
